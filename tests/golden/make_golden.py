@@ -1,0 +1,187 @@
+"""Generate golden vectors by running the UNMODIFIED reference (`/root/reference/vae`) on CPU.
+
+Run in the build container only (the reference does not travel to the GPU box):
+
+    python tests/golden/make_golden.py
+
+Writes `tests/golden/<case>.npz` (small, committed).  Each file holds the reference's own
+`state_dict`, the seeded synthetic batch, the replayed reparameterisation noise, and what the
+reference computed from them: `decoder_logits`, latent params, every loss term
+(`run.py:128-163` `compute_all_losses`), every gradient after `total_loss.backward()`, the
+clip norm (`run.py:255`) and the parameters after one `Adam.step()` (`run.py:261`).
+
+Parity-mode settings: dropout 0.0, teacher_forcing_prob 1.0, train mode, eps
+replayed in the reference's order (2 draws per space in train mode, 2nd used; `model.py:391-395`).
+"""
+import os
+import sys
+import random
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+
+from oracle.ref_shim import load_reference  # noqa: E402
+
+ref_model, ref_losses, ref_utils = load_reference()
+
+PAD, UNK, SOS, EOS = 0, 1, 2, 3
+
+
+def make_params(**over):
+    p = {"name": "golden", "random_seed": 10, "data_dir": "", "combined_dataset": False,
+         "dataset_minibatch_ratios": {}, "checkpoint_dir": "", "glove_path": "",
+         "num_train_examples": -1, "lowercase": True, "reverse_input": False,
+         "embedding_dim": 12, "hidden_dim": 16, "num_rnn_layers": 2,
+         "bidirectional_encoder": False, "bow_encoder": False,
+         "latent_dims": {"total": 6, "polarity": 1}, "epochs": 3, "batch_size": 5,
+         "learn_rate": 5e-3, "encoder_dropout": 0.0, "decoder_dropout": 0.0,
+         "teacher_forcing_prob": 1.0, "lambdas": {"default": 0.01, "polarity": 0.005},
+         "adversarial_loss": False, "mi_loss": False, "train": True, "validate": False,
+         "test": False}
+    p.update(over)
+    ref_utils.validate_params(p)
+    return p
+
+
+def make_batch(gen, B, T, V, label_dims, full_row=True):
+    lengths = torch.randint(3, T + 1, (B,), generator=gen)
+    if full_row:
+        lengths[gen.initial_seed() % B] = T
+    X = torch.zeros(B, T, dtype=torch.long)
+    for b in range(B):
+        n = int(lengths[b])
+        X[b, 0] = SOS
+        X[b, 1:n - 1] = torch.randint(4, V, (n - 2,), generator=gen)
+        X[b, n - 1] = EOS
+    Y = {}
+    for name, dim in label_dims.items():
+        if dim == 1:
+            Y[name] = (torch.rand(B, 1, generator=gen) < 0.4).float()
+        else:
+            Y[name] = torch.randint(0, dim, (B, 1), generator=gen)
+    return X, lengths, Y
+
+
+def run_case(name, params, V, label_dims, B, T, kl_weights, seed=10, eps_seed=1234, mode="train"):
+    ref_utils.set_seed(seed)
+    vae = ref_model.build_vae(params, V, None, label_dims, torch.device("cpu"), SOS, EOS)
+    gen = torch.Generator().manual_seed(seed + 1)
+    X, lengths, Y = make_batch(gen, B, T, V, label_dims)
+    out = {"B": B, "T": T, "V": V, "sos": SOS, "eos": EOS, "inputs": X.numpy(),
+           "lengths": lengths.numpy(), "lr": params["learn_rate"]}
+    for k, v in Y.items():
+        out[f"Y.{k}"] = v.numpy()
+    for k, v in vae.state_dict().items():
+        out[f"sd.{k}"] = v.detach().numpy().copy()
+    space_names = list(vae.context2params.keys())
+    out["space_names"] = np.array(space_names)
+    out["space_dims"] = np.array([vae.context2params[n].out_features // 2 for n in space_names])
+    out["label_names"] = np.array(list(label_dims.keys()))
+    out["label_dims"] = np.array(list(label_dims.values()))
+    for k in space_names:
+        out[f"klw.{k}"] = np.float64(kl_weights.get(k, kl_weights["default"]))
+
+    vae.train(mode == "train")
+    # replay the reference's noise order (model.py:387-396)
+    torch.manual_seed(eps_seed)
+    for n in space_names:
+        zs = vae.context2params[n].out_features // 2
+        if mode == "train":
+            torch.randn(B, zs)
+        out[f"eps.{n}"] = torch.randn(B, zs).numpy()
+    torch.manual_seed(eps_seed)
+    random.seed(seed)
+    opt = torch.optim.Adam(vae.trainable_parameters(), lr=params["learn_rate"])
+    output = vae(X, lengths, teacher_forcing_prob=params["teacher_forcing_prob"])
+    for n in space_names:
+        P = output["latent_params"][n]
+        z_replay = P.mu + torch.from_numpy(out[f"eps.{n}"]) * torch.exp(P.logvar)
+        assert torch.equal(z_replay, P.z), f"eps replay failed for {n}"
+        out[f"z.{n}"] = P.z.detach().numpy()
+        out[f"mu.{n}"] = P.mu.detach().numpy()
+        out[f"logvar.{n}"] = P.logvar.detach().numpy()
+    for n, l in output["dsc_logits"].items():
+        out[f"dsc_logits.{n}"] = l.detach().numpy()
+    out["decoder_logits"] = output["decoder_logits"].detach().numpy()
+    out["token_predictions"] = output["token_predictions"].numpy()
+    _, ctx, (hn, cn) = vae.encode(X, lengths)
+    out["context"] = ctx.detach().numpy()
+    out["enc_hn"] = hn.detach().numpy()
+    out["enc_cn"] = cn.detach().numpy()
+    z = torch.cat([output["latent_params"][n].z for n in space_names], dim=1)
+    h0, c0 = vae.compute_hidden(z, B)
+    out["dec_h0"] = h0.detach().numpy()
+    out["dec_c0"] = c0.detach().numpy()
+
+    # losses: run.py:128-163, mi weight 0.01 (run.py:239)
+    sys.path.insert(0, "/root/reference")
+    L = {}
+    L.update(ref_losses.reconstruction_loss(X, output["decoder_logits"], lengths))
+    L.update(ref_losses.compute_kl_divergence_losses(vae, output["latent_params"], kl_weights))
+    L.update(ref_losses.compute_discriminator_losses(vae, output["dsc_logits"], Y))
+    L.update(ref_losses.compute_adversarial_losses(vae, output["adv_logits"], Y))
+    L.update(ref_losses.compute_mi_losses(vae, output["latent_params"], beta=0.01))
+    total = (L["reconstruction_loss"] + L["total_weighted_kl"] + L["total_dsc_loss"]
+             + L["total_adv_loss"] + L["total_mi"])
+    out["loss.reconstruction"] = L["reconstruction_loss"].item()
+    out["loss.total_weighted_kl"] = L["total_weighted_kl"].item()
+    out["loss.total_kl"] = L["total_kl"]
+    out["loss.total_dsc"] = L["total_dsc_loss"].item()
+    out["loss.total"] = total.item()
+    for n, v in L["idv_kls"].items():
+        out[f"kl.{n}"] = v
+    for n, v in L["idv_dsc_losses"].items():
+        out[f"dsc_loss.{n}"] = v
+    for n, v in L["idv_dsc_accs"].items():
+        out[f"dsc_acc.{n}"] = v
+
+    if mode == "train":
+        total.backward(retain_graph=True)
+        for k, p in vae.named_parameters():
+            if p.grad is not None:
+                out[f"grad.{k}"] = p.grad.detach().numpy().copy()
+        norm = torch.nn.utils.clip_grad_norm_(vae.trainable_parameters(), 5.0)
+        out["grad_norm"] = norm.item()
+        opt.step()
+        for k, v in vae.state_dict().items():
+            out[f"sd_after.{k}"] = v.detach().numpy().copy()
+
+    path = os.path.join(HERE, f"{name}.npz")
+    np.savez_compressed(path, **out)
+    print(f"wrote {path}: {os.path.getsize(path) / 1024:.1f} KiB, total loss {total.item():.6f}")
+
+
+def cyclic_table():
+    rows = []
+    for total in (100, 31260, 7):
+        for step in list(range(0, 30)) + [total // 4, total // 4 + 1, total - 1, total // 2 + 3]:
+            rows.append((step, total, float(ref_losses.get_cyclic_kl_weight(step, total))))
+    path = os.path.join(HERE, "cyclic_kl.npz")
+    np.savez_compressed(path, table=np.array(rows, dtype=np.float64))
+    print(f"wrote {path}")
+
+
+if __name__ == "__main__":
+    torch.set_num_threads(1)
+    # cfg-1-like: uni-directional encoder, polarity + content (config_example.json shape, shrunk)
+    run_case("tiny_uni", make_params(), V=37, label_dims={"polarity": 1}, B=5, T=8,
+             kl_weights={"default": 0.01, "polarity": 0.005})
+    # cfg-2-like: bi-directional encoder, uncertainty + polarity + content, ragged lengths;
+    # the clip (5.0) is made to bite by a large lr-independent loss scale via short rows
+    run_case("tiny_bi", make_params(bidirectional_encoder=True, embedding_dim=10, hidden_dim=8,
+                                    latent_dims={"total": 7, "polarity": 1, "uncertainty": 2},
+                                    learn_rate=3e-4,
+                                    lambdas={"default": 0.37, "polarity": 0.005, "uncertainty": 0.005}),
+             V=29, label_dims={"uncertainty": 1, "polarity": 1}, B=6, T=9,
+             kl_weights={"default": 0.37, "polarity": 0.005, "uncertainty": 0.005})
+    # eval mode (single eps draw, model.py:393-395), multi-class label head, 1-layer config
+    # (decoder silently gets 2 layers: model.py:123-124)
+    run_case("tiny_eval_mc", make_params(num_rnn_layers=1, embedding_dim=6, hidden_dim=8,
+                                         latent_dims={"total": 5, "modality": 2}),
+             V=23, label_dims={"modality": 3}, B=4, T=6,
+             kl_weights={"default": 1.0}, mode="eval")
+    cyclic_table()
