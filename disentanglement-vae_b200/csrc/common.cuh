@@ -1,0 +1,92 @@
+// Shared device/host helpers for the dvae_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/dvae_b200.h"
+
+namespace dvae {
+
+// ---- error plumbing -------------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+void count_launch(int n = 1);
+
+#define DVAE_REQUIRE(cond, ...)            \
+  do {                                     \
+    if (!(cond)) {                         \
+      ::dvae::set_error(__VA_ARGS__);      \
+      return DVAE_EINVAL;                  \
+    }                                      \
+  } while (0)
+
+#define DVAE_CUDA(call)                                                                  \
+  do {                                                                                   \
+    cudaError_t e__ = (call);                                                            \
+    if (e__ != cudaSuccess) {                                                            \
+      ::dvae::set_error("%s failed at %s:%d: %s", #call, __FILE__, __LINE__,             \
+                        cudaGetErrorString(e__));                                        \
+      return DVAE_ECUDA;                                                                 \
+    }                                                                                    \
+  } while (0)
+
+#define DVAE_LAUNCH_CHECK()                                                              \
+  do {                                                                                   \
+    ::dvae::count_launch();                                                              \
+    cudaError_t e__ = cudaGetLastError();                                                \
+    if (e__ != cudaSuccess) {                                                            \
+      ::dvae::set_error("kernel launch failed at %s:%d: %s", __FILE__, __LINE__,         \
+                        cudaGetErrorString(e__));                                        \
+      return DVAE_ECUDA;                                                                 \
+    }                                                                                    \
+  } while (0)
+
+static inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+// ---- Philox4x32-10 (counter-based; same mask in forward and backward without storing it) ------
+struct Philox {
+  static constexpr uint32_t kM0 = 0xD2511F53u, kM1 = 0xCD9E8D57u, kW0 = 0x9E3779B9u, kW1 = 0xBB67AE85u;
+  __host__ __device__ static inline void round(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+#ifdef __CUDA_ARCH__
+    uint32_t hi0 = __umulhi(kM0, c[0]), hi1 = __umulhi(kM1, c[2]);
+#else
+    uint32_t hi0 = (uint32_t)(((uint64_t)kM0 * c[0]) >> 32), hi1 = (uint32_t)(((uint64_t)kM1 * c[2]) >> 32);
+#endif
+    uint32_t lo0 = kM0 * c[0], lo1 = kM1 * c[2];
+    uint32_t n0 = hi1 ^ c[1] ^ k0, n1 = lo1, n2 = hi0 ^ c[3] ^ k1, n3 = lo0;
+    c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+  }
+  // 4 x uint32 for (seed, salt, 64-bit counter)
+  __host__ __device__ static inline void gen(uint64_t seed, uint32_t salt, uint64_t ctr, uint32_t (&out)[4]) {
+    uint32_t c[4] = {(uint32_t)ctr, (uint32_t)(ctr >> 32), salt, 0x5eedu};
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+      round(c, k0, k1);
+      k0 += kW0;
+      k1 += kW1;
+    }
+    out[0] = c[0]; out[1] = c[1]; out[2] = c[2]; out[3] = c[3];
+  }
+};
+
+// Dropout keep-scale for element `idx` (idx = row * width + col): 0 or 1/(1-p).
+// One Philox call serves 4 consecutive elements (idx / 4 is the counter, idx % 4 the lane).
+__device__ __forceinline__ void dropout_scale4(uint64_t seed, uint32_t salt, uint64_t idx4, float p,
+                                               float inv_keep, float (&s)[4]) {
+  uint32_t r[4];
+  Philox::gen(seed, salt, idx4, r);
+  // keep iff u >= p with u = r * 2^-32 in [0,1)
+#pragma unroll
+  for (int i = 0; i < 4; ++i) s[i] = ((float)r[i] * 2.3283064365386963e-10f >= p) ? inv_keep : 0.f;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+
+}  // namespace dvae

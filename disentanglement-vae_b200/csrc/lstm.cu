@@ -1,0 +1,387 @@
+// LSTM layer forward / backward-through-time (see include/dvae_b200.h, dvae_lstm_seq_fwd/bwd).
+//
+// General-shape path: the input projection for all T steps is one dense GEMM (dvae_linear), the
+// recurrence is one launch per time step (both directions in the same grid) with the carried
+// state ping-ponged in a small L2-resident buffer; the weight gradients are dense GEMMs over the
+// saved gate gradients.  Exact fp32.  (lstm_persist.cu holds the SMEM-resident persistent-cluster
+// variant for H <= 256.)
+#include "common.cuh"
+
+namespace dvae {
+
+int linear_impl(const float* A, int64_t lda, int trans_a, const float* B, int64_t ldb, int trans_b, float* C,
+                int64_t ldc, int M, int N, int K, const float* bias, const float* bias2, float beta, int act,
+                cudaStream_t st);
+int colsum_impl(const float* X, int64_t ldx, int M, int N, float* out, float beta, cudaStream_t st);
+
+// ---- small utility kernels --------------------------------------------------------------------
+// dst[d][b][0..H) (row stride ldd, direction stride dird) = src[d][b][..] or 0 when src == NULL
+__global__ void copy_state_kernel(const float* __restrict__ src, int64_t lds, int64_t dirs, float* __restrict__ dst,
+                                  int64_t ldd, int64_t dird, int D, int B, int H) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)D * B * H) return;
+  int u = i % H, b = (i / H) % B, d = i / ((int64_t)H * B);
+  dst[d * dird + b * ldd + u] = src ? src[d * dirs + b * lds + u] : 0.f;
+}
+
+// out [C,R] = in [R,C]^T
+__global__ void transpose_kernel(const float* __restrict__ in, float* __restrict__ out, int R, int C) {
+  __shared__ float tile[32][33];
+  int c = blockIdx.x * 32 + threadIdx.x, r0 = blockIdx.y * 32;
+  for (int j = threadIdx.y; j < 32; j += 8)
+    if (r0 + j < R && c < C) tile[j][threadIdx.x] = in[(int64_t)(r0 + j) * C + c];
+  __syncthreads();
+  int r = r0 + threadIdx.x, c0 = blockIdx.x * 32;
+  for (int j = threadIdx.y; j < 32; j += 8)
+    if (c0 + j < C && r < R) out[(int64_t)(c0 + j) * R + r] = tile[threadIdx.x][j];
+}
+
+// ---- per-step mini GEMM -----------------------------------------------------------------------
+// acc[r][c] = sum_k A[row0 + rb*2 + r][k] * W[wrow(c)][k]   (both K-contiguous)
+// 256 threads: rb = tid / 16 (16 row pairs -> 32 rows), tu = tid % 16; the caller maps (tu, c) to a
+// W row.  K is consumed in chunks of KC through shared memory (rows padded to KC+4 floats so the
+// float4 reads of 8 consecutive tu hit 8 distinct bank groups).
+constexpr int kStepRows = 32, kStepKC = 64, kStepThreads = 256;
+
+template <int NC>
+struct StepGemm {
+  static constexpr int WR = 16 * NC;  // W rows per tile
+  static constexpr int LDS_ = kStepKC + 4;
+  static constexpr int SMEM_FLOATS = (kStepRows + WR) * LDS_;
+
+  template <class WRowFn>
+  __device__ static __forceinline__ void run(const float* __restrict__ A, int64_t lda, int row0, int nrows,
+                                             const float* __restrict__ W, int64_t ldw, WRowFn wrow, int K,
+                                             float* smem, float (&acc)[2][NC]) {
+    const int tid = threadIdx.x, rb = tid / 16, tu = tid % 16;
+    float* As = smem;
+    float* Ws = smem + kStepRows * LDS_;
+    const bool a_vec = ((reinterpret_cast<uintptr_t>(A) & 15) == 0) && (lda % 4 == 0);
+    const bool w_vec = ((reinterpret_cast<uintptr_t>(W) & 15) == 0) && (ldw % 4 == 0);
+    for (int k0 = 0; k0 < K; k0 += kStepKC) {
+      // A chunk: 32 rows x 64 k = 512 float4
+      for (int v = tid; v < kStepRows * kStepKC / 4; v += kStepThreads) {
+        int r = v / (kStepKC / 4), kq = v % (kStepKC / 4), gk = k0 + kq * 4, gr = row0 + r;
+        float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (gr < nrows && gk < K) {
+          const float* q = A + (int64_t)gr * lda + gk;
+          if (a_vec && gk + 3 < K) val = *reinterpret_cast<const float4*>(q);
+          else { val.x = q[0]; if (gk + 1 < K) val.y = q[1]; if (gk + 2 < K) val.z = q[2]; if (gk + 3 < K) val.w = q[3]; }
+        }
+        *reinterpret_cast<float4*>(&As[r * LDS_ + kq * 4]) = val;
+      }
+      for (int v = tid; v < WR * kStepKC / 4; v += kStepThreads) {
+        int r = v / (kStepKC / 4), kq = v % (kStepKC / 4), gk = k0 + kq * 4;
+        int64_t gr = wrow(r % 16, r / 16);  // < 0 when out of range
+        float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (gr >= 0 && gk < K) {
+          const float* q = W + gr * ldw + gk;
+          if (w_vec && gk + 3 < K) val = *reinterpret_cast<const float4*>(q);
+          else { val.x = q[0]; if (gk + 1 < K) val.y = q[1]; if (gk + 2 < K) val.z = q[2]; if (gk + 3 < K) val.w = q[3]; }
+        }
+        *reinterpret_cast<float4*>(&Ws[r * LDS_ + kq * 4]) = val;
+      }
+      __syncthreads();
+#pragma unroll 4
+      for (int kq = 0; kq < kStepKC / 4; ++kq) {
+        float4 a0 = *reinterpret_cast<const float4*>(&As[(rb * 2 + 0) * LDS_ + kq * 4]);
+        float4 a1 = *reinterpret_cast<const float4*>(&As[(rb * 2 + 1) * LDS_ + kq * 4]);
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+          float4 w = *reinterpret_cast<const float4*>(&Ws[(c * 16 + tu) * LDS_ + kq * 4]);
+          acc[0][c] = fmaf(a0.x, w.x, acc[0][c]); acc[0][c] = fmaf(a0.y, w.y, acc[0][c]);
+          acc[0][c] = fmaf(a0.z, w.z, acc[0][c]); acc[0][c] = fmaf(a0.w, w.w, acc[0][c]);
+          acc[1][c] = fmaf(a1.x, w.x, acc[1][c]); acc[1][c] = fmaf(a1.y, w.y, acc[1][c]);
+          acc[1][c] = fmaf(a1.z, w.z, acc[1][c]); acc[1][c] = fmaf(a1.w, w.w, acc[1][c]);
+        }
+      }
+      __syncthreads();
+    }
+  }
+};
+
+// ---- forward step -----------------------------------------------------------------------------
+struct FwdStepArgs {
+  const float* w_hh[2];
+  float* gates;            // [D,T,B,4H]
+  float* cs;               // [D,T,B,H]
+  const float* h_in;       // carried state, [D,B,H]
+  const float* c_in;
+  float* h_out;
+  float* c_out;
+  float* hs;               // [T,B,D*H]
+  int64_t ldhs;
+  const int64_t* lengths;
+  int s, T, B, H;
+};
+
+// grid (ceil(H/16), ceil(B/32), D); tile = 32 rows x 16 units x 4 gates
+__global__ void __launch_bounds__(kStepThreads) lstm_step_fwd_kernel(FwdStepArgs p) {
+  __shared__ __align__(16) float smem[StepGemm<4>::SMEM_FLOATS];
+  const int d = blockIdx.z, H = p.H, B = p.B;
+  const int t = d == 0 ? p.s : p.T - 1 - p.s;
+  const int u0 = blockIdx.x * 16, b0 = blockIdx.y * kStepRows;
+  const int tid = threadIdx.x, rb = tid / 16, tu = tid % 16;
+  const float* h_in = p.h_in + (int64_t)d * B * H;
+  float acc[2][4] = {};
+  auto wrow = [&](int u, int g) -> int64_t { return (u0 + u < H) ? (int64_t)g * H + u0 + u : -1; };
+  StepGemm<4>::run(h_in, H, b0, B, p.w_hh[d], H, wrow, H, smem, acc);
+  const int u = u0 + tu;
+  if (u >= H) return;
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int b = b0 + rb * 2 + r;
+    if (b >= B) continue;
+    const int64_t sb = ((int64_t)d * B + b) * H + u;                       // carried-state index
+    const int64_t gi = (((int64_t)d * p.T + t) * B + b) * 4 * H + u;       // gate slab index (gate 0)
+    const int64_t ci = (((int64_t)d * p.T + t) * B + b) * H + u;
+    const float c_prev = p.c_in[sb], h_prev = p.h_in[sb];
+    const bool live = p.lengths == nullptr || t < p.lengths[b];
+    float* hs = p.hs + ((int64_t)t * B + b) * p.ldhs + d * H + u;
+    if (live) {
+      const float ig = sigmoidf_(p.gates[gi] + acc[r][0]);
+      const float fg = sigmoidf_(p.gates[gi + H] + acc[r][1]);
+      const float gg = tanhf(p.gates[gi + 2 * H] + acc[r][2]);
+      const float og = sigmoidf_(p.gates[gi + 3 * H] + acc[r][3]);
+      const float c = fmaf(fg, c_prev, ig * gg);
+      const float h = og * tanhf(c);
+      p.gates[gi] = ig; p.gates[gi + H] = fg; p.gates[gi + 2 * H] = gg; p.gates[gi + 3 * H] = og;
+      p.cs[ci] = c; p.c_out[sb] = c; p.h_out[sb] = h; *hs = h;
+    } else {
+      p.gates[gi] = 0.f; p.gates[gi + H] = 0.f; p.gates[gi + 2 * H] = 0.f; p.gates[gi + 3 * H] = 0.f;
+      p.cs[ci] = c_prev; p.c_out[sb] = c_prev; p.h_out[sb] = h_prev; *hs = 0.f;
+    }
+  }
+}
+
+// ---- backward step ----------------------------------------------------------------------------
+struct BwdStepArgs {
+  const float* w_hh_t[2];  // [H,4H] (transposed recurrent weights)
+  float* gates;            // [D,T,B,4H]: post-activation gates in, dG out
+  const float* cs;         // [D,T,B,H]
+  const float* c0;         // initial cell state [D][B] rows (ld0, dir0) or NULL
+  int64_t ld0, dir0;
+  const float* d_hs;       // [T,B,D*H] or NULL
+  int64_t lddhs;
+  const float* carry_in;   // [D,B,H] gradient carried by frozen rows / final-state gradient
+  const float* dc_in;
+  float* carry_out;
+  float* dc_out;
+  float* d_h0;             // final launch only: gradient w.r.t. the initial state
+  float* d_c0;
+  int64_t ldd0, dird0;
+  const int64_t* lengths;
+  int s, T, B, H, final_;
+};
+
+// grid (ceil(H/32), ceil(B/32), D); tile = 32 rows x 32 units
+__global__ void __launch_bounds__(kStepThreads) lstm_step_bwd_kernel(BwdStepArgs p) {
+  __shared__ __align__(16) float smem[StepGemm<2>::SMEM_FLOATS];
+  const int d = blockIdx.z, H = p.H, B = p.B, T = p.T;
+  // time index processed at this step and the one processed at the previous step
+  const int t = d == 0 ? T - 1 - p.s : p.s;
+  const int t_next = d == 0 ? t + 1 : t - 1;
+  const int u0 = blockIdx.x * 32, b0 = blockIdx.y * kStepRows;
+  const int tid = threadIdx.x, rb = tid / 16, tu = tid % 16;
+  float acc[2][2] = {};
+  if (p.s > 0) {
+    const float* dg_next = p.gates + ((int64_t)d * T + t_next) * B * 4 * H;
+    auto wrow = [&](int u, int c) -> int64_t { return (u0 + c * 16 + u < H) ? (int64_t)(u0 + c * 16 + u) : -1; };
+    StepGemm<2>::run(dg_next, 4 * H, b0, B, p.w_hh_t[d], 4 * H, wrow, 4 * H, smem, acc);
+  }
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int b = b0 + rb * 2 + r;
+    if (b >= B) continue;
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      const int u = u0 + c * 16 + tu;
+      if (u >= H) continue;
+      const int64_t sb = ((int64_t)d * B + b) * H + u;
+      const float dh_in = p.carry_in[sb] + acc[r][c];
+      const float dc_in = p.dc_in[sb];
+      if (p.final_) {
+        if (p.d_h0) p.d_h0[d * p.dird0 + (int64_t)b * p.ldd0 + u] = dh_in;
+        if (p.d_c0) p.d_c0[d * p.dird0 + (int64_t)b * p.ldd0 + u] = dc_in;
+        continue;
+      }
+      const int64_t gi = (((int64_t)d * T + t) * B + b) * 4 * H + u;
+      const bool live = p.lengths == nullptr || t < p.lengths[b];
+      if (!live) {
+        p.gates[gi] = 0.f; p.gates[gi + H] = 0.f; p.gates[gi + 2 * H] = 0.f; p.gates[gi + 3 * H] = 0.f;
+        p.carry_out[sb] = dh_in; p.dc_out[sb] = dc_in;
+        continue;
+      }
+      const int64_t ci = (((int64_t)d * T + t) * B + b) * H + u;
+      const int t_prev = d == 0 ? t - 1 : t + 1;     // step that ran before t in the forward traversal
+      float c_prev;
+      if (t_prev >= 0 && t_prev < T) c_prev = p.cs[(((int64_t)d * T + t_prev) * B + b) * H + u];
+      else c_prev = p.c0 ? p.c0[d * p.dir0 + (int64_t)b * p.ld0 + u] : 0.f;
+      const float dh = dh_in + (p.d_hs ? p.d_hs[((int64_t)t * B + b) * p.lddhs + d * H + u] : 0.f);
+      const float ig = p.gates[gi], fg = p.gates[gi + H], gg = p.gates[gi + 2 * H], og = p.gates[gi + 3 * H];
+      const float tc = tanhf(p.cs[ci]);
+      const float dc = fmaf(dh * og, 1.f - tc * tc, dc_in);
+      p.gates[gi] = dc * gg * ig * (1.f - ig);
+      p.gates[gi + H] = dc * c_prev * fg * (1.f - fg);
+      p.gates[gi + 2 * H] = dc * ig * (1.f - gg * gg);
+      p.gates[gi + 3 * H] = dh * tc * og * (1.f - og);
+      p.carry_out[sb] = 0.f;
+      p.dc_out[sb] = dc * fg;
+    }
+  }
+}
+
+// ---- host orchestration -----------------------------------------------------------------------
+static int64_t state_floats(int B, int H, int D) { return 4LL * D * B * H; }
+
+int lstm_seq_fwd_impl(const float* x, int64_t ldx, int T, int B, int I, int H, int D, const float* const* w_ih,
+                      const float* const* w_hh, const float* const* b_ih, const float* const* b_hh,
+                      const float* h0, const float* c0, int64_t ld0, int64_t dir0, const int64_t* lengths,
+                      float* hs, int64_t ldhs, float* hn, float* cn, int64_t ldn, int64_t dirn, float* gates,
+                      float* cs, float* ws, cudaStream_t st) {
+  DVAE_REQUIRE(x && hs && gates && cs && ws && w_ih && w_hh, "dvae_lstm_seq_fwd: null pointer");
+  DVAE_REQUIRE(T > 0 && B > 0 && I > 0 && H > 0 && (D == 1 || D == 2), "dvae_lstm_seq_fwd: bad shape T=%d B=%d I=%d H=%d D=%d", T, B, I, H, D);
+  DVAE_REQUIRE(!(lengths && h0), "dvae_lstm_seq_fwd: length-masked layers start from the zero state");
+  const int64_t slab = (int64_t)T * B * 4 * H, sf = (int64_t)D * B * H;
+  for (int d = 0; d < D; ++d) {
+    int rc = linear_impl(x, ldx, 0, w_ih[d], I, 0, gates + d * slab, 4 * H, T * B, 4 * H, I, b_ih ? b_ih[d] : nullptr,
+                         b_hh ? b_hh[d] : nullptr, 0.f, 0, st);
+    if (rc) return rc;
+  }
+  float* hbuf[2] = {ws, ws + 2 * sf};
+  float* cbuf[2] = {ws + sf, ws + 3 * sf};
+  const int nthr = 256, nblk = ceil_div(sf, nthr);
+  copy_state_kernel<<<nblk, nthr, 0, st>>>(h0, ld0, dir0, hbuf[0], H, (int64_t)B * H, D, B, H);
+  DVAE_LAUNCH_CHECK();
+  copy_state_kernel<<<nblk, nthr, 0, st>>>(c0, ld0, dir0, cbuf[0], H, (int64_t)B * H, D, B, H);
+  DVAE_LAUNCH_CHECK();
+  FwdStepArgs a;
+  for (int d = 0; d < 2; ++d) a.w_hh[d] = w_hh[d < D ? d : 0];
+  a.gates = gates; a.cs = cs; a.hs = hs; a.ldhs = ldhs; a.lengths = lengths; a.T = T; a.B = B; a.H = H;
+  dim3 grid(ceil_div(H, 16), ceil_div(B, kStepRows), D);
+  for (int s = 0; s < T; ++s) {
+    a.s = s;
+    a.h_in = hbuf[s & 1]; a.c_in = cbuf[s & 1]; a.h_out = hbuf[(s + 1) & 1]; a.c_out = cbuf[(s + 1) & 1];
+    lstm_step_fwd_kernel<<<grid, kStepThreads, 0, st>>>(a);
+    DVAE_LAUNCH_CHECK();
+  }
+  if (hn) {
+    copy_state_kernel<<<nblk, nthr, 0, st>>>(hbuf[T & 1], H, (int64_t)B * H, hn, ldn, dirn, D, B, H);
+    DVAE_LAUNCH_CHECK();
+  }
+  if (cn) {
+    copy_state_kernel<<<nblk, nthr, 0, st>>>(cbuf[T & 1], H, (int64_t)B * H, cn, ldn, dirn, D, B, H);
+    DVAE_LAUNCH_CHECK();
+  }
+  return DVAE_OK;
+}
+
+int lstm_seq_bwd_impl(const float* x, int64_t ldx, int T, int B, int I, int H, int D, const float* const* w_ih,
+                      const float* const* w_hh, const float* h0, const float* c0, int64_t ld0, int64_t dir0,
+                      const int64_t* lengths, const float* hs, int64_t ldhs, float* gates, const float* cs,
+                      const float* d_hs, int64_t lddhs, const float* d_hn, const float* d_cn, int64_t ldn,
+                      int64_t dirn, float* d_x, int64_t lddx, float* const* d_w_ih, float* const* d_w_hh,
+                      float* const* d_b_ih, float* const* d_b_hh, float* d_h0, float* d_c0, int64_t ldd0,
+                      int64_t dird0, float* ws, cudaStream_t st) {
+  DVAE_REQUIRE(x && hs && gates && cs && ws && w_ih && w_hh, "dvae_lstm_seq_bwd: null pointer");
+  DVAE_REQUIRE(T > 0 && B > 0 && I > 0 && H > 0 && (D == 1 || D == 2), "dvae_lstm_seq_bwd: bad shape");
+  DVAE_REQUIRE(!(lengths && h0), "dvae_lstm_seq_bwd: length-masked layers start from the zero state");
+  const int64_t slab = (int64_t)T * B * 4 * H, sf = (int64_t)D * B * H;
+  float* carry[2] = {ws, ws + 2 * sf};
+  float* dcb[2] = {ws + sf, ws + 3 * sf};
+  float* wt = ws + 4 * sf;  // [D][H,4H]
+  for (int d = 0; d < D; ++d) {
+    transpose_kernel<<<dim3(ceil_div(H, 32), ceil_div(4 * H, 32)), dim3(32, 8), 0, st>>>(w_hh[d], wt + (int64_t)d * 4 * H * H, 4 * H, H);
+    DVAE_LAUNCH_CHECK();
+  }
+  const int nthr = 256, nblk = ceil_div(sf, nthr);
+  copy_state_kernel<<<nblk, nthr, 0, st>>>(d_hn, ldn, dirn, carry[0], H, (int64_t)B * H, D, B, H);
+  DVAE_LAUNCH_CHECK();
+  copy_state_kernel<<<nblk, nthr, 0, st>>>(d_cn, ldn, dirn, dcb[0], H, (int64_t)B * H, D, B, H);
+  DVAE_LAUNCH_CHECK();
+  BwdStepArgs a;
+  for (int d = 0; d < 2; ++d) a.w_hh_t[d] = wt + (int64_t)(d < D ? d : 0) * 4 * H * H;
+  a.gates = gates; a.cs = cs; a.c0 = c0; a.ld0 = ld0; a.dir0 = dir0; a.d_hs = d_hs; a.lddhs = lddhs;
+  a.d_h0 = d_h0; a.d_c0 = d_c0; a.ldd0 = ldd0; a.dird0 = dird0; a.lengths = lengths; a.T = T; a.B = B; a.H = H;
+  dim3 grid(ceil_div(H, 32), ceil_div(B, kStepRows), D);
+  const int nsteps = T + ((d_h0 || d_c0) ? 1 : 0);
+  for (int s = 0; s < nsteps; ++s) {
+    a.s = s; a.final_ = (s == T);
+    a.carry_in = carry[s & 1]; a.dc_in = dcb[s & 1]; a.carry_out = carry[(s + 1) & 1]; a.dc_out = dcb[(s + 1) & 1];
+    if (a.final_) {
+      // s == T: t_next must be the last processed index; reuse the formulas with s = T
+      // (dir 0: t = -1 -> t_next = 0; dir 1: t = T -> t_next = T-1)
+    }
+    lstm_step_bwd_kernel<<<grid, kStepThreads, 0, st>>>(a);
+    DVAE_LAUNCH_CHECK();
+  }
+  // dense gradients from the saved dG slabs
+  for (int d = 0; d < D; ++d) {
+    const float* dG = gates + d * slab;
+    int rc;
+    if (d_x) {
+      rc = linear_impl(dG, 4 * H, 0, w_ih[d], I, 1, d_x, lddx, T * B, I, 4 * H, nullptr, nullptr, d == 0 ? 0.f : 1.f, 0, st);
+      if (rc) return rc;
+    }
+    if (d_w_ih && d_w_ih[d]) {
+      rc = linear_impl(dG, 4 * H, 1, x, ldx, 1, d_w_ih[d], I, 4 * H, I, T * B, nullptr, nullptr, 0.f, 0, st);
+      if (rc) return rc;
+    }
+    if (d_w_hh && d_w_hh[d]) {
+      // h_prev[t] = hs at the previously traversed step (zero / h0 at the first one)
+      bool wrote = false;
+      if (T > 1) {
+        const float* dGs = d == 0 ? dG + (int64_t)B * 4 * H : dG;
+        const float* hp = d == 0 ? hs + d * H : hs + (int64_t)B * ldhs + d * H;
+        rc = linear_impl(dGs, 4 * H, 1, hp, ldhs, 1, d_w_hh[d], H, 4 * H, H, (T - 1) * B, nullptr, nullptr, 0.f, 0, st);
+        if (rc) return rc;
+        wrote = true;
+      }
+      if (h0) {
+        const float* dG0 = d == 0 ? dG : dG + (int64_t)(T - 1) * B * 4 * H;
+        rc = linear_impl(dG0, 4 * H, 1, h0 + d * dir0, ld0, 1, d_w_hh[d], H, 4 * H, H, B, nullptr, nullptr, wrote ? 1.f : 0.f, 0, st);
+        if (rc) return rc;
+        wrote = true;
+      }
+      if (!wrote) DVAE_CUDA(cudaMemsetAsync(d_w_hh[d], 0, sizeof(float) * 4 * H * H, st));
+    }
+    if (d_b_ih && d_b_ih[d]) {
+      rc = colsum_impl(dG, 4 * H, T * B, 4 * H, d_b_ih[d], 0.f, st);
+      if (rc) return rc;
+      if (d_b_hh && d_b_hh[d]) DVAE_CUDA(cudaMemcpyAsync(d_b_hh[d], d_b_ih[d], sizeof(float) * 4 * H, cudaMemcpyDeviceToDevice, st));
+    } else if (d_b_hh && d_b_hh[d]) {
+      rc = colsum_impl(dG, 4 * H, T * B, 4 * H, d_b_hh[d], 0.f, st);
+      if (rc) return rc;
+    }
+  }
+  return DVAE_OK;
+}
+
+}  // namespace dvae
+
+extern "C" int64_t dvae_lstm_state_ws_floats(int B, int H, int D) {
+  return dvae::state_floats(B, H, D) + 4LL * D * H * H;
+}
+
+extern "C" int dvae_lstm_seq_fwd(const float* x, int64_t ldx, int T, int B, int I, int H, int D,
+                                 const float* const* w_ih, const float* const* w_hh, const float* const* b_ih,
+                                 const float* const* b_hh, const float* h0, const float* c0, int64_t ld0,
+                                 int64_t dir0, const int64_t* lengths, float* hs, int64_t ldhs, float* hn,
+                                 float* cn, int64_t ldn, int64_t dirn, float* gates, float* cs, float* state_ws,
+                                 void* stream) {
+  return dvae::lstm_seq_fwd_impl(x, ldx, T, B, I, H, D, w_ih, w_hh, b_ih, b_hh, h0, c0, ld0, dir0, lengths, hs,
+                                 ldhs, hn, cn, ldn, dirn, gates, cs, state_ws, (cudaStream_t)stream);
+}
+
+extern "C" int dvae_lstm_seq_bwd(const float* x, int64_t ldx, int T, int B, int I, int H, int D,
+                                 const float* const* w_ih, const float* const* w_hh, const float* h0,
+                                 const float* c0, int64_t ld0, int64_t dir0, const int64_t* lengths,
+                                 const float* hs, int64_t ldhs, float* gates, const float* cs, const float* d_hs,
+                                 int64_t lddhs, const float* d_hn, const float* d_cn, int64_t ldn, int64_t dirn,
+                                 float* d_x, int64_t lddx, float* const* d_w_ih, float* const* d_w_hh,
+                                 float* const* d_b_ih, float* const* d_b_hh, float* d_h0, float* d_c0,
+                                 int64_t ldd0, int64_t dird0, float* state_ws, void* stream) {
+  return dvae::lstm_seq_bwd_impl(x, ldx, T, B, I, H, D, w_ih, w_hh, h0, c0, ld0, dir0, lengths, hs, ldhs, gates, cs,
+                                 d_hs, lddhs, d_hn, d_cn, ldn, dirn, d_x, lddx, d_w_ih, d_w_hh, d_b_ih, d_b_hh,
+                                 d_h0, d_c0, ldd0, dird0, state_ws, (cudaStream_t)stream);
+}

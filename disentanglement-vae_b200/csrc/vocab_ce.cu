@@ -1,0 +1,269 @@
+// Fused vocabulary projection + online log-softmax + masked NLL (see include/dvae_b200.h).
+//
+// Forward: each CTA owns a 128-row tile of decoder outputs and a slice of the vocabulary; it walks
+// its slice in 128-column tiles (fp32 SIMT tile GEMM, K = H), folds every logits tile into running
+// (max, sum-exp, argmax, target-logit) registers and never writes logits.  A single-CTA finalise
+// kernel merges the vocabulary slices in a fixed order -> lse, nll, argmax and the masked, batch-
+// averaged loss (deterministic).
+// Backward (this round): softmax tiles are recomputed from h, W and the saved lse into an
+// L2-sized chunk buffer P[N, Vc] and consumed by two dense GEMMs per chunk (dh += P W, dW = P^T h).
+#include <math.h>
+
+#include "gemm_simt.cuh"
+
+namespace dvae {
+
+int linear_impl(const float* A, int64_t lda, int trans_a, const float* B, int64_t ldb, int trans_b, float* C,
+                int64_t ldc, int M, int N, int K, const float* bias, const float* bias2, float beta, int act,
+                cudaStream_t st);
+int colsum_impl(const float* X, int64_t ldx, int M, int N, float* out, float beta, cudaStream_t st);
+
+using GCE = GemmTile<128, 128, 16, 8, 8, true, true>;
+
+struct CeArgs {
+  const float* h; int64_t ldh;
+  const float* w; const float* bias;
+  const int64_t* targets; int64_t tgt_stride_b;
+  const int64_t* lengths;
+  int N, B, H, V, sos;
+  int tiles_per_split, nsplit;
+  float* part;      // [nsplit][N][4]: max, sumexp, target logit, argmax value
+  int* part_idx;    // [nsplit][N]
+};
+
+__device__ __forceinline__ void merge_ms(float& m, float& s, float m2, float s2) {
+  float M = fmaxf(m, m2);
+  if (M == -INFINITY) { s = 0.f; m = M; return; }
+  s = s * expf(m - M) + s2 * expf(m2 - M);
+  m = M;
+}
+
+__global__ void __launch_bounds__(GCE::NT) vocab_ce_fwd_kernel(CeArgs p) {
+  __shared__ __align__(16) float smem[GCE::SMEM_FLOATS];
+  const int m0 = blockIdx.x * GCE::BM, split = blockIdx.y;
+  const int ty = threadIdx.x / GCE::TX, tx = threadIdx.x % GCE::TX;
+  const int vtiles = (p.V + GCE::BN - 1) / GCE::BN;
+  const int vt0 = split * p.tiles_per_split, vt1 = min(vtiles, vt0 + p.tiles_per_split);
+  float rm[GCE::TM], rs[GCE::TM], rt[GCE::TM], rav[GCE::TM];
+  int rai[GCE::TM], tgt[GCE::TM];
+#pragma unroll
+  for (int i = 0; i < GCE::TM; ++i) {
+    rm[i] = -INFINITY; rs[i] = 0.f; rt[i] = 0.f; rav[i] = -INFINITY; rai[i] = 0x7fffffff;
+    int n = m0 + GCE::row_of(ty, i);
+    tgt[i] = -1;
+    if (n < p.N) tgt[i] = (int)p.targets[(int64_t)(n % p.B) * p.tgt_stride_b + (n / p.B) + 1];
+  }
+  for (int vt = vt0; vt < vt1; ++vt) {
+    const int n0 = vt * GCE::BN;
+    float acc[GCE::TM][GCE::TN];
+#pragma unroll
+    for (int i = 0; i < GCE::TM; ++i)
+#pragma unroll
+      for (int j = 0; j < GCE::TN; ++j) acc[i][j] = 0.f;
+    GCE::run(p.h, p.ldh, m0, p.N, p.w, p.H, n0, p.V, 0, p.H, p.H, smem, acc);
+    float bj[GCE::TN];
+    int cj[GCE::TN];
+#pragma unroll
+    for (int j = 0; j < GCE::TN; ++j) {
+      cj[j] = n0 + GCE::col_of(tx, j);
+      bj[j] = cj[j] < p.V ? p.bias[cj[j]] : 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < GCE::TM; ++i) {
+      float tmax = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < GCE::TN; ++j) {
+        float v = cj[j] < p.V ? acc[i][j] + bj[j] : -INFINITY;
+        acc[i][j] = v;
+        tmax = fmaxf(tmax, v);
+        if (v > rav[i] || (v == rav[i] && cj[j] < rai[i])) { rav[i] = v; rai[i] = cj[j]; }
+        if (cj[j] == tgt[i]) rt[i] = v;
+      }
+      if (tmax > rm[i]) { rs[i] *= expf(rm[i] - tmax); rm[i] = tmax; }
+      if (rm[i] != -INFINITY) {
+#pragma unroll
+        for (int j = 0; j < GCE::TN; ++j) rs[i] += expf(acc[i][j] - rm[i]);
+      }
+    }
+  }
+  // combine the 16 threads (tx) that share each row: lanes [16*(ty&1), +16) of the warp
+#pragma unroll
+  for (int i = 0; i < GCE::TM; ++i) {
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) {
+      float m2 = __shfl_xor_sync(0xffffffffu, rm[i], o), s2 = __shfl_xor_sync(0xffffffffu, rs[i], o);
+      float t2 = __shfl_xor_sync(0xffffffffu, rt[i], o), av2 = __shfl_xor_sync(0xffffffffu, rav[i], o);
+      int ai2 = __shfl_xor_sync(0xffffffffu, rai[i], o);
+      merge_ms(rm[i], rs[i], m2, s2);
+      rt[i] += t2;
+      if (av2 > rav[i] || (av2 == rav[i] && ai2 < rai[i])) { rav[i] = av2; rai[i] = ai2; }
+    }
+    int n = m0 + GCE::row_of(ty, i);
+    if (tx == 0 && n < p.N) {
+      float4 o4 = make_float4(rm[i], rs[i], rt[i], rav[i]);
+      *reinterpret_cast<float4*>(p.part + ((int64_t)split * p.N + n) * 4) = o4;
+      p.part_idx[(int64_t)split * p.N + n] = rai[i];
+    }
+  }
+}
+
+__global__ void __launch_bounds__(1024) vocab_ce_finalize_kernel(CeArgs p, float* lse, float* nll, int32_t* argmax,
+                                                                 float* loss) {
+  __shared__ float red[32];
+  float local = 0.f;
+  for (int n = threadIdx.x; n < p.N; n += blockDim.x) {
+    float m = -INFINITY, s = 0.f, t = 0.f, av = -INFINITY;
+    int ai = 0x7fffffff;
+    for (int sp = 0; sp < p.nsplit; ++sp) {
+      float4 q = *reinterpret_cast<const float4*>(p.part + ((int64_t)sp * p.N + n) * 4);
+      int qi = p.part_idx[(int64_t)sp * p.N + n];
+      merge_ms(m, s, q.x, q.y);
+      t += q.z;
+      if (q.w > av || (q.w == av && qi < ai)) { av = q.w; ai = qi; }
+    }
+    float l = m + logf(s), e = l - t;
+    if (lse) lse[n] = l;
+    if (nll) nll[n] = e;
+    if (argmax) argmax[n] = ai;
+    int b = n % p.B, tpos = n / p.B + 1;
+    if (tpos < p.lengths[b]) local += e;
+  }
+  // position 0: one-hot(1.0) pseudo-logits at <SOS> (model.py:454): lse = 1 + log(1 + (V-1)/e)
+  for (int b = threadIdx.x; b < p.B; b += blockDim.x) {
+    if (p.lengths[b] > 0) {
+      float l0 = (float)(1.0 + log(1.0 + (double)(p.V - 1) * exp(-1.0)));
+      local += l0 - (p.targets[(int64_t)b * p.tgt_stride_b] == p.sos ? 1.f : 0.f);
+    }
+  }
+  local = warp_sum(local);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = local;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float tot = 0.f;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) tot += red[i];
+    loss[0] = tot / (float)p.B;
+  }
+}
+
+// P[n][v - v0] = (softmax(logits[n])[v] - [v == target_n]) * mask_n * scale / B for v in [v0, v0+vc)
+struct PArgs {
+  const float* h; int64_t ldh;
+  const float* w; const float* bias;
+  const int64_t* targets; int64_t tgt_stride_b;
+  const int64_t* lengths;
+  const float* lse;
+  const float* grad_scale;
+  int N, B, H, V, v0, vc;
+  float* P; int64_t ldp;
+};
+
+__global__ void __launch_bounds__(GCE::NT) vocab_p_kernel(PArgs p) {
+  __shared__ __align__(16) float smem[GCE::SMEM_FLOATS];
+  const int m0 = blockIdx.y * GCE::BM, n0 = p.v0 + blockIdx.x * GCE::BN;
+  const int ty = threadIdx.x / GCE::TX, tx = threadIdx.x % GCE::TX;
+  float acc[GCE::TM][GCE::TN];
+#pragma unroll
+  for (int i = 0; i < GCE::TM; ++i)
+#pragma unroll
+    for (int j = 0; j < GCE::TN; ++j) acc[i][j] = 0.f;
+  GCE::run(p.h, p.ldh, m0, p.N, p.w, p.H, n0, min(p.V, p.v0 + p.vc), 0, p.H, p.H, smem, acc);
+  const float gs = (p.grad_scale ? p.grad_scale[0] : 1.f) / (float)p.B;
+#pragma unroll
+  for (int i = 0; i < GCE::TM; ++i) {
+    int n = m0 + GCE::row_of(ty, i);
+    if (n >= p.N) continue;
+    int b = n % p.B, tpos = n / p.B + 1;
+    float scale = (tpos < p.lengths[b]) ? gs : 0.f;
+    int tgt = (int)p.targets[(int64_t)b * p.tgt_stride_b + tpos];
+    float l = p.lse[n];
+#pragma unroll
+    for (int j = 0; j < GCE::TN; ++j) {
+      int v = n0 + GCE::col_of(tx, j);
+      if (v >= p.V || v >= p.v0 + p.vc) continue;
+      float pr = scale == 0.f ? 0.f : (expf(acc[i][j] + p.bias[v] - l) - (v == tgt ? 1.f : 0.f)) * scale;
+      p.P[(int64_t)n * p.ldp + (v - p.v0)] = pr;
+    }
+  }
+}
+
+static int ce_nsplit(int N, int V, int* tiles_per_split) {
+  int row_tiles = ceil_div(N, GCE::BM), vtiles = ceil_div(V, GCE::BN);
+  int want = ceil_div(2 * 148, row_tiles);
+  if (want < 1) want = 1;
+  if (want > vtiles) want = vtiles;
+  int tps = ceil_div(vtiles, want);
+  *tiles_per_split = tps;
+  return ceil_div(vtiles, tps);
+}
+
+static int p_chunk(int N, int V) {
+  // keep the softmax chunk around 48 MB so it stays L2-resident between producer and consumers
+  int64_t vc = (12LL << 20) / (N > 0 ? N : 1);
+  vc = vc / 128 * 128;
+  if (vc < 128) vc = 128;
+  int64_t vr = (int64_t)ceil_div(V, 128) * 128;
+  if (vc > vr) vc = vr;
+  return (int)vc;
+}
+
+}  // namespace dvae
+
+using namespace dvae;
+
+extern "C" int64_t dvae_vocab_ce_ws_floats(int N, int V) {
+  int tps;
+  int ns = ce_nsplit(N, V, &tps);
+  return (int64_t)ns * N * 5 + 8;
+}
+
+extern "C" int dvae_vocab_ce_fwd(const float* h, int64_t ldh, int T1, int B, int H, int V, const float* w,
+                                 const float* bias, const int64_t* targets, int64_t tgt_stride_b,
+                                 const int64_t* lengths, int sos, float* lse, float* nll, int32_t* argmax,
+                                 float* loss, float* ws, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  DVAE_REQUIRE(h && w && bias && targets && lengths && loss && ws, "dvae_vocab_ce_fwd: null pointer");
+  DVAE_REQUIRE(T1 > 0 && B > 0 && H > 0 && V > 0, "dvae_vocab_ce_fwd: bad shape T1=%d B=%d H=%d V=%d", T1, B, H, V);
+  CeArgs p;
+  p.h = h; p.ldh = ldh; p.w = w; p.bias = bias; p.targets = targets; p.tgt_stride_b = tgt_stride_b;
+  p.lengths = lengths; p.N = T1 * B; p.B = B; p.H = H; p.V = V; p.sos = sos;
+  p.nsplit = ce_nsplit(p.N, V, &p.tiles_per_split);
+  p.part = ws;
+  p.part_idx = reinterpret_cast<int*>(ws + (int64_t)p.nsplit * p.N * 4);
+  dim3 grid(ceil_div(p.N, GCE::BM), p.nsplit);
+  vocab_ce_fwd_kernel<<<grid, GCE::NT, 0, st>>>(p);
+  DVAE_LAUNCH_CHECK();
+  vocab_ce_finalize_kernel<<<1, 1024, 0, st>>>(p, lse, nll, argmax, loss);
+  DVAE_LAUNCH_CHECK();
+  return DVAE_OK;
+}
+
+extern "C" int64_t dvae_vocab_ce_bwd_ws_floats(int N, int V) { return (int64_t)N * p_chunk(N, V); }
+
+extern "C" int dvae_vocab_ce_bwd(const float* h, int64_t ldh, int T1, int B, int H, int V, const float* w,
+                                 const float* bias, const int64_t* targets, int64_t tgt_stride_b,
+                                 const int64_t* lengths, const float* lse, const float* grad_scale_dev,
+                                 float* d_h, int64_t lddh, float* d_w, float* d_bias, float* ws, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  DVAE_REQUIRE(h && w && bias && targets && lengths && lse && d_h && d_w && d_bias && ws, "dvae_vocab_ce_bwd: null pointer");
+  DVAE_REQUIRE(T1 > 0 && B > 0 && H > 0 && V > 0, "dvae_vocab_ce_bwd: bad shape");
+  const int N = T1 * B, vc_max = p_chunk(N, V);
+  PArgs p;
+  p.h = h; p.ldh = ldh; p.w = w; p.bias = bias; p.targets = targets; p.tgt_stride_b = tgt_stride_b;
+  p.lengths = lengths; p.lse = lse; p.grad_scale = grad_scale_dev; p.N = N; p.B = B; p.H = H; p.V = V;
+  p.P = ws; p.ldp = vc_max;
+  int chunk = 0;
+  for (int v0 = 0; v0 < V; v0 += vc_max, ++chunk) {
+    const int vc = min(vc_max, V - v0);
+    p.v0 = v0; p.vc = vc;
+    dim3 grid(ceil_div(vc, GCE::BN), ceil_div(N, GCE::BM));
+    vocab_p_kernel<<<grid, GCE::NT, 0, st>>>(p);
+    DVAE_LAUNCH_CHECK();
+    int rc;
+    // d_h [N,H] (+)= P [N,vc] . W[v0:v0+vc, :]        (B stored [K=vc][N=H])
+    if ((rc = linear_impl(ws, vc_max, 0, w + (int64_t)v0 * H, H, 1, d_h, lddh, N, H, vc, nullptr, nullptr, chunk ? 1.f : 0.f, 0, st))) return rc;
+    // d_w[v0:v0+vc, :] = P^T [vc,N] . h [N,H]
+    if ((rc = linear_impl(ws, vc_max, 1, h, ldh, 1, d_w + (int64_t)v0 * H, H, vc, H, N, nullptr, nullptr, 0.f, 0, st))) return rc;
+    if ((rc = colsum_impl(ws, vc_max, N, vc, d_bias + v0, 0.f, st))) return rc;
+  }
+  return DVAE_OK;
+}

@@ -1,0 +1,290 @@
+"""Kernel sequencing for one (batch, length) shape: owns every activation / workspace buffer and
+issues the C-ABI calls of `include/dvae_b200.h` in forward and backward order.
+
+Used by both host paths: the drop-in module (`model.py`, through autograd Functions) and the
+graph-captured training engine (`engine.py`).  No torch compute ops on the path -- torch only
+allocates memory and provides the stream.
+
+Data layout in HBM (all fp32 unless noted), T = padded length, T1 = T-1, N = T1*B:
+  x_enc   [T,B,E]            embedded (+dropout) encoder input, time-major
+  e_gates [Le][D,T,B,4H]     pre-activations -> post-activation gates -> (backward) dG, in place
+  e_cs    [Le][D,T,B,H]      cell states;  e_hs [Le][T,B,D*H] layer outputs (zeros at padding)
+  ctx     [B,C]              concat of final hidden states, written in place by the LSTM kernels
+  eps,z,mu,logvar [B,Z]; hid [B,2*H*Ld]; dsc_logits [B,OD]; scalars [27]
+  x_dec   [T1,B,E]; d_gates/d_cs/d_hs as above with D=1
+  lse,nll [N]; argmax [N] int32; recon [1]
+"""
+import torch
+
+from . import _lib
+from ._lib import ptr, ptr_array, int_array, check
+
+SALT_ENC_EMB, SALT_DEC_EMB, SALT_ENC_LAYER, SALT_DEC_LAYER, SALT_EPS = 1, 3, 16, 32, 64
+
+
+class Dims:
+    """Static shape information derived from the module (mirrors vae/model.py:261-321)."""
+
+    def __init__(self, model):
+        enc, dec = model.encoder, model.decoder
+        self.V, self.E = enc.embedding.weight.shape
+        self.H = enc.hidden_size
+        self.D = enc.num_directions
+        self.Le = enc.num_layers
+        self.Ld = dec.num_layers
+        self.C = self.H * self.Le * self.D
+        self.space_names = list(model.context2params.keys())
+        self.space_dims = [model.context2params[n].out_features // 2 for n in self.space_names]
+        self.S = len(self.space_names)
+        self.Z = sum(self.space_dims)
+        self.dsc_out = [model.discriminators[n].output_dim if n in model.discriminators else 0
+                        for n in self.space_names]
+        self.OD = sum(self.dsc_out)
+        self.H2L = 2 * self.H * self.Ld
+        self.sos, self.eos = model.sos_token_idx, model.eos_token_idx
+        self.p_enc, self.p_dec = float(enc.dropout_rate), float(dec.dropout_rate)
+        assert self.S <= _lib.MAX_SPACES, f"at most {_lib.MAX_SPACES} latent spaces"
+
+
+class StepPlan:
+    def __init__(self, model, B, T, device):
+        self.lib = _lib.load()
+        self.d = d = Dims(model)
+        self.B, self.T, self.T1 = B, T, T - 1
+        self.N = self.T1 * B
+        self.device = device
+        self.busy = False
+        f32 = dict(device=device, dtype=torch.float32)
+        H, D, E = d.H, d.D, d.E
+
+        def buf(*shape):
+            return torch.empty(*shape, **f32)
+
+        self.x_enc = buf(T, B, E)
+        self.e_gates = [buf(D, T, B, 4 * H) for _ in range(d.Le)]
+        self.e_cs = [buf(D, T, B, H) for _ in range(d.Le)]
+        self.e_hs = [buf(T, B, D * H) for _ in range(d.Le)]
+        self.e_xin = [None] + [buf(T, B, D * H) for _ in range(1, d.Le)]   # dropped-out layer inputs
+        self.ctx = buf(B, d.C)
+        self.ctx_c = buf(B, d.C)
+        self.eps = buf(B, d.Z)
+        self.z, self.mu, self.logvar = buf(B, d.Z), buf(B, d.Z), buf(B, d.Z)
+        self.hid = buf(B, d.H2L)
+        self.dsc_logits = buf(B, max(d.OD, 1))
+        self.scalars = torch.zeros(_lib.HEADS_NSCALARS, **f32)
+        self.heads_ws = buf(self.lib.dvae_heads_ws_floats(B, d.S))
+        T1 = max(self.T1, 1)
+        self.x_dec = buf(T1, B, E)
+        self.d_gates = [buf(1, T1, B, 4 * H) for _ in range(d.Ld)]
+        self.d_cs = [buf(1, T1, B, H) for _ in range(d.Ld)]
+        self.d_hs = [buf(T1, B, H) for _ in range(d.Ld)]
+        self.d_xin = [None] + [buf(T1, B, H) for _ in range(1, d.Ld)]
+        self.state_ws = buf(self.lib.dvae_lstm_state_ws_floats(B, H, D))
+        self.lse, self.nll = buf(max(self.N, 1)), buf(max(self.N, 1))
+        self.argmax = torch.zeros(max(self.N, 1), device=device, dtype=torch.int32)
+        self.recon = torch.zeros(1, **f32)
+        self.ce_ws = buf(self.lib.dvae_vocab_ce_ws_floats(max(self.N, 1), d.V))
+        self._bwd_ready = False
+        self.seed_dev = torch.zeros(1, device=device, dtype=torch.int64)
+        self.labels = buf(max(sum(1 for o in d.dsc_out if o > 0), 1), B)
+        self._space_dims = int_array(d.space_dims)
+        self._dsc_out = int_array(d.dsc_out)
+        self.train_mode = False
+
+    # ------------------------------------------------------------------------------------------
+    def _alloc_bwd(self):
+        if self._bwd_ready:
+            return
+        d, B, T, T1 = self.d, self.B, self.T, max(self.T1, 1)
+        f32 = dict(device=self.device, dtype=torch.float32)
+        w = max(d.E, d.H * d.D)
+        self.g_top = torch.empty(T1, B, d.H, **f32)
+        self.g_dx = [torch.empty(max(T, T1), B, w, **f32) for _ in range(2)]
+        self.g_hid = torch.empty(B, d.H2L, **f32)
+        self.g_ctx = torch.empty(B, d.C, **f32)
+        self.heads_bwd_ws = torch.empty(self.lib.dvae_heads_bwd_ws_floats(B, d.Z, d.H2L), **f32)
+        self.ce_bwd_ws = torch.empty(self.lib.dvae_vocab_ce_bwd_ws_floats(max(self.N, 1), d.V), **f32)
+        self._bwd_ready = True
+
+    @staticmethod
+    def _enc_w(P, l, dirs):
+        sfx = [f"_l{l}" + ("_reverse" if k else "") for k in range(dirs)]
+        return tuple([P[f"encoder.recurrent.{n}{s}"] for s in sfx] for n in ("weight_ih", "weight_hh", "bias_ih", "bias_hh"))
+
+    @staticmethod
+    def _dec_w(P, l):
+        return tuple([P[f"decoder.recurrent.{n}_l{l}"]] for n in ("weight_ih", "weight_hh", "bias_ih", "bias_hh"))
+
+    # ------------------------------------------------------------------------------------------
+    # forward pieces.  P: dict name -> parameter tensor (reference state_dict names + fused groups)
+    # ------------------------------------------------------------------------------------------
+    def encode(self, P, inputs, lengths, train):
+        """a1 + a2 (vae/model.py:88-101,373-382): inputs [B,T] int64 (row stride = inputs.stride(0))."""
+        lib, d, st = self.lib, self.d, _lib.stream_ptr()
+        B, T = self.B, self.T
+        p = d.p_enc if train else 0.0
+        check(lib.dvae_embedding_fwd(ptr(P["encoder.embedding.weight"]), d.E, ptr(inputs), inputs.stride(0),
+                                     inputs.stride(1), T, B, p, ptr(self.seed_dev), SALT_ENC_EMB, -1,
+                                     ptr(self.x_enc), st), "dvae_embedding_fwd")
+        x, I = self.x_enc, d.E
+        for l in range(d.Le):
+            if l > 0:
+                I = d.D * d.H
+                if p > 0.0:
+                    check(lib.dvae_dropout(ptr(self.e_hs[l - 1]), I, T * B, I, p, ptr(self.seed_dev),
+                                           SALT_ENC_LAYER + l, ptr(self.e_xin[l]), I, st), "dvae_dropout")
+                    x = self.e_xin[l]
+                else:
+                    x = self.e_hs[l - 1]
+            w_ih, w_hh, b_ih, b_hh = self._enc_w(P, l, d.D)
+            off = l * d.D * d.H
+            check(lib.dvae_lstm_seq_fwd(ptr(x), I, T, B, I, d.H, d.D, ptr_array(w_ih), ptr_array(w_hh),
+                                        ptr_array(b_ih), ptr_array(b_hh), None, None, 0, 0, ptr(lengths),
+                                        ptr(self.e_hs[l]), d.D * d.H, self.ctx.data_ptr() + 4 * off,
+                                        self.ctx_c.data_ptr() + 4 * off, d.C, d.H, ptr(self.e_gates[l]),
+                                        ptr(self.e_cs[l]), ptr(self.state_ws), st), "dvae_lstm_seq_fwd(enc)")
+        self._enc_p = p
+        return self.ctx
+
+    def heads(self, P, ctx, eps, labels, kl_w):
+        """a3 + a4 + a5 + a8 fused.  labels: packed [n_dsc,B] float tensor or None; kl_w: [S] or None."""
+        lib, d, st = self.lib, self.d, _lib.stream_ptr()
+        check(lib.dvae_latent_heads_fwd(ptr(ctx), self.B, d.C, d.S, self._space_dims, self._dsc_out,
+                                        ptr(P["_c2p.weight"]), ptr(P["_c2p.bias"]), ptr(eps),
+                                        ptr(P.get("_dsc.weight")), ptr(P.get("_dsc.bias")), ptr(labels), ptr(kl_w),
+                                        ptr(P["z2hidden.weight"]), ptr(P["z2hidden.bias"]), d.H2L, ptr(self.z),
+                                        ptr(self.mu), ptr(self.logvar), ptr(self.hid), ptr(self.dsc_logits),
+                                        ptr(self.scalars), ptr(self.heads_ws), st), "dvae_latent_heads_fwd")
+
+    def decode_forced(self, P, tokens, first_token, train, hid=None):
+        """a6 under teacher forcing: `tokens` [B,>=T1] supplies the decoder input at step t (t>=1 when
+        first_token >= 0 overrides step 0 with <SOS>)."""
+        lib, d, st = self.lib, self.d, _lib.stream_ptr()
+        B, T1 = self.B, self.T1
+        hid = self.hid if hid is None else hid
+        p = d.p_dec if train else 0.0
+        check(lib.dvae_embedding_fwd(ptr(P["decoder.embedding.weight"]), d.E, ptr(tokens), tokens.stride(0),
+                                     tokens.stride(1), T1, B, p, ptr(self.seed_dev), SALT_DEC_EMB, first_token,
+                                     ptr(self.x_dec), st), "dvae_embedding_fwd")
+        x, I = self.x_dec, d.E
+        for l in range(d.Ld):
+            if l > 0:
+                I = d.H
+                if p > 0.0:
+                    check(lib.dvae_dropout(ptr(self.d_hs[l - 1]), I, T1 * B, I, p, ptr(self.seed_dev),
+                                           SALT_DEC_LAYER + l, ptr(self.d_xin[l]), I, st), "dvae_dropout")
+                    x = self.d_xin[l]
+                else:
+                    x = self.d_hs[l - 1]
+            w_ih, w_hh, b_ih, b_hh = self._dec_w(P, l)
+            check(lib.dvae_lstm_seq_fwd(ptr(x), I, T1, B, I, d.H, 1, ptr_array(w_ih), ptr_array(w_hh),
+                                        ptr_array(b_ih), ptr_array(b_hh), hid.data_ptr() + 4 * l * d.H,
+                                        hid.data_ptr() + 4 * (d.Ld + l) * d.H, d.H2L, 0, None, ptr(self.d_hs[l]),
+                                        d.H, None, None, 0, 0, ptr(self.d_gates[l]), ptr(self.d_cs[l]),
+                                        ptr(self.state_ws), st), "dvae_lstm_seq_fwd(dec)")
+        self._dec_p = p
+        self._dec_tokens, self._dec_first = tokens, first_token
+        self._dec_hid = hid
+        return self.d_hs[-1]
+
+    def vocab_ce(self, P, h_top, targets, lengths):
+        """a7 fused with the vocabulary projection of a6."""
+        lib, d, st = self.lib, self.d, _lib.stream_ptr()
+        check(lib.dvae_vocab_ce_fwd(ptr(h_top), d.H, self.T1, self.B, d.H, d.V, ptr(P["decoder.linear.weight"]),
+                                    ptr(P["decoder.linear.bias"]), ptr(targets), targets.stride(0), ptr(lengths),
+                                    d.sos, ptr(self.lse), ptr(self.nll), ptr(self.argmax), ptr(self.recon),
+                                    ptr(self.ce_ws), st), "dvae_vocab_ce_fwd")
+        return self.recon
+
+    # ------------------------------------------------------------------------------------------
+    # backward pieces.  G: dict name -> gradient tensor to WRITE (same names as P)
+    # ------------------------------------------------------------------------------------------
+    def vocab_ce_bwd(self, P, G, h_top, targets, lengths, grad_scale_dev):
+        self._alloc_bwd()
+        lib, d, st = self.lib, self.d, _lib.stream_ptr()
+        check(lib.dvae_vocab_ce_bwd(ptr(h_top), d.H, self.T1, self.B, d.H, d.V, ptr(P["decoder.linear.weight"]),
+                                    ptr(P["decoder.linear.bias"]), ptr(targets), targets.stride(0), ptr(lengths),
+                                    ptr(self.lse), ptr(grad_scale_dev), ptr(self.g_top), d.H,
+                                    ptr(G["decoder.linear.weight"]), ptr(G["decoder.linear.bias"]),
+                                    ptr(self.ce_bwd_ws), st), "dvae_vocab_ce_bwd")
+        return self.g_top
+
+    def decode_bwd(self, P, G, g_top, emb_grad=True):
+        """BPTT through the decoder stack; leaves d(hid) in self.g_hid."""
+        self._alloc_bwd()
+        lib, d, st = self.lib, self.d, _lib.stream_ptr()
+        B, T1 = self.B, self.T1
+        hid = self._dec_hid
+        g_in, p = g_top, self._dec_p
+        for l in range(d.Ld - 1, -1, -1):
+            I = d.E if l == 0 else d.H
+            x = self.x_dec if l == 0 else (self.d_xin[l] if p > 0.0 else self.d_hs[l - 1])
+            g_out = self.g_dx[l % 2]
+            w_ih, w_hh, _, _ = self._dec_w(P, l)
+            gw_ih, gw_hh, gb_ih, gb_hh = self._dec_w(G, l)
+            need_dx = l > 0 or emb_grad
+            check(lib.dvae_lstm_seq_bwd(ptr(x), I, T1, B, I, d.H, 1, ptr_array(w_ih), ptr_array(w_hh),
+                                        hid.data_ptr() + 4 * l * d.H, hid.data_ptr() + 4 * (d.Ld + l) * d.H,
+                                        d.H2L, 0, None, ptr(self.d_hs[l]), d.H, ptr(self.d_gates[l]),
+                                        ptr(self.d_cs[l]), ptr(g_in), d.H, None, None, 0, 0,
+                                        ptr(g_out) if need_dx else None, I, ptr_array(gw_ih), ptr_array(gw_hh),
+                                        ptr_array(gb_ih), ptr_array(gb_hh), self.g_hid.data_ptr() + 4 * l * d.H,
+                                        self.g_hid.data_ptr() + 4 * (d.Ld + l) * d.H, d.H2L, 0,
+                                        ptr(self.state_ws), st), "dvae_lstm_seq_bwd(dec)")
+            if l > 0 and p > 0.0:
+                check(lib.dvae_dropout(ptr(g_out), I, T1 * B, I, p, ptr(self.seed_dev), SALT_DEC_LAYER + l,
+                                       ptr(g_out), I, st), "dvae_dropout(bwd)")
+            g_in = g_out
+        if emb_grad:
+            tok = self._dec_tokens
+            check(lib.dvae_embedding_bwd(ptr(g_in), d.E, ptr(tok), tok.stride(0), tok.stride(1), T1, B, p,
+                                         ptr(self.seed_dev), SALT_DEC_EMB, self._dec_first,
+                                         ptr(G["decoder.embedding.weight"]), st), "dvae_embedding_bwd")
+        return self.g_hid
+
+    def heads_bwd(self, P, G, ctx, eps, labels, kl_w, g_hid, g_z=None, g_mu=None, g_logvar=None, g_logits=None):
+        self._alloc_bwd()
+        lib, d, st = self.lib, self.d, _lib.stream_ptr()
+        check(lib.dvae_latent_heads_bwd(ptr(ctx), self.B, d.C, d.S, self._space_dims, self._dsc_out,
+                                        ptr(P["_c2p.weight"]), ptr(eps), ptr(P.get("_dsc.weight")), ptr(labels),
+                                        ptr(kl_w), ptr(P["z2hidden.weight"]), d.H2L, ptr(self.z), ptr(self.mu),
+                                        ptr(self.logvar), ptr(self.hid), ptr(self.dsc_logits), ptr(g_hid),
+                                        ptr(g_z), ptr(g_mu), ptr(g_logvar), ptr(g_logits), ptr(G["_c2p.weight"]),
+                                        ptr(G["_c2p.bias"]), ptr(G.get("_dsc.weight")), ptr(G.get("_dsc.bias")),
+                                        ptr(G["z2hidden.weight"]), ptr(G["z2hidden.bias"]), ptr(self.g_ctx),
+                                        ptr(self.heads_bwd_ws), st), "dvae_latent_heads_bwd")
+        return self.g_ctx
+
+    def encode_bwd(self, P, G, inputs, lengths, g_ctx, emb_grad=True):
+        self._alloc_bwd()
+        lib, d, st = self.lib, self.d, _lib.stream_ptr()
+        B, T = self.B, self.T
+        p = self._enc_p
+        g_in = None
+        for l in range(d.Le - 1, -1, -1):
+            I = d.E if l == 0 else d.D * d.H
+            x = self.x_enc if l == 0 else (self.e_xin[l] if p > 0.0 else self.e_hs[l - 1])
+            g_out = self.g_dx[l % 2]
+            w_ih, w_hh, _, _ = self._enc_w(P, l, d.D)
+            gw_ih, gw_hh, gb_ih, gb_hh = self._enc_w(G, l, d.D)
+            need_dx = l > 0 or emb_grad
+            off = l * d.D * d.H
+            check(lib.dvae_lstm_seq_bwd(ptr(x), I, T, B, I, d.H, d.D, ptr_array(w_ih), ptr_array(w_hh), None, None,
+                                        0, 0, ptr(lengths), ptr(self.e_hs[l]), d.D * d.H, ptr(self.e_gates[l]),
+                                        ptr(self.e_cs[l]), ptr(g_in), d.D * d.H, g_ctx.data_ptr() + 4 * off, None,
+                                        d.C, d.H, ptr(g_out) if need_dx else None, I, ptr_array(gw_ih),
+                                        ptr_array(gw_hh), ptr_array(gb_ih), ptr_array(gb_hh), None, None, 0, 0,
+                                        ptr(self.state_ws), st), "dvae_lstm_seq_bwd(enc)")
+            if l > 0 and p > 0.0:
+                check(lib.dvae_dropout(ptr(g_out), I, T * B, I, p, ptr(self.seed_dev), SALT_ENC_LAYER + l,
+                                       ptr(g_out), I, st), "dvae_dropout(bwd)")
+            g_in = g_out
+        if emb_grad:
+            check(lib.dvae_embedding_bwd(ptr(g_in), d.E, ptr(inputs), inputs.stride(0), inputs.stride(1), T, B, p,
+                                         ptr(self.seed_dev), SALT_ENC_EMB, -1, ptr(G["encoder.embedding.weight"]),
+                                         st), "dvae_embedding_bwd")
+
+    def randn_eps(self):
+        check(self.lib.dvae_randn(ptr(self.eps), self.eps.numel(), ptr(self.seed_dev), SALT_EPS, _lib.stream_ptr()),
+              "dvae_randn")
+        return self.eps

@@ -1,0 +1,225 @@
+/*
+ * dvae_b200.h -- C ABI of the B200-native disentangled sentence-VAE hot path.
+ *
+ * The reference (jvasilakes/disentanglement-vae) is pure Python and has no FFI: its de-facto
+ * plugin boundary is `vae.model.build_vae()` (vae/model.py:515-559) plus the `vae.losses` free
+ * functions (vae/losses.py:137-242).  The Python package `disentanglement-vae_b200/` mirrors that
+ * surface and lowers every tensor op on the path to the entry points below, bound with ctypes
+ * (see INTEGRATION.md for the stub).  Each entry point cites the reference code it replaces.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in `_host`;
+ *   - all real data is float32, token ids / lengths are int64 (as in the reference);
+ *   - matrices are row-major with an explicit row stride (`ld*`, in elements);
+ *   - sequence buffers are TIME-MAJOR: [T][B][width];
+ *   - no allocation, no ownership transfer, no synchronisation: kernels are enqueued on `stream`
+ *     (a cudaStream_t) and the call returns; buffers (incl. workspaces) are caller-allocated;
+ *   - per-step scalars that change between replays of a captured CUDA graph (dropout seed, KL
+ *     weights, Adam step/lr) are read from device memory, never baked into launch arguments;
+ *   - return value: 0 on success, negative `DVAE_E*` otherwise (`dvae_last_error_string()`
+ *     describes the last failure on the calling thread).  There is no CPU fallback.
+ */
+#ifndef DVAE_B200_H_
+#define DVAE_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DVAE_OK 0
+#define DVAE_EINVAL (-1)   /* bad argument (null pointer, non-positive size, unsupported shape) */
+#define DVAE_ECUDA (-2)    /* a CUDA runtime call or kernel launch failed                        */
+#define DVAE_EWORKSPACE (-3) /* caller-provided workspace too small                              */
+
+#define DVAE_MAX_SPACES 8  /* latent spaces per model (labels + "content")                        */
+
+const char* dvae_last_error_string(void);
+int dvae_version(void);
+/* Number of kernels this library has launched in the calling process (for bench.py's
+ * `gpu_launches`). */
+int64_t dvae_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Dense layer: C[M,N] = act(A . B^T + bias + bias2) + beta * C          (fp32 SIMT GEMM)
+ * Replaces nn.Linear / torch.mm call sites on the path (vae/model.py:164,196,388,403 and the
+ * input projections inside nn.LSTM, vae/model.py:95,158) and their autograd transposes.
+ *   trans_a == 0: A is [M,K] row-major (row stride lda);  trans_a == 1: A is stored [K,M].
+ *   trans_b == 0: B is [N,K] row-major (an nn.Linear weight); trans_b == 1: B is stored [K,N].
+ *   bias, bias2: [N] or NULL.  act: 0 none, 1 tanh.  beta: 0 overwrites C, 1 accumulates.
+ * ------------------------------------------------------------------------------------------- */
+int dvae_linear(const float* A, int64_t lda, int trans_a, const float* B, int64_t ldb, int trans_b,
+                float* C, int64_t ldc, int M, int N, int K, const float* bias, const float* bias2,
+                float beta, int act, void* stream);
+
+/* out[n] = sum_m X[m, n] (+ out[n] if beta == 1); X is [M,N] row-major with row stride ldx. */
+int dvae_colsum(const float* X, int64_t ldx, int M, int N, float* out, float beta, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Embedding lookup + element-wise dropout (vae/model.py:90,153):
+ *   x[t][b][:] = emb[tokens[b*tok_stride_b + t*tok_stride_t]][:] * mask(t,b,:) / (1-p)
+ * mask is a counter-based Philox4x32-10 Bernoulli(1-p) keyed by (*seed_dev, salt, element index);
+ * p == 0 (or seed_dev == NULL) disables it.  `dvae_dropout` applies the same kind of mask to a
+ * dense [rows, width] activation (the nn.LSTM inter-layer dropout, vae/model.py:74-77,137-140).
+ * `dvae_embedding_bwd` scatter-ADDS d_x (masked the same way) into d_emb [V, E].
+ * first_token >= 0 replaces the token at t == 0 for every row (the decoder is always fed <SOS>
+ * first, vae/model.py:445-447, then inputs[:, t] under teacher forcing, model.py:464-466).
+ * `dvae_randn` fills out[n] with N(0,1) draws (Philox + Box-Muller): the reparameterisation
+ * noise of vae/model.py:392-395 when the caller does not supply it.
+ * ------------------------------------------------------------------------------------------- */
+int dvae_randn(float* out, int64_t n, const uint64_t* seed_dev, uint32_t salt, void* stream);
+int dvae_embedding_fwd(const float* emb, int E, const int64_t* tokens, int64_t tok_stride_b,
+                       int64_t tok_stride_t, int T, int B, float p, const uint64_t* seed_dev,
+                       uint32_t salt, int64_t first_token, float* x, void* stream);
+int dvae_embedding_bwd(const float* d_x, int E, const int64_t* tokens, int64_t tok_stride_b,
+                       int64_t tok_stride_t, int T, int B, float p, const uint64_t* seed_dev,
+                       uint32_t salt, int64_t first_token, float* d_emb, void* stream);
+int dvae_dropout(const float* x, int64_t ldx, int64_t rows, int width, float p,
+                 const uint64_t* seed_dev, uint32_t salt, float* y, int64_t ldy, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * One LSTM layer (1 or 2 directions) over a padded, time-major batch.  Replaces nn.LSTM inside
+ * VariationalEncoder.forward (vae/model.py:88-101, incl. pack/pad = per-row length masking) and
+ * the T-1 single-step calls of VariationalDecoder.forward (vae/model.py:152-165,457-460) when the
+ * decoder inputs are known (teacher forcing).  Gate order i,f,g,o (PyTorch).
+ *
+ *   x        [T,B,I] (row stride ldx) -- already embedded / dropped out
+ *   w_ih[d]  [4H,I], w_hh[d] [4H,H], b_ih[d], b_hh[d] [4H]   (d = 0 forward, 1 reverse)
+ *   h0, c0   [D][B] rows of H with row stride ld0 and direction stride dir0, or NULL (zeros)
+ *   lengths  [B] int64 or NULL (every row runs all T steps, as the decoder does, model.py:448)
+ *   hs       [T,B,D*H] (row stride ldhs; direction d occupies columns [d*H,(d+1)*H)); rows with
+ *            t >= lengths[b] are written as zeros (pad_packed_sequence)
+ *   hn, cn   final state of each row's own traversal, [D][B] rows with stride ldn / dirn; NULL ok
+ *   gates    [D,T,B,4H] post-activation gates, cs [D,T,B,H] cell states: saved for backward.
+ *            `gates` doubles as the pre-activation workspace.
+ *   state_ws scratch of dvae_lstm_state_ws_floats(B,H,D) floats (carried h/c ping-pong)
+ * ------------------------------------------------------------------------------------------- */
+int64_t dvae_lstm_state_ws_floats(int B, int H, int D);
+int dvae_lstm_seq_fwd(const float* x, int64_t ldx, int T, int B, int I, int H, int D,
+                      const float* const* w_ih_host, const float* const* w_hh_host,
+                      const float* const* b_ih_host, const float* const* b_hh_host,
+                      const float* h0, const float* c0, int64_t ld0, int64_t dir0,
+                      const int64_t* lengths, float* hs, int64_t ldhs, float* hn, float* cn,
+                      int64_t ldn, int64_t dirn, float* gates, float* cs, float* state_ws,
+                      void* stream);
+
+/* Back-propagation through time for dvae_lstm_seq_fwd (the autograd of nn.LSTM).
+ *   d_hs [T,B,D*H] (row stride lddhs) or NULL; d_hn, d_cn as hn/cn or NULL.
+ *   gates is OVERWRITTEN with the pre-activation gradients dG [D,T,B,4H].
+ *   Outputs (overwritten): d_x [T,B,I] (sum over directions; NULL to skip), d_w_ih[d], d_w_hh[d],
+ *   d_b_ih[d], d_b_hh[d], d_h0/d_c0 (layout of h0/c0; NULL to skip). */
+int dvae_lstm_seq_bwd(const float* x, int64_t ldx, int T, int B, int I, int H, int D,
+                      const float* const* w_ih_host, const float* const* w_hh_host,
+                      const float* h0, const float* c0, int64_t ld0, int64_t dir0,
+                      const int64_t* lengths, const float* hs, int64_t ldhs, float* gates,
+                      const float* cs, const float* d_hs, int64_t lddhs, const float* d_hn,
+                      const float* d_cn, int64_t ldn, int64_t dirn, float* d_x, int64_t lddx,
+                      float* const* d_w_ih_host, float* const* d_w_hh_host,
+                      float* const* d_b_ih_host, float* const* d_b_hh_host, float* d_h0,
+                      float* d_c0, int64_t ldd0, int64_t dird0, float* state_ws, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Fused latent heads.  Replaces compute_latent_params (vae/model.py:384-398), the
+ * discriminators' forward / loss / accuracy (vae/model.py:195-216, vae/losses.py:180-196),
+ * kl_divergence + compute_kl_divergence_losses (vae/losses.py:153-177) and compute_hidden
+ * (vae/model.py:400-411) in ONE kernel.
+ *
+ *   ctx [B,C]; w_c2p [2Z,C] = the context2params weights concatenated in space order, each space
+ *   contributing rows [mu(zs); raw(zs)]; b_c2p [2Z]; eps [B,Z] (N(0,1) draws, space-concatenated);
+ *   space_dims_host[S]; w_dsc / b_dsc: discriminator weights concatenated over the spaces that
+ *   have one (dsc_out_host[s] = output dim, 0 = none): rows [out_s, zs]; labels [ND_total? no: one
+ *   float per (dsc, b)] laid out [n_dsc][B] (class index as float for multi-class heads), NULL in
+ *   inference; kl_w_dev [S] KL weights (lambda or the cyclic value, vae/losses.py:143-150);
+ *   w_z2h [2*H*Ld, Z], b_z2h.
+ * Outputs: z, mu, logvar [B,Z]; hid [B,2*H*Ld] = tanh(z2hidden(z)) -- decoder layer l takes
+ *   h0 = hid[:, l*H:(l+1)*H], c0 = hid[:, (Ld+l)*H:(Ld+l+1)*H] (row stride 2*H*Ld);
+ *   dsc_logits [B, sum(out)]; scalars[ ] (device, DVAE_HEADS_NSCALARS floats):
+ *   [0] total_weighted_kl, [1] total_kl, [2] total_dsc_loss, [3..3+S) kl per space,
+ *   [3+S..3+2S) dsc loss per space (0 where none), [3+2S..3+3S) dsc accuracy per space.
+ *   ws: dvae_heads_ws_floats(B,S) floats of scratch (zeroed by the call).
+ * ------------------------------------------------------------------------------------------- */
+#define DVAE_HEADS_NSCALARS (3 + 3 * DVAE_MAX_SPACES)
+int64_t dvae_heads_ws_floats(int B, int S);
+int dvae_latent_heads_fwd(const float* ctx, int B, int C, int S, const int* space_dims_host,
+                          const int* dsc_out_host, const float* w_c2p, const float* b_c2p,
+                          const float* eps, const float* w_dsc, const float* b_dsc,
+                          const float* labels, const float* kl_w_dev, const float* w_z2h,
+                          const float* b_z2h, int H2L, float* z, float* mu, float* logvar,
+                          float* hid, float* dsc_logits, float* scalars, float* ws, void* stream);
+
+/* Backward of the fused heads w.r.t. total = weighted KL + dsc losses + (decoder path via d_hid).
+ *   d_hid [B,H2L] gradient w.r.t. `hid`;  d_z_extra / d_mu_extra / d_logvar_extra [B,Z] and
+ *   d_logits_extra [B,sum(out)]: optional upstream gradients on the returned tensors (NULL ok) --
+ *   how the adversarial / MI objectives (vae/losses.py:199-242) and losses computed outside the
+ *   fused kernel reach the encoder.
+ *   Outputs (overwritten): d_w_c2p, d_b_c2p, d_w_dsc, d_b_dsc, d_w_z2h, d_b_z2h, d_ctx [B,C].
+ *   ws: dvae_heads_bwd_ws_floats(B,Z,H2L) floats. */
+int64_t dvae_heads_bwd_ws_floats(int B, int Z, int H2L);
+int dvae_latent_heads_bwd(const float* ctx, int B, int C, int S, const int* space_dims_host,
+                          const int* dsc_out_host, const float* w_c2p, const float* eps,
+                          const float* w_dsc, const float* labels, const float* kl_w_dev,
+                          const float* w_z2h, int H2L, const float* z, const float* mu,
+                          const float* logvar, const float* hid, const float* dsc_logits,
+                          const float* d_hid, const float* d_z_extra, const float* d_mu_extra,
+                          const float* d_logvar_extra, const float* d_logits_extra, float* d_w_c2p,
+                          float* d_b_c2p, float* d_w_dsc, float* d_b_dsc, float* d_w_z2h,
+                          float* d_b_z2h, float* d_ctx, float* ws, void* stream);
+
+/* Discriminator loss on its own (Discriminator.compute_loss / compute_accuracy,
+ * vae/model.py:199-216; vae/losses.py:180-196) for callers that did not pass labels to the fused
+ * forward: out[s] = loss, out[S+s] = accuracy (NULL to skip); when d_logits != NULL it receives
+ * d_out[s] * d(loss_s)/d(logits). */
+int dvae_dsc_loss(const float* dsc_logits, const float* labels, int B, int S,
+                  const int* space_dims_host, const int* dsc_out_host, float* out,
+                  const float* d_out, float* d_logits, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Fused vocabulary projection + online log-softmax + masked NLL.  Replaces the per-step
+ * decoder.linear (vae/model.py:164,462), the [B,T,V] `out_logits` buffer (model.py:452-454) and
+ * reconstruction_loss -> texar sequence_sparse_softmax_cross_entropy (vae/losses.py:137-140).
+ * The logits are never written to memory.
+ *
+ *   h [N,H] time-major decoder outputs, N = T1*B, row n = (t-1)*B + b covers target position t
+ *   (t = 1..T1); w [V,H], bias [V]; targets [B, *] int64 with strides (tgt_stride_b, 1);
+ *   lengths [B] int64; sos = <SOS> id.
+ * Outputs: lse [N]; nll [N] (unmasked); argmax [N] int32 (token-level reconstruction argmax);
+ *   loss[0] = (1/B) * sum_b ( nll0_b + sum_{1<=t<len_b} nll[b,t] ) where nll0_b is the constant
+ *   contribution of the one-hot pseudo-logit row at t = 0 (model.py:454):
+ *   log(e + V - 1) - [targets[b,0] == sos].
+ *   ws: dvae_vocab_ce_ws_floats(N, V) floats.
+ * ------------------------------------------------------------------------------------------- */
+int64_t dvae_vocab_ce_ws_floats(int N, int V);
+int dvae_vocab_ce_fwd(const float* h, int64_t ldh, int T1, int B, int H, int V, const float* w,
+                      const float* bias, const int64_t* targets, int64_t tgt_stride_b,
+                      const int64_t* lengths, int sos, float* lse, float* nll, int32_t* argmax,
+                      float* loss, float* ws, void* stream);
+
+/* Backward: d_h [N,H], d_w [V,H], d_bias [V] (all overwritten) for d(loss) = grad_scale_dev[0]
+ * (NULL = 1).  Softmax tiles are recomputed from h, w and the saved lse.
+ *   ws: dvae_vocab_ce_bwd_ws_floats(N, V) floats. */
+int64_t dvae_vocab_ce_bwd_ws_floats(int N, int V);
+int dvae_vocab_ce_bwd(const float* h, int64_t ldh, int T1, int B, int H, int V, const float* w,
+                      const float* bias, const int64_t* targets, int64_t tgt_stride_b,
+                      const int64_t* lengths, const float* lse, const float* grad_scale_dev,
+                      float* d_h, int64_t lddh, float* d_w, float* d_bias, float* ws,
+                      void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Train-step tail: clip_grad_norm_(5.0) + Adam + zero_grad (run.py:255,261-262) over ONE flat
+ * parameter buffer.
+ *   dvae_grad_sumsq: sumsq[0] = sum(g^2) (deterministic two-stage reduction; ws >= 1024 floats+1)
+ *   dvae_clip_adam : coef = min(1, max_norm / (sqrt(sumsq) + 1e-6)); g *= coef * grad_scale;
+ *                    torch.optim.Adam update with hyper[0]=lr, hyper[1]=beta1, hyper[2]=beta2,
+ *                    hyper[3]=eps, hyper[4]=step (1-based, as float), all read from DEVICE memory;
+ *                    g is zeroed afterwards when zero_grad != 0.
+ * ------------------------------------------------------------------------------------------- */
+int dvae_grad_sumsq(const float* g, int64_t n, float* sumsq, float* ws, void* stream);
+int dvae_clip_adam(float* p, float* g, float* m, float* v, int64_t n, const float* sumsq,
+                   float max_norm, float grad_scale, const float* hyper_dev, int zero_grad,
+                   void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DVAE_B200_H_ */

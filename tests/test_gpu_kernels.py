@@ -1,0 +1,388 @@
+"""Kernel-level parity: every C-ABI entry point against the numpy oracle on seeded inputs.
+
+Tolerances (BASELINE.json north_star): fp32 forward within 1e-5 relative, gradients within 1e-3
+relative; integer outputs (argmax) identical.  The oracle is evaluated in float64.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import dvae_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def lib(dvae):
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return dvae._lib.load()
+
+
+@pytest.fixture(scope="module")
+def L(dvae):
+    return dvae._lib
+
+
+def dev(x, dtype=torch.float32):
+    return torch.as_tensor(np.ascontiguousarray(x)).to(device="cuda", dtype=dtype).contiguous()
+
+
+def rel(a, b):
+    a = a.detach().cpu().numpy().astype(np.float64) if torch.is_tensor(a) else np.asarray(a, np.float64)
+    b = np.asarray(b, np.float64)
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-30)
+
+
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("M,N,K", [(5, 7, 3), (64, 64, 16), (130, 257, 100), (300, 1024, 256), (2560, 1024, 256), (17, 40, 1030)])
+@pytest.mark.parametrize("ta,tb", [(0, 0), (0, 1), (1, 1), (1, 0)])
+def test_linear(lib, L, M, N, K, ta, tb):
+    rng = np.random.default_rng(M * 7 + N * 3 + K + ta * 2 + tb)
+    A = rng.standard_normal((M, K)).astype(np.float32)
+    Bm = rng.standard_normal((N, K)).astype(np.float32)
+    bias = rng.standard_normal(N).astype(np.float32)
+    C0 = rng.standard_normal((M, N)).astype(np.float32)
+    a_d = dev(A.T if ta else A)
+    b_d = dev(Bm.T if tb else Bm)
+    c_d = dev(C0)
+    st = L.stream_ptr()
+    L.check(lib.dvae_linear(L.ptr(a_d), a_d.stride(0), ta, L.ptr(b_d), b_d.stride(0), tb, L.ptr(c_d), N, M, N, K,
+                            L.ptr(dev(bias)), None, 1.0, 0, st), "linear")
+    want = A.astype(np.float64) @ Bm.astype(np.float64).T + bias + C0
+    assert rel(c_d, want) < 2e-6
+    L.check(lib.dvae_linear(L.ptr(a_d), a_d.stride(0), ta, L.ptr(b_d), b_d.stride(0), tb, L.ptr(c_d), N, M, N, K,
+                            L.ptr(dev(bias)), L.ptr(dev(bias)), 0.0, 1, st), "linear")
+    want = np.tanh(A.astype(np.float64) @ Bm.astype(np.float64).T + 2 * bias)
+    assert np.abs(c_d.cpu().numpy() - want).max() < 2e-6
+
+
+def test_linear_strided_output_and_colsum(lib, L):
+    rng = np.random.default_rng(0)
+    A = rng.standard_normal((70, 33)).astype(np.float32)
+    Bm = rng.standard_normal((20, 33)).astype(np.float32)
+    big = torch.zeros(70, 50, device="cuda")
+    L.check(lib.dvae_linear(L.ptr(dev(A)), 33, 0, L.ptr(dev(Bm)), 33, 0, big.data_ptr() + 4 * 10, 50, 70, 20, 33,
+                            None, None, 0.0, 0, L.stream_ptr()), "linear")
+    assert rel(big[:, 10:30], A.astype(np.float64) @ Bm.T) < 2e-6
+    assert float(big[:, :10].abs().max()) == 0 and float(big[:, 30:].abs().max()) == 0
+    out = torch.zeros(20, device="cuda")
+    L.check(lib.dvae_colsum(big.data_ptr() + 40, 50, 70, 20, L.ptr(out), 0.0, L.stream_ptr()), "colsum")
+    assert rel(out, (A.astype(np.float64) @ Bm.T).sum(0)) < 2e-6
+
+
+def test_linear_rejects_bad_arguments(lib, L):
+    rc = lib.dvae_linear(None, 1, 0, None, 1, 0, None, 1, 1, 1, 1, None, None, 0.0, 0, None)
+    assert rc == -1 and b"null" in lib.dvae_last_error_string()
+    x = torch.zeros(4, device="cuda")
+    rc = lib.dvae_linear(L.ptr(x), 1, 0, L.ptr(x), 1, 0, L.ptr(x), 1, 0, 1, 1, None, None, 0.0, 0, None)
+    assert rc == -1
+
+
+# ---------------------------------------------------------------------------------------------
+def _lstm_case(lib, L, T, B, I, H, D, with_len, with_h0, seed):
+    rng = np.random.default_rng(seed)
+    x = rng.standard_normal((T, B, I)).astype(np.float32)
+    k = 1.0 / np.sqrt(H)
+    W = [dict(w_ih=rng.uniform(-k, k, (4 * H, I)).astype(np.float32), w_hh=rng.uniform(-k, k, (4 * H, H)).astype(np.float32),
+              b_ih=rng.uniform(-k, k, 4 * H).astype(np.float32), b_hh=rng.uniform(-k, k, 4 * H).astype(np.float32))
+         for _ in range(D)]
+    lengths = None
+    if with_len:
+        lengths = rng.integers(1, T + 1, B)
+        lengths[0] = T
+    h0 = c0 = None
+    if with_h0:
+        h0 = rng.standard_normal((D, B, H)).astype(np.float32) * 0.5
+        c0 = rng.standard_normal((D, B, H)).astype(np.float32) * 0.5
+    d_hs = rng.standard_normal((T, B, D * H)).astype(np.float32)
+    d_hn = rng.standard_normal((D, B, H)).astype(np.float32)
+    d_cn = rng.standard_normal((D, B, H)).astype(np.float32)
+    # oracle (float64)
+    want = []
+    for d in range(D):
+        w = {k_: v.astype(np.float64) for k_, v in W[d].items()}
+        z = np.zeros((B, H))
+        hs, hn, cn, cache = O.lstm_seq_fwd(x.astype(np.float64), w["w_ih"], w["w_hh"], w["b_ih"], w["b_hh"],
+                                           h0[d].astype(np.float64) if with_h0 else z,
+                                           c0[d].astype(np.float64) if with_h0 else z, lengths, reverse=(d == 1))
+        g = O.lstm_seq_bwd(cache, d_hs=d_hs[:, :, d * H:(d + 1) * H].astype(np.float64), d_hn=d_hn[d].astype(np.float64),
+                           d_cn=d_cn[d].astype(np.float64))
+        want.append((hs, hn, cn, g))
+    # device
+    st = L.stream_ptr()
+    xd = dev(x)
+    Wd = [{k_: dev(v) for k_, v in W[d].items()} for d in range(D)]
+    len_d = dev(lengths, torch.int64) if with_len else None
+    h0d, c0d = (dev(h0), dev(c0)) if with_h0 else (None, None)
+    hs = torch.full((T, B, D * H), 7.0, device="cuda")
+    hn = torch.zeros(D, B, H, device="cuda")
+    cn = torch.zeros(D, B, H, device="cuda")
+    gates = torch.zeros(D, T, B, 4 * H, device="cuda")
+    cs = torch.zeros(D, T, B, H, device="cuda")
+    ws = torch.zeros(lib.dvae_lstm_state_ws_floats(B, H, D), device="cuda")
+    pa = lambda key: L.ptr_array([Wd[d][key] for d in range(D)])
+    L.check(lib.dvae_lstm_seq_fwd(L.ptr(xd), I, T, B, I, H, D, pa("w_ih"), pa("w_hh"), pa("b_ih"), pa("b_hh"),
+                                  L.ptr(h0d), L.ptr(c0d), H, B * H, L.ptr(len_d), L.ptr(hs), D * H, L.ptr(hn), L.ptr(cn),
+                                  H, B * H, L.ptr(gates), L.ptr(cs), L.ptr(ws), st), "lstm fwd")
+    for d in range(D):
+        assert rel(hs[:, :, d * H:(d + 1) * H], want[d][0]) < 5e-6
+        assert rel(hn[d], want[d][1]) < 5e-6
+        assert rel(cn[d], want[d][2]) < 5e-6
+    # backward
+    G = [{k_: torch.full_like(v, 3.0) for k_, v in Wd[d].items()} for d in range(D)]
+    ga = lambda key: L.ptr_array([G[d][key] for d in range(D)])
+    d_x = torch.zeros(T, B, I, device="cuda")
+    d_h0 = torch.zeros(D, B, H, device="cuda")
+    d_c0 = torch.zeros(D, B, H, device="cuda")
+    L.check(lib.dvae_lstm_seq_bwd(L.ptr(xd), I, T, B, I, H, D, pa("w_ih"), pa("w_hh"), L.ptr(h0d), L.ptr(c0d), H, B * H,
+                                  L.ptr(len_d), L.ptr(hs), D * H, L.ptr(gates), L.ptr(cs), L.ptr(dev(d_hs)), D * H,
+                                  L.ptr(dev(d_hn)), L.ptr(dev(d_cn)), H, B * H, L.ptr(d_x), I, ga("w_ih"), ga("w_hh"),
+                                  ga("b_ih"), ga("b_hh"), L.ptr(d_h0) if with_h0 else None,
+                                  L.ptr(d_c0) if with_h0 else None, H, B * H, L.ptr(ws), st), "lstm bwd")
+    dx_want = sum(want[d][3]["dx"] for d in range(D))
+    assert rel(d_x, dx_want) < 1e-4
+    for d in range(D):
+        g = want[d][3]
+        assert rel(G[d]["w_ih"], g["dw_ih"]) < 1e-4
+        assert rel(G[d]["w_hh"], g["dw_hh"]) < 1e-4
+        assert rel(G[d]["b_ih"], g["db_ih"]) < 1e-4
+        assert rel(G[d]["b_hh"], g["db_hh"]) < 1e-4
+        if with_h0:
+            assert rel(d_h0[d], g["dh0"]) < 1e-4
+            assert rel(d_c0[d], g["dc0"]) < 1e-4
+
+
+@pytest.mark.parametrize("T,B,I,H,D,with_len,with_h0", [
+    (5, 3, 6, 8, 1, False, True),        # decoder-like: initial state given, all rows run all steps
+    (7, 5, 10, 16, 2, True, False),      # encoder-like: bidirectional, ragged lengths
+    (1, 4, 5, 4, 2, True, False),        # single step
+    (9, 33, 12, 20, 1, True, False),     # rows / units not multiples of the tile sizes
+    (22, 128, 64, 256, 2, True, False),  # cfg-2 hidden size
+    (6, 40, 256, 64, 1, False, True),
+    (4, 7, 7, 5, 2, True, False),        # widths not divisible by 4 (scalar load path)
+])
+def test_lstm_seq(lib, L, T, B, I, H, D, with_len, with_h0):
+    _lstm_case(lib, L, T, B, I, H, D, with_len, with_h0, seed=T * 31 + B)
+
+
+# ---------------------------------------------------------------------------------------------
+def _heads_oracle(ctx, Wc, bc, eps, dims, dsc_out, Wd, bd, labels, klw, Wz, bz, d_hid, B):
+    """float64 forward + backward of the fused heads, written directly from vae/model.py:384-411."""
+    out = {}
+    Z = sum(dims)
+    zcat, mus, lvs = [], [], []
+    off = 0
+    kls, dls, das, logits = [], [], [], []
+    woff = boff = 0
+    for s, zs in enumerate(dims):
+        p = ctx @ Wc[2 * off:2 * off + 2 * zs].T + bc[2 * off:2 * off + 2 * zs]
+        mu, lv = p[:, :zs], np.tanh(p[:, zs:])
+        z = mu + eps[:, off:off + zs] * np.exp(lv)
+        zcat.append(z); mus.append(mu); lvs.append(lv)
+        kls.append(O.kl_divergence(mu, lv))
+        if dsc_out[s] > 0:
+            o = dsc_out[s]
+            W = Wd[woff:woff + o * zs].reshape(o, zs)
+            lg = z @ W.T + bd[boff:boff + o]
+            logits.append(lg)
+            woff += o * zs; boff += o
+        off += zs
+    out["z"], out["mu"], out["logvar"] = (np.concatenate(v, 1) for v in (zcat, mus, lvs))
+    out["kl"] = np.array(kls)
+    out["hid"] = np.tanh(out["z"] @ Wz.T + bz)
+    out["logits"] = np.concatenate(logits, 1) if logits else np.zeros((B, 0))
+    return out
+
+
+@pytest.mark.parametrize("B,C,dims,dsc_out", [
+    (6, 32, [1, 2, 4], [1, 1, 0]),
+    (128, 1024, [1, 1, 62], [1, 1, 0]),
+    (9, 24, [2, 3], [3, 0]),
+    (5, 16, [4], [0]),
+])
+def test_latent_heads_forward(lib, L, B, C, dims, dsc_out):
+    rng = np.random.default_rng(B + C)
+    S, Z = len(dims), sum(dims)
+    H2L = 4 * 12
+    ctx = rng.standard_normal((B, C)).astype(np.float32) * 0.5
+    Wc = rng.uniform(-1, 1, (2 * Z, C)).astype(np.float32) / np.sqrt(C)
+    bc = rng.uniform(-0.1, 0.1, 2 * Z).astype(np.float32)
+    eps = rng.standard_normal((B, Z)).astype(np.float32)
+    n_w = sum(o * z for o, z in zip(dsc_out, dims))
+    OD = sum(dsc_out)
+    Wd = rng.uniform(-1, 1, max(n_w, 1)).astype(np.float32)
+    bd = rng.uniform(-1, 1, max(OD, 1)).astype(np.float32)
+    Wz = rng.uniform(-1, 1, (H2L, Z)).astype(np.float32) / np.sqrt(Z)
+    bz = rng.uniform(-0.1, 0.1, H2L).astype(np.float32)
+    nd = sum(1 for o in dsc_out if o > 0)
+    labels = np.zeros((max(nd, 1), B), np.float32)
+    i = 0
+    for o in dsc_out:
+        if o > 0:
+            labels[i] = rng.integers(0, max(o, 2), B)
+            i += 1
+    klw = rng.uniform(0, 1, S).astype(np.float32)
+    f64 = lambda a: a.astype(np.float64)
+    want = _heads_oracle(f64(ctx), f64(Wc), f64(bc), f64(eps), dims, dsc_out, f64(Wd), f64(bd), labels, klw, f64(Wz), f64(bz), None, B)
+    z, mu, lv = (torch.zeros(B, Z, device="cuda") for _ in range(3))
+    hid = torch.zeros(B, H2L, device="cuda")
+    lg = torch.zeros(B, max(OD, 1), device="cuda")
+    sc = torch.zeros(L.HEADS_NSCALARS, device="cuda")
+    ws = torch.zeros(lib.dvae_heads_ws_floats(B, S), device="cuda")
+    L.check(lib.dvae_latent_heads_fwd(L.ptr(dev(ctx)), B, C, S, L.int_array(dims), L.int_array(dsc_out), L.ptr(dev(Wc)),
+                                      L.ptr(dev(bc)), L.ptr(dev(eps)), L.ptr(dev(Wd)), L.ptr(dev(bd)), L.ptr(dev(labels)),
+                                      L.ptr(dev(klw)), L.ptr(dev(Wz)), L.ptr(dev(bz)), H2L, L.ptr(z), L.ptr(mu), L.ptr(lv),
+                                      L.ptr(hid), L.ptr(lg), L.ptr(sc), L.ptr(ws), L.stream_ptr()), "heads fwd")
+    assert rel(z, want["z"]) < 5e-6 and rel(mu, want["mu"]) < 5e-6 and rel(lv, want["logvar"]) < 5e-6
+    assert rel(hid, want["hid"]) < 5e-6
+    if OD:
+        assert rel(lg[:, :OD], want["logits"]) < 5e-6
+    sc = sc.cpu().numpy()
+    assert np.abs(sc[3:3 + S] - want["kl"]).max() < 1e-5 * max(1.0, np.abs(want["kl"]).max())
+    assert abs(sc[0] - float((klw * want["kl"]).sum())) < 1e-5 * max(1.0, abs(float((klw * want["kl"]).sum())))
+    assert abs(sc[1] - want["kl"].sum()) < 1e-5 * max(1.0, want["kl"].sum())
+    # discriminator losses
+    off = 0
+    i = 0
+    tot = 0.0
+    for s, o in enumerate(dsc_out):
+        if o == 0:
+            continue
+        l = want["logits"][:, off:off + o]
+        y = labels[i]
+        if o == 1:
+            x = l[:, 0]
+            loss = (np.maximum(x, 0) - x * y + np.log1p(np.exp(-np.abs(x)))).mean()
+            acc = ((x > 0) == (y > 0.5)).mean()
+        else:
+            m = l.max(1)
+            loss = (m + np.log(np.exp(l - m[:, None]).sum(1)) - l[np.arange(B), y.astype(int)]).mean()
+            acc = (l.argmax(1) == y.astype(int)).mean()
+        assert abs(sc[3 + S + s] - loss) < 1e-5 and abs(sc[3 + 2 * S + s] - acc) < 1e-6
+        tot += loss
+        off += o
+        i += 1
+    assert abs(sc[2] - tot) < 1e-5
+
+
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("T1,B,H,V", [(4, 3, 8, 23), (7, 5, 16, 37), (19, 128, 256, 10000), (3, 130, 20, 300), (5, 9, 12, 1000)])
+def test_vocab_ce(lib, L, T1, B, H, V):
+    rng = np.random.default_rng(T1 + B + V)
+    N, T = T1 * B, T1 + 1
+    h = rng.standard_normal((T1, B, H)).astype(np.float32) * 0.5
+    W = rng.uniform(-1, 1, (V, H)).astype(np.float32) / np.sqrt(H) * 3
+    b = rng.uniform(-0.1, 0.1, V).astype(np.float32)
+    lengths = rng.integers(1, T + 1, B)
+    lengths[0] = T
+    targets = rng.integers(0, V, (B, T))
+    sos = 2
+    targets[:, 0] = sos
+    targets[1 % B, 0] = 5       # a row whose first target is not <SOS>
+    logits = np.zeros((B, T, V))
+    logits[:, 0, sos] = 1.0
+    logits[:, 1:, :] = (h.astype(np.float64) @ W.astype(np.float64).T + b).transpose(1, 0, 2)
+    want_loss, cache = O.seq_ce_fwd(logits, targets, lengths)
+    dl = O.seq_ce_bwd(cache)[:, 1:, :].transpose(1, 0, 2).reshape(N, V)
+    hd, Wd, bd = dev(h), dev(W), dev(b)
+    td, ld = dev(targets, torch.int64), dev(lengths, torch.int64)
+    lse, nll = torch.zeros(N, device="cuda"), torch.zeros(N, device="cuda")
+    am = torch.zeros(N, device="cuda", dtype=torch.int32)
+    loss = torch.zeros(1, device="cuda")
+    ws = torch.zeros(lib.dvae_vocab_ce_ws_floats(N, V), device="cuda")
+    st = L.stream_ptr()
+    L.check(lib.dvae_vocab_ce_fwd(L.ptr(hd), H, T1, B, H, V, L.ptr(Wd), L.ptr(bd), L.ptr(td), T, L.ptr(ld), sos,
+                                  L.ptr(lse), L.ptr(nll), L.ptr(am), L.ptr(loss), L.ptr(ws), st), "ce fwd")
+    assert abs(loss.item() - want_loss) < 1e-5 * abs(want_loss)
+    assert rel(nll.view(T1, B), cache["nll"][:, 1:].T) < 1e-5
+    ref_am = logits[:, 1:, :].argmax(-1).T.reshape(N)
+    got_am = am.cpu().numpy()
+    if not np.array_equal(got_am, ref_am):      # only exact fp32 near-ties may differ
+        bad = np.nonzero(got_am != ref_am)[0]
+        flat = logits[:, 1:, :].transpose(1, 0, 2).reshape(N, V)
+        gap = np.abs(flat[bad, got_am[bad]] - flat[bad, ref_am[bad]])
+        assert gap.max() < 1e-6, f"argmax differs on {len(bad)} rows with gap {gap.max()}"
+    # backward
+    d_h = torch.zeros(N, H, device="cuda")
+    d_w = torch.full((V, H), 9.0, device="cuda")
+    d_b = torch.full((V,), 9.0, device="cuda")
+    wsb = torch.zeros(lib.dvae_vocab_ce_bwd_ws_floats(N, V), device="cuda")
+    gs = torch.tensor([1.0], device="cuda")
+    L.check(lib.dvae_vocab_ce_bwd(L.ptr(hd), H, T1, B, H, V, L.ptr(Wd), L.ptr(bd), L.ptr(td), T, L.ptr(ld), L.ptr(lse),
+                                  L.ptr(gs), L.ptr(d_h), H, L.ptr(d_w), L.ptr(d_b), L.ptr(wsb), st), "ce bwd")
+    hf = h.reshape(N, H).astype(np.float64)
+    assert rel(d_h, dl @ W.astype(np.float64)) < 1e-4
+    assert rel(d_w, dl.T @ hf) < 1e-4
+    assert rel(d_b, dl.sum(0)) < 1e-4
+
+
+# ---------------------------------------------------------------------------------------------
+def test_clip_adam(lib, L):
+    rng = np.random.default_rng(5)
+    n = 100003
+    p = rng.standard_normal(n).astype(np.float32)
+    g = (rng.standard_normal(n) * 0.1).astype(np.float32)
+    m = (rng.standard_normal(n) * 0.01).astype(np.float32)
+    v = (rng.uniform(0, 1, n) * 1e-3).astype(np.float32)
+    pd, gd, md, vd = dev(p), dev(g), dev(m), dev(v)
+    ss = torch.zeros(1, device="cuda")
+    ws = torch.zeros(2048, device="cuda")
+    hyper = dev(np.array([3e-4, 0.9, 0.999, 1e-8, 7.0], np.float32))
+    st = L.stream_ptr()
+    for _ in range(2):     # the reduction re-arms its own counter
+        L.check(lib.dvae_grad_sumsq(L.ptr(gd), n, L.ptr(ss), L.ptr(ws), st), "sumsq")
+        assert abs(ss.item() - float((g.astype(np.float64) ** 2).sum())) < 1e-5 * float((g.astype(np.float64) ** 2).sum())
+    L.check(lib.dvae_clip_adam(L.ptr(pd), L.ptr(gd), L.ptr(md), L.ptr(vd), n, L.ptr(ss), 5.0, 1.0, L.ptr(hyper), 1, st), "adam")
+    P, G, M, V = {"w": p.astype(np.float64)}, {"w": g.astype(np.float64)}, {"w": m.astype(np.float64)}, {"w": v.astype(np.float64)}
+    norm = O.clip_and_adam(P, G, M, V, step=7, lr=3e-4)
+    assert norm > 5.0      # the clip is active in this case
+    assert rel(md, M["w"]) < 1e-5 and rel(vd, V["w"]) < 1e-5
+    assert np.abs(pd.cpu().numpy() - P["w"]).max() < 1e-6
+    assert float(gd.abs().max()) == 0.0
+
+
+def test_embedding_dropout_roundtrip(lib, L):
+    rng = np.random.default_rng(1)
+    V, E, T, B = 50, 20, 6, 9
+    emb = rng.standard_normal((V, E)).astype(np.float32)
+    tok = rng.integers(0, V, (B, T + 3))
+    embd, tokd = dev(emb), dev(tok, torch.int64)
+    seed = torch.tensor([1234567], device="cuda", dtype=torch.int64)
+    x0 = torch.zeros(T, B, E, device="cuda")
+    st = L.stream_ptr()
+    L.check(lib.dvae_embedding_fwd(L.ptr(embd), E, L.ptr(tokd), T + 3, 1, T, B, 0.0, None, 1, 2, L.ptr(x0), st), "emb")
+    want = emb[tok[:, :T].T]
+    want[0] = emb[2]
+    assert np.array_equal(x0.cpu().numpy(), want)
+    x1 = torch.zeros_like(x0)
+    x2 = torch.zeros_like(x0)
+    for x in (x1, x2):
+        L.check(lib.dvae_embedding_fwd(L.ptr(embd), E, L.ptr(tokd), T + 3, 1, T, B, 0.5, L.ptr(seed), 1, 2, L.ptr(x), st), "emb")
+    assert torch.equal(x1, x2)                      # same seed -> same mask
+    mask = (x1 != 0)
+    assert torch.allclose(x1[mask], 2.0 * x0[mask])
+    keep = mask.float().mean().item()
+    assert 0.4 < keep < 0.6
+    # dense dropout uses the same counter layout -> same mask for the same (seed, salt, shape)
+    y = torch.zeros_like(x0)
+    L.check(lib.dvae_dropout(L.ptr(x0), E, T * B, E, 0.5, L.ptr(seed), 1, L.ptr(y), E, st), "dropout")
+    assert torch.equal(y, x1)
+    # backward scatter-add with the same mask
+    d_x = dev(rng.standard_normal((T, B, E)).astype(np.float32))
+    d_emb = torch.zeros(V, E, device="cuda")
+    L.check(lib.dvae_embedding_bwd(L.ptr(d_x), E, L.ptr(tokd), T + 3, 1, T, B, 0.5, L.ptr(seed), 1, 2, L.ptr(d_emb), st), "emb bwd")
+    want = np.zeros((V, E))
+    toks = tok[:, :T].T.copy()
+    toks[0] = 2
+    np.add.at(want, toks.reshape(-1), (d_x.cpu().numpy() * mask.cpu().numpy() * 2.0).reshape(-1, E))
+    assert rel(d_emb, want) < 1e-5
+
+
+def test_randn_statistics(lib, L):
+    n = 1 << 20
+    out = torch.zeros(n, device="cuda")
+    seed = torch.tensor([99], device="cuda", dtype=torch.int64)
+    L.check(lib.dvae_randn(L.ptr(out), n, L.ptr(seed), 64, L.stream_ptr()), "randn")
+    assert abs(out.mean().item()) < 5e-3 and abs(out.std().item() - 1.0) < 5e-3
+    assert abs((out ** 4).mean().item() - 3.0) < 0.05
