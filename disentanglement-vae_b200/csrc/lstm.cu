@@ -5,7 +5,10 @@
 // state ping-ponged in a small L2-resident buffer; the weight gradients are dense GEMMs over the
 // saved gate gradients.  Exact fp32.  (lstm_persist.cu holds the SMEM-resident persistent-cluster
 // variant for H <= 256.)
+#include <stdlib.h>
+
 #include "common.cuh"
+#include "lstm_persist.cuh"
 
 namespace dvae {
 
@@ -232,6 +235,11 @@ __global__ void __launch_bounds__(kStepThreads) lstm_step_bwd_kernel(BwdStepArgs
 }
 
 // ---- host orchestration -----------------------------------------------------------------------
+// DVAE_LSTM_IMPL=step forces the general per-step path (A/B tests of the persistent kernels)
+static bool force_step_path() {
+  const char* e = getenv("DVAE_LSTM_IMPL");
+  return e && e[0] == 's';
+}
 static int64_t state_floats(int B, int H, int D) { return 4LL * D * B * H; }
 
 int lstm_seq_fwd_impl(const float* x, int64_t ldx, int T, int B, int I, int H, int D, const float* const* w_ih,
@@ -247,6 +255,18 @@ int lstm_seq_fwd_impl(const float* x, int64_t ldx, int T, int B, int I, int H, i
     int rc = linear_impl(x, ldx, 0, w_ih[d], I, 0, gates + d * slab, 4 * H, T * B, 4 * H, I, b_ih ? b_ih[d] : nullptr,
                          b_hh ? b_hh[d] : nullptr, 0.f, 0, st);
     if (rc) return rc;
+  }
+  {
+    const void* ptrs[] = {x, w_hh[0], w_hh[D - 1], h0, c0, hs, hn, cn, gates, cs, ws};
+    const int64_t lds[] = {ld0, dir0, ldhs, ldn, dirn};
+    if (!force_step_path() && persist_supported(B, H, D, ptrs, 11, lds, 5)) {
+      PersistFwdArgs a;
+      a.w_hh[0] = w_hh[0]; a.w_hh[1] = w_hh[D - 1];
+      a.gates = gates; a.cs = cs; a.hs = hs; a.ldhs = ldhs; a.h0 = h0; a.c0 = c0; a.ld0 = ld0; a.dir0 = dir0;
+      a.hstate = ws; a.hn = hn; a.cn = cn; a.ldn = ldn; a.dirn = dirn; a.lengths = lengths;
+      a.T = T; a.B = B; a.D = D; a.n_slices = ceil_div(B, 16);
+      return persist_fwd(H, a, st);
+    }
   }
   float* hbuf[2] = {ws, ws + 2 * sf};
   float* cbuf[2] = {ws + sf, ws + 3 * sf};
@@ -287,24 +307,41 @@ int lstm_seq_bwd_impl(const float* x, int64_t ldx, int T, int B, int I, int H, i
   DVAE_REQUIRE(T > 0 && B > 0 && I > 0 && H > 0 && (D == 1 || D == 2), "dvae_lstm_seq_bwd: bad shape");
   DVAE_REQUIRE(!(lengths && h0), "dvae_lstm_seq_bwd: length-masked layers start from the zero state");
   const int64_t slab = (int64_t)T * B * 4 * H, sf = (int64_t)D * B * H;
+  bool persisted = false;
+  {
+    const void* ptrs[] = {w_hh[0], w_hh[D - 1], c0, gates, cs, d_hs, d_hn, d_cn, d_h0, d_c0};
+    const int64_t lds[] = {ld0, dir0, lddhs, ldn, dirn, ldd0, dird0};
+    if (!force_step_path() && persist_supported(B, H, D, ptrs, 10, lds, 7)) {
+      PersistBwdArgs a;
+      a.w_hh[0] = w_hh[0]; a.w_hh[1] = w_hh[D - 1];
+      a.gates = gates; a.cs = cs; a.c0 = c0; a.ld0 = ld0; a.dir0 = dir0; a.d_hs = d_hs; a.lddhs = lddhs;
+      a.d_hn = d_hn; a.d_cn = d_cn; a.ldn = ldn; a.dirn = dirn; a.d_h0 = d_h0; a.d_c0 = d_c0; a.ldd0 = ldd0;
+      a.dird0 = dird0; a.lengths = lengths; a.T = T; a.B = B; a.D = D; a.n_slices = ceil_div(B, 16);
+      int rc = persist_bwd(H, a, st);
+      if (rc) return rc;
+      persisted = true;
+    }
+  }
   float* carry[2] = {ws, ws + 2 * sf};
   float* dcb[2] = {ws + sf, ws + 3 * sf};
   float* wt = ws + 4 * sf;  // [D][H,4H]
-  for (int d = 0; d < D; ++d) {
+  for (int d = 0; d < D && !persisted; ++d) {
     transpose_kernel<<<dim3(ceil_div(H, 32), ceil_div(4 * H, 32)), dim3(32, 8), 0, st>>>(w_hh[d], wt + (int64_t)d * 4 * H * H, 4 * H, H);
     DVAE_LAUNCH_CHECK();
   }
   const int nthr = 256, nblk = ceil_div(sf, nthr);
-  copy_state_kernel<<<nblk, nthr, 0, st>>>(d_hn, ldn, dirn, carry[0], H, (int64_t)B * H, D, B, H);
-  DVAE_LAUNCH_CHECK();
-  copy_state_kernel<<<nblk, nthr, 0, st>>>(d_cn, ldn, dirn, dcb[0], H, (int64_t)B * H, D, B, H);
-  DVAE_LAUNCH_CHECK();
+  if (!persisted) {
+    copy_state_kernel<<<nblk, nthr, 0, st>>>(d_hn, ldn, dirn, carry[0], H, (int64_t)B * H, D, B, H);
+    DVAE_LAUNCH_CHECK();
+    copy_state_kernel<<<nblk, nthr, 0, st>>>(d_cn, ldn, dirn, dcb[0], H, (int64_t)B * H, D, B, H);
+    DVAE_LAUNCH_CHECK();
+  }
   BwdStepArgs a;
   for (int d = 0; d < 2; ++d) a.w_hh_t[d] = wt + (int64_t)(d < D ? d : 0) * 4 * H * H;
   a.gates = gates; a.cs = cs; a.c0 = c0; a.ld0 = ld0; a.dir0 = dir0; a.d_hs = d_hs; a.lddhs = lddhs;
   a.d_h0 = d_h0; a.d_c0 = d_c0; a.ldd0 = ldd0; a.dird0 = dird0; a.lengths = lengths; a.T = T; a.B = B; a.H = H;
   dim3 grid(ceil_div(H, 32), ceil_div(B, kStepRows), D);
-  const int nsteps = T + ((d_h0 || d_c0) ? 1 : 0);
+  const int nsteps = persisted ? 0 : T + ((d_h0 || d_c0) ? 1 : 0);
   for (int s = 0; s < nsteps; ++s) {
     a.s = s; a.final_ = (s == T);
     a.carry_in = carry[s & 1]; a.dc_in = dcb[s & 1]; a.carry_out = carry[(s + 1) & 1]; a.dc_out = dcb[(s + 1) & 1];

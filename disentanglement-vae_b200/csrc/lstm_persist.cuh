@@ -1,0 +1,34 @@
+// Argument blocks and entry points of the persistent (cluster, SMEM-resident W_hh) LSTM kernels.
+#pragma once
+#include "common.cuh"
+
+namespace dvae {
+
+struct PersistFwdArgs {
+  const float* w_hh[2];
+  float* gates; float* cs; float* hs; int64_t ldhs;
+  const float* h0; const float* c0; int64_t ld0, dir0;
+  float* hstate;                 // [2][D][B][H] carried-h exchange buffer
+  float* hn; float* cn; int64_t ldn, dirn;
+  const int64_t* lengths;
+  int T, B, D, n_slices;
+};
+
+struct PersistBwdArgs {
+  const float* w_hh[2];
+  float* gates;                  // post-activation gates in, dG out
+  const float* cs;
+  const float* c0; int64_t ld0, dir0;
+  const float* d_hs; int64_t lddhs;
+  const float* d_hn; const float* d_cn; int64_t ldn, dirn;
+  float* d_h0; float* d_c0; int64_t ldd0, dird0;
+  const int64_t* lengths;
+  int T, B, D, n_slices;
+};
+
+// true when the persistent kernels can take this call (H in {64,128,256}, 16-byte aligned buffers)
+bool persist_supported(int B, int H, int D, const void* const* ptrs, int nptr, const int64_t* lds, int nld);
+int persist_fwd(int H, const PersistFwdArgs& a, cudaStream_t st);
+int persist_bwd(int H, const PersistBwdArgs& a, cudaStream_t st);
+
+}  // namespace dvae

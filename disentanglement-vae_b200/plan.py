@@ -71,7 +71,10 @@ class StepPlan:
         self.z, self.mu, self.logvar = buf(B, d.Z), buf(B, d.Z), buf(B, d.Z)
         self.hid = buf(B, d.H2L)
         self.dsc_logits = buf(B, max(d.OD, 1))
-        self.scalars = torch.zeros(_lib.HEADS_NSCALARS, **f32)
+        # one small result block so a step's scalars come back in a single D2H read:
+        # out[:27] = fused-head scalars (weighted KL, KL, dsc loss, per-space ...), out[27] = recon loss
+        self.out = torch.zeros(_lib.HEADS_NSCALARS + 5, **f32)
+        self.scalars = self.out[:_lib.HEADS_NSCALARS]
         self.heads_ws = buf(self.lib.dvae_heads_ws_floats(B, d.S))
         T1 = max(self.T1, 1)
         self.x_dec = buf(T1, B, E)
@@ -82,7 +85,7 @@ class StepPlan:
         self.state_ws = buf(self.lib.dvae_lstm_state_ws_floats(B, H, D))
         self.lse, self.nll = buf(max(self.N, 1)), buf(max(self.N, 1))
         self.argmax = torch.zeros(max(self.N, 1), device=device, dtype=torch.int32)
-        self.recon = torch.zeros(1, **f32)
+        self.recon = self.out[_lib.HEADS_NSCALARS:_lib.HEADS_NSCALARS + 1]
         self.ce_ws = buf(self.lib.dvae_vocab_ce_ws_floats(max(self.N, 1), d.V))
         self._bwd_ready = False
         self.seed_dev = torch.zeros(1, device=device, dtype=torch.int64)

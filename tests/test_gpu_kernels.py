@@ -169,9 +169,19 @@ def _lstm_case(lib, L, T, B, I, H, D, with_len, with_h0, seed):
     (22, 128, 64, 256, 2, True, False),  # cfg-2 hidden size
     (6, 40, 256, 64, 1, False, True),
     (4, 7, 7, 5, 2, True, False),        # widths not divisible by 4 (scalar load path)
+    (11, 50, 24, 128, 2, True, False),   # persistent-cluster kernels: H=128, ragged, partial 16-row slice
+    (21, 128, 256, 256, 1, False, True), # persistent-cluster kernels: cfg-2 decoder layer
+    (30, 64, 32, 64, 1, True, False),
 ])
 def test_lstm_seq(lib, L, T, B, I, H, D, with_len, with_h0):
     _lstm_case(lib, L, T, B, I, H, D, with_len, with_h0, seed=T * 31 + B)
+
+
+@pytest.mark.parametrize("H,D,with_len,with_h0", [(256, 2, True, False), (64, 1, False, True)])
+def test_lstm_step_path_matches_oracle_too(lib, L, H, D, with_len, with_h0, monkeypatch):
+    """DVAE_LSTM_IMPL=step forces the general per-step kernels on shapes the persistent kernels take."""
+    monkeypatch.setenv("DVAE_LSTM_IMPL", "step")
+    _lstm_case(lib, L, 9, 48, 32, H, D, with_len, with_h0, seed=H + D)
 
 
 # ---------------------------------------------------------------------------------------------
