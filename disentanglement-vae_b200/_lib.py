@@ -31,6 +31,7 @@ SIGNATURES = {
     "dvae_version": (_i, []),
     "dvae_launch_count": (_l, []),
     "dvae_linear": (_i, [_p, _l, _i, _p, _l, _i, _p, _l, _i, _i, _i, _p, _p, _f, _i, _p]),
+    "dvae_tc_linear": (_i, [_p, _l, _i, _p, _l, _i, _p, _l, _i, _i, _i, _p, _p, _f, _i, _i, _p]),
     "dvae_colsum": (_i, [_p, _l, _i, _i, _p, _f, _p]),
     "dvae_randn": (_i, [_p, _l, _p, _u32, _p]),
     "dvae_embedding_fwd": (_i, [_p, _i, _p, _l, _l, _i, _i, _f, _p, _u32, _l, _p, _p]),

@@ -1,5 +1,6 @@
 // Error / bookkeeping entry points of the C ABI (see include/dvae_b200.h).
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include <atomic>
 
@@ -16,6 +17,10 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+bool force_simt_gemm() {
+  const char* e = getenv("DVAE_GEMM_IMPL");
+  return e && e[0] == 's';
+}
 }  // namespace dvae
 
 extern "C" const char* dvae_last_error_string(void) { return dvae::g_err; }

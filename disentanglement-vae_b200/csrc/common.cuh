@@ -43,6 +43,22 @@ void count_launch(int n = 1);
 
 static inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
+// DVAE_GEMM_IMPL=simt forces the fp32 SIMT kernels (A/B tests of the tensor-core path)
+bool force_simt_gemm();
+
+namespace tc {
+bool tc_linear_supported(const float* A, int64_t lda, const float* B, int64_t ldb, int M, int N, int K);
+int tc_linear_impl(const float* A, int64_t lda, int trans_a, const float* B, int64_t ldb, int trans_b, float* C, int64_t ldc,
+                   int M, int N, int K, const float* bias, const float* bias2, float beta, int act, int passes,
+                   cudaStream_t st);
+int tc_ce_partials(const float* h, int64_t ldh, int N, int B, int H, int V, const float* w, const float* bias,
+                   const int64_t* targets, int64_t tgt_stride_b, const int64_t* lengths, int tiles_per_split, int nsplit,
+                   float* part, int* part_idx, cudaStream_t st);
+int tc_softmax_grad(const float* h, int64_t ldh, int N, int B, int H, int v0, int vc, const float* w, const float* bias,
+                    const int64_t* targets, int64_t tgt_stride_b, const int64_t* lengths, const float* lse,
+                    const float* grad_scale, float* P, int64_t ldp, cudaStream_t st);
+}  // namespace tc
+
 // ---- Philox4x32-10 (counter-based; same mask in forward and backward without storing it) ------
 struct Philox {
   static constexpr uint32_t kM0 = 0xD2511F53u, kM1 = 0xCD9E8D57u, kW0 = 0x9E3779B9u, kW1 = 0xBB67AE85u;

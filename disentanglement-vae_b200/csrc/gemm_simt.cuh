@@ -122,10 +122,18 @@ struct GemmTile {
           float4 t = *reinterpret_cast<const float4*>(&Bc[k * LDB_S + j * (BN / (TN / 4)) + tx * 4]);
           b[j * 4 + 0] = t.x; b[j * 4 + 1] = t.y; b[j * 4 + 2] = t.z; b[j * 4 + 3] = t.w;
         }
+        // packed fp32 FMA: (acc[i][j], acc[i][j+1]) += (a[i], a[i]) * (b[j], b[j+1]).  Two IEEE fmas per
+        // FFMA2, bit-identical to the scalar form; scalar FFMA issues at half rate on sm_100.
 #pragma unroll
-        for (int i = 0; i < TM; ++i)
+        for (int i = 0; i < TM; ++i) {
+          const float2 aa = make_float2(a[i], a[i]);
 #pragma unroll
-          for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+          for (int j = 0; j < TN; j += 2) {
+            float2 c = make_float2(acc[i][j], acc[i][j + 1]);
+            c = __ffma2_rn(aa, make_float2(b[j], b[j + 1]), c);
+            acc[i][j] = c.x; acc[i][j + 1] = c.y;
+          }
+        }
       }
       if (it + 1 < nk) {
         float* An = smem + ((it + 1) & 1) * STAGE_FLOATS;

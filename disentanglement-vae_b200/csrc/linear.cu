@@ -83,6 +83,11 @@ int linear_impl(const float* A, int64_t lda, int trans_a, const float* B, int64_
   DVAE_REQUIRE(A && B && C, "dvae_linear: null pointer");
   DVAE_REQUIRE(M > 0 && N > 0 && K > 0, "dvae_linear: non-positive size M=%d N=%d K=%d", M, N, K);
   DVAE_REQUIRE(act == 0 || act == 1, "dvae_linear: unknown activation %d", act);
+  // Dense-contraction shapes go to the tensor cores (TMA + tcgen05, 3xTF32 = fp32-grade accuracy); small or
+  // unaligned problems stay on the fp32 SIMT kernels below.
+  if (!force_simt_gemm() && M >= 64 && N >= 64 && K >= 32 && (double)M * N * K >= (double)(1 << 23) &&
+      tc::tc_linear_supported(A, lda, B, ldb, M, N, K))
+    return tc::tc_linear_impl(A, lda, trans_a, B, ldb, trans_b, C, ldc, M, N, K, bias, bias2, beta, act, 3, st);
   // Tile choice: 128x128 when that already fills the 148 SMs, else 64x64; split-K (atomic
   // accumulation) when even the small tiles leave most SMs idle and K is deep.
   const int kSMs = 148;

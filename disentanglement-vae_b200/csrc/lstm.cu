@@ -264,7 +264,7 @@ int lstm_seq_fwd_impl(const float* x, int64_t ldx, int T, int B, int I, int H, i
       a.w_hh[0] = w_hh[0]; a.w_hh[1] = w_hh[D - 1];
       a.gates = gates; a.cs = cs; a.hs = hs; a.ldhs = ldhs; a.h0 = h0; a.c0 = c0; a.ld0 = ld0; a.dir0 = dir0;
       a.hstate = ws; a.hn = hn; a.cn = cn; a.ldn = ldn; a.dirn = dirn; a.lengths = lengths;
-      a.T = T; a.B = B; a.D = D; a.n_slices = ceil_div(B, 16);
+      a.T = T; a.B = B; a.D = D; a.n_slices = ceil_div(B, 16); a.d_off = 0;
       return persist_fwd(H, a, st);
     }
   }
@@ -316,7 +316,7 @@ int lstm_seq_bwd_impl(const float* x, int64_t ldx, int T, int B, int I, int H, i
       a.w_hh[0] = w_hh[0]; a.w_hh[1] = w_hh[D - 1];
       a.gates = gates; a.cs = cs; a.c0 = c0; a.ld0 = ld0; a.dir0 = dir0; a.d_hs = d_hs; a.lddhs = lddhs;
       a.d_hn = d_hn; a.d_cn = d_cn; a.ldn = ldn; a.dirn = dirn; a.d_h0 = d_h0; a.d_c0 = d_c0; a.ldd0 = ldd0;
-      a.dird0 = dird0; a.lengths = lengths; a.T = T; a.B = B; a.D = D; a.n_slices = ceil_div(B, 16);
+      a.dird0 = dird0; a.lengths = lengths; a.T = T; a.B = B; a.D = D; a.n_slices = ceil_div(B, 16); a.d_off = 0;
       int rc = persist_bwd(H, a, st);
       if (rc) return rc;
       persisted = true;

@@ -25,6 +25,7 @@ namespace dvae {
 constexpr int kPRows = 16;        // batch rows per cluster
 constexpr int kPThreads = 256;
 constexpr int kClusterSize = 8;
+constexpr int kMaxResidentClusters = 15;
 
 // acc[8][2] = sum over this thread's K range of A[rh*8 + r][k] * W[col(c)][k]
 //   A: smem [16][K + 4];  W: smem [NCOLS][K + 4];  thread tile = 8 rows x cols {cp, cp + NCOLS/2}
@@ -38,26 +39,30 @@ __device__ __forceinline__ void persist_gemm(const float* __restrict__ a_s, cons
   const float* a_base = a_s + (rh * 8) * LD + ks * KPS;
   const float* w0 = w_s + cp * LD + ks * KPS;
   const float* w1 = w_s + (cp + NCOLS / 2) * LD + ks * KPS;
-  float acc[8][2];
+  // packed fp32 FMA (FFMA2): each accumulator is an (even k, odd k) pair, so both operands of every
+  // FFMA2 are the natural register pairs of the LDS.128 results -- no duplication moves.  Scalar
+  // FFMA issues at half rate on sm_100; FFMA2 is what reaches the fp32 peak.
+  float2 acc[8][2];
 #pragma unroll
-  for (int r = 0; r < 8; ++r) { acc[r][0] = 0.f; acc[r][1] = 0.f; }
+  for (int r = 0; r < 8; ++r) { acc[r][0] = make_float2(0.f, 0.f); acc[r][1] = make_float2(0.f, 0.f); }
 #pragma unroll 2
   for (int kq = 0; kq < KPS / 4; ++kq) {
     const float4 b0 = *reinterpret_cast<const float4*>(w0 + kq * 4);
     const float4 b1 = *reinterpret_cast<const float4*>(w1 + kq * 4);
+    const float2 b0l = make_float2(b0.x, b0.y), b0h = make_float2(b0.z, b0.w);
+    const float2 b1l = make_float2(b1.x, b1.y), b1h = make_float2(b1.z, b1.w);
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
       const float4 a = *reinterpret_cast<const float4*>(a_base + r * LD + kq * 4);
-      acc[r][0] = fmaf(a.x, b0.x, acc[r][0]); acc[r][0] = fmaf(a.y, b0.y, acc[r][0]);
-      acc[r][0] = fmaf(a.z, b0.z, acc[r][0]); acc[r][0] = fmaf(a.w, b0.w, acc[r][0]);
-      acc[r][1] = fmaf(a.x, b1.x, acc[r][1]); acc[r][1] = fmaf(a.y, b1.y, acc[r][1]);
-      acc[r][1] = fmaf(a.z, b1.z, acc[r][1]); acc[r][1] = fmaf(a.w, b1.w, acc[r][1]);
+      const float2 al = make_float2(a.x, a.y), ah = make_float2(a.z, a.w);
+      acc[r][0] = __ffma2_rn(al, b0l, acc[r][0]); acc[r][0] = __ffma2_rn(ah, b0h, acc[r][0]);
+      acc[r][1] = __ffma2_rn(al, b1l, acc[r][1]); acc[r][1] = __ffma2_rn(ah, b1h, acc[r][1]);
     }
   }
 #pragma unroll
   for (int r = 0; r < 8; ++r) {
-    part_s[(ks * kPRows + rh * 8 + r) * NCOLS + cp] = acc[r][0];
-    part_s[(ks * kPRows + rh * 8 + r) * NCOLS + cp + NCOLS / 2] = acc[r][1];
+    part_s[(ks * kPRows + rh * 8 + r) * NCOLS + cp] = acc[r][0].x + acc[r][0].y;
+    part_s[(ks * kPRows + rh * 8 + r) * NCOLS + cp + NCOLS / 2] = acc[r][1].x + acc[r][1].y;
   }
 }
 
@@ -81,7 +86,7 @@ lstm_persist_fwd_kernel(PersistFwdArgs p) {
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (int)cluster.block_rank();
   const int cid = blockIdx.x / kClusterSize;
-  const int d = cid / p.n_slices, slice = cid % p.n_slices;
+  const int d = p.d_off + cid / p.n_slices, slice = cid % p.n_slices;
   const int b0 = slice * kPRows, u0 = rank * UPC;
   const int tid = threadIdx.x, B = p.B, T = p.T;
 
@@ -124,18 +129,27 @@ lstm_persist_fwd_kernel(PersistFwdArgs p) {
 #pragma unroll
       for (int g = 0; g < 4; ++g) pre[g] = *reinterpret_cast<const float4*>(p.gates + gi + g * H);
     }
-    // (2) stage the 16 carried h rows
-    for (int v = tid; v < kPRows * (H / 4); v += kPThreads) {
-      const int r = v / (H / 4), kq = v % (H / 4), b = b0 + r;
-      float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (b < B) {
-        if (s == 0) {
-          if (p.h0) val = *reinterpret_cast<const float4*>(p.h0 + d * p.dir0 + (int64_t)b * p.ld0 + kq * 4);
-        } else {
-          val = ldcg4(p.hstate + (s & 1) * state_stride + ((int64_t)d * B + b) * H + kq * 4);
+    // (2) stage the 16 carried h rows: all loads in flight before the first shared store
+    {
+      constexpr int NV = kPRows * (H / 4) / kPThreads;
+      float4 val[NV];
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int v = tid + i * kPThreads, r = v / (H / 4), kq = v % (H / 4), b = b0 + r;
+        val[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (b < B) {
+          if (s == 0) {
+            if (p.h0) val[i] = *reinterpret_cast<const float4*>(p.h0 + d * p.dir0 + (int64_t)b * p.ld0 + kq * 4);
+          } else {
+            val[i] = ldcg4(p.hstate + (s & 1) * state_stride + ((int64_t)d * B + b) * H + kq * 4);
+          }
         }
       }
-      *reinterpret_cast<float4*>(&a_s[r * LD + kq * 4]) = val;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int v = tid + i * kPThreads, r = v / (H / 4), kq = v % (H / 4);
+        *reinterpret_cast<float4*>(&a_s[r * LD + kq * 4]) = val[i];
+      }
     }
     __syncthreads();
     // (3) recurrent pre-activations of this CTA's gate columns
@@ -184,8 +198,7 @@ lstm_persist_fwd_kernel(PersistFwdArgs p) {
       *reinterpret_cast<float4*>(p.hstate + ((s + 1) & 1) * state_stride + ((int64_t)d * B + eb) * H + eu) =
           make_float4(h_reg[0], h_reg[1], h_reg[2], h_reg[3]);
     }
-    __threadfence();
-    cluster.sync();
+    cluster.sync();      // barrier.cluster arrive.release / wait.acquire orders the global stores above
   }
   if (erow) {
     if (p.hn) *reinterpret_cast<float4*>(p.hn + d * p.dirn + (int64_t)eb * p.ldn + eu) = make_float4(h_reg[0], h_reg[1], h_reg[2], h_reg[3]);
@@ -212,7 +225,7 @@ lstm_persist_bwd_kernel(PersistBwdArgs p) {
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (int)cluster.block_rank();
   const int cid = blockIdx.x / kClusterSize;
-  const int d = cid / p.n_slices, slice = cid % p.n_slices;
+  const int d = p.d_off + cid / p.n_slices, slice = cid % p.n_slices;
   const int b0 = slice * kPRows, u0 = rank * UPC;
   const int tid = threadIdx.x, B = p.B, T = p.T;
   {
@@ -254,11 +267,22 @@ lstm_persist_bwd_kernel(PersistBwdArgs p) {
     float rec[4] = {0.f, 0.f, 0.f, 0.f};
     if (s > 0) {
       const float* src = p.gates + ((int64_t)d * T + t_next) * B * K;
-      for (int v = tid; v < kPRows * (K / 4); v += kPThreads) {
-        const int r = v / (K / 4), kq = v % (K / 4), b = b0 + r;
-        float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (b < B) val = ldcg4(src + (int64_t)b * K + kq * 4);
-        *reinterpret_cast<float4*>(&a_s[r * LD + kq * 4]) = val;
+      constexpr int NV = kPRows * (K / 4) / kPThreads;      // 16 at H = 256: two batches of 8 loads
+      constexpr int NB = NV > 8 ? 8 : NV;
+#pragma unroll
+      for (int i0 = 0; i0 < NV; i0 += NB) {
+        float4 val[NB];
+#pragma unroll
+        for (int i = 0; i < NB; ++i) {
+          const int v = tid + (i0 + i) * kPThreads, r = v / (K / 4), kq = v % (K / 4), b = b0 + r;
+          val[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (b < B) val[i] = ldcg4(src + (int64_t)b * K + kq * 4);
+        }
+#pragma unroll
+        for (int i = 0; i < NB; ++i) {
+          const int v = tid + (i0 + i) * kPThreads, r = v / (K / 4), kq = v % (K / 4);
+          *reinterpret_cast<float4*>(&a_s[r * LD + kq * 4]) = val[i];
+        }
       }
       __syncthreads();
       persist_gemm<NCOLS, K, KPS>(a_s, w_s, part_s);
@@ -303,8 +327,7 @@ lstm_persist_bwd_kernel(PersistBwdArgs p) {
         for (int g = 0; g < 4; ++g) *reinterpret_cast<float4*>(p.gates + gi + g * H) = make_float4(o[g][0], o[g][1], o[g][2], o[g][3]);
       }
     }
-    __threadfence();
-    cluster.sync();
+    cluster.sync();      // barrier.cluster arrive.release / wait.acquire orders the global stores above
   }
 }
 
@@ -331,8 +354,17 @@ static int launch_fwd(const PersistFwdArgs& a, cudaStream_t st) {
     DVAE_CUDA(cudaFuncSetAttribute(lstm_persist_fwd_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     ready = true;
   }
-  lstm_persist_fwd_kernel<H><<<kClusterSize * a.n_slices * a.D, kPThreads, smem, st>>>(a);
-  DVAE_LAUNCH_CHECK();
+  // at one CTA per SM a B200 keeps at most 15 clusters of 8 resident (measured with
+  // cudaOccupancyMaxActiveClusters, profiles/probes/cluster_occupancy.cu): when both directions
+  // together need more but one direction fits, run them back to back instead of spilling one
+  // cluster into a second wave.
+  const bool split = a.D == 2 && 2 * a.n_slices > kMaxResidentClusters && a.n_slices <= kMaxResidentClusters;
+  for (int d0 = 0; d0 < (split ? 2 : 1); ++d0) {
+    PersistFwdArgs b = a;
+    b.d_off = d0;
+    lstm_persist_fwd_kernel<H><<<kClusterSize * a.n_slices * (split ? 1 : a.D), kPThreads, smem, st>>>(b);
+    DVAE_LAUNCH_CHECK();
+  }
   return DVAE_OK;
 }
 
@@ -344,8 +376,13 @@ static int launch_bwd(const PersistBwdArgs& a, cudaStream_t st) {
     DVAE_CUDA(cudaFuncSetAttribute(lstm_persist_bwd_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     ready = true;
   }
-  lstm_persist_bwd_kernel<H><<<kClusterSize * a.n_slices * a.D, kPThreads, smem, st>>>(a);
-  DVAE_LAUNCH_CHECK();
+  const bool split = a.D == 2 && 2 * a.n_slices > kMaxResidentClusters && a.n_slices <= kMaxResidentClusters;
+  for (int d0 = 0; d0 < (split ? 2 : 1); ++d0) {
+    PersistBwdArgs b = a;
+    b.d_off = d0;
+    lstm_persist_bwd_kernel<H><<<kClusterSize * a.n_slices * (split ? 1 : a.D), kPThreads, smem, st>>>(b);
+    DVAE_LAUNCH_CHECK();
+  }
   return DVAE_OK;
 }
 

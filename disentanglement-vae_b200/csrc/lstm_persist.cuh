@@ -11,7 +11,7 @@ struct PersistFwdArgs {
   float* hstate;                 // [2][D][B][H] carried-h exchange buffer
   float* hn; float* cn; int64_t ldn, dirn;
   const int64_t* lengths;
-  int T, B, D, n_slices;
+  int T, B, D, n_slices, d_off;
 };
 
 struct PersistBwdArgs {
@@ -23,7 +23,7 @@ struct PersistBwdArgs {
   const float* d_hn; const float* d_cn; int64_t ldn, dirn;
   float* d_h0; float* d_c0; int64_t ldd0, dird0;
   const int64_t* lengths;
-  int T, B, D, n_slices;
+  int T, B, D, n_slices, d_off;
 };
 
 // true when the persistent kernels can take this call (H in {64,128,256}, 16-byte aligned buffers)

@@ -229,9 +229,16 @@ extern "C" int dvae_vocab_ce_fwd(const float* h, int64_t ldh, int T1, int B, int
   p.nsplit = ce_nsplit(p.N, V, &p.tiles_per_split);
   p.part = ws;
   p.part_idx = reinterpret_cast<int*>(ws + (int64_t)p.nsplit * p.N * 4);
-  dim3 grid(ceil_div(p.N, GCE::BM), p.nsplit);
-  vocab_ce_fwd_kernel<<<grid, GCE::NT, 0, st>>>(p);
-  DVAE_LAUNCH_CHECK();
+  if (!force_simt_gemm() && p.N >= 64 && V >= 128 && H >= 32 && tc::tc_linear_supported(h, ldh, w, H, p.N, V, H)) {
+    // tensor-core path: same (row tile, vocabulary split) decomposition and partials format
+    int rc = tc::tc_ce_partials(h, ldh, p.N, B, H, V, w, bias, targets, tgt_stride_b, lengths, p.tiles_per_split, p.nsplit,
+                                p.part, p.part_idx, st);
+    if (rc) return rc;
+  } else {
+    dim3 grid(ceil_div(p.N, GCE::BM), p.nsplit);
+    vocab_ce_fwd_kernel<<<grid, GCE::NT, 0, st>>>(p);
+    DVAE_LAUNCH_CHECK();
+  }
   vocab_ce_finalize_kernel<<<1, 1024, 0, st>>>(p, lse, nll, argmax, loss);
   DVAE_LAUNCH_CHECK();
   return DVAE_OK;
@@ -255,10 +262,15 @@ extern "C" int dvae_vocab_ce_bwd(const float* h, int64_t ldh, int T1, int B, int
   for (int v0 = 0; v0 < V; v0 += vc_max, ++chunk) {
     const int vc = min(vc_max, V - v0);
     p.v0 = v0; p.vc = vc;
-    dim3 grid(ceil_div(vc, GCE::BN), ceil_div(N, GCE::BM));
-    vocab_p_kernel<<<grid, GCE::NT, 0, st>>>(p);
-    DVAE_LAUNCH_CHECK();
     int rc;
+    if (!force_simt_gemm() && N >= 64 && vc >= 128 && H >= 32 && tc::tc_linear_supported(h, ldh, w, H, N, vc, H)) {
+      if ((rc = tc::tc_softmax_grad(h, ldh, N, B, H, v0, vc, w, bias, targets, tgt_stride_b, lengths, lse, grad_scale_dev, ws,
+                                    vc_max, st))) return rc;
+    } else {
+      dim3 grid(ceil_div(vc, GCE::BN), ceil_div(N, GCE::BM));
+      vocab_p_kernel<<<grid, GCE::NT, 0, st>>>(p);
+      DVAE_LAUNCH_CHECK();
+    }
     // d_h [N,H] (+)= P [N,vc] . W[v0:v0+vc, :]        (B stored [K=vc][N=H])
     if ((rc = linear_impl(ws, vc_max, 0, w + (int64_t)v0 * H, H, 1, d_h, lddh, N, H, vc, nullptr, nullptr, chunk ? 1.f : 0.f, 0, st))) return rc;
     // d_w[v0:v0+vc, :] = P^T [vc,N] . h [N,H]

@@ -53,6 +53,14 @@ int dvae_linear(const float* A, int64_t lda, int trans_a, const float* B, int64_
                 float* C, int64_t ldc, int M, int N, int K, const float* bias, const float* bias2,
                 float beta, int act, void* stream);
 
+/* Same contract as dvae_linear, computed on the 5th-generation tensor cores (TMA-staged 128x128x32
+ * tiles, tcgen05.mma.kind::tf32 into TMEM).  passes = 3: 3xTF32 split (hi*hi + hi*lo + lo*hi), fp32-grade
+ * accuracy -- the forward path's setting; passes = 1: single TF32 pass with round-to-nearest operands.
+ * Requires 16-byte aligned A, B and lda, ldb multiples of 4 (TMA). */
+int dvae_tc_linear(const float* A, int64_t lda, int trans_a, const float* B, int64_t ldb, int trans_b,
+                   float* C, int64_t ldc, int M, int N, int K, const float* bias, const float* bias2,
+                   float beta, int act, int passes, void* stream);
+
 /* out[n] = sum_m X[m, n] (+ out[n] if beta == 1); X is [M,N] row-major with row stride ldx. */
 int dvae_colsum(const float* X, int64_t ldx, int M, int N, float* out, float beta, void* stream);
 

@@ -65,6 +65,40 @@ def test_linear(lib, L, M, N, K, ta, tb):
     assert np.abs(c_d.cpu().numpy() - want).max() < 1e-5
 
 
+@pytest.mark.parametrize("M,N,K", [(128, 128, 32), (128, 128, 256), (256, 384, 64), (130, 257, 100), (2688, 1024, 256), (100, 10000, 256), (1024, 256, 2688)])
+@pytest.mark.parametrize("ta,tb", [(0, 0), (0, 1), (1, 1), (1, 0)])
+def test_tc_linear_3xtf32(lib, L, M, N, K, ta, tb):
+    """tcgen05 / TMA / TMEM GEMM: 3xTF32 must be fp32-grade, 1xTF32 within TF32 rounding."""
+    rng = np.random.default_rng(M + 3 * N + 7 * K + ta * 2 + tb)
+    A = (rng.standard_normal((M, K)) / np.sqrt(K)).astype(np.float32)
+    Bm = rng.standard_normal((N, K)).astype(np.float32)
+    bias = rng.standard_normal(N).astype(np.float32)
+    # TMA needs row strides that are multiples of 16 bytes: pad the leading dimension of the stored matrix
+    def stored(X, t):
+        S = np.ascontiguousarray(X.T if t else X)
+        ld = (S.shape[1] + 3) // 4 * 4
+        buf = torch.zeros(S.shape[0], ld, device="cuda")
+        buf[:, :S.shape[1]] = torch.from_numpy(S).cuda()
+        _KEEP.append(buf)
+        return buf, ld
+    a_d, lda = stored(A, ta)
+    b_d, ldb = stored(Bm, tb)
+    want = A.astype(np.float64) @ Bm.astype(np.float64).T + bias
+    bias_d = dev(bias)
+    st = L.stream_ptr()
+    for passes, tol in ((3, max(2e-6, 1e-8 * K)), (1, 2e-3)):   # in-TMEM fp32 accumulation error grows ~5e-9*K
+        c_d = torch.full((M, N), 7.0, device="cuda")
+        L.check(lib.dvae_tc_linear(L.ptr(a_d), lda, ta, L.ptr(b_d), ldb, tb, L.ptr(c_d), N, M, N, K, L.ptr(bias_d), None,
+                                   0.0, 0, passes, st), "tc_linear")
+        torch.cuda.synchronize()
+        assert rel(c_d, want) < tol, (passes, rel(c_d, want))
+    # beta accumulate + second bias
+    c_d = torch.ones(M, N, device="cuda")
+    L.check(lib.dvae_tc_linear(L.ptr(a_d), lda, ta, L.ptr(b_d), ldb, tb, L.ptr(c_d), N, M, N, K, L.ptr(bias_d), L.ptr(bias_d),
+                               1.0, 0, 3, st), "tc_linear")
+    assert rel(c_d, want + bias + 1.0) < max(2e-6, 1e-8 * K)
+
+
 def test_linear_strided_output_and_colsum(lib, L):
     rng = np.random.default_rng(0)
     A = rng.standard_normal((70, 33)).astype(np.float32)
@@ -285,7 +319,7 @@ def test_latent_heads_forward(lib, L, B, C, dims, dsc_out):
 
 
 # ---------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("T1,B,H,V", [(4, 3, 8, 23), (7, 5, 16, 37), (19, 128, 256, 10000), (3, 130, 20, 300), (5, 9, 12, 1000)])
+@pytest.mark.parametrize("T1,B,H,V", [(4, 3, 8, 23), (7, 5, 16, 37), (19, 128, 256, 10000), (3, 130, 20, 300), (5, 9, 12, 1000), (6, 50, 64, 3001), (21, 128, 256, 10000)])
 def test_vocab_ce(lib, L, T1, B, H, V):
     rng = np.random.default_rng(T1 + B + V)
     N, T = T1 * B, T1 + 1
@@ -333,6 +367,12 @@ def test_vocab_ce(lib, L, T1, B, H, V):
     assert rel(d_h, dl @ W.astype(np.float64)) < 1e-4
     assert rel(d_w, dl.T @ hf) < 1e-4
     assert rel(d_b, dl.sum(0)) < 1e-4
+
+
+def test_vocab_ce_simt_path_matches_oracle_too(lib, L, monkeypatch):
+    """DVAE_GEMM_IMPL=simt forces the fp32 SIMT kernels on a shape the tensor-core path takes."""
+    monkeypatch.setenv("DVAE_GEMM_IMPL", "simt")
+    test_vocab_ce(lib, L, 19, 128, 256, 10000)
 
 
 # ---------------------------------------------------------------------------------------------
