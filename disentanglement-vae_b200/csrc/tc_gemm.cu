@@ -23,7 +23,8 @@ constexpr int BM = 128, BN = 128, BK = 32, STAGES = 3;
 constexpr int TILE_BYTES = BM * BK * 4;            // 16 KB
 constexpr int STAGE_BYTES = 4 * TILE_BYTES;        // A_hi, A_lo, B_hi, B_lo
 constexpr int NUM_THREADS = 192;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /* alignment slack */ + 256 /* barriers */;
+constexpr int EPI_SCRATCH_BYTES = 4 * 32 * 33 * 4;  // per epilogue warp: one padded 32x32 fp32 chunk (transpose for coalesced stores)
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /* alignment slack */ + 256 /* barriers */ + EPI_SCRATCH_BYTES;
 constexpr int TMEM_COLS = 128;
 
 struct Params {
@@ -40,6 +41,7 @@ struct Params {
   const int64_t* targets; int64_t tgt_stride_b; const int64_t* lengths; int B;
   float* part; int* part_idx;            // mode 1: [nsplit][M][4] (max, sumexp, target logit, argmax value), [nsplit][M]
   const float* lse; const float* grad_scale; int v0;   // mode 2: C = P[:, v0:v0+N]
+  unsigned long long* dbg;   // optional: pipeline milestone timestamps (ns) of CTA (0,0,0)
 };
 
 __device__ __forceinline__ uint32_t to_tf32(float x) {
@@ -48,10 +50,17 @@ __device__ __forceinline__ uint32_t to_tf32(float x) {
   return r;
 }
 
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define DBG_MARK(i) do { if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) p.dbg[i] = gtime(); } while (0)
+
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, Params p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t smem[];          // SWIZZLE_128B tiles need 1024-byte alignment
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
   uint64_t* full_raw = bars;
   uint64_t* full_split = bars + STAGES;
@@ -59,8 +68,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* tmem_full = bars + 3 * STAGES;
   uint64_t* tmem_empty = bars + 3 * STAGES + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * STAGES + 2);
+  float* epi_scratch = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 256);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) DBG_MARK(0);
   const int m0 = blockIdx.x * BM;
   const int nt0 = blockIdx.y * p.tiles_per_cta;
   const int n_tiles = (p.N + BN - 1) / BN;
@@ -88,6 +99,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (tid == 0) DBG_MARK(1);
 
   if (warp == 0) {
     // ===== TMA producer =====
@@ -112,6 +124,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int j = 0; j < BN / 32; ++j)
               tma_load_2d(st + 2 * TILE_BYTES + j * (BK * 128), &tmB, n0 + 32 * j, (kb0 + kb) * BK, &full_raw[stage]);
           }
+          if (nt == nt0 && kb == 0) DBG_MARK(2);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -136,6 +149,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(&full_split[stage], phase);
           tc_fence_after();
+          if (nt == nt0 && kb == 0) DBG_MARK(4);
           const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES), sb = sa + 2 * TILE_BYTES;
 #pragma unroll
           for (int k = 0; k < BK / 8; ++k) {
@@ -155,6 +169,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         tc_commit(tmem_full);
+        if (nt == nt0) DBG_MARK(5);
       }
     }
   } else {
@@ -180,19 +195,27 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int n0 = nt * BN;
       for (int kb = 0; kb < nkb; ++kb) {
         mbar_wait(&full_raw[stage], phase);
-        uint8_t* st = smem + stage * STAGE_BYTES;
-#pragma unroll 4
+        if (wtid == 0 && nt == nt0 && kb == 0) DBG_MARK(3);
+        const uint8_t* st = smem + stage * STAGE_BYTES;
+        // hi = x rounded to the nearest tf32 (add half an ulp to the bit pattern, clear the 13 low mantissa bits),
+        // lo = x - hi (exact in fp32; the tensor core keeps its leading 11 bits).  Pure integer/FADD work -- the
+        // conversion pipe (cvt.rna.tf32) is an order of magnitude slower at 16K elements per k-block.
+        const uint32_t st_u = smem_u32(st);
+#pragma unroll 8
         for (int i = 0; i < 2 * TILE_BYTES / 16 / 128; ++i) {
           const int idx = wtid + i * 128;                         // float4 index over [A tile | B tile]
-          uint8_t* q = st + (idx < TILE_BYTES / 16 ? 0 : TILE_BYTES) + idx * 16;
-          const float4 v = *reinterpret_cast<const float4*>(q);
+          const uint32_t q = st_u + (idx < TILE_BYTES / 16 ? 0 : TILE_BYTES) + idx * 16;
+          const uint4 v = lds128(q);
           uint4 hi, lo;
-          hi.x = to_tf32(v.x); hi.y = to_tf32(v.y); hi.z = to_tf32(v.z); hi.w = to_tf32(v.w);
-          *reinterpret_cast<uint4*>(q) = hi;
+          hi.x = (v.x + 0x1000u) & 0xFFFFE000u; hi.y = (v.y + 0x1000u) & 0xFFFFE000u;
+          hi.z = (v.z + 0x1000u) & 0xFFFFE000u; hi.w = (v.w + 0x1000u) & 0xFFFFE000u;
+          sts128(q, hi);
           if (p.passes == 3) {
-            lo.x = to_tf32(v.x - __uint_as_float(hi.x)); lo.y = to_tf32(v.y - __uint_as_float(hi.y));
-            lo.z = to_tf32(v.z - __uint_as_float(hi.z)); lo.w = to_tf32(v.w - __uint_as_float(hi.w));
-            *reinterpret_cast<uint4*>(q + TILE_BYTES) = lo;
+            lo.x = __float_as_uint(__uint_as_float(v.x) - __uint_as_float(hi.x));
+            lo.y = __float_as_uint(__uint_as_float(v.y) - __uint_as_float(hi.y));
+            lo.z = __float_as_uint(__uint_as_float(v.z) - __uint_as_float(hi.z));
+            lo.w = __float_as_uint(__uint_as_float(v.w) - __uint_as_float(hi.w));
+            sts128(q + TILE_BYTES, lo);
           }
         }
         fence_proxy_async();
@@ -204,33 +227,70 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       // ---- epilogue for this tile: accumulator row -> registers, 32 columns at a time ----
       mbar_wait(tmem_full, tile & 1);
       tc_fence_after();
+      if (wtid == 0 && nt == nt0) DBG_MARK(6);
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
         float v[32];
         tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + c * 32, v);
+        if (wtid == 0 && nt == nt0) DBG_MARK(9 + 3 * c);
         const int col0 = n0 + c * 32;
-        if (!row_ok || col0 >= p.N) continue;
-        if (p.mode == 0) {
-          float* crow = p.C + (int64_t)row * p.ldc + col0;
-          const bool split = gridDim.z > 1;
+        if (col0 >= p.N) continue;                       // warp-uniform
+        if (p.mode != 1) {
+          // modes 0 / 2 store a [32 rows x 32 cols] chunk: transpose it through padded shared memory so each
+          // store instruction covers 32 consecutive columns of one row (coalesced) instead of 32 different rows
+          const uint32_t sc = smem_u32(epi_scratch) + (warp - 2) * (32 * 33 * 4);
+          if (p.mode == 2) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            if (col0 + j < p.N) {
-              float x = v[j];
-              if (!split || blockIdx.z == 0) {
-                if (p.bias) x += __ldg(p.bias + col0 + j);
-                if (p.bias2) x += __ldg(p.bias2 + col0 + j);
-              }
-              if (split) {
-                atomicAdd(crow + j, x);        // C was pre-scaled by beta on the host side
+            for (int j = 0; j < 32; ++j) {
+              const int col = col0 + j;
+              v[j] = (row_scale == 0.f || col >= p.N) ? 0.f
+                     : (expf(v[j] + __ldg(p.bias + col) - row_lse) - (col == tgt ? 1.f : 0.f)) * row_scale;
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) sts32(sc + (lane * 33 + j) * 4, v[j]);
+          __syncwarp();
+          if (wtid == 0 && nt == nt0) DBG_MARK(10 + 3 * c);
+          const int col = col0 + lane;
+          const int r0 = m0 + quarter * 32;
+          const int nr = min(32, p.M - r0);              // valid rows of this warp's 32-row band
+          if (col < p.N && nr > 0) {
+            const bool split = gridDim.z > 1;
+            float badd = 0.f;
+            if (p.mode == 0 && (!split || blockIdx.z == 0)) {
+              if (p.bias) badd += __ldg(p.bias + col);
+              if (p.bias2) badd += __ldg(p.bias2 + col);
+            }
+            float* cp = p.C + (int64_t)r0 * p.ldc + col;
+            const int64_t ldc = p.ldc;
+            const uint32_t src = sc + lane * 4;
+            // all mode / flag decisions are hoisted: each variant is a tight LDS -> (op) -> coalesced STG loop
+            if (p.mode == 2 || (!split && p.act == 0 && p.beta == 0.f)) {
+              if (nr == 32) {
+#pragma unroll
+                for (int rr = 0; rr < 32; ++rr) cp[rr * ldc] = lds32(src + rr * 132) + badd;
               } else {
-                if (p.act == 1) x = tanhf(x);
-                if (p.beta != 0.f) x += p.beta * crow[j];
-                crow[j] = x;
+                for (int rr = 0; rr < nr; ++rr) cp[rr * ldc] = lds32(src + rr * 132) + badd;
+              }
+            } else if (split) {
+              for (int rr = 0; rr < nr; ++rr) atomicAdd(cp + rr * ldc, lds32(src + rr * 132) + badd);   // C pre-scaled by beta
+            } else {
+              const float beta = p.beta;
+              const bool do_tanh = p.act == 1;
+              for (int rr = 0; rr < nr; ++rr) {
+                float x = lds32(src + rr * 132) + badd;
+                if (do_tanh) x = tanhf(x);
+                if (beta != 0.f) x = fmaf(beta, cp[rr * ldc], x);
+                cp[rr * ldc] = x;
               }
             }
           }
-        } else if (p.mode == 1) {
+          __syncwarp();
+          if (wtid == 0 && nt == nt0) DBG_MARK(11 + 3 * c);
+          continue;
+        }
+        if (!row_ok) continue;
+        {
           // online log-softmax statistics of this row over the tile's columns (logits never leave registers)
           float tmax = -INFINITY;
 #pragma unroll
@@ -245,18 +305,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (tmax > rm) { rs *= expf(rm - tmax); rm = tmax; }
 #pragma unroll
           for (int j = 0; j < 32; ++j) rs += expf(v[j] - rm);
-        } else {
-          float* prow = p.C + (int64_t)row * p.ldc + col0;
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int col = col0 + j;
-            if (col < p.N) {
-              const float pr = row_scale == 0.f ? 0.f : (expf(v[j] + __ldg(p.bias + col) - row_lse) - (col == tgt ? 1.f : 0.f)) * row_scale;
-              prow[j] = pr;
-            }
-          }
         }
       }
+      if (wtid == 0 && nt == nt0) DBG_MARK(7);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tmem_empty);
@@ -269,6 +320,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+  if (tid == 0) DBG_MARK(8);
 }
 
 // ---- host ------------------------------------------------------------------------------------------
@@ -352,6 +404,7 @@ int tc_linear_impl(const float* A, int64_t lda, int trans_a, const float* B, int
   Params p = {};
   p.M = M; p.N = N; p.K = K; p.a_mn = trans_a ? 1 : 0; p.b_mn = trans_b ? 1 : 0; p.passes = passes; p.tiles_per_cta = 1;
   p.C = C; p.ldc = ldc; p.bias = bias; p.bias2 = bias2; p.beta = beta; p.act = act; p.mode = 0;
+  if (const char* e = getenv("DVAE_TC_DBG")) p.dbg = reinterpret_cast<unsigned long long*>(strtoull(e, nullptr, 0));
   // split-K when the output has too few tiles to occupy the 148 SMs and K is deep (weight-gradient shapes)
   const int tiles = ceil_div(M, BM) * ceil_div(N, BN), nkb = ceil_div(K, BK);
   int splits = 1;
