@@ -1,0 +1,29 @@
+"""Data-parallel helpers: the path shards over the batch dimension, one exchange per step.
+
+Every loss term of the reference is a batch mean (`vae/losses.py:155`, texar `average_across_batch`, BCE mean), so
+with equal shards   grad(global mean) = (1/world) * sum_r grad(mean over rank r's shard).
+Rank r takes rows r::world of the global batch -- a strided split keeps `RatioSampler`'s per-source ratio inside
+every shard because a batch is laid out [source 0 rows..., source 1 rows...] (`vae/data_utils.py:41-46`).
+"""
+import torch
+import torch.distributed as dist
+
+
+def shard_rows(n_rows, rank, world):
+    """Row indices of the global batch owned by `rank`."""
+    if n_rows % world != 0:
+        raise ValueError(f"global batch {n_rows} is not divisible by world size {world}")
+    return torch.arange(rank, n_rows, world)
+
+
+def shard_batch(inputs, lengths, labels, rank, world):
+    idx = shard_rows(inputs.size(0), rank, world)
+    return inputs[idx], lengths[idx], {k: v[idx] for k, v in labels.items()}
+
+
+def allreduce_mean_(flat, group=None):
+    """In-place average of a flat gradient buffer over the process group (SUM then 1/world)."""
+    world = dist.get_world_size(group)
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    flat.mul_(1.0 / world)
+    return flat
