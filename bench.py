@@ -68,7 +68,7 @@ class ClockSampler:
         try:
             self.f = open(self.path, "w")
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+                                          "-lms", "20"], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
 
@@ -196,7 +196,18 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL prints its version banner on stdout at first use: keep stdout clean for the ONE JSON line
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
 
     import __graft_entry__ as ge
     dvae = ge.build()
@@ -290,10 +301,10 @@ def main():
     flops = 2.0 * N * d.H * d.V
     tf = flops / (k_ms * 1e-3) / 1e12
     alg_bytes = 4.0 * (N * d.H + d.V * d.H + d.V + 2 * N)
-    roof = {"kernel": "vocab_ce_fwd_kernel (fused vocab projection + online log-softmax + NLL, fp32 SIMT this round)",
+    roof = {"kernel": "tc_gemm_kernel mode 1 = vocab-CE forward (TMA + tcgen05.mma.kind::tf32 3xTF32 + online log-softmax epilogue from TMEM; logits never in HBM)",
             "bound": "tensor", "achieved": tf, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": tf / peaks["bf16_tflops"],
             "peak_source": f"MEASURED_PEAKS.json bf16 burst ({peaks['src']})", "traffic": None,
-            "launch_ms": k_ms, "algorithmic_flops": flops, "algorithmic_bytes": alg_bytes,
+            "launch_ms": k_ms, "tensor_flops_executed": 3 * flops, "algorithmic_flops": flops, "algorithmic_bytes": alg_bytes,
             "hbm_frac": alg_bytes / (k_ms * 1e-3) / 1e9 / peaks["hbm_gbs"]}
     line = {"metric": "train_tokens_per_sec", "value": tok_sum / (dev_ms * 1e-3), "unit": "tokens/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps, "higher_is_better": True,

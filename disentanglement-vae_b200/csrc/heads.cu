@@ -15,7 +15,7 @@ int linear_impl(const float* A, int64_t lda, int trans_a, const float* B, int64_
                 cudaStream_t st);
 int colsum_impl(const float* X, int64_t ldx, int M, int N, float* out, float beta, cudaStream_t st);
 
-constexpr int kRows = 4;
+constexpr int kRows = 2;
 constexpr int kHeadsThreads = 256;
 constexpr int kMaxDscOut = 64;
 
@@ -73,20 +73,30 @@ __global__ void __launch_bounds__(kHeadsThreads) heads_fwd_kernel(HeadsFwdArgs a
     ctx_s[i] = (b0 + r < B) ? a.ctx[(int64_t)(b0 + r) * C + k] : 0.f;
   }
   __syncthreads();
-  // (mu, raw) projections: one warp per output column, lanes stride the context width
-  for (int j = warp; j < 2 * Z; j += nwarp) {
-    const float* w = a.w_c2p + (int64_t)j * C;
-    float acc[kRows] = {};
+  // (mu, raw) projections: each warp owns 4 output columns per pass (4 independent coalesced weight streams in
+  // flight per lane), lanes stride the context width, shuffle reduction
+  for (int j0 = warp * 4; j0 < 2 * Z; j0 += nwarp * 4) {
+    const int nj = min(4, 2 * Z - j0);
+    const float* w = a.w_c2p + (int64_t)j0 * C;
+    float acc[4][kRows] = {};
     for (int k = lane; k < C; k += 32) {
-      float wv = w[k];
+      float wv[4];
 #pragma unroll
-      for (int r = 0; r < kRows; ++r) acc[r] = fmaf(ctx_s[r * C + k], wv, acc[r]);
+      for (int q = 0; q < 4; ++q) wv[q] = q < nj ? w[(int64_t)q * C + k] : 0.f;
+#pragma unroll
+      for (int r = 0; r < kRows; ++r) {
+        const float c = ctx_s[r * C + k];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc[q][r] = fmaf(c, wv[q], acc[q][r]);
+      }
     }
 #pragma unroll
-    for (int r = 0; r < kRows; ++r) {
-      float v = warp_sum(acc[r]);
-      if (lane == 0) par_s[r * 2 * Z + j] = v + a.b_c2p[j];
-    }
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+      for (int r = 0; r < kRows; ++r) {
+        float v = warp_sum(acc[q][r]);
+        if (lane == 0 && q < nj) par_s[r * 2 * Z + j0 + q] = v + a.b_c2p[j0 + q];
+      }
   }
   __syncthreads();
   // reparameterisation + KL terms
@@ -120,16 +130,28 @@ __global__ void __launch_bounds__(kHeadsThreads) heads_fwd_kernel(HeadsFwdArgs a
     lg_s[i] = acc;
     if (b < B) a.dsc_logits[(int64_t)b * OD + od] = acc;
   }
-  // decoder initial state: hid = tanh(z . Wz^T + bz)
+  // decoder initial state: hid = tanh(z . Wz^T + bz); one thread per output column, vectorised weight row
   for (int j = tid; j < a.H2L; j += kHeadsThreads) {
     const float* w = a.w_z2h + (int64_t)j * Z;
     float acc[kRows];
 #pragma unroll
     for (int r = 0; r < kRows; ++r) acc[r] = a.b_z2h[j];
-    for (int k = 0; k < Z; ++k) {
-      float wv = w[k];
+    if ((Z & 3) == 0 && (reinterpret_cast<uintptr_t>(a.w_z2h) & 15) == 0) {
+      for (int k = 0; k < Z; k += 4) {
+        const float4 wv = *reinterpret_cast<const float4*>(w + k);
 #pragma unroll
-      for (int r = 0; r < kRows; ++r) acc[r] = fmaf(z_s[r * Z + k], wv, acc[r]);
+        for (int r = 0; r < kRows; ++r) {
+          const float* zr = z_s + r * Z + k;
+          acc[r] = fmaf(zr[0], wv.x, acc[r]); acc[r] = fmaf(zr[1], wv.y, acc[r]);
+          acc[r] = fmaf(zr[2], wv.z, acc[r]); acc[r] = fmaf(zr[3], wv.w, acc[r]);
+        }
+      }
+    } else {
+      for (int k = 0; k < Z; ++k) {
+        const float wv = w[k];
+#pragma unroll
+        for (int r = 0; r < kRows; ++r) acc[r] = fmaf(z_s[r * Z + k], wv, acc[r]);
+      }
     }
 #pragma unroll
     for (int r = 0; r < kRows; ++r)

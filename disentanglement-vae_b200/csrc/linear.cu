@@ -117,27 +117,48 @@ int linear_impl(const float* A, int64_t lda, int trans_a, const float* B, int64_
 #undef DVAE_DISPATCH
 }
 
-// out[n] = sum_m X[m][n]: one block per 32 columns, 32x8 threads, coalesced row reads.
+// out[n] (+)= sum_m X[m][n]: blocks of 32 columns x a slice of the rows (grid.y), 32x8 threads, coalesced row
+// reads; row slices combine with one atomicAdd per (column, slice) into the pre-scaled output.
 __global__ void colsum_kernel(const float* __restrict__ X, int64_t ldx, int M, int N, float* __restrict__ out,
-                              float beta) {
+                              int rows_per_block) {
   __shared__ float red[8][33];
-  int n = blockIdx.x * 32 + threadIdx.x;
-  float s = 0.f;
-  if (n < N)
-    for (int m = threadIdx.y; m < M; m += 8) s += X[(int64_t)m * ldx + n];
-  red[threadIdx.y][threadIdx.x] = s;
+  const int n = blockIdx.x * 32 + threadIdx.x;
+  const int m0 = blockIdx.y * rows_per_block, m1 = min(M, m0 + rows_per_block);
+  float s0 = 0.f, s1 = 0.f;
+  if (n < N) {
+    int m = m0 + threadIdx.y;
+    for (; m + 8 < m1; m += 16) { s0 += X[(int64_t)m * ldx + n]; s1 += X[(int64_t)(m + 8) * ldx + n]; }
+    if (m < m1) s0 += X[(int64_t)m * ldx + n];
+  }
+  red[threadIdx.y][threadIdx.x] = s0 + s1;
   __syncthreads();
   if (threadIdx.y == 0 && n < N) {
     float t = 0.f;
 #pragma unroll
     for (int i = 0; i < 8; ++i) t += red[i][threadIdx.x];
-    out[n] = (beta != 0.f ? beta * out[n] : 0.f) + t;
+    atomicAdd(out + n, t);
   }
+}
+
+__global__ void scale_vec_kernel(float* out, int N, float beta) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < N) out[i] *= beta;
 }
 
 int colsum_impl(const float* X, int64_t ldx, int M, int N, float* out, float beta, cudaStream_t st) {
   DVAE_REQUIRE(X && out && M > 0 && N > 0, "dvae_colsum: bad argument");
-  colsum_kernel<<<ceil_div(N, 32), dim3(32, 8), 0, st>>>(X, ldx, M, N, out, beta);
+  if (beta == 0.f) {
+    DVAE_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * N, st));
+  } else if (beta != 1.f) {
+    scale_vec_kernel<<<ceil_div(N, 256), 256, 0, st>>>(out, N, beta);
+    DVAE_LAUNCH_CHECK();
+  }
+  const int col_blocks = ceil_div(N, 32);
+  int row_blocks = ceil_div(2 * 148, col_blocks);                 // aim for ~2 CTAs per SM
+  if (row_blocks > ceil_div(M, 64)) row_blocks = ceil_div(M, 64);
+  if (row_blocks < 1) row_blocks = 1;
+  const int rows_per_block = ceil_div(M, row_blocks);
+  colsum_kernel<<<dim3(col_blocks, ceil_div(M, rows_per_block)), dim3(32, 8), 0, st>>>(X, ldx, M, N, out, rows_per_block);
   DVAE_LAUNCH_CHECK();
   return DVAE_OK;
 }

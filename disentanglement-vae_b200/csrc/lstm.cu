@@ -265,6 +265,8 @@ int lstm_seq_fwd_impl(const float* x, int64_t ldx, int T, int B, int I, int H, i
       a.gates = gates; a.cs = cs; a.hs = hs; a.ldhs = ldhs; a.h0 = h0; a.c0 = c0; a.ld0 = ld0; a.dir0 = dir0;
       a.hstate = ws; a.hn = hn; a.cn = cn; a.ldn = ldn; a.dirn = dirn; a.lengths = lengths;
       a.T = T; a.B = B; a.D = D; a.n_slices = ceil_div(B, 16); a.d_off = 0;
+      a.dbg = nullptr;
+      if (const char* e = getenv("DVAE_LSTM_DBG")) a.dbg = reinterpret_cast<unsigned long long*>(strtoull(e, nullptr, 0));
       return persist_fwd(H, a, st);
     }
   }

@@ -66,6 +66,13 @@ __device__ __forceinline__ void persist_gemm(const float* __restrict__ a_s, cons
   }
 }
 
+__device__ __forceinline__ unsigned long long gtime_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define LSTM_MARK(i) do { if (p.dbg && blockIdx.x == 0 && threadIdx.x == 0 && s == 6) p.dbg[i] = gtime_ns(); } while (0)
+
 __device__ __forceinline__ float4 ldcg4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
 
 
@@ -122,6 +129,7 @@ lstm_persist_fwd_kernel(PersistFwdArgs p) {
 
   for (int s = 0; s < T; ++s) {
     const int t = d == 0 ? s : T - 1 - s;
+    LSTM_MARK(0);
     // (1) prefetch the hoisted input projection for this thread's 4 units x 4 gates
     float4 pre[4];
     const int64_t gi = (((int64_t)d * T + t) * B + eb) * 4 * H + eu;
@@ -152,9 +160,11 @@ lstm_persist_fwd_kernel(PersistFwdArgs p) {
       }
     }
     __syncthreads();
+    LSTM_MARK(1);
     // (3) recurrent pre-activations of this CTA's gate columns
     persist_gemm<NCOLS, H, KPS>(a_s, w_s, part_s);
     __syncthreads();
+    LSTM_MARK(2);
     // (4) gates, cell update, outputs
     if (erow) {
       float gate[4][4];
@@ -198,7 +208,9 @@ lstm_persist_fwd_kernel(PersistFwdArgs p) {
       *reinterpret_cast<float4*>(p.hstate + ((s + 1) & 1) * state_stride + ((int64_t)d * B + eb) * H + eu) =
           make_float4(h_reg[0], h_reg[1], h_reg[2], h_reg[3]);
     }
+    LSTM_MARK(3);
     cluster.sync();      // barrier.cluster arrive.release / wait.acquire orders the global stores above
+    LSTM_MARK(4);
   }
   if (erow) {
     if (p.hn) *reinterpret_cast<float4*>(p.hn + d * p.dirn + (int64_t)eb * p.ldn + eu) = make_float4(h_reg[0], h_reg[1], h_reg[2], h_reg[3]);

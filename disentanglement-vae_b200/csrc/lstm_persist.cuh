@@ -12,6 +12,7 @@ struct PersistFwdArgs {
   float* hn; float* cn; int64_t ldn, dirn;
   const int64_t* lengths;
   int T, B, D, n_slices, d_off;
+  unsigned long long* dbg;   // optional per-step milestone timestamps (probes)
 };
 
 struct PersistBwdArgs {

@@ -416,8 +416,12 @@ int tc_linear_impl(const float* A, int64_t lda, int trans_a, const float* B, int
   p.kb_per_split = ceil_div(nkb, splits);
   splits = ceil_div(nkb, p.kb_per_split);
   if (splits > 1 && beta != 1.f) {
-    tc_scale_rows_kernel<<<ceil_div((int64_t)M * N, 256), 256, 0, st>>>(C, ldc, M, N, beta);
-    DVAE_LAUNCH_CHECK();
+    if (beta == 0.f && ldc == N) {
+      DVAE_CUDA(cudaMemsetAsync(C, 0, sizeof(float) * (size_t)M * N, st));
+    } else {
+      tc_scale_rows_kernel<<<ceil_div((int64_t)M * N, 256), 256, 0, st>>>(C, ldc, M, N, beta);
+      DVAE_LAUNCH_CHECK();
+    }
   }
   return launch(ma, mb, p, dim3(ceil_div(M, BM), ceil_div(N, BN), splits), st);
 }
