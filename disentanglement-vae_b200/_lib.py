@@ -34,9 +34,11 @@ SIGNATURES = {
     "dvae_tc_linear": (_i, [_p, _l, _i, _p, _l, _i, _p, _l, _i, _i, _i, _p, _p, _f, _i, _i, _p]),
     "dvae_colsum": (_i, [_p, _l, _i, _i, _p, _f, _p]),
     "dvae_randn": (_i, [_p, _l, _p, _u32, _p]),
-    "dvae_embedding_fwd": (_i, [_p, _i, _p, _l, _l, _i, _i, _f, _p, _u32, _l, _p, _p]),
-    "dvae_embedding_bwd": (_i, [_p, _i, _p, _l, _l, _i, _i, _f, _p, _u32, _l, _p, _p]),
-    "dvae_dropout": (_i, [_p, _l, _l, _i, _f, _p, _u32, _p, _l, _p]),
+    "dvae_embedding_fwd": (_i, [_p, _i, _p, _l, _l, _i, _i, _f, _p, _u32, _l, _i, _p, _p]),
+    "dvae_embedding_bwd": (_i, [_p, _i, _p, _l, _l, _i, _i, _f, _p, _u32, _l, _i, _p, _p]),
+    "dvae_dropout": (_i, [_p, _l, _l, _i, _f, _p, _u32, _p, _l, _l, _p]),
+    "dvae_lstm_step": (_i, [_p, _l, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _l, _p, _p, _p, _p, _p]),
+    "dvae_vocab_sample_step": (_i, [_p, _l, _i, _i, _i, _p, _p, _p, _u32, _p, _l, _p, _p]),
     "dvae_lstm_state_ws_floats": (_l, [_i, _i, _i]),
     "dvae_lstm_seq_fwd": (_i, [_p, _l, _i, _i, _i, _i, _i, _pp, _pp, _pp, _pp, _p, _p, _l, _l, _p, _p, _l, _p, _p,
                                _l, _l, _p, _p, _p, _p]),

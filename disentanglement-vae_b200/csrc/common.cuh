@@ -53,7 +53,7 @@ int tc_linear_impl(const float* A, int64_t lda, int trans_a, const float* B, int
                    cudaStream_t st);
 int tc_ce_partials(const float* h, int64_t ldh, int N, int B, int H, int V, const float* w, const float* bias,
                    const int64_t* targets, int64_t tgt_stride_b, const int64_t* lengths, int tiles_per_split, int nsplit,
-                   float* part, int* part_idx, cudaStream_t st);
+                   float* part, int* part_idx, const uint64_t* gumbel_seed, uint32_t gumbel_salt, cudaStream_t st);
 int tc_softmax_grad(const float* h, int64_t ldh, int N, int B, int H, int v0, int vc, const float* w, const float* bias,
                     const int64_t* targets, int64_t tgt_stride_b, const int64_t* lengths, const float* lse,
                     const float* grad_scale, float* P, int64_t ldp, cudaStream_t st);
@@ -95,6 +95,18 @@ __device__ __forceinline__ void dropout_scale4(uint64_t seed, uint32_t salt, uin
   // keep iff u >= p with u = r * 2^-32 in [0,1)
 #pragma unroll
   for (int i = 0; i < 4; ++i) s[i] = ((float)r[i] * 2.3283064365386963e-10f >= p) ? inv_keep : 0.f;
+}
+
+// Gumbel(0,1) noise for (row, col..col+3): one Philox call per 4 consecutive columns (col % 4 == 0).
+// u is a 24-bit uniform in (0,1) so the host can reproduce it exactly.  argmax_v(logit_v + g_v) ~ softmax(logits).
+__device__ __forceinline__ void gumbel4(uint64_t seed, uint32_t salt, int row, int col, int ncol4, float (&g)[4]) {
+  uint32_t r[4];
+  Philox::gen(seed, salt, (uint64_t)row * ncol4 + (col >> 2), r);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float u = ((float)(r[i] >> 8) + 0.5f) * (1.f / 16777216.f);
+    g[i] = -logf(-logf(u));
+  }
 }
 
 __device__ __forceinline__ float warp_sum(float v) {

@@ -10,13 +10,13 @@ constexpr int kSMs = 148;
 // x[t][b][:] = emb[tok(t,b)][:] * keep_scale ; one warp-quad of float4 lanes per row
 __global__ void embedding_fwd_kernel(const float* __restrict__ emb, int E, const int64_t* __restrict__ tokens,
                                      int64_t sb, int64_t st_, int T, int B, float p, const uint64_t* seed_dev,
-                                     uint32_t salt, int64_t first_token, float* __restrict__ x) {
+                                     uint32_t salt, int64_t first_token, int t0, float* __restrict__ x) {
   const int64_t total4 = (int64_t)T * B * ((E + 3) / 4);
   const uint64_t seed = (p > 0.f && seed_dev) ? *seed_dev : 0;
   const float inv_keep = p > 0.f ? 1.f / (1.f - p) : 1.f;
   const int e4n = (E + 3) / 4;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t row = i / e4n;
+    const int64_t row = i / e4n + (int64_t)t0 * B;      // absolute (t, b) row: the dropout counters match the full-sequence call
     const int e0 = (int)(i % e4n) * 4;
     const int t = (int)(row / B), b = (int)(row % B);
     const int64_t tok = (t == 0 && first_token >= 0) ? first_token : tokens[b * sb + t * st_];
@@ -32,13 +32,13 @@ __global__ void embedding_fwd_kernel(const float* __restrict__ emb, int E, const
 
 __global__ void embedding_bwd_kernel(const float* __restrict__ d_x, int E, const int64_t* __restrict__ tokens,
                                      int64_t sb, int64_t st_, int T, int B, float p, const uint64_t* seed_dev,
-                                     uint32_t salt, int64_t first_token, float* __restrict__ d_emb) {
+                                     uint32_t salt, int64_t first_token, int t0, float* __restrict__ d_emb) {
   const int e4n = (E + 3) / 4;
   const int64_t total4 = (int64_t)T * B * e4n;
   const uint64_t seed = (p > 0.f && seed_dev) ? *seed_dev : 0;
   const float inv_keep = p > 0.f ? 1.f / (1.f - p) : 1.f;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t row = i / e4n;
+    const int64_t row = i / e4n + (int64_t)t0 * B;      // absolute (t, b) row: the dropout counters match the full-sequence call
     const int e0 = (int)(i % e4n) * 4;
     const int t = (int)(row / B), b = (int)(row % B);
     const int64_t tok = (t == 0 && first_token >= 0) ? first_token : tokens[b * sb + t * st_];
@@ -56,13 +56,13 @@ __global__ void embedding_bwd_kernel(const float* __restrict__ d_x, int E, const
 }
 
 __global__ void dropout_kernel(const float* __restrict__ x, int64_t ldx, int64_t rows, int width, float p,
-                               const uint64_t* seed_dev, uint32_t salt, float* __restrict__ y, int64_t ldy) {
+                               const uint64_t* seed_dev, uint32_t salt, float* __restrict__ y, int64_t ldy, int64_t row0) {
   const int w4n = (width + 3) / 4;
   const int64_t total4 = rows * w4n;
   const uint64_t seed = (p > 0.f && seed_dev) ? *seed_dev : 0;
   const float inv_keep = p > 0.f ? 1.f / (1.f - p) : 1.f;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t row = i / w4n;
+    const int64_t row = i / w4n + row0;
     const int c0 = (int)(i % w4n) * 4;
     float s[4] = {1.f, 1.f, 1.f, 1.f};
     if (p > 0.f && seed_dev) dropout_scale4(seed, salt, (uint64_t)(row * w4n + c0 / 4), p, inv_keep, s);
@@ -173,25 +173,25 @@ static int ew_grid(int64_t work) {
 }
 
 extern "C" int dvae_embedding_fwd(const float* emb, int E, const int64_t* tokens, int64_t sb, int64_t st_, int T,
-                                  int B, float p, const uint64_t* seed_dev, uint32_t salt, int64_t first_token, float* x, void* stream) {
+                                  int B, float p, const uint64_t* seed_dev, uint32_t salt, int64_t first_token, int t0, float* x, void* stream) {
   DVAE_REQUIRE(emb && tokens && x && E > 0 && T > 0 && B > 0 && p >= 0.f && p < 1.f, "dvae_embedding_fwd: bad argument");
-  embedding_fwd_kernel<<<ew_grid((int64_t)T * B * ((E + 3) / 4)), 256, 0, (cudaStream_t)stream>>>(emb, E, tokens, sb, st_, T, B, p, seed_dev, salt, first_token, x);
+  embedding_fwd_kernel<<<ew_grid((int64_t)T * B * ((E + 3) / 4)), 256, 0, (cudaStream_t)stream>>>(emb, E, tokens, sb, st_, T, B, p, seed_dev, salt, first_token, t0, x);
   DVAE_LAUNCH_CHECK();
   return DVAE_OK;
 }
 
 extern "C" int dvae_embedding_bwd(const float* d_x, int E, const int64_t* tokens, int64_t sb, int64_t st_, int T,
-                                  int B, float p, const uint64_t* seed_dev, uint32_t salt, int64_t first_token, float* d_emb, void* stream) {
+                                  int B, float p, const uint64_t* seed_dev, uint32_t salt, int64_t first_token, int t0, float* d_emb, void* stream) {
   DVAE_REQUIRE(d_x && tokens && d_emb && E > 0 && T > 0 && B > 0 && p >= 0.f && p < 1.f, "dvae_embedding_bwd: bad argument");
-  embedding_bwd_kernel<<<ew_grid((int64_t)T * B * ((E + 3) / 4)), 256, 0, (cudaStream_t)stream>>>(d_x, E, tokens, sb, st_, T, B, p, seed_dev, salt, first_token, d_emb);
+  embedding_bwd_kernel<<<ew_grid((int64_t)T * B * ((E + 3) / 4)), 256, 0, (cudaStream_t)stream>>>(d_x, E, tokens, sb, st_, T, B, p, seed_dev, salt, first_token, t0, d_emb);
   DVAE_LAUNCH_CHECK();
   return DVAE_OK;
 }
 
 extern "C" int dvae_dropout(const float* x, int64_t ldx, int64_t rows, int width, float p, const uint64_t* seed_dev,
-                            uint32_t salt, float* y, int64_t ldy, void* stream) {
+                            uint32_t salt, float* y, int64_t ldy, int64_t row0, void* stream) {
   DVAE_REQUIRE(x && y && rows > 0 && width > 0 && p >= 0.f && p < 1.f, "dvae_dropout: bad argument");
-  dropout_kernel<<<ew_grid(rows * ((width + 3) / 4)), 256, 0, (cudaStream_t)stream>>>(x, ldx, rows, width, p, seed_dev, salt, y, ldy);
+  dropout_kernel<<<ew_grid(rows * ((width + 3) / 4)), 256, 0, (cudaStream_t)stream>>>(x, ldx, rows, width, p, seed_dev, salt, y, ldy, row0);
   DVAE_LAUNCH_CHECK();
   return DVAE_OK;
 }

@@ -396,7 +396,45 @@ int lstm_seq_bwd_impl(const float* x, int64_t ldx, int T, int B, int I, int H, i
   return DVAE_OK;
 }
 
+// One time step of one (uni-directional) layer on the full-sequence buffers: used by sampled decoding, where step
+// t+1's input token is only known after step t's vocabulary sample (vae/model.py:457-472).
+int lstm_step_impl(const float* x, int64_t ldx, int t, int T, int B, int I, int H, const float* w_ih, const float* w_hh,
+                   const float* b_ih, const float* b_hh, const float* h0, const float* c0, int64_t ld0, float* hs,
+                   float* gates, float* cs, float* ws, cudaStream_t st) {
+  DVAE_REQUIRE(x && w_ih && w_hh && hs && gates && cs && ws, "dvae_lstm_step: null pointer");
+  DVAE_REQUIRE(t >= 0 && t < T && B > 0 && I > 0 && H > 0, "dvae_lstm_step: bad shape");
+  int rc = linear_impl(x + (int64_t)t * B * ldx, ldx, 0, w_ih, I, 0, gates + (int64_t)t * B * 4 * H, 4 * H, B, 4 * H, I, b_ih, b_hh,
+                       0.f, 0, st);
+  if (rc) return rc;
+  const int64_t sf = (int64_t)B * H;
+  const float *h_in, *c_in;
+  if (t == 0) {
+    const int nthr = 256, nblk = ceil_div(sf, nthr);
+    copy_state_kernel<<<nblk, nthr, 0, st>>>(h0, ld0, 0, ws, H, sf, 1, B, H);
+    DVAE_LAUNCH_CHECK();
+    copy_state_kernel<<<nblk, nthr, 0, st>>>(c0, ld0, 0, ws + sf, H, sf, 1, B, H);
+    DVAE_LAUNCH_CHECK();
+    h_in = ws; c_in = ws + sf;
+  } else {
+    h_in = hs + (int64_t)(t - 1) * sf; c_in = cs + (int64_t)(t - 1) * sf;
+  }
+  FwdStepArgs a;
+  a.w_hh[0] = w_hh; a.w_hh[1] = w_hh;
+  a.gates = gates; a.cs = cs; a.hs = hs; a.ldhs = H; a.lengths = nullptr; a.T = T; a.B = B; a.H = H; a.s = t;
+  a.h_in = h_in; a.c_in = c_in; a.h_out = ws + 2 * sf; a.c_out = ws + 3 * sf;
+  lstm_step_fwd_kernel<<<dim3(ceil_div(H, 16), ceil_div(B, kStepRows), 1), kStepThreads, 0, st>>>(a);
+  DVAE_LAUNCH_CHECK();
+  return DVAE_OK;
+}
+
 }  // namespace dvae
+
+extern "C" int dvae_lstm_step(const float* x, int64_t ldx, int t, int T, int B, int I, int H, const float* w_ih,
+                              const float* w_hh, const float* b_ih, const float* b_hh, const float* h0, const float* c0,
+                              int64_t ld0, float* hs, float* gates, float* cs, float* state_ws, void* stream) {
+  return dvae::lstm_step_impl(x, ldx, t, T, B, I, H, w_ih, w_hh, b_ih, b_hh, h0, c0, ld0, hs, gates, cs, state_ws,
+                              (cudaStream_t)stream);
+}
 
 extern "C" int64_t dvae_lstm_state_ws_floats(int B, int H, int D) {
   return dvae::state_floats(B, H, D) + 4LL * D * H * H;

@@ -41,6 +41,7 @@ struct Params {
   const int64_t* targets; int64_t tgt_stride_b; const int64_t* lengths; int B;
   float* part; int* part_idx;            // mode 1: [nsplit][M][4] (max, sumexp, target logit, argmax value), [nsplit][M]
   const float* lse; const float* grad_scale; int v0;   // mode 2: C = P[:, v0:v0+N]
+  const uint64_t* gumbel_seed; uint32_t gumbel_salt;   // mode 1: when set, the arg-max is taken over logits + Gumbel noise (sampling)
   unsigned long long* dbg;   // optional: pipeline milestone timestamps (ns) of CTA (0,0,0)
 };
 
@@ -183,7 +184,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     int rai = 0x7fffffff, tgt = -1;
     if (p.mode != 0 && row_ok) {
       const int b = row % p.B, tpos = row / p.B + 1;
-      tgt = (int)p.targets[(int64_t)b * p.tgt_stride_b + tpos];
+      if (p.targets) tgt = (int)p.targets[(int64_t)b * p.tgt_stride_b + tpos];
       if (p.mode == 2) {
         row_lse = p.lse[row];
         row_scale = (tpos < p.lengths[b]) ? (p.grad_scale ? p.grad_scale[0] : 1.f) / (float)p.B : 0.f;
@@ -293,14 +294,22 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         {
           // online log-softmax statistics of this row over the tile's columns (logits never leave registers)
           float tmax = -INFINITY;
+          const bool sample = p.gumbel_seed != nullptr;
+          const uint64_t gseed = sample ? *p.gumbel_seed : 0;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int col = col0 + j;
-            float x = col < p.N ? v[j] + __ldg(p.bias + col) : -INFINITY;
-            v[j] = x;
-            tmax = fmaxf(tmax, x);
-            if (x > rav) { rav = x; rai = col; }         // columns ascend, so ties keep the first index
-            if (col == tgt) rt = x;
+          for (int j4 = 0; j4 < 32; j4 += 4) {
+            float g[4] = {0.f, 0.f, 0.f, 0.f};
+            if (sample) gumbel4(gseed, p.gumbel_salt, row, col0 + j4, (p.N + 3) >> 2, g);
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+              const int j = j4 + jj, col = col0 + j;
+              float x = col < p.N ? v[j] + __ldg(p.bias + col) : -INFINITY;
+              v[j] = x;
+              tmax = fmaxf(tmax, x);
+              const float xs = x + g[jj];
+              if (xs > rav) { rav = xs; rai = col; }       // columns ascend, so ties keep the first index
+              if (col == tgt) rt = x;
+            }
           }
           if (tmax > rm) { rs *= expf(rm - tmax); rm = tmax; }
 #pragma unroll
@@ -429,7 +438,7 @@ int tc_linear_impl(const float* A, int64_t lda, int trans_a, const float* B, int
 // vocab-CE forward: per-(row, vocabulary-split) partials (max, sumexp, target logit, argmax) for rows of h [N,H]
 int tc_ce_partials(const float* h, int64_t ldh, int N, int B, int H, int V, const float* w, const float* bias,
                    const int64_t* targets, int64_t tgt_stride_b, const int64_t* lengths, int tiles_per_split, int nsplit,
-                   float* part, int* part_idx, cudaStream_t st) {
+                   float* part, int* part_idx, const uint64_t* gumbel_seed, uint32_t gumbel_salt, cudaStream_t st) {
   CUtensorMap ma, mb;
   int rc = make_operand_maps(&ma, &mb, h, ldh, 0, w, H, 0, N, V, H);
   if (rc) return rc;
@@ -437,6 +446,7 @@ int tc_ce_partials(const float* h, int64_t ldh, int N, int B, int H, int V, cons
   p.M = N; p.N = V; p.K = H; p.passes = 3; p.tiles_per_cta = tiles_per_split; p.bias = bias; p.mode = 1;
   p.kb_per_split = ceil_div(H, BK);
   p.targets = targets; p.tgt_stride_b = tgt_stride_b; p.lengths = lengths; p.B = B; p.part = part; p.part_idx = part_idx;
+  p.gumbel_seed = gumbel_seed; p.gumbel_salt = gumbel_salt;
   return launch(ma, mb, p, dim3(ceil_div(N, BM), nsplit, 1), st);
 }
 

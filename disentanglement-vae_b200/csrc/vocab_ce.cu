@@ -29,6 +29,7 @@ struct CeArgs {
   int tiles_per_split, nsplit;
   float* part;      // [nsplit][N][4]: max, sumexp, target logit, argmax value
   int* part_idx;    // [nsplit][N]
+  const uint64_t* gumbel_seed; uint32_t gumbel_salt;   // sampling: arg-max over logits + Gumbel noise
 };
 
 __device__ __forceinline__ void merge_ms(float& m, float& s, float m2, float s2) {
@@ -51,7 +52,7 @@ __global__ void __launch_bounds__(GCE::NT) vocab_ce_fwd_kernel(CeArgs p) {
     rm[i] = -INFINITY; rs[i] = 0.f; rt[i] = 0.f; rav[i] = -INFINITY; rai[i] = 0x7fffffff;
     int n = m0 + GCE::row_of(ty, i);
     tgt[i] = -1;
-    if (n < p.N) tgt[i] = (int)p.targets[(int64_t)(n % p.B) * p.tgt_stride_b + (n / p.B) + 1];
+    if (n < p.N && p.targets) tgt[i] = (int)p.targets[(int64_t)(n % p.B) * p.tgt_stride_b + (n / p.B) + 1];
   }
   for (int vt = vt0; vt < vt1; ++vt) {
     const int n0 = vt * GCE::BN;
@@ -71,12 +72,26 @@ __global__ void __launch_bounds__(GCE::NT) vocab_ce_fwd_kernel(CeArgs p) {
 #pragma unroll
     for (int i = 0; i < GCE::TM; ++i) {
       float tmax = -INFINITY;
+      float gn[GCE::TN];
+#pragma unroll
+      for (int j = 0; j < GCE::TN; ++j) gn[j] = 0.f;
+      if (p.gumbel_seed) {
+        const uint64_t gseed = *p.gumbel_seed;
+        const int n = m0 + GCE::row_of(ty, i);
+#pragma unroll
+        for (int j4 = 0; j4 < GCE::TN; j4 += 4) {
+          float g[4];
+          gumbel4(gseed, p.gumbel_salt, n, cj[j4], (p.V + 3) >> 2, g);
+          gn[j4] = g[0]; gn[j4 + 1] = g[1]; gn[j4 + 2] = g[2]; gn[j4 + 3] = g[3];
+        }
+      }
 #pragma unroll
       for (int j = 0; j < GCE::TN; ++j) {
         float v = cj[j] < p.V ? acc[i][j] + bj[j] : -INFINITY;
         acc[i][j] = v;
         tmax = fmaxf(tmax, v);
-        if (v > rav[i] || (v == rav[i] && cj[j] < rai[i])) { rav[i] = v; rai[i] = cj[j]; }
+        const float vs = v + gn[j];
+        if (vs > rav[i] || (vs == rav[i] && cj[j] < rai[i])) { rav[i] = vs; rai[i] = cj[j]; }
         if (cj[j] == tgt[i]) rt[i] = v;
       }
       if (tmax > rm[i]) { rs[i] *= expf(rm[i] - tmax); rm[i] = tmax; }
@@ -145,6 +160,20 @@ __global__ void __launch_bounds__(1024) vocab_ce_finalize_kernel(CeArgs p, float
   }
 }
 
+// sampled token per row = arg-max over the vocabulary splits of (logit + Gumbel noise)
+__global__ void vocab_sample_finalize_kernel(CeArgs p, int64_t* tokens, int64_t tok_stride) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= p.N) return;
+  float av = -INFINITY;
+  int ai = 0x7fffffff;
+  for (int sp = 0; sp < p.nsplit; ++sp) {
+    const float q = p.part[((int64_t)sp * p.N + n) * 4 + 3];
+    const int qi = p.part_idx[(int64_t)sp * p.N + n];
+    if (q > av || (q == av && qi < ai)) { av = q; ai = qi; }
+  }
+  tokens[(int64_t)n * tok_stride] = ai;
+}
+
 // P[n][v - v0] = (softmax(logits[n])[v] - [v == target_n]) * mask_n * scale / B for v in [v0, v0+vc)
 struct PArgs {
   const float* h; int64_t ldh;
@@ -184,6 +213,17 @@ __global__ void __launch_bounds__(GCE::NT) vocab_p_kernel(PArgs p) {
       p.P[(int64_t)n * p.ldp + (v - p.v0)] = pr;
     }
   }
+}
+
+// per-(row, vocabulary split) partials: tensor-core kernel when the shape allows, fp32 SIMT otherwise
+static int ce_partials(const CeArgs& p, cudaStream_t st) {
+  if (!force_simt_gemm() && p.N >= 64 && p.V >= 128 && p.H >= 32 && tc::tc_linear_supported(p.h, p.ldh, p.w, p.H, p.N, p.V, p.H))
+    return tc::tc_ce_partials(p.h, p.ldh, p.N, p.B, p.H, p.V, p.w, p.bias, p.targets, p.tgt_stride_b, p.lengths,
+                              p.tiles_per_split, p.nsplit, p.part, p.part_idx, p.gumbel_seed, p.gumbel_salt, st);
+  dim3 grid(ceil_div(p.N, GCE::BM), p.nsplit);
+  vocab_ce_fwd_kernel<<<grid, GCE::NT, 0, st>>>(p);
+  DVAE_LAUNCH_CHECK();
+  return DVAE_OK;
 }
 
 static int ce_nsplit(int N, int V, int* tiles_per_split) {
@@ -229,16 +269,8 @@ extern "C" int dvae_vocab_ce_fwd(const float* h, int64_t ldh, int T1, int B, int
   p.nsplit = ce_nsplit(p.N, V, &p.tiles_per_split);
   p.part = ws;
   p.part_idx = reinterpret_cast<int*>(ws + (int64_t)p.nsplit * p.N * 4);
-  if (!force_simt_gemm() && p.N >= 64 && V >= 128 && H >= 32 && tc::tc_linear_supported(h, ldh, w, H, p.N, V, H)) {
-    // tensor-core path: same (row tile, vocabulary split) decomposition and partials format
-    int rc = tc::tc_ce_partials(h, ldh, p.N, B, H, V, w, bias, targets, tgt_stride_b, lengths, p.tiles_per_split, p.nsplit,
-                                p.part, p.part_idx, st);
-    if (rc) return rc;
-  } else {
-    dim3 grid(ceil_div(p.N, GCE::BM), p.nsplit);
-    vocab_ce_fwd_kernel<<<grid, GCE::NT, 0, st>>>(p);
-    DVAE_LAUNCH_CHECK();
-  }
+  p.gumbel_seed = nullptr; p.gumbel_salt = 0;
+  { int rc = ce_partials(p, st); if (rc) return rc; }
   vocab_ce_finalize_kernel<<<1, 1024, 0, st>>>(p, lse, nll, argmax, loss);
   DVAE_LAUNCH_CHECK();
   return DVAE_OK;
@@ -277,5 +309,25 @@ extern "C" int dvae_vocab_ce_bwd(const float* h, int64_t ldh, int T1, int B, int
     if ((rc = linear_impl(ws, vc_max, 1, h, ldh, 1, d_w + (int64_t)v0 * H, H, vc, H, N, nullptr, nullptr, 0.f, 0, st))) return rc;
     if ((rc = colsum_impl(ws, vc_max, N, vc, d_bias + v0, 0.f, st))) return rc;
   }
+  return DVAE_OK;
+}
+
+extern "C" int dvae_vocab_sample_step(const float* h, int64_t ldh, int B, int H, int V, const float* w, const float* bias,
+                                      const uint64_t* seed_dev, uint32_t salt, int64_t* tokens_out, int64_t tok_stride,
+                                      float* ws, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  DVAE_REQUIRE(h && w && bias && seed_dev && tokens_out && ws, "dvae_vocab_sample_step: null pointer");
+  DVAE_REQUIRE(B > 0 && H > 0 && V > 0, "dvae_vocab_sample_step: bad shape");
+  CeArgs p;
+  p.h = h; p.ldh = ldh; p.w = w; p.bias = bias; p.targets = nullptr; p.tgt_stride_b = 0; p.lengths = nullptr;
+  p.N = B; p.B = B; p.H = H; p.V = V; p.sos = 0;
+  p.nsplit = ce_nsplit(p.N, V, &p.tiles_per_split);
+  p.part = ws;
+  p.part_idx = reinterpret_cast<int*>(ws + (int64_t)p.nsplit * p.N * 4);
+  p.gumbel_seed = seed_dev; p.gumbel_salt = salt;
+  int rc = ce_partials(p, st);
+  if (rc) return rc;
+  vocab_sample_finalize_kernel<<<ceil_div(B, 128), 128, 0, st>>>(p, tokens_out, tok_stride);
+  DVAE_LAUNCH_CHECK();
   return DVAE_OK;
 }

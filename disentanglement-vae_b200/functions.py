@@ -40,10 +40,15 @@ def _param_list(model):
 class _EncDecFn(Function):
     @staticmethod
     def forward(ctx, model, plan, inputs, lengths, eps, dec_tokens, first_token, train, *params):
+        """`first_token`: int = <SOS> id for the teacher-forced whole-sequence decoder; a tuple of per-step
+        coins = sampled decoding (sampling.py), where dec_tokens is the [B,T] prediction buffer."""
         P = model._P
         plan.encode(P, inputs, lengths, train)
         plan.heads(P, plan.ctx, eps, None, None)
-        plan.decode_forced(P, dec_tokens, first_token, train)
+        if isinstance(first_token, tuple):
+            plan.decode_sampled(P, dec_tokens, first_token, train)
+        else:
+            plan.decode_forced(P, dec_tokens, first_token, train)
         ctx.model, ctx.plan, ctx.token = model, plan, _PlanToken(plan)
         ctx.inputs, ctx.lengths, ctx.eps = inputs, lengths, eps
         S = plan.d.S

@@ -19,7 +19,7 @@ import torch
 from . import _lib
 from ._lib import ptr, ptr_array, int_array, check
 
-SALT_ENC_EMB, SALT_DEC_EMB, SALT_ENC_LAYER, SALT_DEC_LAYER, SALT_EPS = 1, 3, 16, 32, 64
+SALT_ENC_EMB, SALT_DEC_EMB, SALT_ENC_LAYER, SALT_DEC_LAYER, SALT_EPS, SALT_SAMPLE = 1, 3, 16, 32, 64, 4096
 
 
 class Dims:
@@ -87,6 +87,7 @@ class StepPlan:
         self.argmax = torch.zeros(max(self.N, 1), device=device, dtype=torch.int32)
         self.recon = self.out[_lib.HEADS_NSCALARS:_lib.HEADS_NSCALARS + 1]
         self.ce_ws = buf(self.lib.dvae_vocab_ce_ws_floats(max(self.N, 1), d.V))
+        self.sample_ws = None                      # allocated on first sampled decode
         self._bwd_ready = False
         self.seed_dev = torch.zeros(1, device=device, dtype=torch.int64)
         self.labels = buf(max(sum(1 for o in d.dsc_out if o > 0), 1), B)
@@ -127,7 +128,7 @@ class StepPlan:
         B, T = self.B, self.T
         p = d.p_enc if train else 0.0
         check(lib.dvae_embedding_fwd(ptr(P["encoder.embedding.weight"]), d.E, ptr(inputs), inputs.stride(0),
-                                     inputs.stride(1), T, B, p, ptr(self.seed_dev), SALT_ENC_EMB, -1,
+                                     inputs.stride(1), T, B, p, ptr(self.seed_dev), SALT_ENC_EMB, -1, 0,
                                      ptr(self.x_enc), st), "dvae_embedding_fwd")
         x, I = self.x_enc, d.E
         for l in range(d.Le):
@@ -135,7 +136,7 @@ class StepPlan:
                 I = d.D * d.H
                 if p > 0.0:
                     check(lib.dvae_dropout(ptr(self.e_hs[l - 1]), I, T * B, I, p, ptr(self.seed_dev),
-                                           SALT_ENC_LAYER + l, ptr(self.e_xin[l]), I, st), "dvae_dropout")
+                                           SALT_ENC_LAYER + l, ptr(self.e_xin[l]), I, 0, st), "dvae_dropout")
                     x = self.e_xin[l]
                 else:
                     x = self.e_hs[l - 1]
@@ -167,7 +168,7 @@ class StepPlan:
         hid = self.hid if hid is None else hid
         p = d.p_dec if train else 0.0
         check(lib.dvae_embedding_fwd(ptr(P["decoder.embedding.weight"]), d.E, ptr(tokens), tokens.stride(0),
-                                     tokens.stride(1), T1, B, p, ptr(self.seed_dev), SALT_DEC_EMB, first_token,
+                                     tokens.stride(1), T1, B, p, ptr(self.seed_dev), SALT_DEC_EMB, first_token, 0,
                                      ptr(self.x_dec), st), "dvae_embedding_fwd")
         x, I = self.x_dec, d.E
         for l in range(d.Ld):
@@ -175,7 +176,7 @@ class StepPlan:
                 I = d.H
                 if p > 0.0:
                     check(lib.dvae_dropout(ptr(self.d_hs[l - 1]), I, T1 * B, I, p, ptr(self.seed_dev),
-                                           SALT_DEC_LAYER + l, ptr(self.d_xin[l]), I, st), "dvae_dropout")
+                                           SALT_DEC_LAYER + l, ptr(self.d_xin[l]), I, 0, st), "dvae_dropout")
                     x = self.d_xin[l]
                 else:
                     x = self.d_hs[l - 1]
@@ -187,6 +188,51 @@ class StepPlan:
                                         ptr(self.state_ws), st), "dvae_lstm_seq_fwd(dec)")
         self._dec_p = p
         self._dec_tokens, self._dec_first = tokens, first_token
+        self._dec_hid = hid
+        return self.d_hs[-1]
+
+    def decode_sampled(self, P, preds, coins, train, hid=None):
+        """a6 / a12 with sampled inputs (vae/model.py:457-472,498-508).  `preds` [B,T] int64 is both the
+        decoder-input buffer and the returned `token_predictions`: preds[:,0] = <SOS>, preds[:,i] = the forced
+        token (pre-filled by the caller) when coins[i-1] is true, else the token sampled from position i's
+        logits, which is written here by the sampling kernel before step i reads it.  Leaves x_dec / d_gates /
+        d_cs / d_hs exactly as a whole-sequence call would, so decode_bwd / vocab_ce are shared."""
+        lib, d, st = self.lib, self.d, _lib.stream_ptr()
+        B, T1 = self.B, self.T1
+        hid = self.hid if hid is None else hid
+        p = d.p_dec if train else 0.0
+        if self.sample_ws is None:
+            self.sample_ws = torch.empty(lib.dvae_vocab_ce_ws_floats(B, d.V), device=self.device, dtype=torch.float32)
+        emb = P["decoder.embedding.weight"]
+        W = [self._dec_w(P, l) for l in range(d.Ld)]
+        for s in range(T1):
+            check(lib.dvae_embedding_fwd(ptr(emb), d.E, ptr(preds), preds.stride(0), preds.stride(1), 1, B, p,
+                                         ptr(self.seed_dev), SALT_DEC_EMB, d.sos, s, ptr(self.x_dec), st),
+                  "dvae_embedding_fwd(step)")
+            x, I = self.x_dec, d.E
+            for l in range(d.Ld):
+                if l > 0:
+                    I = d.H
+                    if p > 0.0:
+                        check(lib.dvae_dropout(ptr(self.d_hs[l - 1]), I, B, I, p, ptr(self.seed_dev),
+                                               SALT_DEC_LAYER + l, ptr(self.d_xin[l]), I, s * B, st), "dvae_dropout(step)")
+                        x = self.d_xin[l]
+                    else:
+                        x = self.d_hs[l - 1]
+                w_ih, w_hh, b_ih, b_hh = W[l]
+                check(lib.dvae_lstm_step(ptr(x), I, s, T1, B, I, d.H, ptr(w_ih[0]), ptr(w_hh[0]), ptr(b_ih[0]),
+                                         ptr(b_hh[0]), hid.data_ptr() + 4 * l * d.H,
+                                         hid.data_ptr() + 4 * (d.Ld + l) * d.H, d.H2L, ptr(self.d_hs[l]),
+                                         ptr(self.d_gates[l]), ptr(self.d_cs[l]), ptr(self.state_ws), st),
+                      "dvae_lstm_step")
+            if not coins[s]:
+                h_s = self.d_hs[-1].data_ptr() + 4 * s * B * d.H
+                check(lib.dvae_vocab_sample_step(h_s, d.H, B, d.H, d.V, ptr(P["decoder.linear.weight"]),
+                                                 ptr(P["decoder.linear.bias"]), ptr(self.seed_dev), SALT_SAMPLE + s,
+                                                 preds.data_ptr() + 8 * (s + 1) * preds.stride(1), preds.stride(0),
+                                                 ptr(self.sample_ws), st), "dvae_vocab_sample_step")
+        self._dec_p = p
+        self._dec_tokens, self._dec_first = preds, d.sos
         self._dec_hid = hid
         return self.d_hs[-1]
 
@@ -236,12 +282,12 @@ class StepPlan:
                                         ptr(self.state_ws), st), "dvae_lstm_seq_bwd(dec)")
             if l > 0 and p > 0.0:
                 check(lib.dvae_dropout(ptr(g_out), I, T1 * B, I, p, ptr(self.seed_dev), SALT_DEC_LAYER + l,
-                                       ptr(g_out), I, st), "dvae_dropout(bwd)")
+                                       ptr(g_out), I, 0, st), "dvae_dropout(bwd)")
             g_in = g_out
         if emb_grad:
             tok = self._dec_tokens
             check(lib.dvae_embedding_bwd(ptr(g_in), d.E, ptr(tok), tok.stride(0), tok.stride(1), T1, B, p,
-                                         ptr(self.seed_dev), SALT_DEC_EMB, self._dec_first,
+                                         ptr(self.seed_dev), SALT_DEC_EMB, self._dec_first, 0,
                                          ptr(G["decoder.embedding.weight"]), st), "dvae_embedding_bwd")
         return self.g_hid
 
@@ -280,11 +326,11 @@ class StepPlan:
                                         ptr(self.state_ws), st), "dvae_lstm_seq_bwd(enc)")
             if l > 0 and p > 0.0:
                 check(lib.dvae_dropout(ptr(g_out), I, T * B, I, p, ptr(self.seed_dev), SALT_ENC_LAYER + l,
-                                       ptr(g_out), I, st), "dvae_dropout(bwd)")
+                                       ptr(g_out), I, 0, st), "dvae_dropout(bwd)")
             g_in = g_out
         if emb_grad:
             check(lib.dvae_embedding_bwd(ptr(g_in), d.E, ptr(inputs), inputs.stride(0), inputs.stride(1), T, B, p,
-                                         ptr(self.seed_dev), SALT_ENC_EMB, -1, ptr(G["encoder.embedding.weight"]),
+                                         ptr(self.seed_dev), SALT_ENC_EMB, -1, 0, ptr(G["encoder.embedding.weight"]),
                                          st), "dvae_embedding_bwd")
 
     def randn_eps(self):

@@ -73,18 +73,22 @@ int dvae_colsum(const float* X, int64_t ldx, int M, int N, float* out, float bet
  * `dvae_embedding_bwd` scatter-ADDS d_x (masked the same way) into d_emb [V, E].
  * first_token >= 0 replaces the token at t == 0 for every row (the decoder is always fed <SOS>
  * first, vae/model.py:445-447, then inputs[:, t] under teacher forcing, model.py:464-466).
+ * t0 / row0: the call covers time steps [t0, t0+T) (rows [row0, row0+rows)) of buffers addressed by ABSOLUTE
+ * step / row, so a single decode step uses the same dropout counters as the full-sequence call (and the
+ * full-sequence backward regenerates the same masks).
  * `dvae_randn` fills out[n] with N(0,1) draws (Philox + Box-Muller): the reparameterisation
  * noise of vae/model.py:392-395 when the caller does not supply it.
  * ------------------------------------------------------------------------------------------- */
 int dvae_randn(float* out, int64_t n, const uint64_t* seed_dev, uint32_t salt, void* stream);
 int dvae_embedding_fwd(const float* emb, int E, const int64_t* tokens, int64_t tok_stride_b,
                        int64_t tok_stride_t, int T, int B, float p, const uint64_t* seed_dev,
-                       uint32_t salt, int64_t first_token, float* x, void* stream);
+                       uint32_t salt, int64_t first_token, int t0, float* x, void* stream);
 int dvae_embedding_bwd(const float* d_x, int E, const int64_t* tokens, int64_t tok_stride_b,
                        int64_t tok_stride_t, int T, int B, float p, const uint64_t* seed_dev,
-                       uint32_t salt, int64_t first_token, float* d_emb, void* stream);
+                       uint32_t salt, int64_t first_token, int t0, float* d_emb, void* stream);
 int dvae_dropout(const float* x, int64_t ldx, int64_t rows, int width, float p,
-                 const uint64_t* seed_dev, uint32_t salt, float* y, int64_t ldy, void* stream);
+                 const uint64_t* seed_dev, uint32_t salt, float* y, int64_t ldy, int64_t row0,
+                 void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * One LSTM layer (1 or 2 directions) over a padded, time-major batch.  Replaces nn.LSTM inside
@@ -111,6 +115,16 @@ int dvae_lstm_seq_fwd(const float* x, int64_t ldx, int T, int B, int I, int H, i
                       const int64_t* lengths, float* hs, int64_t ldhs, float* hn, float* cn,
                       int64_t ldn, int64_t dirn, float* gates, float* cs, float* state_ws,
                       void* stream);
+
+/* One time step t of one uni-directional layer, operating on the full-sequence buffers of dvae_lstm_seq_fwd
+ * (x [T,B,I], hs [T,B,H], gates [1,T,B,4H], cs [1,T,B,H]).  Sampled decoding (teacher_forcing_prob < 1, sample();
+ * vae/model.py:457-472,498-508) needs step t's vocabulary sample before step t+1's input exists, so the decoder
+ * advances one step per call; the buffers end up exactly as after a whole-sequence call, so the backward pass
+ * (dvae_lstm_seq_bwd) is shared.  h0/c0 (row stride ld0, NULL = zeros) are read at t == 0. */
+int dvae_lstm_step(const float* x, int64_t ldx, int t, int T, int B, int I, int H, const float* w_ih,
+                   const float* w_hh, const float* b_ih, const float* b_hh, const float* h0,
+                   const float* c0, int64_t ld0, float* hs, float* gates, float* cs, float* state_ws,
+                   void* stream);
 
 /* Back-propagation through time for dvae_lstm_seq_fwd (the autograd of nn.LSTM).
  *   d_hs [T,B,D*H] (row stride lddhs) or NULL; d_hn, d_cn as hn/cn or NULL.
@@ -202,6 +216,15 @@ int dvae_vocab_ce_fwd(const float* h, int64_t ldh, int T1, int B, int H, int V, 
                       const float* bias, const int64_t* targets, int64_t tgt_stride_b,
                       const int64_t* lengths, int sos, float* lse, float* nll, int32_t* argmax,
                       float* loss, float* ws, void* stream);
+
+/* Sampled next token per row without materialising [B,V] logits or probabilities: replaces
+ * decoder.linear + torch.softmax + torch.multinomial (vae/model.py:164,468-469,504-505).
+ * tokens_out[b*tok_stride] = argmax_v( h[b].w[v] + bias[v] + g(b,v) ), g ~ Gumbel(0,1) from Philox keyed by
+ * (*seed_dev, salt, b, v) -- the Gumbel-max trick: the arg-max is distributed as softmax(logits).
+ *   ws: dvae_vocab_ce_ws_floats(B, V) floats. */
+int dvae_vocab_sample_step(const float* h, int64_t ldh, int B, int H, int V, const float* w,
+                           const float* bias, const uint64_t* seed_dev, uint32_t salt, int64_t* tokens_out,
+                           int64_t tok_stride, float* ws, void* stream);
 
 /* Backward: d_h [N,H], d_w [V,H], d_bias [V] (all overwritten) for d(loss) = grad_scale_dev[0]
  * (NULL = 1).  Softmax tiles are recomputed from h, w and the saved lse.

@@ -409,14 +409,14 @@ def test_embedding_dropout_roundtrip(lib, L):
     seed = torch.tensor([1234567], device="cuda", dtype=torch.int64)
     x0 = torch.zeros(T, B, E, device="cuda")
     st = L.stream_ptr()
-    L.check(lib.dvae_embedding_fwd(L.ptr(embd), E, L.ptr(tokd), T + 3, 1, T, B, 0.0, None, 1, 2, L.ptr(x0), st), "emb")
+    L.check(lib.dvae_embedding_fwd(L.ptr(embd), E, L.ptr(tokd), T + 3, 1, T, B, 0.0, None, 1, 2, 0, L.ptr(x0), st), "emb")
     want = emb[tok[:, :T].T]
     want[0] = emb[2]
     assert np.array_equal(x0.cpu().numpy(), want)
     x1 = torch.zeros_like(x0)
     x2 = torch.zeros_like(x0)
     for x in (x1, x2):
-        L.check(lib.dvae_embedding_fwd(L.ptr(embd), E, L.ptr(tokd), T + 3, 1, T, B, 0.5, L.ptr(seed), 1, 2, L.ptr(x), st), "emb")
+        L.check(lib.dvae_embedding_fwd(L.ptr(embd), E, L.ptr(tokd), T + 3, 1, T, B, 0.5, L.ptr(seed), 1, 2, 0, L.ptr(x), st), "emb")
     assert torch.equal(x1, x2)                      # same seed -> same mask
     mask = (x1 != 0)
     assert torch.allclose(x1[mask], 2.0 * x0[mask])
@@ -424,12 +424,16 @@ def test_embedding_dropout_roundtrip(lib, L):
     assert 0.4 < keep < 0.6
     # dense dropout uses the same counter layout -> same mask for the same (seed, salt, shape)
     y = torch.zeros_like(x0)
-    L.check(lib.dvae_dropout(L.ptr(x0), E, T * B, E, 0.5, L.ptr(seed), 1, L.ptr(y), E, st), "dropout")
+    L.check(lib.dvae_dropout(L.ptr(x0), E, T * B, E, 0.5, L.ptr(seed), 1, L.ptr(y), E, 0, st), "dropout")
+    # a single-step call (t0 = 2, T = 1) reproduces that slice of the full-sequence call bit for bit
+    x3 = torch.zeros_like(x0)
+    L.check(lib.dvae_embedding_fwd(L.ptr(embd), E, L.ptr(tokd), T + 3, 1, 1, B, 0.5, L.ptr(seed), 1, 2, 2, L.ptr(x3), st), "emb")
+    assert torch.equal(x3[2], x1[2]) and float(x3[3:].abs().max()) == 0
     assert torch.equal(y, x1)
     # backward scatter-add with the same mask
     d_x = dev(rng.standard_normal((T, B, E)).astype(np.float32))
     d_emb = torch.zeros(V, E, device="cuda")
-    L.check(lib.dvae_embedding_bwd(L.ptr(d_x), E, L.ptr(tokd), T + 3, 1, T, B, 0.5, L.ptr(seed), 1, 2, L.ptr(d_emb), st), "emb bwd")
+    L.check(lib.dvae_embedding_bwd(L.ptr(d_x), E, L.ptr(tokd), T + 3, 1, T, B, 0.5, L.ptr(seed), 1, 2, 0, L.ptr(d_emb), st), "emb bwd")
     want = np.zeros((V, E))
     toks = tok[:, :T].T.copy()
     toks[0] = 2

@@ -207,7 +207,7 @@ def test_dropout_train_step_matches_oracle_with_replayed_masks(dvae):
     def mask(rows, width, salt):
         ones = torch.ones(rows, width, device="cuda")
         y = torch.zeros_like(ones)
-        L_.check(lib.dvae_dropout(L_.ptr(ones), width, rows, width, 0.5, L_.ptr(plan.seed_dev), salt, L_.ptr(y), width,
+        L_.check(lib.dvae_dropout(L_.ptr(ones), width, rows, width, 0.5, L_.ptr(plan.seed_dev), salt, L_.ptr(y), width, 0,
                                   L_.stream_ptr()), "dropout")
         return y.cpu().numpy().astype(np.float64)
 

@@ -1,0 +1,214 @@
+"""Sampled decoding (vae/model.py:463-472 teacher_forcing_prob < 1, :484-512 sample()) through the C ABI.
+
+The reference's `torch.multinomial` stream cannot be reproduced, so parity is established through
+(a) host replay of the kernel's Philox/Gumbel noise: token == argmax(logits64 + noise) exactly (away from ties),
+(b) a chi-square style frequency check that the draws follow softmax(logits),
+(c) the oracle run teacher-forced on the tokens the kernel sampled: loss and all gradients must match, which also
+    proves the step-by-step decoder leaves the same buffers as the whole-sequence kernels.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import dvae_oracle as O
+from oracle import philox
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _need_cuda():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+
+
+def _params(**over):
+    p = dict(bow_encoder=False, embedding_dim=32, hidden_dim=32, num_rnn_layers=2, encoder_dropout=0.0,
+             decoder_dropout=0.0, bidirectional_encoder=True, latent_dims={"total": 8, "polarity": 1},
+             adversarial_loss=False, mi_loss=False)
+    p.update(over)
+    return p
+
+
+def _synthetic(B, T, V, gen):
+    lengths = torch.randint(3, T + 1, (B,), generator=gen)
+    lengths[0] = T
+    X = torch.zeros(B, T, dtype=torch.long)
+    for b in range(B):
+        n = int(lengths[b])
+        X[b, 0], X[b, n - 1] = 2, 3
+        X[b, 1:n - 1] = torch.randint(4, V, (n - 2,), generator=gen)
+    Y = {"polarity": (torch.rand(B, 1, generator=gen) < 0.3).float()}
+    return X, lengths, Y
+
+
+def test_device_philox_matches_host_replica(dvae):
+    """The dropout mask the kernels derive from Philox equals the numpy replica bit for bit."""
+    L = dvae._lib
+    lib = L.load()
+    rows, width, seed, salt = 37, 50, 987654321012345, 19
+    ones = torch.ones(rows, width, device="cuda")
+    y = torch.zeros_like(ones)
+    sd = torch.tensor([seed], device="cuda", dtype=torch.int64)
+    L.check(lib.dvae_dropout(L.ptr(ones), width, rows, width, 0.25, L.ptr(sd), salt, L.ptr(y), width, 0, L.stream_ptr()), "dropout")
+    assert np.array_equal(y.cpu().numpy(), philox.dropout_mask(seed, salt, rows, width, 0.25))
+
+
+@pytest.mark.parametrize("B,H,V", [(5, 16, 37), (128, 64, 1000), (96, 256, 10000), (1024, 256, 10000)])
+def test_vocab_sample_step_is_gumbel_argmax(dvae, B, H, V):
+    L = dvae._lib
+    lib = L.load()
+    rng = np.random.default_rng(B + V)
+    h = rng.standard_normal((B, H)).astype(np.float32)
+    w = (rng.standard_normal((V, H)) / np.sqrt(H) * 2).astype(np.float32)
+    bias = rng.standard_normal(V).astype(np.float32)
+    seed, salt = 424242424242, 4096 + 3
+    hd, wd, bd = (torch.from_numpy(a).cuda() for a in (h, w, bias))
+    sd = torch.tensor([seed], device="cuda", dtype=torch.int64)
+    toks = torch.full((B, 3), -1, device="cuda", dtype=torch.int64)
+    ws = torch.empty(lib.dvae_vocab_ce_ws_floats(B, V), device="cuda")
+    L.check(lib.dvae_vocab_sample_step(L.ptr(hd), H, B, H, V, L.ptr(wd), L.ptr(bd), L.ptr(sd), salt,
+                                       toks.data_ptr() + 8, 3, L.ptr(ws), L.stream_ptr()), "sample")
+    got = toks.cpu().numpy()
+    assert (got[:, 0] == -1).all() and (got[:, 2] == -1).all()       # strided write touches column 1 only
+    score = h.astype(np.float64) @ w.astype(np.float64).T + bias + philox.gumbel_noise(seed, salt, B, V)
+    want = score.argmax(1)
+    srt = np.sort(score, axis=1)
+    clear = (srt[:, -1] - srt[:, -2]) > 1e-4                          # skip numerical near-ties
+    assert clear.mean() > 0.95
+    assert np.array_equal(got[clear, 1], want[clear])
+    # and every drawn token scores within rounding of the best one
+    assert (score[np.arange(B), got[:, 1]] >= srt[:, -1] - 1e-4).all()
+
+
+def test_vocab_sample_step_follows_softmax(dvae):
+    """Same logits in every row, independent noise per row: token frequencies ~ softmax(logits)."""
+    L = dvae._lib
+    lib = L.load()
+    B, H, V = 8192, 16, 12
+    rng = np.random.default_rng(0)
+    h1 = rng.standard_normal(H).astype(np.float32)
+    h = np.tile(h1, (B, 1))
+    w = rng.standard_normal((V, H)).astype(np.float32) * 0.4
+    bias = rng.standard_normal(V).astype(np.float32) * 0.5
+    logits = h1.astype(np.float64) @ w.astype(np.float64).T + bias
+    prob = np.exp(logits - logits.max())
+    prob /= prob.sum()
+    hd, wd, bd = (torch.from_numpy(a).cuda() for a in (h, w, bias))
+    sd = torch.tensor([20261018], device="cuda", dtype=torch.int64)
+    toks = torch.zeros(B, device="cuda", dtype=torch.int64)
+    ws = torch.empty(lib.dvae_vocab_ce_ws_floats(B, V), device="cuda")
+    L.check(lib.dvae_vocab_sample_step(L.ptr(hd), H, B, H, V, L.ptr(wd), L.ptr(bd), L.ptr(sd), 4096, L.ptr(toks), 1,
+                                       L.ptr(ws), L.stream_ptr()), "sample")
+    freq = np.bincount(toks.cpu().numpy(), minlength=V) / B
+    sigma = np.sqrt(prob * (1 - prob) / B)
+    assert (np.abs(freq - prob) < 5 * sigma + 1e-4).all(), (freq, prob)
+
+
+def _oracle_on_tokens(vae, X, lengths, Y, eps, klw, preds, dec_masks=None):
+    sd = O.cast_state_dict({k: v.detach().cpu().numpy() for k, v in vae.state_dict().items()})
+    spec = O.ModelSpec(sd, list(vae.context2params.keys()), vae.sos_token_idx, vae.eos_token_idx)
+    eps_d, off = {}, 0
+    for n, zs in zip(spec.space_names, spec.space_dims):
+        eps_d[n] = eps[:, off:off + zs].cpu().numpy()
+        off += zs
+    T = X.size(1)
+    fw = O.model_forward(sd, spec, X.numpy(), lengths.numpy(), eps_d, labels={k: v.numpy() for k, v in Y.items()},
+                         kl_weights=klw, dec_inputs=preds[:, :T - 1], dec_masks=dec_masks)
+    return fw, O.model_backward(sd, spec, fw)
+
+
+def _rel(a, b):
+    a = a.detach().cpu().numpy().astype(np.float64) if torch.is_tensor(a) else np.asarray(a, np.float64)
+    b = np.asarray(b, np.float64)
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-30)
+
+
+@pytest.mark.parametrize("tf,H,V,B,T", [(0.0, 32, 300, 9, 8), (0.5, 32, 300, 16, 11), (0.0, 256, 2000, 64, 10)])
+def test_sampled_forward_backward_matches_oracle_on_sampled_tokens(dvae, tf, H, V, B, T):
+    import random
+    dvae.set_seed(10)
+    vae = dvae.build_vae(_params(embedding_dim=H, hidden_dim=H), V, None, {"polarity": 1}, torch.device("cuda"), 2, 3)
+    vae.train()
+    gen = torch.Generator().manual_seed(B * T + 1)
+    X, lengths, Y = _synthetic(B, T, V, gen)
+    eps = torch.randn(B, 8, generator=gen)
+    klw = {"default": 0.4, "polarity": 0.005}
+    random.seed(4)
+    coins = [random.random() < tf for _ in range(1, T)]
+    random.seed(4)                                        # forward() draws the same coins (vae/model.py:463)
+    out = vae(X.cuda(), lengths.cuda(), teacher_forcing_prob=tf, eps=eps.cuda())
+    preds = out["token_predictions"].cpu().numpy()
+    assert preds.shape == (B, T) and (preds[:, 0] == 2).all()
+    assert ((preds >= 0) & (preds < V)).all()
+    for i in range(1, T):
+        if coins[i - 1]:
+            assert np.array_equal(preds[:, i], X[:, i].numpy())       # forced positions copy the input
+    if tf == 0.0:
+        assert (preds[:, 1:] != X[:, 1:].numpy()).mean() > 0.5        # sampled, not copied
+    total, Ls = dvae.losses.compute_all_losses(vae, out, X.cuda(), Y, lengths.cuda(), klw)
+    total.backward()
+    fw, grads = _oracle_on_tokens(vae, X, lengths, Y, eps, klw, preds)
+    assert abs(total.item() - fw["total_loss"]) <= 1e-5 * abs(fw["total_loss"])
+    for k, prm in vae.named_parameters():
+        assert _rel(prm.grad, grads[k]) < 1e-3, k
+    # the sampled tokens really are Gumbel-max draws from the oracle's logits at each sampled position
+    plan = vae._plans[(B, T)][0]
+    seed = int(plan.seed_dev.item())
+    lg = fw["decoder_logits"]                                          # [B,T,V], position i from decode step i-1
+    for i in range(1, T):
+        if not coins[i - 1]:
+            score = lg[:, i, :] + philox.gumbel_noise(seed, 4096 + (i - 1), B, V)
+            srt = np.sort(score, axis=1)
+            clear = (srt[:, -1] - srt[:, -2]) > 1e-3
+            assert np.array_equal(preds[clear, i], score.argmax(1)[clear])
+
+
+def test_sampled_decode_with_dropout_equals_whole_sequence_decode_on_same_tokens(dvae):
+    """Step-by-step decoding regenerates exactly the dropout masks of the whole-sequence call (absolute-row Philox
+    counters), so re-running the teacher-forced decoder on the sampled tokens reproduces the same top states."""
+    dvae.set_seed(3)
+    V, B, T, H = 400, 12, 9, 32
+    vae = dvae.build_vae(_params(decoder_dropout=0.5, encoder_dropout=0.5), V, None, {"polarity": 1}, torch.device("cuda"), 2, 3)
+    vae.train()
+    gen = torch.Generator().manual_seed(11)
+    X, lengths, Y = _synthetic(B, T, V, gen)
+    eps = torch.randn(B, 8, generator=gen).cuda()
+    with torch.no_grad():
+        out = vae(X.cuda(), lengths.cuda(), teacher_forcing_prob=0.0, eps=eps)
+        plan = vae._plans[(B, T)][0]
+        h_sampled = plan.d_hs[-1].clone()
+        x_sampled = plan.x_dec.clone()
+        preds = out["token_predictions"].clone()
+        plan.decode_forced(vae._P, preds, vae.sos_token_idx, True)      # same seed_dev, same tokens
+        assert torch.equal(plan.x_dec, x_sampled)                        # embedding + dropout mask bit-identical
+        assert (x_sampled == 0).float().mean() > 0.3
+        assert _rel(plan.d_hs[-1], h_sampled.cpu().numpy()) < 1e-5
+
+
+def test_sample_surface_and_logits(dvae):
+    """sample(z, max_length) (vae/model.py:484-512): shapes, <SOS> first, tokens in range, and the lazily
+    materialised logits equal the oracle decoder run on the sampled tokens from the same z."""
+    dvae.set_seed(10)
+    V, B, Tm, H = 300, 7, 12, 32
+    vae = dvae.build_vae(_params(), V, None, {"polarity": 1}, torch.device("cuda"), 2, 3)
+    vae.eval()
+    z = torch.randn(B, 8, generator=torch.Generator().manual_seed(2))
+    out = vae.sample(z.cuda(), max_length=Tm)
+    preds = out["token_predictions"].cpu().numpy()
+    assert preds.shape == (B, Tm) and (preds[:, 0] == 2).all() and ((preds >= 0) & (preds < V)).all()
+    dense = out["decoder_logits"].materialize().detach().cpu().numpy()
+    assert dense.shape == (B, Tm, V)
+    sd = O.cast_state_dict({k: v.detach().cpu().numpy() for k, v in vae.state_dict().items()})
+    Hd, Ld = H, 2
+    hid = np.tanh(z.numpy().astype(np.float64) @ sd["z2hidden.weight"].T + sd["z2hidden.bias"])
+    layer_in = sd["decoder.embedding.weight"][preds[:, :Tm - 1].T]
+    for l in range(Ld):
+        w = [sd[f"decoder.recurrent.{n}_l{l}"] for n in ("weight_ih", "weight_hh", "bias_ih", "bias_hh")]
+        layer_in, _, _, _ = O.lstm_seq_fwd(layer_in, *w, hid[:, l * Hd:(l + 1) * Hd], hid[:, (Ld + l) * Hd:(Ld + l + 1) * Hd], None)
+    want = (layer_in @ sd["decoder.linear.weight"].T + sd["decoder.linear.bias"]).transpose(1, 0, 2)
+    assert np.abs(dense[:, 1:] - want).max() < 1e-4
+    assert (dense[:, 0, 2] == 1.0).all() and np.abs(dense[:, 0]).sum() == B     # one-hot <SOS> at position 0
+    # two calls draw different sentences (fresh seed per call)
+    again = vae.sample(z.cuda(), max_length=Tm)["token_predictions"].cpu().numpy()
+    assert (again != preds).any()
