@@ -7,6 +7,8 @@
 // variant for H <= 256.)
 #include <stdlib.h>
 
+#include <cstring>
+
 #include "common.cuh"
 #include "lstm_persist.cuh"
 
@@ -238,7 +240,7 @@ __global__ void __launch_bounds__(kStepThreads) lstm_step_bwd_kernel(BwdStepArgs
 // DVAE_LSTM_IMPL=step forces the general per-step path (A/B tests of the persistent kernels)
 static bool force_step_path() {
   const char* e = getenv("DVAE_LSTM_IMPL");
-  return e && e[0] == 's';
+  return e && !strcmp(e, "step");
 }
 static int64_t state_floats(int B, int H, int D) { return 4LL * D * B * H; }
 

@@ -399,12 +399,14 @@ static int launch_bwd(const PersistBwdArgs& a, cudaStream_t st) {
 }
 
 int persist_fwd(int H, const PersistFwdArgs& a, cudaStream_t st) {
+  if (tc_lstm_supported(H)) return tc_lstm_fwd(a, st);
   if (H == 256) return launch_fwd<256>(a, st);
   if (H == 128) return launch_fwd<128>(a, st);
   return launch_fwd<64>(a, st);
 }
 
 int persist_bwd(int H, const PersistBwdArgs& a, cudaStream_t st) {
+  if (tc_lstm_supported(H)) return tc_lstm_bwd(a, st);
   if (H == 256) return launch_bwd<256>(a, st);
   if (H == 128) return launch_bwd<128>(a, st);
   return launch_bwd<64>(a, st);

@@ -32,4 +32,10 @@ bool persist_supported(int B, int H, int D, const void* const* ptrs, int nptr, c
 int persist_fwd(int H, const PersistFwdArgs& a, cudaStream_t st);
 int persist_bwd(int H, const PersistBwdArgs& a, cudaStream_t st);
 
+// tcgen05 variant (lstm_tc.cu): H = 256, fp16 hi/lo split operands resident in SMEM, accumulators in TMEM.
+// DVAE_LSTM_IMPL=simt keeps the fp32 SIMT persistent kernels (A/B tests).
+bool tc_lstm_supported(int H);
+int tc_lstm_fwd(const PersistFwdArgs& a, cudaStream_t st);
+int tc_lstm_bwd(const PersistBwdArgs& a, cudaStream_t st);
+
 }  // namespace dvae

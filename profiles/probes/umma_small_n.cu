@@ -1,0 +1,145 @@
+// Probe: cycles per tcgen05.mma.kind::f16 (M=128, K=16) at small N, as a function of
+//   - operand source for A: shared memory (SS) vs tensor memory (TS)
+//   - number of independent accumulators the issue loop round-robins over (dependent-accumulate latency)
+//   - N (16, 32, 64)
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -I disentanglement-vae_b200/csrc \
+//        profiles/probes/umma_small_n.cu -o profiles/probes/bin/umma_small_n
+#include <cstdio>
+#include <cuda_fp16.h>
+#include "tc_gemm.cuh"
+namespace dvae { void set_error(const char*, ...) {} void count_launch(int) {} }
+using namespace dvae::tc;
+
+__device__ __forceinline__ void mma_ss(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d), "l"(a), "l"(b), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void mma_ts(uint32_t d, uint32_t a_tmem, uint64_t b, uint32_t idesc, uint32_t acc) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d), "r"(a_tmem), "l"(b), "r"(idesc), "r"(acc) : "memory");
+}
+__host__ __device__ constexpr uint32_t idesc_f16(int M, int N) { return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24); }
+
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.b32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
+// issue-style probe: 48 MMAs (16 k-steps x 3 products, as the LSTM step does), fully unrolled, N = 16
+template <int STYLE>
+__device__ __forceinline__ void issue48(uint32_t tmem, uint32_t sb, uint64_t* bar) {
+  constexpr uint32_t idesc = idesc_f16(128, 16);
+  const uint64_t ahi = make_smem_desc(sb, 128, 4096, 0), alo = make_smem_desc(sb + 65536, 128, 4096, 0);
+  const uint64_t bhi = make_smem_desc(sb + 131072, 256, 128, 0), blo = make_smem_desc(sb + 131072 + 8192, 256, 128, 0);
+#pragma unroll
+  for (int ks = 0; ks < 16; ++ks) {
+    const uint64_t da = (uint64_t)(ks * 16), db = (uint64_t)(ks * 32);
+    mma_ss(tmem, ahi + da, bhi + db, idesc, ks > 0);
+    mma_ss(tmem + 16, ahi + da, blo + db, idesc, ks > 0);
+    mma_ss(tmem + 16, alo + da, bhi + db, idesc, 1);
+  }
+  tc_commit(bar);
+}
+
+__global__ void __launch_bounds__(128, 1) probe_style(long long* out) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t slot;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < 160 * 1024 / 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
+  if (tid == 0) { mbar_init(&bar, 1); fence_barrier_init(); }
+  if (tid < 32) tmem_alloc(&slot, 64);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = slot, sb = smem_u32(smem);
+  int phase = 0;
+  for (int rep = 0; rep < 3; ++rep) {
+    // style 0: divergent single thread
+    long long t0 = clock64(), t1 = 0;
+    if (tid == 0) { issue48<0>(tmem, sb, &bar); t1 = clock64(); }
+    mbar_wait(&bar, phase); phase ^= 1;
+    long long t2 = clock64();
+    if (tid == 0) { out[rep * 4 + 0] = t1 - t0; out[rep * 4 + 1] = t2 - t0; }
+    __syncthreads();
+    // style 1: warp-uniform branch + elect.sync
+    t0 = clock64(); t1 = 0;
+    if (warp == 0) {
+      if (elect_one()) { issue48<1>(tmem, sb, &bar); t1 = clock64(); }
+      __syncwarp();
+    }
+    mbar_wait(&bar, phase); phase ^= 1;
+    t2 = clock64();
+    if (tid == 0) { out[rep * 4 + 2] = t1 - t0; out[rep * 4 + 3] = t2 - t0; }
+    __syncthreads();
+  }
+  if (tid < 32) tmem_dealloc(tmem, 64);
+}
+
+__global__ void __launch_bounds__(128, 1) probe(long long* out) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t slot;
+  const int tid = threadIdx.x;
+  for (int i = tid; i < 160 * 1024 / 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;   // fp16 1.0
+  if (tid == 0) { mbar_init(&bar, 1); fence_barrier_init(); }
+  if (tid < 32) tmem_alloc(&slot, 512);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = slot, sb = smem_u32(smem);
+  if (tid == 0) {
+    int phase = 0, o = 0;
+    const int Ns[3] = {16, 32, 64};
+    for (int ni = 0; ni < 3; ++ni) {
+      const int N = Ns[ni];
+      const uint32_t idesc = idesc_f16(128, N);
+      for (int mode = 0; mode < 2; ++mode) {          // 0 = SS, 1 = TS
+        for (int nacc = 1; nacc <= 4; ++nacc) {
+          const int R = 96;
+          long long t0 = clock64();
+          for (int r = 0; r < R; ++r) {
+            const int ks = r & 15;
+            const uint64_t a = make_smem_desc(sb + ks * 256, 128, 4096, 0);
+            const uint64_t b = make_smem_desc(sb + 131072 + ks * 2 * N * 16, N * 16, 128, 0);
+            const uint32_t d = tmem + 256 + (r % nacc) * N;
+            if (mode == 0) mma_ss(d, a, b, idesc, r >= nacc);
+            else mma_ts(d, tmem + ks * 8, b, idesc, r >= nacc);
+          }
+          tc_commit(&bar);
+          long long t1 = clock64();
+          mbar_wait(&bar, phase); phase ^= 1;
+          long long t2 = clock64();
+          out[o++] = t1 - t0; out[o++] = t2 - t0;
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (tid < 32) tmem_dealloc(tmem, 512);
+}
+
+int main() {
+  long long* d; cudaMalloc(&d, 1024);
+  cudaFuncSetAttribute(probe, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaFuncSetAttribute(probe_style, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  for (int it = 0; it < 2; ++it) probe<<<1, 128, 200 * 1024>>>(d);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) { printf("error: %s\n", cudaGetErrorString(e)); return 1; }
+  long long h[128]; cudaMemcpy(h, d, sizeof(h[0]) * 96, cudaMemcpyDeviceToHost);
+  int o = 0;
+  const int Ns[3] = {16, 32, 64};
+  for (int ni = 0; ni < 3; ++ni) for (int mode = 0; mode < 2; ++mode) for (int nacc = 1; nacc <= 4; ++nacc) {
+    printf("N=%2d A=%s accumulators=%d : issue %6.1f cyc/MMA, complete %6.1f cyc/MMA (96 MMAs)\n", Ns[ni], mode ? "TMEM" : "SMEM", nacc, h[o] / 96.0, h[o + 1] / 96.0);
+    o += 2;
+  }
+  probe_style<<<1, 128, 200 * 1024>>>(d);
+  e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) { printf("error: %s\n", cudaGetErrorString(e)); return 1; }
+  cudaMemcpy(h, d, sizeof(h[0]) * 12, cudaMemcpyDeviceToHost);
+  for (int rep = 0; rep < 3; ++rep)
+    printf("48 unrolled MMAs (N=16, SS): tid==0 style issue %lld complete %lld cyc | warp+elect style issue %lld complete %lld cyc\n",
+           h[rep * 4], h[rep * 4 + 1], h[rep * 4 + 2], h[rep * 4 + 3]);
+  return 0;
+}

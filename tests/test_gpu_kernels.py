@@ -206,9 +206,20 @@ def _lstm_case(lib, L, T, B, I, H, D, with_len, with_h0, seed):
     (11, 50, 24, 128, 2, True, False),   # persistent-cluster kernels: H=128, ragged, partial 16-row slice
     (21, 128, 256, 256, 1, False, True), # persistent-cluster kernels: cfg-2 decoder layer
     (30, 64, 32, 64, 1, True, False),
+    (9, 50, 32, 256, 2, True, False),    # tcgen05 kernels: partial 16-row slice, ragged, both directions in one launch
+    (7, 40, 48, 256, 1, False, True),    # tcgen05 kernels: initial state + d_h0/d_c0, partial slice
+    (1, 16, 32, 256, 1, False, True),    # tcgen05 kernels: single step
+    (2, 20, 32, 256, 2, True, False),
 ])
 def test_lstm_seq(lib, L, T, B, I, H, D, with_len, with_h0):
     _lstm_case(lib, L, T, B, I, H, D, with_len, with_h0, seed=T * 31 + B)
+
+
+@pytest.mark.parametrize("D,with_len,with_h0", [(2, True, False), (1, False, True)])
+def test_lstm_simt_persistent_path_matches_oracle_too(lib, L, D, with_len, with_h0, monkeypatch):
+    """DVAE_LSTM_IMPL=simt keeps the fp32 SIMT persistent-cluster kernels at H=256 (the tcgen05 kernels' A/B partner)."""
+    monkeypatch.setenv("DVAE_LSTM_IMPL", "simt")
+    _lstm_case(lib, L, 9, 48, 32, 256, D, with_len, with_h0, seed=77 + D)
 
 
 @pytest.mark.parametrize("H,D,with_len,with_h0", [(256, 2, True, False), (64, 1, False, True)])
