@@ -32,6 +32,7 @@ SIGNATURES = {
     "dvae_launch_count": (_l, []),
     "dvae_linear": (_i, [_p, _l, _i, _p, _l, _i, _p, _l, _i, _i, _i, _p, _p, _f, _i, _p]),
     "dvae_tc_linear": (_i, [_p, _l, _i, _p, _l, _i, _p, _l, _i, _i, _i, _p, _p, _f, _i, _i, _p]),
+    "dvae_tc16_linear": (_i, [_p, _l, _i, _p, _l, _i, _p, _l, _i, _i, _i, _p, _p, _f, _i, _f, _f, _p, _p, _p]),
     "dvae_colsum": (_i, [_p, _l, _i, _i, _p, _f, _p]),
     "dvae_randn": (_i, [_p, _l, _p, _u32, _p]),
     "dvae_embedding_fwd": (_i, [_p, _i, _p, _l, _l, _i, _i, _f, _p, _u32, _l, _i, _p, _p]),

@@ -21,6 +21,60 @@ bool force_simt_gemm() {
   const char* e = getenv("DVAE_GEMM_IMPL");
   return e && e[0] == 's';
 }
+
+// ---- fork / join side streams ---------------------------------------------------------------------
+namespace {
+struct SideStreams {
+  cudaStream_t s[3];
+  cudaEvent_t fork_ev, join_ev[3];
+  bool ok = false;
+};
+SideStreams* side_streams() {
+  static thread_local SideStreams* per_dev[64] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  if (!per_dev[dev]) {
+    SideStreams* ss = new SideStreams();
+    ss->ok = cudaEventCreateWithFlags(&ss->fork_ev, cudaEventDisableTiming) == cudaSuccess;
+    for (int i = 0; i < 3 && ss->ok; ++i)
+      ss->ok = cudaStreamCreateWithFlags(&ss->s[i], cudaStreamNonBlocking) == cudaSuccess &&
+               cudaEventCreateWithFlags(&ss->join_ev[i], cudaEventDisableTiming) == cudaSuccess;
+    per_dev[dev] = ss;
+  }
+  return per_dev[dev]->ok ? per_dev[dev] : nullptr;
+}
+bool fork_enabled() {
+  const char* e = getenv("DVAE_FORK");
+  return !(e && e[0] == '0');
+}
+}  // namespace
+
+Fork::Fork(cudaStream_t main) : main_(main), ok_(false) {
+  if (!fork_enabled()) return;
+  SideStreams* ss = side_streams();
+  if (!ss) return;
+  ok_ = cudaEventRecord(ss->fork_ev, main_) == cudaSuccess;
+}
+cudaStream_t Fork::side(int i) {
+  if (!ok_) return main_;
+  SideStreams* ss = side_streams();
+  if (!used_[i]) {
+    if (cudaStreamWaitEvent(ss->s[i], ss->fork_ev, 0) != cudaSuccess) return main_;
+    used_[i] = true;
+  }
+  return ss->s[i];
+}
+int Fork::join() {
+  if (!ok_) return DVAE_OK;
+  SideStreams* ss = side_streams();
+  for (int i = 0; i < 3; ++i)
+    if (used_[i]) {
+      DVAE_CUDA(cudaEventRecord(ss->join_ev[i], ss->s[i]));
+      DVAE_CUDA(cudaStreamWaitEvent(main_, ss->join_ev[i], 0));
+      used_[i] = false;
+    }
+  return DVAE_OK;
+}
 }  // namespace dvae
 
 extern "C" const char* dvae_last_error_string(void) { return dvae::g_err; }

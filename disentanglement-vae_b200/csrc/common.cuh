@@ -43,8 +43,37 @@ void count_launch(int n = 1);
 
 static inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
-// DVAE_GEMM_IMPL=simt forces the fp32 SIMT kernels (A/B tests of the tensor-core path)
+// Fork / join of independent kernels onto library-owned side streams (also valid inside CUDA graph capture, where it
+// becomes parallel branches of the graph).  The small backward GEMMs of one layer are independent of each other and
+// each far too small to fill 148 SMs; run back to back they pay their fixed latencies serially.
+//   Fork f(st);  launch on st / f.side(0..2);  f.join();     DVAE_FORK=0 keeps everything on the caller's stream.
+class Fork {
+ public:
+  explicit Fork(cudaStream_t main);
+  cudaStream_t side(int i);      // i in [0, 3); returns the main stream when forking is disabled
+  int join();                    // main waits for every side stream that was used; returns a DVAE_* code
+ private:
+  cudaStream_t main_;
+  bool used_[3] = {false, false, false};
+  bool ok_;
+};
+
+// DVAE_GEMM_IMPL=simt forces the fp32 SIMT kernels, =tf32 the 3xTF32 tensor-core kernel (A/B tests of the fp16-split path)
 bool force_simt_gemm();
+
+// What the caller knows about the dynamic range of a GEMM's operands.  The fp16-split tensor-core kernel multiplies an
+// operand by a power of two before splitting it into fp16 planes: either a host constant (`*_scale`) or
+// 2^(13 - floor(log2 amax)) from the bit pattern of a device-side max |x| (`*_amax_bits`).  An operand flagged `wide`
+// (a gradient of unknown magnitude) without an amax keeps the 3xTF32 kernel, whose operands have fp32 range.
+struct GemmHints {
+  const uint32_t* a_amax_bits = nullptr;
+  const uint32_t* b_amax_bits = nullptr;
+  float a_scale = 1.f, b_scale = 1.f;
+  bool a_wide = false, b_wide = false;
+};
+int linear_impl_ex(const float* A, int64_t lda, int trans_a, const float* B, int64_t ldb, int trans_b, float* C,
+                   int64_t ldc, int M, int N, int K, const float* bias, const float* bias2, float beta, int act,
+                   const GemmHints& hints, cudaStream_t st);
 
 namespace tc {
 bool tc_linear_supported(const float* A, int64_t lda, const float* B, int64_t ldb, int M, int N, int K);

@@ -400,13 +400,16 @@ extern "C" int dvae_latent_heads_bwd(const float* ctx, int B, int C, int S, cons
   float* d_z = d_pre + (int64_t)B * H2L;          // [B,Z]
   float* dp = d_z + (int64_t)B * Z;               // [B,2Z]
   float* dl = dp + (int64_t)B * 2 * Z;            // [B,OD]
+  GemmHints grad_hints;            // A operands below are gradients of unknown magnitude
+  grad_hints.a_wide = true;
   const int64_t n = (int64_t)B * H2L;
   heads_bwd_pre_kernel<<<ceil_div(n, 256), 256, 0, st>>>(d_hid, hid, d_pre, n);
   DVAE_LAUNCH_CHECK();
   // z2hidden: d_w = d_pre^T z, d_b = colsum(d_pre), d_z = d_pre Wz
-  if ((rc = linear_impl(d_pre, H2L, 1, z, Z, 1, d_w_z2h, Z, H2L, Z, B, nullptr, nullptr, 0.f, 0, st))) return rc;
-  if ((rc = colsum_impl(d_pre, H2L, B, H2L, d_b_z2h, 0.f, st))) return rc;
-  if ((rc = linear_impl(d_pre, H2L, 0, w_z2h, Z, 1, d_z, Z, B, Z, H2L, nullptr, nullptr, 0.f, 0, st))) return rc;
+  Fork fork(st);          // weight / bias gradients branch off the d_z -> dp -> d_ctx chain
+  if ((rc = linear_impl_ex(d_pre, H2L, 1, z, Z, 1, d_w_z2h, Z, H2L, Z, B, nullptr, nullptr, 0.f, 0, grad_hints, fork.side(0)))) return rc;
+  if ((rc = colsum_impl(d_pre, H2L, B, H2L, d_b_z2h, 0.f, fork.side(1)))) return rc;
+  if ((rc = linear_impl_ex(d_pre, H2L, 0, w_z2h, Z, 1, d_z, Z, B, Z, H2L, nullptr, nullptr, 0.f, 0, grad_hints, st))) return rc;
   HeadsBwdArgs a{eps, w_dsc, labels, kl_w_dev, z, mu, logvar, dsc_logits, d_z, d_z_extra, d_mu_extra, d_logvar_extra, d_logits_extra, dp, dl, B};
   heads_bwd_elem_kernel<<<ceil_div((int64_t)B * Z, 256), 256, 0, st>>>(a, m);
   DVAE_LAUNCH_CHECK();
@@ -418,8 +421,14 @@ extern "C" int dvae_latent_heads_bwd(const float* ctx, int B, int C, int S, cons
     DVAE_LAUNCH_CHECK();
   }
   // context2params: d_w = dp^T ctx, d_b = colsum(dp), d_ctx = dp W
-  if ((rc = linear_impl(dp, 2 * Z, 1, ctx, C, 1, d_w_c2p, C, 2 * Z, C, B, nullptr, nullptr, 0.f, 0, st))) return rc;
-  if ((rc = colsum_impl(dp, 2 * Z, B, 2 * Z, d_b_c2p, 0.f, st))) return rc;
-  if ((rc = linear_impl(dp, 2 * Z, 0, w_c2p, C, 1, d_ctx, C, B, C, 2 * Z, nullptr, nullptr, 0.f, 0, st))) return rc;
+  {
+    // side streams 0 / 1 are still running the z2hidden gradients; dp is ready on the main stream only
+    Fork fork2(st);
+    if ((rc = linear_impl_ex(dp, 2 * Z, 1, ctx, C, 1, d_w_c2p, C, 2 * Z, C, B, nullptr, nullptr, 0.f, 0, grad_hints, fork2.side(2)))) return rc;
+    if ((rc = linear_impl_ex(dp, 2 * Z, 0, w_c2p, C, 1, d_ctx, C, B, C, 2 * Z, nullptr, nullptr, 0.f, 0, grad_hints, st))) return rc;
+    if ((rc = colsum_impl(dp, 2 * Z, B, 2 * Z, d_b_c2p, 0.f, st))) return rc;
+    if ((rc = fork2.join())) return rc;
+  }
+  if ((rc = fork.join())) return rc;
   return DVAE_OK;
 }

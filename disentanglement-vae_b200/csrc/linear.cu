@@ -1,5 +1,6 @@
 // dvae_linear / dvae_colsum: dense fp32 layers on the path (see include/dvae_b200.h).
 #include "gemm_simt.cuh"
+#include "tc_gemm16.cuh"
 
 namespace dvae {
 
@@ -80,14 +81,25 @@ __global__ void scale_rows_kernel(float* C, int64_t ldc, int M, int N, float bet
 int linear_impl(const float* A, int64_t lda, int trans_a, const float* B, int64_t ldb, int trans_b, float* C,
                 int64_t ldc, int M, int N, int K, const float* bias, const float* bias2, float beta, int act,
                 cudaStream_t st) {
+  return linear_impl_ex(A, lda, trans_a, B, ldb, trans_b, C, ldc, M, N, K, bias, bias2, beta, act, GemmHints(), st);
+}
+
+int linear_impl_ex(const float* A, int64_t lda, int trans_a, const float* B, int64_t ldb, int trans_b, float* C,
+                   int64_t ldc, int M, int N, int K, const float* bias, const float* bias2, float beta, int act,
+                   const GemmHints& hints, cudaStream_t st) {
   DVAE_REQUIRE(A && B && C, "dvae_linear: null pointer");
   DVAE_REQUIRE(M > 0 && N > 0 && K > 0, "dvae_linear: non-positive size M=%d N=%d K=%d", M, N, K);
   DVAE_REQUIRE(act == 0 || act == 1, "dvae_linear: unknown activation %d", act);
   // Dense-contraction shapes go to the tensor cores (TMA + tcgen05, 3xTF32 = fp32-grade accuracy); small or
   // unaligned problems stay on the fp32 SIMT kernels below.
-  if (!force_simt_gemm() && M >= 64 && N >= 64 && K >= 32 && (double)M * N * K >= (double)(1 << 23) &&
-      tc::tc_linear_supported(A, lda, B, ldb, M, N, K))
-    return tc::tc_linear_impl(A, lda, trans_a, B, ldb, trans_b, C, ldc, M, N, K, bias, bias2, beta, act, 3, st);
+  if (!force_simt_gemm() && M >= 64 && N >= 64 && K >= 32 && (double)M * N * K >= (double)(1 << 23)) {
+    // fp16-split kernel unless an operand's dynamic range is unknown (then 3xTF32, whose operands have fp32 range)
+    const bool unscaled_wide = (hints.a_wide && !hints.a_amax_bits) || (hints.b_wide && !hints.b_amax_bits);
+    if (!unscaled_wide && tc16::supported(A, lda, trans_a, B, ldb, trans_b, M, N, K))
+      return tc16::linear(A, lda, trans_a, B, ldb, trans_b, C, ldc, M, N, K, bias, bias2, beta, act, hints, st);
+    if (tc::tc_linear_supported(A, lda, B, ldb, M, N, K))
+      return tc::tc_linear_impl(A, lda, trans_a, B, ldb, trans_b, C, ldc, M, N, K, bias, bias2, beta, act, 3, st);
+  }
   // Tile choice: 128x128 when that already fills the 148 SMs, else 64x64; split-K (atomic
   // accumulation) when even the small tiles leave most SMs idle and K is deep.
   const int kSMs = 148;
@@ -168,7 +180,9 @@ int colsum_impl(const float* X, int64_t ldx, int M, int N, float* out, float bet
 extern "C" int dvae_linear(const float* A, int64_t lda, int trans_a, const float* B, int64_t ldb, int trans_b,
                            float* C, int64_t ldc, int M, int N, int K, const float* bias, const float* bias2,
                            float beta, int act, void* stream) {
-  return dvae::linear_impl(A, lda, trans_a, B, ldb, trans_b, C, ldc, M, N, K, bias, bias2, beta, act,
+  dvae::GemmHints hints;           // a public entry point knows nothing about its operands' dynamic range
+  hints.a_wide = hints.b_wide = true;
+  return dvae::linear_impl_ex(A, lda, trans_a, B, ldb, trans_b, C, ldc, M, N, K, bias, bias2, beta, act, hints,
                            (cudaStream_t)stream);
 }
 

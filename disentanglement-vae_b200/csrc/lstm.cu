@@ -253,9 +253,14 @@ int lstm_seq_fwd_impl(const float* x, int64_t ldx, int T, int B, int I, int H, i
   DVAE_REQUIRE(T > 0 && B > 0 && I > 0 && H > 0 && (D == 1 || D == 2), "dvae_lstm_seq_fwd: bad shape T=%d B=%d I=%d H=%d D=%d", T, B, I, H, D);
   DVAE_REQUIRE(!(lengths && h0), "dvae_lstm_seq_fwd: length-masked layers start from the zero state");
   const int64_t slab = (int64_t)T * B * 4 * H, sf = (int64_t)D * B * H;
-  for (int d = 0; d < D; ++d) {
-    int rc = linear_impl(x, ldx, 0, w_ih[d], I, 0, gates + d * slab, 4 * H, T * B, 4 * H, I, b_ih ? b_ih[d] : nullptr,
-                         b_hh ? b_hh[d] : nullptr, 0.f, 0, st);
+  {
+    Fork fork(st);           // the two directions' input projections are independent
+    for (int d = 0; d < D; ++d) {
+      int rc = linear_impl(x, ldx, 0, w_ih[d], I, 0, gates + d * slab, 4 * H, T * B, 4 * H, I, b_ih ? b_ih[d] : nullptr,
+                           b_hh ? b_hh[d] : nullptr, 0.f, 0, d == 0 ? st : fork.side(0));
+      if (rc) return rc;
+    }
+    int rc = fork.join();
     if (rc) return rc;
   }
   {
@@ -312,6 +317,7 @@ int lstm_seq_bwd_impl(const float* x, int64_t ldx, int T, int B, int I, int H, i
   DVAE_REQUIRE(!(lengths && h0), "dvae_lstm_seq_bwd: length-masked layers start from the zero state");
   const int64_t slab = (int64_t)T * B * 4 * H, sf = (int64_t)D * B * H;
   bool persisted = false;
+  uint32_t* amax = nullptr;
   {
     const void* ptrs[] = {w_hh[0], w_hh[D - 1], c0, gates, cs, d_hs, d_hn, d_cn, d_h0, d_c0};
     const int64_t lds[] = {ld0, dir0, lddhs, ldn, dirn, ldd0, dird0};
@@ -321,6 +327,12 @@ int lstm_seq_bwd_impl(const float* x, int64_t ldx, int T, int B, int I, int H, i
       a.gates = gates; a.cs = cs; a.c0 = c0; a.ld0 = ld0; a.dir0 = dir0; a.d_hs = d_hs; a.lddhs = lddhs;
       a.d_hn = d_hn; a.d_cn = d_cn; a.ldn = ldn; a.dirn = dirn; a.d_h0 = d_h0; a.d_c0 = d_c0; a.ldd0 = ldd0;
       a.dird0 = dird0; a.lengths = lengths; a.T = T; a.B = B; a.D = D; a.n_slices = ceil_div(B, 16); a.d_off = 0;
+      a.amax_out = nullptr;
+      if (tc_lstm_supported(H)) {      // the tcgen05 kernel also reports max |dG|: the operand scale of the GEMMs below
+        amax = reinterpret_cast<uint32_t*>(ws + state_floats(B, H, D) + 4LL * D * H * H);
+        DVAE_CUDA(cudaMemsetAsync(amax, 0, sizeof(uint32_t), st));
+        a.amax_out = amax;
+      }
       int rc = persist_bwd(H, a, st);
       if (rc) return rc;
       persisted = true;
@@ -356,44 +368,56 @@ int lstm_seq_bwd_impl(const float* x, int64_t ldx, int T, int B, int I, int H, i
     lstm_step_bwd_kernel<<<grid, kStepThreads, 0, st>>>(a);
     DVAE_LAUNCH_CHECK();
   }
-  // dense gradients from the saved dG slabs
+  // dense gradients from the saved dG slabs (A operand = dG: a gradient, scaled by its measured amax when known)
+  GemmHints gh;
+  gh.a_wide = true;
+  gh.a_amax_bits = amax;
+  // d_x accumulates over the directions (main stream, in order); the weight / bias gradients of each direction are
+  // independent of it and of each other: parallel branches
+  Fork fork(st);
   for (int d = 0; d < D; ++d) {
     const float* dG = gates + d * slab;
     int rc;
     if (d_x) {
-      rc = linear_impl(dG, 4 * H, 0, w_ih[d], I, 1, d_x, lddx, T * B, I, 4 * H, nullptr, nullptr, d == 0 ? 0.f : 1.f, 0, st);
+      rc = linear_impl_ex(dG, 4 * H, 0, w_ih[d], I, 1, d_x, lddx, T * B, I, 4 * H, nullptr, nullptr, d == 0 ? 0.f : 1.f, 0, gh, st);
       if (rc) return rc;
     }
     if (d_w_ih && d_w_ih[d]) {
-      rc = linear_impl(dG, 4 * H, 1, x, ldx, 1, d_w_ih[d], I, 4 * H, I, T * B, nullptr, nullptr, 0.f, 0, st);
+      rc = linear_impl_ex(dG, 4 * H, 1, x, ldx, 1, d_w_ih[d], I, 4 * H, I, T * B, nullptr, nullptr, 0.f, 0, gh, fork.side(0));
       if (rc) return rc;
     }
     if (d_w_hh && d_w_hh[d]) {
+      cudaStream_t s1 = fork.side(1);
       // h_prev[t] = hs at the previously traversed step (zero / h0 at the first one)
       bool wrote = false;
       if (T > 1) {
         const float* dGs = d == 0 ? dG + (int64_t)B * 4 * H : dG;
         const float* hp = d == 0 ? hs + d * H : hs + (int64_t)B * ldhs + d * H;
-        rc = linear_impl(dGs, 4 * H, 1, hp, ldhs, 1, d_w_hh[d], H, 4 * H, H, (T - 1) * B, nullptr, nullptr, 0.f, 0, st);
+        rc = linear_impl_ex(dGs, 4 * H, 1, hp, ldhs, 1, d_w_hh[d], H, 4 * H, H, (T - 1) * B, nullptr, nullptr, 0.f, 0, gh, s1);
         if (rc) return rc;
         wrote = true;
       }
       if (h0) {
         const float* dG0 = d == 0 ? dG : dG + (int64_t)(T - 1) * B * 4 * H;
-        rc = linear_impl(dG0, 4 * H, 1, h0 + d * dir0, ld0, 1, d_w_hh[d], H, 4 * H, H, B, nullptr, nullptr, wrote ? 1.f : 0.f, 0, st);
+        rc = linear_impl_ex(dG0, 4 * H, 1, h0 + d * dir0, ld0, 1, d_w_hh[d], H, 4 * H, H, B, nullptr, nullptr, wrote ? 1.f : 0.f, 0, gh, s1);
         if (rc) return rc;
         wrote = true;
       }
-      if (!wrote) DVAE_CUDA(cudaMemsetAsync(d_w_hh[d], 0, sizeof(float) * 4 * H * H, st));
+      if (!wrote) DVAE_CUDA(cudaMemsetAsync(d_w_hh[d], 0, sizeof(float) * 4 * H * H, s1));
     }
+    cudaStream_t s2 = fork.side(2);
     if (d_b_ih && d_b_ih[d]) {
-      rc = colsum_impl(dG, 4 * H, T * B, 4 * H, d_b_ih[d], 0.f, st);
+      rc = colsum_impl(dG, 4 * H, T * B, 4 * H, d_b_ih[d], 0.f, s2);
       if (rc) return rc;
-      if (d_b_hh && d_b_hh[d]) DVAE_CUDA(cudaMemcpyAsync(d_b_hh[d], d_b_ih[d], sizeof(float) * 4 * H, cudaMemcpyDeviceToDevice, st));
+      if (d_b_hh && d_b_hh[d]) DVAE_CUDA(cudaMemcpyAsync(d_b_hh[d], d_b_ih[d], sizeof(float) * 4 * H, cudaMemcpyDeviceToDevice, s2));
     } else if (d_b_hh && d_b_hh[d]) {
-      rc = colsum_impl(dG, 4 * H, T * B, 4 * H, d_b_hh[d], 0.f, st);
+      rc = colsum_impl(dG, 4 * H, T * B, 4 * H, d_b_hh[d], 0.f, s2);
       if (rc) return rc;
     }
+  }
+  {
+    int rc = fork.join();
+    if (rc) return rc;
   }
   return DVAE_OK;
 }
@@ -439,7 +463,7 @@ extern "C" int dvae_lstm_step(const float* x, int64_t ldx, int t, int T, int B, 
 }
 
 extern "C" int64_t dvae_lstm_state_ws_floats(int B, int H, int D) {
-  return dvae::state_floats(B, H, D) + 4LL * D * H * H;
+  return dvae::state_floats(B, H, D) + 4LL * D * H * H + 4;   // + the max |dG| slot of the backward pass
 }
 
 extern "C" int dvae_lstm_seq_fwd(const float* x, int64_t ldx, int T, int B, int I, int H, int D,

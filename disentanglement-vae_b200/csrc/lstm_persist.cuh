@@ -25,6 +25,7 @@ struct PersistBwdArgs {
   float* d_h0; float* d_c0; int64_t ldd0, dird0;
   const int64_t* lengths;
   int T, B, D, n_slices, d_off;
+  uint32_t* amax_out;            // optional: atomicMax of the bit pattern of max |dG| (operand scale of the dense gradient GEMMs)
 };
 
 // true when the persistent kernels can take this call (H in {64,128,256}, 16-byte aligned buffers)

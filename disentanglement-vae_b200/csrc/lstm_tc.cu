@@ -53,14 +53,6 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
   return r;
 }
-__device__ __forceinline__ void mma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
-      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
 // kind::f16, A = B = fp16, D = fp32, both operands K-major
 __host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
   return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
@@ -83,11 +75,6 @@ __device__ __forceinline__ void bulk_copy_to_peer(uint32_t dst_cluster, uint32_t
 }
 // hardware barrier of one 512-thread row group (barrier 0 is __syncthreads)
 __device__ __forceinline__ void group_sync(int grp) { asm volatile("bar.sync %0, 512;" ::"r"(grp + 1) : "memory"); }
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred;
-  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.b32 %0, 1, 0, p;\n\t}" : "=r"(pred));
-  return pred != 0;
-}
 // 32 lanes x 4 consecutive fp32 columns
 __device__ __forceinline__ void tmem_ld4(uint32_t taddr, float (&v)[4]) {
   uint32_t r[4];
@@ -366,6 +353,7 @@ __global__ void __cluster_dims__(kCS, 1, 1) __launch_bounds__(kGT, 1) lstm_tc_bw
   const uint32_t tmem = *tmem_slot;
   constexpr uint32_t kIdesc = make_idesc_f16(128, kNB);
   const int nsteps = T + ((p.d_h0 || p.d_c0) ? 1 : 0);
+  unsigned amax_run = 0;           // bit pattern of max |dG| over this warp's row, all steps
 
   for (int s = 0; s < nsteps; ++s) {
     const bool final_ = (s == T);
@@ -472,6 +460,7 @@ __global__ void __cluster_dims__(kCS, 1, 1) __launch_bounds__(kGT, 1) lstm_tc_bw
     // row scale 2^(13 - floor(log2(max |dG[row, own 128 gate rows]|))): exact, undone when the accumulator is read
     const float am = fmaxf(fmaxf(fabsf(o[0]), fabsf(o[1])), fmaxf(fabsf(o[2]), fabsf(o[3])));
     const unsigned mx = __reduce_max_sync(0xffffffffu, __float_as_uint(am));
+    amax_run = max(amax_run, mx);
     int se = 267 - (int)(mx >> 23);
     se = se < 1 ? 1 : (se > 253 ? 253 : se);
     const float sc = __uint_as_float((unsigned)se << 23);
@@ -489,6 +478,7 @@ __global__ void __cluster_dims__(kCS, 1, 1) __launch_bounds__(kGT, 1) lstm_tc_bw
     tc_fence_before();
     __syncthreads();
   }
+  if (p.amax_out && lane == 0 && amax_run) atomicMax(p.amax_out, amax_run);
   tc_fence_before();
   __syncthreads();
   cluster.sync();

@@ -1,0 +1,43 @@
+// fp16 (hi, lo)-split tensor-core GEMM (tc_gemm16.cu): argument block and host entry points.
+#pragma once
+#include "common.cuh"
+
+namespace dvae {
+namespace tc16 {
+
+struct Params {
+  const float* A; int64_t lda;     // [M,K] row-major (a_mn = 0) or [K,M] row-major (a_mn = 1)
+  const float* Bm; int64_t ldb;    // [N,K] row-major (b_mn = 0) or [K,N] row-major (b_mn = 1)
+  int M, N, K;
+  int a_mn, b_mn;
+  int tiles_per_cta;     // consecutive N tiles per CTA
+  float* C; int64_t ldc;
+  const float* bias; const float* bias2;
+  float beta; int act;
+  int mode;              // 0: C = act(alpha * acc + bias) + beta*C;  1: vocab-CE forward partials;  2: softmax-gradient tile
+  int kb_per_split;      // k-blocks per blockIdx.z (split-K, mode 0; partial tiles are atomically accumulated)
+  // power-of-two operand scales: from the bit pattern of a device-side max |x| (when given) or a host constant
+  const uint32_t* a_amax; const uint32_t* b_amax; float a_scale, b_scale;
+  float alpha; const float* alpha_dev;
+  // modes 1 / 2 (rows are decoder positions n = (t-1)*B + b, columns are vocabulary ids)
+  const int64_t* targets; int64_t tgt_stride_b; const int64_t* lengths; int B;
+  float* part; int* part_idx;            // mode 1: [nsplit][M][4] (max, sumexp, target logit, argmax value), [nsplit][M]
+  const float* lse; const float* grad_scale; int v0;   // mode 2: C = P[:, v0:v0+N]
+  const uint64_t* gumbel_seed; uint32_t gumbel_salt;   // mode 1: when set, the arg-max is taken over logits + Gumbel noise
+  unsigned long long* dbg;   // optional: pipeline milestone timestamps (ns) of CTA (0,0,0), profiles/probes/tc16_timeline.py
+};
+
+bool enabled();     // DVAE_GEMM_IMPL=f16
+bool shape_ok(const float* A, int64_t lda, int trans_a, const float* B, int64_t ldb, int trans_b, int M, int N, int K);
+bool supported(const float* A, int64_t lda, int trans_a, const float* B, int64_t ldb, int trans_b, int M, int N, int K);
+int linear(const float* A, int64_t lda, int trans_a, const float* B, int64_t ldb, int trans_b, float* C, int64_t ldc, int M,
+           int N, int K, const float* bias, const float* bias2, float beta, int act, const GemmHints& hints, cudaStream_t st);
+int ce_partials(const float* h, int64_t ldh, int N, int B, int H, int V, const float* w, const float* bias,
+                const int64_t* targets, int64_t tgt_stride_b, const int64_t* lengths, int tiles_per_split, int nsplit,
+                float* part, int* part_idx, const uint64_t* gumbel_seed, uint32_t gumbel_salt, cudaStream_t st);
+int softmax_grad(const float* h, int64_t ldh, int N, int B, int H, int v0, int vc, const float* w, const float* bias,
+                 const int64_t* targets, int64_t tgt_stride_b, const int64_t* lengths, const float* lse,
+                 const float* grad_scale, float* P, int64_t ldp, cudaStream_t st);
+
+}  // namespace tc16
+}  // namespace dvae

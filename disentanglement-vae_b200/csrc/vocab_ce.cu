@@ -10,6 +10,7 @@
 #include <math.h>
 
 #include "gemm_simt.cuh"
+#include "tc_gemm16.cuh"
 
 namespace dvae {
 
@@ -217,6 +218,9 @@ __global__ void __launch_bounds__(GCE::NT) vocab_p_kernel(PArgs p) {
 
 // per-(row, vocabulary split) partials: tensor-core kernel when the shape allows, fp32 SIMT otherwise
 static int ce_partials(const CeArgs& p, cudaStream_t st) {
+  if (!force_simt_gemm() && p.N >= 64 && p.V >= 128 && p.H >= 32 && tc16::supported(p.h, p.ldh, 0, p.w, p.H, 0, p.N, p.V, p.H))
+    return tc16::ce_partials(p.h, p.ldh, p.N, p.B, p.H, p.V, p.w, p.bias, p.targets, p.tgt_stride_b, p.lengths,
+                             p.tiles_per_split, p.nsplit, p.part, p.part_idx, p.gumbel_seed, p.gumbel_salt, st);
   if (!force_simt_gemm() && p.N >= 64 && p.V >= 128 && p.H >= 32 && tc::tc_linear_supported(p.h, p.ldh, p.w, p.H, p.N, p.V, p.H))
     return tc::tc_ce_partials(p.h, p.ldh, p.N, p.B, p.H, p.V, p.w, p.bias, p.targets, p.tgt_stride_b, p.lengths,
                               p.tiles_per_split, p.nsplit, p.part, p.part_idx, p.gumbel_seed, p.gumbel_salt, st);
@@ -290,12 +294,20 @@ extern "C" int dvae_vocab_ce_bwd(const float* h, int64_t ldh, int T1, int B, int
   p.h = h; p.ldh = ldh; p.w = w; p.bias = bias; p.targets = targets; p.tgt_stride_b = tgt_stride_b;
   p.lengths = lengths; p.lse = lse; p.grad_scale = grad_scale_dev; p.N = N; p.B = B; p.H = H; p.V = V;
   p.P = ws; p.ldp = vc_max;
+  // P = (softmax - onehot) * mask * grad_scale / B: |P| <= grad_scale / B, so a power-of-two scale near B brings it to
+  // O(1) for the fp16-split GEMMs (exact; undone in their epilogue)
+  GemmHints ph;
+  ph.a_scale = 1.f;
+  while (ph.a_scale * 2.f <= (float)B) ph.a_scale *= 2.f;
   int chunk = 0;
   for (int v0 = 0; v0 < V; v0 += vc_max, ++chunk) {
     const int vc = min(vc_max, V - v0);
     p.v0 = v0; p.vc = vc;
     int rc;
-    if (!force_simt_gemm() && N >= 64 && vc >= 128 && H >= 32 && tc::tc_linear_supported(h, ldh, w, H, N, vc, H)) {
+    if (!force_simt_gemm() && N >= 64 && vc >= 128 && H >= 32 && tc16::supported(h, ldh, 0, w, H, 0, N, vc, H)) {
+      if ((rc = tc16::softmax_grad(h, ldh, N, B, H, v0, vc, w, bias, targets, tgt_stride_b, lengths, lse, grad_scale_dev, ws,
+                                   vc_max, st))) return rc;
+    } else if (!force_simt_gemm() && N >= 64 && vc >= 128 && H >= 32 && tc::tc_linear_supported(h, ldh, w, H, N, vc, H)) {
       if ((rc = tc::tc_softmax_grad(h, ldh, N, B, H, v0, vc, w, bias, targets, tgt_stride_b, lengths, lse, grad_scale_dev, ws,
                                     vc_max, st))) return rc;
     } else {
@@ -304,10 +316,12 @@ extern "C" int dvae_vocab_ce_bwd(const float* h, int64_t ldh, int T1, int B, int
       DVAE_LAUNCH_CHECK();
     }
     // d_h [N,H] (+)= P [N,vc] . W[v0:v0+vc, :]        (B stored [K=vc][N=H])
-    if ((rc = linear_impl(ws, vc_max, 0, w + (int64_t)v0 * H, H, 1, d_h, lddh, N, H, vc, nullptr, nullptr, chunk ? 1.f : 0.f, 0, st))) return rc;
+    Fork fork(st);         // the three consumers of this chunk of P are independent of each other
+    if ((rc = linear_impl_ex(ws, vc_max, 0, w + (int64_t)v0 * H, H, 1, d_h, lddh, N, H, vc, nullptr, nullptr, chunk ? 1.f : 0.f, 0, ph, st))) return rc;
     // d_w[v0:v0+vc, :] = P^T [vc,N] . h [N,H]
-    if ((rc = linear_impl(ws, vc_max, 1, h, ldh, 1, d_w + (int64_t)v0 * H, H, vc, H, N, nullptr, nullptr, 0.f, 0, st))) return rc;
-    if ((rc = colsum_impl(ws, vc_max, N, vc, d_bias + v0, 0.f, st))) return rc;
+    if ((rc = linear_impl_ex(ws, vc_max, 1, h, ldh, 1, d_w + (int64_t)v0 * H, H, vc, H, N, nullptr, nullptr, 0.f, 0, ph, fork.side(0)))) return rc;
+    if ((rc = colsum_impl(ws, vc_max, N, vc, d_bias + v0, 0.f, fork.side(1)))) return rc;
+    if ((rc = fork.join())) return rc;       // the next chunk overwrites P
   }
   return DVAE_OK;
 }

@@ -61,6 +61,18 @@ int dvae_tc_linear(const float* A, int64_t lda, int trans_a, const float* B, int
                    float* C, int64_t ldc, int M, int N, int K, const float* bias, const float* bias2,
                    float beta, int act, int passes, void* stream);
 
+/* Same contract again, second-generation tensor-core kernel (tc_gemm16.cu): the fp32 operands are split on the fly
+ * into fp16 (hi, lo * 2^11) planes -- 22 mantissa bits each -- and multiplied by tcgen05.mma.kind::f16 into two TMEM
+ * accumulators (hi*hi | hi*lo + lo*hi); three K=16 MMAs per 16 k instead of 3xTF32's six K=8 ones, and a third of the
+ * shared-memory traffic.  fp16 has a narrow exponent range, so each operand is first multiplied by a power of two:
+ * `a_scale` / `b_scale` (host constants, 1 = none) or, when `a_amax_bits` / `b_amax_bits` (device, may be NULL) is
+ * given, 2^(13 - floor(log2 amax)) from the bit pattern of a device-side max |x|.  The product is unscaled in the
+ * epilogue.  K-major operands need 16-byte alignment, ld % 4 == 0 and K % 4 == 0; returns DVAE_EINVAL otherwise. */
+int dvae_tc16_linear(const float* A, int64_t lda, int trans_a, const float* B, int64_t ldb, int trans_b,
+                     float* C, int64_t ldc, int M, int N, int K, const float* bias, const float* bias2,
+                     float beta, int act, float a_scale, float b_scale, const uint32_t* a_amax_bits,
+                     const uint32_t* b_amax_bits, void* stream);
+
 /* out[n] = sum_m X[m, n] (+ out[n] if beta == 1); X is [M,N] row-major with row stride ldx. */
 int dvae_colsum(const float* X, int64_t ldx, int M, int N, float* out, float beta, void* stream);
 

@@ -99,6 +99,69 @@ def test_tc_linear_3xtf32(lib, L, M, N, K, ta, tb):
     assert rel(c_d, want + bias + 1.0) < max(2e-6, 1e-8 * K)
 
 
+@pytest.mark.parametrize("M,N,K", [(128, 128, 32), (128, 128, 256), (256, 384, 64), (130, 257, 100), (2688, 1024, 256), (100, 10000, 256),
+                                   (1024, 256, 2688), (2816, 256, 1024), (64, 64, 36)])
+@pytest.mark.parametrize("ta,tb", [(0, 0), (0, 1), (1, 1), (1, 0)])
+def test_tc16_linear_fp16_split(lib, L, M, N, K, ta, tb):
+    """fp16 (hi, lo)-split tcgen05 GEMM: fp32-grade against float64, incl. transposed operands, partial tiles, split-K,
+    multi-tile CTAs and the operand scales (host constant and device amax) on tiny-magnitude 'gradient' operands."""
+    rng = np.random.default_rng(M + 3 * N + 7 * K + ta * 2 + tb)
+    A = (rng.standard_normal((M, K)) / np.sqrt(K)).astype(np.float32)
+    Bm = rng.standard_normal((N, K)).astype(np.float32)
+    bias = rng.standard_normal(N).astype(np.float32)
+
+    def stored(X, t):
+        S = np.ascontiguousarray(X.T if t else X)
+        ld = (S.shape[1] + 3) // 4 * 4
+        buf = torch.zeros(S.shape[0], ld, device="cuda")
+        buf[:, :S.shape[1]] = torch.from_numpy(S).cuda()
+        _KEEP.append(buf)
+        return buf, ld
+    a_d, lda = stored(A, ta)
+    b_d, ldb = stored(Bm, tb)
+    want = A.astype(np.float64) @ Bm.astype(np.float64).T + bias
+    bias_d = dev(bias)
+    st = L.stream_ptr()
+    tol = max(2e-6, 1e-8 * K)
+    c_d = torch.full((M, N), 7.0, device="cuda")
+    L.check(lib.dvae_tc16_linear(L.ptr(a_d), lda, ta, L.ptr(b_d), ldb, tb, L.ptr(c_d), N, M, N, K, L.ptr(bias_d), None,
+                                 0.0, 0, 1.0, 1.0, None, None, st), "tc16_linear")
+    assert rel(c_d, want) < tol, rel(c_d, want)
+    # beta accumulate + second bias
+    c_d = torch.ones(M, N, device="cuda")
+    L.check(lib.dvae_tc16_linear(L.ptr(a_d), lda, ta, L.ptr(b_d), ldb, tb, L.ptr(c_d), N, M, N, K, L.ptr(bias_d), L.ptr(bias_d),
+                                 1.0, 0, 1.0, 1.0, None, None, st), "tc16_linear")
+    assert rel(c_d, want + bias + 1.0) < tol
+    # a "gradient" A operand far below fp16's normal range: exact with the measured-amax scale, and with a host scale
+    tiny = 1e-9
+    a_t, _ = stored(A * np.float32(tiny), ta)
+    amax = torch.tensor([float(np.abs(A * np.float32(tiny)).max())], device="cuda").view(torch.int32)
+    want_t = (A * np.float32(tiny)).astype(np.float64) @ Bm.astype(np.float64).T
+    c_d = torch.zeros(M, N, device="cuda")
+    L.check(lib.dvae_tc16_linear(L.ptr(a_t), lda, ta, L.ptr(b_d), ldb, tb, L.ptr(c_d), N, M, N, K, None, None,
+                                 0.0, 0, 1.0, 1.0, L.ptr(amax), None, st), "tc16_linear")
+    assert rel(c_d, want_t) < tol, rel(c_d, want_t)
+    c_d = torch.zeros(M, N, device="cuda")
+    L.check(lib.dvae_tc16_linear(L.ptr(a_t), lda, ta, L.ptr(b_d), ldb, tb, L.ptr(c_d), N, M, N, K, None, None,
+                                 0.0, 0, float(2 ** 28), 1.0, None, None, st), "tc16_linear")
+    assert rel(c_d, want_t) < tol, rel(c_d, want_t)
+
+
+def test_tc16_linear_tanh_and_rejects_unaligned(lib, L):
+    rng = np.random.default_rng(5)
+    M, N, K = 128, 512, 64
+    A = rng.standard_normal((M, K)).astype(np.float32) * 0.3
+    Bm = rng.standard_normal((N, K)).astype(np.float32) * 0.3
+    bias = rng.standard_normal(N).astype(np.float32)
+    c_d = torch.zeros(M, N, device="cuda")
+    L.check(lib.dvae_tc16_linear(L.ptr(dev(A)), K, 0, L.ptr(dev(Bm)), K, 0, L.ptr(c_d), N, M, N, K, L.ptr(dev(bias)), None,
+                                 0.0, 1, 1.0, 1.0, None, None, L.stream_ptr()), "tc16_linear")
+    assert rel(c_d, np.tanh(A.astype(np.float64) @ Bm.astype(np.float64).T + bias)) < 2e-6
+    x = torch.zeros(64 * 70, device="cuda")
+    rc = lib.dvae_tc16_linear(L.ptr(x), 70, 0, L.ptr(x), 70, 0, L.ptr(c_d), 64, 64, 64, 70, None, None, 0.0, 0, 1.0, 1.0, None, None, None)
+    assert rc == -1 and b"aligned" in lib.dvae_last_error_string()
+
+
 def test_linear_strided_output_and_colsum(lib, L):
     rng = np.random.default_rng(0)
     A = rng.standard_normal((70, 33)).astype(np.float32)

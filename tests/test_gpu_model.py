@@ -183,6 +183,32 @@ def test_train_step_matches_oracle_synthetic(dvae, bi, H, E, V, B, T):
         assert _rel(prm.grad, grads[k]) < 1e-3, k
 
 
+@pytest.mark.parametrize("env", [{"DVAE_GEMM_IMPL": "f16"}, {"DVAE_FORK": "0"}, {"DVAE_LSTM_IMPL": "simt"}, {"DVAE_LSTM_GROUPS": "2"}])
+def test_train_step_alternative_kernel_paths_match_oracle(dvae, env, monkeypatch):
+    """The opt-in / A-B kernel selections keep the same parity gates: fp16-split tcgen05 GEMMs (incl. the max|dG| operand
+    scale reported by the LSTM backward kernel), no fork/join side streams, fp32 SIMT persistent LSTM, two row groups."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    dvae.set_seed(10)
+    E = H = 256
+    V, B, T = 2000, 40, 9
+    p = _params(embedding_dim=E, hidden_dim=H, bidirectional_encoder=True,
+                latent_dims={"total": 16, "polarity": 1, "uncertainty": 1})
+    vae = dvae.build_vae(p, V, None, {"uncertainty": 1, "polarity": 1}, torch.device("cuda"), 2, 3)
+    vae.train()
+    gen = torch.Generator().manual_seed(1234)
+    X, lengths, Y = _synthetic(B, T, V, gen, ("uncertainty", "polarity"))
+    eps = torch.randn(B, 16, generator=gen)
+    klw = {"default": 0.4, "polarity": 0.005, "uncertainty": 0.005}
+    out = vae(X.cuda(), lengths.cuda(), teacher_forcing_prob=1.0, eps=eps.cuda())
+    total, L = dvae.losses.compute_all_losses(vae, out, X.cuda(), Y, lengths.cuda(), klw)
+    total.backward()
+    fw, grads = _oracle_run(vae, X, lengths, Y, eps, klw)
+    assert abs(total.item() - fw["total_loss"]) <= 1e-5 * abs(fw["total_loss"])
+    for k, prm in vae.named_parameters():
+        assert _rel(prm.grad, grads[k]) < 1e-3, k
+
+
 def test_dropout_train_step_matches_oracle_with_replayed_masks(dvae):
     """encoder/decoder dropout 0.5 (the reproduction configs' value): the Philox masks the kernels
     used are re-generated through the same C-ABI call and handed to the oracle."""
