@@ -30,6 +30,8 @@ SIGNATURES = {
     "dvae_last_error_string": (C.c_char_p, []),
     "dvae_version": (_i, []),
     "dvae_launch_count": (_l, []),
+    "dvae_defer_joins": (_i, [_i]),
+    "dvae_join_side_streams": (_i, [_p]),
     "dvae_linear": (_i, [_p, _l, _i, _p, _l, _i, _p, _l, _i, _i, _i, _p, _p, _f, _i, _p]),
     "dvae_tc_linear": (_i, [_p, _l, _i, _p, _l, _i, _p, _l, _i, _i, _i, _p, _p, _f, _i, _i, _p]),
     "dvae_tc16_linear": (_i, [_p, _l, _i, _p, _l, _i, _p, _l, _i, _i, _i, _p, _p, _f, _i, _f, _f, _p, _p, _p]),

@@ -23,12 +23,16 @@ bool force_simt_gemm() {
 }
 
 // ---- fork / join side streams ---------------------------------------------------------------------
+int join_side_streams(cudaStream_t main);
+void set_defer_joins(bool on);
 namespace {
 struct SideStreams {
   cudaStream_t s[3];
   cudaEvent_t fork_ev, join_ev[3];
   bool ok = false;
+  bool pending[3] = {false, false, false};     // detached work (deferred joins)
 };
+thread_local bool g_defer_joins = false;
 SideStreams* side_streams() {
   static thread_local SideStreams* per_dev[64] = {};
   int dev = 0;
@@ -72,11 +76,42 @@ int Fork::join() {
       DVAE_CUDA(cudaEventRecord(ss->join_ev[i], ss->s[i]));
       DVAE_CUDA(cudaStreamWaitEvent(main_, ss->join_ev[i], 0));
       used_[i] = false;
+      ss->pending[i] = false;      // stream order: everything detached earlier on this side stream is covered too
     }
   return DVAE_OK;
 }
+int Fork::join_or_defer() {
+  if (!ok_ || !g_defer_joins) return join();
+  SideStreams* ss = side_streams();
+  for (int i = 0; i < 3; ++i)
+    if (used_[i]) {
+      ss->pending[i] = true;
+      used_[i] = false;
+    }
+  return DVAE_OK;
+}
+int join_side_streams(cudaStream_t main) {
+  SideStreams* ss = side_streams();
+  if (!ss) return DVAE_OK;
+  for (int i = 0; i < 3; ++i)
+    if (ss->pending[i]) {
+      DVAE_CUDA(cudaEventRecord(ss->join_ev[i], ss->s[i]));
+      DVAE_CUDA(cudaStreamWaitEvent(main, ss->join_ev[i], 0));
+      ss->pending[i] = false;
+    }
+  return DVAE_OK;
+}
+void set_defer_joins(bool on) { g_defer_joins = on; }
 }  // namespace dvae
 
+extern "C" int dvae_defer_joins(int on) {
+  dvae::set_defer_joins(on != 0);
+  return DVAE_OK;
+}
+extern "C" int dvae_join_side_streams(void* stream) {
+  dvae::set_defer_joins(false);
+  return dvae::join_side_streams((cudaStream_t)stream);
+}
 extern "C" const char* dvae_last_error_string(void) { return dvae::g_err; }
 extern "C" int dvae_version(void) { return 100; }
 extern "C" int64_t dvae_launch_count(void) { return dvae::g_launches.load(); }

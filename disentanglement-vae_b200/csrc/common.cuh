@@ -52,6 +52,10 @@ class Fork {
   explicit Fork(cudaStream_t main);
   cudaStream_t side(int i);      // i in [0, 3); returns the main stream when forking is disabled
   int join();                    // main waits for every side stream that was used; returns a DVAE_* code
+  // Like join(), unless the caller enabled deferred joins (dvae_defer_joins): then the side streams keep running past
+  // this call -- e.g. a layer's weight-gradient GEMMs overlap the next layer's recurrence -- until
+  // dvae_join_side_streams().  Only for work whose inputs / outputs nothing on the main stream touches before that.
+  int join_or_defer();
  private:
   cudaStream_t main_;
   bool used_[3] = {false, false, false};

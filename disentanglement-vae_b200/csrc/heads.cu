@@ -427,8 +427,8 @@ extern "C" int dvae_latent_heads_bwd(const float* ctx, int B, int C, int S, cons
     if ((rc = linear_impl_ex(dp, 2 * Z, 1, ctx, C, 1, d_w_c2p, C, 2 * Z, C, B, nullptr, nullptr, 0.f, 0, grad_hints, fork2.side(2)))) return rc;
     if ((rc = linear_impl_ex(dp, 2 * Z, 0, w_c2p, C, 1, d_ctx, C, B, C, 2 * Z, nullptr, nullptr, 0.f, 0, grad_hints, st))) return rc;
     if ((rc = colsum_impl(dp, 2 * Z, B, 2 * Z, d_b_c2p, 0.f, st))) return rc;
-    if ((rc = fork2.join())) return rc;
+    if ((rc = fork2.join_or_defer())) return rc;
   }
-  if ((rc = fork.join())) return rc;
+  if ((rc = fork.join_or_defer())) return rc;
   return DVAE_OK;
 }

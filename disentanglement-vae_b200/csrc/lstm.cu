@@ -329,7 +329,9 @@ int lstm_seq_bwd_impl(const float* x, int64_t ldx, int T, int B, int I, int H, i
       a.dird0 = dird0; a.lengths = lengths; a.T = T; a.B = B; a.D = D; a.n_slices = ceil_div(B, 16); a.d_off = 0;
       a.amax_out = nullptr;
       if (tc_lstm_supported(H)) {      // the tcgen05 kernel also reports max |dG|: the operand scale of the GEMMs below
-        amax = reinterpret_cast<uint32_t*>(ws + state_floats(B, H, D) + 4LL * D * H * H);
+        // 8 rotating slots: with deferred joins the previous layers' GEMMs may still be reading theirs
+        static thread_local unsigned slot = 0;
+        amax = reinterpret_cast<uint32_t*>(ws + state_floats(B, H, D) + 4LL * D * H * H) + 4 * (slot++ & 7);
         DVAE_CUDA(cudaMemsetAsync(amax, 0, sizeof(uint32_t), st));
         a.amax_out = amax;
       }
@@ -416,7 +418,7 @@ int lstm_seq_bwd_impl(const float* x, int64_t ldx, int T, int B, int I, int H, i
     }
   }
   {
-    int rc = fork.join();
+    int rc = fork.join_or_defer();
     if (rc) return rc;
   }
   return DVAE_OK;
@@ -463,7 +465,7 @@ extern "C" int dvae_lstm_step(const float* x, int64_t ldx, int t, int T, int B, 
 }
 
 extern "C" int64_t dvae_lstm_state_ws_floats(int B, int H, int D) {
-  return dvae::state_floats(B, H, D) + 4LL * D * H * H + 4;   // + the max |dG| slot of the backward pass
+  return dvae::state_floats(B, H, D) + 4LL * D * H * H + 32;   // + the max |dG| slots of the backward pass
 }
 
 extern "C" int dvae_lstm_seq_fwd(const float* x, int64_t ldx, int T, int B, int I, int H, int D,

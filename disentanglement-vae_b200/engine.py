@@ -77,9 +77,14 @@ class TrainEngine:
         h_top = pl.decode_forced(P, self.inputs, m.sos_token_idx, True)
         pl.vocab_ce(P, h_top, self.inputs, self.lengths)
         g_top = pl.vocab_ce_bwd(P, G, h_top, self.inputs, self.lengths, None)
-        g_hid = pl.decode_bwd(P, G, g_top, emb_grad="decoder.embedding.weight" in m._layout)
-        g_ctx = pl.heads_bwd(P, G, pl.ctx, pl.eps, self.labels, self.kl_w, g_hid)
-        pl.encode_bwd(P, G, self.inputs, self.lengths, g_ctx, emb_grad="encoder.embedding.weight" in m._layout)
+        # weight-gradient GEMMs of each layer keep running on side streams while the next layer's recurrence starts
+        check(self.lib.dvae_defer_joins(1), "dvae_defer_joins")
+        try:
+            g_hid = pl.decode_bwd(P, G, g_top, emb_grad="decoder.embedding.weight" in m._layout)
+            g_ctx = pl.heads_bwd(P, G, pl.ctx, pl.eps, self.labels, self.kl_w, g_hid)
+            pl.encode_bwd(P, G, self.inputs, self.lengths, g_ctx, emb_grad="encoder.embedding.weight" in m._layout)
+        finally:
+            check(self.lib.dvae_join_side_streams(st), "dvae_join_side_streams")
 
     def _optim(self):
         st = _lib.stream_ptr()

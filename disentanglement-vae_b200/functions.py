@@ -69,12 +69,17 @@ class _EncDecFn(Function):
             G["decoder.embedding.weight"].zero_()
         if g_htop is None:
             g_htop = torch.zeros_like(plan.d_hs[-1])
-        g_hid = plan.decode_bwd(P, G, _c(g_htop), emb_grad=dec_emb)
-        kl_w = _c(g_kl)
-        g_c = plan.heads_bwd(P, G, plan.ctx, ctx.eps, None, kl_w, g_hid, _c(g_z), _c(g_mu), _c(g_logvar), _c(g_dsc))
-        if g_ctx is not None:
-            g_c.add_(g_ctx)
-        plan.encode_bwd(P, G, ctx.inputs, ctx.lengths, g_c, emb_grad=enc_emb)
+        lib = _lib.load()
+        check(lib.dvae_defer_joins(1), "dvae_defer_joins")      # weight-gradient GEMMs overlap the next layer's recurrence
+        try:
+            g_hid = plan.decode_bwd(P, G, _c(g_htop), emb_grad=dec_emb)
+            kl_w = _c(g_kl)
+            g_c = plan.heads_bwd(P, G, plan.ctx, ctx.eps, None, kl_w, g_hid, _c(g_z), _c(g_mu), _c(g_logvar), _c(g_dsc))
+            if g_ctx is not None:
+                g_c.add_(g_ctx)
+            plan.encode_bwd(P, G, ctx.inputs, ctx.lengths, g_c, emb_grad=enc_emb)
+        finally:
+            check(lib.dvae_join_side_streams(_lib.stream_ptr()), "dvae_join_side_streams")
         plan.busy = False
         names = list(model._layout.keys())
         skip = ("decoder.linear.weight", "decoder.linear.bias")

@@ -73,6 +73,15 @@ int dvae_tc16_linear(const float* A, int64_t lda, int trans_a, const float* B, i
                      float beta, int act, float a_scale, float b_scale, const uint32_t* a_amax_bits,
                      const uint32_t* b_amax_bits, void* stream);
 
+/* Independent kernels inside one call (e.g. the weight-gradient GEMMs of an LSTM layer) run on library-owned side
+ * streams and are joined back into `stream` before the call returns.  dvae_defer_joins(1) lets the backward entry
+ * points (dvae_lstm_seq_bwd, dvae_latent_heads_bwd) return with that side work still in flight, so that it overlaps
+ * the next layer's recurrence; the caller must then call dvae_join_side_streams(stream) -- which also switches the
+ * deferral off -- before anything consumes the weight / bias gradients (or before a graph capture ends).
+ * Per host thread.  Replaces nothing in the reference: it is scheduling of run.py:254's backward() work. */
+int dvae_defer_joins(int on);
+int dvae_join_side_streams(void* stream);
+
 /* out[n] = sum_m X[m, n] (+ out[n] if beta == 1); X is [M,N] row-major with row stride ldx. */
 int dvae_colsum(const float* X, int64_t ldx, int M, int N, float* out, float beta, void* stream);
 
