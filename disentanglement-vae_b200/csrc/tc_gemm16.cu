@@ -6,11 +6,13 @@
 // arg-max) for THREE K=16 MMAs per 16 k, where the 3xTF32 kernel (tc_gemm.cu) needs six K=8 ones and twice the
 // shared-memory bytes per k.  Shared-memory bandwidth is what bounds both kernels, so the work is organised to
 // touch SMEM as little as possible:
-//   warps 5-12 (producers): coalesced / sector-exact global loads straight into registers (no TMA landing zone),
-//              scale + split, 16-byte stores into the UMMA no-swizzle K-major core-matrix layout (bank-conflict free).
-//              MN-major sources (transposed operands of the backward GEMMs) are transposed in registers on the way,
-//              so the MMA only ever sees K-major tiles.  Per 128x128x32 k-block: 32 KB written, 48 KB read by the MMAs
-//              (the 3xTF32 kernel moves 224 KB).
+//   warp 5    (TMA): cp.async.bulk.tensor (no swizzle, zero fill handles every tail) of raw fp32 A / B k-blocks into a
+//              3-stage landing ring, so 96 KB of loads are in flight per SM (bytes in flight, not SMEM bandwidth or
+//              MMA issue, is what bounds these fp32-operand GEMMs: profiles/probes/tc16_timeline.py).
+//   warps 6-13 (converters): conflict-free LDS of the landed tile, scale + split, 16-byte stores into the UMMA
+//              no-swizzle K-major core-matrix layout (padded so that the stores are conflict-free too).  MN-major
+//              sources (transposed operands of the backward GEMMs) are transposed on the way, so the MMA only ever
+//              sees K-major tiles.
 //   warp 4    (MMA): elect.sync'ed single-thread issue from a warp-uniform branch (descriptors stay in uniform
 //              registers), 5-stage ring, tcgen05.commit frees ring slots and publishes accumulators.
 //   warps 0-3 (epilogue): double-buffered accumulators (2 x (D1, D2) = 512 TMEM columns) so read-out, bias /
@@ -28,16 +30,19 @@ namespace tc16 {
 
 using namespace tc;
 
-constexpr int BM = 128, BN = 128, BK = 32, STAGES = 5;
+constexpr int BM = 128, BN = 128, BK = 32, STAGES = 3 /* operand-plane ring */, RAW_STAGES = 2 /* TMA landing ring */;
 constexpr int T_LBO = 160, T_SBO = 4 * T_LBO;      // chunk(row, kc) at (row >> 3) * 640 + kc * 160 + (row & 7) * 16:
                                                    // core matrices (8 rows x 16 B) 160 B apart along K so that the 16
                                                    // chunks a warp stores per instruction spread over all banks
 constexpr int PLANE = (BM / 8) * T_SBO;            // one fp16 plane of a 128 x 32 tile: 10 KB
 constexpr int STAGE_BYTES = 4 * PLANE;             // A_hi, A_lo, B_hi, B_lo
-constexpr int EPI_WARPS = 4, MMA_WARP = 4, PROD_WARP0 = 5, PROD_WARPS = 8;
-constexpr int NUM_THREADS = (PROD_WARP0 + PROD_WARPS) * 32;      // 416
+constexpr int RAW_TILE = BM * BK * 4;              // one landed fp32 tile: 16 KB
+constexpr int RAW_BYTES = 2 * RAW_TILE;            // A, B
+constexpr int EPI_WARPS = 4, MMA_WARP = 4, TMA_WARP = 5, PROD_WARP0 = 6, PROD_WARPS = 16;
+constexpr int NUM_THREADS = (PROD_WARP0 + PROD_WARPS) * 32;      // 704: <= 93 registers per thread
 constexpr int EPI_SCRATCH_BYTES = 4 * 32 * 33 * 4;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 256 + EPI_SCRATCH_BYTES + 1024;
+constexpr int OFF_RAW = STAGES * STAGE_BYTES, OFF_BAR = OFF_RAW + RAW_STAGES * RAW_BYTES, OFF_SCRATCH = OFF_BAR + 256;
+constexpr int SMEM_BYTES = OFF_SCRATCH + EPI_SCRATCH_BYTES + 1024;
 constexpr int TMEM_COLS = 512;
 constexpr float kLoScale = 2048.f, kLoInv = 1.f / 2048.f;
 
@@ -56,47 +61,48 @@ __device__ __forceinline__ float scale_from_amax(const uint32_t* amax_bits, floa
   return __uint_as_float((unsigned)se << 23);
 }
 
-__device__ __forceinline__ uint32_t pack_hi_lo(float x0, float x1, uint32_t& lo) {
-  const __half2 h = __floats2half2_rn(x0, x1);
+// (x0, x1) * s -> packed fp16 hi pair (returned) and lo pair; packed fp32 arithmetic (FMUL2 / FFMA2)
+__device__ __forceinline__ uint32_t pack_hi_lo(float x0, float x1, float s, uint32_t& lo) {
+  const float2 x = __fmul2_rn(make_float2(x0, x1), make_float2(s, s));
+  const __half2 h = __float22half2_rn(x);
   const float2 hf = __half22float2(h);
-  const __half2 l = __floats2half2_rn((x0 - hf.x) * kLoScale, (x1 - hf.y) * kLoScale);
+  // (x - hi) * 2^11 = x * 2^11 - hi * 2^11 (both products exact)
+  const float2 r = __ffma2_rn(x, make_float2(kLoScale, kLoScale), __fmul2_rn(hf, make_float2(-kLoScale, -kLoScale)));
+  const __half2 l = __float22half2_rn(r);
   lo = *reinterpret_cast<const uint32_t*>(&l);
   return *reinterpret_cast<const uint32_t*>(&h);
 }
 
-// One k-block (128 rows x 32 k) of one operand -> 16 registers per producer thread (256 threads).
-//   K-major source ([rows, K] row-major): piece p = ptid + 256*i (i < 4) is the float4 at row p >> 3, k 4*(p & 7): the 8
-//     lanes of a row read 128 contiguous bytes (4 fully used lines per warp instruction).
-//   MN-major source ([K, rows] row-major): thread = (row ptid & 127, k half ptid >> 7), 16 scalar loads, each
-//     coalesced across the warp (lanes hold consecutive rows): the transposition happens in registers.
-__device__ __forceinline__ void load_tile(const float* __restrict__ X, int64_t ld, int mn_major, int ptid, int row0, int rows,
-                                          int k0, int K, float (&v)[16]) {
+// One landed k-block (128 rows x 32 k, fp32) of one operand -> 8 registers per converter thread (512 threads).
+//   K-major source: the tile is [128 rows][32 k]; piece p = ptid + 512*i (i < 2) is the float4 at row p >> 3, k 4*(p & 7):
+//     a warp reads 512 contiguous bytes per instruction (conflict-free).
+//   MN-major source: the tile is [32 k][128 rows]; thread = (row ptid & 127, k chunk ptid >> 7), 8 scalar reads with the
+//     warp's lanes on consecutive rows (conflict-free): the transposition happens in registers.
+__device__ __forceinline__ void load_tile(uint32_t raw, int mn_major, int ptid, float (&v)[8]) {
   if (!mn_major) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int pc = ptid + 256 * i, row = row0 + (pc >> 3), k = k0 + 4 * (pc & 7);
-      float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (row < rows && k < K) t = __ldcg(reinterpret_cast<const float4*>(X + (int64_t)row * ld + k));   // K % 4 == 0
-      v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
+    for (int i = 0; i < 2; ++i) {
+      const uint4 t = lds128(raw + (uint32_t)(ptid + 512 * i) * 16);
+      v[4 * i] = __uint_as_float(t.x); v[4 * i + 1] = __uint_as_float(t.y);
+      v[4 * i + 2] = __uint_as_float(t.z); v[4 * i + 3] = __uint_as_float(t.w);
     }
   } else {
-    const int row = row0 + (ptid & 127), kk = k0 + 16 * (ptid >> 7);
-    const float* src = X + (int64_t)kk * ld + row;
+    const uint32_t src = raw + (uint32_t)(8 * (ptid >> 7)) * (BM * 4) + (uint32_t)(ptid & 127) * 4;
 #pragma unroll
-    for (int j = 0; j < 16; ++j) v[j] = (row < rows && kk + j < K) ? __ldcg(src + (int64_t)j * ld) : 0.f;
+    for (int j = 0; j < 8; ++j) v[j] = lds32(src + j * (BM * 4));
   }
 }
 
 // scale, split into fp16 (hi, lo) and store into the stage's operand planes (hi plane at `plane_hi`, lo at + PLANE)
-__device__ __forceinline__ void store_tile(uint32_t plane_hi, int mn_major, int ptid, float s, const float (&v)[16]) {
+__device__ __forceinline__ void store_tile(uint32_t plane_hi, int mn_major, int ptid, float s, const float (&v)[8]) {
   if (!mn_major) {
     const int odd = ptid & 1;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int pc = ptid + 256 * i, row = pc >> 3, kc = (pc & 7) >> 1;
+    for (int i = 0; i < 2; ++i) {
+      const int pc = ptid + 512 * i, row = pc >> 3, kc = (pc & 7) >> 1;
       uint32_t lo0, lo1;
-      const uint32_t hi0 = pack_hi_lo(v[4 * i] * s, v[4 * i + 1] * s, lo0);
-      const uint32_t hi1 = pack_hi_lo(v[4 * i + 2] * s, v[4 * i + 3] * s, lo1);
+      const uint32_t hi0 = pack_hi_lo(v[4 * i], v[4 * i + 1], s, lo0);
+      const uint32_t hi1 = pack_hi_lo(v[4 * i + 2], v[4 * i + 3], s, lo1);
       // lanes (2j, 2j+1) hold k 0-3 / 4-7 of one 8-k chunk: the even lane assembles the hi chunk, the odd lane the lo chunk
       const uint32_t r0 = __shfl_xor_sync(0xffffffffu, odd ? hi0 : lo0, 1);
       const uint32_t r1 = __shfl_xor_sync(0xffffffffu, odd ? hi1 : lo1, 1);
@@ -104,31 +110,31 @@ __device__ __forceinline__ void store_tile(uint32_t plane_hi, int mn_major, int 
       sts128(plane_hi + (odd ? PLANE : 0) + (uint32_t)(row >> 3) * T_SBO + (uint32_t)kc * T_LBO + (row & 7) * 16, chunk);
     }
   } else {
-    const int row = ptid & 127, half = ptid >> 7;
-    const uint32_t base = plane_hi + (uint32_t)(row >> 3) * T_SBO + (uint32_t)(2 * half) * T_LBO + (row & 7) * 16;
-#pragma unroll
-    for (int c = 0; c < 2; ++c) {
-      uint4 hi, lo;
-      hi.x = pack_hi_lo(v[8 * c + 0] * s, v[8 * c + 1] * s, lo.x);
-      hi.y = pack_hi_lo(v[8 * c + 2] * s, v[8 * c + 3] * s, lo.y);
-      hi.z = pack_hi_lo(v[8 * c + 4] * s, v[8 * c + 5] * s, lo.z);
-      hi.w = pack_hi_lo(v[8 * c + 6] * s, v[8 * c + 7] * s, lo.w);
-      sts128(base + c * T_LBO, hi);
-      sts128(base + c * T_LBO + PLANE, lo);
-    }
+    const int row = ptid & 127, kc = ptid >> 7;
+    const uint32_t base = plane_hi + (uint32_t)(row >> 3) * T_SBO + (uint32_t)kc * T_LBO + (row & 7) * 16;
+    uint4 hi, lo;
+    hi.x = pack_hi_lo(v[0], v[1], s, lo.x);
+    hi.y = pack_hi_lo(v[2], v[3], s, lo.y);
+    hi.z = pack_hi_lo(v[4], v[5], s, lo.z);
+    hi.w = pack_hi_lo(v[6], v[7], s, lo.w);
+    sts128(base, hi);
+    sts128(base + PLANE, lo);
   }
 }
 
-__global__ void __launch_bounds__(NUM_THREADS, 1) tc16_gemm_kernel(Params p) {
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+tc16_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, Params p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
-  uint64_t* full = bars;                       // [STAGES] producers -> MMA   (8 warp arrivals)
-  uint64_t* empty = bars + STAGES;             // [STAGES] MMA -> producers   (tcgen05.commit)
-  uint64_t* tmem_full = bars + 2 * STAGES;     // [2] MMA -> epilogue
-  uint64_t* tmem_empty = bars + 2 * STAGES + 2;  // [2] epilogue -> MMA (4 warp arrivals)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
-  float* epi_scratch = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 256);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
+  uint64_t* full = bars;                       // [STAGES] converters -> MMA   (8 warp arrivals)
+  uint64_t* empty = bars + STAGES;             // [STAGES] MMA -> converters   (tcgen05.commit)
+  uint64_t* raw_full = bars + 2 * STAGES;      // [RAW_STAGES] TMA -> converters (transaction bytes)
+  uint64_t* raw_empty = raw_full + RAW_STAGES; // [RAW_STAGES] converters -> TMA (8 warp arrivals)
+  uint64_t* tmem_full = raw_empty + RAW_STAGES;  // [2] MMA -> epilogue
+  uint64_t* tmem_empty = tmem_full + 2;          // [2] epilogue -> MMA (4 warp arrivals)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  float* epi_scratch = reinterpret_cast<float*>(smem + OFF_SCRATCH);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) DBG16(0);
@@ -145,11 +151,19 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc16_gemm_kernel(Params p) {
       mbar_init(&full[s], PROD_WARPS);
       mbar_init(&empty[s], 1);
     }
+    for (int s = 0; s < RAW_STAGES; ++s) {
+      mbar_init(&raw_full[s], 1);
+      mbar_init(&raw_empty[s], PROD_WARPS);
+    }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full[a], 1);
       mbar_init(&tmem_empty[a], EPI_WARPS);
     }
     fence_barrier_init();
+  }
+  if (warp == TMA_WARP && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
   }
   if (warp == MMA_WARP) tmem_alloc(tmem_slot, TMEM_COLS);
   tc_fence_before();
@@ -158,52 +172,54 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc16_gemm_kernel(Params p) {
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t smem_u = smem_u32(smem);
 
-  if (warp >= PROD_WARP0) {
-    // ===== producers: global -> registers -> (scale, split) -> operand planes =====
+  if (warp == TMA_WARP) {
+    // ===== TMA producer: raw fp32 k-blocks into the landing ring =====
+    if (lane == 0) {
+      int rs = 0, rphase = 0;
+      for (int nt = nt0; nt < nt1; ++nt) {
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(&raw_empty[rs], rphase ^ 1);
+          uint8_t* dst = smem + OFF_RAW + rs * RAW_BYTES;
+          mbar_expect_tx(&raw_full[rs], RAW_BYTES);
+          const int k0 = (kb0 + kb) * BK;
+          if (!p.a_mn) tma_load_2d(dst, &tmA, k0, m0, &raw_full[rs]);
+          else tma_load_2d(dst, &tmA, m0, k0, &raw_full[rs]);
+          if (!p.b_mn) tma_load_2d(dst + RAW_TILE, &tmB, k0, nt * BN, &raw_full[rs]);
+          else tma_load_2d(dst + RAW_TILE, &tmB, nt * BN, k0, &raw_full[rs]);
+          if (++rs == RAW_STAGES) { rs = 0; rphase ^= 1; }
+        }
+      }
+    }
+  } else if (warp >= PROD_WARP0) {
+    // ===== converters: landed fp32 tile -> (scale, split) -> fp16 operand planes =====
     const int ptid = tid - PROD_WARP0 * 32;
     const float sa = scale_from_amax(p.a_amax, p.a_scale), sb = scale_from_amax(p.b_amax, p.b_scale);
     const int n_items = (nt1 - nt0) * nkb;
-    // Three rotating register buffers: the loads of k-blocks i+1 and i+2 are in flight while k-block i is converted
-    // and stored (one L2 round trip per k-block would otherwise bound the kernel).
-    float a0[16], b0[16], a1[16], b1[16], a2[16], b2[16];
-    auto fetch = [&](int it, float (&va)[16], float (&vb)[16]) {
-      if (it < n_items) {
-        const int nt = nt0 + it / nkb, kb = it % nkb;
-        load_tile(p.A, p.lda, p.a_mn, ptid, m0, p.M, (kb0 + kb) * BK, p.K, va);
-        load_tile(p.Bm, p.ldb, p.b_mn, ptid, nt * BN, p.N, (kb0 + kb) * BK, p.K, vb);
-      }
-    };
-    int stage = 0, phase = 0, done = 0;
-    auto commit = [&](const float (&va)[16], const float (&vb)[16]) {
-      const bool mark = ptid == 0 && done == 12;
+    int stage = 0, phase = 0, rs = 0, rphase = 0;
+    for (int it = 0; it < n_items; ++it) {
+      const bool mark = ptid == 0 && it == 12;
       if (mark) DBG16(2);
-      mbar_wait(&empty[stage], phase ^ 1);
+      mbar_wait(&raw_full[rs], rphase);
       if (mark) DBG16(3);
+      float va[8], vb[8];
+      const uint32_t raw = smem_u + OFF_RAW + rs * RAW_BYTES;
+      load_tile(raw, p.a_mn, ptid, va);
+      load_tile(raw + RAW_TILE, p.b_mn, ptid, vb);
+      mbar_wait(&empty[stage], phase ^ 1);
       const uint32_t st = smem_u + stage * STAGE_BYTES;
       store_tile(st, p.a_mn, ptid, sa, va);
       store_tile(st + 2 * PLANE, p.b_mn, ptid, sb, vb);
       if (mark) DBG16(4);
       fence_proxy_async();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&full[stage]);
+      if (lane == 0) {
+        mbar_arrive(&full[stage]);
+        mbar_arrive(&raw_empty[rs]);
+      }
       if (mark) DBG16(5);
-      if (ptid == 0 && done == 13) DBG16(6);
+      if (ptid == 0 && it == 13) DBG16(6);
       if (++stage == STAGES) { stage = 0; phase ^= 1; }
-      ++done;
-    };
-    fetch(0, a0, b0);
-    fetch(1, a1, b1);
-    for (int it = 0; it < n_items; it += 3) {
-      fetch(it + 2, a2, b2);
-      commit(a0, b0);
-      if (it + 1 < n_items) {
-        fetch(it + 3, a0, b0);
-        commit(a1, b1);
-      }
-      if (it + 2 < n_items) {
-        fetch(it + 4, a1, b1);
-        commit(a2, b2);
-      }
+      if (++rs == RAW_STAGES) { rs = 0; rphase ^= 1; }
     }
   } else if (warp == MMA_WARP) {
     // ===== MMA issuer =====
@@ -269,31 +285,29 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc16_gemm_kernel(Params p) {
       if (tid == 0 && tile == 0) DBG16(14);
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
-        float v[32];
-        {
-          float w[32];
-          const uint32_t ta = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * 256 + c * 32;
-          tmem_ld32(ta, v);
-          tmem_ld32(ta + 128, w);
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = fmaf(w[j], kLoInv, v[j]) * oscale;
-        }
         const int col0 = n0 + c * 32;
         if (col0 >= p.N) continue;                       // warp-uniform
+        const uint32_t ta = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * 256 + c * 32;
         if (p.mode != 1) {
           // modes 0 / 2 store a [32 rows x 32 cols] chunk: transpose it through padded shared memory so each
           // store instruction covers 32 consecutive columns of one row (coalesced) instead of 32 different rows
           const uint32_t sc = smem_u32(epi_scratch) + warp * (32 * 33 * 4);
-          if (p.mode == 2) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const int col = col0 + j;
-              v[j] = (row_scale == 0.f || col >= p.N) ? 0.f
-                     : (expf(v[j] + __ldg(p.bias + col) - row_lse) - (col == tgt ? 1.f : 0.f)) * row_scale;
+          for (int hh = 0; hh < 2; ++hh) {
+            float v[16], w[16];
+            tmem_ld16(ta + hh * 16, v);
+            tmem_ld16(ta + 128 + hh * 16, w);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              float x = fmaf(w[j], kLoInv, v[j]) * oscale;
+              if (p.mode == 2) {
+                const int col = col0 + hh * 16 + j;
+                x = (row_scale == 0.f || col >= p.N) ? 0.f
+                    : (expf(x + __ldg(p.bias + col) - row_lse) - (col == tgt ? 1.f : 0.f)) * row_scale;
+              }
+              sts32(sc + (lane * 33 + hh * 16 + j) * 4, x);
             }
           }
-#pragma unroll
-          for (int j = 0; j < 32; ++j) sts32(sc + (lane * 33 + j) * 4, v[j]);
           __syncwarp();
           const int col = col0 + lane;
           const int r0 = m0 + quarter * 32;
@@ -331,20 +345,24 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc16_gemm_kernel(Params p) {
           __syncwarp();
           continue;
         }
-        if (!row_ok) continue;
-        {
-          // online log-softmax statistics of this row over the tile's columns (logits never leave registers)
-          float tmax = -INFINITY;
-          const bool sample = p.gumbel_seed != nullptr;
-          const uint64_t gseed = sample ? *p.gumbel_seed : 0;
+        // mode 1: online log-softmax statistics of this row over the tile's columns (logits never leave registers)
+        const bool sample = p.gumbel_seed != nullptr;
+        const uint64_t gseed = sample ? *p.gumbel_seed : 0;
 #pragma unroll
-          for (int j4 = 0; j4 < 32; j4 += 4) {
+        for (int hh = 0; hh < 2; ++hh) {
+          float v[16], w[16];
+          tmem_ld16(ta + hh * 16, v);
+          tmem_ld16(ta + 128 + hh * 16, w);
+          if (!row_ok) continue;
+          float tmax = -INFINITY;
+#pragma unroll
+          for (int j4 = 0; j4 < 16; j4 += 4) {
             float g[4] = {0.f, 0.f, 0.f, 0.f};
-            if (sample) gumbel4(gseed, p.gumbel_salt, row, col0 + j4, (p.N + 3) >> 2, g);
+            if (sample) gumbel4(gseed, p.gumbel_salt, row, col0 + hh * 16 + j4, (p.N + 3) >> 2, g);
 #pragma unroll
             for (int jj = 0; jj < 4; ++jj) {
-              const int j = j4 + jj, col = col0 + j;
-              float x = col < p.N ? v[j] + __ldg(p.bias + col) : -INFINITY;
+              const int j = j4 + jj, col = col0 + hh * 16 + j;
+              float x = col < p.N ? fmaf(w[j], kLoInv, v[j]) * oscale + __ldg(p.bias + col) : -INFINITY;
               v[j] = x;
               tmax = fmaxf(tmax, x);
               const float xs = x + g[jj];
@@ -354,7 +372,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc16_gemm_kernel(Params p) {
           }
           if (tmax > rm) { rs *= expf(rm - tmax); rm = tmax; }
 #pragma unroll
-          for (int j = 0; j < 32; ++j) rs += expf(v[j] - rm);
+          for (int j = 0; j < 16; ++j) rs += expf(v[j] - rm);
         }
       }
       tc_fence_before();
@@ -379,18 +397,44 @@ bool supported(const float* A, int64_t lda, int trans_a, const float* B, int64_t
 }
 
 bool enabled() {
-  // Opt-in (DVAE_GEMM_IMPL=f16): on the cfg-2 shapes this kernel and the 3xTF32 one (tc_gemm.cu) both sit at about
-  // 1 us per 32 KB k-block -- bound by fp32-operand bytes in flight per SM, not by SMEM traffic or MMA issue
-  // (profiles/probes/tc16_perf.py, tc16_timeline.py) -- and the TMA ring of the older kernel hides slightly more latency.
+  // default; DVAE_GEMM_IMPL=tf32 keeps the 3xTF32 kernel (tc_gemm.cu) for A/B runs, =simt the fp32 SIMT kernels
   const char* e = getenv("DVAE_GEMM_IMPL");
-  return e && e[0] == 'f';
+  return !(e && (e[0] == 't' || e[0] == 's'));
 }
 
 bool shape_ok(const float* A, int64_t lda, int trans_a, const float* B, int64_t ldb, int trans_b, int M, int N, int K) {
-  // K-major operands are read with 16-byte loads along K
-  if (!trans_a && ((reinterpret_cast<uintptr_t>(A) & 15) || lda % 4 || K % 4)) return false;
-  if (!trans_b && ((reinterpret_cast<uintptr_t>(B) & 15) || ldb % 4 || K % 4)) return false;
+  // TMA: 16-byte aligned bases and row strides
+  if (((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B)) & 15) || lda % 4 || ldb % 4) return false;
   return M >= 1 && N >= 1 && K >= 1;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* q = nullptr;
+    cudaDriverEntryPointQueryResult r;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &q, cudaEnableDefault, &r) == cudaSuccess && r == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(q);
+  }
+  return fn;
+}
+// un-swizzled 2-D fp32 map over a row-major [outer, inner] matrix with row stride ld: K-major operands land as
+// [128 rows][32 k] (box 32 x 128), MN-major ones as [32 k][128 rows] (box 128 x 32)
+static int make_map(CUtensorMap* m, const float* base, int64_t ld, int mn_major, int rows, int K) {
+  EncodeTiledFn fn = encode_fn();
+  DVAE_REQUIRE(fn != nullptr, "tc16_gemm: cuTensorMapEncodeTiled is not available from the driver");
+  cuuint64_t dims[2] = {(cuuint64_t)(mn_major ? rows : K), (cuuint64_t)(mn_major ? K : rows)};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
+  cuuint32_t box[2] = {(cuuint32_t)(mn_major ? BM : BK), (cuuint32_t)(mn_major ? BK : BM)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  DVAE_REQUIRE(r == CUDA_SUCCESS, "tc16_gemm: cuTensorMapEncodeTiled failed (%d) rows=%d K=%d ld=%lld", (int)r, rows, K, (long long)ld);
+  return DVAE_OK;
 }
 
 static int launch(const Params& p, dim3 grid, cudaStream_t st) {
@@ -399,7 +443,11 @@ static int launch(const Params& p, dim3 grid, cudaStream_t st) {
     DVAE_CUDA(cudaFuncSetAttribute(tc16_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     ready = true;
   }
-  tc16_gemm_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(p);
+  CUtensorMap ma, mb;
+  int rc = make_map(&ma, p.A, p.lda, p.a_mn, p.M, p.K);
+  if (rc) return rc;
+  if ((rc = make_map(&mb, p.Bm, p.ldb, p.b_mn, p.N, p.K))) return rc;
+  tc16_gemm_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(ma, mb, p);
   DVAE_LAUNCH_CHECK();
   return DVAE_OK;
 }
@@ -482,7 +530,7 @@ extern "C" int dvae_tc16_linear(const float* A, int64_t lda, int trans_a, const 
   DVAE_REQUIRE(A && B && C && M > 0 && N > 0 && K > 0, "dvae_tc16_linear: bad argument");
   DVAE_REQUIRE(act == 0 || act == 1, "dvae_tc16_linear: unknown activation %d", act);
   DVAE_REQUIRE(dvae::tc16::shape_ok(A, lda, trans_a, B, ldb, trans_b, M, N, K),
-               "dvae_tc16_linear: K-major operands must be 16-byte aligned with ld %% 4 == 0 and K %% 4 == 0");
+               "dvae_tc16_linear: operands must be 16-byte aligned with ld %% 4 == 0 (TMA)");
   dvae::GemmHints h;
   h.a_scale = a_scale; h.b_scale = b_scale; h.a_amax_bits = a_amax_bits; h.b_amax_bits = b_amax_bits;
   return dvae::tc16::linear(A, lda, trans_a, B, ldb, trans_b, C, ldc, M, N, K, bias, bias2, beta, act, h, (cudaStream_t)stream);

@@ -183,10 +183,10 @@ def test_train_step_matches_oracle_synthetic(dvae, bi, H, E, V, B, T):
         assert _rel(prm.grad, grads[k]) < 1e-3, k
 
 
-@pytest.mark.parametrize("env", [{"DVAE_GEMM_IMPL": "f16"}, {"DVAE_FORK": "0"}, {"DVAE_LSTM_IMPL": "simt"}, {"DVAE_LSTM_GROUPS": "2"}])
+@pytest.mark.parametrize("env", [{"DVAE_GEMM_IMPL": "tf32"}, {"DVAE_GEMM_IMPL": "simt"}, {"DVAE_FORK": "0"}, {"DVAE_LSTM_IMPL": "simt"}, {"DVAE_LSTM_GROUPS": "2"}])
 def test_train_step_alternative_kernel_paths_match_oracle(dvae, env, monkeypatch):
-    """The opt-in / A-B kernel selections keep the same parity gates: fp16-split tcgen05 GEMMs (incl. the max|dG| operand
-    scale reported by the LSTM backward kernel), no fork/join side streams, fp32 SIMT persistent LSTM, two row groups."""
+    """The A/B kernel selections keep the same parity gates: 3xTF32 tcgen05 GEMMs and fp32 SIMT GEMMs instead of the default
+    fp16-split ones, no fork/join side streams, fp32 SIMT persistent LSTM, two row groups per cluster."""
     for k, v in env.items():
         monkeypatch.setenv(k, v)
     dvae.set_seed(10)
