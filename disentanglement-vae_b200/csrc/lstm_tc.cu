@@ -19,7 +19,7 @@
 // double-buffered by step parity -- no barrier.cluster and no __syncthreads on the exchange path.
 //
 // Backward (lstm_tc_bwd_kernel) is K-split instead: the CTA keeps W_hh[own gate rows, :]^T (M = 256 units, K = 128)
-// resident, multiplies it with its OWN gate gradients dG[t+1] (per-row power-of-two scaling keeps them inside fp16
+// resident (in tensor memory), multiplies it with its OWN gate gradients dG[t+1] (per-row power-of-two scaling keeps them inside fp16
 // range; exact, undone in the epilogue), and the partial d(h) values are reduce-scattered straight from registers into
 // the unit owners' shared memory with the same remote-store + mbarrier mechanism.  Carried dh / dc stay in registers.
 //
@@ -53,6 +53,26 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
   return r;
 }
+// D[tmem] (+)= A[tmem] * B[smem]^T: the A operand (lane = row, each 32-bit column = two consecutive k) stays in tensor
+// memory, so an MMA reads only its small B tile from shared memory
+__device__ __forceinline__ void mma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// registers -> 32 lanes x 16 consecutive 32-bit columns
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+      "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 // kind::f16, A = B = fp16, D = fp32, both operands K-major
 __host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
   return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
@@ -99,10 +119,17 @@ __device__ __forceinline__ unsigned long long gtimer_ns() {
 // ------------------------------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------------------------------
+// DVAE_LSTM_A_TMEM: keep the resident weights in TENSOR memory instead of shared memory (tcgen05.mma with the A operand
+// in TMEM): an MMA then reads only its 512-byte state tile from SMEM instead of 4 KB of weights, which is what paces
+// the N = 16 MMAs of the SMEM variant (profiles/probes/umma_small_n.cu).  TMEM columns: [0, 64) accumulators,
+// [64, 192) A_hi (k pair j of gate row m at lane m, column 64 + j), [192, 320) A_lo.
+#ifndef DVAE_LSTM_A_TMEM
+#define DVAE_LSTM_A_TMEM 1
+#endif
 // shared memory map (bytes): resident weights, then one block per row group
 constexpr int kF_A = 0;                          // A_hi [128 x 256 fp16] 64 KB, A_lo 64 KB
 constexpr int kF_APlane = 65536;
-constexpr int kF_GRP = 131072;                   // per-group blocks start here
+constexpr int kF_GRP = DVAE_LSTM_A_TMEM ? 0 : 131072;   // per-group blocks start here (no SMEM weights in the TMEM variant)
 constexpr int kF_BPlane = kNB * kH * 2;          // one plane of the state operand: NB x 256 fp16 = 8 KB
 constexpr int kG_B = 0;                          // [2 buffers][2 planes][NB x 256 fp16]
 constexpr int kG_SG = 4 * kF_BPlane;             // activated gates [4][NB][32] fp32
@@ -115,6 +142,7 @@ constexpr int fwd_smem_bytes(int G) { return kF_GRP + G * kG_BYTES + 16; }
 //   B: chunk(n, kc) at kc * (NB * 16) + n * 16                         SBO = 128, LBO = NB * 16
 constexpr int kF_A_SBO = 4096, kF_A_LBO = 128, kB_SBO = 128, kB_LBO = kNB * 16;
 constexpr int kSlice = 4 * kB_LBO;               // this CTA's 4 K-chunks (32 units) of one plane: 1 KB
+constexpr int kT_AHI = 64, kT_ALO = 192, kT_FWD_COLS = DVAE_LSTM_A_TMEM ? 512 : 64;
 
 // G row groups of NB = 16 batch rows share the resident weights; each group is 16 warps with its own operand
 // buffers, accumulators and barriers and runs the step loop independently, so one group's state exchange and gate
@@ -142,9 +170,9 @@ __global__ void __cluster_dims__(kCS, 1, 1) __launch_bounds__(kGT * G, 1) lstm_t
     mbar_init(&bars[2], 1);
     fence_barrier_init();
   }
-  if (tid < 32) tmem_alloc(tmem_slot, 32 * G);
+  if (tid < 32) tmem_alloc(tmem_slot, DVAE_LSTM_A_TMEM ? kT_FWD_COLS : 32 * G);
   // resident weights: gate row m = g*32 + u  <-  W_hh[g*H + u0 + u][:], split into fp16 hi / lo planes
-  {
+  if (!DVAE_LSTM_A_TMEM) {
     const float* W = p.w_hh[d];
     for (int it = tid; it < 128 * 32; it += kGT * G) {
       const int m = it >> 5, kc = it & 31;
@@ -175,6 +203,31 @@ __global__ void __cluster_dims__(kCS, 1, 1) __launch_bounds__(kGT * G, 1) lstm_t
   __syncthreads();
   cluster.sync();           // every CTA's mbarriers are initialised before any peer can signal them
   tc_fence_after();
+  if (DVAE_LSTM_A_TMEM && grp == 0) {
+    // weights -> tensor memory: this thread owns gate row m = 32*q + lane (its TMEM lane) and k in [64*cgp, 64*cgp + 64)
+    const float* wrow = p.w_hh[d] + (int64_t)(q * kH + u0 + lane) * kH + 64 * cgp;
+    const uint32_t tbase = *tmem_slot + ((uint32_t)(q * 32) << 16) + 32 * cgp;
+#pragma unroll
+    for (int part = 0; part < 2; ++part) {
+      uint32_t hi[16], lo[16];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 x = *reinterpret_cast<const float4*>(wrow + part * 32 + 4 * j);
+        __half h0, l0, h1, l1, h2, l2, h3, l3;
+        split_f16(x.x, h0, l0); split_f16(x.y, h1, l1); split_f16(x.z, h2, l2); split_f16(x.w, h3, l3);
+        hi[2 * j] = pack2(h0, h1); hi[2 * j + 1] = pack2(h2, h3);
+        lo[2 * j] = pack2(l0, l1); lo[2 * j + 1] = pack2(l2, l3);
+      }
+      tmem_st16(tbase + kT_AHI + part * 16, hi);
+      tmem_st16(tbase + kT_ALO + part * 16, lo);
+    }
+    tmem_st_wait();
+    tc_fence_before();
+  }
+  if (DVAE_LSTM_A_TMEM) {
+    __syncthreads();
+    tc_fence_after();
+  }
   const uint32_t tmem = *tmem_slot + 32 * grp;
   const uint32_t slice_off = (uint32_t)(4 * rank) * kB_LBO;
   constexpr uint32_t kIdesc = make_idesc_f16(128, kNB);
@@ -223,9 +276,16 @@ __global__ void __cluster_dims__(kCS, 1, 1) __launch_bounds__(kGT * G, 1) lstm_t
 #pragma unroll
         for (int ks = 0; ks < kH / 16; ++ks) {
           const uint64_t da = (uint64_t)(ks * 2 * kF_A_LBO >> 4), db = (uint64_t)(ks * 2 * kB_LBO >> 4);
-          mma_f16(tmem, ahi + da, bhi + db, kIdesc, ks > 0);
-          mma_f16(tmem + kNB, ahi + da, blo + db, kIdesc, ks > 0);
-          mma_f16(tmem + kNB, alo + da, bhi + db, kIdesc, 1);
+          if (DVAE_LSTM_A_TMEM) {
+            const uint32_t ta_hi = *tmem_slot + kT_AHI + 8 * ks, ta_lo = *tmem_slot + kT_ALO + 8 * ks;
+            mma_f16_ts(tmem, ta_hi, bhi + db, kIdesc, ks > 0);
+            mma_f16_ts(tmem + kNB, ta_hi, blo + db, kIdesc, ks > 0);
+            mma_f16_ts(tmem + kNB, ta_lo, bhi + db, kIdesc, 1);
+          } else {
+            mma_f16(tmem, ahi + da, bhi + db, kIdesc, ks > 0);
+            mma_f16(tmem + kNB, ahi + da, blo + db, kIdesc, ks > 0);
+            mma_f16(tmem + kNB, alo + da, bhi + db, kIdesc, 1);
+          }
         }
         tc_commit(&bars[2]);
       }
@@ -280,77 +340,88 @@ __global__ void __cluster_dims__(kCS, 1, 1) __launch_bounds__(kGT * G, 1) lstm_t
   tc_fence_before();
   __syncthreads();
   cluster.sync();           // no CTA leaves while a peer's bulk copy may still read from / write to it
-  if (tid < 32) tmem_dealloc(*tmem_slot, 32 * G);
+  if (tid < 32) tmem_dealloc(*tmem_slot, DVAE_LSTM_A_TMEM ? kT_FWD_COLS : 32 * G);
 }
 
 // ------------------------------------------------------------------------------------------------------------------
 // backward
 // ------------------------------------------------------------------------------------------------------------------
-constexpr int kB_A = 0;                            // A_hi [256 units x 128 k fp16] 64 KB, A_lo 64 KB
-constexpr int kB_APlane = 65536;
-constexpr int kB_AHalf = 32768;                    // rows 128..255 start here
-constexpr int kB_B = 131072;                       // dG operand [2 planes][NB x 128 fp16]
-constexpr int kB_BPlane = kNB * 128 * 2;           // 4 KB
+// shared memory map (bytes): one block per row group (the weights live in tensor memory)
+constexpr int kB_BPlane = kNB * 128 * 2;           // one plane of the dG operand: NB x 128 fp16 = 4 KB
 constexpr int kB_Tile = kNB * 32 * 4;              // one [NB][32] fp32 partial-dh tile: 2 KB
-constexpr int kB_STAGE = kB_B + 2 * kB_BPlane;     // outgoing partial dh [2 bufs][8 peers][NB][32] fp32
-constexpr int kB_RED = kB_STAGE + 2 * 8 * kB_Tile; // incoming partials [2 bufs][8 source CTAs][NB][32] fp32
-constexpr int kB_INV = kB_RED + 2 * 8 * kB_Tile;   // float inv_scale[NB]
-constexpr int kB_BAR = kB_INV + kNB * 4;           // red_full[2], mma_done, tmem slot
-constexpr int kB_TOTAL = kB_BAR + 64;
-//   A: chunk(m, kc) at (m >> 3) * 2048 + kc * 128 + (m & 7) * 16  (K = 128 -> 16 chunks)   SBO = 2048, LBO = 128
-constexpr int kB_A_SBO = 2048, kB_A_LBO = 128;
+constexpr int kBG_B = 0;                           // dG operand [2 planes]
+constexpr int kBG_STAGE = kBG_B + 2 * kB_BPlane;   // outgoing partial dh [2 bufs][8 peers][NB][32] fp32
+constexpr int kBG_RED = kBG_STAGE + 2 * 8 * kB_Tile;  // incoming partials [2 bufs][8 source CTAs][NB][32] fp32
+constexpr int kBG_INV = kBG_RED + 2 * 8 * kB_Tile;    // float inv_scale[NB]
+constexpr int kBG_BAR = kBG_INV + kNB * 4;            // red_full[2], mma_done
+constexpr int kBG_BYTES = kBG_BAR + 64;
+constexpr int bwd_smem_bytes(int G) { return G * kBG_BYTES + 16; }
+// tensor memory columns: [0, 128) accumulators (row group g: 64 g + 32 half + {0: D1, 16: D2}),
+// [128, 256) A_hi (half h at 128 + 64 h: k pair j of unit 128 h + lane at column j), [256, 384) A_lo
+constexpr int kTB_AHI = 128, kTB_ALO = 256, kTB_COLS = 512;
 
-__global__ void __cluster_dims__(kCS, 1, 1) __launch_bounds__(kGT, 1) lstm_tc_bwd_kernel(PersistBwdArgs p) {
+template <int G>
+__global__ void __cluster_dims__(kCS, 1, 1) __launch_bounds__(kGT * G, 1) lstm_tc_bwd_kernel(PersistBwdArgs p) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  const uint32_t sbase = smem_u32(smem);
-  float* stage = reinterpret_cast<float*>(smem + kB_STAGE);
-  float* red = reinterpret_cast<float*>(smem + kB_RED);
-  float* inv_s = reinterpret_cast<float*>(smem + kB_INV);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kB_BAR);        // [0],[1] = red_full, [2] = mma_done
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kB_BAR + 32);
+  const int tid = threadIdx.x, grp = tid / kGT, gtid = tid % kGT, warp = gtid >> 5, lane = tid & 31, B = p.B, T = p.T;
+  uint8_t* gsm = smem + grp * kBG_BYTES;
+  const uint32_t gbase = smem_u32(gsm);
+  float* stage = reinterpret_cast<float*>(gsm + kBG_STAGE);
+  float* red = reinterpret_cast<float*>(gsm + kBG_RED);
+  float* inv_s = reinterpret_cast<float*>(gsm + kBG_INV);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(gsm + kBG_BAR);        // [0],[1] = red_full, [2] = mma_done
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + G * kBG_BYTES);
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (int)cluster.block_rank();
   const int cid = blockIdx.x / kCS;
   const int d = p.d_off + cid / p.n_slices, slice = cid % p.n_slices;
-  const int b0 = slice * kNB, u0 = rank * kUPC;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, B = p.B, T = p.T;
+  const int b0 = (slice * G + grp) * kNB, u0 = rank * kUPC;
 
-  if (tid == 0) {
+  if (gtid == 0) {
     mbar_init(&bars[0], 1);
     mbar_init(&bars[1], 1);
     mbar_init(&bars[2], 1);
     fence_barrier_init();
   }
-  if (warp == 0) tmem_alloc(tmem_slot, 64);
-  // resident weights, transposed: A[m = unit j][k = g*32 + u] = W_hh[g*H + u0 + u][j]
-  {
-    const float* W = p.w_hh[d];
-    for (int it = tid; it < 16 * kH; it += kGT) {
-      const int kc = it >> 8, j = it & 255;
-      __half hi[8], lo[8];
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const int k = kc * 8 + e, gg = k >> 5, u = k & 31;
-        split_f16(W[(int64_t)(gg * kH + u0 + u) * kH + j], hi[e], lo[e]);
-      }
-      const uint32_t off = (uint32_t)(j >> 3) * kB_A_SBO + kc * kB_A_LBO + (j & 7) * 16;
-      sts128(sbase + kB_A + off, make_uint4(pack2(hi[0], hi[1]), pack2(hi[2], hi[3]), pack2(hi[4], hi[5]), pack2(hi[6], hi[7])));
-      sts128(sbase + kB_A + kB_APlane + off, make_uint4(pack2(lo[0], lo[1]), pack2(lo[2], lo[3]), pack2(lo[4], lo[5]), pack2(lo[6], lo[7])));
-    }
-  }
-  if (tid < kNB) inv_s[tid] = 1.f;
+  if (tid < 32) tmem_alloc(tmem_slot, kTB_COLS);
+  if (gtid < kNB) inv_s[gtid] = 1.f;
   // roles.  read-out: TMEM lane quadrant q (units 32q + lane of each 128-unit half), rows 4*cgp .. 4*cgp + 3.
   //         cell backward: row `warp`, unit u0 + lane -- carried dh / dc live in registers.
   const int q = warp & 3, cgp = warp >> 2, prow = warp, pb = b0 + prow;
   const int plen = pb < B ? (p.lengths ? (int)p.lengths[pb] : T) : 0;
   float carry = (p.d_hn && pb < B) ? p.d_hn[d * p.dirn + (int64_t)pb * p.ldn + u0 + lane] : 0.f;
   float dc = (p.d_cn && pb < B) ? p.d_cn[d * p.dirn + (int64_t)pb * p.ldn + u0 + lane] : 0.f;
-  fence_proxy_async();
   tc_fence_before();
   __syncthreads();
   cluster.sync();
   tc_fence_after();
-  const uint32_t tmem = *tmem_slot;
+  const uint32_t tmem0 = *tmem_slot;
+  if (grp == 0) {
+    // resident weights, transposed, into tensor memory: A[m = unit j][k = g*32 + u] = W_hh[g*H + u0 + u][j].
+    // This thread owns TMEM lane 32q + lane of both 128-unit halves and the k range of gate cgp (32 values).
+    const float* W = p.w_hh[d] + (int64_t)(cgp * kH + u0) * kH;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const int j = 128 * half + 32 * q + lane;
+      uint32_t hi[16], lo[16];
+#pragma unroll
+      for (int e = 0; e < 16; ++e) {
+        __half h0, l0, h1, l1;
+        split_f16(W[(int64_t)(2 * e) * kH + j], h0, l0);
+        split_f16(W[(int64_t)(2 * e + 1) * kH + j], h1, l1);
+        hi[e] = pack2(h0, h1);
+        lo[e] = pack2(l0, l1);
+      }
+      const uint32_t tb = tmem0 + ((uint32_t)(q * 32) << 16) + 64 * half + 16 * cgp;
+      tmem_st16(tb + kTB_AHI, hi);
+      tmem_st16(tb + kTB_ALO, lo);
+    }
+    tmem_st_wait();
+    tc_fence_before();
+  }
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem0 + 64 * grp;
   constexpr uint32_t kIdesc = make_idesc_f16(128, kNB);
   const int nsteps = T + ((p.d_h0 || p.d_c0) ? 1 : 0);
   unsigned amax_run = 0;           // bit pattern of max |dG| over this warp's row, all steps
@@ -378,19 +449,18 @@ __global__ void __cluster_dims__(kCS, 1, 1) __launch_bounds__(kGT, 1) lstm_tc_bw
       if (warp == 0) {
         tc_fence_after();
         if (elect_one()) {
-          const uint64_t bhi = make_smem_desc(sbase + kB_B, kB_LBO, kB_SBO, 0);
-          const uint64_t blo = make_smem_desc(sbase + kB_B + kB_BPlane, kB_LBO, kB_SBO, 0);
+          const uint64_t bhi = make_smem_desc(gbase + kBG_B, kB_LBO, kB_SBO, 0);
+          const uint64_t blo = make_smem_desc(gbase + kBG_B + kB_BPlane, kB_LBO, kB_SBO, 0);
 #pragma unroll
           for (int half = 0; half < 2; ++half) {
-            const uint64_t ahi = make_smem_desc(sbase + kB_A + half * kB_AHalf, kB_A_LBO, kB_A_SBO, 0);
-            const uint64_t alo = make_smem_desc(sbase + kB_A + kB_APlane + half * kB_AHalf, kB_A_LBO, kB_A_SBO, 0);
             const uint32_t d1 = tmem + half * 2 * kNB, d2 = d1 + kNB;
 #pragma unroll
             for (int ks = 0; ks < 128 / 16; ++ks) {
-              const uint64_t da = (uint64_t)(ks * 2 * kB_A_LBO >> 4), db = (uint64_t)(ks * 2 * kB_LBO >> 4);
-              mma_f16(d1, ahi + da, bhi + db, kIdesc, ks > 0);
-              mma_f16(d2, ahi + da, blo + db, kIdesc, ks > 0);
-              mma_f16(d2, alo + da, bhi + db, kIdesc, 1);
+              const uint64_t db = (uint64_t)(ks * 2 * kB_LBO >> 4);
+              const uint32_t ahi = tmem0 + kTB_AHI + 64 * half + 8 * ks, alo = tmem0 + kTB_ALO + 64 * half + 8 * ks;
+              mma_f16_ts(d1, ahi, bhi + db, kIdesc, ks > 0);
+              mma_f16_ts(d2, ahi, blo + db, kIdesc, ks > 0);
+              mma_f16_ts(d2, alo, bhi + db, kIdesc, 1);
             }
           }
           tc_commit(&bars[2]);
@@ -398,7 +468,7 @@ __global__ void __cluster_dims__(kCS, 1, 1) __launch_bounds__(kGT, 1) lstm_tc_bw
         __syncwarp();
         mbar_wait(&bars[2], (s - 1) & 1);
       }
-      __syncthreads();
+      group_sync(grp);
       tc_fence_after();
       // read-out: each partial value goes to the staging tile of the CTA that owns its unit
       float* st_out = stage + (size_t)buf * 8 * kNB * 32;
@@ -414,16 +484,16 @@ __global__ void __cluster_dims__(kCS, 1, 1) __launch_bounds__(kGT, 1) lstm_tc_bw
       }
       fence_proxy_async();
       tc_fence_before();
-      __syncthreads();
-      if (tid == 0) mbar_expect_tx(&bars[buf], 7 * kB_Tile);
+      group_sync(grp);
+      if (gtid == 0) mbar_expect_tx(&bars[buf], 7 * kB_Tile);
       if (warp == 1 && lane < 7) {
         const int peer = lane + (lane >= rank ? 1 : 0);
-        const uint32_t src = sbase + kB_STAGE + (uint32_t)(buf * 8 + peer) * kB_Tile;
-        const uint32_t dst = sbase + kB_RED + (uint32_t)(buf * 8 + rank) * kB_Tile;
+        const uint32_t src = gbase + kBG_STAGE + (uint32_t)(buf * 8 + peer) * kB_Tile;
+        const uint32_t dst = gbase + kBG_RED + (uint32_t)(buf * 8 + rank) * kB_Tile;
         bulk_copy_to_peer(mapa_u32(dst, peer), src, kB_Tile, mapa_u32(smem_u32(&bars[buf]), peer));
       }
       if (warp == 0) mbar_wait(&bars[buf], ((s - 1) >> 1) & 1);
-      __syncthreads();
+      group_sync(grp);
       const float* rin = red + (size_t)buf * 8 * kNB * 32 + prow * 32 + lane;
       rec = st_out[(size_t)rank * kNB * 32 + prow * 32 + lane];
 #pragma unroll
@@ -465,7 +535,7 @@ __global__ void __cluster_dims__(kCS, 1, 1) __launch_bounds__(kGT, 1) lstm_tc_bw
     se = se < 1 ? 1 : (se > 253 ? 253 : se);
     const float sc = __uint_as_float((unsigned)se << 23);
     if (lane == 0) inv_s[prow] = __uint_as_float((unsigned)(254 - se) << 23);
-    const uint32_t bhi = sbase + kB_B, blo = bhi + kB_BPlane;
+    const uint32_t bhi = gbase + kBG_B, blo = bhi + kB_BPlane;
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
       __half hi, lo;
@@ -476,13 +546,13 @@ __global__ void __cluster_dims__(kCS, 1, 1) __launch_bounds__(kGT, 1) lstm_tc_bw
     }
     fence_proxy_async();
     tc_fence_before();
-    __syncthreads();
+    group_sync(grp);
   }
   if (p.amax_out && lane == 0 && amax_run) atomicMax(p.amax_out, amax_run);
   tc_fence_before();
   __syncthreads();
   cluster.sync();
-  if (warp == 0) tmem_dealloc(tmem, 64);
+  if (tid < 32) tmem_dealloc(tmem0, kTB_COLS);
 }
 
 }  // namespace
@@ -516,20 +586,25 @@ int tc_lstm_fwd(const PersistFwdArgs& a, cudaStream_t st) {
   return want >= 2 ? launch_tc_fwd<2>(a, st) : launch_tc_fwd<1>(a, st);
 }
 
-int tc_lstm_bwd(const PersistBwdArgs& a, cudaStream_t st) {
+template <int G>
+static int launch_tc_bwd(const PersistBwdArgs& a, cudaStream_t st) {
   static bool ready = false;
   if (!ready) {
-    DVAE_CUDA(cudaFuncSetAttribute(lstm_tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kB_TOTAL));
+    DVAE_CUDA(cudaFuncSetAttribute(lstm_tc_bwd_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd_smem_bytes(G)));
     ready = true;
   }
-  const bool split = a.D == 2 && 2 * a.n_slices > 15 && a.n_slices <= 15;
-  for (int d0 = 0; d0 < (split ? 2 : 1); ++d0) {
-    PersistBwdArgs b = a;
-    b.d_off = d0;
-    lstm_tc_bwd_kernel<<<kCS * a.n_slices * (split ? 1 : a.D), kGT, kB_TOTAL, st>>>(b);
-    DVAE_LAUNCH_CHECK();
-  }
+  PersistBwdArgs b = a;
+  b.n_slices = ceil_div(a.B, kNB * G);
+  b.d_off = 0;
+  lstm_tc_bwd_kernel<G><<<kCS * b.n_slices * a.D, kGT * G, bwd_smem_bytes(G), st>>>(b);
+  DVAE_LAUNCH_CHECK();
   return DVAE_OK;
+}
+
+int tc_lstm_bwd(const PersistBwdArgs& a, cudaStream_t st) {
+  const char* e = getenv("DVAE_LSTM_GROUPS");
+  const int want = e ? atoi(e) : (a.D * ceil_div(a.B, kNB) <= 15 ? 1 : 2);
+  return want >= 2 ? launch_tc_bwd<2>(a, st) : launch_tc_bwd<1>(a, st);
 }
 
 }  // namespace dvae

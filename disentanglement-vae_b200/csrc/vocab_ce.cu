@@ -123,11 +123,14 @@ __global__ void __launch_bounds__(GCE::NT) vocab_ce_fwd_kernel(CeArgs p) {
   }
 }
 
-__global__ void __launch_bounds__(1024) vocab_ce_finalize_kernel(CeArgs p, float* lse, float* nll, int32_t* argmax,
-                                                                 float* loss) {
-  __shared__ float red[32];
+// Merge the vocabulary splits of each row (fixed order: deterministic), write lse / nll / arg-max, and leave one
+// partial NLL sum per CTA in `block_sums`; vocab_ce_loss_kernel adds them up (fixed order again) into the loss.
+constexpr int kFinThreads = 128, kFinMaxBlocks = 96;
+__global__ void __launch_bounds__(kFinThreads) vocab_ce_finalize_kernel(CeArgs p, float* lse, float* nll, int32_t* argmax,
+                                                                       float* block_sums) {
+  __shared__ float red[kFinThreads / 32];
   float local = 0.f;
-  for (int n = threadIdx.x; n < p.N; n += blockDim.x) {
+  for (int n = blockIdx.x * kFinThreads + threadIdx.x; n < p.N; n += gridDim.x * kFinThreads) {
     float m = -INFINITY, s = 0.f, t = 0.f, av = -INFINITY;
     int ai = 0x7fffffff;
     for (int sp = 0; sp < p.nsplit; ++sp) {
@@ -144,6 +147,19 @@ __global__ void __launch_bounds__(1024) vocab_ce_finalize_kernel(CeArgs p, float
     int b = n % p.B, tpos = n / p.B + 1;
     if (tpos < p.lengths[b]) local += e;
   }
+  local = warp_sum(local);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = local;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float tot = 0.f;
+    for (int i = 0; i < kFinThreads / 32; ++i) tot += red[i];
+    block_sums[blockIdx.x] = tot;
+  }
+}
+
+__global__ void __launch_bounds__(128) vocab_ce_loss_kernel(CeArgs p, const float* block_sums, int nblocks, float* loss) {
+  __shared__ float red[4];
+  float local = 0.f;
   // position 0: one-hot(1.0) pseudo-logits at <SOS> (model.py:454): lse = 1 + log(1 + (V-1)/e)
   for (int b = threadIdx.x; b < p.B; b += blockDim.x) {
     if (p.lengths[b] > 0) {
@@ -155,8 +171,8 @@ __global__ void __launch_bounds__(1024) vocab_ce_finalize_kernel(CeArgs p, float
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = local;
   __syncthreads();
   if (threadIdx.x == 0) {
-    float tot = 0.f;
-    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) tot += red[i];
+    float tot = red[0] + red[1] + red[2] + red[3];
+    for (int i = 0; i < nblocks; ++i) tot += block_sums[i];
     loss[0] = tot / (float)p.B;
   }
 }
@@ -257,7 +273,7 @@ using namespace dvae;
 extern "C" int64_t dvae_vocab_ce_ws_floats(int N, int V) {
   int tps;
   int ns = ce_nsplit(N, V, &tps);
-  return (int64_t)ns * N * 5 + 8;
+  return (int64_t)ns * N * 5 + 8 + kFinMaxBlocks;
 }
 
 extern "C" int dvae_vocab_ce_fwd(const float* h, int64_t ldh, int T1, int B, int H, int V, const float* w,
@@ -275,7 +291,11 @@ extern "C" int dvae_vocab_ce_fwd(const float* h, int64_t ldh, int T1, int B, int
   p.part_idx = reinterpret_cast<int*>(ws + (int64_t)p.nsplit * p.N * 4);
   p.gumbel_seed = nullptr; p.gumbel_salt = 0;
   { int rc = ce_partials(p, st); if (rc) return rc; }
-  vocab_ce_finalize_kernel<<<1, 1024, 0, st>>>(p, lse, nll, argmax, loss);
+  float* block_sums = ws + (int64_t)p.nsplit * p.N * 5 + 8;
+  const int nblk = min(kFinMaxBlocks, ceil_div(p.N, kFinThreads));
+  vocab_ce_finalize_kernel<<<nblk, kFinThreads, 0, st>>>(p, lse, nll, argmax, block_sums);
+  DVAE_LAUNCH_CHECK();
+  vocab_ce_loss_kernel<<<1, 128, 0, st>>>(p, block_sums, nblk, loss);
   DVAE_LAUNCH_CHECK();
   return DVAE_OK;
 }
