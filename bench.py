@@ -41,9 +41,14 @@ WORKLOAD = ("cfg2 sfu_amazon_100k reproduction shape: per-GPU batch 128, T=22 (S
             "content 62), dropout 0.5, teacher forcing 1.0, cyclic KL")
 
 
-def synth_batch(rng, B, T=SEQ_T, V=VOCAB):
-    """rows [SOS, w..., EOS, PAD...], Zipf(1.0) body tokens, SFU-like lengths, 10% labels."""
-    lengths = np.clip(np.round(rng.gamma(9.7, 1.06, B)), 3, T).astype(np.int64)
+def synth_batch(rng, B, T=None, V=None, uniform_lengths=None):
+    """rows [SOS, w..., EOS, PAD...], Zipf(1.0) body tokens, SFU-like lengths (or U{lo..hi}), 10% labels."""
+    T = SEQ_T if T is None else T
+    V = VOCAB if V is None else V
+    if uniform_lengths is not None:
+        lengths = rng.integers(uniform_lengths[0], uniform_lengths[1] + 1, B).astype(np.int64)
+    else:
+        lengths = np.clip(np.round(rng.gamma(9.7, 1.06, B)), 3, T).astype(np.int64)
     lengths[0] = T
     ranks = np.arange(4, V)
     pz = 1.0 / (ranks - 3.0)
@@ -175,6 +180,72 @@ def run_reference_arm(args):
 
 
 # ------------------------------------------------------------------------------------------------
+# Secondary workloads (BASELINE.json configs[3] / configs[4]); the headline line is always cfg 2.
+# ------------------------------------------------------------------------------------------------
+def select_workload(name):
+    """Rebinds the module-level workload description.  cfg4 = scaled decoder (H 1024, V 50k, T 64: stresses the fused
+    vocab-CE kernels; SURVEY.md 8 states B = 128, lengths U{16..64})."""
+    global CFG2, VOCAB, SEQ_T, WORKLOAD, TOTAL_STEPS
+    if name == "cfg4":
+        CFG2 = dict(CFG2, name="bench/scaled_decoder", hidden_dim=1024)
+        VOCAB, SEQ_T = 50000, 64
+        WORKLOAD = ("cfg4 scaled decoder: per-GPU batch 128, T=64 (lengths U{16..64}), V=50000, E=256, H=1024, 2-layer bi-LSTM "
+                    "encoder, 2-layer decoder, Z=64, dropout 0.5, teacher forcing 1.0, cyclic KL")
+        return (16, 64)
+    return None
+
+
+def run_inference_workload(args):
+    """cfg5: consistency-evaluation shape (scripts/evaluation/consistency.py:163-205): for each batch of 1024 sentences,
+    R = 30 resamples of [forward(x, tf=0) -> sampled reconstruction x_hat -> on-device length recount -> forward(x_hat,
+    tf=0)], model in train mode (fresh latents and dropout each time), no gradients.  One 'step' = one resample pair."""
+    import __graft_entry__ as ge
+    dvae = ge.build()
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(0)
+    B, T, R = 1024, SEQ_T, 30
+    dvae.set_seed(10)
+    vae = dvae.build_vae(CFG2, VOCAB, None, LABELS, dev, SOS, EOS)
+    vae.train()
+    rng = np.random.default_rng(5)
+    X, L, _ = synth_batch(rng, B)
+    Xd, Ld = torch.from_numpy(X).to(dev), torch.from_numpy(L).to(dev)
+
+    def pair():
+        with torch.no_grad():
+            out = vae(Xd, Ld, teacher_forcing_prob=0.0)
+            xh = out["token_predictions"]
+            lh = xh.size(1) - ((xh == EOS) | (xh == PAD)).sum(1)          # consistency.py:186-190
+            lh = lh.clamp_(min=1)
+            out2 = vae(xh, lh, teacher_forcing_prob=0.0)
+            return out2["dsc_logits"]
+
+    n0 = dvae.launch_count()
+    for _ in range(max(args.warmup, 3)):
+        pair()
+    torch.cuda.synchronize()
+    launches = (dvae.launch_count() - n0) // max(args.warmup, 3)
+    steps = args.steps if args.steps != 50 else R
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    clocks = ClockSampler(0)
+    a.record()
+    for _ in range(steps):
+        pair()
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b)
+    clk = clocks.stop()
+    toks = float(L.sum()) * 2 * steps
+    line = {"metric": "inference_tokens_per_sec", "value": toks / (ms * 1e-3), "unit": "tokens/s", "n_gpus": 1, "steps": steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "cfg5 inference: batch 1024, T=22, V=10000, E=H=256; per step = forward(x, tf=0) with sampled "
+                                   "decoding + re-encode of the sampled sentences (consistency.py loop body), 30 resamples per batch",
+                       "global_batch": B, "seq_len": T, "tokens": "valid input tokens x 2 forwards"},
+            "gpu_launches": int(launches * steps), "launches_per_step": int(launches), "clocks": clk}
+    print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -184,9 +255,14 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--batch", type=int, default=128, help="per-GPU batch")
+    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg4", "cfg5"],
+                    help="cfg2 = headline (BASELINE.json configs[1]); cfg4 / cfg5 = secondary configs, recorded under profiles/")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
+    if args.workload == "cfg5":
+        return run_inference_workload(args)
+    uniform_lengths = select_workload(args.workload)
 
     import torch.distributed as dist
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -220,7 +296,7 @@ def main():
     vae.train()
     eng = engine_mod.TrainEngine(vae, CFG2, B, T, total_steps=TOTAL_STEPS, use_graph=not args.no_graph, seed=10 + rank)
     rng = np.random.default_rng(1000 + rank)             # each rank draws its own shard of the global batch
-    pool = [synth_batch(rng, B) for _ in range(8)]
+    pool = [synth_batch(rng, B, uniform_lengths=uniform_lengths) for _ in range(8)]
     dpool = [(torch.from_numpy(X).to(dev), torch.from_numpy(L).to(dev), torch.from_numpy(Y).to(dev)) for X, L, Y in pool]
     hpool = [(torch.from_numpy(X), torch.from_numpy(L), {n: torch.from_numpy(Y[j]) for j, n in enumerate(LABELS)}) for X, L, Y in pool]
     tokens = [int(L.sum()) for _, L, _ in pool]
@@ -345,7 +421,7 @@ def main():
                     "d2h_bytes_per_step": eng.d2h_bytes_per_step, "ms_per_step": e2e_s * 1e3 / args.steps},
             "gpu_launches": int(launches_per_step * args.steps), "launches_per_step": int(launches_per_step),
             "roofline": roof, "clocks": clk, "loss_after_warmup": loss_warm, "loss_last": loss_last}
-    if not args.no_cpu_baseline and world == 1:
+    if not args.no_cpu_baseline and world == 1 and args.workload == "cfg2":
         tps, sps, sample = cpu_port_steps(3, 1, budget_s=25.0)
         line["cpu_baseline"] = {"value": tps, "unit": "tokens/s", "cores": os.cpu_count(), "kind": "port", "sample": sample,
                                 "s_per_step": sps}
