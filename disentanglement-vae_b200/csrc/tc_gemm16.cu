@@ -38,9 +38,10 @@ constexpr int PLANE = (BM / 8) * T_SBO;            // one fp16 plane of a 128 x 
 constexpr int STAGE_BYTES = 4 * PLANE;             // A_hi, A_lo, B_hi, B_lo
 constexpr int RAW_TILE = BM * BK * 4;              // one landed fp32 tile: 16 KB
 constexpr int RAW_BYTES = 2 * RAW_TILE;            // A, B
-constexpr int EPI_WARPS = 4, MMA_WARP = 4, TMA_WARP = 5, PROD_WARP0 = 6, PROD_WARPS = 16;
-constexpr int NUM_THREADS = (PROD_WARP0 + PROD_WARPS) * 32;      // 704: <= 93 registers per thread
-constexpr int EPI_SCRATCH_BYTES = 4 * 32 * 33 * 4;
+constexpr int EPI_WARPS = 8, MMA_WARP = 4, TMA_WARP = 5, PROD_WARP0 = 6, PROD_WARPS = 16, EPI2_WARP0 = PROD_WARP0 + PROD_WARPS;
+// warps 0-3: epilogue of tile columns 0-63; warps 22-25 (22 % 4 == 2: TMEM lane quarter = warp & 3): columns 64-127
+constexpr int NUM_THREADS = (EPI2_WARP0 + 4) * 32;               // 832: <= 78 registers per thread
+constexpr int EPI_SCRATCH_BYTES = 8 * 32 * 33 * 4;
 constexpr int OFF_RAW = STAGES * STAGE_BYTES, OFF_BAR = OFF_RAW + RAW_STAGES * RAW_BYTES, OFF_SCRATCH = OFF_BAR + 256;
 constexpr int SMEM_BYTES = OFF_SCRATCH + EPI_SCRATCH_BYTES + 1024;
 constexpr int TMEM_COLS = 512;
@@ -190,7 +191,7 @@ tc16_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
       }
     }
-  } else if (warp >= PROD_WARP0) {
+  } else if (warp >= PROD_WARP0 && warp < EPI2_WARP0) {
     // ===== converters: landed fp32 tile -> (scale, split) -> fp16 operand planes =====
     const int ptid = tid - PROD_WARP0 * 32;
     const float sa = scale_from_amax(p.a_amax, p.a_scale), sb = scale_from_amax(p.b_amax, p.b_scale);
@@ -259,8 +260,8 @@ tc16_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
     }
   } else {
-    // ===== epilogue (warps 0..3 = TMEM lane quarters 0..3) =====
-    const int quarter = warp;
+    // ===== epilogue: 8 warps = 4 TMEM lane quarters x 2 column halves of the tile =====
+    const int quarter = warp & 3, ehalf = warp >= EPI2_WARP0 ? 1 : 0, ew = ehalf * 4 + quarter;
     const int row = m0 + quarter * 32 + lane;      // output row owned by this thread (TMEM lane)
     const bool row_ok = row < p.M;
     const float oscale = p.alpha * (p.alpha_dev ? *p.alpha_dev : 1.f) /
@@ -284,14 +285,14 @@ tc16_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       tc_fence_after();
       if (tid == 0 && tile == 0) DBG16(14);
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = 2 * ehalf; c < 2 * ehalf + 2; ++c) {
         const int col0 = n0 + c * 32;
         if (col0 >= p.N) continue;                       // warp-uniform
         const uint32_t ta = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * 256 + c * 32;
         if (p.mode != 1) {
           // modes 0 / 2 store a [32 rows x 32 cols] chunk: transpose it through padded shared memory so each
           // store instruction covers 32 consecutive columns of one row (coalesced) instead of 32 different rows
-          const uint32_t sc = smem_u32(epi_scratch) + warp * (32 * 33 * 4);
+          const uint32_t sc = smem_u32(epi_scratch) + ew * (32 * 33 * 4);
 #pragma unroll
           for (int hh = 0; hh < 2; ++hh) {
             float v[16], w[16];
@@ -303,7 +304,7 @@ tc16_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               if (p.mode == 2) {
                 const int col = col0 + hh * 16 + j;
                 x = (row_scale == 0.f || col >= p.N) ? 0.f
-                    : (expf(x + __ldg(p.bias + col) - row_lse) - (col == tgt ? 1.f : 0.f)) * row_scale;
+                    : (__expf(x + __ldg(p.bias + col) - row_lse) - (col == tgt ? 1.f : 0.f)) * row_scale;
               }
               sts32(sc + (lane * 33 + hh * 16 + j) * 4, x);
             }
@@ -334,11 +335,27 @@ tc16_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             } else {
               const float beta = p.beta;
               const bool do_tanh = p.act == 1;
-              for (int rr = 0; rr < nr; ++rr) {
-                float x = lds32(src + rr * 132) + badd;
-                if (do_tanh) x = tanhf(x);
-                if (beta != 0.f) x = fmaf(beta, cp[rr * ldc], x);
-                cp[rr * ldc] = x;
+              if (nr == 32 && beta != 0.f) {
+                // read-modify-write of C: all 32 loads in flight before the first dependent store
+#pragma unroll 1
+                for (int r8 = 0; r8 < 32; r8 += 8) {
+                  float old[8];
+#pragma unroll
+                  for (int rr = 0; rr < 8; ++rr) old[rr] = cp[(r8 + rr) * ldc];
+#pragma unroll
+                  for (int rr = 0; rr < 8; ++rr) {
+                    float x = lds32(src + (r8 + rr) * 132) + badd;
+                    if (do_tanh) x = tanhf(x);
+                    cp[(r8 + rr) * ldc] = fmaf(beta, old[rr], x);
+                  }
+                }
+              } else {
+                for (int rr = 0; rr < nr; ++rr) {
+                  float x = lds32(src + rr * 132) + badd;
+                  if (do_tanh) x = tanhf(x);
+                  if (beta != 0.f) x = fmaf(beta, cp[rr * ldc], x);
+                  cp[rr * ldc] = x;
+                }
               }
             }
           }
@@ -370,9 +387,9 @@ tc16_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               if (col == tgt) rt = x;
             }
           }
-          if (tmax > rm) { rs *= expf(rm - tmax); rm = tmax; }
+          if (tmax > rm) { rs *= __expf(rm - tmax); rm = tmax; }
 #pragma unroll
-          for (int j = 0; j < 16; ++j) rs += expf(v[j] - rm);
+          for (int j = 0; j < 16; ++j) rs += __expf(v[j] - rm);
         }
       }
       tc_fence_before();
@@ -380,9 +397,10 @@ tc16_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
       if (tid == 0 && tile == 0) DBG16(15);
     }
-    if (p.mode == 1 && row_ok) {
-      *reinterpret_cast<float4*>(p.part + ((int64_t)blockIdx.y * p.M + row) * 4) = make_float4(rm, rs, rt, rav);
-      p.part_idx[(int64_t)blockIdx.y * p.M + row] = rai;
+    if (p.mode == 1 && row_ok) {      // the two column halves are separate vocabulary splits for the finalize kernel
+      const int64_t sp = (int64_t)blockIdx.y * 2 + ehalf;
+      *reinterpret_cast<float4*>(p.part + (sp * p.M + row) * 4) = make_float4(rm, rs, rt, rav);
+      p.part_idx[sp * p.M + row] = rai;
     }
   }
   tc_fence_before();
@@ -491,7 +509,9 @@ int linear(const float* A, int64_t lda, int trans_a, const float* B, int64_t ldb
       DVAE_LAUNCH_CHECK();
     }
   }
-  return launch(p, dim3(ceil_div(M, BM), ceil_div(N, BN), splits), st);
+  // more tiles than SMs: two N tiles per CTA, so the second tile's main loop hides the first one's epilogue
+  if (splits == 1 && tiles > 148 && ceil_div(N, BN) >= 2) p.tiles_per_cta = 2;
+  return launch(p, dim3(ceil_div(M, BM), ceil_div(ceil_div(N, BN), p.tiles_per_cta), splits), st);
 }
 
 int ce_partials(const float* h, int64_t ldh, int N, int B, int H, int V, const float* w, const float* bias,
@@ -512,12 +532,16 @@ int softmax_grad(const float* h, int64_t ldh, int N, int B, int H, int v0, int v
                  const float* grad_scale, float* P, int64_t ldp, cudaStream_t st) {
   Params p = {};
   p.A = h; p.lda = ldh; p.Bm = w + (int64_t)v0 * H; p.ldb = H;
-  p.M = N; p.N = vc; p.K = H; p.tiles_per_cta = 1; p.bias = bias + v0; p.mode = 2;
+  // a run of vocabulary tiles per CTA so the epilogue of one tile overlaps the main loop of the next; ~one wave of CTAs
+  const int row_tiles = ceil_div(N, BM), col_tiles = ceil_div(vc, BN);
+  int per_cta = ceil_div(col_tiles, max(1, 148 / row_tiles));
+  if (per_cta < 1) per_cta = 1;
+  p.M = N; p.N = vc; p.K = H; p.tiles_per_cta = per_cta; p.bias = bias + v0; p.mode = 2;
   p.kb_per_split = ceil_div(H, BK);
   p.targets = targets; p.tgt_stride_b = tgt_stride_b; p.lengths = lengths; p.B = B; p.lse = lse; p.grad_scale = grad_scale;
   p.v0 = v0; p.C = P; p.ldc = ldp;
   apply_hints(p, GemmHints());
-  return launch(p, dim3(ceil_div(N, BM), ceil_div(vc, BN), 1), st);
+  return launch(p, dim3(row_tiles, ceil_div(col_tiles, per_cta), 1), st);
 }
 
 }  // namespace tc16

@@ -233,10 +233,16 @@ __global__ void __launch_bounds__(GCE::NT) vocab_p_kernel(PArgs p) {
 }
 
 // per-(row, vocabulary split) partials: tensor-core kernel when the shape allows, fp32 SIMT otherwise
-static int ce_partials(const CeArgs& p, cudaStream_t st) {
-  if (!force_simt_gemm() && p.N >= 64 && p.V >= 128 && p.H >= 32 && tc16::supported(p.h, p.ldh, 0, p.w, p.H, 0, p.N, p.V, p.H))
+// On return p.nsplit / p.part_idx describe the partials that were actually written (the fp16-split kernel's two
+// epilogue warp sets each emit their own split).
+static int ce_partials(CeArgs& p, cudaStream_t st) {
+  if (!force_simt_gemm() && p.N >= 64 && p.V >= 128 && p.H >= 32 && tc16::supported(p.h, p.ldh, 0, p.w, p.H, 0, p.N, p.V, p.H)) {
+    const int launched = p.nsplit;
+    p.nsplit = 2 * launched;
+    p.part_idx = reinterpret_cast<int*>(p.part + (int64_t)p.nsplit * p.N * 4);
     return tc16::ce_partials(p.h, p.ldh, p.N, p.B, p.H, p.V, p.w, p.bias, p.targets, p.tgt_stride_b, p.lengths,
-                             p.tiles_per_split, p.nsplit, p.part, p.part_idx, p.gumbel_seed, p.gumbel_salt, st);
+                             p.tiles_per_split, launched, p.part, p.part_idx, p.gumbel_seed, p.gumbel_salt, st);
+  }
   if (!force_simt_gemm() && p.N >= 64 && p.V >= 128 && p.H >= 32 && tc::tc_linear_supported(p.h, p.ldh, p.w, p.H, p.N, p.V, p.H))
     return tc::tc_ce_partials(p.h, p.ldh, p.N, p.B, p.H, p.V, p.w, p.bias, p.targets, p.tgt_stride_b, p.lengths,
                               p.tiles_per_split, p.nsplit, p.part, p.part_idx, p.gumbel_seed, p.gumbel_salt, st);
@@ -273,7 +279,7 @@ using namespace dvae;
 extern "C" int64_t dvae_vocab_ce_ws_floats(int N, int V) {
   int tps;
   int ns = ce_nsplit(N, V, &tps);
-  return (int64_t)ns * N * 5 + 8 + kFinMaxBlocks;
+  return 2LL * ns * N * 5 + 8 + kFinMaxBlocks;    // x2: the fp16-split kernel writes two partials per (row, split)
 }
 
 extern "C" int dvae_vocab_ce_fwd(const float* h, int64_t ldh, int T1, int B, int H, int V, const float* w,
@@ -291,7 +297,7 @@ extern "C" int dvae_vocab_ce_fwd(const float* h, int64_t ldh, int T1, int B, int
   p.part_idx = reinterpret_cast<int*>(ws + (int64_t)p.nsplit * p.N * 4);
   p.gumbel_seed = nullptr; p.gumbel_salt = 0;
   { int rc = ce_partials(p, st); if (rc) return rc; }
-  float* block_sums = ws + (int64_t)p.nsplit * p.N * 5 + 8;
+  float* block_sums = ws + (int64_t)p.nsplit * p.N * 5 + 8;      // p.nsplit: as updated by ce_partials
   const int nblk = min(kFinMaxBlocks, ceil_div(p.N, kFinThreads));
   vocab_ce_finalize_kernel<<<nblk, kFinThreads, 0, st>>>(p, lse, nll, argmax, block_sums);
   DVAE_LAUNCH_CHECK();
