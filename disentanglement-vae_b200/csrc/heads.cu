@@ -79,15 +79,35 @@ __global__ void __launch_bounds__(kHeadsThreads) heads_fwd_kernel(HeadsFwdArgs a
     const int nj = min(4, 2 * Z - j0);
     const float* w = a.w_c2p + (int64_t)j0 * C;
     float acc[4][kRows] = {};
-    for (int k = lane; k < C; k += 32) {
-      float wv[4];
+    if ((C & 3) == 0 && (reinterpret_cast<uintptr_t>(a.w_c2p) & 15) == 0) {
+      // 16-byte loads: 4 weight rows x 4 k per lane and iteration, two iterations in flight
+#pragma unroll 2
+      for (int k = lane * 4; k < C; k += 128) {
+        float4 wv[4];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) wv[q] = q < nj ? w[(int64_t)q * C + k] : 0.f;
+        for (int q = 0; q < 4; ++q)
+          wv[q] = q < nj ? __ldg(reinterpret_cast<const float4*>(w + (int64_t)q * C + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-      for (int r = 0; r < kRows; ++r) {
-        const float c = ctx_s[r * C + k];
+        for (int r = 0; r < kRows; ++r) {
+          const float4 c = *reinterpret_cast<const float4*>(ctx_s + r * C + k);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) acc[q][r] = fmaf(c, wv[q], acc[q][r]);
+          for (int q = 0; q < 4; ++q) {
+            acc[q][r] = fmaf(c.x, wv[q].x, acc[q][r]); acc[q][r] = fmaf(c.y, wv[q].y, acc[q][r]);
+            acc[q][r] = fmaf(c.z, wv[q].z, acc[q][r]); acc[q][r] = fmaf(c.w, wv[q].w, acc[q][r]);
+          }
+        }
+      }
+    } else {
+      for (int k = lane; k < C; k += 32) {
+        float wv[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) wv[q] = q < nj ? w[(int64_t)q * C + k] : 0.f;
+#pragma unroll
+        for (int r = 0; r < kRows; ++r) {
+          const float c = ctx_s[r * C + k];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) acc[q][r] = fmaf(c, wv[q], acc[q][r]);
+        }
       }
     }
 #pragma unroll

@@ -7,6 +7,8 @@ optimiser tail when world_size > 1.
 Same kernels and the same `StepPlan` as the drop-in autograd path (`functions.py`); what the
 engine removes is per-op host work (autograd bookkeeping, ctypes marshalling, allocator traffic).
 """
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -62,29 +64,41 @@ class TrainEngine:
         self._gen = torch.Generator().manual_seed(int(params.get("random_seed", 10)) if seed is None else seed)
         self.use_graph = use_graph
         self._graphs = None
+        self._buckets = None
+        self._comm = None
         self.label_names = [n for n, o in zip(d.space_names, d.dsc_out) if o > 0]
 
     # ---- the kernel sequences ------------------------------------------------------------------
-    def _fwd_bwd(self):
+    def _fwd_bwd(self, part=None):
+        """part = None: the whole forward + backward; 1: forward, vocabulary backward and decoder backward (every
+        decoder.* gradient final); 2: heads and encoder backward.  The split lets the all-reduce of the decoder
+        gradients (half of the parameters) run under part 2 when training data-parallel."""
         pl, P, G, m = self.plan, self.model._P, self.G, self.model
         st = _lib.stream_ptr()
-        # unpack the per-step scalar block (device-to-device, inside the graph)
-        self.hyper[:5].copy_(self.d_scal[:5])
-        self.kl_w.copy_(self.d_scal[8:8 + self.kl_w.numel()])
-        pl.randn_eps()
-        pl.encode(P, self.inputs, self.lengths, True)
-        pl.heads(P, pl.ctx, pl.eps, self.labels, self.kl_w)
-        h_top = pl.decode_forced(P, self.inputs, m.sos_token_idx, True)
-        pl.vocab_ce(P, h_top, self.inputs, self.lengths)
-        g_top = pl.vocab_ce_bwd(P, G, h_top, self.inputs, self.lengths, None)
-        # weight-gradient GEMMs of each layer keep running on side streams while the next layer's recurrence starts
-        check(self.lib.dvae_defer_joins(1), "dvae_defer_joins")
-        try:
-            g_hid = pl.decode_bwd(P, G, g_top, emb_grad="decoder.embedding.weight" in m._layout)
-            g_ctx = pl.heads_bwd(P, G, pl.ctx, pl.eps, self.labels, self.kl_w, g_hid)
-            pl.encode_bwd(P, G, self.inputs, self.lengths, g_ctx, emb_grad="encoder.embedding.weight" in m._layout)
-        finally:
-            check(self.lib.dvae_join_side_streams(st), "dvae_join_side_streams")
+        if part in (None, 1):
+            # unpack the per-step scalar block (device-to-device, inside the graph)
+            self.hyper[:5].copy_(self.d_scal[:5])
+            self.kl_w.copy_(self.d_scal[8:8 + self.kl_w.numel()])
+            pl.randn_eps()
+            pl.encode(P, self.inputs, self.lengths, True)
+            pl.heads(P, pl.ctx, pl.eps, self.labels, self.kl_w)
+            h_top = pl.decode_forced(P, self.inputs, m.sos_token_idx, True)
+            pl.vocab_ce(P, h_top, self.inputs, self.lengths)
+            g_top = pl.vocab_ce_bwd(P, G, h_top, self.inputs, self.lengths, None)
+            # weight-gradient GEMMs of each layer keep running on side streams while the next layer's recurrence starts
+            check(self.lib.dvae_defer_joins(1), "dvae_defer_joins")
+            try:
+                pl.decode_bwd(P, G, g_top, emb_grad="decoder.embedding.weight" in m._layout)
+            finally:
+                if part == 1:
+                    check(self.lib.dvae_join_side_streams(st), "dvae_join_side_streams")
+        if part in (None, 2):
+            check(self.lib.dvae_defer_joins(1), "dvae_defer_joins")
+            try:
+                g_ctx = pl.heads_bwd(P, G, pl.ctx, pl.eps, self.labels, self.kl_w, pl.g_hid)
+                pl.encode_bwd(P, G, self.inputs, self.lengths, g_ctx, emb_grad="encoder.embedding.weight" in m._layout)
+            finally:
+                check(self.lib.dvae_join_side_streams(st), "dvae_join_side_streams")
 
     def _optim(self):
         st = _lib.stream_ptr()
@@ -92,22 +106,58 @@ class TrainEngine:
         check(self.lib.dvae_clip_adam(ptr(self.flat), ptr(self.grad), ptr(self.m), ptr(self.v), self.n, ptr(self.sumsq),
                                       self.max_norm, 1.0 / self.world, ptr(self.hyper), 1, st), "dvae_clip_adam")
 
-    def _allreduce(self):
-        if self.world > 1:
-            dist.all_reduce(self.grad, op=dist.ReduceOp.SUM, group=self.pg)
+    def _grad_buckets(self):
+        """(decoder bucket, [remaining buckets]) as views of the flat gradient buffer: decoder.* is one contiguous range."""
+        lay, named = self.model._layout, dict(self.model.named_parameters())
+        dec = [n for n in lay if n.startswith("decoder.")]
+        lo = min(lay[n] for n in dec)
+        hi = max((lay[n] + named[n].numel() + 3) // 4 * 4 for n in dec)
+        rest = [self.grad[a:b] for a, b in ((0, lo), (hi, self.n)) if b > a]
+        return self.grad[lo:hi], rest
 
     def _run(self):
-        if not self.use_graph:
-            self._fwd_bwd()
-            self._allreduce()
-            self._optim()
+        if self.world == 1:
+            if not self.use_graph:
+                self._fwd_bwd()
+                self._optim()
+                return
+            if self._graphs is None:
+                self._capture()
+            ga, gb = self._graphs
+            ga.replay()
+            gb.replay()
             return
-        if self._graphs is None:
+        # data parallel: all-reduce the decoder gradients on a side stream while heads + encoder backward run
+        if self._buckets is None:
+            self._buckets = self._grad_buckets()
+            self._comm = torch.cuda.Stream(device=self.device)
+        dec_bucket, rest = self._buckets
+        cur = torch.cuda.current_stream()
+        if self.use_graph and self._graphs is None:
             self._capture()
-        ga, gb = self._graphs
-        ga.replay()
-        self._allreduce()
-        gb.replay()
+        if self.use_graph:
+            self._graphs[0].replay()
+        else:
+            self._fwd_bwd(1)
+        overlap = os.environ.get("DVAE_DP_OVERLAP", "1") != "0"
+        if overlap:
+            self._comm.wait_stream(cur)
+            with torch.cuda.stream(self._comm):
+                dist.all_reduce(dec_bucket, op=dist.ReduceOp.SUM, group=self.pg)
+        if self.use_graph:
+            self._graphs[1].replay()
+        else:
+            self._fwd_bwd(2)
+        if overlap:
+            for b in rest:
+                dist.all_reduce(b, op=dist.ReduceOp.SUM, group=self.pg)
+            cur.wait_stream(self._comm)
+        else:
+            dist.all_reduce(self.grad, op=dist.ReduceOp.SUM, group=self.pg)
+        if self.use_graph:
+            self._graphs[2].replay()
+        else:
+            self._optim()
 
     def _capture(self):
         # warm up eagerly on a side stream (lazy module loading, cudaFuncSetAttribute, allocator), then capture
@@ -120,16 +170,22 @@ class TrainEngine:
                 self._optim()
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
-        ga, gb = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
-        with torch.cuda.graph(ga, stream=s):
-            self._fwd_bwd()
+        parts = [None] if self.world == 1 else [1, 2]
+        graphs = []
+        for part in parts:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=s):
+                self._fwd_bwd(part)
+            graphs.append(g)
+        gb = torch.cuda.CUDAGraph()
         with torch.cuda.graph(gb, stream=s):
             self._optim()
+        graphs.append(gb)
         torch.cuda.synchronize()
         # undo the warm-up updates so that capture leaves the training state untouched
         self.flat.copy_(snap[0]); self.m.copy_(snap[1]); self.v.copy_(snap[2])
         self.grad.zero_()
-        self._graphs = (ga, gb)
+        self._graphs = tuple(graphs)
 
     # ---- per-step host scalars -----------------------------------------------------------------
     def _fill_scalars(self):
