@@ -22,6 +22,9 @@ class TrainEngine:
     def __init__(self, model, params, B, T, lr=None, total_steps=None, use_graph=True, max_norm=5.0,
                  process_group=None, seed=None):
         model._require_cuda()
+        if len(model.adversaries) or len(model.mi_estimators):
+            raise NotImplementedError("TrainEngine captures the ELBO + discriminator step; models with adversarial_loss / mi_loss "
+                                      "train through the drop-in path (forward / compute_all_losses / backward, run.py:217-276)")
         self.model, self.params, self.B, self.T = model, params, B, T
         self.lib = _lib.load()
         self.device = model._flat.device

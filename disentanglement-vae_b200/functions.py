@@ -138,6 +138,123 @@ class _LogitsFn(Function):
         return d_h, d_w, d_b
 
 
+class _SmallLinearFn(Function):
+    """y = act(x W^T + b) for the small heads on the latent spaces (adversaries, CLUB estimators).
+    act: 0 none, 1 tanh, 2 ReLU.  x may be a column slice of a wider matrix (row stride = x.stride(0))."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, act):
+        lib = _lib.load()
+        if x.stride(-1) != 1:
+            x = x.contiguous()
+        Bn, K, N = x.size(0), x.size(1), weight.size(0)
+        st = _lib.stream_ptr()
+        out = torch.empty(Bn, N, device=x.device, dtype=torch.float32)
+        check(lib.dvae_linear(ptr(x), x.stride(0), 0, ptr(weight), K, 0, ptr(out), N, Bn, N, K, ptr(bias), None, 0.0,
+                              1 if act == 1 else 0, st), "dvae_linear")
+        if act == 2:
+            check(lib.dvae_relu(ptr(out), out.numel(), st), "dvae_relu")
+        ctx.save_for_backward(x, weight, out)
+        ctx.act = act
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = _lib.load()
+        x, weight, out = ctx.saved_tensors
+        Bn, K, N = x.size(0), x.size(1), weight.size(0)
+        st = _lib.stream_ptr()
+        g = g.contiguous()
+        if ctx.act:
+            d = torch.empty_like(g)
+            check(lib.dvae_act_bwd(ptr(out), ptr(g), ptr(d), g.numel(), ctx.act, st), "dvae_act_bwd")
+            g = d
+        d_x = d_w = d_b = None
+        if ctx.needs_input_grad[0]:
+            d_x = torch.empty(Bn, K, device=g.device, dtype=torch.float32)
+            check(lib.dvae_linear(ptr(g), N, 0, ptr(weight), K, 1, ptr(d_x), K, Bn, K, N, None, None, 0.0, 0, st), "dvae_linear")
+        if ctx.needs_input_grad[1]:
+            d_w = torch.empty_like(weight)
+            check(lib.dvae_linear(ptr(g), N, 1, ptr(x), x.stride(0), 1, ptr(d_w), K, N, K, Bn, None, None, 0.0, 0, st), "dvae_linear")
+        if ctx.needs_input_grad[2]:
+            d_b = torch.empty(N, device=g.device, dtype=torch.float32)
+            check(lib.dvae_colsum(ptr(g), N, Bn, N, ptr(d_b), 0.0, st), "dvae_colsum")
+        return d_x, d_w, d_b, None
+
+
+class _EntropyLossFn(Function):
+    """mean_b sum_c p log p of clamped sigmoid / softmax probabilities (vae/model.py:247-258)."""
+
+    @staticmethod
+    def forward(ctx, logits):
+        lib = _lib.load()
+        logits = logits.contiguous()
+        loss = torch.empty(1, device=logits.device, dtype=torch.float32)
+        check(lib.dvae_entropy_loss(ptr(logits), logits.size(0), logits.size(1), ptr(loss), None, None, _lib.stream_ptr()),
+              "dvae_entropy_loss")
+        ctx.save_for_backward(logits)
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = _lib.load()
+        (logits,) = ctx.saved_tensors
+        d = torch.empty_like(logits)
+        gs = g.reshape(1).to(torch.float32).contiguous()
+        check(lib.dvae_entropy_loss(ptr(logits), logits.size(0), logits.size(1), None, ptr(gs), ptr(d), _lib.stream_ptr()),
+              "dvae_entropy_loss")
+        return d
+
+
+class _ClubMiFn(Function):
+    """CLUB.forward's estimate from (mu, logvar) = q(y|x) and the samples y (vae/losses.py:53-67)."""
+
+    @staticmethod
+    def forward(ctx, mu, logvar, y):
+        lib = _lib.load()
+        mu, logvar, y = mu.contiguous(), logvar.contiguous(), y.contiguous()
+        out = torch.empty(1, device=mu.device, dtype=torch.float32)
+        check(lib.dvae_club_mi(ptr(mu), ptr(logvar), ptr(y), mu.size(0), mu.size(1), ptr(out), None, None, None, None, None,
+                               _lib.stream_ptr()), "dvae_club_mi")
+        ctx.save_for_backward(mu, logvar, y)
+        return out.reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = _lib.load()
+        mu, logvar, y = ctx.saved_tensors
+        d_mu, d_lv, d_y = torch.empty_like(mu), torch.empty_like(mu), torch.empty_like(mu)
+        ws = torch.empty(3 * mu.size(1), device=mu.device, dtype=torch.float32)
+        gs = g.reshape(1).to(torch.float32).contiguous()
+        check(lib.dvae_club_mi(ptr(mu), ptr(logvar), ptr(y), mu.size(0), mu.size(1), None, ptr(gs), ptr(d_mu), ptr(d_lv),
+                               ptr(d_y), ptr(ws), _lib.stream_ptr()), "dvae_club_mi")
+        return d_mu, d_lv, d_y
+
+
+class _ClubNllFn(Function):
+    """CLUB.learning_loss = -loglikeli (vae/losses.py:69-74)."""
+
+    @staticmethod
+    def forward(ctx, mu, logvar, y):
+        lib = _lib.load()
+        mu, logvar, y = mu.contiguous(), logvar.contiguous(), y.contiguous()
+        out = torch.empty(1, device=mu.device, dtype=torch.float32)
+        check(lib.dvae_club_nll(ptr(mu), ptr(logvar), ptr(y), mu.size(0), mu.size(1), ptr(out), None, None, None,
+                                _lib.stream_ptr()), "dvae_club_nll")
+        ctx.save_for_backward(mu, logvar, y)
+        return out.reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = _lib.load()
+        mu, logvar, y = ctx.saved_tensors
+        d_mu, d_lv = torch.empty_like(mu), torch.empty_like(mu)
+        gs = g.reshape(1).to(torch.float32).contiguous()
+        check(lib.dvae_club_nll(ptr(mu), ptr(logvar), ptr(y), mu.size(0), mu.size(1), None, ptr(gs), ptr(d_mu), ptr(d_lv),
+                                _lib.stream_ptr()), "dvae_club_nll")
+        return d_mu, d_lv, None
+
+
 class _DscLossFn(Function):
     """Per-discriminator loss and accuracy from packed logits (vae/losses.py:180-196)."""
 
@@ -231,8 +348,16 @@ def run_forward(model, inputs, lengths, coins, eps=None):
     preds = inputs.clone()
     preds[:, 0] = model.sos_token_idx          # tf: predictions are the forced next inputs (model.py:464-472)
     logits = FusedLogits(model, plan, outs[0], B, T)
-    return {"decoder_logits": logits, "latent_params": lat, "dsc_logits": dsc, "adv_logits": {},
+    return {"decoder_logits": logits, "latent_params": lat, "dsc_logits": dsc, "adv_logits": adversary_logits(model, lat),
             "token_predictions": preds, "context": context}
+
+
+def adversary_logits(model, latent_params):
+    """vae/model.py:432-436: every adversary reads the sampled z of its latent space."""
+    out = {}
+    for name, adv in model.adversaries.items():
+        out[name] = adv(latent_params[name.split('-')[0]].z)
+    return out
 
 
 def run_encoder(model, inputs, lengths):

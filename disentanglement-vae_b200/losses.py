@@ -8,9 +8,50 @@ per-space KL from the fused-heads kernel, the discriminator losses from `dvae_ds
 import math
 
 import torch
+import torch.nn as nn
 
 from . import _lib
 from .model import FusedLogits, LatentParams, DscLogits
+
+
+class CLUB(nn.Module):
+    """CLUB upper bound on I(X;Y) with a variational q(Y|X) (Cheng et al., ICML 2020; vae/losses.py:10-74).  The
+    nn.Sequential members are parameter containers with the reference's names and initialisation; the arithmetic runs
+    in the C-ABI kernels (dvae_linear, dvae_relu / dvae_act_bwd, dvae_club_mi, dvae_club_nll)."""
+
+    def __init__(self, x_dim, y_dim, hidden_size):
+        super().__init__()
+        self.p_mu = nn.Sequential(nn.Linear(x_dim, hidden_size // 2), nn.ReLU(), nn.Linear(hidden_size // 2, y_dim))
+        self.p_logvar = nn.Sequential(nn.Linear(x_dim, hidden_size // 2), nn.ReLU(), nn.Linear(hidden_size // 2, y_dim),
+                                      nn.Tanh())
+        self.optimizer = torch.optim.Adam(self.parameters(), lr=5e-4)      # vae/losses.py:41
+
+    def optimizer_step(self, loss):
+        self.optimizer.zero_grad()
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(self.parameters(), 1.0)
+        self.optimizer.step()
+
+    def get_mu_logvar(self, x_samples):
+        from .functions import _SmallLinearFn
+        h = _SmallLinearFn.apply(x_samples, self.p_mu[0].weight, self.p_mu[0].bias, 2)
+        mu = _SmallLinearFn.apply(h, self.p_mu[2].weight, self.p_mu[2].bias, 0)
+        h = _SmallLinearFn.apply(x_samples, self.p_logvar[0].weight, self.p_logvar[0].bias, 2)
+        logvar = _SmallLinearFn.apply(h, self.p_logvar[2].weight, self.p_logvar[2].bias, 1)
+        return mu, logvar
+
+    def forward(self, x_samples, y_samples):
+        from .functions import _ClubMiFn
+        mu, logvar = self.get_mu_logvar(x_samples)
+        return _ClubMiFn.apply(mu, logvar, y_samples)
+
+    def loglikeli(self, x_samples, y_samples):
+        return -self.learning_loss(x_samples, y_samples)
+
+    def learning_loss(self, x_samples, y_samples):
+        from .functions import _ClubNllFn
+        mu, logvar = self.get_mu_logvar(x_samples)
+        return _ClubNllFn.apply(mu, logvar, y_samples)
 
 
 def reconstruction_loss(targets, logits, target_lengths):
@@ -88,18 +129,37 @@ def _single_dsc_loss(dsc, logits, targets):
 
 
 def compute_adversarial_losses(model, adversary_logits, Ybatch):
-    """vae/losses.py:199-223 with no adversaries configured (the accelerated path's scope)."""
-    if len(adversary_logits) > 0:
-        raise NotImplementedError("adversarial objective: SURVEY.md 8f n2")
-    return {"total_adv_loss": torch.tensor(0.0, device=model.device), "idv_adv_losses": {},
-            "idv_adv_dsc_losses": {}, "idv_adv_dsc_accs": {}}
+    """vae/losses.py:199-223."""
+    idv_adv_losses, idv_dsc_losses, idv_dsc_accs = dict(), dict(), dict()
+    total_adv_loss = torch.tensor(0.0, device=model.device)
+    for adv_name, adv_logits in adversary_logits.items():
+        adv = model.adversaries[adv_name]
+        latent_name, label_name = adv_name.split('-')
+        targets = Ybatch[label_name].to(model.device)
+        adv_loss = adv.compute_adversarial_loss(adv_logits)
+        idv_adv_losses[adv_name] = adv_loss.item()
+        total_adv_loss = total_adv_loss + adv_loss
+        idv_dsc_losses[adv_name] = adv.compute_discriminator_loss(adv_logits, targets)     # updates the adversary later
+        idv_dsc_accs[adv_name] = adv.compute_accuracy(adv_logits.detach(), targets).item()
+    return {"total_adv_loss": total_adv_loss, "idv_adv_losses": idv_adv_losses,
+            "idv_adv_dsc_losses": idv_dsc_losses, "idv_adv_dsc_accs": idv_dsc_accs}
 
 
 def compute_mi_losses(model, latent_params, beta=1.0):
-    """vae/losses.py:226-242 with no MI estimators configured."""
-    if len(model.mi_estimators) > 0:
-        raise NotImplementedError("MI objective: SURVEY.md 8f n2")
-    return {"total_mi": torch.tensor(0.0, device=model.device), "idv_mi_estimates": {}}
+    """vae/losses.py:226-242."""
+    idv_mi_estimates = dict()
+    total_mi = torch.tensor(0.0, device=model.device)
+    for name1, params1 in latent_params.items():
+        for name2, params2 in latent_params.items():
+            if name1 == name2:
+                continue
+            mi_estimator = model.mi_estimators.get(f"{name1}-{name2}")
+            if mi_estimator is None:
+                continue
+            mi_estimate = mi_estimator(params1.z, params2.z) * beta
+            idv_mi_estimates[f"{name1}-{name2}"] = mi_estimate.item()
+            total_mi = total_mi + mi_estimate
+    return {"total_mi": total_mi, "idv_mi_estimates": idv_mi_estimates}
 
 
 def compute_all_losses(model, model_outputs, Xbatch, Ybatch, lengths, kl_weights_dict, mi_loss_weight=0.01):

@@ -112,6 +112,43 @@ class Discriminator(_DeviceMixin, nn.Module):
         return losses._single_dsc_loss(self, logits, targets)[1]
 
 
+class AdversarialDiscriminator(Discriminator):
+    """Tries to predict label `label_name` from latent space `latent_name` (vae/model.py:219-258).  The VAE is trained
+    to maximise the entropy of its predictions; the adversary itself is trained, with its own Adam (lr 3e-4), on the
+    DETACHED latent.  As in the reference, when `optimizer_step` runs the adversary's .grad already holds the
+    entropy-term gradients from `total_loss.backward()` (run.py:254-260): both are applied."""
+
+    def __init__(self, latent_name, label_name, latent_dim, output_dim):
+        super().__init__(f"{latent_name}-{label_name}", latent_dim, output_dim)
+        self.latent_name, self.label_name = latent_name, label_name
+        self.optimizer = torch.optim.Adam(self.parameters(), lr=3e-4)
+        self.detached_inputs = None
+
+    def forward(self, inputs):
+        from .functions import _SmallLinearFn
+        self.detached_inputs = inputs.detach()
+        return _SmallLinearFn.apply(inputs, self.linear.weight, self.linear.bias, 0)
+
+    def compute_discriminator_loss(self, logits, targets):
+        from . import losses
+        from .functions import _SmallLinearFn
+        detached_logits = _SmallLinearFn.apply(self.detached_inputs, self.linear.weight, self.linear.bias, 0)
+        return losses._single_dsc_loss(self, detached_logits, targets)[0]
+
+    def optimizer_step(self, dsc_loss):
+        dsc_loss.backward(retain_graph=True)
+        self.optimizer.step()
+        self.optimizer.zero_grad()
+
+    def compute_adversarial_loss(self, logits):
+        from .functions import _EntropyLossFn
+        if logits.dim() == 1:
+            logits = logits.unsqueeze(1)
+        elif logits.dim() > 2:
+            raise ValueError(f"Got unexpected logits shape {logits.size()}")
+        return _EntropyLossFn.apply(logits)        # = -H: minimising it maximises the entropy
+
+
 class LatentParams(OrderedDict):
     """{space: Params(z, mu, logvar)} plus the fused per-space KL vector (autograd-connected)."""
     kl = None
@@ -169,12 +206,9 @@ class VariationalSeq2Seq(_DeviceMixin, nn.Module):
             leftover = self.latent_dim - self.dsc_latent_dim
             self.context2params["content"] = nn.Linear(linear_insize, 2 * leftover)
         self.adversarial_loss, self.mi_loss = adversarial_loss, mi_loss
-        if adversarial_loss or mi_loss:
-            raise NotImplementedError(
-                "adversarial / MI objectives (vae/model.py:323-355) are scheduled after the core path "
-                "(SURVEY.md 8f n2); build with adversarial_loss=false, mi_loss=false")
-        self.adversaries = dict()
-        self.mi_estimators = dict()
+        # same construction order as the reference (vae/model.py:304-317), so a seed gives the same initial weights
+        self.adversaries = self._get_adversaries() if adversarial_loss is True else dict()
+        self.mi_estimators = self._get_mi_estimators() if mi_loss is True else dict()
         self.z2hidden = nn.Linear(self.latent_dim, 2 * decoder.hidden_size * decoder.num_layers)
         self.sos_token_idx, self.eos_token_idx = sos_token_idx, eos_token_idx
         self._plans = {}
@@ -182,9 +216,37 @@ class VariationalSeq2Seq(_DeviceMixin, nn.Module):
         self._flat = None
         self._dims = None
 
+    def _get_adversaries(self):
+        """vae/model.py:323-335: one adversary per (latent space, label) pair with latent != label."""
+        adversaries = nn.ModuleDict()
+        for latent_name, layer in self.context2params.items():
+            latent_size = layer.out_features // 2
+            for label_name, dsc in self.discriminators.items():
+                if latent_name == label_name:
+                    continue
+                adversaries[f"{latent_name}-{label_name}"] = AdversarialDiscriminator(latent_name, label_name, latent_size,
+                                                                                   dsc.output_dim)
+        return adversaries
+
+    def _get_mi_estimators(self):
+        """vae/model.py:337-355: one CLUB estimator per unordered pair of latent spaces (a plain dict, as in the
+        reference: not part of state_dict / parameters())."""
+        from . import losses
+        mi_estimators, seen = dict(), set()
+        for ni, li in self.context2params.items():
+            for nj, lj in self.context2params.items():
+                if ni == nj or (nj, ni) in seen:
+                    continue
+                seen.add((ni, nj))
+                si, sj = li.out_features // 2, lj.out_features // 2
+                mi_estimators[f"{ni}-{nj}"] = losses.CLUB(si, sj, max([si, sj, 5]))
+        return mi_estimators
+
     # ---- parameter fusion: one flat fp32 buffer, nn.Parameters are views into it ----------------
     def _apply(self, fn, *a, **k):
         out = super()._apply(fn, *a, **k)
+        for est in self.mi_estimators.values():       # plain dict: nn.Module._apply does not reach them
+            est._apply(fn, *a, **k)
         self._fuse_parameters()
         return out
 
@@ -194,7 +256,8 @@ class VariationalSeq2Seq(_DeviceMixin, nn.Module):
     def flat_order(self):
         """Names of the trainable parameters in flat-buffer order (grouped so that the fused-head
         kernel sees the per-space context2params / discriminator tensors as single matrices)."""
-        named = OrderedDict((n, p) for n, p in self.named_parameters() if p.requires_grad)
+        named = OrderedDict((n, p) for n, p in self.named_parameters()
+                            if p.requires_grad and not n.startswith("adversaries"))     # adversaries own their optimizers
         spaces = list(self.context2params.keys())
         c2p_w = [f"context2params.{s}.weight" for s in spaces]
         c2p_b = [f"context2params.{s}.bias" for s in spaces]

@@ -29,7 +29,7 @@ def _seed_sampling(plan):
 
 def run_forward_sampled(model, inputs, lengths, coins, eps=None):
     """forward() when at least one decoding step samples its input (coins[i-1] False for position i)."""
-    from .functions import _EncDecFn, _param_list, _package
+    from .functions import _EncDecFn, _param_list, _package, adversary_logits
     B, T = inputs.shape
     need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in model.parameters())
     plan = model.get_plan(B, T, need_grad)
@@ -43,7 +43,7 @@ def run_forward_sampled(model, inputs, lengths, coins, eps=None):
     outs = _EncDecFn.apply(model, plan, inputs, lengths, eps, preds, tuple(coins), model.training, *params)
     lat, dsc, context = _package(model, plan, outs, B, T, inputs)
     logits = FusedLogits(model, plan, outs[0], B, T)
-    return {"decoder_logits": logits, "latent_params": lat, "dsc_logits": dsc, "adv_logits": {},
+    return {"decoder_logits": logits, "latent_params": lat, "dsc_logits": dsc, "adv_logits": adversary_logits(model, lat),
             "token_predictions": preds, "context": context}
 
 

@@ -73,6 +73,28 @@ int dvae_tc16_linear(const float* A, int64_t lda, int trans_a, const float* B, i
                      float beta, int act, float a_scale, float b_scale, const uint32_t* a_amax_bits,
                      const uint32_t* b_amax_bits, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Auxiliary disentanglement objectives on the latent spaces (adversaries and CLUB mutual-information estimators;
+ * vae/model.py:219-258,323-355, vae/losses.py:10-74,199-242).  Operands are [B, O] / [B, D] row-major matrices of a few
+ * KB; each entry point is forward + backward: gradients are written when their output pointers are non-NULL,
+ * multiplied by *g (device scalar, NULL = 1).
+ *   dvae_entropy_loss: loss = mean_b sum_c p log p with p = clamp(sigmoid(x) if O == 1 else softmax(x), 1e-8, 1-1e-8)
+ *                      -- AdversarialDiscriminator.compute_adversarial_loss (model.py:247-258).
+ *   dvae_club_mi:      mi = mean_i sum_d [ -(mu_id - y_id)^2 + mean_j (y_jd - mu_id)^2 ] / (2 exp(logvar_id))
+ *                      -- CLUB.forward (losses.py:53-67); gradients w.r.t. mu, logvar AND y; ws: 3*D floats.
+ *   dvae_club_nll:     loss = mean_b sum_d [ (mu - y)^2 / exp(logvar) + logvar ] -- CLUB.learning_loss (losses.py:69-74).
+ *   dvae_act_bwd:      d = g * (1 - y^2) (act 1, tanh) or g * [y > 0] (act 2, ReLU), y = the activation's OUTPUT.
+ *   dvae_relu:         in-place ReLU.
+ * ------------------------------------------------------------------------------------------- */
+int dvae_entropy_loss(const float* logits, int B, int O, float* loss, const float* g_loss, float* d_logits,
+                      void* stream);
+int dvae_club_mi(const float* mu, const float* logvar, const float* y, int B, int D, float* mi,
+                 const float* g_mi, float* d_mu, float* d_logvar, float* d_y, float* ws, void* stream);
+int dvae_club_nll(const float* mu, const float* logvar, const float* y, int B, int D, float* loss,
+                  const float* g_loss, float* d_mu, float* d_logvar, void* stream);
+int dvae_act_bwd(const float* y, const float* g, float* d, int64_t n, int act, void* stream);
+int dvae_relu(float* x, int64_t n, void* stream);
+
 /* Independent kernels inside one call (e.g. the weight-gradient GEMMs of an LSTM layer) run on library-owned side
  * streams and are joined back into `stream` before the call returns.  dvae_defer_joins(1) lets the backward entry
  * points (dvae_lstm_seq_bwd, dvae_latent_heads_bwd) return with that side work still in flight, so that it overlaps

@@ -155,6 +155,100 @@ def run_case(name, params, V, label_dims, B, T, kl_weights, seed=10, eps_seed=12
     print(f"wrote {path}: {os.path.getsize(path) / 1024:.1f} KiB, total loss {total.item():.6f}")
 
 
+def run_adv_mi_case(name, params, V, label_dims, B, T, kl_weights, seed=10, eps_seed=4321):
+    """Full reference train step with the adversarial + MI objectives enabled, in run.py:217-276's order:
+    forward, compute_all_losses, total.backward(retain_graph), clip 5.0, adversary optimizer steps, VAE Adam step,
+    MI-estimator (CLUB) learning steps.  Records every intermediate the B200 path must reproduce."""
+    ref_utils.set_seed(seed)
+    vae = ref_model.build_vae(params, V, None, label_dims, torch.device("cpu"), SOS, EOS)
+    gen = torch.Generator().manual_seed(seed + 7)
+    X, lengths, Y = make_batch(gen, B, T, V, label_dims)
+    out = {"B": B, "T": T, "V": V, "sos": SOS, "eos": EOS, "inputs": X.numpy(), "lengths": lengths.numpy(),
+           "lr": params["learn_rate"]}
+    for k, v in Y.items():
+        out[f"Y.{k}"] = v.numpy()
+    for k, v in vae.state_dict().items():
+        out[f"sd.{k}"] = v.detach().numpy().copy()
+    for n, est in vae.mi_estimators.items():            # not part of the state_dict (plain dict, model.py:337)
+        for k, v in est.state_dict().items():
+            out[f"mi0.{n}.{k}"] = v.detach().numpy().copy()
+    space_names = list(vae.context2params.keys())
+    out["space_names"] = np.array(space_names)
+    out["space_dims"] = np.array([vae.context2params[n].out_features // 2 for n in space_names])
+    out["label_names"] = np.array(list(label_dims.keys()))
+    out["label_dims"] = np.array(list(label_dims.values()))
+    out["adv_names"] = np.array(list(vae.adversaries.keys()))
+    out["mi_names"] = np.array(list(vae.mi_estimators.keys()))
+    for k in space_names:
+        out[f"klw.{k}"] = np.float64(kl_weights.get(k, kl_weights["default"]))
+    vae.train()
+    torch.manual_seed(eps_seed)
+    for n in space_names:
+        zs = vae.context2params[n].out_features // 2
+        torch.randn(B, zs)
+        out[f"eps.{n}"] = torch.randn(B, zs).numpy()
+    torch.manual_seed(eps_seed)
+    random.seed(seed)
+    opt = torch.optim.Adam(vae.trainable_parameters(), lr=params["learn_rate"])
+    output = vae(X, lengths, teacher_forcing_prob=1.0)
+    for n in space_names:
+        out[f"z.{n}"] = output["latent_params"][n].z.detach().numpy()
+    for n, l in output["adv_logits"].items():
+        out[f"adv_logits.{n}"] = l.detach().numpy()
+    L = {}
+    L.update(ref_losses.reconstruction_loss(X, output["decoder_logits"], lengths))
+    L.update(ref_losses.compute_kl_divergence_losses(vae, output["latent_params"], kl_weights))
+    L.update(ref_losses.compute_discriminator_losses(vae, output["dsc_logits"], Y))
+    L.update(ref_losses.compute_adversarial_losses(vae, output["adv_logits"], Y))
+    L.update(ref_losses.compute_mi_losses(vae, output["latent_params"], beta=0.01))
+    total = (L["reconstruction_loss"] + L["total_weighted_kl"] + L["total_dsc_loss"] + L["total_adv_loss"] + L["total_mi"])
+    out["loss.total"] = total.item()
+    out["loss.total_adv"] = L["total_adv_loss"].item()
+    out["loss.total_mi"] = L["total_mi"].item()
+    for n, v in L["idv_adv_losses"].items():
+        out[f"adv_loss.{n}"] = v
+    for n, v in L["idv_adv_dsc_losses"].items():
+        out[f"adv_dsc_loss.{n}"] = v.item()
+    for n, v in L["idv_adv_dsc_accs"].items():
+        out[f"adv_dsc_acc.{n}"] = v
+    for n, v in L["idv_mi_estimates"].items():
+        out[f"mi_est.{n}"] = v
+    total.backward(retain_graph=True)
+    for k, p in vae.named_parameters():
+        if p.grad is not None:
+            out[f"grad.{k}"] = p.grad.detach().numpy().copy()       # adversaries.*: entropy-term gradients only
+    out["grad_norm"] = torch.nn.utils.clip_grad_norm_(vae.trainable_parameters(), 5.0).item()
+    for n, dl in L["idv_adv_dsc_losses"].items():                  # AdversarialDiscriminator.optimizer_step, unrolled
+        adv = vae.adversaries[n]
+        dl.backward(retain_graph=True)
+        for k, p in adv.named_parameters():
+            out[f"adv_grad_at_step.{n}.{k}"] = p.grad.detach().numpy().copy()   # entropy + discriminator gradients
+        adv.optimizer.step()
+        adv.optimizer.zero_grad()
+    opt.step()
+    opt.zero_grad()
+    for n, est in vae.mi_estimators.items():                       # run.py:264-276
+        n1, n2 = n.split('-')
+        z1, z2 = output["latent_params"][n1].z.detach(), output["latent_params"][n2].z.detach()
+        est.train()
+        ll = est.learning_loss(z1, z2)
+        out[f"mi_learning_loss.{n}"] = ll.item()
+        est.optimizer.zero_grad()
+        ll.backward()
+        for k, p in est.named_parameters():
+            out[f"mi_grad.{n}.{k}"] = p.grad.detach().numpy().copy()
+        torch.nn.utils.clip_grad_norm_(est.parameters(), 1.0)
+        est.optimizer.step()
+        for k, v in est.state_dict().items():
+            out[f"mi_after.{n}.{k}"] = v.detach().numpy().copy()
+    for k, v in vae.state_dict().items():
+        out[f"sd_after.{k}"] = v.detach().numpy().copy()
+    path = os.path.join(HERE, f"{name}.npz")
+    np.savez_compressed(path, **out)
+    print(f"wrote {path}: {os.path.getsize(path) / 1024:.1f} KiB, total loss {total.item():.6f}, adv {out['loss.total_adv']:.6f}, "
+          f"mi {out['loss.total_mi']:.6f}")
+
+
 def cyclic_table():
     rows = []
     for total in (100, 31260, 7):
@@ -167,6 +261,14 @@ def cyclic_table():
 
 if __name__ == "__main__":
     torch.set_num_threads(1)
+    if "--adv-mi" in sys.argv:          # only the adversarial + MI case (leaves the other files untouched)
+        run_adv_mi_case("tiny_adv_mi", make_params(bidirectional_encoder=True, embedding_dim=10, hidden_dim=8,
+                                                    latent_dims={"total": 9, "polarity": 1, "uncertainty": 2},
+                                                    learn_rate=3e-4, adversarial_loss=True, mi_loss=True,
+                                                    lambdas={"default": 0.2, "polarity": 0.005, "uncertainty": 0.005}),
+                        V=31, label_dims={"uncertainty": 3, "polarity": 1}, B=6, T=7,
+                        kl_weights={"default": 0.2, "polarity": 0.005, "uncertainty": 0.005})
+        sys.exit(0)
     # cfg-1-like: uni-directional encoder, polarity + content (config_example.json shape, shrunk)
     run_case("tiny_uni", make_params(), V=37, label_dims={"polarity": 1}, B=5, T=8,
              kl_weights={"default": 0.01, "polarity": 0.005})

@@ -116,7 +116,35 @@ def test_cpu_model_refuses_to_run(dvae):
     with pytest.raises(dvae.DvaeError, match="no CPU fallback"):
         vae(torch.zeros(2, 5, dtype=torch.long), torch.tensor([5, 3]))
     with pytest.raises(NotImplementedError):
-        dvae.build_vae(_params(adversarial_loss=True), 30, None, {"polarity": 1}, torch.device("cpu"), 2, 3)
+        dvae.build_vae(_params(bow_encoder=True), 30, None, {"polarity": 1}, torch.device("cpu"), 2, 3)
+
+
+@pytest.mark.skipif(not ref_shim.reference_available(), reason="reference checkout not present (GPU box)")
+def test_adversarial_and_mi_modules_match_reference_structure_and_seeded_init(dvae):
+    """adversarial_loss / mi_loss: same adversary and estimator names, same state_dict keys, and -- because the
+    construction order is the reference's -- bit-identical seeded initial weights (incl. the CLUB estimators, which the
+    reference keeps in a plain dict outside the state_dict)."""
+    ref_model, _, ref_utils = ref_shim.load_reference()
+    p = _params(adversarial_loss=True, mi_loss=True, latent_dims={"total": 9, "polarity": 1, "uncertainty": 2})
+    label_dims = {"uncertainty": 3, "polarity": 1}
+    ref_utils.set_seed(10)
+    ref = ref_model.build_vae(p, 41, None, label_dims, torch.device("cpu"), 2, 3)
+    dvae.set_seed(10)
+    mine = dvae.build_vae(p, 41, None, label_dims, torch.device("cpu"), 2, 3)
+    assert list(ref.adversaries.keys()) == list(mine.adversaries.keys())
+    assert list(ref.mi_estimators.keys()) == list(mine.mi_estimators.keys())
+    rs, ms = ref.state_dict(), mine.state_dict()
+    assert list(rs.keys()) == list(ms.keys())
+    for k in rs:
+        assert torch.equal(rs[k], ms[k]), k
+    for n in ref.mi_estimators:
+        a, b = ref.mi_estimators[n].state_dict(), mine.mi_estimators[n].state_dict()
+        assert list(a.keys()) == list(b.keys())
+        for k in a:
+            assert torch.equal(a[k], b[k]), (n, k)
+    assert [n for n, _ in mine.named_parameters() if n.startswith("adversaries")]
+    assert not [q for q in mine.trainable_parameters() if any(q is w for w in mine.adversaries.parameters())]
+    assert not any(n.startswith("adversaries") for n in mine._layout)      # adversaries own their optimizers
 
 
 @pytest.mark.skipif(not ref_shim.reference_available(), reason="reference checkout not present (GPU box)")

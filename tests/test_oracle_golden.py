@@ -106,3 +106,25 @@ def test_float32_oracle_close_to_float64():
     g, sd, spec, fw64 = _setup("tiny_bi", np.float64)
     _, _, _, fw32 = _setup("tiny_bi", np.float32)
     assert abs(fw32["total_loss"] - fw64["total_loss"]) < 1e-5 * abs(fw64["total_loss"])
+
+
+def test_oracle_auxiliary_objectives_match_reference_golden():
+    """entropy loss of the adversaries, CLUB MI estimate (x beta 0.01) and CLUB learning loss, restated in numpy, against
+    what the unmodified reference computed (tests/golden/tiny_adv_mi.npz, make_golden.py --adv-mi)."""
+    g = load_golden("tiny_adv_mi")
+    for n in [str(x) for x in g["adv_names"]]:
+        loss, _ = O.entropy_loss(g[f"adv_logits.{n}"].astype(np.float64))
+        assert abs(loss - float(g[f"adv_loss.{n}"])) < 1e-6, n
+    total = 0.0
+    for n in [str(x) for x in g["mi_names"]]:
+        n1, n2 = n.split("-")
+        W = {k[len(f"mi0.{n}."):]: g[k].astype(np.float64) for k in g if k.startswith(f"mi0.{n}.")}
+        x, y = g[f"z.{n1}"].astype(np.float64), g[f"z.{n2}"].astype(np.float64)
+        mu, _ = O.club_mlp(x, W, "p_mu")
+        lv, _ = O.club_mlp(x, W, "p_logvar")
+        mi = O.club_mi(mu, lv, y)[0] * 0.01
+        assert abs(mi - float(g[f"mi_est.{n}"])) < 1e-7, n
+        total += mi
+        assert abs(O.club_nll(mu, lv, y)[0] - float(g[f"mi_learning_loss.{n}"])) < 1e-5, n
+    assert abs(total - float(g["loss.total_mi"])) < 1e-7
+    assert abs(sum(float(g[f"adv_loss.{n}"]) for n in g["adv_names"]) - float(g["loss.total_adv"])) < 1e-5
