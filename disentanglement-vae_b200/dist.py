@@ -27,3 +27,28 @@ def allreduce_mean_(flat, group=None):
     dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
     flat.mul_(1.0 / world)
     return flat
+
+
+def grad_buckets(model, flat_grad):
+    """(decoder bucket, [remaining buckets]) as views of a flat gradient buffer laid out like `model._layout`.
+    decoder.* is one contiguous range (named_parameters order) and its gradients are final as soon as the decoder's
+    backward has run, so their all-reduce can overlap the heads' and the encoder's backward (engine.TrainEngine)."""
+    lay, named = model._layout, dict(model.named_parameters())
+    dec = [n for n in lay if n.startswith("decoder.")]
+    lo = min(lay[n] for n in dec)
+    hi = max((lay[n] + named[n].numel() + 3) // 4 * 4 for n in dec)
+    n = flat_grad.numel()
+    for name, off in lay.items():        # nothing else may live inside the decoder range
+        if not name.startswith("decoder.") and lo <= off < hi:
+            raise AssertionError(f"{name} lies inside the decoder gradient bucket")
+    rest = [flat_grad[a:b] for a, b in ((0, lo), (hi, n)) if b > a]
+    return flat_grad[lo:hi], rest
+
+
+def allreduce_buckets_(flat_grad, buckets, group=None):
+    """All-reduce (SUM) every bucket; together they cover `flat_grad` exactly once."""
+    dec, rest = buckets
+    dist.all_reduce(dec, op=dist.ReduceOp.SUM, group=group)
+    for b in rest:
+        dist.all_reduce(b, op=dist.ReduceOp.SUM, group=group)
+    return flat_grad

@@ -110,13 +110,8 @@ class TrainEngine:
                                       self.max_norm, 1.0 / self.world, ptr(self.hyper), 1, st), "dvae_clip_adam")
 
     def _grad_buckets(self):
-        """(decoder bucket, [remaining buckets]) as views of the flat gradient buffer: decoder.* is one contiguous range."""
-        lay, named = self.model._layout, dict(self.model.named_parameters())
-        dec = [n for n in lay if n.startswith("decoder.")]
-        lo = min(lay[n] for n in dec)
-        hi = max((lay[n] + named[n].numel() + 3) // 4 * 4 for n in dec)
-        rest = [self.grad[a:b] for a, b in ((0, lo), (hi, self.n)) if b > a]
-        return self.grad[lo:hi], rest
+        from .dist import grad_buckets
+        return grad_buckets(self.model, self.grad)
 
     def _run(self):
         if self.world == 1:

@@ -78,3 +78,36 @@ def test_shard_rows_rejects_uneven_split(dvae):
     with pytest.raises(ValueError):
         d.shard_rows(7, 0, 2)
     assert d.shard_rows(8, 1, 4).tolist() == [1, 5]
+
+
+def _bucket_worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    import importlib
+    dvae = importlib.import_module("disentanglement-vae_b200")
+    dvae_dist = importlib.import_module("disentanglement-vae_b200.dist")
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    p = dict(bow_encoder=False, embedding_dim=12, hidden_dim=16, num_rnn_layers=2, encoder_dropout=0.0, decoder_dropout=0.0,
+             bidirectional_encoder=True, latent_dims={"total": 6, "polarity": 1}, adversarial_loss=False, mi_loss=False)
+    dvae.set_seed(10)
+    vae = dvae.build_vae(p, 41, None, {"polarity": 1}, torch.device("cpu"), 2, 3)      # CPU model: layout only, never run
+    n = vae._flat_numel
+    flat = torch.arange(n, dtype=torch.float32) * (rank + 1)
+    buckets = dvae_dist.grad_buckets(vae, flat)
+    dec, rest = buckets
+    assert dec.numel() + sum(b.numel() for b in rest) == n                # the buckets tile the flat buffer
+    named = dict(vae.named_parameters())
+    assert dec.numel() >= sum(q.numel() for k, q in named.items() if k.startswith("decoder."))
+    dvae_dist.allreduce_buckets_(flat, buckets)
+    if rank == 0:
+        np.save(os.path.join(out_dir, "buckets.npy"), flat.numpy())
+    dist.destroy_process_group()
+
+
+def test_bucketed_allreduce_covers_flat_gradient_exactly_once(tmp_path):
+    """The engine all-reduces the decoder bucket early (overlapping encoder backward) and the rest afterwards: summed
+    over 2 gloo ranks every element of the flat gradient must come out as (1 + 2) x its single-rank value."""
+    world = 2
+    mp.spawn(_bucket_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    got = np.load(tmp_path / "buckets.npy")
+    assert np.array_equal(got, np.arange(got.size, dtype=np.float32) * 3)
