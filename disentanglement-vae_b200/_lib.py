@@ -39,6 +39,8 @@ SIGNATURES = {
     "dvae_randn": (_i, [_p, _l, _p, _u32, _p]),
     "dvae_embedding_fwd": (_i, [_p, _i, _p, _l, _l, _i, _i, _f, _p, _u32, _l, _i, _p, _p]),
     "dvae_embedding_bwd": (_i, [_p, _i, _p, _l, _l, _i, _i, _f, _p, _u32, _l, _i, _p, _p]),
+    "dvae_bow_encoder_fwd": (_i, [_p, _i, _p, _l, _l, _i, _i, _f, _p, _u32, _p, _l, _p, _p]),
+    "dvae_bow_encoder_bwd": (_i, [_p, _l, _p, _i, _p, _l, _l, _i, _i, _f, _p, _u32, _p, _p]),
     "dvae_dropout": (_i, [_p, _l, _l, _i, _f, _p, _u32, _p, _l, _l, _p]),
     "dvae_lstm_step": (_i, [_p, _l, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _l, _p, _p, _p, _p, _p]),
     "dvae_vocab_sample_step": (_i, [_p, _l, _i, _i, _i, _p, _p, _p, _u32, _p, _l, _p, _p]),

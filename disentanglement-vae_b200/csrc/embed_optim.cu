@@ -55,6 +55,57 @@ __global__ void embedding_bwd_kernel(const float* __restrict__ d_x, int E, const
   }
 }
 
+// BOWEncoder (vae/model.py:42-49): ctx[b][e] = max_t emb[tok(b,t)][e] * keep_scale(t,b,e) over ALL T positions (padding
+// tokens included, as the reference); argmax keeps the first position attaining the maximum (torch.max).  Same Philox
+// counters as embedding_fwd_kernel, so the backward pass regenerates the mask of the winning position.
+__global__ void bow_max_fwd_kernel(const float* __restrict__ emb, int E, const int64_t* __restrict__ tokens, int64_t sb,
+                                   int64_t st_, int T, int B, float p, const uint64_t* seed_dev, uint32_t salt,
+                                   float* __restrict__ ctx, int64_t ldctx, int32_t* __restrict__ argmax) {
+  const int e4n = (E + 3) / 4;
+  const int64_t total = (int64_t)B * e4n;
+  const uint64_t seed = (p > 0.f && seed_dev) ? *seed_dev : 0;
+  const float inv_keep = p > 0.f ? 1.f / (1.f - p) : 1.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int b = (int)(i / e4n), e0 = (int)(i % e4n) * 4;
+    float best[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+    int arg[4] = {0, 0, 0, 0};
+    for (int t = 0; t < T; ++t) {
+      const int64_t tok = tokens[b * sb + t * st_];
+      float s[4] = {1.f, 1.f, 1.f, 1.f};
+      if (p > 0.f && seed_dev) dropout_scale4(seed, salt, (uint64_t)(((int64_t)t * B + b) * e4n + e0 / 4), p, inv_keep, s);
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (e0 + j < E) {
+          const float v = emb[tok * E + e0 + j] * s[j];
+          if (v > best[j]) { best[j] = v; arg[j] = t; }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (e0 + j < E) {
+        ctx[(int64_t)b * ldctx + e0 + j] = best[j];
+        argmax[(int64_t)b * E + e0 + j] = arg[j];
+      }
+  }
+}
+
+__global__ void bow_max_bwd_kernel(const float* __restrict__ d_ctx, int64_t ldd, const int32_t* __restrict__ argmax, int E,
+                                   const int64_t* __restrict__ tokens, int64_t sb, int64_t st_, int T, int B, float p,
+                                   const uint64_t* seed_dev, uint32_t salt, float* __restrict__ d_emb) {
+  const int e4n = (E + 3) / 4;
+  const int64_t total = (int64_t)B * E;
+  const uint64_t seed = (p > 0.f && seed_dev) ? *seed_dev : 0;
+  const float inv_keep = p > 0.f ? 1.f / (1.f - p) : 1.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int b = (int)(i / E), e = (int)(i % E);
+    const int t = argmax[i];
+    float s[4] = {1.f, 1.f, 1.f, 1.f};
+    if (p > 0.f && seed_dev) dropout_scale4(seed, salt, (uint64_t)(((int64_t)t * B + b) * e4n + e / 4), p, inv_keep, s);
+    const float v = d_ctx[(int64_t)b * ldd + e] * s[e & 3];
+    if (v != 0.f) atomicAdd(d_emb + tokens[b * sb + t * st_] * E + e, v);
+  }
+}
+
 __global__ void dropout_kernel(const float* __restrict__ x, int64_t ldx, int64_t rows, int width, float p,
                                const uint64_t* seed_dev, uint32_t salt, float* __restrict__ y, int64_t ldy, int64_t row0) {
   const int w4n = (width + 3) / 4;
@@ -184,6 +235,22 @@ extern "C" int dvae_embedding_bwd(const float* d_x, int E, const int64_t* tokens
                                   int B, float p, const uint64_t* seed_dev, uint32_t salt, int64_t first_token, int t0, float* d_emb, void* stream) {
   DVAE_REQUIRE(d_x && tokens && d_emb && E > 0 && T > 0 && B > 0 && p >= 0.f && p < 1.f, "dvae_embedding_bwd: bad argument");
   embedding_bwd_kernel<<<ew_grid((int64_t)T * B * ((E + 3) / 4)), 256, 0, (cudaStream_t)stream>>>(d_x, E, tokens, sb, st_, T, B, p, seed_dev, salt, first_token, t0, d_emb);
+  DVAE_LAUNCH_CHECK();
+  return DVAE_OK;
+}
+
+extern "C" int dvae_bow_encoder_fwd(const float* emb, int E, const int64_t* tokens, int64_t sb, int64_t st_, int T, int B, float p,
+                                    const uint64_t* seed_dev, uint32_t salt, float* ctx, int64_t ldctx, int32_t* argmax, void* stream) {
+  DVAE_REQUIRE(emb && tokens && ctx && argmax && E > 0 && T > 0 && B > 0 && p >= 0.f && p < 1.f, "dvae_bow_encoder_fwd: bad argument");
+  bow_max_fwd_kernel<<<ew_grid((int64_t)B * ((E + 3) / 4)), 256, 0, (cudaStream_t)stream>>>(emb, E, tokens, sb, st_, T, B, p, seed_dev, salt, ctx, ldctx, argmax);
+  DVAE_LAUNCH_CHECK();
+  return DVAE_OK;
+}
+
+extern "C" int dvae_bow_encoder_bwd(const float* d_ctx, int64_t ldd, const int32_t* argmax, int E, const int64_t* tokens, int64_t sb,
+                                    int64_t st_, int T, int B, float p, const uint64_t* seed_dev, uint32_t salt, float* d_emb, void* stream) {
+  DVAE_REQUIRE(d_ctx && argmax && tokens && d_emb && E > 0 && T > 0 && B > 0 && p >= 0.f && p < 1.f, "dvae_bow_encoder_bwd: bad argument");
+  bow_max_bwd_kernel<<<ew_grid((int64_t)B * E), 256, 0, (cudaStream_t)stream>>>(d_ctx, ldd, argmax, E, tokens, sb, st_, T, B, p, seed_dev, salt, d_emb);
   DVAE_LAUNCH_CHECK();
   return DVAE_OK;
 }

@@ -363,6 +363,9 @@ def adversary_logits(model, latent_params):
 def run_encoder(model, inputs, lengths):
     """encode() for inspection callers (vae/model.py:373-382); forward only."""
     model._require_cuda()
+    if model._dims.bow:
+        raise _lib.DvaeError("encode() is the recurrent encoder's inspection API (vae/model.py:373-382); the BOW encoder has "
+                             "no hidden states -- use forward()")
     inputs, lengths = _prep_tokens(model, inputs, lengths)
     B, T = inputs.shape
     plan = model.get_plan(B, T, False)

@@ -32,6 +32,28 @@ class _DeviceMixin:
         self.to(value)
 
 
+class BOWEncoder(_DeviceMixin, nn.Module):
+    """Bag-of-words encoder (vae/model.py:13-49): context = max over positions of dropout(embedding(inputs)).
+    Parameters only; the arithmetic is dvae_bow_encoder_fwd / _bwd."""
+
+    def __init__(self, vocab_size, emb_dim, emb_matrix=None, dropout_rate=0.5):
+        super().__init__()
+        self._device = torch.device("cpu")
+        self.vocab_size, self.emb_dim = vocab_size, emb_dim
+        if emb_matrix is not None:
+            self.embedding = nn.Embedding.from_pretrained(torch.tensor(emb_matrix, dtype=torch.float32))
+            self.embedding.weight.requires_grad = False
+            self.vocab_size, self.emb_dim = emb_matrix.shape
+        else:
+            self.embedding = nn.Embedding(self.vocab_size, self.emb_dim)
+        self.dropout = nn.Dropout(dropout_rate)
+        self.dropout_rate = dropout_rate
+        self.hidden_size, self.num_layers, self.num_directions = self.emb_dim, 1, 1      # "compatibility" (model.py:28-31)
+
+    def forward(self, *a, **k):
+        raise _lib.DvaeError("call VariationalSeq2Seq.forward(); sub-modules are parameter containers")
+
+
 class VariationalEncoder(_DeviceMixin, nn.Module):
     """embedding -> dropout -> (bi)LSTM (vae/model.py:52-109); parameters only, see module doc."""
 
@@ -380,10 +402,12 @@ def build_vae(params, vocab_size, emb_matrix, label_dims, device, sos_token_idx,
     """vae/model.py:515-559 -- same arguments, same construction order (so the same seed gives the
     same initial weights as the reference)."""
     if params["bow_encoder"] is True:
-        raise NotImplementedError("bow_encoder (vae/model.py:13-49) is outside the accelerated path (SURVEY.md 8f n4)")
-    encoder = VariationalEncoder(vocab_size, params["embedding_dim"], params["hidden_dim"], params["num_rnn_layers"],
-                                 dropout_rate=params["encoder_dropout"], emb_matrix=emb_matrix,
-                                 bidirectional=params["bidirectional_encoder"])
+        encoder = BOWEncoder(vocab_size, params["embedding_dim"], emb_matrix=emb_matrix,
+                             dropout_rate=params["encoder_dropout"])
+    else:
+        encoder = VariationalEncoder(vocab_size, params["embedding_dim"], params["hidden_dim"], params["num_rnn_layers"],
+                                     dropout_rate=params["encoder_dropout"], emb_matrix=emb_matrix,
+                                     bidirectional=params["bidirectional_encoder"])
     encoder.set_device(device)
     decoder = VariationalDecoder(vocab_size, params["embedding_dim"], params["hidden_dim"], params["num_rnn_layers"],
                                  dropout_rate=params["decoder_dropout"], emb_matrix=emb_matrix)

@@ -28,11 +28,13 @@ class Dims:
     def __init__(self, model):
         enc, dec = model.encoder, model.decoder
         self.V, self.E = enc.embedding.weight.shape
-        self.H = enc.hidden_size
+        self.H = enc.hidden_size                 # encoder hidden size (= embedding size for the BOW encoder)
+        self.Hd = dec.hidden_size                # decoder hidden size
+        self.bow = not hasattr(enc, "recurrent")
         self.D = enc.num_directions
-        self.Le = enc.num_layers
+        self.Le = 0 if not hasattr(enc, "recurrent") else enc.num_layers
         self.Ld = dec.num_layers
-        self.C = self.H * self.Le * self.D
+        self.C = self.H * enc.num_layers * self.D
         self.space_names = list(model.context2params.keys())
         self.space_dims = [model.context2params[n].out_features // 2 for n in self.space_names]
         self.S = len(self.space_names)
@@ -40,7 +42,7 @@ class Dims:
         self.dsc_out = [model.discriminators[n].output_dim if n in model.discriminators else 0
                         for n in self.space_names]
         self.OD = sum(self.dsc_out)
-        self.H2L = 2 * self.H * self.Ld
+        self.H2L = 2 * self.Hd * self.Ld
         self.sos, self.eos = model.sos_token_idx, model.eos_token_idx
         self.p_enc, self.p_dec = float(enc.dropout_rate), float(dec.dropout_rate)
         assert self.S <= _lib.MAX_SPACES, f"at most {_lib.MAX_SPACES} latent spaces"
@@ -78,11 +80,13 @@ class StepPlan:
         self.heads_ws = buf(self.lib.dvae_heads_ws_floats(B, d.S))
         T1 = max(self.T1, 1)
         self.x_dec = buf(T1, B, E)
-        self.d_gates = [buf(1, T1, B, 4 * H) for _ in range(d.Ld)]
-        self.d_cs = [buf(1, T1, B, H) for _ in range(d.Ld)]
-        self.d_hs = [buf(T1, B, H) for _ in range(d.Ld)]
-        self.d_xin = [None] + [buf(T1, B, H) for _ in range(1, d.Ld)]
-        self.state_ws = buf(self.lib.dvae_lstm_state_ws_floats(B, H, D))
+        Hd = d.Hd
+        self.d_gates = [buf(1, T1, B, 4 * Hd) for _ in range(d.Ld)]
+        self.d_cs = [buf(1, T1, B, Hd) for _ in range(d.Ld)]
+        self.d_hs = [buf(T1, B, Hd) for _ in range(d.Ld)]
+        self.d_xin = [None] + [buf(T1, B, Hd) for _ in range(1, d.Ld)]
+        self.state_ws = buf(self.lib.dvae_lstm_state_ws_floats(B, max(H, Hd), D))
+        self.bow_argmax = torch.zeros(B, E, device=device, dtype=torch.int32) if d.bow else None
         self.lse, self.nll = buf(max(self.N, 1)), buf(max(self.N, 1))
         self.argmax = torch.zeros(max(self.N, 1), device=device, dtype=torch.int32)
         self.recon = self.out[_lib.HEADS_NSCALARS:_lib.HEADS_NSCALARS + 1]
@@ -101,8 +105,8 @@ class StepPlan:
             return
         d, B, T, T1 = self.d, self.B, self.T, max(self.T1, 1)
         f32 = dict(device=self.device, dtype=torch.float32)
-        w = max(d.E, d.H * d.D)
-        self.g_top = torch.empty(T1, B, d.H, **f32)
+        w = max(d.E, d.H * d.D, d.Hd)
+        self.g_top = torch.empty(T1, B, d.Hd, **f32)
         self.g_dx = [torch.empty(max(T, T1), B, w, **f32) for _ in range(2)]
         self.g_hid = torch.empty(B, d.H2L, **f32)
         self.g_ctx = torch.empty(B, d.C, **f32)
@@ -127,6 +131,12 @@ class StepPlan:
         lib, d, st = self.lib, self.d, _lib.stream_ptr()
         B, T = self.B, self.T
         p = d.p_enc if train else 0.0
+        if d.bow:      # BOWEncoder (vae/model.py:42-49): context = max over positions of dropout(embedding)
+            check(lib.dvae_bow_encoder_fwd(ptr(P["encoder.embedding.weight"]), d.E, ptr(inputs), inputs.stride(0),
+                                           inputs.stride(1), T, B, p, ptr(self.seed_dev), SALT_ENC_EMB, ptr(self.ctx), d.C,
+                                           ptr(self.bow_argmax), st), "dvae_bow_encoder_fwd")
+            self._enc_p = p
+            return self.ctx
         check(lib.dvae_embedding_fwd(ptr(P["encoder.embedding.weight"]), d.E, ptr(inputs), inputs.stride(0),
                                      inputs.stride(1), T, B, p, ptr(self.seed_dev), SALT_ENC_EMB, -1, 0,
                                      ptr(self.x_enc), st), "dvae_embedding_fwd")
@@ -173,7 +183,7 @@ class StepPlan:
         x, I = self.x_dec, d.E
         for l in range(d.Ld):
             if l > 0:
-                I = d.H
+                I = d.Hd
                 if p > 0.0:
                     check(lib.dvae_dropout(ptr(self.d_hs[l - 1]), I, T1 * B, I, p, ptr(self.seed_dev),
                                            SALT_DEC_LAYER + l, ptr(self.d_xin[l]), I, 0, st), "dvae_dropout")
@@ -181,10 +191,10 @@ class StepPlan:
                 else:
                     x = self.d_hs[l - 1]
             w_ih, w_hh, b_ih, b_hh = self._dec_w(P, l)
-            check(lib.dvae_lstm_seq_fwd(ptr(x), I, T1, B, I, d.H, 1, ptr_array(w_ih), ptr_array(w_hh),
-                                        ptr_array(b_ih), ptr_array(b_hh), hid.data_ptr() + 4 * l * d.H,
-                                        hid.data_ptr() + 4 * (d.Ld + l) * d.H, d.H2L, 0, None, ptr(self.d_hs[l]),
-                                        d.H, None, None, 0, 0, ptr(self.d_gates[l]), ptr(self.d_cs[l]),
+            check(lib.dvae_lstm_seq_fwd(ptr(x), I, T1, B, I, d.Hd, 1, ptr_array(w_ih), ptr_array(w_hh),
+                                        ptr_array(b_ih), ptr_array(b_hh), hid.data_ptr() + 4 * l * d.Hd,
+                                        hid.data_ptr() + 4 * (d.Ld + l) * d.Hd, d.H2L, 0, None, ptr(self.d_hs[l]),
+                                        d.Hd, None, None, 0, 0, ptr(self.d_gates[l]), ptr(self.d_cs[l]),
                                         ptr(self.state_ws), st), "dvae_lstm_seq_fwd(dec)")
         self._dec_p = p
         self._dec_tokens, self._dec_first = tokens, first_token
@@ -212,7 +222,7 @@ class StepPlan:
             x, I = self.x_dec, d.E
             for l in range(d.Ld):
                 if l > 0:
-                    I = d.H
+                    I = d.Hd
                     if p > 0.0:
                         check(lib.dvae_dropout(ptr(self.d_hs[l - 1]), I, B, I, p, ptr(self.seed_dev),
                                                SALT_DEC_LAYER + l, ptr(self.d_xin[l]), I, s * B, st), "dvae_dropout(step)")
@@ -220,14 +230,14 @@ class StepPlan:
                     else:
                         x = self.d_hs[l - 1]
                 w_ih, w_hh, b_ih, b_hh = W[l]
-                check(lib.dvae_lstm_step(ptr(x), I, s, T1, B, I, d.H, ptr(w_ih[0]), ptr(w_hh[0]), ptr(b_ih[0]),
-                                         ptr(b_hh[0]), hid.data_ptr() + 4 * l * d.H,
-                                         hid.data_ptr() + 4 * (d.Ld + l) * d.H, d.H2L, ptr(self.d_hs[l]),
+                check(lib.dvae_lstm_step(ptr(x), I, s, T1, B, I, d.Hd, ptr(w_ih[0]), ptr(w_hh[0]), ptr(b_ih[0]),
+                                         ptr(b_hh[0]), hid.data_ptr() + 4 * l * d.Hd,
+                                         hid.data_ptr() + 4 * (d.Ld + l) * d.Hd, d.H2L, ptr(self.d_hs[l]),
                                          ptr(self.d_gates[l]), ptr(self.d_cs[l]), ptr(self.state_ws), st),
                       "dvae_lstm_step")
             if not coins[s]:
-                h_s = self.d_hs[-1].data_ptr() + 4 * s * B * d.H
-                check(lib.dvae_vocab_sample_step(h_s, d.H, B, d.H, d.V, ptr(P["decoder.linear.weight"]),
+                h_s = self.d_hs[-1].data_ptr() + 4 * s * B * d.Hd
+                check(lib.dvae_vocab_sample_step(h_s, d.Hd, B, d.Hd, d.V, ptr(P["decoder.linear.weight"]),
                                                  ptr(P["decoder.linear.bias"]), ptr(self.seed_dev), SALT_SAMPLE + s,
                                                  preds.data_ptr() + 8 * (s + 1) * preds.stride(1), preds.stride(0),
                                                  ptr(self.sample_ws), st), "dvae_vocab_sample_step")
@@ -239,7 +249,7 @@ class StepPlan:
     def vocab_ce(self, P, h_top, targets, lengths):
         """a7 fused with the vocabulary projection of a6."""
         lib, d, st = self.lib, self.d, _lib.stream_ptr()
-        check(lib.dvae_vocab_ce_fwd(ptr(h_top), d.H, self.T1, self.B, d.H, d.V, ptr(P["decoder.linear.weight"]),
+        check(lib.dvae_vocab_ce_fwd(ptr(h_top), d.Hd, self.T1, self.B, d.Hd, d.V, ptr(P["decoder.linear.weight"]),
                                     ptr(P["decoder.linear.bias"]), ptr(targets), targets.stride(0), ptr(lengths),
                                     d.sos, ptr(self.lse), ptr(self.nll), ptr(self.argmax), ptr(self.recon),
                                     ptr(self.ce_ws), st), "dvae_vocab_ce_fwd")
@@ -251,9 +261,9 @@ class StepPlan:
     def vocab_ce_bwd(self, P, G, h_top, targets, lengths, grad_scale_dev):
         self._alloc_bwd()
         lib, d, st = self.lib, self.d, _lib.stream_ptr()
-        check(lib.dvae_vocab_ce_bwd(ptr(h_top), d.H, self.T1, self.B, d.H, d.V, ptr(P["decoder.linear.weight"]),
+        check(lib.dvae_vocab_ce_bwd(ptr(h_top), d.Hd, self.T1, self.B, d.Hd, d.V, ptr(P["decoder.linear.weight"]),
                                     ptr(P["decoder.linear.bias"]), ptr(targets), targets.stride(0), ptr(lengths),
-                                    ptr(self.lse), ptr(grad_scale_dev), ptr(self.g_top), d.H,
+                                    ptr(self.lse), ptr(grad_scale_dev), ptr(self.g_top), d.Hd,
                                     ptr(G["decoder.linear.weight"]), ptr(G["decoder.linear.bias"]),
                                     ptr(self.ce_bwd_ws), st), "dvae_vocab_ce_bwd")
         return self.g_top
@@ -266,19 +276,19 @@ class StepPlan:
         hid = self._dec_hid
         g_in, p = g_top, self._dec_p
         for l in range(d.Ld - 1, -1, -1):
-            I = d.E if l == 0 else d.H
+            I = d.E if l == 0 else d.Hd
             x = self.x_dec if l == 0 else (self.d_xin[l] if p > 0.0 else self.d_hs[l - 1])
             g_out = self.g_dx[l % 2]
             w_ih, w_hh, _, _ = self._dec_w(P, l)
             gw_ih, gw_hh, gb_ih, gb_hh = self._dec_w(G, l)
             need_dx = l > 0 or emb_grad
-            check(lib.dvae_lstm_seq_bwd(ptr(x), I, T1, B, I, d.H, 1, ptr_array(w_ih), ptr_array(w_hh),
-                                        hid.data_ptr() + 4 * l * d.H, hid.data_ptr() + 4 * (d.Ld + l) * d.H,
-                                        d.H2L, 0, None, ptr(self.d_hs[l]), d.H, ptr(self.d_gates[l]),
-                                        ptr(self.d_cs[l]), ptr(g_in), d.H, None, None, 0, 0,
+            check(lib.dvae_lstm_seq_bwd(ptr(x), I, T1, B, I, d.Hd, 1, ptr_array(w_ih), ptr_array(w_hh),
+                                        hid.data_ptr() + 4 * l * d.Hd, hid.data_ptr() + 4 * (d.Ld + l) * d.Hd,
+                                        d.H2L, 0, None, ptr(self.d_hs[l]), d.Hd, ptr(self.d_gates[l]),
+                                        ptr(self.d_cs[l]), ptr(g_in), d.Hd, None, None, 0, 0,
                                         ptr(g_out) if need_dx else None, I, ptr_array(gw_ih), ptr_array(gw_hh),
-                                        ptr_array(gb_ih), ptr_array(gb_hh), self.g_hid.data_ptr() + 4 * l * d.H,
-                                        self.g_hid.data_ptr() + 4 * (d.Ld + l) * d.H, d.H2L, 0,
+                                        ptr_array(gb_ih), ptr_array(gb_hh), self.g_hid.data_ptr() + 4 * l * d.Hd,
+                                        self.g_hid.data_ptr() + 4 * (d.Ld + l) * d.Hd, d.H2L, 0,
                                         ptr(self.state_ws), st), "dvae_lstm_seq_bwd(dec)")
             if l > 0 and p > 0.0:
                 check(lib.dvae_dropout(ptr(g_out), I, T1 * B, I, p, ptr(self.seed_dev), SALT_DEC_LAYER + l,
@@ -309,6 +319,12 @@ class StepPlan:
         lib, d, st = self.lib, self.d, _lib.stream_ptr()
         B, T = self.B, self.T
         p = self._enc_p
+        if d.bow:
+            if emb_grad:
+                check(lib.dvae_bow_encoder_bwd(ptr(g_ctx), d.C, ptr(self.bow_argmax), d.E, ptr(inputs), inputs.stride(0),
+                                               inputs.stride(1), T, B, p, ptr(self.seed_dev), SALT_ENC_EMB,
+                                               ptr(G["encoder.embedding.weight"]), st), "dvae_bow_encoder_bwd")
+            return
         g_in = None
         for l in range(d.Le - 1, -1, -1):
             I = d.E if l == 0 else d.D * d.H

@@ -129,6 +129,15 @@ int dvae_embedding_fwd(const float* emb, int E, const int64_t* tokens, int64_t t
 int dvae_embedding_bwd(const float* d_x, int E, const int64_t* tokens, int64_t tok_stride_b,
                        int64_t tok_stride_t, int T, int B, float p, const uint64_t* seed_dev,
                        uint32_t salt, int64_t first_token, int t0, float* d_emb, void* stream);
+/* Bag-of-words encoder (BOWEncoder.forward, vae/model.py:42-49): ctx[b, e] = max over all T positions of
+ * emb[tokens[b, t], e] * dropout keep-scale; argmax [B, E] int32 records the winning position (first on ties) for the
+ * backward pass, which scatter-adds d_ctx (masked like the forward) into d_emb. */
+int dvae_bow_encoder_fwd(const float* emb, int E, const int64_t* tokens, int64_t tok_stride_b, int64_t tok_stride_t,
+                         int T, int B, float p, const uint64_t* seed_dev, uint32_t salt, float* ctx, int64_t ldctx,
+                         int32_t* argmax, void* stream);
+int dvae_bow_encoder_bwd(const float* d_ctx, int64_t ldd, const int32_t* argmax, int E, const int64_t* tokens,
+                         int64_t tok_stride_b, int64_t tok_stride_t, int T, int B, float p, const uint64_t* seed_dev,
+                         uint32_t salt, float* d_emb, void* stream);
 int dvae_dropout(const float* x, int64_t ldx, int64_t rows, int width, float p,
                  const uint64_t* seed_dev, uint32_t salt, float* y, int64_t ldy, int64_t row0,
                  void* stream);

@@ -108,10 +108,13 @@ def run_case(name, params, V, label_dims, B, T, kl_weights, seed=10, eps_seed=12
         out[f"dsc_logits.{n}"] = l.detach().numpy()
     out["decoder_logits"] = output["decoder_logits"].detach().numpy()
     out["token_predictions"] = output["token_predictions"].numpy()
-    _, ctx, (hn, cn) = vae.encode(X, lengths)
-    out["context"] = ctx.detach().numpy()
-    out["enc_hn"] = hn.detach().numpy()
-    out["enc_cn"] = cn.detach().numpy()
+    if params["bow_encoder"] is True:
+        out["context"] = vae.encoder(X).detach().numpy()
+    else:
+        _, ctx, (hn, cn) = vae.encode(X, lengths)
+        out["context"] = ctx.detach().numpy()
+        out["enc_hn"] = hn.detach().numpy()
+        out["enc_cn"] = cn.detach().numpy()
     z = torch.cat([output["latent_params"][n].z for n in space_names], dim=1)
     h0, c0 = vae.compute_hidden(z, B)
     out["dec_h0"] = h0.detach().numpy()
@@ -261,6 +264,11 @@ def cyclic_table():
 
 if __name__ == "__main__":
     torch.set_num_threads(1)
+    if "--bow" in sys.argv:             # only the BOWEncoder case (vae/model.py:13-49)
+        run_case("tiny_bow", make_params(bow_encoder=True, embedding_dim=10, hidden_dim=8,
+                                         latent_dims={"total": 5, "polarity": 1}),
+                 V=27, label_dims={"polarity": 1}, B=5, T=7, kl_weights={"default": 0.1, "polarity": 0.005})
+        sys.exit(0)
     if "--adv-mi" in sys.argv:          # only the adversarial + MI case (leaves the other files untouched)
         run_adv_mi_case("tiny_adv_mi", make_params(bidirectional_encoder=True, embedding_dim=10, hidden_dim=8,
                                                     latent_dims={"total": 9, "polarity": 1, "uncertainty": 2},

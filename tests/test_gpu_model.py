@@ -209,6 +209,50 @@ def test_train_step_alternative_kernel_paths_match_oracle(dvae, env, monkeypatch
         assert _rel(prm.grad, grads[k]) < 1e-3, k
 
 
+def test_bow_encoder_train_step_matches_reference_golden_and_oracle(dvae):
+    """bow_encoder=true (vae/model.py:13-49): golden vectors of the reference, then a larger batch with encoder dropout
+    (mask replayed on the host from the kernels' Philox stream) and an embedding width that is not a multiple of 4."""
+    from oracle import philox
+    g = load_golden("tiny_bow")
+    sd = golden_state_dict(g)
+    names = [str(s) for s in g["space_names"]]
+    p = _params(bow_encoder=True, embedding_dim=sd["encoder.embedding.weight"].shape[1],
+                hidden_dim=sd["decoder.recurrent.weight_hh_l0"].shape[1], latent_dims={"total": 5, "polarity": 1})
+    vae = dvae.build_vae(p, int(g["V"]), None, {"polarity": 1}, torch.device("cuda"), 2, 3)
+    vae.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+    vae.train()
+    X, lengths = torch.from_numpy(g["inputs"]).cuda(), torch.from_numpy(g["lengths"]).cuda()
+    eps = torch.from_numpy(np.concatenate([g[f"eps.{n}"] for n in names], axis=1)).cuda()
+    klw = {n: float(g[f"klw.{n}"]) for n in names}
+    klw["default"] = klw["content"]
+    out = vae(X, lengths, teacher_forcing_prob=1.0, eps=eps)
+    assert _rel(out["context"], g["context"]) < 1e-6
+    total, _ = dvae.losses.compute_all_losses(vae, out, X, {"polarity": torch.from_numpy(g["Y.polarity"])}, lengths, klw)
+    total.backward()
+    assert abs(total.item() - float(g["loss.total"])) <= 1e-5 * abs(float(g["loss.total"]))
+    for k, prm in vae.named_parameters():
+        assert _rel(prm.grad, g[f"grad.{k}"]) < 1e-3, k
+    # larger, dropout 0.5, E = 30
+    dvae.set_seed(4)
+    E, H, V, B, T = 30, 32, 300, 37, 9
+    p = _params(bow_encoder=True, embedding_dim=E, hidden_dim=H, encoder_dropout=0.5, latent_dims={"total": 8, "polarity": 1})
+    vae = dvae.build_vae(p, V, None, {"polarity": 1}, torch.device("cuda"), 2, 3)
+    vae.train()
+    gen = torch.Generator().manual_seed(9)
+    X, lengths, Y = _synthetic(B, T, V, gen, ("polarity",))
+    eps = torch.randn(B, 8, generator=gen)
+    klw = {"default": 0.3, "polarity": 0.005}
+    out = vae(X.cuda(), lengths.cuda(), teacher_forcing_prob=1.0, eps=eps.cuda())
+    total, _ = dvae.losses.compute_all_losses(vae, out, X.cuda(), Y, lengths.cuda(), klw)
+    total.backward()
+    plan = vae._plans[(B, T)][0]
+    mask = philox.dropout_mask(int(plan.seed_dev.item()), 1, T * B, E, 0.5).astype(np.float64).reshape(T, B, E)
+    fw, grads = _oracle_run(vae, X, lengths, Y, eps, klw, enc_masks=[mask])
+    assert abs(total.item() - fw["total_loss"]) <= 1e-5 * abs(fw["total_loss"])
+    for k, prm in vae.named_parameters():
+        assert _rel(prm.grad, grads[k]) < 1e-3, k
+
+
 def test_dropout_train_step_matches_oracle_with_replayed_masks(dvae):
     """encoder/decoder dropout 0.5 (the reproduction configs' value): the Philox masks the kernels
     used are re-generated through the same C-ABI call and handed to the oracle."""

@@ -115,8 +115,10 @@ def test_cpu_model_refuses_to_run(dvae):
     vae = dvae.build_vae(_params(), 30, None, {"polarity": 1}, torch.device("cpu"), 2, 3)
     with pytest.raises(dvae.DvaeError, match="no CPU fallback"):
         vae(torch.zeros(2, 5, dtype=torch.long), torch.tensor([5, 3]))
-    with pytest.raises(NotImplementedError):
-        dvae.build_vae(_params(bow_encoder=True), 30, None, {"polarity": 1}, torch.device("cpu"), 2, 3)
+    bow = dvae.build_vae(_params(bow_encoder=True), 30, None, {"polarity": 1}, torch.device("cpu"), 2, 3)
+    assert [k for k in bow.state_dict() if k.startswith("encoder.")] == ["encoder.embedding.weight"]      # vae/model.py:13-49
+    assert (bow.encoder.hidden_size, bow.encoder.num_layers, bow.encoder.num_directions) == (bow.encoder.emb_dim, 1, 1)
+    assert bow.context2params["content"].in_features == bow.encoder.emb_dim
 
 
 @pytest.mark.skipif(not ref_shim.reference_available(), reason="reference checkout not present (GPU box)")

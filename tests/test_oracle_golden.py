@@ -128,3 +128,20 @@ def test_oracle_auxiliary_objectives_match_reference_golden():
         assert abs(O.club_nll(mu, lv, y)[0] - float(g[f"mi_learning_loss.{n}"])) < 1e-5, n
     assert abs(total - float(g["loss.total_mi"])) < 1e-7
     assert abs(sum(float(g[f"adv_loss.{n}"]) for n in g["adv_names"]) - float(g["loss.total_adv"])) < 1e-5
+
+
+def test_oracle_bow_encoder_matches_reference_golden():
+    """BOWEncoder (vae/model.py:13-49) restated in the oracle: loss, context and every gradient of the reference."""
+    g = load_golden("tiny_bow")
+    sd = O.cast_state_dict(golden_state_dict(g))
+    spec = O.ModelSpec(sd, [str(s) for s in g["space_names"]], int(g["sos"]), int(g["eos"]))
+    assert spec.bow and spec.C == spec.E
+    fw = O.model_forward(sd, spec, g["inputs"], g["lengths"], {n: g[f"eps.{n}"] for n in spec.space_names},
+                         labels={str(n): g[f"Y.{n}"] for n in g["label_names"]},
+                         kl_weights={n: float(g[f"klw.{n}"]) for n in spec.space_names})
+    assert np.abs(fw["context"] - g["context"]).max() < 1e-7
+    assert abs(fw["total_loss"] - float(g["loss.total"])) < 1e-5 * abs(float(g["loss.total"]))
+    grads = O.model_backward(sd, spec, fw)
+    for k in sd:
+        if f"grad.{k}" in g:
+            assert np.abs(grads[k] - g[f"grad.{k}"]).max() <= 2e-4 * max(np.abs(g[f"grad.{k}"]).max(), 1e-8), k
