@@ -16,7 +16,8 @@ int linear_impl(const float* A, int64_t lda, int trans_a, const float* B, int64_
 int colsum_impl(const float* X, int64_t ldx, int M, int N, float* out, float beta, cudaStream_t st);
 
 constexpr int kRows = 2;
-constexpr int kHeadsThreads = 256;
+constexpr int kHeadsThreads = 1024;   // 32 warps: all 128 (mu, raw) columns in one pass, one z2hidden column per thread -- every CTA streams
+                                      // the full weight matrices from L2, so the number of loads in flight per CTA is what sets its time
 constexpr int kMaxDscOut = 64;
 
 struct HeadsMeta {
