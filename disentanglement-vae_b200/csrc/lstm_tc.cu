@@ -73,6 +73,11 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16
       : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// Programmatic dependent launch: the kernel is launched while its stream predecessor (typically the hoisted input
+// projection GEMM) is still running; everything up to pdl_wait() -- barrier init, TMEM allocation, the split of the
+// resident weights into tensor memory -- overlaps the predecessor's tail, and nothing the predecessor wrote is read
+// before it.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 // kind::f16, A = B = fp16, D = fp32, both operands K-major
 __host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
   return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
@@ -195,8 +200,6 @@ __global__ void __cluster_dims__(kCS, 1, 1) __launch_bounds__(kGT * G, 1) lstm_t
   // roles.  phase 1 (accumulator read-out): gate q of unit u0 + lane, rows 4*cgp .. 4*cgp + 3 (TMEM lane quadrant q).
   //         phase 2 (cell update): row `warp`, unit u0 + lane -- c / h live in registers across all steps.
   const int q = warp & 3, cgp = warp >> 2, prow = warp, pb = b0 + prow;
-  float c_reg = (p.c0 && pb < B) ? p.c0[d * p.dir0 + (int64_t)pb * p.ld0 + u0 + lane] : 0.f;
-  float h_reg = (p.h0 && pb < B) ? p.h0[d * p.dir0 + (int64_t)pb * p.ld0 + u0 + lane] : 0.f;
   const int plen = pb < B ? (p.lengths ? (int)p.lengths[pb] : T) : 0;
   fence_proxy_async();
   tc_fence_before();
@@ -232,6 +235,7 @@ __global__ void __cluster_dims__(kCS, 1, 1) __launch_bounds__(kGT * G, 1) lstm_t
   const uint32_t slice_off = (uint32_t)(4 * rank) * kB_LBO;
   constexpr uint32_t kIdesc = make_idesc_f16(128, kNB);
 
+  float c_reg = 0.f, h_reg = 0.f;
   // Write this warp's row of the new state (fp16 hi / lo, operand layout) into the CTA's own operand buffer `buf`;
   // once the group's 16 rows are in, push the CTA's slice to the 7 peers (bulk copies completing on THEIR mbarrier).
   auto publish = [&](int buf) {
@@ -252,6 +256,9 @@ __global__ void __cluster_dims__(kCS, 1, 1) __launch_bounds__(kGT * G, 1) lstm_t
     }
   };
   TC_MARK(1);
+  pdl_wait();               // from here on the predecessor's outputs (gates, h0 / c0) are read
+  c_reg = (p.c0 && pb < B) ? p.c0[d * p.dir0 + (int64_t)pb * p.ld0 + u0 + lane] : 0.f;
+  h_reg = (p.h0 && pb < B) ? p.h0[d * p.dir0 + (int64_t)pb * p.ld0 + u0 + lane] : 0.f;
   publish(0);               // initial state = "output of step -1"
 
   const int gcol = q * kH + u0 + lane;
@@ -389,8 +396,6 @@ __global__ void __cluster_dims__(kCS, 1, 1) __launch_bounds__(kGT * G, 1) lstm_t
   //         cell backward: row `warp`, unit u0 + lane -- carried dh / dc live in registers.
   const int q = warp & 3, cgp = warp >> 2, prow = warp, pb = b0 + prow;
   const int plen = pb < B ? (p.lengths ? (int)p.lengths[pb] : T) : 0;
-  float carry = (p.d_hn && pb < B) ? p.d_hn[d * p.dirn + (int64_t)pb * p.ldn + u0 + lane] : 0.f;
-  float dc = (p.d_cn && pb < B) ? p.d_cn[d * p.dirn + (int64_t)pb * p.ldn + u0 + lane] : 0.f;
   tc_fence_before();
   __syncthreads();
   cluster.sync();
@@ -425,6 +430,9 @@ __global__ void __cluster_dims__(kCS, 1, 1) __launch_bounds__(kGT * G, 1) lstm_t
   constexpr uint32_t kIdesc = make_idesc_f16(128, kNB);
   const int nsteps = T + ((p.d_h0 || p.d_c0) ? 1 : 0);
   unsigned amax_run = 0;           // bit pattern of max |dG| over this warp's row, all steps
+  pdl_wait();                      // from here on the predecessor's outputs (d_hs, d_hn / d_cn) are read
+  float carry = (p.d_hn && pb < B) ? p.d_hn[d * p.dirn + (int64_t)pb * p.ldn + u0 + lane] : 0.f;
+  float dc = (p.d_cn && pb < B) ? p.d_cn[d * p.dirn + (int64_t)pb * p.ldn + u0 + lane] : 0.f;
 
   for (int s = 0; s < nsteps; ++s) {
     const bool final_ = (s == T);
@@ -562,6 +570,20 @@ bool tc_lstm_supported(int H) {
   return H == kH && !(e && !strcmp(e, "simt"));
 }
 
+// launch with programmatic stream serialization (DVAE_PDL=0: plain launch)
+template <class Args>
+static cudaError_t launch_pdl(void (*kernel)(Args), int grid, int block, size_t smem, cudaStream_t st, const Args& args) {
+  const char* e = getenv("DVAE_PDL");
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = (e && e[0] == '0') ? 0 : 1;
+  return cudaLaunchKernelEx(&cfg, kernel, args);
+}
+
 template <int G>
 static int launch_tc_fwd(const PersistFwdArgs& a, cudaStream_t st) {
   static bool ready = false;
@@ -572,7 +594,7 @@ static int launch_tc_fwd(const PersistFwdArgs& a, cudaStream_t st) {
   PersistFwdArgs b = a;
   b.n_slices = ceil_div(a.B, kNB * G);
   b.d_off = 0;
-  lstm_tc_fwd_kernel<G><<<kCS * b.n_slices * a.D, kGT * G, fwd_smem_bytes(G), st>>>(b);
+  DVAE_CUDA(launch_pdl(lstm_tc_fwd_kernel<G>, kCS * b.n_slices * a.D, kGT * G, fwd_smem_bytes(G), st, b));
   DVAE_LAUNCH_CHECK();
   return DVAE_OK;
 }
@@ -596,7 +618,7 @@ static int launch_tc_bwd(const PersistBwdArgs& a, cudaStream_t st) {
   PersistBwdArgs b = a;
   b.n_slices = ceil_div(a.B, kNB * G);
   b.d_off = 0;
-  lstm_tc_bwd_kernel<G><<<kCS * b.n_slices * a.D, kGT * G, bwd_smem_bytes(G), st>>>(b);
+  DVAE_CUDA(launch_pdl(lstm_tc_bwd_kernel<G>, kCS * b.n_slices * a.D, kGT * G, bwd_smem_bytes(G), st, b));
   DVAE_LAUNCH_CHECK();
   return DVAE_OK;
 }

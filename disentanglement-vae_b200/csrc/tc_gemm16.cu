@@ -138,6 +138,9 @@ tc16_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   float* epi_scratch = reinterpret_cast<float*>(smem + OFF_SCRATCH);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // a programmatically-launched successor (the persistent LSTM kernels) may start its prologue now; it still waits for
+  // this grid to complete (griddepcontrol.wait) before it reads anything written here
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   if (tid == 0) DBG16(0);
   const int m0 = blockIdx.x * BM;
   const int nt0 = blockIdx.y * p.tiles_per_cta;
