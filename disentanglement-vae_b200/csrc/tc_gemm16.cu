@@ -21,6 +21,7 @@
 // log-softmax / arg-max / Gumbel-max sampling), 2 softmax-gradient chunk.
 #include <cuda_fp16.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include "tc_gemm.cuh"
 #include "tc_gemm16.cuh"
@@ -42,8 +43,25 @@ constexpr int EPI_WARPS = 8, MMA_WARP = 4, TMA_WARP = 5, PROD_WARP0 = 6, PROD_WA
 // warps 0-3: epilogue of tile columns 0-63; warps 22-25 (22 % 4 == 2: TMEM lane quarter = warp & 3): columns 64-127
 constexpr int NUM_THREADS = (EPI2_WARP0 + 4) * 32;               // 832: <= 78 registers per thread
 constexpr int EPI_SCRATCH_BYTES = 8 * 32 * 33 * 4;
-constexpr int OFF_RAW = STAGES * STAGE_BYTES, OFF_BAR = OFF_RAW + RAW_STAGES * RAW_BYTES, OFF_SCRATCH = OFF_BAR + 256;
-constexpr int SMEM_BYTES = OFF_SCRATCH + EPI_SCRATCH_BYTES + 1024;
+// [operand rings][epilogue transpose scratch][bias tiles][barriers]: the scratch directly follows the operand region so
+// that the A-stationary ring can grow into it when the epilogue does not use it (mode 1)
+constexpr int OFF_RAW = STAGES * STAGE_BYTES, OFF_OPER_END = OFF_RAW + RAW_STAGES * RAW_BYTES, OFF_SCRATCH = OFF_OPER_END;
+// Pre-split mode (operands already split into fp16 planes in global memory, blocked by core matrix): no landing ring and
+// no converters -- TMA delivers UMMA-ready dense tiles (core matrices 128 B apart) straight into a 5-stage operand ring.
+constexpr int PS_PLANE = BM * BK * 2, PS_STAGE_BYTES = 4 * PS_PLANE, PS_STAGES = 5, MAX_STAGES = 5;
+constexpr int PS_LBO = 128, PS_SBO = 512;
+// A-stationary variant (K <= 256, no split-K): the CTA's A rows (both planes, all k-blocks: 128 KB) are loaded once and
+// stay in shared memory for the CTA's whole run of N tiles; only B tiles stream through a 3-stage ring.  With 128 x 128
+// tiles and K = 256 the operand loads (256 KB per tile) otherwise make the kernel L2-bandwidth bound.
+constexpr int AS_MAX_KB = 8, AS_A_BYTES = AS_MAX_KB * 2 * PS_PLANE, AS_STAGE_BYTES = 2 * PS_PLANE;
+constexpr int AS_STAGES = 3, AS_STAGES_NOSCRATCH = 5;      // mode 1 has no transpose scratch: the ring grows into it
+static_assert(AS_A_BYTES + AS_STAGES * AS_STAGE_BYTES <= OFF_OPER_END, "A-stationary layout must fit in the operand region");
+static_assert(AS_STAGES_NOSCRATCH <= MAX_STAGES, "barrier arrays");
+static_assert(PS_STAGES * PS_STAGE_BYTES <= OFF_OPER_END, "pre-split ring must fit in the plane + landing rings");
+constexpr int OFF_BIAS = OFF_SCRATCH + EPI_SCRATCH_BYTES;          // per epilogue warp: the 64 bias values of its tile columns
+constexpr int OFF_BAR = OFF_BIAS + 8 * 64 * 4;
+constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
+static_assert(AS_A_BYTES + AS_STAGES_NOSCRATCH * AS_STAGE_BYTES <= OFF_BIAS, "A-stationary mode-1 ring must end before the bias tiles");
 constexpr int TMEM_COLS = 512;
 constexpr float kLoScale = 2048.f, kLoInv = 1.f / 2048.f;
 
@@ -123,18 +141,47 @@ __device__ __forceinline__ void store_tile(uint32_t plane_hi, int mn_major, int 
   }
 }
 
+__device__ __forceinline__ void tma_load_3d(uint32_t smem_dst, const CUtensorMap* m, int c0, int c1, int c2, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(smem_dst),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+
+// X [R, K] fp32 (row stride ld) -> fp16 planes hi / lo, each blocked by UMMA core matrix:
+//   plane[((r / 8) * KC + k / 8) * 64 + (r % 8) * 8 + k % 8],  KC = ceil(K / 8); rows / columns beyond R / K are zero.
+__global__ void split_planes_kernel(const float* __restrict__ X, int64_t ld, int R, int K, float scale, __half* __restrict__ hi,
+                                    __half* __restrict__ lo) {
+  const int KC = (K + 7) / 8, RP = (R + 7) / 8 * 8;
+  const int64_t total = (int64_t)RP * KC;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int kc = (int)(i % KC), r = (int)(i / KC);            // consecutive threads: consecutive 32-byte pieces of a row
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = (r < R && kc * 8 + e < K) ? __ldg(X + (int64_t)r * ld + kc * 8 + e) : 0.f;
+    uint4 h, l;
+    h.x = pack_hi_lo(v[0], v[1], scale, l.x); h.y = pack_hi_lo(v[2], v[3], scale, l.y);
+    h.z = pack_hi_lo(v[4], v[5], scale, l.z); h.w = pack_hi_lo(v[6], v[7], scale, l.w);
+    const int64_t off = (((int64_t)(r >> 3) * KC + kc) * 64 + (r & 7) * 8);
+    *reinterpret_cast<uint4*>(hi + off) = h;
+    *reinterpret_cast<uint4*>(lo + off) = l;
+  }
+}
+
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-tc16_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, Params p) {
+tc16_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2, Params p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
-  uint64_t* full = bars;                       // [STAGES] converters -> MMA   (8 warp arrivals)
-  uint64_t* empty = bars + STAGES;             // [STAGES] MMA -> converters   (tcgen05.commit)
-  uint64_t* raw_full = bars + 2 * STAGES;      // [RAW_STAGES] TMA -> converters (transaction bytes)
+  uint64_t* full = bars;                       // [MAX_STAGES] converters (or TMA, pre-split mode) -> MMA
+  uint64_t* empty = bars + MAX_STAGES;         // [MAX_STAGES] MMA -> converters / TMA   (tcgen05.commit)
+  uint64_t* raw_full = bars + 2 * MAX_STAGES;  // [RAW_STAGES] TMA -> converters (transaction bytes)
   uint64_t* raw_empty = raw_full + RAW_STAGES; // [RAW_STAGES] converters -> TMA (8 warp arrivals)
   uint64_t* tmem_full = raw_empty + RAW_STAGES;  // [2] MMA -> epilogue
   uint64_t* tmem_empty = tmem_full + 2;          // [2] epilogue -> MMA (4 warp arrivals)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* a_full = tmem_empty + 2;             // [1] A-stationary mode: all A k-blocks landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_full + 1);
   float* epi_scratch = reinterpret_cast<float*>(smem + OFF_SCRATCH);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -151,8 +198,8 @@ tc16_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int nkb = max(0, min(nkb_total, kb0 + p.kb_per_split) - kb0);
 
   if (tid == 0) {
-    for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full[s], PROD_WARPS);
+    for (int s = 0; s < MAX_STAGES; ++s) {
+      mbar_init(&full[s], p.presplit ? 1 : PROD_WARPS);
       mbar_init(&empty[s], 1);
     }
     for (int s = 0; s < RAW_STAGES; ++s) {
@@ -163,12 +210,21 @@ tc16_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_init(&tmem_full[a], 1);
       mbar_init(&tmem_empty[a], EPI_WARPS);
     }
+    mbar_init(a_full, 1);
     fence_barrier_init();
   }
   if (warp == TMA_WARP && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if (p.presplit) {
+      tma_prefetch_desc(&tmA2);
+      tma_prefetch_desc(&tmB2);
+    }
   }
+  const bool a_stat = p.presplit && nkb_total <= AS_MAX_KB && gridDim.z == 1;
+  const int nstages = a_stat ? (p.mode == 1 ? AS_STAGES_NOSCRATCH : AS_STAGES) : (p.presplit ? PS_STAGES : STAGES);
+  const uint32_t stage_bytes = a_stat ? AS_STAGE_BYTES : (p.presplit ? PS_STAGE_BYTES : STAGE_BYTES);
+  const uint32_t plane_bytes = p.presplit ? PS_PLANE : PLANE;
   if (warp == MMA_WARP) tmem_alloc(tmem_slot, TMEM_COLS);
   tc_fence_before();
   __syncthreads();
@@ -178,7 +234,42 @@ tc16_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   if (warp == TMA_WARP) {
     // ===== TMA producer: raw fp32 k-blocks into the landing ring =====
-    if (lane == 0) {
+    if (lane == 0 && a_stat) {
+      // A rows once (all k-blocks, both planes), then only B tiles through the ring
+      mbar_expect_tx(a_full, (uint32_t)nkb * 2 * PS_PLANE);
+      for (int kb = 0; kb < nkb; ++kb) {
+        tma_load_3d(smem_u + kb * 2 * PS_PLANE, &tmA, 0, kb * (BK / 8), m0 / 8, a_full);
+        tma_load_3d(smem_u + kb * 2 * PS_PLANE + PS_PLANE, &tmA2, 0, kb * (BK / 8), m0 / 8, a_full);
+      }
+      int stage = 0, phase = 0;
+      for (int nt = nt0; nt < nt1; ++nt) {
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          const uint32_t dst = smem_u + AS_A_BYTES + stage * AS_STAGE_BYTES;
+          mbar_expect_tx(&full[stage], AS_STAGE_BYTES);
+          const int rb = (nt * BN + p.b_row0) / 8;
+          tma_load_3d(dst, &tmB, 0, kb * (BK / 8), rb, &full[stage]);
+          tma_load_3d(dst + PS_PLANE, &tmB2, 0, kb * (BK / 8), rb, &full[stage]);
+          if (++stage == nstages) { stage = 0; phase ^= 1; }
+        }
+      }
+    } else if (lane == 0 && p.presplit) {
+      // operand planes straight into the operand ring: 4 x 8 KB dense tiles per k-block
+      int stage = 0, phase = 0;
+      for (int nt = nt0; nt < nt1; ++nt) {
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          const uint32_t dst = smem_u + stage * PS_STAGE_BYTES;
+          mbar_expect_tx(&full[stage], PS_STAGE_BYTES);
+          const int kc0 = (kb0 + kb) * (BK / 8), ra = m0 / 8, rb = (nt * BN + p.b_row0) / 8;
+          tma_load_3d(dst, &tmA, 0, kc0, ra, &full[stage]);
+          tma_load_3d(dst + PS_PLANE, &tmA2, 0, kc0, ra, &full[stage]);
+          tma_load_3d(dst + 2 * PS_PLANE, &tmB, 0, kc0, rb, &full[stage]);
+          tma_load_3d(dst + 3 * PS_PLANE, &tmB2, 0, kc0, rb, &full[stage]);
+          if (++stage == PS_STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    } else if (lane == 0) {
       int rs = 0, rphase = 0;
       for (int nt = nt0; nt < nt1; ++nt) {
         for (int kb = 0; kb < nkb; ++kb) {
@@ -198,7 +289,7 @@ tc16_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // ===== converters: landed fp32 tile -> (scale, split) -> fp16 operand planes =====
     const int ptid = tid - PROD_WARP0 * 32;
     const float sa = scale_from_amax(p.a_amax, p.a_scale), sb = scale_from_amax(p.b_amax, p.b_scale);
-    const int n_items = (nt1 - nt0) * nkb;
+    const int n_items = p.presplit ? 0 : (nt1 - nt0) * nkb;
     int stage = 0, phase = 0, rs = 0, rphase = 0;
     for (int it = 0; it < n_items; ++it) {
       const bool mark = ptid == 0 && it == 12;
@@ -229,6 +320,7 @@ tc16_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // ===== MMA issuer =====
     constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);   // f16 x f16 -> f32
     int stage = 0, phase = 0, tile = 0;
+    if (a_stat && nkb > 0) mbar_wait(a_full, 0);
     for (int nt = nt0; nt < nt1 && nkb > 0; ++nt, ++tile) {
       const int acc = tile & 1;
       if (tile >= 2) {
@@ -238,17 +330,22 @@ tc16_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const uint32_t d1 = tmem_base + acc * 256, d2 = d1 + 128;
       for (int kb = 0; kb < nkb; ++kb) {
         if (lane == 0 && tile == 0 && kb == 12) DBG16(8);
+        if (lane == 0 && tile == 1 && kb < 4) DBG16(20 + 2 * kb);
         mbar_wait(&full[stage], phase);
+        if (lane == 0 && tile == 1 && kb < 4) DBG16(21 + 2 * kb);
         if (lane == 0 && tile == 0 && kb == 12) DBG16(9);
         if (lane == 0 && tile == 0 && kb == 13) DBG16(11);
         tc_fence_after();
         if (elect_one()) {
-          const uint32_t sa = smem_u + stage * STAGE_BYTES;
-          const uint64_t ahi = make_smem_desc(sa, T_LBO, T_SBO, 0), alo = make_smem_desc(sa + PLANE, T_LBO, T_SBO, 0);
-          const uint64_t bhi = make_smem_desc(sa + 2 * PLANE, T_LBO, T_SBO, 0), blo = make_smem_desc(sa + 3 * PLANE, T_LBO, T_SBO, 0);
+          const uint32_t lbo = p.presplit ? PS_LBO : T_LBO, sbo = p.presplit ? PS_SBO : T_SBO;
+          // operand bases: ring stage [A_hi, A_lo, B_hi, B_lo], or stationary A (k-block kb) + ring stage [B_hi, B_lo]
+          const uint32_t sa = a_stat ? smem_u + kb * 2 * PS_PLANE : smem_u + stage * stage_bytes;
+          const uint32_t sb = a_stat ? smem_u + AS_A_BYTES + stage * AS_STAGE_BYTES : sa + 2 * plane_bytes;
+          const uint64_t ahi = make_smem_desc(sa, lbo, sbo, 0), alo = make_smem_desc(sa + plane_bytes, lbo, sbo, 0);
+          const uint64_t bhi = make_smem_desc(sb, lbo, sbo, 0), blo = make_smem_desc(sb + plane_bytes, lbo, sbo, 0);
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
-            const uint64_t adv = (uint64_t)(k * 2 * T_LBO >> 4);
+            const uint64_t adv = (uint64_t)(k * 2 * lbo >> 4);
             const uint32_t accum = (kb | k) ? 1u : 0u;
             mma_f16(d1, ahi + adv, bhi + adv, idesc, accum);
             mma_f16(d2, ahi + adv, blo + adv, idesc, accum);
@@ -259,7 +356,7 @@ tc16_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
         __syncwarp();
         if (lane == 0 && tile == 0 && kb == 12) DBG16(10);
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        if (++stage == nstages) { stage = 0; phase ^= 1; }
       }
     }
   } else {
@@ -286,7 +383,18 @@ tc16_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int n0 = nt * BN, acc = tile & 1;
       mbar_wait(&tmem_full[acc], (tile >> 1) & 1);
       tc_fence_after();
-      if (tid == 0 && tile == 0) DBG16(14);
+      if (tid == 0 && tile < 4) DBG16(14 + 2 * tile);
+      // this warp's 64 bias values (vocabulary modes) -> shared memory: broadcast reads instead of 64 global loads
+      float* sbias = reinterpret_cast<float*>(smem + OFF_BIAS) + ew * 64;
+      if (p.mode != 0) {
+        __syncwarp();
+#pragma unroll
+        for (int h2 = 0; h2 < 2; ++h2) {
+          const int col = n0 + ehalf * 64 + h2 * 32 + lane;
+          sbias[h2 * 32 + lane] = col < p.N ? __ldg(p.bias + col) : 0.f;
+        }
+        __syncwarp();
+      }
 #pragma unroll 1
       for (int c = 2 * ehalf; c < 2 * ehalf + 2; ++c) {
         const int col0 = n0 + c * 32;
@@ -307,7 +415,7 @@ tc16_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               if (p.mode == 2) {
                 const int col = col0 + hh * 16 + j;
                 x = (row_scale == 0.f || col >= p.N) ? 0.f
-                    : (__expf(x + __ldg(p.bias + col) - row_lse) - (col == tgt ? 1.f : 0.f)) * row_scale;
+                    : (__expf(x + sbias[(c & 1) * 32 + hh * 16 + j] - row_lse) - (col == tgt ? 1.f : 0.f)) * row_scale;
               }
               sts32(sc + (lane * 33 + hh * 16 + j) * 4, x);
             }
@@ -374,31 +482,62 @@ tc16_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           tmem_ld16(ta + hh * 16, v);
           tmem_ld16(ta + 128 + hh * 16, w);
           if (!row_ok) continue;
-          float tmax = -INFINITY;
+          // 16 logits of this row: everything below is a tree or independent per element (the serial running-max /
+          // arg-max / sum chains of the obvious loop made this epilogue, not the MMAs, the kernel's critical path)
+          const int base = col0 + hh * 16;
+          float x[16], xs[16];
 #pragma unroll
-          for (int j4 = 0; j4 < 16; j4 += 4) {
-            float g[4] = {0.f, 0.f, 0.f, 0.f};
-            if (sample) gumbel4(gseed, p.gumbel_salt, row, col0 + hh * 16 + j4, (p.N + 3) >> 2, g);
+          for (int j = 0; j < 16; ++j)
+            x[j] = base + j < p.N ? fmaf(w[j], kLoInv, v[j]) * oscale + sbias[(c & 1) * 32 + hh * 16 + j] : -INFINITY;
+          if (sample) {
 #pragma unroll
-            for (int jj = 0; jj < 4; ++jj) {
-              const int j = j4 + jj, col = col0 + hh * 16 + j;
-              float x = col < p.N ? fmaf(w[j], kLoInv, v[j]) * oscale + __ldg(p.bias + col) : -INFINITY;
-              v[j] = x;
-              tmax = fmaxf(tmax, x);
-              const float xs = x + g[jj];
-              if (xs > rav) { rav = xs; rai = col; }       // columns ascend, so ties keep the first index
-              if (col == tgt) rt = x;
+            for (int j4 = 0; j4 < 16; j4 += 4) {
+              float g[4];
+              gumbel4(gseed, p.gumbel_salt, row, base + j4, (p.N + 3) >> 2, g);
+#pragma unroll
+              for (int jj = 0; jj < 4; ++jj) xs[j4 + jj] = x[j4 + jj] + g[jj];
             }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) xs[j] = x[j];
+          }
+          float m8[8], m4[4];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) m8[j] = fmaxf(xs[2 * j], xs[2 * j + 1]);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) m4[j] = fmaxf(m8[2 * j], m8[2 * j + 1]);
+          const float smax = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));       // max of the (noisy) scores
+          if (smax > rav) {                                  // columns ascend: ties keep the earlier index
+            unsigned eq = 0;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) eq |= (xs[j] == smax ? 1u : 0u) << j;
+            rav = smax;
+            rai = base + __ffs(eq) - 1;
+          }
+          if (tgt >= base && tgt < base + 16) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (base + j == tgt) rt = x[j];
+          }
+          float tmax = smax;
+          if (sample) {                                      // the softmax statistics use the noise-free logits
+#pragma unroll
+            for (int j = 0; j < 8; ++j) m8[j] = fmaxf(x[2 * j], x[2 * j + 1]);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) m4[j] = fmaxf(m8[2 * j], m8[2 * j + 1]);
+            tmax = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
           }
           if (tmax > rm) { rs *= __expf(rm - tmax); rm = tmax; }
+          float e8[8];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) rs += __expf(v[j] - rm);
+          for (int j = 0; j < 8; ++j) e8[j] = __expf(x[2 * j] - rm) + __expf(x[2 * j + 1] - rm);
+          rs += ((e8[0] + e8[1]) + (e8[2] + e8[3])) + ((e8[4] + e8[5]) + (e8[6] + e8[7]));
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
-      if (tid == 0 && tile == 0) DBG16(15);
+      if (tid == 0 && tile < 4) DBG16(15 + 2 * tile);
     }
     if (p.mode == 1 && row_ok) {      // the two column halves are separate vocabulary splits for the finalize kernel
       const int64_t sp = (int64_t)blockIdx.y * 2 + ehalf;
@@ -458,17 +597,65 @@ static int make_map(CUtensorMap* m, const float* base, int64_t ld, int mn_major,
   return DVAE_OK;
 }
 
+// 3-D map over one fp16 plane in the blocked layout of split_planes: dim0 = one core matrix (64 elements, 128 B),
+// dim1 = k chunks, dim2 = 8-row groups; a box of 64 x 4 x 16 is a dense UMMA-ready 128 x 32 operand tile
+static int make_plane_map(CUtensorMap* m, const void* plane, int rows, int K) {
+  EncodeTiledFn fn = encode_fn();
+  DVAE_REQUIRE(fn != nullptr, "tc16_gemm: cuTensorMapEncodeTiled is not available from the driver");
+  const int KC = ceil_div(K, 8), RG = ceil_div(rows, 8);
+  cuuint64_t dims[3] = {64, (cuuint64_t)KC, (cuuint64_t)RG};
+  cuuint64_t strides[2] = {128, (cuuint64_t)KC * 128};
+  cuuint32_t box[3] = {64, BK / 8, BM / 8};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(plane), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  DVAE_REQUIRE(r == CUDA_SUCCESS, "tc16_gemm: plane tensor map failed (%d) rows=%d K=%d", (int)r, rows, K);
+  return DVAE_OK;
+}
+
+int64_t plane_floats(int R, int K) { return (int64_t)ceil_div(R, 8) * 8 * ceil_div(K, 8) * 8; }
+
+bool presplit_enabled() {
+  const char* e = getenv("DVAE_VOCAB_PRESPLIT");
+  return !(e && e[0] == '0');
+}
+
+int split_planes(const float* X, int64_t ld, int R, int K, float scale, void* planes, cudaStream_t st) {
+  DVAE_REQUIRE(X && planes && R > 0 && K > 0, "tc16 split_planes: bad argument");
+  const int64_t n = plane_floats(R, K);                 // fp16 elements per plane = floats of both planes / ... (2 B each)
+  __half* hi = reinterpret_cast<__half*>(planes);
+  __half* lo = hi + n;
+  const int64_t work = (int64_t)ceil_div(R, 8) * 8 * ceil_div(K, 8);
+  int blocks = ceil_div(work, 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  split_planes_kernel<<<blocks, 256, 0, st>>>(X, ld, R, K, scale, hi, lo);
+  DVAE_LAUNCH_CHECK();
+  return DVAE_OK;
+}
+
 static int launch(const Params& p, dim3 grid, cudaStream_t st) {
   static bool ready = false;
   if (!ready) {
     DVAE_CUDA(cudaFuncSetAttribute(tc16_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     ready = true;
   }
-  CUtensorMap ma, mb;
-  int rc = make_map(&ma, p.A, p.lda, p.a_mn, p.M, p.K);
-  if (rc) return rc;
-  if ((rc = make_map(&mb, p.Bm, p.ldb, p.b_mn, p.N, p.K))) return rc;
-  tc16_gemm_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(ma, mb, p);
+  CUtensorMap ma, mb, ma2, mb2;
+  memset(&ma2, 0, sizeof(ma2));
+  memset(&mb2, 0, sizeof(mb2));
+  int rc;
+  if (p.presplit) {
+    const __half* ah = reinterpret_cast<const __half*>(p.a_planes);
+    const __half* bh = reinterpret_cast<const __half*>(p.b_planes);
+    if ((rc = make_plane_map(&ma, ah, p.a_rows, p.K))) return rc;
+    if ((rc = make_plane_map(&ma2, ah + plane_floats(p.a_rows, p.K), p.a_rows, p.K))) return rc;
+    if ((rc = make_plane_map(&mb, bh, p.b_rows, p.K))) return rc;
+    if ((rc = make_plane_map(&mb2, bh + plane_floats(p.b_rows, p.K), p.b_rows, p.K))) return rc;
+  } else {
+    if ((rc = make_map(&ma, p.A, p.lda, p.a_mn, p.M, p.K))) return rc;
+    if ((rc = make_map(&mb, p.Bm, p.ldb, p.b_mn, p.N, p.K))) return rc;
+  }
+  tc16_gemm_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(ma, mb, ma2, mb2, p);
   DVAE_LAUNCH_CHECK();
   return DVAE_OK;
 }
@@ -519,8 +706,10 @@ int linear(const float* A, int64_t lda, int trans_a, const float* B, int64_t ldb
 
 int ce_partials(const float* h, int64_t ldh, int N, int B, int H, int V, const float* w, const float* bias,
                 const int64_t* targets, int64_t tgt_stride_b, const int64_t* lengths, int tiles_per_split, int nsplit,
-                float* part, int* part_idx, const uint64_t* gumbel_seed, uint32_t gumbel_salt, cudaStream_t st) {
+                float* part, int* part_idx, const uint64_t* gumbel_seed, uint32_t gumbel_salt, const void* h_planes,
+                const void* w_planes, cudaStream_t st) {
   Params p = {};
+  if (h_planes && w_planes) { p.presplit = 1; p.a_planes = h_planes; p.b_planes = w_planes; p.a_rows = N; p.b_rows = V; }
   p.A = h; p.lda = ldh; p.Bm = w; p.ldb = H;
   p.M = N; p.N = V; p.K = H; p.tiles_per_cta = tiles_per_split; p.bias = bias; p.mode = 1;
   p.kb_per_split = ceil_div(H, BK);
@@ -530,10 +719,11 @@ int ce_partials(const float* h, int64_t ldh, int N, int B, int H, int V, const f
   return launch(p, dim3(ceil_div(N, BM), nsplit, 1), st);
 }
 
-int softmax_grad(const float* h, int64_t ldh, int N, int B, int H, int v0, int vc, const float* w, const float* bias,
+int softmax_grad(const float* h, int64_t ldh, int N, int B, int H, int V, int v0, int vc, const float* w, const float* bias,
                  const int64_t* targets, int64_t tgt_stride_b, const int64_t* lengths, const float* lse,
-                 const float* grad_scale, float* P, int64_t ldp, cudaStream_t st) {
+                 const float* grad_scale, float* P, int64_t ldp, const void* h_planes, const void* w_planes, cudaStream_t st) {
   Params p = {};
+  if (h_planes && w_planes) { p.presplit = 1; p.a_planes = h_planes; p.b_planes = w_planes; p.a_rows = N; p.b_rows = V; p.b_row0 = v0; }
   p.A = h; p.lda = ldh; p.Bm = w + (int64_t)v0 * H; p.ldb = H;
   // a run of vocabulary tiles per CTA so the epilogue of one tile overlaps the main loop of the next; ~one wave of CTAs
   const int row_tiles = ceil_div(N, BM), col_tiles = ceil_div(vc, BN);

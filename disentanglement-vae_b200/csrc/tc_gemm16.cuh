@@ -24,6 +24,9 @@ struct Params {
   float* part; int* part_idx;            // mode 1: [nsplit][M][4] (max, sumexp, target logit, argmax value), [nsplit][M]
   const float* lse; const float* grad_scale; int v0;   // mode 2: C = P[:, v0:v0+N]
   const uint64_t* gumbel_seed; uint32_t gumbel_salt;   // mode 1: when set, the arg-max is taken over logits + Gumbel noise
+  // pre-split mode: the operands are fp16 (hi, lo) planes in global memory (split_planes), blocked by core matrix
+  int presplit; int b_row0;     // b_row0: first B row of this call inside the B planes (a vocabulary chunk)
+  const void* a_planes; const void* b_planes; int a_rows, b_rows;      // hi plane first, lo plane right after it
   unsigned long long* dbg;   // optional: pipeline milestone timestamps (ns) of CTA (0,0,0), profiles/probes/tc16_timeline.py
 };
 
@@ -32,12 +35,20 @@ bool shape_ok(const float* A, int64_t lda, int trans_a, const float* B, int64_t 
 bool supported(const float* A, int64_t lda, int trans_a, const float* B, int64_t ldb, int trans_b, int M, int N, int K);
 int linear(const float* A, int64_t lda, int trans_a, const float* B, int64_t ldb, int trans_b, float* C, int64_t ldc, int M,
            int N, int K, const float* bias, const float* bias2, float beta, int act, const GemmHints& hints, cudaStream_t st);
+// Operand planes: X [R, K] fp32 -> fp16 hi / lo planes (blocked by core matrix, zero padded to 8 rows / 8 columns).
+// plane_floats: size of BOTH planes in floats.  Operands that many tiles re-read (the decoder states and the vocabulary
+// matrix in the vocab-CE kernels) are split once; the GEMM then runs without landing ring and converter warps.
+int64_t plane_floats(int R, int K);
+int split_planes(const float* X, int64_t ld, int R, int K, float scale, void* planes, cudaStream_t st);
+bool presplit_enabled();      // DVAE_VOCAB_PRESPLIT=0 disables
+// h_planes / w_planes (both or neither): planes of h [N, H] and of the WHOLE w [V, H]
 int ce_partials(const float* h, int64_t ldh, int N, int B, int H, int V, const float* w, const float* bias,
                 const int64_t* targets, int64_t tgt_stride_b, const int64_t* lengths, int tiles_per_split, int nsplit,
-                float* part, int* part_idx, const uint64_t* gumbel_seed, uint32_t gumbel_salt, cudaStream_t st);
-int softmax_grad(const float* h, int64_t ldh, int N, int B, int H, int v0, int vc, const float* w, const float* bias,
+                float* part, int* part_idx, const uint64_t* gumbel_seed, uint32_t gumbel_salt, const void* h_planes,
+                const void* w_planes, cudaStream_t st);
+int softmax_grad(const float* h, int64_t ldh, int N, int B, int H, int V, int v0, int vc, const float* w, const float* bias,
                  const int64_t* targets, int64_t tgt_stride_b, const int64_t* lengths, const float* lse,
-                 const float* grad_scale, float* P, int64_t ldp, cudaStream_t st);
+                 const float* grad_scale, float* P, int64_t ldp, const void* h_planes, const void* w_planes, cudaStream_t st);
 
 }  // namespace tc16
 }  // namespace dvae

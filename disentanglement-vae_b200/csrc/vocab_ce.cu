@@ -21,6 +21,13 @@ int colsum_impl(const float* X, int64_t ldx, int M, int N, float* out, float bet
 
 using GCE = GemmTile<128, 128, 16, 8, 8, true, true>;
 
+struct CeArgs;
+static bool use_tc16(int N, int V, int H, const float* h, int64_t ldh, const float* w) {
+  return !force_simt_gemm() && N >= 64 && V >= 128 && H >= 32 && tc16::supported(h, ldh, 0, w, H, 0, N, V, H);
+}
+// pre-split operand planes pay off when both operands are re-read by many tiles and K is a whole number of k-blocks
+static bool use_presplit(int N, int V, int H) { return tc16::presplit_enabled() && H % 32 == 0 && N >= 256 && V >= 1024; }
+
 struct CeArgs {
   const float* h; int64_t ldh;
   const float* w; const float* bias;
@@ -31,6 +38,7 @@ struct CeArgs {
   float* part;      // [nsplit][N][4]: max, sumexp, target logit, argmax value
   int* part_idx;    // [nsplit][N]
   const uint64_t* gumbel_seed; uint32_t gumbel_salt;   // sampling: arg-max over logits + Gumbel noise
+  const void* h_planes; const void* w_planes;          // optional pre-split fp16 operand planes (tc16::split_planes)
 };
 
 __device__ __forceinline__ void merge_ms(float& m, float& s, float m2, float s2) {
@@ -241,7 +249,8 @@ static int ce_partials(CeArgs& p, cudaStream_t st) {
     p.nsplit = 2 * launched;
     p.part_idx = reinterpret_cast<int*>(p.part + (int64_t)p.nsplit * p.N * 4);
     return tc16::ce_partials(p.h, p.ldh, p.N, p.B, p.H, p.V, p.w, p.bias, p.targets, p.tgt_stride_b, p.lengths,
-                             p.tiles_per_split, launched, p.part, p.part_idx, p.gumbel_seed, p.gumbel_salt, st);
+                             p.tiles_per_split, launched, p.part, p.part_idx, p.gumbel_seed, p.gumbel_salt, p.h_planes,
+                             p.w_planes, st);
   }
   if (!force_simt_gemm() && p.N >= 64 && p.V >= 128 && p.H >= 32 && tc::tc_linear_supported(p.h, p.ldh, p.w, p.H, p.N, p.V, p.H))
     return tc::tc_ce_partials(p.h, p.ldh, p.N, p.B, p.H, p.V, p.w, p.bias, p.targets, p.tgt_stride_b, p.lengths,
@@ -276,10 +285,14 @@ static int p_chunk(int N, int V) {
 
 using namespace dvae;
 
-extern "C" int64_t dvae_vocab_ce_ws_floats(int N, int V) {
+// workspace layout (floats): [partials 2*ns*N*5 + 8][block sums][pad to 4][operand planes of h and w]
+static int64_t ce_part_floats(int N, int V) {
   int tps;
   int ns = ce_nsplit(N, V, &tps);
-  return 2LL * ns * N * 5 + 8 + kFinMaxBlocks;    // x2: the fp16-split kernel writes two partials per (row, split)
+  return (2LL * ns * N * 5 + 8 + kFinMaxBlocks + 3) / 4 * 4;    // x2: the fp16-split kernel writes two partials per (row, split)
+}
+extern "C" int64_t dvae_vocab_ce_ws_floats(int N, int V, int H) {
+  return ce_part_floats(N, V) + tc16::plane_floats(N, H) + tc16::plane_floats(V, H);
 }
 
 extern "C" int dvae_vocab_ce_fwd(const float* h, int64_t ldh, int T1, int B, int H, int V, const float* w,
@@ -296,6 +309,16 @@ extern "C" int dvae_vocab_ce_fwd(const float* h, int64_t ldh, int T1, int B, int
   p.part = ws;
   p.part_idx = reinterpret_cast<int*>(ws + (int64_t)p.nsplit * p.N * 4);
   p.gumbel_seed = nullptr; p.gumbel_salt = 0;
+  p.h_planes = p.w_planes = nullptr;
+  if (use_tc16(p.N, V, H, h, ldh, w) && use_presplit(p.N, V, H)) {
+    // both operands are re-read by every tile of the other dimension: split them into fp16 planes once
+    float* hp = ws + ce_part_floats(p.N, V);
+    float* wp = hp + tc16::plane_floats(p.N, H);
+    int rc;
+    if ((rc = tc16::split_planes(h, ldh, p.N, H, 1.f, hp, st))) return rc;
+    if ((rc = tc16::split_planes(w, H, V, H, 1.f, wp, st))) return rc;
+    p.h_planes = hp; p.w_planes = wp;
+  }
   { int rc = ce_partials(p, st); if (rc) return rc; }
   float* block_sums = ws + (int64_t)p.nsplit * p.N * 5 + 8;      // p.nsplit: as updated by ce_partials
   const int nblk = min(kFinMaxBlocks, ceil_div(p.N, kFinThreads));
@@ -306,7 +329,9 @@ extern "C" int dvae_vocab_ce_fwd(const float* h, int64_t ldh, int T1, int B, int
   return DVAE_OK;
 }
 
-extern "C" int64_t dvae_vocab_ce_bwd_ws_floats(int N, int V) { return (int64_t)N * p_chunk(N, V); }
+extern "C" int64_t dvae_vocab_ce_bwd_ws_floats(int N, int V, int H) {
+  return (int64_t)N * p_chunk(N, V) + tc16::plane_floats(N, H) + tc16::plane_floats(V, H);
+}
 
 extern "C" int dvae_vocab_ce_bwd(const float* h, int64_t ldh, int T1, int B, int H, int V, const float* w,
                                  const float* bias, const int64_t* targets, int64_t tgt_stride_b,
@@ -325,14 +350,23 @@ extern "C" int dvae_vocab_ce_bwd(const float* h, int64_t ldh, int T1, int B, int
   GemmHints ph;
   ph.a_scale = 1.f;
   while (ph.a_scale * 2.f <= (float)B) ph.a_scale *= 2.f;
+  const void *h_planes = nullptr, *w_planes = nullptr;
+  if (use_tc16(N, min(vc_max, V), H, h, ldh, w) && use_presplit(N, V, H)) {
+    float* hp = ws + (int64_t)N * vc_max;
+    float* wp = hp + tc16::plane_floats(N, H);
+    int rc;
+    if ((rc = tc16::split_planes(h, ldh, N, H, 1.f, hp, st))) return rc;
+    if ((rc = tc16::split_planes(w, H, V, H, 1.f, wp, st))) return rc;
+    h_planes = hp; w_planes = wp;
+  }
   int chunk = 0;
   for (int v0 = 0; v0 < V; v0 += vc_max, ++chunk) {
     const int vc = min(vc_max, V - v0);
     p.v0 = v0; p.vc = vc;
     int rc;
     if (!force_simt_gemm() && N >= 64 && vc >= 128 && H >= 32 && tc16::supported(h, ldh, 0, w, H, 0, N, vc, H)) {
-      if ((rc = tc16::softmax_grad(h, ldh, N, B, H, v0, vc, w, bias, targets, tgt_stride_b, lengths, lse, grad_scale_dev, ws,
-                                   vc_max, st))) return rc;
+      if ((rc = tc16::softmax_grad(h, ldh, N, B, H, V, v0, vc, w, bias, targets, tgt_stride_b, lengths, lse, grad_scale_dev, ws,
+                                   vc_max, h_planes, w_planes, st))) return rc;
     } else if (!force_simt_gemm() && N >= 64 && vc >= 128 && H >= 32 && tc::tc_linear_supported(h, ldh, w, H, N, vc, H)) {
       if ((rc = tc::tc_softmax_grad(h, ldh, N, B, H, v0, vc, w, bias, targets, tgt_stride_b, lengths, lse, grad_scale_dev, ws,
                                     vc_max, st))) return rc;
@@ -365,6 +399,7 @@ extern "C" int dvae_vocab_sample_step(const float* h, int64_t ldh, int B, int H,
   p.part = ws;
   p.part_idx = reinterpret_cast<int*>(ws + (int64_t)p.nsplit * p.N * 4);
   p.gumbel_seed = seed_dev; p.gumbel_salt = salt;
+  p.h_planes = p.w_planes = nullptr;      // one decode step: h has B rows only, splitting w per step would not pay
   int rc = ce_partials(p, st);
   if (rc) return rc;
   vocab_sample_finalize_kernel<<<ceil_div(B, 128), 128, 0, st>>>(p, tokens_out, tok_stride);

@@ -90,7 +90,7 @@ class StepPlan:
         self.lse, self.nll = buf(max(self.N, 1)), buf(max(self.N, 1))
         self.argmax = torch.zeros(max(self.N, 1), device=device, dtype=torch.int32)
         self.recon = self.out[_lib.HEADS_NSCALARS:_lib.HEADS_NSCALARS + 1]
-        self.ce_ws = buf(self.lib.dvae_vocab_ce_ws_floats(max(self.N, 1), d.V))
+        self.ce_ws = buf(self.lib.dvae_vocab_ce_ws_floats(max(self.N, 1), d.V, d.Hd))
         self.sample_ws = None                      # allocated on first sampled decode
         self._bwd_ready = False
         self.seed_dev = torch.zeros(1, device=device, dtype=torch.int64)
@@ -111,7 +111,7 @@ class StepPlan:
         self.g_hid = torch.empty(B, d.H2L, **f32)
         self.g_ctx = torch.empty(B, d.C, **f32)
         self.heads_bwd_ws = torch.empty(self.lib.dvae_heads_bwd_ws_floats(B, d.Z, d.H2L), **f32)
-        self.ce_bwd_ws = torch.empty(self.lib.dvae_vocab_ce_bwd_ws_floats(max(self.N, 1), d.V), **f32)
+        self.ce_bwd_ws = torch.empty(self.lib.dvae_vocab_ce_bwd_ws_floats(max(self.N, 1), d.V, d.Hd), **f32)
         self._bwd_ready = True
 
     @staticmethod
@@ -212,7 +212,7 @@ class StepPlan:
         hid = self.hid if hid is None else hid
         p = d.p_dec if train else 0.0
         if self.sample_ws is None:
-            self.sample_ws = torch.empty(lib.dvae_vocab_ce_ws_floats(B, d.V), device=self.device, dtype=torch.float32)
+            self.sample_ws = torch.empty(lib.dvae_vocab_ce_ws_floats(B, d.V, d.Hd), device=self.device, dtype=torch.float32)
         emb = P["decoder.embedding.weight"]
         W = [self._dec_w(P, l) for l in range(d.Ld)]
         for s in range(T1):

@@ -261,9 +261,9 @@ int dvae_dsc_loss(const float* dsc_logits, const float* labels, int B, int S,
  *   loss[0] = (1/B) * sum_b ( nll0_b + sum_{1<=t<len_b} nll[b,t] ) where nll0_b is the constant
  *   contribution of the one-hot pseudo-logit row at t = 0 (model.py:454):
  *   log(e + V - 1) - [targets[b,0] == sos].
- *   ws: dvae_vocab_ce_ws_floats(N, V) floats.
+ *   ws: dvae_vocab_ce_ws_floats(N, V, H) floats.
  * ------------------------------------------------------------------------------------------- */
-int64_t dvae_vocab_ce_ws_floats(int N, int V);
+int64_t dvae_vocab_ce_ws_floats(int N, int V, int H);
 int dvae_vocab_ce_fwd(const float* h, int64_t ldh, int T1, int B, int H, int V, const float* w,
                       const float* bias, const int64_t* targets, int64_t tgt_stride_b,
                       const int64_t* lengths, int sos, float* lse, float* nll, int32_t* argmax,
@@ -273,15 +273,15 @@ int dvae_vocab_ce_fwd(const float* h, int64_t ldh, int T1, int B, int H, int V, 
  * decoder.linear + torch.softmax + torch.multinomial (vae/model.py:164,468-469,504-505).
  * tokens_out[b*tok_stride] = argmax_v( h[b].w[v] + bias[v] + g(b,v) ), g ~ Gumbel(0,1) from Philox keyed by
  * (*seed_dev, salt, b, v) -- the Gumbel-max trick: the arg-max is distributed as softmax(logits).
- *   ws: dvae_vocab_ce_ws_floats(B, V) floats. */
+ *   ws: dvae_vocab_ce_ws_floats(B, V, H) floats. */
 int dvae_vocab_sample_step(const float* h, int64_t ldh, int B, int H, int V, const float* w,
                            const float* bias, const uint64_t* seed_dev, uint32_t salt, int64_t* tokens_out,
                            int64_t tok_stride, float* ws, void* stream);
 
 /* Backward: d_h [N,H], d_w [V,H], d_bias [V] (all overwritten) for d(loss) = grad_scale_dev[0]
  * (NULL = 1).  Softmax tiles are recomputed from h, w and the saved lse.
- *   ws: dvae_vocab_ce_bwd_ws_floats(N, V) floats. */
-int64_t dvae_vocab_ce_bwd_ws_floats(int N, int V);
+ *   ws: dvae_vocab_ce_bwd_ws_floats(N, V, H) floats. */
+int64_t dvae_vocab_ce_bwd_ws_floats(int N, int V, int H);
 int dvae_vocab_ce_bwd(const float* h, int64_t ldh, int T1, int B, int H, int V, const float* w,
                       const float* bias, const int64_t* targets, int64_t tgt_stride_b,
                       const int64_t* lengths, const float* lse, const float* grad_scale_dev,

@@ -18,7 +18,7 @@ h = r(T1, Bt, H) * 0.5; w = r(V, H) * 0.05; bias = torch.zeros(V, device="cuda")
 tg = torch.randint(4, V, (Bt, T1 + 1), device="cuda"); ln = torch.full((Bt,), T1 + 1, device="cuda", dtype=torch.int64)
 lse, nll = torch.zeros(N, device="cuda"), torch.zeros(N, device="cuda")
 am = torch.zeros(N, device="cuda", dtype=torch.int32); loss = torch.zeros(1, device="cuda")
-ws = torch.zeros(lib.dvae_vocab_ce_ws_floats(N, V), device="cuda")
+ws = torch.zeros(lib.dvae_vocab_ce_ws_floats(N, V, H), device="cuda")
 for _ in range(3):
     L.check(lib.dvae_vocab_ce_fwd(L.ptr(h), H, T1, Bt, H, V, L.ptr(w), L.ptr(bias), L.ptr(tg), tg.stride(0), L.ptr(ln), 2, L.ptr(lse), L.ptr(nll),
                                   L.ptr(am), L.ptr(loss), L.ptr(ws), st), "ce")

@@ -43,8 +43,8 @@ ln = torch.full((Bt,), T1 + 1, device="cuda", dtype=torch.int64)
 lse, nll = torch.zeros(N, device="cuda"), torch.zeros(N, device="cuda")
 am = torch.zeros(N, device="cuda", dtype=torch.int32)
 loss = torch.zeros(1, device="cuda")
-ws = torch.zeros(lib.dvae_vocab_ce_ws_floats(N, V), device="cuda")
-wsb = torch.zeros(lib.dvae_vocab_ce_bwd_ws_floats(N, V), device="cuda")
+ws = torch.zeros(lib.dvae_vocab_ce_ws_floats(N, V, H), device="cuda")
+wsb = torch.zeros(lib.dvae_vocab_ce_bwd_ws_floats(N, V, H), device="cuda")
 dh, dw, db = torch.zeros(N, H, device="cuda"), torch.zeros(V, H, device="cuda"), torch.zeros(V, device="cuda")
 fwd = lambda: lib.dvae_vocab_ce_fwd(L.ptr(h), H, T1, Bt, H, V, L.ptr(w), L.ptr(bias), L.ptr(tg), tg.stride(0), L.ptr(ln), 2, L.ptr(lse), L.ptr(nll), L.ptr(am), L.ptr(loss), L.ptr(ws), st)
 bwd = lambda: lib.dvae_vocab_ce_bwd(L.ptr(h), H, T1, Bt, H, V, L.ptr(w), L.ptr(bias), L.ptr(tg), tg.stride(0), L.ptr(ln), L.ptr(lse), None, L.ptr(dh), H, L.ptr(dw), L.ptr(db), L.ptr(wsb), st)

@@ -18,12 +18,6 @@ __device__ __forceinline__ void mma_ts(uint32_t d, uint32_t a_tmem, uint64_t b, 
 }
 __host__ __device__ constexpr uint32_t idesc_f16(int M, int N) { return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24); }
 
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred;
-  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.b32 %0, 1, 0, p;\n\t}" : "=r"(pred));
-  return pred != 0;
-}
-
 // issue-style probe: 48 MMAs (16 k-steps x 3 products, as the LSTM step does), fully unrolled, N = 16
 template <int STYLE>
 __device__ __forceinline__ void issue48(uint32_t tmem, uint32_t sb, uint64_t* bar) {
@@ -38,6 +32,56 @@ __device__ __forceinline__ void issue48(uint32_t tmem, uint32_t sb, uint64_t* ba
     mma_ss(tmem + 16, alo + da, bhi + db, idesc, 1);
   }
   tc_commit(bar);
+}
+
+// layout probe: 48 MMAs M=128 N=128 K=16 (8 k-steps x 3 products x 2), no-swizzle K-major operands, two core-matrix placements
+template <int LBO, int SBO, int KSTEP>
+__device__ __forceinline__ void issue_n128(uint32_t tmem, uint32_t sb, uint64_t* bar) {
+  constexpr uint32_t idesc = idesc_f16(128, 128);
+  const uint64_t ahi = make_smem_desc(sb, LBO, SBO, 0), alo = make_smem_desc(sb + 16384, LBO, SBO, 0);
+  const uint64_t bhi = make_smem_desc(sb + 32768, LBO, SBO, 0), blo = make_smem_desc(sb + 49152, LBO, SBO, 0);
+#pragma unroll
+  for (int ks = 0; ks < 16; ++ks) {
+    const uint64_t d = (uint64_t)(((ks & 1) * KSTEP) >> 4);     // the two k-steps of one 32-k block, re-read (timing only)
+    mma_ss(tmem, ahi + d, bhi + d, idesc, ks > 0);
+    mma_ss(tmem + 128, ahi + d, blo + d, idesc, ks > 0);
+    mma_ss(tmem + 128, alo + d, bhi + d, idesc, 1);
+  }
+  tc_commit(bar);
+}
+
+__global__ void __launch_bounds__(128, 1) probe_layout(long long* out) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t slot;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < 200 * 1024 / 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
+  if (tid == 0) { mbar_init(&bar, 1); fence_barrier_init(); }
+  if (tid < 32) tmem_alloc(&slot, 256);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = slot, sb = smem_u32(smem);
+  int phase = 0;
+  for (int rep = 0; rep < 2; ++rep) {
+    for (int lay = 0; lay < 3; ++lay) {
+      long long t0 = clock64();
+      if (warp == 0) {
+        if (elect_one()) {
+          if (lay == 0) issue_n128<128, 512, 256>(tmem, sb, &bar);          // row-group blocks of 4 chunks (dense, tc_gemm16 pre-split)
+          else if (lay == 1) issue_n128<160, 640, 320>(tmem, sb, &bar);     // padded (tc_gemm16 converter path)
+          else issue_n128<2048, 128, 4096>(tmem, sb, &bar);                 // k-chunk columns of 128 rows x 16 B
+        }
+        __syncwarp();
+      }
+      mbar_wait(&bar, phase); phase ^= 1;
+      long long t2 = clock64();
+      if (tid == 0) out[rep * 3 + lay] = t2 - t0;
+      __syncthreads();
+    }
+  }
+  if (tid < 32) tmem_dealloc(tmem, 256);
 }
 
 __global__ void __launch_bounds__(128, 1) probe_style(long long* out) {
@@ -134,6 +178,14 @@ int main() {
     printf("N=%2d A=%s accumulators=%d : issue %6.1f cyc/MMA, complete %6.1f cyc/MMA (96 MMAs)\n", Ns[ni], mode ? "TMEM" : "SMEM", nacc, h[o] / 96.0, h[o + 1] / 96.0);
     o += 2;
   }
+  cudaFuncSetAttribute(probe_layout, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  probe_layout<<<1, 128, 200 * 1024>>>(d);
+  e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) { printf("error: %s\n", cudaGetErrorString(e)); return 1; }
+  cudaMemcpy(h, d, sizeof(h[0]) * 6, cudaMemcpyDeviceToHost);
+  for (int rep = 0; rep < 2; ++rep)
+    printf("48 MMAs M=128 N=128 K=16 f16 SS no-swizzle: LBO128/SBO512 %lld cyc (%.0f/MMA) | LBO160/SBO640 %lld cyc (%.0f/MMA) | LBO2048/SBO128 %lld cyc (%.0f/MMA)\n",
+           h[rep * 3], h[rep * 3] / 48.0, h[rep * 3 + 1], h[rep * 3 + 1] / 48.0, h[rep * 3 + 2], h[rep * 3 + 2] / 48.0);
   probe_style<<<1, 128, 200 * 1024>>>(d);
   e = cudaDeviceSynchronize();
   if (e != cudaSuccess) { printf("error: %s\n", cudaGetErrorString(e)); return 1; }

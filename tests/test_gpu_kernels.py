@@ -416,7 +416,7 @@ def test_vocab_ce(lib, L, T1, B, H, V):
     lse, nll = torch.zeros(N, device="cuda"), torch.zeros(N, device="cuda")
     am = torch.zeros(N, device="cuda", dtype=torch.int32)
     loss = torch.zeros(1, device="cuda")
-    ws = torch.zeros(lib.dvae_vocab_ce_ws_floats(N, V), device="cuda")
+    ws = torch.zeros(lib.dvae_vocab_ce_ws_floats(N, V, H), device="cuda")
     st = L.stream_ptr()
     L.check(lib.dvae_vocab_ce_fwd(L.ptr(hd), H, T1, B, H, V, L.ptr(Wd), L.ptr(bd), L.ptr(td), T, L.ptr(ld), sos,
                                   L.ptr(lse), L.ptr(nll), L.ptr(am), L.ptr(loss), L.ptr(ws), st), "ce fwd")
@@ -433,7 +433,7 @@ def test_vocab_ce(lib, L, T1, B, H, V):
     d_h = torch.zeros(N, H, device="cuda")
     d_w = torch.full((V, H), 9.0, device="cuda")
     d_b = torch.full((V,), 9.0, device="cuda")
-    wsb = torch.zeros(lib.dvae_vocab_ce_bwd_ws_floats(N, V), device="cuda")
+    wsb = torch.zeros(lib.dvae_vocab_ce_bwd_ws_floats(N, V, H), device="cuda")
     gs = torch.tensor([1.0], device="cuda")
     L.check(lib.dvae_vocab_ce_bwd(L.ptr(hd), H, T1, B, H, V, L.ptr(Wd), L.ptr(bd), L.ptr(td), T, L.ptr(ld), L.ptr(lse),
                                   L.ptr(gs), L.ptr(d_h), H, L.ptr(d_w), L.ptr(d_b), L.ptr(wsb), st), "ce bwd")

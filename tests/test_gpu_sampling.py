@@ -66,7 +66,7 @@ def test_vocab_sample_step_is_gumbel_argmax(dvae, B, H, V):
     hd, wd, bd = (torch.from_numpy(a).cuda() for a in (h, w, bias))
     sd = torch.tensor([seed], device="cuda", dtype=torch.int64)
     toks = torch.full((B, 3), -1, device="cuda", dtype=torch.int64)
-    ws = torch.empty(lib.dvae_vocab_ce_ws_floats(B, V), device="cuda")
+    ws = torch.empty(lib.dvae_vocab_ce_ws_floats(B, V, H), device="cuda")
     L.check(lib.dvae_vocab_sample_step(L.ptr(hd), H, B, H, V, L.ptr(wd), L.ptr(bd), L.ptr(sd), salt,
                                        toks.data_ptr() + 8, 3, L.ptr(ws), L.stream_ptr()), "sample")
     got = toks.cpu().numpy()
@@ -97,7 +97,7 @@ def test_vocab_sample_step_follows_softmax(dvae):
     hd, wd, bd = (torch.from_numpy(a).cuda() for a in (h, w, bias))
     sd = torch.tensor([20261018], device="cuda", dtype=torch.int64)
     toks = torch.zeros(B, device="cuda", dtype=torch.int64)
-    ws = torch.empty(lib.dvae_vocab_ce_ws_floats(B, V), device="cuda")
+    ws = torch.empty(lib.dvae_vocab_ce_ws_floats(B, V, H), device="cuda")
     L.check(lib.dvae_vocab_sample_step(L.ptr(hd), H, B, H, V, L.ptr(wd), L.ptr(bd), L.ptr(sd), 4096, L.ptr(toks), 1,
                                        L.ptr(ws), L.stream_ptr()), "sample")
     freq = np.bincount(toks.cpu().numpy(), minlength=V) / B
