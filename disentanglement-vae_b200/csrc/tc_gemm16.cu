@@ -398,7 +398,7 @@ tc16_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll 1
       for (int c = 2 * ehalf; c < 2 * ehalf + 2; ++c) {
         const int col0 = n0 + c * 32;
-        if (col0 >= p.N) continue;                       // warp-uniform
+        if (col0 >= p.N || p.dbg_skip_epilogue) continue;                       // warp-uniform
         const uint32_t ta = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * 256 + c * 32;
         if (p.mode != 1) {
           // modes 0 / 2 store a [32 rows x 32 cols] chunk: transpose it through padded shared memory so each
@@ -669,6 +669,7 @@ __global__ void tc16_scale_rows_kernel(float* C, int64_t ldc, int M, int N, floa
 
 static void apply_hints(Params& p, const GemmHints& h) {
   if (const char* e = getenv("DVAE_TC_DBG")) p.dbg = reinterpret_cast<unsigned long long*>(strtoull(e, nullptr, 0));
+  if (const char* e = getenv("DVAE_TC_SKIP_EPILOGUE")) p.dbg_skip_epilogue = atoi(e);     // probes only: main-loop speed in isolation
   p.a_amax = h.a_amax_bits; p.b_amax = h.b_amax_bits;
   p.a_scale = h.a_scale; p.b_scale = h.b_scale;
   p.alpha = 1.f; p.alpha_dev = nullptr;
