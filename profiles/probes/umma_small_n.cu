@@ -50,6 +50,58 @@ __device__ __forceinline__ void issue_n128(uint32_t tmem, uint32_t sb, uint64_t*
   tc_commit(bar);
 }
 
+// commit-frequency probe: the same 48 MMAs (M=128 N=128), with a tcgen05.commit after every `per` MMAs
+template <int PER>
+__device__ __forceinline__ void issue_commit_every(uint32_t tmem, uint32_t sb, uint64_t* bar, uint64_t* dummy) {
+  constexpr uint32_t idesc = idesc_f16(128, 128);
+  const uint64_t ahi = make_smem_desc(sb, 128, 512, 0), alo = make_smem_desc(sb + 16384, 128, 512, 0);
+  const uint64_t bhi = make_smem_desc(sb + 32768, 128, 512, 0), blo = make_smem_desc(sb + 49152, 128, 512, 0);
+#pragma unroll
+  for (int ks = 0; ks < 16; ++ks) {
+    const uint64_t d = (uint64_t)(((ks & 1) * 256) >> 4);
+    mma_ss(tmem, ahi + d, bhi + d, idesc, ks > 0);
+    mma_ss(tmem + 128, ahi + d, blo + d, idesc, ks > 0);
+    mma_ss(tmem + 128, alo + d, bhi + d, idesc, 1);
+    if (PER > 0 && ((ks + 1) * 3) % PER == 0 && ks != 15) tc_commit(dummy);
+  }
+  tc_commit(bar);
+}
+
+__global__ void __launch_bounds__(128, 1) probe_commit(long long* out) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bar, dummy;
+  __shared__ uint32_t slot;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < 200 * 1024 / 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
+  if (tid == 0) { mbar_init(&bar, 1); mbar_init(&dummy, 1); fence_barrier_init(); }
+  if (tid < 32) tmem_alloc(&slot, 256);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = slot, sb = smem_u32(smem);
+  int phase = 0;
+  for (int rep = 0; rep < 2; ++rep) {
+    for (int v = 0; v < 3; ++v) {
+      long long t0 = clock64(), t1 = 0;
+      if (warp == 0) {
+        if (elect_one()) {
+          if (v == 0) issue_commit_every<0>(tmem, sb, &bar, &dummy);
+          else if (v == 1) issue_commit_every<12>(tmem, sb, &bar, &dummy);
+          else issue_commit_every<6>(tmem, sb, &bar, &dummy);
+          t1 = clock64();
+        }
+        __syncwarp();
+      }
+      mbar_wait(&bar, phase); phase ^= 1;
+      long long t2 = clock64();
+      if (tid == 0) { out[rep * 6 + 2 * v] = t1 - t0; out[rep * 6 + 2 * v + 1] = t2 - t0; }
+      __syncthreads();
+    }
+  }
+  if (tid < 32) tmem_dealloc(tmem, 256);
+}
+
 __global__ void __launch_bounds__(128, 1) probe_layout(long long* out) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t bar;
@@ -178,6 +230,14 @@ int main() {
     printf("N=%2d A=%s accumulators=%d : issue %6.1f cyc/MMA, complete %6.1f cyc/MMA (96 MMAs)\n", Ns[ni], mode ? "TMEM" : "SMEM", nacc, h[o] / 96.0, h[o + 1] / 96.0);
     o += 2;
   }
+  cudaFuncSetAttribute(probe_commit, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  probe_commit<<<1, 128, 200 * 1024>>>(d);
+  e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) { printf("error: %s\n", cudaGetErrorString(e)); return 1; }
+  cudaMemcpy(h, d, sizeof(h[0]) * 12, cudaMemcpyDeviceToHost);
+  for (int rep = 0; rep < 2; ++rep)
+    printf("48 MMAs M=128 N=128: one commit at the end: issue %lld / done %lld cyc | commit every 12 MMAs: %lld / %lld | every 6: %lld / %lld\n",
+           h[rep * 6], h[rep * 6 + 1], h[rep * 6 + 2], h[rep * 6 + 3], h[rep * 6 + 4], h[rep * 6 + 5]);
   cudaFuncSetAttribute(probe_layout, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   probe_layout<<<1, 128, 200 * 1024>>>(d);
   e = cudaDeviceSynchronize();
