@@ -48,7 +48,7 @@ constexpr int EPI_SCRATCH_BYTES = 8 * 32 * 33 * 4;
 constexpr int OFF_RAW = STAGES * STAGE_BYTES, OFF_OPER_END = OFF_RAW + RAW_STAGES * RAW_BYTES, OFF_SCRATCH = OFF_OPER_END;
 // Pre-split mode (operands already split into fp16 planes in global memory, blocked by core matrix): no landing ring and
 // no converters -- TMA delivers UMMA-ready dense tiles (core matrices 128 B apart) straight into a 5-stage operand ring.
-constexpr int PS_PLANE = BM * BK * 2, PS_STAGE_BYTES = 4 * PS_PLANE, PS_STAGES = 5, MAX_STAGES = 5;
+constexpr int PS_PLANE = BM * BK * 2, PS_TILE = 2 * PS_PLANE, PS_STAGE_BYTES = 2 * PS_TILE, PS_STAGES = 5, MAX_STAGES = 5;
 constexpr int PS_LBO = 128, PS_SBO = 512;
 // A-stationary variant (K <= 256, no split-K): the CTA's A rows (both planes, all k-blocks: 128 KB) are loaded once and
 // stay in shared memory for the CTA's whole run of N tiles; only B tiles stream through a 3-stage ring.  With 128 x 128
@@ -65,11 +65,29 @@ static_assert(AS_A_BYTES + AS_STAGES_NOSCRATCH * AS_STAGE_BYTES <= OFF_BIAS, "A-
 constexpr int TMEM_COLS = 512;
 constexpr float kLoScale = 2048.f, kLoInv = 1.f / 2048.f;
 
+// 2^x, flush-to-zero: ONE MUFU.  `__expf` without -use_fast_math wraps its ex2 in a denormal-range fix-up (FSETP + two
+// predicated FMULs through a single predicate register), which serialised the 16 exponentials of an epilogue block.
+__device__ __forceinline__ float ex2_ftz(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+constexpr float kLog2e = 1.4426950408889634f;
+
 __device__ __forceinline__ unsigned long long gtime16() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
+// Main-loop probes (profiles/probes/tc16_*timeline.py) are compiled in only with -DDVAE_TC16_PROBES: per-k-block marks
+// and the DVAE_TC_SKIP_EPILOGUE bit switches cost instructions in the loops they observe.
+#ifdef DVAE_TC16_PROBES
+#define DVAE_TC16_FLAG(bit) (p.dbg_skip_epilogue & (bit))
+#define DVAE_TC16_MARK(cond, i) do { if (cond) DBG16(i); } while (0)
+#else
+#define DVAE_TC16_FLAG(bit) false
+#define DVAE_TC16_MARK(cond, i) do { } while (0)
+#endif
 #define DBG16(i) do { if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) p.dbg[i] = gtime16(); } while (0)
 
 __device__ __forceinline__ float scale_from_amax(const uint32_t* amax_bits, float static_scale) {
@@ -141,18 +159,20 @@ __device__ __forceinline__ void store_tile(uint32_t plane_hi, int mn_major, int 
   }
 }
 
-__device__ __forceinline__ void tma_load_3d(uint32_t smem_dst, const CUtensorMap* m, int c0, int c1, int c2, uint64_t* bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(smem_dst),
-      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
-      : "memory");
+// contiguous global -> shared bulk copy (no tensor map), completion on an mbarrier
+__device__ __forceinline__ void bulk_load(uint32_t smem_dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_dst), "l"(src),
+               "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
 }
 
-// X [R, K] fp32 (row stride ld) -> fp16 planes hi / lo, each blocked by UMMA core matrix:
-//   plane[((r / 8) * KC + k / 8) * 64 + (r % 8) * 8 + k % 8],  KC = ceil(K / 8); rows / columns beyond R / K are zero.
-__global__ void split_planes_kernel(const float* __restrict__ X, int64_t ld, int R, int K, float scale, __half* __restrict__ hi,
-                                    __half* __restrict__ lo) {
-  const int KC = (K + 7) / 8, RP = (R + 7) / 8 * 8;
+// X [R, K] fp32 (row stride ld) -> fp16 planes hi / lo, stored tile by tile exactly as the MMA reads them from shared
+// memory, so that one 16 KB bulk copy delivers a k-block of a 128-row operand tile:
+//   tile (rb, kb) = rows rb*128.., k kb*32..  at byte ((rb * KB + kb) * 16384), KB = ceil(K / 32): [hi plane 8 KB][lo plane 8 KB],
+//   element (r, k) of a plane at ((r / 8) * 4 + k / 8) * 128 + (r % 8) * 16 + (k % 8) * 2   (core matrices: LBO 128, SBO 512).
+// Rows / columns beyond R / K are zero (R padded to 128, K to 32).
+__global__ void split_planes_kernel(const float* __restrict__ X, int64_t ld, int R, int K, float scale, uint8_t* __restrict__ planes) {
+  const int KB = (K + BK - 1) / BK, KC = KB * (BK / 8), RP = (R + BM - 1) / BM * BM;
   const int64_t total = (int64_t)RP * KC;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int kc = (int)(i % KC), r = (int)(i / KC);            // consecutive threads: consecutive 32-byte pieces of a row
@@ -162,15 +182,14 @@ __global__ void split_planes_kernel(const float* __restrict__ X, int64_t ld, int
     uint4 h, l;
     h.x = pack_hi_lo(v[0], v[1], scale, l.x); h.y = pack_hi_lo(v[2], v[3], scale, l.y);
     h.z = pack_hi_lo(v[4], v[5], scale, l.z); h.w = pack_hi_lo(v[6], v[7], scale, l.w);
-    const int64_t off = (((int64_t)(r >> 3) * KC + kc) * 64 + (r & 7) * 8);
-    *reinterpret_cast<uint4*>(hi + off) = h;
-    *reinterpret_cast<uint4*>(lo + off) = l;
+    const int64_t off = ((int64_t)(r >> 7) * KB + (kc >> 2)) * (2 * PS_PLANE) + ((r & 127) >> 3) * PS_SBO + (kc & 3) * PS_LBO + (r & 7) * 16;
+    *reinterpret_cast<uint4*>(planes + off) = h;
+    *reinterpret_cast<uint4*>(planes + off + PS_PLANE) = l;
   }
 }
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-tc16_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                 const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2, Params p) {
+tc16_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, Params p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
@@ -185,6 +204,10 @@ tc16_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   float* epi_scratch = reinterpret_cast<float*>(smem + OFF_SCRATCH);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // pre-split vocab-CE forward: no converters are needed, so the first 8 converter warps join the epilogue (16 warps,
+  // one 32-column chunk each) -- with 8 warps the exp / max / arg-max epilogue took 4.1 us per tile against 1.7 us of MMAs
+  const bool wide_epi = p.presplit && p.mode == 1;
+  const bool conv_as_epi = wide_epi && warp >= PROD_WARP0 && warp < PROD_WARP0 + EPI_WARPS;
   // a programmatically-launched successor (the persistent LSTM kernels) may start its prologue now; it still waits for
   // this grid to complete (griddepcontrol.wait) before it reads anything written here
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
@@ -196,6 +219,7 @@ tc16_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int nkb_total = (p.K + BK - 1) / BK;
   const int kb0 = blockIdx.z * p.kb_per_split;
   const int nkb = max(0, min(nkb_total, kb0 + p.kb_per_split) - kb0);
+  const int b_tile0 = p.b_row0 / BN;          // pre-split B planes: first row block of this launch's vocabulary chunk
 
   if (tid == 0) {
     for (int s = 0; s < MAX_STAGES; ++s) {
@@ -208,18 +232,14 @@ tc16_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full[a], 1);
-      mbar_init(&tmem_empty[a], EPI_WARPS);
+      mbar_init(&tmem_empty[a], wide_epi ? 2 * EPI_WARPS : EPI_WARPS);
     }
     mbar_init(a_full, 1);
     fence_barrier_init();
   }
-  if (warp == TMA_WARP && lane == 0) {
+  if (warp == TMA_WARP && lane == 0 && !p.presplit) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
-    if (p.presplit) {
-      tma_prefetch_desc(&tmA2);
-      tma_prefetch_desc(&tmB2);
-    }
   }
   const bool a_stat = p.presplit && nkb_total <= AS_MAX_KB && gridDim.z == 1;
   const int nstages = a_stat ? (p.mode == 1 ? AS_STAGES_NOSCRATCH : AS_STAGES) : (p.presplit ? PS_STAGES : STAGES);
@@ -234,38 +254,41 @@ tc16_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   if (warp == TMA_WARP) {
     // ===== TMA producer: raw fp32 k-blocks into the landing ring =====
-    if (lane == 0 && a_stat) {
+    if (DVAE_TC16_FLAG(16)) {
+      // probes only: no operand traffic at all
+    } else if (lane == 0 && a_stat) {
       // A rows once (all k-blocks, both planes), then only B tiles through the ring
-      mbar_expect_tx(a_full, (uint32_t)nkb * 2 * PS_PLANE);
-      for (int kb = 0; kb < nkb; ++kb) {
-        tma_load_3d(smem_u + kb * 2 * PS_PLANE, &tmA, 0, kb * (BK / 8), m0 / 8, a_full);
-        tma_load_3d(smem_u + kb * 2 * PS_PLANE + PS_PLANE, &tmA2, 0, kb * (BK / 8), m0 / 8, a_full);
-      }
+      const uint8_t* a_tiles = reinterpret_cast<const uint8_t*>(p.a_planes) + (int64_t)blockIdx.x * nkb_total * PS_TILE;
+      const uint8_t* b_planes = reinterpret_cast<const uint8_t*>(p.b_planes);
+      mbar_expect_tx(a_full, (uint32_t)nkb * PS_TILE);
+      for (int kb = 0; kb < nkb; ++kb) bulk_load(smem_u + kb * PS_TILE, a_tiles + (int64_t)kb * PS_TILE, PS_TILE, a_full);
       int stage = 0, phase = 0;
       for (int nt = nt0; nt < nt1; ++nt) {
         for (int kb = 0; kb < nkb; ++kb) {
-          mbar_wait(&empty[stage], phase ^ 1);
+          DVAE_TC16_MARK(nt == nt0 + 1 && kb < 8, 32 + 2 * kb);
+          if (!DVAE_TC16_FLAG(8)) mbar_wait(&empty[stage], phase ^ 1);
+          else mbar_wait(&full[stage], phase ^ 1);      // probes only: free-running ring (previous fill of the slot has landed)
+          DVAE_TC16_MARK(nt == nt0 + 1 && kb < 8, 33 + 2 * kb);
           const uint32_t dst = smem_u + AS_A_BYTES + stage * AS_STAGE_BYTES;
           mbar_expect_tx(&full[stage], AS_STAGE_BYTES);
-          const int rb = (nt * BN + p.b_row0) / 8;
-          tma_load_3d(dst, &tmB, 0, kb * (BK / 8), rb, &full[stage]);
-          tma_load_3d(dst + PS_PLANE, &tmB2, 0, kb * (BK / 8), rb, &full[stage]);
+          bulk_load(dst, b_planes + ((int64_t)(nt + b_tile0) * nkb_total + kb) * PS_TILE, PS_TILE, &full[stage]);
           if (++stage == nstages) { stage = 0; phase ^= 1; }
         }
       }
+      if (DVAE_TC16_FLAG(8))                            // probes only: nothing may still be in flight at exit
+        for (int s2 = 0; s2 < nstages; ++s2) mbar_wait(&full[s2], s2 < stage ? phase : phase ^ 1);
     } else if (lane == 0 && p.presplit) {
-      // operand planes straight into the operand ring: 4 x 8 KB dense tiles per k-block
+      // operand planes straight into the operand ring: one 16 KB tile k-block [hi, lo] per operand
+      const uint8_t* a_tiles = reinterpret_cast<const uint8_t*>(p.a_planes) + (int64_t)blockIdx.x * nkb_total * PS_TILE;
+      const uint8_t* b_planes = reinterpret_cast<const uint8_t*>(p.b_planes);
       int stage = 0, phase = 0;
       for (int nt = nt0; nt < nt1; ++nt) {
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
           const uint32_t dst = smem_u + stage * PS_STAGE_BYTES;
           mbar_expect_tx(&full[stage], PS_STAGE_BYTES);
-          const int kc0 = (kb0 + kb) * (BK / 8), ra = m0 / 8, rb = (nt * BN + p.b_row0) / 8;
-          tma_load_3d(dst, &tmA, 0, kc0, ra, &full[stage]);
-          tma_load_3d(dst + PS_PLANE, &tmA2, 0, kc0, ra, &full[stage]);
-          tma_load_3d(dst + 2 * PS_PLANE, &tmB, 0, kc0, rb, &full[stage]);
-          tma_load_3d(dst + 3 * PS_PLANE, &tmB2, 0, kc0, rb, &full[stage]);
+          bulk_load(dst, a_tiles + (int64_t)(kb0 + kb) * PS_TILE, PS_TILE, &full[stage]);
+          bulk_load(dst + PS_TILE, b_planes + ((int64_t)(nt + b_tile0) * nkb_total + kb0 + kb) * PS_TILE, PS_TILE, &full[stage]);
           if (++stage == PS_STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -285,17 +308,16 @@ tc16_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
       }
     }
-  } else if (warp >= PROD_WARP0 && warp < EPI2_WARP0) {
+  } else if (warp >= PROD_WARP0 && warp < EPI2_WARP0 && !conv_as_epi) {
     // ===== converters: landed fp32 tile -> (scale, split) -> fp16 operand planes =====
     const int ptid = tid - PROD_WARP0 * 32;
     const float sa = scale_from_amax(p.a_amax, p.a_scale), sb = scale_from_amax(p.b_amax, p.b_scale);
     const int n_items = p.presplit ? 0 : (nt1 - nt0) * nkb;
     int stage = 0, phase = 0, rs = 0, rphase = 0;
     for (int it = 0; it < n_items; ++it) {
-      const bool mark = ptid == 0 && it == 12;
-      if (mark) DBG16(2);
+      DVAE_TC16_MARK(ptid == 0 && it == 12, 2);
       mbar_wait(&raw_full[rs], rphase);
-      if (mark) DBG16(3);
+      DVAE_TC16_MARK(ptid == 0 && it == 12, 3);
       float va[8], vb[8];
       const uint32_t raw = smem_u + OFF_RAW + rs * RAW_BYTES;
       load_tile(raw, p.a_mn, ptid, va);
@@ -304,81 +326,105 @@ tc16_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const uint32_t st = smem_u + stage * STAGE_BYTES;
       store_tile(st, p.a_mn, ptid, sa, va);
       store_tile(st + 2 * PLANE, p.b_mn, ptid, sb, vb);
-      if (mark) DBG16(4);
+      DVAE_TC16_MARK(ptid == 0 && it == 12, 4);
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) {
         mbar_arrive(&full[stage]);
         mbar_arrive(&raw_empty[rs]);
       }
-      if (mark) DBG16(5);
-      if (ptid == 0 && it == 13) DBG16(6);
+      DVAE_TC16_MARK(ptid == 0 && it == 12, 5);
+      DVAE_TC16_MARK(ptid == 0 && it == 13, 6);
       if (++stage == STAGES) { stage = 0; phase ^= 1; }
       if (++rs == RAW_STAGES) { rs = 0; rphase ^= 1; }
     }
   } else if (warp == MMA_WARP) {
     // ===== MMA issuer =====
+    // ONE elected thread runs the whole loop, and the loop body is kept to a few dozen instructions: six 128x128x16
+    // MMAs are ~390 cycles of tensor-pipe work, and a single thread issues dependent scalar instructions at one per
+    // 4-6 cycles -- a 145-instruction body (per-k-block elect/reconverge, descriptor re-derivation, probe marks) made
+    // the issuing thread, not the tensor pipe or operand delivery, the limiter (~820 cycles per k-block).
     constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);   // f16 x f16 -> f32
-    int stage = 0, phase = 0, tile = 0;
-    if (a_stat && nkb > 0) mbar_wait(a_full, 0);
-    for (int nt = nt0; nt < nt1 && nkb > 0; ++nt, ++tile) {
-      const int acc = tile & 1;
-      if (tile >= 2) {
-        mbar_wait(&tmem_empty[acc], ((tile >> 1) - 1) & 1);
-        tc_fence_after();
-      }
-      const uint32_t d1 = tmem_base + acc * 256, d2 = d1 + 128;
-      for (int kb = 0; kb < nkb; ++kb) {
-        if (lane == 0 && tile == 0 && kb == 12) DBG16(8);
-        if (lane == 0 && tile == 1 && kb < 4) DBG16(20 + 2 * kb);
-        mbar_wait(&full[stage], phase);
-        if (lane == 0 && tile == 1 && kb < 4) DBG16(21 + 2 * kb);
-        if (lane == 0 && tile == 0 && kb == 12) DBG16(9);
-        if (lane == 0 && tile == 0 && kb == 13) DBG16(11);
-        // no tcgen05.fence here: the operands arrive through the async proxy (TMA) or behind the converters'
-        // fence.proxy.async, and the mbarrier wait orders them; a tcgen05.fence::after_thread_sync per k-block makes the
-        // issuing thread wait for the MMAs already in flight (0.45 us instead of 0.2 us per k-block)
-        if (elect_one()) {
-          const uint32_t lbo = p.presplit ? PS_LBO : T_LBO, sbo = p.presplit ? PS_SBO : T_SBO;
-          // operand bases: ring stage [A_hi, A_lo, B_hi, B_lo], or stationary A (k-block kb) + ring stage [B_hi, B_lo]
-          const uint32_t sa = a_stat ? smem_u + kb * 2 * PS_PLANE : smem_u + stage * stage_bytes;
-          const uint32_t sb = a_stat ? smem_u + AS_A_BYTES + stage * AS_STAGE_BYTES : sa + 2 * plane_bytes;
-          const uint64_t ahi = make_smem_desc(sa, lbo, sbo, 0), alo = make_smem_desc(sa + plane_bytes, lbo, sbo, 0);
-          const uint64_t bhi = make_smem_desc(sb, lbo, sbo, 0), blo = make_smem_desc(sb + plane_bytes, lbo, sbo, 0);
-#pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            const uint64_t adv = (uint64_t)(k * 2 * lbo >> 4);
-            const uint32_t accum = (kb | k) ? 1u : 0u;
-            if (p.dbg_skip_epilogue == 2) continue;        // probes only: operand delivery in isolation
-            mma_f16(d1, ahi + adv, bhi + adv, idesc, accum);
-            mma_f16(d2, ahi + adv, blo + adv, idesc, accum);
-            mma_f16(d2, alo + adv, bhi + adv, idesc, 1u);
-          }
-          tc_commit(&empty[stage]);
-          if (kb == nkb - 1) tc_commit(&tmem_full[acc]);
+    if (elect_one() && nkb > 0) {
+      if (a_stat && !(DVAE_TC16_FLAG(16))) mbar_wait(a_full, 0);
+      const uint32_t lbo = p.presplit ? PS_LBO : T_LBO, sbo = p.presplit ? PS_SBO : T_SBO;
+      // shared-memory descriptor = constant high word | (LBO field | address >> 4): only the 14-bit address field moves
+      const uint32_t d_hi = ((sbo >> 4) & 0x3FFF) | (1u << 14);                 // SBO, descriptor version, no swizzle
+      const uint32_t d_lo = ((lbo >> 4) & 0x3FFF) << 16;
+      const uint32_t kstep16 = (2 * lbo) >> 4, plane16 = plane_bytes >> 4, stage16 = stage_bytes >> 4;
+      const uint32_t base16 = smem_u >> 4;
+      // operand bases: ring stage [A_hi, A_lo, B_hi, B_lo], or stationary A (k-block kb) + ring stage [B_hi, B_lo]
+      const uint32_t ring16 = a_stat ? base16 + (AS_A_BYTES >> 4) : base16;
+      const uint32_t a_kb16 = a_stat ? (2 * PS_PLANE) >> 4 : 0;
+      const uint32_t b_off16 = a_stat ? 0 : 2 * plane16;
+      auto desc = [&](uint32_t addr16) { return ((uint64_t)d_hi << 32) | (uint64_t)(d_lo | (addr16 & 0x3FFF)); };
+      int stage = 0, phase = 0;
+      uint32_t st16 = ring16;
+      for (int tile = 0; tile < nt1 - nt0; ++tile) {
+        const int acc = tile & 1;
+        if (tile >= 2) {
+          mbar_wait(&tmem_empty[acc], ((tile >> 1) - 1) & 1);
+          tc_fence_after();
         }
-        __syncwarp();
-        if (lane == 0 && tile == 0 && kb == 12) DBG16(10);
-        if (++stage == nstages) { stage = 0; phase ^= 1; }
+        const uint32_t d1 = tmem_base + acc * 256, d2 = d1 + 128;
+        uint32_t a16 = a_stat ? base16 : 0;
+        for (int kb = 0; kb < nkb; ++kb) {
+          DVAE_TC16_MARK(tile == 1 && kb < 8, 48 + 2 * kb);
+          // no tcgen05.fence here: the operands arrive through the async proxy (TMA) or behind the converters'
+          // fence.proxy.async, and the mbarrier wait orders them
+          if (!DVAE_TC16_FLAG(4)) mbar_wait(&full[stage], phase);
+          DVAE_TC16_MARK(tile == 1 && kb < 8, 49 + 2 * kb);
+          const uint32_t sa16 = a_stat ? a16 : st16, sb16 = st16 + b_off16;
+          if (!DVAE_TC16_FLAG(2)) {
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k) {
+              const uint32_t adv = k * kstep16;
+              const uint32_t accum = (kb | k) ? 1u : 0u;
+              mma_f16(d1, desc(sa16 + adv), desc(sb16 + adv), idesc, accum);
+              mma_f16(d2, desc(sa16 + adv), desc(sb16 + plane16 + adv), idesc, accum);
+              mma_f16(d2, desc(sa16 + plane16 + adv), desc(sb16 + adv), idesc, 1u);
+            }
+          }
+          if (!DVAE_TC16_FLAG(8)) tc_commit(&empty[stage]);
+          a16 += a_kb16;
+          st16 += stage16;
+          if (++stage == nstages) { stage = 0; phase ^= 1; st16 = ring16; }
+        }
+        tc_commit(&tmem_full[acc]);
       }
     }
+    __syncwarp();
   } else {
     // ===== epilogue: 8 warps = 4 TMEM lane quarters x 2 column halves of the tile =====
-    const int quarter = warp & 3, ehalf = warp >= EPI2_WARP0 ? 1 : 0, ew = ehalf * 4 + quarter;
+    // default: warps 0-3 own column chunks {0,1}, warps 22-25 chunks {2,3}.  wide (16 warps): one chunk per warp --
+    // warps 0-3 chunk 0, 6-9 chunk 1, 22-25 chunk 2, 10-13 chunk 3 (any 4 consecutive warps cover the 4 TMEM lane quarters)
+    const int quarter = warp & 3, ehalf = warp >= EPI2_WARP0 ? 1 : 0;
+    const int c_lo = !wide_epi ? 2 * ehalf : (conv_as_epi ? 1 + 2 * ((warp - PROD_WARP0) >> 2) : 2 * ehalf);
+    const int c_hi = wide_epi ? c_lo + 1 : c_lo + 2;
+    const int ew = wide_epi ? c_lo * 4 + quarter : ehalf * 4 + quarter;      // 0..15 | 0..7
     const int row = m0 + quarter * 32 + lane;      // output row owned by this thread (TMEM lane)
     const bool row_ok = row < p.M;
     const float oscale = p.alpha * (p.alpha_dev ? *p.alpha_dev : 1.f) /
                          (scale_from_amax(p.a_amax, p.a_scale) * scale_from_amax(p.b_amax, p.b_scale));
     // per-row state of the fused vocabulary epilogues
-    float rm = -INFINITY, rs = 0.f, rt = 0.f, rav = -INFINITY, row_lse = 0.f, row_scale = 0.f;
+    float rm = -INFINITY, rs = 0.f, rt = 0.f, rav = -INFINITY, row_lse = 0.f, row_nlse2 = 0.f, row_scale = 0.f;
     int rai = 0x7fffffff, tgt = -1;
     if (p.mode != 0 && row_ok) {
       const int b = row % p.B, tpos = row / p.B + 1;
       if (p.targets) tgt = (int)p.targets[(int64_t)b * p.tgt_stride_b + tpos];
       if (p.mode == 2) {
         row_lse = p.lse[row];
+        row_nlse2 = -row_lse * kLog2e;
         row_scale = (tpos < p.lengths[b]) ? (p.grad_scale ? p.grad_scale[0] : 1.f) / (float)p.B : 0.f;
         tgt -= p.v0;
+      }
+    }
+    float bias_next[2] = {0.f, 0.f};      // this warp's bias values of the next tile (vocabulary modes)
+    if (p.mode != 0 && nkb > 0) {
+#pragma unroll
+      for (int h2 = 0; h2 < 2; ++h2) {
+        const int col = nt0 * BN + (c_lo + h2) * 32 + lane;
+        bias_next[h2] = (nt0 < nt1 && h2 < c_hi - c_lo && col < p.N) ? __ldg(p.bias + col) : 0.f;
       }
     }
     int tile = 0;
@@ -387,21 +433,27 @@ tc16_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_wait(&tmem_full[acc], (tile >> 1) & 1);
       tc_fence_after();
       if (tid == 0 && tile < 4) DBG16(14 + 2 * tile);
+      DVAE_TC16_MARK(tid == 0 && tile == 2, 96);
       // this warp's 64 bias values (vocabulary modes) -> shared memory: broadcast reads instead of 64 global loads
-      float* sbias = reinterpret_cast<float*>(smem + OFF_BIAS) + ew * 64;
+      float* sbias = reinterpret_cast<float*>(smem + OFF_BIAS) + (wide_epi ? ew * 32 : ew * 64);
       if (p.mode != 0) {
         __syncwarp();
 #pragma unroll
-        for (int h2 = 0; h2 < 2; ++h2) {
-          const int col = n0 + ehalf * 64 + h2 * 32 + lane;
-          sbias[h2 * 32 + lane] = col < p.N ? __ldg(p.bias + col) : 0.f;
-        }
+        for (int h2 = 0; h2 < 2; ++h2)
+          if (h2 < c_hi - c_lo) sbias[h2 * 32 + lane] = bias_next[h2];
         __syncwarp();
+        // the next tile's bias values are fetched now: their global-load latency hides behind this tile's epilogue
+#pragma unroll
+        for (int h2 = 0; h2 < 2; ++h2) {
+          const int col = n0 + BN + (c_lo + h2) * 32 + lane;
+          bias_next[h2] = (nt + 1 < nt1 && h2 < c_hi - c_lo && col < p.N) ? __ldg(p.bias + col) : 0.f;
+        }
       }
+      DVAE_TC16_MARK(tid == 0 && tile == 2, 97);
 #pragma unroll 1
-      for (int c = 2 * ehalf; c < 2 * ehalf + 2; ++c) {
+      for (int c = c_lo; c < c_hi; ++c) {
         const int col0 = n0 + c * 32;
-        if (col0 >= p.N || p.dbg_skip_epilogue) continue;                       // warp-uniform (probes: 1 = no epilogue, 2 = no MMAs either)
+        if (col0 >= p.N || DVAE_TC16_FLAG(~0)) continue;                        // warp-uniform (probe builds: any switch skips the epilogue)
         const uint32_t ta = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * 256 + c * 32;
         if (p.mode != 1) {
           // modes 0 / 2 store a [32 rows x 32 cols] chunk: transpose it through padded shared memory so each
@@ -418,7 +470,7 @@ tc16_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               if (p.mode == 2) {
                 const int col = col0 + hh * 16 + j;
                 x = (row_scale == 0.f || col >= p.N) ? 0.f
-                    : (__expf(x + sbias[(c & 1) * 32 + hh * 16 + j] - row_lse) - (col == tgt ? 1.f : 0.f)) * row_scale;
+                    : (ex2_ftz(fmaf(x + sbias[(c - c_lo) * 32 + hh * 16 + j], kLog2e, row_nlse2)) - (col == tgt ? 1.f : 0.f)) * row_scale;
               }
               sts32(sc + (lane * 33 + hh * 16 + j) * 4, x);
             }
@@ -482,16 +534,34 @@ tc16_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
         for (int hh = 0; hh < 2; ++hh) {
           float v[16], w[16];
+          DVAE_TC16_MARK(tid == 0 && tile == 2, 98 + 3 * hh);
           tmem_ld16(ta + hh * 16, v);
           tmem_ld16(ta + 128 + hh * 16, w);
+          DVAE_TC16_MARK(tid == 0 && tile == 2, 99 + 3 * hh);
           if (!row_ok) continue;
           // 16 logits of this row: everything below is a tree or independent per element (the serial running-max /
           // arg-max / sum chains of the obvious loop made this epilogue, not the MMAs, the kernel's critical path)
           const int base = col0 + hh * 16;
           float x[16], xs[16];
+          {
+            // bias: four 16-byte shared loads (explicit shared-space: through the generic `sbias` pointer these were
+            // sixteen predicated generic LD.E, each feeding its own FFMA)
+            const uint32_t ba = smem_u + OFF_BIAS + ((wide_epi ? ew * 32 : ew * 64) + (c - c_lo) * 32 + hh * 16) * 4;
+            float bv[16];
 #pragma unroll
-          for (int j = 0; j < 16; ++j)
-            x[j] = base + j < p.N ? fmaf(w[j], kLoInv, v[j]) * oscale + sbias[(c & 1) * 32 + hh * 16 + j] : -INFINITY;
+            for (int q = 0; q < 4; ++q) {
+              const uint4 t = lds128(ba + q * 16);
+              bv[4 * q] = __uint_as_float(t.x); bv[4 * q + 1] = __uint_as_float(t.y);
+              bv[4 * q + 2] = __uint_as_float(t.z); bv[4 * q + 3] = __uint_as_float(t.w);
+            }
+#pragma unroll
+            for (int j = 0; j < 16; ++j) x[j] = fmaf(fmaf(w[j], kLoInv, v[j]), oscale, bv[j]);
+            if (base + 16 > p.N) {                           // last, partial vocabulary tile only (warp-uniform)
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                if (base + j >= p.N) x[j] = -INFINITY;
+            }
+          }
           if (sample) {
 #pragma unroll
             for (int j4 = 0; j4 < 16; j4 += 4) {
@@ -530,11 +600,13 @@ tc16_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             for (int j = 0; j < 4; ++j) m4[j] = fmaxf(m8[2 * j], m8[2 * j + 1]);
             tmax = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
           }
-          if (tmax > rm) { rs *= __expf(rm - tmax); rm = tmax; }
+          if (tmax > rm) { rs *= ex2_ftz((rm - tmax) * kLog2e); rm = tmax; }
+          const float nrm2 = -rm * kLog2e;
           float e8[8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) e8[j] = __expf(x[2 * j] - rm) + __expf(x[2 * j + 1] - rm);
+          for (int j = 0; j < 8; ++j) e8[j] = ex2_ftz(fmaf(x[2 * j], kLog2e, nrm2)) + ex2_ftz(fmaf(x[2 * j + 1], kLog2e, nrm2));
           rs += ((e8[0] + e8[1]) + (e8[2] + e8[3])) + ((e8[4] + e8[5]) + (e8[6] + e8[7]));
+          DVAE_TC16_MARK(tid == 0 && tile == 2, 100 + 3 * hh);
         }
       }
       tc_fence_before();
@@ -542,8 +614,8 @@ tc16_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
       if (tid == 0 && tile < 4) DBG16(15 + 2 * tile);
     }
-    if (p.mode == 1 && row_ok) {      // the two column halves are separate vocabulary splits for the finalize kernel
-      const int64_t sp = (int64_t)blockIdx.y * 2 + ehalf;
+    if (p.mode == 1 && row_ok) {      // every epilogue warp set is a separate vocabulary split for the finalize kernel
+      const int64_t sp = wide_epi ? (int64_t)blockIdx.y * 4 + c_lo : (int64_t)blockIdx.y * 2 + ehalf;
       *reinterpret_cast<float4*>(p.part + (sp * p.M + row) * 4) = make_float4(rm, rs, rt, rav);
       p.part_idx[sp * p.M + row] = rai;
     }
@@ -602,22 +674,8 @@ static int make_map(CUtensorMap* m, const float* base, int64_t ld, int mn_major,
 
 // 3-D map over one fp16 plane in the blocked layout of split_planes: dim0 = one core matrix (64 elements, 128 B),
 // dim1 = k chunks, dim2 = 8-row groups; a box of 64 x 4 x 16 is a dense UMMA-ready 128 x 32 operand tile
-static int make_plane_map(CUtensorMap* m, const void* plane, int rows, int K) {
-  EncodeTiledFn fn = encode_fn();
-  DVAE_REQUIRE(fn != nullptr, "tc16_gemm: cuTensorMapEncodeTiled is not available from the driver");
-  const int KC = ceil_div(K, 8), RG = ceil_div(rows, 8);
-  cuuint64_t dims[3] = {64, (cuuint64_t)KC, (cuuint64_t)RG};
-  cuuint64_t strides[2] = {128, (cuuint64_t)KC * 128};
-  cuuint32_t box[3] = {64, BK / 8, BM / 8};
-  cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(plane), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  DVAE_REQUIRE(r == CUDA_SUCCESS, "tc16_gemm: plane tensor map failed (%d) rows=%d K=%d", (int)r, rows, K);
-  return DVAE_OK;
-}
-
-int64_t plane_floats(int R, int K) { return (int64_t)ceil_div(R, 8) * 8 * ceil_div(K, 8) * 8; }
+// floats occupied by both fp16 planes of X [R, K] in the tile-blocked layout (R padded to 128, K to 32)
+int64_t plane_floats(int R, int K) { return (int64_t)ceil_div(R, BM) * BM * ceil_div(K, BK) * BK; }
 
 bool presplit_enabled() {
   const char* e = getenv("DVAE_VOCAB_PRESPLIT");
@@ -626,13 +684,10 @@ bool presplit_enabled() {
 
 int split_planes(const float* X, int64_t ld, int R, int K, float scale, void* planes, cudaStream_t st) {
   DVAE_REQUIRE(X && planes && R > 0 && K > 0, "tc16 split_planes: bad argument");
-  const int64_t n = plane_floats(R, K);                 // fp16 elements per plane = floats of both planes / ... (2 B each)
-  __half* hi = reinterpret_cast<__half*>(planes);
-  __half* lo = hi + n;
-  const int64_t work = (int64_t)ceil_div(R, 8) * 8 * ceil_div(K, 8);
+  const int64_t work = (int64_t)ceil_div(R, BM) * BM * ceil_div(K, BK) * (BK / 8);
   int blocks = ceil_div(work, 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
-  split_planes_kernel<<<blocks, 256, 0, st>>>(X, ld, R, K, scale, hi, lo);
+  split_planes_kernel<<<blocks, 256, 0, st>>>(X, ld, R, K, scale, reinterpret_cast<uint8_t*>(planes));
   DVAE_LAUNCH_CHECK();
   return DVAE_OK;
 }
@@ -643,22 +698,16 @@ static int launch(const Params& p, dim3 grid, cudaStream_t st) {
     DVAE_CUDA(cudaFuncSetAttribute(tc16_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     ready = true;
   }
-  CUtensorMap ma, mb, ma2, mb2;
-  memset(&ma2, 0, sizeof(ma2));
-  memset(&mb2, 0, sizeof(mb2));
+  CUtensorMap ma, mb;
   int rc;
-  if (p.presplit) {
-    const __half* ah = reinterpret_cast<const __half*>(p.a_planes);
-    const __half* bh = reinterpret_cast<const __half*>(p.b_planes);
-    if ((rc = make_plane_map(&ma, ah, p.a_rows, p.K))) return rc;
-    if ((rc = make_plane_map(&ma2, ah + plane_floats(p.a_rows, p.K), p.a_rows, p.K))) return rc;
-    if ((rc = make_plane_map(&mb, bh, p.b_rows, p.K))) return rc;
-    if ((rc = make_plane_map(&mb2, bh + plane_floats(p.b_rows, p.K), p.b_rows, p.K))) return rc;
+  if (p.presplit) {          // tile-blocked fp16 planes are fetched with plain bulk copies: no tensor maps
+    memset(&ma, 0, sizeof(ma));
+    memset(&mb, 0, sizeof(mb));
   } else {
     if ((rc = make_map(&ma, p.A, p.lda, p.a_mn, p.M, p.K))) return rc;
     if ((rc = make_map(&mb, p.Bm, p.ldb, p.b_mn, p.N, p.K))) return rc;
   }
-  tc16_gemm_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(ma, mb, ma2, mb2, p);
+  tc16_gemm_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(ma, mb, p);
   DVAE_LAUNCH_CHECK();
   return DVAE_OK;
 }
@@ -727,6 +776,7 @@ int softmax_grad(const float* h, int64_t ldh, int N, int B, int H, int V, int v0
                  const int64_t* targets, int64_t tgt_stride_b, const int64_t* lengths, const float* lse,
                  const float* grad_scale, float* P, int64_t ldp, const void* h_planes, const void* w_planes, cudaStream_t st) {
   Params p = {};
+  DVAE_REQUIRE(!(h_planes && w_planes) || v0 % BN == 0, "tc16 softmax_grad: pre-split chunks must start on a %d-row block (v0=%d)", BN, v0);
   if (h_planes && w_planes) { p.presplit = 1; p.a_planes = h_planes; p.b_planes = w_planes; p.a_rows = N; p.b_rows = V; p.b_row0 = v0; }
   p.A = h; p.lda = ldh; p.Bm = w + (int64_t)v0 * H; p.ldb = H;
   // a run of vocabulary tiles per CTA so the epilogue of one tile overlaps the main loop of the next; ~one wave of CTAs

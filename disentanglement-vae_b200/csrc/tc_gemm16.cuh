@@ -26,7 +26,7 @@ struct Params {
   const uint64_t* gumbel_seed; uint32_t gumbel_salt;   // mode 1: when set, the arg-max is taken over logits + Gumbel noise
   // pre-split mode: the operands are fp16 (hi, lo) planes in global memory (split_planes), blocked by core matrix
   int presplit; int b_row0;     // b_row0: first B row of this call inside the B planes (a vocabulary chunk)
-  const void* a_planes; const void* b_planes; int a_rows, b_rows;      // hi plane first, lo plane right after it
+  const void* a_planes; const void* b_planes; int a_rows, b_rows;      // tile-blocked fp16 planes (split_planes)
   int dbg_skip_epilogue;     // probes only (DVAE_TC_SKIP_EPILOGUE=1): accumulators are released unread
   unsigned long long* dbg;   // optional: pipeline milestone timestamps (ns) of CTA (0,0,0), profiles/probes/tc16_timeline.py
 };

@@ -242,11 +242,11 @@ __global__ void __launch_bounds__(GCE::NT) vocab_p_kernel(PArgs p) {
 
 // per-(row, vocabulary split) partials: tensor-core kernel when the shape allows, fp32 SIMT otherwise
 // On return p.nsplit / p.part_idx describe the partials that were actually written (the fp16-split kernel's two
-// epilogue warp sets each emit their own split).
+// -- four with pre-split operands -- epilogue warp sets each emit their own split).
 static int ce_partials(CeArgs& p, cudaStream_t st) {
   if (!force_simt_gemm() && p.N >= 64 && p.V >= 128 && p.H >= 32 && tc16::supported(p.h, p.ldh, 0, p.w, p.H, 0, p.N, p.V, p.H)) {
     const int launched = p.nsplit;
-    p.nsplit = 2 * launched;
+    p.nsplit = (p.h_planes && p.w_planes ? 4 : 2) * launched;      // pre-split operands: 16 epilogue warps, 4 column chunks
     p.part_idx = reinterpret_cast<int*>(p.part + (int64_t)p.nsplit * p.N * 4);
     return tc16::ce_partials(p.h, p.ldh, p.N, p.B, p.H, p.V, p.w, p.bias, p.targets, p.tgt_stride_b, p.lengths,
                              p.tiles_per_split, launched, p.part, p.part_idx, p.gumbel_seed, p.gumbel_salt, p.h_planes,
@@ -285,11 +285,11 @@ static int p_chunk(int N, int V) {
 
 using namespace dvae;
 
-// workspace layout (floats): [partials 2*ns*N*5 + 8][block sums][pad to 4][operand planes of h and w]
+// workspace layout (floats): [partials 4*ns*N*5 + 8][block sums][pad to 4][operand planes of h and w]
 static int64_t ce_part_floats(int N, int V) {
   int tps;
   int ns = ce_nsplit(N, V, &tps);
-  return (2LL * ns * N * 5 + 8 + kFinMaxBlocks + 3) / 4 * 4;    // x2: the fp16-split kernel writes two partials per (row, split)
+  return (4LL * ns * N * 5 + 8 + kFinMaxBlocks + 3) / 4 * 4;    // x4: the fp16-split kernel writes up to four partials per (row, split)
 }
 extern "C" int64_t dvae_vocab_ce_ws_floats(int N, int V, int H) {
   return ce_part_floats(N, V) + tc16::plane_floats(N, H) + tc16::plane_floats(V, H);

@@ -5,7 +5,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)
 sys.path.insert(0, ROOT)
 import torch
 dvae = importlib.import_module("disentanglement-vae_b200"); L = dvae._lib; lib = L.load()
-dbg = torch.zeros(32, dtype=torch.int64, device="cuda")
+dbg = torch.zeros(128, dtype=torch.int64, device="cuda")
 os.environ["DVAE_TC_DBG"] = hex(dbg.data_ptr())
 x = torch.randn(4096, 4096, device="cuda")
 for _ in range(200): x @ x
@@ -25,5 +25,11 @@ t = dbg.cpu().tolist()
 print("entry +0.00 us; exit +%.2f us" % ((t[1] - t[0]) / 1e3))
 for k in range(4):
     print(f"  tile {k}: accumulators ready +{(t[14 + 2 * k] - t[0]) / 1e3:6.2f} us, epilogue done +{(t[15 + 2 * k] - t[0]) / 1e3:6.2f} us")
-for k in range(4):
-    print(f"  mma warp, tile 1 k-block {k}: waits from +{(t[20 + 2 * k] - t[0]) / 1e3:6.2f} us, operands ready +{(t[21 + 2 * k] - t[0]) / 1e3:6.2f} us")
+if t[96]:       # probe build (-DDVAE_TC16_PROBES): inside warp 0's epilogue of tile 2, and the per-k-block marks of tile 1
+    names = ["accumulators seen", "bias staged", "hh0: before tmem loads", "hh0: loads done", "hh0: math done", "hh1: before tmem loads",
+             "hh1: loads done", "hh1: math done"]
+    for i, n in enumerate(names):
+        print(f"  tile 2 epilogue (warp 0): {n:24s} +{(t[96 + i] - t[96]) / 1e3:5.2f} us")
+    for k in range(8):
+        print(f"  tile 1 k-block {k}: producer waits for the slot from +{(t[32 + 2 * k] - t[0]) / 1e3:6.2f}, issues TMA +{(t[33 + 2 * k] - t[0]) / 1e3:6.2f} | "
+              f"mma warp waits from +{(t[48 + 2 * k] - t[0]) / 1e3:6.2f}, operands ready +{(t[49 + 2 * k] - t[0]) / 1e3:6.2f} us")

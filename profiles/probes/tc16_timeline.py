@@ -4,7 +4,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)
 sys.path.insert(0, ROOT)
 import torch
 dvae = importlib.import_module("disentanglement-vae_b200"); L = dvae._lib; lib = L.load()
-dbg = torch.zeros(32, dtype=torch.int64, device="cuda")
+dbg = torch.zeros(128, dtype=torch.int64, device="cuda")
 os.environ["DVAE_TC_DBG"] = hex(dbg.data_ptr())
 x = torch.randn(4096, 4096, device="cuda")
 for _ in range(200): x @ x
