@@ -31,37 +31,40 @@ namespace tc16 {
 
 using namespace tc;
 
-constexpr int BM = 128, BN = 128, BK = 32, STAGES = 3 /* operand-plane ring */, RAW_STAGES = 2 /* TMA landing ring */;
-constexpr int T_LBO = 160, T_SBO = 4 * T_LBO;      // chunk(row, kc) at (row >> 3) * 640 + kc * 160 + (row & 7) * 16:
-                                                   // core matrices (8 rows x 16 B) 160 B apart along K so that the 16
-                                                   // chunks a warp stores per instruction spread over all banks
-constexpr int PLANE = (BM / 8) * T_SBO;            // one fp16 plane of a 128 x 32 tile: 10 KB
-constexpr int STAGE_BYTES = 4 * PLANE;             // A_hi, A_lo, B_hi, B_lo
-constexpr int RAW_TILE = BM * BK * 4;              // one landed fp32 tile: 16 KB
-constexpr int RAW_BYTES = 2 * RAW_TILE;            // A, B
+constexpr int BM = 128, BN = 128, BK = 32;
+// Operand ring: 6 stages of 32 KB.  A stage is filled by TMA with the raw fp32 k-block [A 128 x 32 | B 128 x 32] and then
+// converted IN PLACE by the converter warps into the four fp16 planes the MMAs read, [A_hi | A_lo | B_hi | B_lo], each
+// 128 x 32 in the dense core-matrix layout (8 rows x 16 B matrices, LBO 128 B along K, SBO 512 B along rows).  fp32 in,
+// hi + lo out: same bytes, so landing buffers and operand planes share one ring and all of it hides TMA latency
+// (a separate 2-stage landing ring + 3-stage padded plane ring delivered a k-block every 0.73 us; TMA latency under load
+// is ~1.3 us, so the stages in flight, not the converters or the MMAs, set the pace).
+constexpr int STAGES = 6, MAX_STAGES = 6;
+constexpr int RAW_TILE = BM * BK * 4;              // one landed fp32 tile: 16 KB  (= hi + lo fp16 planes of the same tile)
+constexpr int STAGE_BYTES = 2 * RAW_TILE;          // A, B
+constexpr int PS_PLANE = BM * BK * 2, PS_TILE = 2 * PS_PLANE;      // one fp16 plane: 8 KB; [hi, lo] of one operand tile: 16 KB
+constexpr int PS_LBO = 128, PS_SBO = 512;
+static_assert(PS_TILE == RAW_TILE, "in-place conversion: fp16 hi + lo planes occupy exactly the landed fp32 tile");
 constexpr int EPI_WARPS = 8, MMA_WARP = 4, TMA_WARP = 5, PROD_WARP0 = 6, PROD_WARPS = 16, EPI2_WARP0 = PROD_WARP0 + PROD_WARPS;
 // warps 0-3: epilogue of tile columns 0-63; warps 22-25 (22 % 4 == 2: TMEM lane quarter = warp & 3): columns 64-127
 constexpr int NUM_THREADS = (EPI2_WARP0 + 4) * 32;               // 832: <= 78 registers per thread
-constexpr int EPI_SCRATCH_BYTES = 8 * 32 * 33 * 4;
-// [operand rings][epilogue transpose scratch][bias tiles][barriers]: the scratch directly follows the operand region so
-// that the A-stationary ring can grow into it when the epilogue does not use it (mode 1)
-constexpr int OFF_RAW = STAGES * STAGE_BYTES, OFF_OPER_END = OFF_RAW + RAW_STAGES * RAW_BYTES, OFF_SCRATCH = OFF_OPER_END;
-// Pre-split mode (operands already split into fp16 planes in global memory, blocked by core matrix): no landing ring and
-// no converters -- TMA delivers UMMA-ready dense tiles (core matrices 128 B apart) straight into a 5-stage operand ring.
-constexpr int PS_PLANE = BM * BK * 2, PS_TILE = 2 * PS_PLANE, PS_STAGE_BYTES = 2 * PS_TILE, PS_STAGES = 5, MAX_STAGES = 5;
-constexpr int PS_LBO = 128, PS_SBO = 512;
-// A-stationary variant (K <= 256, no split-K): the CTA's A rows (both planes, all k-blocks: 128 KB) are loaded once and
-// stay in shared memory for the CTA's whole run of N tiles; only B tiles stream through a 3-stage ring.  With 128 x 128
-// tiles and K = 256 the operand loads (256 KB per tile) otherwise make the kernel L2-bandwidth bound.
-constexpr int AS_MAX_KB = 8, AS_A_BYTES = AS_MAX_KB * 2 * PS_PLANE, AS_STAGE_BYTES = 2 * PS_PLANE;
-constexpr int AS_STAGES = 3, AS_STAGES_NOSCRATCH = 5;      // mode 1 has no transpose scratch: the ring grows into it
-static_assert(AS_A_BYTES + AS_STAGES * AS_STAGE_BYTES <= OFF_OPER_END, "A-stationary layout must fit in the operand region");
-static_assert(AS_STAGES_NOSCRATCH <= MAX_STAGES, "barrier arrays");
-static_assert(PS_STAGES * PS_STAGE_BYTES <= OFF_OPER_END, "pre-split ring must fit in the plane + landing rings");
-constexpr int OFF_BIAS = OFF_SCRATCH + EPI_SCRATCH_BYTES;          // per epilogue warp: the 64 bias values of its tile columns
+constexpr int CONV_BARRIER = 1;                                  // named barrier of the 512 converter threads
+constexpr int EPI_SCRATCH_BYTES = 8 * 32 * 32 * 4;               // per epilogue warp: a 32 x 32 fp32 transpose tile (XOR-swizzled)
+// Pre-split mode (operands already split into tile-blocked fp16 planes in global memory): no converters -- bulk copies
+// deliver MMA-ready stages [A tile | B tile] straight into the ring.
+// A-stationary variant (pre-split, K <= 256, no split-K): the CTA's A rows (both planes, all k-blocks: 128 KB) are loaded
+// once and stay in shared memory for the CTA's whole run of N tiles; only B tiles (16 KB per k-block) stream through a
+// 4-stage ring (6 stages in mode 1, whose epilogue needs no transpose scratch).
+constexpr int AS_MAX_KB = 8, AS_A_BYTES = AS_MAX_KB * PS_TILE, AS_STAGE_BYTES = PS_TILE;
+constexpr int AS_STAGES = 4, AS_STAGES_NOSCRATCH = 6;
+// [operand ring 192 KB][epilogue transpose scratch 32 KB][bias tiles 2 KB][barriers]
+constexpr int OFF_SCRATCH = STAGES * STAGE_BYTES;
+constexpr int OFF_BIAS = OFF_SCRATCH + EPI_SCRATCH_BYTES;          // per epilogue warp: the bias values of its tile columns
 constexpr int OFF_BAR = OFF_BIAS + 8 * 64 * 4;
-constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
+constexpr int SMEM_BYTES = OFF_BAR + 256;
+static_assert(AS_A_BYTES + AS_STAGES * AS_STAGE_BYTES <= OFF_SCRATCH, "A-stationary layout must fit in the operand ring");
 static_assert(AS_A_BYTES + AS_STAGES_NOSCRATCH * AS_STAGE_BYTES <= OFF_BIAS, "A-stationary mode-1 ring must end before the bias tiles");
+static_assert(AS_STAGES_NOSCRATCH <= MAX_STAGES && (3 * MAX_STAGES + 5) * 8 + 4 <= 256, "barrier area");
+static_assert(SMEM_BYTES <= 232448, "shared memory per CTA");
 constexpr int TMEM_COLS = 512;
 constexpr float kLoScale = 2048.f, kLoInv = 1.f / 2048.f;
 
@@ -110,53 +113,40 @@ __device__ __forceinline__ uint32_t pack_hi_lo(float x0, float x1, float s, uint
   return *reinterpret_cast<const uint32_t*>(&h);
 }
 
-// One landed k-block (128 rows x 32 k, fp32) of one operand -> 8 registers per converter thread (512 threads).
-//   K-major source: the tile is [128 rows][32 k]; piece p = ptid + 512*i (i < 2) is the float4 at row p >> 3, k 4*(p & 7):
-//     a warp reads 512 contiguous bytes per instruction (conflict-free).
-//   MN-major source: the tile is [32 k][128 rows]; thread = (row ptid & 127, k chunk ptid >> 7), 8 scalar reads with the
-//     warp's lanes on consecutive rows (conflict-free): the transposition happens in registers.
+// One landed k-block (128 rows x 32 k, fp32) of one operand -> 8 registers per converter thread (512 threads): thread
+// (row = ptid & 127, k chunk kc = ptid >> 7) owns k 8*kc .. 8*kc+7 of its row, i.e. exactly one 16-byte fp16 chunk of each plane.
+//   K-major source: the tile is [128 rows][32 k] (128-byte rows) landed with TMA's 128-byte swizzle: 16-byte piece c of row r
+//     sits at piece c ^ (r & 7), so the 8 lanes of a quarter warp (8 consecutive rows, same k) read 8 different bank groups.
+//   MN-major source: the tile is [32 k][128 rows], un-swizzled: 8 scalar reads with the warp's lanes on consecutive rows.
 __device__ __forceinline__ void load_tile(uint32_t raw, int mn_major, int ptid, float (&v)[8]) {
+  const int row = ptid & 127, kc = ptid >> 7;
   if (!mn_major) {
+    const uint32_t ra = raw + (uint32_t)row * 128, sw = row & 7;
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
-      const uint4 t = lds128(raw + (uint32_t)(ptid + 512 * i) * 16);
+      const uint4 t = lds128(ra + (((uint32_t)(2 * kc + i) ^ sw) << 4));
       v[4 * i] = __uint_as_float(t.x); v[4 * i + 1] = __uint_as_float(t.y);
       v[4 * i + 2] = __uint_as_float(t.z); v[4 * i + 3] = __uint_as_float(t.w);
     }
   } else {
-    const uint32_t src = raw + (uint32_t)(8 * (ptid >> 7)) * (BM * 4) + (uint32_t)(ptid & 127) * 4;
+    const uint32_t src = raw + (uint32_t)(8 * kc) * (BM * 4) + (uint32_t)row * 4;
 #pragma unroll
     for (int j = 0; j < 8; ++j) v[j] = lds32(src + j * (BM * 4));
   }
 }
 
-// scale, split into fp16 (hi, lo) and store into the stage's operand planes (hi plane at `plane_hi`, lo at + PLANE)
-__device__ __forceinline__ void store_tile(uint32_t plane_hi, int mn_major, int ptid, float s, const float (&v)[8]) {
-  if (!mn_major) {
-    const int odd = ptid & 1;
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      const int pc = ptid + 512 * i, row = pc >> 3, kc = (pc & 7) >> 1;
-      uint32_t lo0, lo1;
-      const uint32_t hi0 = pack_hi_lo(v[4 * i], v[4 * i + 1], s, lo0);
-      const uint32_t hi1 = pack_hi_lo(v[4 * i + 2], v[4 * i + 3], s, lo1);
-      // lanes (2j, 2j+1) hold k 0-3 / 4-7 of one 8-k chunk: the even lane assembles the hi chunk, the odd lane the lo chunk
-      const uint32_t r0 = __shfl_xor_sync(0xffffffffu, odd ? hi0 : lo0, 1);
-      const uint32_t r1 = __shfl_xor_sync(0xffffffffu, odd ? hi1 : lo1, 1);
-      const uint4 chunk = odd ? make_uint4(r0, r1, lo0, lo1) : make_uint4(hi0, hi1, r0, r1);
-      sts128(plane_hi + (odd ? PLANE : 0) + (uint32_t)(row >> 3) * T_SBO + (uint32_t)kc * T_LBO + (row & 7) * 16, chunk);
-    }
-  } else {
-    const int row = ptid & 127, kc = ptid >> 7;
-    const uint32_t base = plane_hi + (uint32_t)(row >> 3) * T_SBO + (uint32_t)kc * T_LBO + (row & 7) * 16;
-    uint4 hi, lo;
-    hi.x = pack_hi_lo(v[0], v[1], s, lo.x);
-    hi.y = pack_hi_lo(v[2], v[3], s, lo.y);
-    hi.z = pack_hi_lo(v[4], v[5], s, lo.z);
-    hi.w = pack_hi_lo(v[6], v[7], s, lo.w);
-    sts128(base, hi);
-    sts128(base + PLANE, lo);
-  }
+// scale, split into fp16 (hi, lo) and store this thread's chunk into the operand planes (hi at `tile`, lo at + PS_PLANE):
+// a quarter warp writes 128 contiguous bytes (8 rows of one core matrix)
+__device__ __forceinline__ void store_tile(uint32_t tile, int ptid, float s, const float (&v)[8]) {
+  const int row = ptid & 127, kc = ptid >> 7;
+  const uint32_t base = tile + (uint32_t)(row >> 3) * PS_SBO + (uint32_t)kc * PS_LBO + (row & 7) * 16;
+  uint4 hi, lo;
+  hi.x = pack_hi_lo(v[0], v[1], s, lo.x);
+  hi.y = pack_hi_lo(v[2], v[3], s, lo.y);
+  hi.z = pack_hi_lo(v[4], v[5], s, lo.z);
+  hi.w = pack_hi_lo(v[6], v[7], s, lo.w);
+  sts128(base, hi);
+  sts128(base + PS_PLANE, lo);
 }
 
 // contiguous global -> shared bulk copy (no tensor map), completion on an mbarrier
@@ -190,18 +180,15 @@ __global__ void split_planes_kernel(const float* __restrict__ X, int64_t ld, int
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 tc16_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, Params p) {
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  extern __shared__ __align__(1024) uint8_t smem[];      // 1024-byte aligned (checked below): TMA 128-byte swizzle atoms
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
-  uint64_t* full = bars;                       // [MAX_STAGES] converters (or TMA, pre-split mode) -> MMA
-  uint64_t* empty = bars + MAX_STAGES;         // [MAX_STAGES] MMA -> converters / TMA   (tcgen05.commit)
-  uint64_t* raw_full = bars + 2 * MAX_STAGES;  // [RAW_STAGES] TMA -> converters (transaction bytes)
-  uint64_t* raw_empty = raw_full + RAW_STAGES; // [RAW_STAGES] converters -> TMA (8 warp arrivals)
-  uint64_t* tmem_full = raw_empty + RAW_STAGES;  // [2] MMA -> epilogue
-  uint64_t* tmem_empty = tmem_full + 2;          // [2] epilogue -> MMA (4 warp arrivals)
+  uint64_t* full = bars;                       // [MAX_STAGES] converters (or bulk copies, pre-split mode) -> MMA
+  uint64_t* empty = bars + MAX_STAGES;         // [MAX_STAGES] MMA -> TMA   (tcgen05.commit)
+  uint64_t* raw_full = bars + 2 * MAX_STAGES;  // [MAX_STAGES] TMA -> converters (transaction bytes)
+  uint64_t* tmem_full = raw_full + MAX_STAGES;   // [2] MMA -> epilogue
+  uint64_t* tmem_empty = tmem_full + 2;          // [2] epilogue -> MMA (one arrival per epilogue warp)
   uint64_t* a_full = tmem_empty + 2;             // [1] A-stationary mode: all A k-blocks landed
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_full + 1);
-  float* epi_scratch = reinterpret_cast<float*>(smem + OFF_SCRATCH);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   // pre-split vocab-CE forward: no converters are needed, so the first 8 converter warps join the epilogue (16 warps,
@@ -222,13 +209,14 @@ tc16_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int b_tile0 = p.b_row0 / BN;          // pre-split B planes: first row block of this launch's vocabulary chunk
 
   if (tid == 0) {
+    if (smem_u32(smem) & 1023) {
+      printf("dvae tc16_gemm: dynamic shared memory base is not 1024-byte aligned\n");
+      __trap();
+    }
     for (int s = 0; s < MAX_STAGES; ++s) {
       mbar_init(&full[s], p.presplit ? 1 : PROD_WARPS);
       mbar_init(&empty[s], 1);
-    }
-    for (int s = 0; s < RAW_STAGES; ++s) {
       mbar_init(&raw_full[s], 1);
-      mbar_init(&raw_empty[s], PROD_WARPS);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full[a], 1);
@@ -242,9 +230,8 @@ tc16_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     tma_prefetch_desc(&tmB);
   }
   const bool a_stat = p.presplit && nkb_total <= AS_MAX_KB && gridDim.z == 1;
-  const int nstages = a_stat ? (p.mode == 1 ? AS_STAGES_NOSCRATCH : AS_STAGES) : (p.presplit ? PS_STAGES : STAGES);
-  const uint32_t stage_bytes = a_stat ? AS_STAGE_BYTES : (p.presplit ? PS_STAGE_BYTES : STAGE_BYTES);
-  const uint32_t plane_bytes = p.presplit ? PS_PLANE : PLANE;
+  const int nstages = a_stat ? (p.mode == 1 ? AS_STAGES_NOSCRATCH : AS_STAGES) : STAGES;
+  const uint32_t stage_bytes = a_stat ? AS_STAGE_BYTES : STAGE_BYTES;
   if (warp == MMA_WARP) tmem_alloc(tmem_slot, TMEM_COLS);
   tc_fence_before();
   __syncthreads();
@@ -285,58 +272,54 @@ tc16_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       for (int nt = nt0; nt < nt1; ++nt) {
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
-          const uint32_t dst = smem_u + stage * PS_STAGE_BYTES;
-          mbar_expect_tx(&full[stage], PS_STAGE_BYTES);
+          const uint32_t dst = smem_u + stage * STAGE_BYTES;
+          mbar_expect_tx(&full[stage], STAGE_BYTES);
           bulk_load(dst, a_tiles + (int64_t)(kb0 + kb) * PS_TILE, PS_TILE, &full[stage]);
           bulk_load(dst + PS_TILE, b_planes + ((int64_t)(nt + b_tile0) * nkb_total + kb0 + kb) * PS_TILE, PS_TILE, &full[stage]);
-          if (++stage == PS_STAGES) { stage = 0; phase ^= 1; }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     } else if (lane == 0) {
-      int rs = 0, rphase = 0;
+      // raw fp32 k-blocks [A | B] into the ring stage the MMAs have released
+      int stage = 0, phase = 0;
       for (int nt = nt0; nt < nt1; ++nt) {
         for (int kb = 0; kb < nkb; ++kb) {
-          mbar_wait(&raw_empty[rs], rphase ^ 1);
-          uint8_t* dst = smem + OFF_RAW + rs * RAW_BYTES;
-          mbar_expect_tx(&raw_full[rs], RAW_BYTES);
+          mbar_wait(&empty[stage], phase ^ 1);
+          uint8_t* dst = smem + stage * STAGE_BYTES;
+          mbar_expect_tx(&raw_full[stage], STAGE_BYTES);
           const int k0 = (kb0 + kb) * BK;
-          if (!p.a_mn) tma_load_2d(dst, &tmA, k0, m0, &raw_full[rs]);
-          else tma_load_2d(dst, &tmA, m0, k0, &raw_full[rs]);
-          if (!p.b_mn) tma_load_2d(dst + RAW_TILE, &tmB, k0, nt * BN, &raw_full[rs]);
-          else tma_load_2d(dst + RAW_TILE, &tmB, nt * BN, k0, &raw_full[rs]);
-          if (++rs == RAW_STAGES) { rs = 0; rphase ^= 1; }
+          if (!p.a_mn) tma_load_2d(dst, &tmA, k0, m0, &raw_full[stage]);
+          else tma_load_2d(dst, &tmA, m0, k0, &raw_full[stage]);
+          if (!p.b_mn) tma_load_2d(dst + RAW_TILE, &tmB, k0, nt * BN, &raw_full[stage]);
+          else tma_load_2d(dst + RAW_TILE, &tmB, nt * BN, k0, &raw_full[stage]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp >= PROD_WARP0 && warp < EPI2_WARP0 && !conv_as_epi) {
-    // ===== converters: landed fp32 tile -> (scale, split) -> fp16 operand planes =====
+    // ===== converters: landed fp32 k-block -> (scale, split) -> fp16 operand planes, in place =====
     const int ptid = tid - PROD_WARP0 * 32;
     const float sa = scale_from_amax(p.a_amax, p.a_scale), sb = scale_from_amax(p.b_amax, p.b_scale);
     const int n_items = p.presplit ? 0 : (nt1 - nt0) * nkb;
-    int stage = 0, phase = 0, rs = 0, rphase = 0;
+    int stage = 0, phase = 0;
     for (int it = 0; it < n_items; ++it) {
       DVAE_TC16_MARK(ptid == 0 && it == 12, 2);
-      mbar_wait(&raw_full[rs], rphase);
+      mbar_wait(&raw_full[stage], phase);
       DVAE_TC16_MARK(ptid == 0 && it == 12, 3);
       float va[8], vb[8];
-      const uint32_t raw = smem_u + OFF_RAW + rs * RAW_BYTES;
-      load_tile(raw, p.a_mn, ptid, va);
-      load_tile(raw + RAW_TILE, p.b_mn, ptid, vb);
-      mbar_wait(&empty[stage], phase ^ 1);
       const uint32_t st = smem_u + stage * STAGE_BYTES;
-      store_tile(st, p.a_mn, ptid, sa, va);
-      store_tile(st + 2 * PLANE, p.b_mn, ptid, sb, vb);
+      load_tile(st, p.a_mn, ptid, va);
+      load_tile(st + RAW_TILE, p.b_mn, ptid, vb);
+      // every converter thread has its fp32 values in registers before anyone overwrites the tile with fp16 planes
+      asm volatile("bar.sync %0, %1;" ::"n"(CONV_BARRIER), "n"(PROD_WARPS * 32) : "memory");
+      store_tile(st, ptid, sa, va);
+      store_tile(st + PS_TILE, ptid, sb, vb);
       DVAE_TC16_MARK(ptid == 0 && it == 12, 4);
       fence_proxy_async();
       __syncwarp();
-      if (lane == 0) {
-        mbar_arrive(&full[stage]);
-        mbar_arrive(&raw_empty[rs]);
-      }
+      if (lane == 0) mbar_arrive(&full[stage]);
       DVAE_TC16_MARK(ptid == 0 && it == 12, 5);
-      DVAE_TC16_MARK(ptid == 0 && it == 13, 6);
       if (++stage == STAGES) { stage = 0; phase ^= 1; }
-      if (++rs == RAW_STAGES) { rs = 0; rphase ^= 1; }
     }
   } else if (warp == MMA_WARP) {
     // ===== MMA issuer =====
@@ -347,15 +330,15 @@ tc16_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);   // f16 x f16 -> f32
     if (elect_one() && nkb > 0) {
       if (a_stat && !(DVAE_TC16_FLAG(16))) mbar_wait(a_full, 0);
-      const uint32_t lbo = p.presplit ? PS_LBO : T_LBO, sbo = p.presplit ? PS_SBO : T_SBO;
       // shared-memory descriptor = constant high word | (LBO field | address >> 4): only the 14-bit address field moves
-      const uint32_t d_hi = ((sbo >> 4) & 0x3FFF) | (1u << 14);                 // SBO, descriptor version, no swizzle
-      const uint32_t d_lo = ((lbo >> 4) & 0x3FFF) << 16;
-      const uint32_t kstep16 = (2 * lbo) >> 4, plane16 = plane_bytes >> 4, stage16 = stage_bytes >> 4;
+      constexpr uint32_t d_hi = ((PS_SBO >> 4) & 0x3FFF) | (1u << 14);          // SBO, descriptor version, no swizzle
+      constexpr uint32_t d_lo = ((PS_LBO >> 4) & 0x3FFF) << 16;
+      constexpr uint32_t kstep16 = (2 * PS_LBO) >> 4, plane16 = PS_PLANE >> 4;
+      const uint32_t stage16 = stage_bytes >> 4;
       const uint32_t base16 = smem_u >> 4;
       // operand bases: ring stage [A_hi, A_lo, B_hi, B_lo], or stationary A (k-block kb) + ring stage [B_hi, B_lo]
       const uint32_t ring16 = a_stat ? base16 + (AS_A_BYTES >> 4) : base16;
-      const uint32_t a_kb16 = a_stat ? (2 * PS_PLANE) >> 4 : 0;
+      const uint32_t a_kb16 = a_stat ? PS_TILE >> 4 : 0;
       const uint32_t b_off16 = a_stat ? 0 : 2 * plane16;
       auto desc = [&](uint32_t addr16) { return ((uint64_t)d_hi << 32) | (uint64_t)(d_lo | (addr16 & 0x3FFF)); };
       int stage = 0, phase = 0;
@@ -436,6 +419,7 @@ tc16_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       DVAE_TC16_MARK(tid == 0 && tile == 2, 96);
       // this warp's 64 bias values (vocabulary modes) -> shared memory: broadcast reads instead of 64 global loads
       float* sbias = reinterpret_cast<float*>(smem + OFF_BIAS) + (wide_epi ? ew * 32 : ew * 64);
+      const uint32_t sbias_u = smem_u + OFF_BIAS + (wide_epi ? ew * 32 : ew * 64) * 4;
       if (p.mode != 0) {
         __syncwarp();
 #pragma unroll
@@ -458,7 +442,8 @@ tc16_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (p.mode != 1) {
           // modes 0 / 2 store a [32 rows x 32 cols] chunk: transpose it through padded shared memory so each
           // store instruction covers 32 consecutive columns of one row (coalesced) instead of 32 different rows
-          const uint32_t sc = smem_u32(epi_scratch) + ew * (32 * 33 * 4);
+          // (element (r, c) of the chunk lives at word r * 32 + (c ^ r): conflict-free both ways without padding)
+          const uint32_t sc = smem_u + OFF_SCRATCH + ew * (32 * 32 * 4);
 #pragma unroll
           for (int hh = 0; hh < 2; ++hh) {
             float v[16], w[16];
@@ -470,9 +455,9 @@ tc16_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               if (p.mode == 2) {
                 const int col = col0 + hh * 16 + j;
                 x = (row_scale == 0.f || col >= p.N) ? 0.f
-                    : (ex2_ftz(fmaf(x + sbias[(c - c_lo) * 32 + hh * 16 + j], kLog2e, row_nlse2)) - (col == tgt ? 1.f : 0.f)) * row_scale;
+                    : (ex2_ftz(fmaf(x + lds32(sbias_u + ((c - c_lo) * 32 + hh * 16 + j) * 4), kLog2e, row_nlse2)) - (col == tgt ? 1.f : 0.f)) * row_scale;
               }
-              sts32(sc + (lane * 33 + hh * 16 + j) * 4, x);
+              sts32(sc + (lane * 32 + ((hh * 16 + j) ^ lane)) * 4, x);
             }
           }
           __syncwarp();
@@ -488,16 +473,16 @@ tc16_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
             float* cp = p.C + (int64_t)r0 * p.ldc + col;
             const int64_t ldc = p.ldc;
-            const uint32_t src = sc + lane * 4;
+            auto chunk_at = [&](int rr) { return lds32(sc + (uint32_t)(rr * 32 + (lane ^ rr)) * 4); };      // element (rr, lane)
             if (p.mode == 2 || (!split && p.act == 0 && p.beta == 0.f)) {
               if (nr == 32) {
 #pragma unroll
-                for (int rr = 0; rr < 32; ++rr) cp[rr * ldc] = lds32(src + rr * 132) + badd;
+                for (int rr = 0; rr < 32; ++rr) cp[rr * ldc] = chunk_at(rr) + badd;
               } else {
-                for (int rr = 0; rr < nr; ++rr) cp[rr * ldc] = lds32(src + rr * 132) + badd;
+                for (int rr = 0; rr < nr; ++rr) cp[rr * ldc] = chunk_at(rr) + badd;
               }
             } else if (split) {
-              for (int rr = 0; rr < nr; ++rr) atomicAdd(cp + rr * ldc, lds32(src + rr * 132) + badd);   // C pre-scaled by beta
+              for (int rr = 0; rr < nr; ++rr) atomicAdd(cp + rr * ldc, chunk_at(rr) + badd);   // C pre-scaled by beta
             } else {
               const float beta = p.beta;
               const bool do_tanh = p.act == 1;
@@ -510,14 +495,14 @@ tc16_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                   for (int rr = 0; rr < 8; ++rr) old[rr] = cp[(r8 + rr) * ldc];
 #pragma unroll
                   for (int rr = 0; rr < 8; ++rr) {
-                    float x = lds32(src + (r8 + rr) * 132) + badd;
+                    float x = chunk_at(r8 + rr) + badd;
                     if (do_tanh) x = tanhf(x);
                     cp[(r8 + rr) * ldc] = fmaf(beta, old[rr], x);
                   }
                 }
               } else {
                 for (int rr = 0; rr < nr; ++rr) {
-                  float x = lds32(src + rr * 132) + badd;
+                  float x = chunk_at(rr) + badd;
                   if (do_tanh) x = tanhf(x);
                   if (beta != 0.f) x = fmaf(beta, cp[rr * ldc], x);
                   cp[rr * ldc] = x;
@@ -546,7 +531,7 @@ tc16_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           {
             // bias: four 16-byte shared loads (explicit shared-space: through the generic `sbias` pointer these were
             // sixteen predicated generic LD.E, each feeding its own FFMA)
-            const uint32_t ba = smem_u + OFF_BIAS + ((wide_epi ? ew * 32 : ew * 64) + (c - c_lo) * 32 + hh * 16) * 4;
+            const uint32_t ba = sbias_u + ((c - c_lo) * 32 + hh * 16) * 4;
             float bv[16];
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
@@ -665,9 +650,10 @@ static int make_map(CUtensorMap* m, const float* base, int64_t ld, int mn_major,
   cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
   cuuint32_t box[2] = {(cuuint32_t)(mn_major ? BM : BK), (cuuint32_t)(mn_major ? BK : BM)};
   cuuint32_t estr[2] = {1, 1};
+  // K-major tiles (128-byte rows) land with the 128-byte swizzle the converters' loads expect (load_tile)
   CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, mn_major ? CU_TENSOR_MAP_SWIZZLE_NONE : CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   DVAE_REQUIRE(r == CUDA_SUCCESS, "tc16_gemm: cuTensorMapEncodeTiled failed (%d) rows=%d K=%d ld=%lld", (int)r, rows, K, (long long)ld);
   return DVAE_OK;
 }
