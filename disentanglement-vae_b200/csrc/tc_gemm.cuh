@@ -145,6 +145,43 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// two loads in flight, ONE wait: 32 lanes x 16 columns from each of two accumulators (hi/lo product sums)
+__device__ __forceinline__ void tmem_ld16_pair(uint32_t ta, uint32_t tb, float (&v)[16], float (&w)[16]) {
+  uint32_t r[16], q[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(ta)
+      : "memory");
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(q[0]), "=r"(q[1]), "=r"(q[2]), "=r"(q[3]), "=r"(q[4]), "=r"(q[5]), "=r"(q[6]), "=r"(q[7]), "=r"(q[8]),
+        "=r"(q[9]), "=r"(q[10]), "=r"(q[11]), "=r"(q[12]), "=r"(q[13]), "=r"(q[14]), "=r"(q[15])
+      : "r"(tb)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) { v[i] = __uint_as_float(r[i]); w[i] = __uint_as_float(q[i]); }
+}
+// the same for 8 columns (epilogues that are short of registers)
+__device__ __forceinline__ void tmem_ld8_pair(uint32_t ta, uint32_t tb, float (&v)[8], float (&w)[8]) {
+  uint32_t r[8], q[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(ta)
+               : "memory");
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(q[0]), "=r"(q[1]), "=r"(q[2]), "=r"(q[3]), "=r"(q[4]), "=r"(q[5]), "=r"(q[6]), "=r"(q[7])
+               : "r"(tb)
+               : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { v[i] = __uint_as_float(r[i]); w[i] = __uint_as_float(q[i]); }
+}
+
 // ---- descriptors -----------------------------------------------------------------------------------
 // Shared-memory matrix descriptor (sm_100 version 1), SWIZZLE_128B canonical layouts of 4-byte elements:
 //   K-major : rows of 128 B (32 floats of K), 8-row swizzle atoms 1024 B apart      -> SBO = 1024, LBO unused (1)

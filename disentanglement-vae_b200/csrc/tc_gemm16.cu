@@ -191,9 +191,9 @@ tc16_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_full + 1);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  // pre-split vocab-CE forward: no converters are needed, so the first 8 converter warps join the epilogue (16 warps,
-  // one 32-column chunk each) -- with 8 warps the exp / max / arg-max epilogue took 4.1 us per tile against 1.7 us of MMAs
-  const bool wide_epi = p.presplit && p.mode == 1;
+  // pre-split vocabulary kernels: no converters are needed, so the first 8 converter warps join the epilogue (16 warps,
+  // one 32-column chunk each) -- with 8 warps the exp-heavy epilogues took 4-7 us per tile against 1.7 us of MMAs
+  const bool wide_epi = p.presplit && p.mode != 0;
   const bool conv_as_epi = wide_epi && warp >= PROD_WARP0 && warp < PROD_WARP0 + EPI_WARPS;
   // a programmatically-launched successor (the persistent LSTM kernels) may start its prologue now; it still waits for
   // this grid to complete (griddepcontrol.wait) before it reads anything written here
@@ -439,27 +439,85 @@ tc16_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int col0 = n0 + c * 32;
         if (col0 >= p.N || DVAE_TC16_FLAG(~0)) continue;                        // warp-uniform (probe builds: any switch skips the epilogue)
         const uint32_t ta = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * 256 + c * 32;
+        if (p.mode == 2 && wide_epi) {
+          // softmax-gradient chunk with 16 epilogue warps: 2 KB of transpose scratch per warp, so the chunk goes out in two
+          // [32 rows x 16 cols] halves; element (r, j) of a half lives at word r * 16 + (j ^ ((r >> 1) & 15)) and store
+          // instruction k writes rows 2k, 2k+1 (lanes 0-15 / 16-31): two full 64-byte segments, no bank conflicts either way
+          const uint32_t sc = smem_u + OFF_SCRATCH + ew * (32 * 16 * 4);
+          const int r0 = m0 + quarter * 32;
+          const int nr = min(32, p.M - r0);
+          const bool dead = row_scale == 0.f;
+          DVAE_TC16_MARK(tid == 0 && tile == 2, 104);
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+#pragma unroll
+            for (int h8 = 0; h8 < 2; ++h8) {            // 8 columns at a time: 72 registers per thread is the cap here
+              float v[8], w[8];
+              tmem_ld8_pair(ta + hh * 16 + h8 * 8, ta + 128 + hh * 16 + h8 * 8, v, w);
+#pragma unroll
+              for (int q = 0; q < 2; ++q) {
+                const uint4 t = lds128(sbias_u + (hh * 16 + h8 * 8 + 4 * q) * 4);
+                const float bq[4] = {__uint_as_float(t.x), __uint_as_float(t.y), __uint_as_float(t.z), __uint_as_float(t.w)};
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) {
+                  const int j = 4 * q + jj, col = col0 + hh * 16 + h8 * 8 + j;
+                  const float e = ex2_ftz(fmaf(fmaf(fmaf(w[j], kLoInv, v[j]), oscale, bq[jj]), kLog2e, row_nlse2));
+                  v[j] = (dead || col >= p.N) ? 0.f : (e - (col == tgt ? 1.f : 0.f)) * row_scale;
+                }
+              }
+#pragma unroll
+              for (int j = 0; j < 8; ++j) sts32(sc + (lane * 16 + ((h8 * 8 + j) ^ ((lane >> 1) & 15))) * 4, v[j]);
+            }
+            __syncwarp();
+            const int colw = col0 + hh * 16 + (lane & 15);
+            float* cp = p.C + (int64_t)(r0 + (lane >> 4)) * p.ldc + colw;
+            if (colw < p.N) {
+#pragma unroll
+              for (int k = 0; k < 16; ++k) {
+                const float val = lds32(sc + ((2 * k + (lane >> 4)) * 16 + ((lane & 15) ^ k)) * 4);
+                if (2 * k + (lane >> 4) < nr) cp[(int64_t)(2 * k) * p.ldc] = val;
+              }
+            }
+            __syncwarp();
+          }
+          DVAE_TC16_MARK(tid == 0 && tile == 2, 105);
+          continue;
+        }
         if (p.mode != 1) {
           // modes 0 / 2 store a [32 rows x 32 cols] chunk: transpose it through padded shared memory so each
           // store instruction covers 32 consecutive columns of one row (coalesced) instead of 32 different rows
           // (element (r, c) of the chunk lives at word r * 32 + (c ^ r): conflict-free both ways without padding)
           const uint32_t sc = smem_u + OFF_SCRATCH + ew * (32 * 32 * 4);
+          DVAE_TC16_MARK(tid == 0 && tile == 2, 104 + 3 * (c - c_lo));
 #pragma unroll
           for (int hh = 0; hh < 2; ++hh) {
             float v[16], w[16];
-            tmem_ld16(ta + hh * 16, v);
-            tmem_ld16(ta + 128 + hh * 16, w);
+            tmem_ld16_pair(ta + hh * 16, ta + 128 + hh * 16, v, w);
+            float x[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              float x = fmaf(w[j], kLoInv, v[j]) * oscale;
-              if (p.mode == 2) {
-                const int col = col0 + hh * 16 + j;
-                x = (row_scale == 0.f || col >= p.N) ? 0.f
-                    : (ex2_ftz(fmaf(x + lds32(sbias_u + ((c - c_lo) * 32 + hh * 16 + j) * 4), kLog2e, row_nlse2)) - (col == tgt ? 1.f : 0.f)) * row_scale;
+            for (int j = 0; j < 16; ++j) x[j] = fmaf(w[j], kLoInv, v[j]) * oscale;
+            if (p.mode == 2) {
+              // all 16 bias values first (4 x LDS.128), then 16 independent exp chains, then the stores: a shared load
+              // per element between the (volatile) stores serialised the whole block (~100 cycles per element)
+              float bv[16];
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const uint4 t = lds128(sbias_u + ((c - c_lo) * 32 + hh * 16 + 4 * q) * 4);
+                bv[4 * q] = __uint_as_float(t.x); bv[4 * q + 1] = __uint_as_float(t.y);
+                bv[4 * q + 2] = __uint_as_float(t.z); bv[4 * q + 3] = __uint_as_float(t.w);
               }
-              sts32(sc + (lane * 32 + ((hh * 16 + j) ^ lane)) * 4, x);
+              const bool dead = row_scale == 0.f;
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                const int col = col0 + hh * 16 + j;
+                const float e = ex2_ftz(fmaf(x[j] + bv[j], kLog2e, row_nlse2));
+                x[j] = (dead || col >= p.N) ? 0.f : (e - (col == tgt ? 1.f : 0.f)) * row_scale;
+              }
             }
+#pragma unroll
+            for (int j = 0; j < 16; ++j) sts32(sc + (lane * 32 + ((hh * 16 + j) ^ lane)) * 4, x[j]);
           }
+          DVAE_TC16_MARK(tid == 0 && tile == 2, 105 + 3 * (c - c_lo));
           __syncwarp();
           const int col = col0 + lane;
           const int r0 = m0 + quarter * 32;
@@ -510,6 +568,7 @@ tc16_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               }
             }
           }
+          DVAE_TC16_MARK(tid == 0 && tile == 2, 106 + 3 * (c - c_lo));
           __syncwarp();
           continue;
         }
@@ -520,8 +579,7 @@ tc16_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int hh = 0; hh < 2; ++hh) {
           float v[16], w[16];
           DVAE_TC16_MARK(tid == 0 && tile == 2, 98 + 3 * hh);
-          tmem_ld16(ta + hh * 16, v);
-          tmem_ld16(ta + 128 + hh * 16, w);
+          tmem_ld16_pair(ta + hh * 16, ta + 128 + hh * 16, v, w);
           DVAE_TC16_MARK(tid == 0 && tile == 2, 99 + 3 * hh);
           if (!row_ok) continue;
           // 16 logits of this row: everything below is a tree or independent per element (the serial running-max /
@@ -678,7 +736,11 @@ int split_planes(const float* X, int64_t ld, int R, int K, float scale, void* pl
   return DVAE_OK;
 }
 
-static int launch(const Params& p, dim3 grid, cudaStream_t st) {
+static int launch(const Params& p_in, dim3 grid, cudaStream_t st) {
+  Params p = p_in;
+  if (p.dbg)      // probes: DVAE_TC_DBG_MODE=<mode> keeps the timeline marks of that kernel flavour only
+    if (const char* e = getenv("DVAE_TC_DBG_MODE"))
+      if (atoi(e) != p.mode) p.dbg = nullptr;
   static bool ready = false;
   if (!ready) {
     DVAE_CUDA(cudaFuncSetAttribute(tc16_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
