@@ -352,10 +352,23 @@ def main():
     d = pl.d
     N = pl.N
     evk = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(10)]
-    for a, b in evk:
+    from importlib import import_module as _im
+    _L = _im("disentanglement-vae_b200._lib")
+    pl.vocab_ce(P, pl.d_hs[-1], eng.inputs, eng.lengths)            # leaves the fp16 operand planes in the workspace
+    call_ms = []
+    for a, b in evk:                                                 # the whole C-ABI call: split + kernel + finalize + loss
         flush.zero_()
         a.record()
         pl.vocab_ce(P, pl.d_hs[-1], eng.inputs, eng.lengths)
+        b.record()
+    torch.cuda.synchronize()
+    call_ms = float(np.median([a.elapsed_time(b) for a, b in evk]))
+    for a, b in evk:                                                 # the kernel alone (one launch between the events)
+        flush.zero_()
+        a.record()
+        _L.check(pl.lib.dvae_vocab_ce_partials(_L.ptr(pl.d_hs[-1]), d.Hd, pl.T1, pl.B, d.Hd, d.V, _L.ptr(P["decoder.linear.weight"]),
+                                                _L.ptr(P["decoder.linear.bias"]), _L.ptr(eng.inputs), eng.inputs.stride(0),
+                                                _L.ptr(eng.lengths), d.sos, _L.ptr(pl.ce_ws), _L.stream_ptr()), "dvae_vocab_ce_partials")
         b.record()
     torch.cuda.synchronize()
     k_ms = float(np.median([a.elapsed_time(b) for a, b in evk]))
@@ -396,15 +409,16 @@ def main():
         pass
     gemm_impl = os.environ.get("DVAE_GEMM_IMPL", "")
     kname = ("tc_gemm_kernel mode 1 (TMA + tcgen05.mma.kind::tf32, 3xTF32)" if gemm_impl.startswith("t")
-             else "tc16_gemm_kernel mode 1 (TMA landing ring, fp16 hi/lo-split operands, tcgen05.mma.kind::f16, two TMEM accumulators)")
+             else "tc16_gemm_kernel mode 1 (pre-split fp16 hi/lo operand planes by bulk copy, A rows stationary in SMEM, tcgen05.mma.kind::f16, two TMEM accumulators, 16 epilogue warps)")
     n_par = eng.n
     adam_bytes = 36.0 * n_par                   # sumsq reads g; clip+Adam reads p, g, m, v and writes p, m, v and the zeroed g
     roof = {"kernel": kname + " = vocab-CE forward: vocabulary projection + online log-softmax / arg-max / NLL epilogue from TMEM; "
-                              "the [N,V] logits are never written to HBM (+ a 1-CTA finalize kernel inside the timed call)",
+                              "the [N,V] logits are never written to HBM; ONE launch between the CUDA events (dvae_vocab_ce_partials)",
             "bound": "tensor", "achieved": tf, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": tf / peaks["bf16_tflops"],
             "peak_source": f"MEASURED_PEAKS.json bf16 burst ({peaks['src']}); fp32-grade emulation executes 3 tensor flops per algorithmic flop",
             "traffic": traffic, "traffic_source": "profiles/r1_ncu_traffic.json (ncu --set full, per launch)",
-            "launch_ms": k_ms, "tensor_flops_executed": 3 * flops, "algorithmic_flops": flops, "algorithmic_bytes": alg_bytes,
+            "launch_ms": k_ms, "call_ms": call_ms, "call": "dvae_vocab_ce_fwd = operand split x2 + this kernel + finalize + loss",
+            "tensor_flops_executed": 3 * flops, "algorithmic_flops": flops, "algorithmic_bytes": alg_bytes,
             "hbm_frac": alg_bytes / (k_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
             "secondary": [{"kernel": "sumsq_kernel + clip_adam_kernel (grad-norm clip 5.0 + Adam + zero_grad over the flat parameter buffer)",
                            "bound": "hbm", "achieved": adam_bytes / (adam_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",

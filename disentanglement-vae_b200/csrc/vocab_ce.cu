@@ -404,6 +404,28 @@ extern "C" int dvae_vocab_ce_bwd(const float* h, int64_t ldh, int T1, int B, int
   return DVAE_OK;
 }
 
+// Measurement entry (bench.py roofline, ncu): ONLY the projection + online-softmax partials kernel of dvae_vocab_ce_fwd.
+// `ws` must come from an earlier dvae_vocab_ce_fwd call with the same arguments (it holds the fp16 operand planes).
+extern "C" int dvae_vocab_ce_partials(const float* h, int64_t ldh, int T1, int B, int H, int V, const float* w,
+                                      const float* bias, const int64_t* targets, int64_t tgt_stride_b,
+                                      const int64_t* lengths, int sos, float* ws, void* stream) {
+  DVAE_REQUIRE(h && w && bias && targets && lengths && ws, "dvae_vocab_ce_partials: null pointer");
+  DVAE_REQUIRE(T1 > 0 && B > 0 && H > 0 && V > 0, "dvae_vocab_ce_partials: bad shape");
+  CeArgs p;
+  p.h = h; p.ldh = ldh; p.w = w; p.bias = bias; p.targets = targets; p.tgt_stride_b = tgt_stride_b;
+  p.lengths = lengths; p.N = T1 * B; p.B = B; p.H = H; p.V = V; p.sos = sos;
+  p.nsplit = ce_nsplit(p.N, V, &p.tiles_per_split);
+  p.part = ws;
+  p.part_idx = reinterpret_cast<int*>(ws + (int64_t)p.nsplit * p.N * 4);
+  p.gumbel_seed = nullptr; p.gumbel_salt = 0;
+  p.h_planes = p.w_planes = nullptr;
+  if (use_tc16(p.N, V, H, h, ldh, w) && use_presplit(p.N, V, H)) {
+    float* hp = ws + ce_part_floats(p.N, V);
+    p.h_planes = hp; p.w_planes = hp + tc16::plane_floats(p.N, H);
+  }
+  return ce_partials(p, (cudaStream_t)stream);
+}
+
 extern "C" int dvae_vocab_sample_step(const float* h, int64_t ldh, int B, int H, int V, const float* w, const float* bias,
                                       const uint64_t* seed_dev, uint32_t salt, int64_t* tokens_out, int64_t tok_stride,
                                       float* ws, void* stream) {

@@ -269,6 +269,13 @@ int dvae_vocab_ce_fwd(const float* h, int64_t ldh, int T1, int B, int H, int V, 
                       const int64_t* lengths, int sos, float* lse, float* nll, int32_t* argmax,
                       float* loss, float* ws, void* stream);
 
+/* Measurement entry (bench.py roofline, ncu): only the projection + online-softmax partials kernel of
+ * dvae_vocab_ce_fwd (no operand split, no finalize).  ws must come from an earlier dvae_vocab_ce_fwd call with the same
+ * arguments.  Not part of the reference-facing surface. */
+int dvae_vocab_ce_partials(const float* h, int64_t ldh, int T1, int B, int H, int V, const float* w,
+                           const float* bias, const int64_t* targets, int64_t tgt_stride_b,
+                           const int64_t* lengths, int sos, float* ws, void* stream);
+
 /* Sampled next token per row without materialising [B,V] logits or probabilities: replaces
  * decoder.linear + torch.softmax + torch.multinomial (vae/model.py:164,468-469,504-505).
  * tokens_out[b*tok_stride] = argmax_v( h[b].w[v] + bias[v] + g(b,v) ), g ~ Gumbel(0,1) from Philox keyed by

@@ -390,6 +390,62 @@ __global__ void __launch_bounds__(128, 1) probe_loop(long long* out, int ntiles,
   if (tid < 32) tmem_dealloc(tmem, 512);
 }
 
+
+// two-issuer probe: the LSTM step's 48 small MMAs (M=128, N=16, K=16; 16 k-steps x 3 products) issued by ONE thread, or
+// split between TWO warps (k-steps 0-7 / 8-15, separate accumulators): is the ~36 cycles per small MMA a per-thread
+// issue cost or a limit of the tensor-core front end?
+template <int K0, int K1>
+__device__ __forceinline__ void issue_ksteps(uint32_t tmem, uint32_t sb, uint64_t* bar) {
+  constexpr uint32_t idesc = idesc_f16(128, 16);
+  const uint64_t ahi = make_smem_desc(sb, 128, 4096, 0), alo = make_smem_desc(sb + 65536, 128, 4096, 0);
+  const uint64_t bhi = make_smem_desc(sb + 131072, 256, 128, 0), blo = make_smem_desc(sb + 131072 + 8192, 256, 128, 0);
+#pragma unroll
+  for (int ks = K0; ks < K1; ++ks) {
+    const uint64_t da = (uint64_t)(ks * 16), db = (uint64_t)(ks * 32);
+    mma_ss(tmem, ahi + da, bhi + db, idesc, ks > K0);
+    mma_ss(tmem + 16, ahi + da, blo + db, idesc, ks > K0);
+    mma_ss(tmem + 16, alo + da, bhi + db, idesc, 1);
+  }
+  tc_commit(bar);
+}
+__global__ void __launch_bounds__(128, 1) probe_two_issuers(long long* out) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bar, bar2;
+  __shared__ uint32_t slot;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < 160 * 1024 / 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
+  if (tid == 0) { mbar_init(&bar, 1); mbar_init(&bar2, 2); fence_barrier_init(); }
+  if (tid < 32) tmem_alloc(&slot, 128);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = slot, sb = smem_u32(smem);
+  for (int rep = 0; rep < 3; ++rep) {
+    long long t0 = clock64();
+    if (warp == 0) {
+      if (elect_one()) issue_ksteps<0, 16>(tmem, sb, &bar);
+      __syncwarp();
+    }
+    mbar_wait(&bar, rep & 1);
+    long long t1 = clock64();
+    __syncthreads();
+    long long t2 = clock64();
+    if (warp == 0) {
+      if (elect_one()) issue_ksteps<0, 8>(tmem, sb, &bar2);
+      __syncwarp();
+    } else if (warp == 1) {
+      if (elect_one()) issue_ksteps<8, 16>(tmem + 32, sb, &bar2);
+      __syncwarp();
+    }
+    mbar_wait(&bar2, rep & 1);
+    long long t3 = clock64();
+    if (tid == 0) { out[rep * 2] = t1 - t0; out[rep * 2 + 1] = t3 - t2; }
+    __syncthreads();
+  }
+  if (tid < 32) tmem_dealloc(tmem, 128);
+}
+
 int main() {
   long long* d; cudaMalloc(&d, 1024);
   cudaFuncSetAttribute(probe, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
@@ -465,6 +521,15 @@ int main() {
     run(probe_loop<1>, "V1 one thread runs the loop, runtime ring addresses");
     run(probe_loop<3>, "V3 = V1 unrolled by 4");
     run(probe_loop<2>, "V2 descriptors precomputed, 40 k-blocks unrolled");
+  }
+  {
+    cudaFuncSetAttribute(probe_two_issuers, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    probe_two_issuers<<<1, 128, 200 * 1024>>>(d);
+    e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { printf("error: %s\n", cudaGetErrorString(e)); return 1; }
+    cudaMemcpy(h, d, sizeof(h[0]) * 6, cudaMemcpyDeviceToHost);
+    for (int rep = 0; rep < 3; ++rep)
+      printf("two issuers: 48 MMAs (N=16) from one thread %lld cyc | split over two warps %lld cyc\n", h[rep * 2], h[rep * 2 + 1]);
   }
   return 0;
 }
