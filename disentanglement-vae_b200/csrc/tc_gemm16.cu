@@ -782,13 +782,22 @@ int linear(const float* A, int64_t lda, int trans_a, const float* B, int64_t ldb
   p.M = M; p.N = N; p.K = K; p.a_mn = trans_a ? 1 : 0; p.b_mn = trans_b ? 1 : 0; p.tiles_per_cta = 1;
   p.C = C; p.ldc = ldc; p.bias = bias; p.bias2 = bias2; p.beta = beta; p.act = act; p.mode = 0;
   apply_hints(p, hints);
-  // split-K when the output has too few tiles to occupy the 148 SMs and K is deep (weight-gradient shapes)
+  // split-K (weight-gradient shapes: few output tiles, deep K): pick the split count with the smallest modelled time
+  //   waves(tiles * s) * (k-blocks per split * t_kb + fixed per-CTA cost)   [us; measured orders of magnitude]
+  // -- "split only when tiles <= 74" left the 80-tile dW_out GEMM of a 5120-column vocabulary chunk at one 84-k-block
+  // CTA per tile on 80 of 148 SMs (128 us instead of ~60).
   const int tiles = ceil_div(M, BM) * ceil_div(N, BN), nkb = ceil_div(K, BK);
   int splits = 1;
-  if (act == 0 && tiles * 2 <= 148 && nkb >= 16) {
-    splits = 148 / tiles;
-    if (splits > nkb / 8) splits = nkb / 8;
-    if (splits < 1) splits = 1;
+  if (act == 0 && nkb >= 16) {
+    const float t_kb = 0.5f + 0.2f * (p.a_mn + p.b_mn);
+    float best = 1e30f;
+    for (int s2 = 1; s2 <= 16 && s2 <= nkb / 4; ++s2) {
+      const int kbs = ceil_div(nkb, s2), se = ceil_div(nkb, kbs);
+      if (se != s2) continue;
+      const int waves = ceil_div(tiles * se, 148);
+      const float t = waves * (kbs * t_kb + (se > 1 ? 6.f : 4.f)) + (se > 1 ? 2.f : 0.f);
+      if (t < best * 0.95f) { best = t; splits = se; }      // a larger split count has to be clearly better
+    }
   }
   p.kb_per_split = ceil_div(nkb, splits);
   splits = ceil_div(nkb, p.kb_per_split);

@@ -290,12 +290,16 @@ static int ce_nsplit(int N, int V, int* tiles_per_split) {
 }
 
 static int p_chunk(int N, int V) {
-  // keep the softmax chunk around 48 MB so it stays L2-resident between producer and consumers
-  int64_t vc = (12LL << 20) / (N > 0 ? N : 1);
-  vc = vc / 128 * 128;
-  if (vc < 128) vc = 128;
-  int64_t vr = (int64_t)ceil_div(V, 128) * 128;
-  if (vc > vr) vc = vr;
+  // keep the softmax chunk under ~56 MB so it stays L2-resident between producer and consumers, and make the chunks
+  // equal: at cfg 2 (N = 2688, V = 10000) two chunks of 5120 / 4880 columns instead of 4608 + 4608 + a 784-column
+  // remainder whose three kernels cost 43 us for 8 % of the work
+  int64_t vmax = (14LL << 20) / (N > 0 ? N : 1);
+  vmax = vmax / 128 * 128;
+  if (vmax < 128) vmax = 128;
+  const int64_t vr = (int64_t)ceil_div(V, 128) * 128;
+  if (vmax >= vr) return (int)vr;
+  const int64_t nc = (vr + vmax - 1) / vmax;
+  const int64_t vc = ((V + nc - 1) / nc + 127) / 128 * 128;
   return (int)vc;
 }
 
@@ -354,7 +358,8 @@ extern "C" int64_t dvae_vocab_ce_bwd_ws_floats(int N, int V, int H) {
 extern "C" int dvae_vocab_ce_bwd(const float* h, int64_t ldh, int T1, int B, int H, int V, const float* w,
                                  const float* bias, const int64_t* targets, int64_t tgt_stride_b,
                                  const int64_t* lengths, const float* lse, const float* grad_scale_dev,
-                                 float* d_h, int64_t lddh, float* d_w, float* d_bias, float* ws, void* stream) {
+                                 float* d_h, int64_t lddh, float* d_w, float* d_bias, const float* fwd_ws, float* ws,
+                                 void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   DVAE_REQUIRE(h && w && bias && targets && lengths && lse && d_h && d_w && d_bias && ws, "dvae_vocab_ce_bwd: null pointer");
   DVAE_REQUIRE(T1 > 0 && B > 0 && H > 0 && V > 0, "dvae_vocab_ce_bwd: bad shape");
@@ -370,12 +375,17 @@ extern "C" int dvae_vocab_ce_bwd(const float* h, int64_t ldh, int T1, int B, int
   while (ph.a_scale * 2.f <= (float)B) ph.a_scale *= 2.f;
   const void *h_planes = nullptr, *w_planes = nullptr;
   if (use_tc16(N, min(vc_max, V), H, h, ldh, w) && use_presplit(N, V, H)) {
-    float* hp = ws + (int64_t)N * vc_max;
-    float* wp = hp + tc16::plane_floats(N, H);
-    int rc;
-    if ((rc = tc16::split_planes(h, ldh, N, H, 1.f, hp, st))) return rc;
-    if ((rc = tc16::split_planes(w, H, V, H, 1.f, wp, st))) return rc;
-    h_planes = hp; w_planes = wp;
+    if (fwd_ws) {        // the forward call's workspace still holds the fp16 planes of the same h and w
+      const float* hp = fwd_ws + ce_part_floats(N, V);
+      h_planes = hp; w_planes = hp + tc16::plane_floats(N, H);
+    } else {
+      float* hp = ws + (int64_t)N * vc_max;
+      float* wp = hp + tc16::plane_floats(N, H);
+      int rc;
+      if ((rc = tc16::split_planes(h, ldh, N, H, 1.f, hp, st))) return rc;
+      if ((rc = tc16::split_planes(w, H, V, H, 1.f, wp, st))) return rc;
+      h_planes = hp; w_planes = wp;
+    }
   }
   int chunk = 0;
   for (int v0 = 0; v0 < V; v0 += vc_max, ++chunk) {

@@ -253,6 +253,8 @@ class StepPlan:
                                     ptr(P["decoder.linear.bias"]), ptr(targets), targets.stride(0), ptr(lengths),
                                     d.sos, ptr(self.lse), ptr(self.nll), ptr(self.argmax), ptr(self.recon),
                                     ptr(self.ce_ws), st), "dvae_vocab_ce_fwd")
+        # the backward of this same step may reuse the operand planes the call left in ce_ws
+        self._ce_planes_valid = (h_top.data_ptr(), P["decoder.linear.weight"].data_ptr())
         return self.recon
 
     # ------------------------------------------------------------------------------------------
@@ -261,11 +263,15 @@ class StepPlan:
     def vocab_ce_bwd(self, P, G, h_top, targets, lengths, grad_scale_dev):
         self._alloc_bwd()
         lib, d, st = self.lib, self.d, _lib.stream_ptr()
+        # operand planes left by this step's forward call (same h_top, same weights): no need to split again
+        reuse = getattr(self, "_ce_planes_valid", None) == (h_top.data_ptr(), P["decoder.linear.weight"].data_ptr())
+        self._ce_planes_valid = None
         check(lib.dvae_vocab_ce_bwd(ptr(h_top), d.Hd, self.T1, self.B, d.Hd, d.V, ptr(P["decoder.linear.weight"]),
                                     ptr(P["decoder.linear.bias"]), ptr(targets), targets.stride(0), ptr(lengths),
                                     ptr(self.lse), ptr(grad_scale_dev), ptr(self.g_top), d.Hd,
                                     ptr(G["decoder.linear.weight"]), ptr(G["decoder.linear.bias"]),
-                                    ptr(self.ce_bwd_ws), st), "dvae_vocab_ce_bwd")
+                                    ptr(self.ce_ws) if reuse else None, ptr(self.ce_bwd_ws), st),
+              "dvae_vocab_ce_bwd")
         return self.g_top
 
     def decode_bwd(self, P, G, g_top, emb_grad=True):

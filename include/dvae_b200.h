@@ -287,12 +287,14 @@ int dvae_vocab_sample_step(const float* h, int64_t ldh, int B, int H, int V, con
 
 /* Backward: d_h [N,H], d_w [V,H], d_bias [V] (all overwritten) for d(loss) = grad_scale_dev[0]
  * (NULL = 1).  Softmax tiles are recomputed from h, w and the saved lse.
- *   ws: dvae_vocab_ce_bwd_ws_floats(N, V, H) floats. */
+ *   ws: dvae_vocab_ce_bwd_ws_floats(N, V, H) floats.
+ *   fwd_ws: NULL, or the workspace of the dvae_vocab_ce_fwd call on the SAME h and w if it has not been touched since:
+ *   its fp16 operand planes are reused instead of being rebuilt (two fewer kernels). */
 int64_t dvae_vocab_ce_bwd_ws_floats(int N, int V, int H);
 int dvae_vocab_ce_bwd(const float* h, int64_t ldh, int T1, int B, int H, int V, const float* w,
                       const float* bias, const int64_t* targets, int64_t tgt_stride_b,
                       const int64_t* lengths, const float* lse, const float* grad_scale_dev,
-                      float* d_h, int64_t lddh, float* d_w, float* d_bias, float* ws,
+                      float* d_h, int64_t lddh, float* d_w, float* d_bias, const float* fwd_ws, float* ws,
                       void* stream);
 
 /* ---------------------------------------------------------------------------------------------

@@ -19,5 +19,5 @@ L.check(lib.dvae_vocab_ce_fwd(L.ptr(h), H, T1, Bt, H, V, L.ptr(w), L.ptr(bias), 
                               L.ptr(am), L.ptr(loss), L.ptr(ws), st), "ce")
 for _ in range(2):
     L.check(lib.dvae_vocab_ce_bwd(L.ptr(h), H, T1, Bt, H, V, L.ptr(w), L.ptr(bias), L.ptr(tg), tg.stride(0), L.ptr(ln), L.ptr(lse), None,
-                                  L.ptr(dh), H, L.ptr(dw), L.ptr(db), L.ptr(wsb), st), "ce bwd")
+                                  L.ptr(dh), H, L.ptr(dw), L.ptr(db), None, L.ptr(wsb), st), "ce bwd")
 torch.cuda.synchronize()

@@ -47,7 +47,7 @@ ws = torch.zeros(lib.dvae_vocab_ce_ws_floats(N, V, H), device="cuda")
 wsb = torch.zeros(lib.dvae_vocab_ce_bwd_ws_floats(N, V, H), device="cuda")
 dh, dw, db = torch.zeros(N, H, device="cuda"), torch.zeros(V, H, device="cuda"), torch.zeros(V, device="cuda")
 fwd = lambda: lib.dvae_vocab_ce_fwd(L.ptr(h), H, T1, Bt, H, V, L.ptr(w), L.ptr(bias), L.ptr(tg), tg.stride(0), L.ptr(ln), 2, L.ptr(lse), L.ptr(nll), L.ptr(am), L.ptr(loss), L.ptr(ws), st)
-bwd = lambda: lib.dvae_vocab_ce_bwd(L.ptr(h), H, T1, Bt, H, V, L.ptr(w), L.ptr(bias), L.ptr(tg), tg.stride(0), L.ptr(ln), L.ptr(lse), None, L.ptr(dh), H, L.ptr(dw), L.ptr(db), L.ptr(wsb), st)
+bwd = lambda: lib.dvae_vocab_ce_bwd(L.ptr(h), H, T1, Bt, H, V, L.ptr(w), L.ptr(bias), L.ptr(tg), tg.stride(0), L.ptr(ln), L.ptr(lse), None, L.ptr(dh), H, L.ptr(dw), L.ptr(db), None, L.ptr(wsb), st)
 uf, ub = bench(fwd), bench(bwd)
 fl = 2.0 * N * H * V
 print(f"vocab-CE forward  (N={N}, H={H}, V={V}): {uf:7.1f} us  {fl / uf / 1e6:6.1f} TF/s algorithmic")

@@ -25,7 +25,7 @@ L.check(lib.dvae_vocab_ce_fwd(L.ptr(h), H, T1, Bt, H, V, L.ptr(w), L.ptr(bias), 
 for _ in range(5):
     dbg.zero_()
     L.check(lib.dvae_vocab_ce_bwd(L.ptr(h), H, T1, Bt, H, V, L.ptr(w), L.ptr(bias), L.ptr(tg), tg.stride(0), L.ptr(ln), L.ptr(lse), None,
-                                  L.ptr(dh), H, L.ptr(dw), L.ptr(db), L.ptr(wsb), st), "ce bwd")
+                                  L.ptr(dh), H, L.ptr(dw), L.ptr(db), None, L.ptr(wsb), st), "ce bwd")
     torch.cuda.synchronize()
 t = dbg.cpu().tolist()
 print("softmax-gradient kernel (last vocabulary chunk): entry +0.00 us; exit +%.2f us" % ((t[1] - t[0]) / 1e3))

@@ -393,7 +393,8 @@ def test_latent_heads_forward(lib, L, B, C, dims, dsc_out):
 
 
 # ---------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("T1,B,H,V", [(4, 3, 8, 23), (7, 5, 16, 37), (19, 128, 256, 10000), (3, 130, 20, 300), (5, 9, 12, 1000), (6, 50, 64, 3001), (21, 128, 256, 10000)])
+@pytest.mark.parametrize("T1,B,H,V", [(4, 3, 8, 23), (7, 5, 16, 37), (19, 128, 256, 10000), (3, 130, 20, 300), (5, 9, 12, 1000), (6, 50, 64, 3001), (21, 128, 256, 10000),
+                                      (5, 60, 512, 2050), (3, 100, 320, 1100)])     # H > 256: pre-split planes without stationary A
 def test_vocab_ce(lib, L, T1, B, H, V):
     rng = np.random.default_rng(T1 + B + V)
     N, T = T1 * B, T1 + 1
@@ -436,11 +437,17 @@ def test_vocab_ce(lib, L, T1, B, H, V):
     wsb = torch.zeros(lib.dvae_vocab_ce_bwd_ws_floats(N, V, H), device="cuda")
     gs = torch.tensor([1.0], device="cuda")
     L.check(lib.dvae_vocab_ce_bwd(L.ptr(hd), H, T1, B, H, V, L.ptr(Wd), L.ptr(bd), L.ptr(td), T, L.ptr(ld), L.ptr(lse),
-                                  L.ptr(gs), L.ptr(d_h), H, L.ptr(d_w), L.ptr(d_b), L.ptr(wsb), st), "ce bwd")
+                                  L.ptr(gs), L.ptr(d_h), H, L.ptr(d_w), L.ptr(d_b), None, L.ptr(wsb), st), "ce bwd")
     hf = h.reshape(N, H).astype(np.float64)
     assert rel(d_h, dl @ W.astype(np.float64)) < 1e-4
     assert rel(d_w, dl.T @ hf) < 1e-4
     assert rel(d_b, dl.sum(0)) < 1e-4
+    # the same call reusing the forward call's operand planes (fwd_ws) must give the same gradients (split-K atomics: not bitwise)
+    d_h2, d_w2, d_b2 = torch.full_like(d_h, 3.0), torch.full_like(d_w, 3.0), torch.full_like(d_b, 3.0)
+    L.check(lib.dvae_vocab_ce_bwd(L.ptr(hd), H, T1, B, H, V, L.ptr(Wd), L.ptr(bd), L.ptr(td), T, L.ptr(ld), L.ptr(lse),
+                                  L.ptr(gs), L.ptr(d_h2), H, L.ptr(d_w2), L.ptr(d_b2), L.ptr(ws), L.ptr(wsb), st), "ce bwd (fwd_ws)")
+    assert rel(d_h2, d_h.cpu().numpy().astype(np.float64)) < 1e-6 and rel(d_w2, d_w.cpu().numpy().astype(np.float64)) < 1e-6
+    assert rel(d_b2, d_b.cpu().numpy().astype(np.float64)) < 1e-6
 
 
 def test_vocab_ce_simt_path_matches_oracle_too(lib, L, monkeypatch):
