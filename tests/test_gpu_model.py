@@ -183,10 +183,12 @@ def test_train_step_matches_oracle_synthetic(dvae, bi, H, E, V, B, T):
         assert _rel(prm.grad, grads[k]) < 1e-3, k
 
 
-@pytest.mark.parametrize("env", [{"DVAE_GEMM_IMPL": "tf32"}, {"DVAE_GEMM_IMPL": "simt"}, {"DVAE_FORK": "0"}, {"DVAE_LSTM_IMPL": "simt"}, {"DVAE_LSTM_GROUPS": "2"}])
+@pytest.mark.parametrize("env", [{"DVAE_GEMM_IMPL": "tf32"}, {"DVAE_GEMM_IMPL": "simt"}, {"DVAE_FORK": "0"}, {"DVAE_LSTM_IMPL": "simt"}, {"DVAE_LSTM_GROUPS": "2"},
+                                 {"DVAE_VOCAB_PRESPLIT": "0"}])
 def test_train_step_alternative_kernel_paths_match_oracle(dvae, env, monkeypatch):
     """The A/B kernel selections keep the same parity gates: 3xTF32 tcgen05 GEMMs and fp32 SIMT GEMMs instead of the default
-    fp16-split ones, no fork/join side streams, fp32 SIMT persistent LSTM, two row groups per cluster."""
+    fp16-split ones, no fork/join side streams, fp32 SIMT persistent LSTM, two row groups per cluster, vocabulary kernels
+    fed by the converter ring instead of pre-split operand planes."""
     for k, v in env.items():
         monkeypatch.setenv(k, v)
     dvae.set_seed(10)
