@@ -72,6 +72,7 @@ bool force_simt_gemm();
 struct GemmHints {
   const uint32_t* a_amax_bits = nullptr;
   const uint32_t* b_amax_bits = nullptr;
+  int a_amax_n = 1, b_amax_n = 1;      // number of partial maxima behind each pointer (the kernels take their maximum)
   float a_scale = 1.f, b_scale = 1.f;
   bool a_wide = false, b_wide = false;
 };

@@ -215,7 +215,9 @@ __global__ void __launch_bounds__(kHeadsThreads) heads_fwd_kernel(HeadsFwdArgs a
   __syncthreads();
   if (tid == 0) {
     unsigned int* counter = reinterpret_cast<unsigned int*>(a.ws + (int64_t)gridDim.x * 3 * S);
-    is_last = (atomicAdd(counter, 1u) == gridDim.x - 1);
+    // atomicInc wraps to 0 on the last arrival: the counter re-arms itself (no memset node in front of the kernel);
+    // the caller zero-fills ws once before the first call
+    is_last = (atomicInc(counter, gridDim.x - 1) == gridDim.x - 1);
   }
   __syncthreads();
   if (is_last && tid == 0) {
@@ -394,7 +396,6 @@ extern "C" int dvae_latent_heads_fwd(const float* ctx, int B, int C, int S, cons
   size_t smem = sizeof(float) * ((size_t)kRows * C + kRows * 4 * m.Z + kRows * (m.OD > 0 ? m.OD : 1) + 3 * S);
   DVAE_REQUIRE(smem <= 200 * 1024, "dvae_latent_heads_fwd: context width %d too large for shared memory", C);
   if (smem > 48 * 1024) DVAE_CUDA(cudaFuncSetAttribute(heads_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  DVAE_CUDA(cudaMemsetAsync(ws + (int64_t)grid * 3 * S, 0, sizeof(unsigned int), st));
   heads_fwd_kernel<<<grid, kHeadsThreads, smem, st>>>(a, m);
   DVAE_LAUNCH_CHECK();
   return DVAE_OK;

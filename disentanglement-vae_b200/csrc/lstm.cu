@@ -318,6 +318,7 @@ int lstm_seq_bwd_impl(const float* x, int64_t ldx, int T, int B, int I, int H, i
   const int64_t slab = (int64_t)T * B * 4 * H, sf = (int64_t)D * B * H;
   bool persisted = false;
   uint32_t* amax = nullptr;
+  int amax_n = 1;
   {
     const void* ptrs[] = {w_hh[0], w_hh[D - 1], c0, gates, cs, d_hs, d_hn, d_cn, d_h0, d_c0};
     const int64_t lds[] = {ld0, dir0, lddhs, ldn, dirn, ldd0, dird0};
@@ -331,9 +332,9 @@ int lstm_seq_bwd_impl(const float* x, int64_t ldx, int T, int B, int I, int H, i
       if (tc_lstm_supported(H)) {      // the tcgen05 kernel also reports max |dG|: the operand scale of the GEMMs below
         // 8 rotating slots: with deferred joins the previous layers' GEMMs may still be reading theirs
         static thread_local unsigned slot = 0;
-        amax = reinterpret_cast<uint32_t*>(ws + state_floats(B, H, D) + 4LL * D * H * H) + 4 * (slot++ & 7);
-        DVAE_CUDA(cudaMemsetAsync(amax, 0, sizeof(uint32_t), st));
-        a.amax_out = amax;
+        amax = reinterpret_cast<uint32_t*>(ws + state_floats(B, H, D) + 4LL * D * H * H) + amax_slot_entries(B, D) * (slot++ & 7);
+        a.amax_out = amax;               // one entry per CTA of the recurrence kernel (<= amax_slot_entries), written, never accumulated
+        amax_n = tc_lstm_bwd_ctas(B, D);
       }
       int rc = persist_bwd(H, a, st);
       if (rc) return rc;
@@ -374,6 +375,7 @@ int lstm_seq_bwd_impl(const float* x, int64_t ldx, int T, int B, int I, int H, i
   GemmHints gh;
   gh.a_wide = true;
   gh.a_amax_bits = amax;
+  gh.a_amax_n = amax_n;
   // d_x accumulates over the directions (main stream, in order); the weight / bias gradients of each direction are
   // independent of it and of each other: parallel branches
   Fork fork(st);
@@ -465,7 +467,7 @@ extern "C" int dvae_lstm_step(const float* x, int64_t ldx, int t, int T, int B, 
 }
 
 extern "C" int64_t dvae_lstm_state_ws_floats(int B, int H, int D) {
-  return dvae::state_floats(B, H, D) + 4LL * D * H * H + 32;   // + the max |dG| slots of the backward pass
+  return dvae::state_floats(B, H, D) + 4LL * D * H * H + 8 * dvae::amax_slot_entries(B, D);   // + 8 rotating sets of per-CTA max |dG| slots
 }
 
 extern "C" int dvae_lstm_seq_fwd(const float* x, int64_t ldx, int T, int B, int I, int H, int D,

@@ -25,7 +25,7 @@ struct PersistBwdArgs {
   float* d_h0; float* d_c0; int64_t ldd0, dird0;
   const int64_t* lengths;
   int T, B, D, n_slices, d_off;
-  uint32_t* amax_out;            // optional: atomicMax of the bit pattern of max |dG| (operand scale of the dense gradient GEMMs)
+  uint32_t* amax_out;            // optional: [grid size] per-CTA bit patterns of max |dG| (operand scale of the dense gradient GEMMs)
 };
 
 // true when the persistent kernels can take this call (H in {64,128,256}, 16-byte aligned buffers)
@@ -38,5 +38,8 @@ int persist_bwd(int H, const PersistBwdArgs& a, cudaStream_t st);
 bool tc_lstm_supported(int H);
 int tc_lstm_fwd(const PersistFwdArgs& a, cudaStream_t st);
 int tc_lstm_bwd(const PersistBwdArgs& a, cudaStream_t st);
+int tc_lstm_bwd_ctas(int B, int D);          // grid size of that launch (= per-CTA max |dG| entries written)
+// entries reserved per max |dG| slot set: the largest grid the backward kernel can have for (B, D) (one row group per cluster)
+inline int amax_slot_entries(int B, int D) { const int n = 8 * ((B + 15) / 16) * D; return n < 128 ? 128 : n; }
 
 }  // namespace dvae

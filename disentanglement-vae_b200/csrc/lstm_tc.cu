@@ -556,9 +556,15 @@ __global__ void __cluster_dims__(kCS, 1, 1) __launch_bounds__(kGT * G, 1) lstm_t
     tc_fence_before();
     group_sync(grp);
   }
-  if (p.amax_out && lane == 0 && amax_run) atomicMax(p.amax_out, amax_run);
+  // max |dG| of this CTA -> its own slot (plain store: nothing to initialise, no memset node in front of the kernel);
+  // the GEMMs that use dG as an operand take the maximum over the grid's slots
+  __shared__ unsigned s_amax;
+  if (tid == 0) s_amax = 0u;
+  __syncthreads();
+  if (lane == 0 && amax_run) atomicMax(&s_amax, amax_run);
   tc_fence_before();
   __syncthreads();
+  if (p.amax_out && tid == 0) p.amax_out[blockIdx.x] = s_amax;
   cluster.sync();
   if (tid < 32) tmem_dealloc(tmem0, kTB_COLS);
 }
@@ -623,10 +629,16 @@ static int launch_tc_bwd(const PersistBwdArgs& a, cudaStream_t st) {
   return DVAE_OK;
 }
 
-int tc_lstm_bwd(const PersistBwdArgs& a, cudaStream_t st) {
+static int bwd_groups(int B, int D) {
   const char* e = getenv("DVAE_LSTM_GROUPS");
-  const int want = e ? atoi(e) : (a.D * ceil_div(a.B, kNB) <= 15 ? 1 : 2);
-  return want >= 2 ? launch_tc_bwd<2>(a, st) : launch_tc_bwd<1>(a, st);
+  return (e ? atoi(e) : (D * ceil_div(B, kNB) <= 15 ? 1 : 2)) >= 2 ? 2 : 1;
 }
+
+int tc_lstm_bwd(const PersistBwdArgs& a, cudaStream_t st) {
+  return bwd_groups(a.B, a.D) == 2 ? launch_tc_bwd<2>(a, st) : launch_tc_bwd<1>(a, st);
+}
+
+// CTAs of the backward launch = entries written to PersistBwdArgs::amax_out
+int tc_lstm_bwd_ctas(int B, int D) { return kCS * ceil_div(B, kNB * bwd_groups(B, D)) * D; }
 
 }  // namespace dvae

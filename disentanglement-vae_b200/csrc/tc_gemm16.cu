@@ -93,10 +93,12 @@ __device__ __forceinline__ unsigned long long gtime16() {
 #endif
 #define DBG16(i) do { if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) p.dbg[i] = gtime16(); } while (0)
 
-__device__ __forceinline__ float scale_from_amax(const uint32_t* amax_bits, float static_scale) {
+__device__ __forceinline__ float scale_from_amax(const uint32_t* amax_bits, int n, float static_scale) {
   if (!amax_bits) return static_scale;
+  uint32_t mx = 0;                       // bit patterns of non-negative floats order like the floats
+  for (int i = 0; i < n; ++i) mx = max(mx, __ldg(amax_bits + i));
   // 2^(13 - floor(log2 amax)): the largest element lands in [2^13, 2^14), well inside fp16 range
-  int se = 267 - (int)(*amax_bits >> 23);
+  int se = 267 - (int)(mx >> 23);
   se = se < 1 ? 1 : (se > 253 ? 253 : se);
   return __uint_as_float((unsigned)se << 23);
 }
@@ -299,7 +301,7 @@ tc16_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   } else if (warp >= PROD_WARP0 && warp < EPI2_WARP0 && !conv_as_epi) {
     // ===== converters: landed fp32 k-block -> (scale, split) -> fp16 operand planes, in place =====
     const int ptid = tid - PROD_WARP0 * 32;
-    const float sa = scale_from_amax(p.a_amax, p.a_scale), sb = scale_from_amax(p.b_amax, p.b_scale);
+    const float sa = scale_from_amax(p.a_amax, p.a_amax_n, p.a_scale), sb = scale_from_amax(p.b_amax, p.b_amax_n, p.b_scale);
     const int n_items = p.presplit ? 0 : (nt1 - nt0) * nkb;
     int stage = 0, phase = 0;
     for (int it = 0; it < n_items; ++it) {
@@ -388,7 +390,7 @@ tc16_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int row = m0 + quarter * 32 + lane;      // output row owned by this thread (TMEM lane)
     const bool row_ok = row < p.M;
     const float oscale = p.alpha * (p.alpha_dev ? *p.alpha_dev : 1.f) /
-                         (scale_from_amax(p.a_amax, p.a_scale) * scale_from_amax(p.b_amax, p.b_scale));
+                         (scale_from_amax(p.a_amax, p.a_amax_n, p.a_scale) * scale_from_amax(p.b_amax, p.b_amax_n, p.b_scale));
     // per-row state of the fused vocabulary epilogues
     float rm = -INFINITY, rs = 0.f, rt = 0.f, rav = -INFINITY, row_lse = 0.f, row_nlse2 = 0.f, row_scale = 0.f;
     int rai = 0x7fffffff, tgt = -1;
@@ -770,7 +772,7 @@ __global__ void tc16_scale_rows_kernel(float* C, int64_t ldc, int M, int N, floa
 static void apply_hints(Params& p, const GemmHints& h) {
   if (const char* e = getenv("DVAE_TC_DBG")) p.dbg = reinterpret_cast<unsigned long long*>(strtoull(e, nullptr, 0));
   if (const char* e = getenv("DVAE_TC_SKIP_EPILOGUE")) p.dbg_skip_epilogue = atoi(e);     // probes only: main-loop speed in isolation
-  p.a_amax = h.a_amax_bits; p.b_amax = h.b_amax_bits;
+  p.a_amax = h.a_amax_bits; p.b_amax = h.b_amax_bits; p.a_amax_n = h.a_amax_n; p.b_amax_n = h.b_amax_n;
   p.a_scale = h.a_scale; p.b_scale = h.b_scale;
   p.alpha = 1.f; p.alpha_dev = nullptr;
 }

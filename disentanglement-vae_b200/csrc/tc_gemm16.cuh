@@ -17,7 +17,7 @@ struct Params {
   int mode;              // 0: C = act(alpha * acc + bias) + beta*C;  1: vocab-CE forward partials;  2: softmax-gradient tile
   int kb_per_split;      // k-blocks per blockIdx.z (split-K, mode 0; partial tiles are atomically accumulated)
   // power-of-two operand scales: from the bit pattern of a device-side max |x| (when given) or a host constant
-  const uint32_t* a_amax; const uint32_t* b_amax; float a_scale, b_scale;
+  const uint32_t* a_amax; const uint32_t* b_amax; float a_scale, b_scale; int a_amax_n, b_amax_n;
   float alpha; const float* alpha_dev;
   // modes 1 / 2 (rows are decoder positions n = (t-1)*B + b, columns are vocabulary ids)
   const int64_t* targets; int64_t tgt_stride_b; const int64_t* lengths; int B;

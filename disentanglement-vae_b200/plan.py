@@ -77,7 +77,7 @@ class StepPlan:
         # out[:27] = fused-head scalars (weighted KL, KL, dsc loss, per-space ...), out[27] = recon loss
         self.out = torch.zeros(_lib.HEADS_NSCALARS + 5, **f32)
         self.scalars = self.out[:_lib.HEADS_NSCALARS]
-        self.heads_ws = buf(self.lib.dvae_heads_ws_floats(B, d.S))
+        self.heads_ws = torch.zeros(self.lib.dvae_heads_ws_floats(B, d.S), **f32)     # arrival counter must start at zero
         T1 = max(self.T1, 1)
         self.x_dec = buf(T1, B, E)
         Hd = d.Hd

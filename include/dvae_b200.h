@@ -211,7 +211,8 @@ int dvae_lstm_seq_bwd(const float* x, int64_t ldx, int T, int B, int I, int H, i
  *   dsc_logits [B, sum(out)]; scalars[ ] (device, DVAE_HEADS_NSCALARS floats):
  *   [0] total_weighted_kl, [1] total_kl, [2] total_dsc_loss, [3..3+S) kl per space,
  *   [3+S..3+2S) dsc loss per space (0 where none), [3+2S..3+3S) dsc accuracy per space.
- *   ws: dvae_heads_ws_floats(B,S) floats of scratch (zeroed by the call).
+ *   ws: dvae_heads_ws_floats(B,S) floats of scratch, zero-filled by the caller before the FIRST call (every call leaves
+ *   its arrival counter re-armed).
  * ------------------------------------------------------------------------------------------- */
 #define DVAE_HEADS_NSCALARS (3 + 3 * DVAE_MAX_SPACES)
 int64_t dvae_heads_ws_floats(int B, int S);
