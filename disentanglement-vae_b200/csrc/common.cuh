@@ -75,6 +75,7 @@ struct GemmHints {
   int a_amax_n = 1, b_amax_n = 1;      // number of partial maxima behind each pointer (the kernels take their maximum)
   float a_scale = 1.f, b_scale = 1.f;
   bool a_wide = false, b_wide = false;
+  bool c_zeroed = false;               // with beta == 0: C already holds zeros (a split-K GEMM then skips its memset node)
 };
 int linear_impl_ex(const float* A, int64_t lda, int trans_a, const float* B, int64_t ldb, int trans_b, float* C,
                    int64_t ldc, int M, int N, int K, const float* bias, const float* bias2, float beta, int act,

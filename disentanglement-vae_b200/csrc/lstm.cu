@@ -319,6 +319,7 @@ int lstm_seq_bwd_impl(const float* x, int64_t ldx, int T, int B, int I, int H, i
   bool persisted = false;
   uint32_t* amax = nullptr;
   int amax_n = 1;
+  bool dx_zeroed = false;
   {
     const void* ptrs[] = {w_hh[0], w_hh[D - 1], c0, gates, cs, d_hs, d_hn, d_cn, d_h0, d_c0};
     const int64_t lds[] = {ld0, dir0, lddhs, ldn, dirn, ldd0, dird0};
@@ -329,12 +330,17 @@ int lstm_seq_bwd_impl(const float* x, int64_t ldx, int T, int B, int I, int H, i
       a.d_hn = d_hn; a.d_cn = d_cn; a.ldn = ldn; a.dirn = dirn; a.d_h0 = d_h0; a.d_c0 = d_c0; a.ldd0 = ldd0;
       a.dird0 = dird0; a.lengths = lengths; a.T = T; a.B = B; a.D = D; a.n_slices = ceil_div(B, 16); a.d_off = 0;
       a.amax_out = nullptr;
+      a.zero_buf = nullptr; a.zero_n4 = 0;
       if (tc_lstm_supported(H)) {      // the tcgen05 kernel also reports max |dG|: the operand scale of the GEMMs below
         // 8 rotating slots: with deferred joins the previous layers' GEMMs may still be reading theirs
         static thread_local unsigned slot = 0;
         amax = reinterpret_cast<uint32_t*>(ws + state_floats(B, H, D) + 4LL * D * H * H) + amax_slot_entries(B, D) * (slot++ & 7);
         a.amax_out = amax;               // one entry per CTA of the recurrence kernel (<= amax_slot_entries), written, never accumulated
         amax_n = tc_lstm_bwd_ctas(B, D);
+        if (d_x && lddx == I && (((uintptr_t)d_x) & 15) == 0 && ((int64_t)T * B * I) % 4 == 0 && d_x != d_hs) {
+          a.zero_buf = d_x; a.zero_n4 = (int64_t)T * B * I / 4;
+          dx_zeroed = true;
+        }
       }
       int rc = persist_bwd(H, a, st);
       if (rc) return rc;
@@ -383,7 +389,9 @@ int lstm_seq_bwd_impl(const float* x, int64_t ldx, int T, int B, int I, int H, i
     const float* dG = gates + d * slab;
     int rc;
     if (d_x) {
-      rc = linear_impl_ex(dG, 4 * H, 0, w_ih[d], I, 1, d_x, lddx, T * B, I, 4 * H, nullptr, nullptr, d == 0 ? 0.f : 1.f, 0, gh, st);
+      GemmHints ghx = gh;
+      ghx.c_zeroed = dx_zeroed;
+      rc = linear_impl_ex(dG, 4 * H, 0, w_ih[d], I, 1, d_x, lddx, T * B, I, 4 * H, nullptr, nullptr, d == 0 ? 0.f : 1.f, 0, ghx, st);
       if (rc) return rc;
     }
     if (d_w_ih && d_w_ih[d]) {

@@ -26,6 +26,7 @@ struct PersistBwdArgs {
   const int64_t* lengths;
   int T, B, D, n_slices, d_off;
   uint32_t* amax_out;            // optional: [grid size] per-CTA bit patterns of max |dG| (operand scale of the dense gradient GEMMs)
+  float* zero_buf; int64_t zero_n4;   // optional: float4s cleared by the kernel on its way in (d_x, which a split-K GEMM accumulates into)
 };
 
 // true when the persistent kernels can take this call (H in {64,128,256}, 16-byte aligned buffers)

@@ -431,6 +431,11 @@ __global__ void __cluster_dims__(kCS, 1, 1) __launch_bounds__(kGT * G, 1) lstm_t
   const int nsteps = T + ((p.d_h0 || p.d_c0) ? 1 : 0);
   unsigned amax_run = 0;           // bit pattern of max |dG| over this warp's row, all steps
   pdl_wait();                      // from here on the predecessor's outputs (d_hs, d_hn / d_cn) are read
+  if (p.zero_buf) {                // d_x of this layer: cleared here, spread over the grid, instead of by a memset node
+    float4* z4 = reinterpret_cast<float4*>(p.zero_buf);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + tid; i < p.zero_n4; i += (int64_t)gridDim.x * blockDim.x)
+      z4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
   float carry = (p.d_hn && pb < B) ? p.d_hn[d * p.dirn + (int64_t)pb * p.ldn + u0 + lane] : 0.f;
   float dc = (p.d_cn && pb < B) ? p.d_cn[d * p.dirn + (int64_t)pb * p.ldn + u0 + lane] : 0.f;
 

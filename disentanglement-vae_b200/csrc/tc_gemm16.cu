@@ -201,6 +201,18 @@ tc16_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   // this grid to complete (griddepcontrol.wait) before it reads anything written here
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   if (tid == 0) DBG16(0);
+  if (p.zero_buf) {
+    // a buffer some later split-K GEMM accumulates into (e.g. d_h of the vocabulary backward): zeroed here, spread over
+    // the grid, instead of by a memset node in front of that GEMM
+    float4* z4 = reinterpret_cast<float4*>(p.zero_buf);
+    const int64_t nblk = (int64_t)gridDim.x * gridDim.y * gridDim.z;
+    const int64_t blk = ((int64_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+    for (int64_t i = blk * NUM_THREADS + tid; i < p.zero_n4; i += nblk * NUM_THREADS) z4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (p.zero_buf2) {
+      float4* y4 = reinterpret_cast<float4*>(p.zero_buf2);
+      for (int64_t i = blk * NUM_THREADS + tid; i < p.zero2_n4; i += nblk * NUM_THREADS) y4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
   const int m0 = blockIdx.x * BM;
   const int nt0 = blockIdx.y * p.tiles_per_cta;
   const int n_tiles = (p.N + BN - 1) / BN;
@@ -803,7 +815,7 @@ int linear(const float* A, int64_t lda, int trans_a, const float* B, int64_t ldb
   }
   p.kb_per_split = ceil_div(nkb, splits);
   splits = ceil_div(nkb, p.kb_per_split);
-  if (splits > 1 && beta != 1.f) {
+  if (splits > 1 && beta != 1.f && !(beta == 0.f && hints.c_zeroed)) {
     if (beta == 0.f && ldc == N) {
       DVAE_CUDA(cudaMemsetAsync(C, 0, sizeof(float) * (size_t)M * N, st));
     } else {
@@ -833,8 +845,11 @@ int ce_partials(const float* h, int64_t ldh, int N, int B, int H, int V, const f
 
 int softmax_grad(const float* h, int64_t ldh, int N, int B, int H, int V, int v0, int vc, const float* w, const float* bias,
                  const int64_t* targets, int64_t tgt_stride_b, const int64_t* lengths, const float* lse,
-                 const float* grad_scale, float* P, int64_t ldp, const void* h_planes, const void* w_planes, cudaStream_t st) {
+                 const float* grad_scale, float* P, int64_t ldp, const void* h_planes, const void* w_planes, float* zero_buf,
+                 int64_t zero_n4, float* zero_buf2, int64_t zero2_n4, cudaStream_t st) {
   Params p = {};
+  p.zero_buf = zero_buf; p.zero_n4 = zero_n4; p.zero_buf2 = zero_buf2; p.zero2_n4 = zero2_n4;
+  if (!p.zero_buf) { p.zero_buf = p.zero_buf2; p.zero_n4 = p.zero2_n4; p.zero_buf2 = nullptr; p.zero2_n4 = 0; }
   DVAE_REQUIRE(!(h_planes && w_planes) || v0 % BN == 0, "tc16 softmax_grad: pre-split chunks must start on a %d-row block (v0=%d)", BN, v0);
   if (h_planes && w_planes) { p.presplit = 1; p.a_planes = h_planes; p.b_planes = w_planes; p.a_rows = N; p.b_rows = V; p.b_row0 = v0; }
   p.A = h; p.lda = ldh; p.Bm = w + (int64_t)v0 * H; p.ldb = H;

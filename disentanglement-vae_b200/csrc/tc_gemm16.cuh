@@ -25,6 +25,8 @@ struct Params {
   const float* lse; const float* grad_scale; int v0;   // mode 2: C = P[:, v0:v0+N]
   const uint64_t* gumbel_seed; uint32_t gumbel_salt;   // mode 1: when set, the arg-max is taken over logits + Gumbel noise
   // pre-split mode: the operands are fp16 (hi, lo) planes in global memory (split_planes), blocked by core matrix
+  float* zero_buf; int64_t zero_n4;      // optional: up to two buffers (float4 counts) the kernel clears on its way in
+  float* zero_buf2; int64_t zero2_n4;    //           (outputs of later split-K GEMMs; see tc_gemm16.cu)
   int presplit; int b_row0;     // b_row0: first B row of this call inside the B planes (a vocabulary chunk)
   const void* a_planes; const void* b_planes; int a_rows, b_rows;      // tile-blocked fp16 planes (split_planes)
   int dbg_skip_epilogue;     // probes only (DVAE_TC_SKIP_EPILOGUE=1): accumulators are released unread
@@ -49,7 +51,8 @@ int ce_partials(const float* h, int64_t ldh, int N, int B, int H, int V, const f
                 const void* w_planes, cudaStream_t st);
 int softmax_grad(const float* h, int64_t ldh, int N, int B, int H, int V, int v0, int vc, const float* w, const float* bias,
                  const int64_t* targets, int64_t tgt_stride_b, const int64_t* lengths, const float* lse,
-                 const float* grad_scale, float* P, int64_t ldp, const void* h_planes, const void* w_planes, cudaStream_t st);
+                 const float* grad_scale, float* P, int64_t ldp, const void* h_planes, const void* w_planes, float* zero_buf,
+                 int64_t zero_n4, float* zero_buf2, int64_t zero2_n4, cudaStream_t st);
 
 }  // namespace tc16
 }  // namespace dvae

@@ -392,9 +392,15 @@ extern "C" int dvae_vocab_ce_bwd(const float* h, int64_t ldh, int T1, int B, int
     const int vc = min(vc_max, V - v0);
     p.v0 = v0; p.vc = vc;
     int rc;
+    bool dh_zeroed = false, dw_zeroed = false;
     if (!force_simt_gemm() && N >= 64 && vc >= 128 && H >= 32 && tc16::supported(h, ldh, 0, w, H, 0, N, vc, H)) {
+      // the kernel also clears the outputs of this chunk's split-K GEMMs (d_h once, this chunk's rows of d_w): no memset nodes
+      const bool zh = chunk == 0 && lddh == H && (((uintptr_t)d_h) & 15) == 0 && ((int64_t)N * H) % 4 == 0;
+      const bool zw = (((uintptr_t)(d_w + (int64_t)v0 * H)) & 15) == 0 && ((int64_t)vc * H) % 4 == 0;
       if ((rc = tc16::softmax_grad(h, ldh, N, B, H, V, v0, vc, w, bias, targets, tgt_stride_b, lengths, lse, grad_scale_dev, ws,
-                                   vc_max, h_planes, w_planes, st))) return rc;
+                                   vc_max, h_planes, w_planes, zh ? d_h : nullptr, (int64_t)N * H / 4,
+                                   zw ? d_w + (int64_t)v0 * H : nullptr, (int64_t)vc * H / 4, st))) return rc;
+      dh_zeroed = zh; dw_zeroed = zw;
     } else if (!force_simt_gemm() && N >= 64 && vc >= 128 && H >= 32 && tc::tc_linear_supported(h, ldh, w, H, N, vc, H)) {
       if ((rc = tc::tc_softmax_grad(h, ldh, N, B, H, v0, vc, w, bias, targets, tgt_stride_b, lengths, lse, grad_scale_dev, ws,
                                     vc_max, st))) return rc;
@@ -405,9 +411,11 @@ extern "C" int dvae_vocab_ce_bwd(const float* h, int64_t ldh, int T1, int B, int
     }
     // d_h [N,H] (+)= P [N,vc] . W[v0:v0+vc, :]        (B stored [K=vc][N=H])
     Fork fork(st);         // the three consumers of this chunk of P are independent of each other
-    if ((rc = linear_impl_ex(ws, vc_max, 0, w + (int64_t)v0 * H, H, 1, d_h, lddh, N, H, vc, nullptr, nullptr, chunk ? 1.f : 0.f, 0, ph, st))) return rc;
+    GemmHints ph_h = ph, ph_w = ph;
+    ph_h.c_zeroed = dh_zeroed; ph_w.c_zeroed = dw_zeroed;
+    if ((rc = linear_impl_ex(ws, vc_max, 0, w + (int64_t)v0 * H, H, 1, d_h, lddh, N, H, vc, nullptr, nullptr, chunk ? 1.f : 0.f, 0, ph_h, st))) return rc;
     // d_w[v0:v0+vc, :] = P^T [vc,N] . h [N,H]
-    if ((rc = linear_impl_ex(ws, vc_max, 1, h, ldh, 1, d_w + (int64_t)v0 * H, H, vc, H, N, nullptr, nullptr, 0.f, 0, ph, fork.side(0)))) return rc;
+    if ((rc = linear_impl_ex(ws, vc_max, 1, h, ldh, 1, d_w + (int64_t)v0 * H, H, vc, H, N, nullptr, nullptr, 0.f, 0, ph_w, fork.side(0)))) return rc;
     if ((rc = colsum_impl(ws, vc_max, N, vc, d_bias + v0, 0.f, fork.side(1)))) return rc;
     if ((rc = fork.join())) return rc;       // the next chunk overwrites P
   }
