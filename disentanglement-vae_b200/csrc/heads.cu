@@ -6,6 +6,7 @@
 // tanh(z2hidden(z)).  Each CTA owns kRows batch rows (context rows staged in shared memory, weight
 // rows streamed coalesced from L2, warp-shuffle reductions); per-CTA partial sums are combined in a
 // fixed order by the last CTA to finish, so the scalars are bit-reproducible.
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace dvae {
@@ -50,7 +51,9 @@ struct HeadsFwdArgs {
   const float *ctx, *w_c2p, *b_c2p, *eps, *w_dsc, *b_dsc, *labels, *kl_w, *w_z2h, *b_z2h;
   float *z, *mu, *logvar, *hid, *dsc_logits, *scalars, *ws;
   int B, C, H2L;
+  unsigned long long* dbg;       // probes (DVAE_HEADS_DBG=<device address>): globaltimer marks of CTA 0
 };
+#define HEADS_MARK(i) do { if (a.dbg && blockIdx.x == 0 && threadIdx.x == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); a.dbg[i] = t_; } } while (0)
 
 __device__ __forceinline__ int space_of(const HeadsMeta& m, int zi) {
   int s = 0;
@@ -68,12 +71,14 @@ __global__ void __launch_bounds__(kHeadsThreads) heads_fwd_kernel(HeadsFwdArgs a
   float* lg_s = klt_s + kRows * Z;           // [kRows][OD]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = kHeadsThreads / 32;
   const int b0 = blockIdx.x * kRows;
+  HEADS_MARK(0);
 
   for (int i = tid; i < kRows * C; i += kHeadsThreads) {
     int r = i / C, k = i % C;
     ctx_s[i] = (b0 + r < B) ? a.ctx[(int64_t)(b0 + r) * C + k] : 0.f;
   }
   __syncthreads();
+  HEADS_MARK(1);
   // (mu, raw) projections: each warp owns 4 output columns per pass (4 independent coalesced weight streams in
   // flight per lane), lanes stride the context width, shuffle reduction
   for (int j0 = warp * 4; j0 < 2 * Z; j0 += nwarp * 4) {
@@ -120,6 +125,7 @@ __global__ void __launch_bounds__(kHeadsThreads) heads_fwd_kernel(HeadsFwdArgs a
       }
   }
   __syncthreads();
+  HEADS_MARK(2);
   // reparameterisation + KL terms
   for (int i = tid; i < kRows * Z; i += kHeadsThreads) {
     int r = i / Z, zi = i % Z, b = b0 + r;
@@ -151,6 +157,7 @@ __global__ void __launch_bounds__(kHeadsThreads) heads_fwd_kernel(HeadsFwdArgs a
     lg_s[i] = acc;
     if (b < B) a.dsc_logits[(int64_t)b * OD + od] = acc;
   }
+  HEADS_MARK(3);
   // decoder initial state: hid = tanh(z . Wz^T + bz); one thread per output column, vectorised weight row
   for (int j = tid; j < a.H2L; j += kHeadsThreads) {
     const float* w = a.w_z2h + (int64_t)j * Z;
@@ -179,6 +186,7 @@ __global__ void __launch_bounds__(kHeadsThreads) heads_fwd_kernel(HeadsFwdArgs a
       if (b0 + r < B) a.hid[(int64_t)(b0 + r) * a.H2L + j] = tanhf(acc[r]);
   }
   __syncthreads();
+  HEADS_MARK(4);
   // per-CTA partial sums, fixed order: thread s handles space s
   if (tid < S) {
     const int s = tid;
@@ -209,6 +217,7 @@ __global__ void __launch_bounds__(kHeadsThreads) heads_fwd_kernel(HeadsFwdArgs a
     float* part = a.ws + (int64_t)blockIdx.x * 3 * S;
     part[s] = kl; part[S + s] = dl; part[2 * S + s] = da;
   }
+  HEADS_MARK(5);
   // last CTA combines the partials in block order
   __shared__ int is_last;
   __threadfence();
@@ -220,14 +229,28 @@ __global__ void __launch_bounds__(kHeadsThreads) heads_fwd_kernel(HeadsFwdArgs a
     is_last = (atomicInc(counter, gridDim.x - 1) == gridDim.x - 1);
   }
   __syncthreads();
+  // all threads of the last CTA fetch the partials into shared memory in parallel; thread 0 then adds them in block
+  // order from there (a single thread walking 3*S*grid dependent L2 loads was a serial tail of this kernel)
+  const int n_part = (int)gridDim.x * 3 * S;
+  const bool staged = n_part <= kRows * C;          // ctx_s is free by now
+  if (is_last && staged) {
+    __threadfence();
+    for (int i = tid; i < n_part; i += kHeadsThreads) ctx_s[i] = __ldcg(a.ws + i);
+  }
+  __syncthreads();
   if (is_last && tid == 0) {
     __threadfence();
     float wkl = 0.f, tkl = 0.f, tdl = 0.f;
     for (int s = 0; s < S; ++s) {
       float kl = 0.f, dl = 0.f, da = 0.f;
       for (unsigned int c = 0; c < gridDim.x; ++c) {
-        const volatile float* part = a.ws + (int64_t)c * 3 * S;
-        kl += part[s]; dl += part[S + s]; da += part[2 * S + s];
+        if (staged) {
+          const float* part = ctx_s + c * 3 * S;
+          kl += part[s]; dl += part[S + s]; da += part[2 * S + s];
+        } else {
+          const volatile float* part = a.ws + (int64_t)c * 3 * S;
+          kl += part[s]; dl += part[S + s]; da += part[2 * S + s];
+        }
       }
       kl /= (float)B;
       dl /= (float)(B * (m.dout[s] == 1 ? 1 : 1));
@@ -241,6 +264,7 @@ __global__ void __launch_bounds__(kHeadsThreads) heads_fwd_kernel(HeadsFwdArgs a
     }
     a.scalars[0] = wkl; a.scalars[1] = tkl; a.scalars[2] = tdl;
   }
+  HEADS_MARK(6);
 }
 
 // ---- backward ---------------------------------------------------------------------------------
@@ -391,7 +415,8 @@ extern "C" int dvae_latent_heads_fwd(const float* ctx, int B, int C, int S, cons
   if (rc) return rc;
   DVAE_REQUIRE(m.OD == 0 || (w_dsc && b_dsc && dsc_logits), "dvae_latent_heads_fwd: discriminator buffers missing");
   HeadsFwdArgs a{ctx, w_c2p, b_c2p, eps, w_dsc, b_dsc, labels, kl_w_dev, w_z2h, b_z2h,
-                 z, mu, logvar, hid, dsc_logits, scalars, ws, B, C, H2L};
+                 z, mu, logvar, hid, dsc_logits, scalars, ws, B, C, H2L, nullptr};
+  if (const char* e = getenv("DVAE_HEADS_DBG")) a.dbg = reinterpret_cast<unsigned long long*>(strtoull(e, nullptr, 0));
   const int grid = ceil_div(B, kRows);
   size_t smem = sizeof(float) * ((size_t)kRows * C + kRows * 4 * m.Z + kRows * (m.OD > 0 ? m.OD : 1) + 3 * S);
   DVAE_REQUIRE(smem <= 200 * 1024, "dvae_latent_heads_fwd: context width %d too large for shared memory", C);
