@@ -383,6 +383,19 @@ def main():
     torch.cuda.synchronize()
     adam_ms = float(np.median([a.elapsed_time(b) for a, b in eva]))
 
+    # ---- K2 latent heads (one launch) and K1 encoder forward (embedding, 4 input GEMMs, 2 recurrence kernels), timed alone ----
+    def _timed(fn, n=10):
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n)]
+        for a, b in evs:
+            flush.zero_()
+            a.record()
+            fn()
+            b.record()
+        torch.cuda.synchronize()
+        return float(np.median([a.elapsed_time(b) for a, b in evs]))
+    heads_ms = _timed(lambda: pl.heads(P, pl.ctx, pl.eps, eng.labels, eng.kl_w))
+    enc_ms = _timed(lambda: pl.encode(P, eng.inputs, eng.lengths, True))
+
     stats = torch.tensor([dev_ms, e2e_s, float(tok_sum), float(e2e_tok)], dtype=torch.float64, device=dev)
     if world > 1:
         mx = stats.clone()
@@ -411,6 +424,10 @@ def main():
     kname = ("tc_gemm_kernel mode 1 (TMA + tcgen05.mma.kind::tf32, 3xTF32)" if gemm_impl.startswith("t")
              else "tc16_gemm_kernel mode 1 (pre-split fp16 hi/lo operand planes by bulk copy, A rows stationary in SMEM, tcgen05.mma.kind::f16, two TMEM accumulators, 16 epilogue warps)")
     n_par = eng.n
+    Zt = d.Z
+    heads_bytes = 4.0 * (B * d.C + d.C * 2 * Zt + 2 * Zt + B * Zt + 3 * B * Zt + Zt * d.H2L + B * d.H2L)
+    Dn = 2 if CFG2.get("bidirectional_encoder", True) else 1
+    enc_flops = float(B * T) * (Dn * 8 * d.H * (d.E + d.H) + Dn * 8 * d.H * (Dn * d.H + d.H))                 # SURVEY 8a, per position
     adam_bytes = 36.0 * n_par                   # sumsq reads g; clip+Adam reads p, g, m, v and writes p, m, v and the zeroed g
     roof = {"kernel": kname + " = vocab-CE forward: vocabulary projection + online log-softmax / arg-max / NLL epilogue from TMEM; "
                               "the [N,V] logits are never written to HBM; ONE launch between the CUDA events (dvae_vocab_ce_partials)",
@@ -423,7 +440,19 @@ def main():
             "secondary": [{"kernel": "sumsq_kernel + clip_adam_kernel (grad-norm clip 5.0 + Adam + zero_grad over the flat parameter buffer)",
                            "bound": "hbm", "achieved": adam_bytes / (adam_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                            "frac": adam_bytes / (adam_ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "launch_ms": adam_ms,
-                           "algorithmic_bytes": adam_bytes}]}
+                           "algorithmic_bytes": adam_bytes},
+                          {"kernel": "heads_fwd_kernel (context2params, reparameterisation, KL, discriminators + losses, z2hidden: ONE launch)",
+                           "bound": "hbm", "achieved": heads_bytes / (heads_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                           "frac": heads_bytes / (heads_ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "launch_ms": heads_ms,
+                           "algorithmic_bytes": heads_bytes,
+                           "note": "launch/latency bound as SURVEY 8d predicts; inside the kernel every CTA streams the full weight "
+                                   "matrices from L2 (profiles/probes/heads_timeline.py)"},
+                          {"kernel": "encoder forward = embedding + dropout + 2 layers x (2 input-projection GEMMs + 1 persistent "
+                                     "bidirectional tcgen05 recurrence kernel)",
+                           "bound": "latency", "achieved": enc_flops / (enc_ms * 1e-3) / 1e12, "peak": peaks["bf16_tflops"],
+                           "unit": "TFLOP/s", "frac": enc_flops / (enc_ms * 1e-3) / 1e12 / peaks["bf16_tflops"], "launch_ms": enc_ms,
+                           "algorithmic_flops": enc_flops, "sequential_steps": 2 * T,
+                           "us_per_sequential_step": enc_ms * 1e3 / (2 * T)}]}
     line = {"metric": "train_tokens_per_sec", "value": tok_sum / (dev_ms * 1e-3), "unit": "tokens/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
