@@ -47,6 +47,9 @@ SIGNATURES = {
     "dvae_lstm_state_ws_floats": (_l, [_i, _i, _i]),
     "dvae_lstm_seq_fwd": (_i, [_p, _l, _i, _i, _i, _i, _i, _pp, _pp, _pp, _pp, _p, _p, _l, _l, _p, _p, _l, _p, _p,
                                _l, _l, _p, _p, _p, _p]),
+    "dvae_lstm_input_proj": (_i, [_p, _l, _i, _i, _i, _i, _i, _pp, _pp, _pp, _p, _p]),
+    "dvae_lstm_seq_fwd_ex": (_i, [_p, _l, _i, _i, _i, _i, _i, _pp, _pp, _pp, _pp, _p, _p, _l, _l, _p, _p, _l, _p, _p,
+                                  _l, _l, _p, _p, _p, _i, _p]),
     "dvae_lstm_seq_bwd": (_i, [_p, _l, _i, _i, _i, _i, _i, _pp, _pp, _p, _p, _l, _l, _p, _p, _l, _p, _p, _p, _l,
                                _p, _p, _l, _l, _p, _l, _pp, _pp, _pp, _pp, _p, _p, _l, _l, _p, _p]),
     "dvae_heads_ws_floats": (_l, [_i, _i]),
@@ -58,6 +61,8 @@ SIGNATURES = {
     "dvae_dsc_loss": (_i, [_p, _p, _i, _i, _ip, _ip, _p, _p, _p, _p]),
     "dvae_vocab_ce_ws_floats": (_l, [_i, _i, _i]),
     "dvae_vocab_ce_fwd": (_i, [_p, _l, _i, _i, _i, _i, _p, _p, _p, _l, _p, _i, _p, _p, _p, _p, _p, _p]),
+    "dvae_vocab_split_w": (_i, [_p, _i, _i, _i, _p, _p]),
+    "dvae_vocab_ce_fwd_ex": (_i, [_p, _l, _i, _i, _i, _i, _p, _p, _p, _l, _p, _i, _p, _p, _p, _p, _p, _i, _p]),
     "dvae_vocab_ce_partials": (_i, [_p, _l, _i, _i, _i, _i, _p, _p, _p, _l, _p, _i, _p, _p]),
     "dvae_vocab_ce_bwd_ws_floats": (_l, [_i, _i, _i]),
     "dvae_vocab_ce_bwd": (_i, [_p, _l, _i, _i, _i, _i, _p, _p, _p, _l, _p, _p, _p, _p, _l, _p, _p, _p, _p, _p]),

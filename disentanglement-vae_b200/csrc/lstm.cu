@@ -244,23 +244,32 @@ static bool force_step_path() {
 }
 static int64_t state_floats(int B, int H, int D) { return 4LL * D * B * H; }
 
+// gates[d] [T*B, 4H] = x . W_ih[d]^T + b_ih[d] + b_hh[d]: the time-parallel half of the layer (one GEMM per direction)
+int lstm_input_proj_impl(const float* x, int64_t ldx, int T, int B, int I, int H, int D, const float* const* w_ih,
+                         const float* const* b_ih, const float* const* b_hh, float* gates, cudaStream_t st) {
+  DVAE_REQUIRE(x && gates && w_ih, "dvae_lstm_input_proj: null pointer");
+  DVAE_REQUIRE(T > 0 && B > 0 && I > 0 && H > 0 && (D == 1 || D == 2), "dvae_lstm_input_proj: bad shape T=%d B=%d I=%d H=%d D=%d", T, B, I, H, D);
+  const int64_t slab = (int64_t)T * B * 4 * H;
+  Fork fork(st);           // the two directions' input projections are independent
+  for (int d = 0; d < D; ++d) {
+    int rc = linear_impl(x, ldx, 0, w_ih[d], I, 0, gates + d * slab, 4 * H, T * B, 4 * H, I, b_ih ? b_ih[d] : nullptr,
+                         b_hh ? b_hh[d] : nullptr, 0.f, 0, d == 0 ? st : fork.side(0));
+    if (rc) return rc;
+  }
+  return fork.join();
+}
+
 int lstm_seq_fwd_impl(const float* x, int64_t ldx, int T, int B, int I, int H, int D, const float* const* w_ih,
                       const float* const* w_hh, const float* const* b_ih, const float* const* b_hh,
                       const float* h0, const float* c0, int64_t ld0, int64_t dir0, const int64_t* lengths,
                       float* hs, int64_t ldhs, float* hn, float* cn, int64_t ldn, int64_t dirn, float* gates,
-                      float* cs, float* ws, cudaStream_t st) {
+                      float* cs, float* ws, bool gates_ready, cudaStream_t st) {
   DVAE_REQUIRE(x && hs && gates && cs && ws && w_ih && w_hh, "dvae_lstm_seq_fwd: null pointer");
   DVAE_REQUIRE(T > 0 && B > 0 && I > 0 && H > 0 && (D == 1 || D == 2), "dvae_lstm_seq_fwd: bad shape T=%d B=%d I=%d H=%d D=%d", T, B, I, H, D);
   DVAE_REQUIRE(!(lengths && h0), "dvae_lstm_seq_fwd: length-masked layers start from the zero state");
-  const int64_t slab = (int64_t)T * B * 4 * H, sf = (int64_t)D * B * H;
-  {
-    Fork fork(st);           // the two directions' input projections are independent
-    for (int d = 0; d < D; ++d) {
-      int rc = linear_impl(x, ldx, 0, w_ih[d], I, 0, gates + d * slab, 4 * H, T * B, 4 * H, I, b_ih ? b_ih[d] : nullptr,
-                           b_hh ? b_hh[d] : nullptr, 0.f, 0, d == 0 ? st : fork.side(0));
-      if (rc) return rc;
-    }
-    int rc = fork.join();
+  const int64_t sf = (int64_t)D * B * H;
+  if (!gates_ready) {
+    int rc = lstm_input_proj_impl(x, ldx, T, B, I, H, D, w_ih, b_ih, b_hh, gates, st);
     if (rc) return rc;
   }
   {
@@ -485,7 +494,26 @@ extern "C" int dvae_lstm_seq_fwd(const float* x, int64_t ldx, int T, int B, int 
                                  float* cn, int64_t ldn, int64_t dirn, float* gates, float* cs, float* state_ws,
                                  void* stream) {
   return dvae::lstm_seq_fwd_impl(x, ldx, T, B, I, H, D, w_ih, w_hh, b_ih, b_hh, h0, c0, ld0, dir0, lengths, hs,
-                                 ldhs, hn, cn, ldn, dirn, gates, cs, state_ws, (cudaStream_t)stream);
+                                 ldhs, hn, cn, ldn, dirn, gates, cs, state_ws, false, (cudaStream_t)stream);
+}
+
+// The two halves of dvae_lstm_seq_fwd separately, so that a caller can run a layer's input projection early, on another
+// stream (the decoder's layer-0 projection under teacher forcing depends on the input tokens only, not on the encoder):
+// dvae_lstm_input_proj fills `gates`; dvae_lstm_seq_fwd_ex with flags bit 0 set then runs the recurrence alone.
+extern "C" int dvae_lstm_input_proj(const float* x, int64_t ldx, int T, int B, int I, int H, int D,
+                                    const float* const* w_ih, const float* const* b_ih, const float* const* b_hh,
+                                    float* gates, void* stream) {
+  return dvae::lstm_input_proj_impl(x, ldx, T, B, I, H, D, w_ih, b_ih, b_hh, gates, (cudaStream_t)stream);
+}
+
+extern "C" int dvae_lstm_seq_fwd_ex(const float* x, int64_t ldx, int T, int B, int I, int H, int D,
+                                    const float* const* w_ih, const float* const* w_hh, const float* const* b_ih,
+                                    const float* const* b_hh, const float* h0, const float* c0, int64_t ld0,
+                                    int64_t dir0, const int64_t* lengths, float* hs, int64_t ldhs, float* hn,
+                                    float* cn, int64_t ldn, int64_t dirn, float* gates, float* cs, float* state_ws,
+                                    int flags, void* stream) {
+  return dvae::lstm_seq_fwd_impl(x, ldx, T, B, I, H, D, w_ih, w_hh, b_ih, b_hh, h0, c0, ld0, dir0, lengths, hs,
+                                 ldhs, hn, cn, ldn, dirn, gates, cs, state_ws, (flags & 1) != 0, (cudaStream_t)stream);
 }
 
 extern "C" int dvae_lstm_seq_bwd(const float* x, int64_t ldx, int T, int B, int I, int H, int D,

@@ -317,10 +317,28 @@ extern "C" int64_t dvae_vocab_ce_ws_floats(int N, int V, int H) {
   return ce_part_floats(N, V) + tc16::plane_floats(N, H) + tc16::plane_floats(V, H);
 }
 
-extern "C" int dvae_vocab_ce_fwd(const float* h, int64_t ldh, int T1, int B, int H, int V, const float* w,
-                                 const float* bias, const int64_t* targets, int64_t tgt_stride_b,
-                                 const int64_t* lengths, int sos, float* lse, float* nll, int32_t* argmax,
-                                 float* loss, float* ws, void* stream) {
+// (ws, w) of the last dvae_vocab_split_w call that actually wrote W planes on this host thread
+static thread_local const void* g_wsplit_ws = nullptr;
+static thread_local const void* g_wsplit_w = nullptr;
+
+// The W half of the operand split of dvae_vocab_ce_fwd, as a call of its own: W_out does not depend on the step's
+// activations, so a caller can run this early, on another stream, and pass flags bit 0 to dvae_vocab_ce_fwd_ex.
+// N, V, H and ws as in the forward call that follows.  A no-op for shapes the pre-split kernels do not take.
+extern "C" int dvae_vocab_split_w(const float* w, int N, int V, int H, float* ws, void* stream) {
+  DVAE_REQUIRE(w && ws && N > 0 && V > 0 && H > 0, "dvae_vocab_split_w: bad argument");
+  g_wsplit_ws = g_wsplit_w = nullptr;
+  if (force_simt_gemm() || !tc16::enabled() || !use_presplit(N, V, H) || (reinterpret_cast<uintptr_t>(w) & 15)) return DVAE_OK;
+  float* wp = ws + ce_part_floats(N, V) + tc16::plane_floats(N, H);
+  int rc = tc16::split_planes(w, H, V, H, 1.f, wp, (cudaStream_t)stream);
+  if (rc) return rc;
+  g_wsplit_ws = ws; g_wsplit_w = w;
+  return DVAE_OK;
+}
+
+static int vocab_ce_fwd_impl(const float* h, int64_t ldh, int T1, int B, int H, int V, const float* w,
+                             const float* bias, const int64_t* targets, int64_t tgt_stride_b,
+                             const int64_t* lengths, int sos, float* lse, float* nll, int32_t* argmax,
+                             float* loss, float* ws, bool w_planes_ready, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   DVAE_REQUIRE(h && w && bias && targets && lengths && loss && ws, "dvae_vocab_ce_fwd: null pointer");
   DVAE_REQUIRE(T1 > 0 && B > 0 && H > 0 && V > 0, "dvae_vocab_ce_fwd: bad shape T1=%d B=%d H=%d V=%d", T1, B, H, V);
@@ -338,9 +356,12 @@ extern "C" int dvae_vocab_ce_fwd(const float* h, int64_t ldh, int T1, int B, int
     float* wp = hp + tc16::plane_floats(p.N, H);
     int rc;
     if ((rc = tc16::split_planes(h, ldh, p.N, H, 1.f, hp, st))) return rc;
-    if ((rc = tc16::split_planes(w, H, V, H, 1.f, wp, st))) return rc;
+    // W planes: skipped when the caller vouches for an earlier dvae_vocab_split_w on the same (ws, w) since the last
+    // weight update, and that call did write them
+    if (!(w_planes_ready && g_wsplit_ws == ws && g_wsplit_w == w) && (rc = tc16::split_planes(w, H, V, H, 1.f, wp, st))) return rc;
     p.h_planes = hp; p.w_planes = wp;
   }
+  g_wsplit_ws = g_wsplit_w = nullptr;
   { int rc = ce_partials(p, st); if (rc) return rc; }
   float* block_sums = ws + (int64_t)p.nsplit * p.N * 5 + 8;      // p.nsplit: as updated by ce_partials
   const int nblk = min(kFinMaxBlocks, ceil_div(p.N, kFinThreads / kFinLanes));
@@ -349,6 +370,23 @@ extern "C" int dvae_vocab_ce_fwd(const float* h, int64_t ldh, int T1, int B, int
   vocab_ce_loss_kernel<<<1, 128, 0, st>>>(p, block_sums, nblk, loss);
   DVAE_LAUNCH_CHECK();
   return DVAE_OK;
+}
+
+extern "C" int dvae_vocab_ce_fwd(const float* h, int64_t ldh, int T1, int B, int H, int V, const float* w,
+                                 const float* bias, const int64_t* targets, int64_t tgt_stride_b,
+                                 const int64_t* lengths, int sos, float* lse, float* nll, int32_t* argmax,
+                                 float* loss, float* ws, void* stream) {
+  return vocab_ce_fwd_impl(h, ldh, T1, B, H, V, w, bias, targets, tgt_stride_b, lengths, sos, lse, nll, argmax, loss, ws,
+                           false, stream);
+}
+
+// flags bit 0: the W planes in ws are current (dvae_vocab_split_w on the same ws / w since the last weight update)
+extern "C" int dvae_vocab_ce_fwd_ex(const float* h, int64_t ldh, int T1, int B, int H, int V, const float* w,
+                                    const float* bias, const int64_t* targets, int64_t tgt_stride_b,
+                                    const int64_t* lengths, int sos, float* lse, float* nll, int32_t* argmax,
+                                    float* loss, float* ws, int flags, void* stream) {
+  return vocab_ce_fwd_impl(h, ldh, T1, B, H, V, w, bias, targets, tgt_stride_b, lengths, sos, lse, nll, argmax, loss, ws,
+                           (flags & 1) != 0, stream);
 }
 
 extern "C" int64_t dvae_vocab_ce_bwd_ws_floats(int N, int V, int H) {

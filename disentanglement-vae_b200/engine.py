@@ -18,6 +18,10 @@ from .plan import StepPlan
 from .losses import get_cyclic_kl_weight
 
 
+def d_bow(plan):
+    return bool(plan.d.bow)
+
+
 class TrainEngine:
     def __init__(self, model, params, B, T, lr=None, total_steps=None, use_graph=True, max_norm=5.0,
                  process_group=None, seed=None):
@@ -69,6 +73,7 @@ class TrainEngine:
         self._graphs = None
         self._buckets = None
         self._comm = None
+        self._side = None
         self.label_names = [n for n, o in zip(d.space_names, d.dsc_out) if o > 0]
 
     # ---- the kernel sequences ------------------------------------------------------------------
@@ -83,8 +88,20 @@ class TrainEngine:
             self.hyper[:5].copy_(self.d_scal[:5])
             self.kl_w.copy_(self.d_scal[8:8 + self.kl_w.numel()])
             pl.randn_eps()
+            # the decoder's input embeddings, its layer-0 input projection and the W_out operand planes do not depend on
+            # the encoder (teacher forcing): they run on a side stream under the encoder's recurrences (64 of 148 SMs)
+            cur = torch.cuda.current_stream()
+            hoist = os.environ.get("DVAE_HOIST", "1") != "0" and not d_bow(pl)
+            if hoist:
+                if self._side is None:
+                    self._side = torch.cuda.Stream(device=self.device)
+                self._side.wait_stream(cur)
+                with torch.cuda.stream(self._side):
+                    pl.decode_prepare(P, self.inputs, m.sos_token_idx, True)
             pl.encode(P, self.inputs, self.lengths, True)
             pl.heads(P, pl.ctx, pl.eps, self.labels, self.kl_w)
+            if hoist:
+                cur.wait_stream(self._side)
             h_top = pl.decode_forced(P, self.inputs, m.sos_token_idx, True)
             pl.vocab_ce(P, h_top, self.inputs, self.lengths)
             g_top = pl.vocab_ce_bwd(P, G, h_top, self.inputs, self.lengths, None)

@@ -177,9 +177,13 @@ class StepPlan:
         B, T1 = self.B, self.T1
         hid = self.hid if hid is None else hid
         p = d.p_dec if train else 0.0
-        check(lib.dvae_embedding_fwd(ptr(P["decoder.embedding.weight"]), d.E, ptr(tokens), tokens.stride(0),
-                                     tokens.stride(1), T1, B, p, ptr(self.seed_dev), SALT_DEC_EMB, first_token, 0,
-                                     ptr(self.x_dec), st), "dvae_embedding_fwd")
+        # decode_prepare() may already have embedded the inputs and projected them through layer 0's W_ih
+        prepared = getattr(self, "_dec_prepared", None) == (tokens.data_ptr(), first_token, p)
+        self._dec_prepared = None
+        if not prepared:
+            check(lib.dvae_embedding_fwd(ptr(P["decoder.embedding.weight"]), d.E, ptr(tokens), tokens.stride(0),
+                                         tokens.stride(1), T1, B, p, ptr(self.seed_dev), SALT_DEC_EMB, first_token, 0,
+                                         ptr(self.x_dec), st), "dvae_embedding_fwd")
         x, I = self.x_dec, d.E
         for l in range(d.Ld):
             if l > 0:
@@ -191,15 +195,34 @@ class StepPlan:
                 else:
                     x = self.d_hs[l - 1]
             w_ih, w_hh, b_ih, b_hh = self._dec_w(P, l)
-            check(lib.dvae_lstm_seq_fwd(ptr(x), I, T1, B, I, d.Hd, 1, ptr_array(w_ih), ptr_array(w_hh),
-                                        ptr_array(b_ih), ptr_array(b_hh), hid.data_ptr() + 4 * l * d.Hd,
-                                        hid.data_ptr() + 4 * (d.Ld + l) * d.Hd, d.H2L, 0, None, ptr(self.d_hs[l]),
-                                        d.Hd, None, None, 0, 0, ptr(self.d_gates[l]), ptr(self.d_cs[l]),
-                                        ptr(self.state_ws), st), "dvae_lstm_seq_fwd(dec)")
+            check(lib.dvae_lstm_seq_fwd_ex(ptr(x), I, T1, B, I, d.Hd, 1, ptr_array(w_ih), ptr_array(w_hh),
+                                           ptr_array(b_ih), ptr_array(b_hh), hid.data_ptr() + 4 * l * d.Hd,
+                                           hid.data_ptr() + 4 * (d.Ld + l) * d.Hd, d.H2L, 0, None, ptr(self.d_hs[l]),
+                                           d.Hd, None, None, 0, 0, ptr(self.d_gates[l]), ptr(self.d_cs[l]),
+                                           ptr(self.state_ws), 1 if (prepared and l == 0) else 0, st),
+                  "dvae_lstm_seq_fwd(dec)")
         self._dec_p = p
         self._dec_tokens, self._dec_first = tokens, first_token
         self._dec_hid = hid
         return self.d_hs[-1]
+
+    def decode_prepare(self, P, tokens, first_token, train):
+        """The part of decode_forced() that does not depend on the encoder: input embeddings (+ dropout) and layer 0's
+        input projection, and the fp16 operand planes of W_out for vocab_ce().  Call it on another stream (the engine
+        runs it under the encoder) and make the stream that calls decode_forced() / vocab_ce() wait for it."""
+        lib, d, st = self.lib, self.d, _lib.stream_ptr()
+        B, T1 = self.B, self.T1
+        p = d.p_dec if train else 0.0
+        check(lib.dvae_embedding_fwd(ptr(P["decoder.embedding.weight"]), d.E, ptr(tokens), tokens.stride(0),
+                                     tokens.stride(1), T1, B, p, ptr(self.seed_dev), SALT_DEC_EMB, first_token, 0,
+                                     ptr(self.x_dec), st), "dvae_embedding_fwd")
+        w_ih, _, b_ih, b_hh = self._dec_w(P, 0)
+        check(lib.dvae_lstm_input_proj(ptr(self.x_dec), d.E, T1, B, d.E, d.Hd, 1, ptr_array(w_ih), ptr_array(b_ih),
+                                       ptr_array(b_hh), ptr(self.d_gates[0]), st), "dvae_lstm_input_proj(dec)")
+        self._dec_prepared = (tokens.data_ptr(), first_token, p)
+        check(lib.dvae_vocab_split_w(ptr(P["decoder.linear.weight"]), max(self.N, 1), d.V, d.Hd, ptr(self.ce_ws), st),
+              "dvae_vocab_split_w")
+        self._w_planes_ready = P["decoder.linear.weight"].data_ptr()
 
     def decode_sampled(self, P, preds, coins, train, hid=None):
         """a6 / a12 with sampled inputs (vae/model.py:457-472,498-508).  `preds` [B,T] int64 is both the
@@ -249,10 +272,12 @@ class StepPlan:
     def vocab_ce(self, P, h_top, targets, lengths):
         """a7 fused with the vocabulary projection of a6."""
         lib, d, st = self.lib, self.d, _lib.stream_ptr()
-        check(lib.dvae_vocab_ce_fwd(ptr(h_top), d.Hd, self.T1, self.B, d.Hd, d.V, ptr(P["decoder.linear.weight"]),
-                                    ptr(P["decoder.linear.bias"]), ptr(targets), targets.stride(0), ptr(lengths),
-                                    d.sos, ptr(self.lse), ptr(self.nll), ptr(self.argmax), ptr(self.recon),
-                                    ptr(self.ce_ws), st), "dvae_vocab_ce_fwd")
+        w_ready = getattr(self, "_w_planes_ready", None) == P["decoder.linear.weight"].data_ptr()
+        self._w_planes_ready = None
+        check(lib.dvae_vocab_ce_fwd_ex(ptr(h_top), d.Hd, self.T1, self.B, d.Hd, d.V, ptr(P["decoder.linear.weight"]),
+                                       ptr(P["decoder.linear.bias"]), ptr(targets), targets.stride(0), ptr(lengths),
+                                       d.sos, ptr(self.lse), ptr(self.nll), ptr(self.argmax), ptr(self.recon),
+                                       ptr(self.ce_ws), 1 if w_ready else 0, st), "dvae_vocab_ce_fwd")
         # the backward of this same step may reuse the operand planes the call left in ce_ws
         self._ce_planes_valid = (h_top.data_ptr(), P["decoder.linear.weight"].data_ptr())
         return self.recon

@@ -178,6 +178,20 @@ int dvae_lstm_step(const float* x, int64_t ldx, int t, int T, int B, int I, int 
                    const float* c0, int64_t ld0, float* hs, float* gates, float* cs, float* state_ws,
                    void* stream);
 
+/* The two halves of dvae_lstm_seq_fwd separately: dvae_lstm_input_proj fills `gates` with x.W_ih^T + b_ih + b_hh for all
+ * time steps (one GEMM per direction); dvae_lstm_seq_fwd_ex with flags bit 0 set then runs the recurrence alone.  Lets a
+ * caller run a layer's projection early on another stream (the decoder's layer 0 under teacher forcing depends on the
+ * input tokens only).  flags = 0: identical to dvae_lstm_seq_fwd. */
+int dvae_lstm_input_proj(const float* x, int64_t ldx, int T, int B, int I, int H, int D,
+                         const float* const* w_ih, const float* const* b_ih, const float* const* b_hh,
+                         float* gates, void* stream);
+int dvae_lstm_seq_fwd_ex(const float* x, int64_t ldx, int T, int B, int I, int H, int D,
+                         const float* const* w_ih, const float* const* w_hh, const float* const* b_ih,
+                         const float* const* b_hh, const float* h0, const float* c0, int64_t ld0,
+                         int64_t dir0, const int64_t* lengths, float* hs, int64_t ldhs, float* hn,
+                         float* cn, int64_t ldn, int64_t dirn, float* gates, float* cs, float* state_ws,
+                         int flags, void* stream);
+
 /* Back-propagation through time for dvae_lstm_seq_fwd (the autograd of nn.LSTM).
  *   d_hs [T,B,D*H] (row stride lddhs) or NULL; d_hn, d_cn as hn/cn or NULL.
  *   gates is OVERWRITTEN with the pre-activation gradients dG [D,T,B,4H].
@@ -269,6 +283,15 @@ int dvae_vocab_ce_fwd(const float* h, int64_t ldh, int T1, int B, int H, int V, 
                       const float* bias, const int64_t* targets, int64_t tgt_stride_b,
                       const int64_t* lengths, int sos, float* lse, float* nll, int32_t* argmax,
                       float* loss, float* ws, void* stream);
+
+/* The operand split of W_out as a call of its own (W_out does not depend on the step's activations): run it early, on
+ * another stream, then pass flags bit 0 to dvae_vocab_ce_fwd_ex (same N = T1*B, V, H, w, ws).  Without the flag, or when
+ * the split call was a no-op for the shape, the forward call splits W itself. */
+int dvae_vocab_split_w(const float* w, int N, int V, int H, float* ws, void* stream);
+int dvae_vocab_ce_fwd_ex(const float* h, int64_t ldh, int T1, int B, int H, int V, const float* w,
+                         const float* bias, const int64_t* targets, int64_t tgt_stride_b,
+                         const int64_t* lengths, int sos, float* lse, float* nll, int32_t* argmax,
+                         float* loss, float* ws, int flags, void* stream);
 
 /* Measurement entry (bench.py roofline, ncu): only the projection + online-softmax partials kernel of
  * dvae_vocab_ce_fwd (no operand split, no finalize).  ws must come from an earlier dvae_vocab_ce_fwd call with the same

@@ -234,6 +234,16 @@ def _lstm_case(lib, L, T, B, I, H, D, with_len, with_h0, seed):
         assert rel(hs[:, :, d * H:(d + 1) * H], want[d][0]) < 5e-6
         assert rel(hn[d], want[d][1]) < 5e-6
         assert rel(cn[d], want[d][2]) < 5e-6
+    # the same layer as two calls (input projection on its own, then the recurrence alone): bit-identical outputs
+    hs2, hn2, cn2 = torch.full_like(hs, 5.0), torch.zeros_like(hn), torch.zeros_like(cn)
+    gates2, cs2 = torch.zeros_like(gates), torch.zeros_like(cs)
+    L.check(lib.dvae_lstm_input_proj(L.ptr(xd), I, T, B, I, H, D, pa("w_ih"), pa("b_ih"), pa("b_hh"), L.ptr(gates2), st), "lstm proj")
+    L.check(lib.dvae_lstm_seq_fwd_ex(L.ptr(xd), I, T, B, I, H, D, pa("w_ih"), pa("w_hh"), pa("b_ih"), pa("b_hh"),
+                                     L.ptr(h0d), L.ptr(c0d), H, B * H, L.ptr(len_d), L.ptr(hs2), D * H, L.ptr(hn2), L.ptr(cn2),
+                                     H, B * H, L.ptr(gates2), L.ptr(cs2), L.ptr(ws), 1, st), "lstm fwd (recurrence only)")
+    live = torch.ones(T, B, dtype=torch.bool, device="cuda") if not with_len else \
+        (torch.arange(T, device="cuda")[:, None] < len_d[None, :])
+    assert torch.equal(hs2[live], hs[live]) and torch.equal(hn2, hn) and torch.equal(cn2, cn)
     # backward
     G = [{k_: torch.full_like(v, 3.0) for k_, v in Wd[d].items()} for d in range(D)]
     ga = lambda key: L.ptr_array([G[d][key] for d in range(D)])
@@ -442,6 +452,14 @@ def test_vocab_ce(lib, L, T1, B, H, V):
     assert rel(d_h, dl @ W.astype(np.float64)) < 1e-4
     assert rel(d_w, dl.T @ hf) < 1e-4
     assert rel(d_b, dl.sum(0)) < 1e-4
+    # W planes prepared ahead of the forward call (dvae_vocab_split_w + flags bit 0): same loss, lse and arg-max
+    ws3 = torch.zeros_like(ws)
+    lse3, nll3 = torch.zeros_like(lse), torch.zeros_like(lse)
+    am3, loss3 = torch.zeros(N, device="cuda", dtype=torch.int32), torch.zeros(1, device="cuda")
+    L.check(lib.dvae_vocab_split_w(L.ptr(Wd), N, V, H, L.ptr(ws3), st), "split w")
+    L.check(lib.dvae_vocab_ce_fwd_ex(L.ptr(hd), H, T1, B, H, V, L.ptr(Wd), L.ptr(bd), L.ptr(td), T, L.ptr(ld), sos, L.ptr(lse3),
+                                     L.ptr(nll3), L.ptr(am3), L.ptr(loss3), L.ptr(ws3), 1, st), "ce fwd_ex")
+    assert torch.equal(lse3, lse) and torch.equal(loss3, loss) and torch.equal(am3, am)
     # the same call reusing the forward call's operand planes (fwd_ws) must give the same gradients (split-K atomics: not bitwise)
     d_h2, d_w2, d_b2 = torch.full_like(d_h, 3.0), torch.full_like(d_w, 3.0), torch.full_like(d_b, 3.0)
     L.check(lib.dvae_vocab_ce_bwd(L.ptr(hd), H, T1, B, H, V, L.ptr(Wd), L.ptr(bd), L.ptr(td), T, L.ptr(ld), L.ptr(lse),
