@@ -108,14 +108,21 @@ class TrainEngine:
             # weight-gradient GEMMs of each layer keep running on side streams while the next layer's recurrence starts
             check(self.lib.dvae_defer_joins(1), "dvae_defer_joins")
             try:
-                pl.decode_bwd(P, G, g_top, emb_grad="decoder.embedding.weight" in m._layout)
+                pl.decode_bwd(P, G, g_top, emb_grad="decoder.embedding.weight" in m._layout,
+                              aux_stream=self._side if hoist else None)
             finally:
                 if part == 1:
                     check(self.lib.dvae_join_side_streams(st), "dvae_join_side_streams")
+                    if hoist:
+                        cur.wait_stream(self._side)
+            self._aux_pending = hoist and part is None
         if part in (None, 2):
             check(self.lib.dvae_defer_joins(1), "dvae_defer_joins")
             try:
                 g_ctx = pl.heads_bwd(P, G, pl.ctx, pl.eps, self.labels, self.kl_w, pl.g_hid)
+                if getattr(self, "_aux_pending", False):      # the decoder's embedding-gradient scatter still reads g_dx[0]
+                    torch.cuda.current_stream().wait_stream(self._side)
+                    self._aux_pending = False
                 pl.encode_bwd(P, G, self.inputs, self.lengths, g_ctx, emb_grad="encoder.embedding.weight" in m._layout)
             finally:
                 check(self.lib.dvae_join_side_streams(st), "dvae_join_side_streams")

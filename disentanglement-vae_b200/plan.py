@@ -299,8 +299,10 @@ class StepPlan:
               "dvae_vocab_ce_bwd")
         return self.g_top
 
-    def decode_bwd(self, P, G, g_top, emb_grad=True):
-        """BPTT through the decoder stack; leaves d(hid) in self.g_hid."""
+    def decode_bwd(self, P, G, g_top, emb_grad=True, aux_stream=None):
+        """BPTT through the decoder stack; leaves d(hid) in self.g_hid.  With `aux_stream` the embedding-gradient
+        scatter (nothing downstream reads it before the optimizer) is enqueued there; the caller makes its stream wait
+        for `aux_stream` before anything overwrites g_dx[0] (encode_bwd) or reads the embedding gradient."""
         self._alloc_bwd()
         lib, d, st = self.lib, self.d, _lib.stream_ptr()
         B, T1 = self.B, self.T1
@@ -327,6 +329,9 @@ class StepPlan:
             g_in = g_out
         if emb_grad:
             tok = self._dec_tokens
+            if aux_stream is not None:
+                aux_stream.wait_stream(torch.cuda.current_stream())
+                st = aux_stream.cuda_stream
             check(lib.dvae_embedding_bwd(ptr(g_in), d.E, ptr(tok), tok.stride(0), tok.stride(1), T1, B, p,
                                          ptr(self.seed_dev), SALT_DEC_EMB, self._dec_first, 0,
                                          ptr(G["decoder.embedding.weight"]), st), "dvae_embedding_bwd")
