@@ -90,9 +90,13 @@ int linear_impl_ex(const float* A, int64_t lda, int trans_a, const float* B, int
   DVAE_REQUIRE(A && B && C, "dvae_linear: null pointer");
   DVAE_REQUIRE(M > 0 && N > 0 && K > 0, "dvae_linear: non-positive size M=%d N=%d K=%d", M, N, K);
   DVAE_REQUIRE(act == 0 || act == 1, "dvae_linear: unknown activation %d", act);
-  // Dense-contraction shapes go to the tensor cores (TMA + tcgen05, 3xTF32 = fp32-grade accuracy); small or
-  // unaligned problems stay on the fp32 SIMT kernels below.
-  if (!force_simt_gemm() && M >= 64 && N >= 64 && K >= 32 && (double)M * N * K >= (double)(1 << 23)) {
+  // Dense-contraction shapes go to the tensor cores (TMA + tcgen05); small (fixed costs of the tensor-core kernels:
+  // ~10 us) or unaligned problems stay on the fp32 SIMT kernels below.
+  static const double tc_min_mnk = [] {
+    const char* e = getenv("DVAE_TC_MIN_LOG2_MNK");      // A/B knob: smallest M*N*K (log2) that goes to the tensor-core kernels
+    return (double)(1ll << (e ? atoi(e) : 24));      // measured on the cfg-2 step: 23: 1.455, 24: 1.438, 25: 1.449, 26: 1.453 ms
+  }();
+  if (!force_simt_gemm() && M >= 64 && N >= 64 && K >= 32 && (double)M * N * K >= tc_min_mnk) {
     // fp16-split kernel unless an operand's dynamic range is unknown (then 3xTF32, whose operands have fp32 range)
     const bool unscaled_wide = (hints.a_wide && !hints.a_amax_bits) || (hints.b_wide && !hints.b_amax_bits);
     if (!unscaled_wide && tc16::supported(A, lda, trans_a, B, ldb, trans_b, M, N, K))

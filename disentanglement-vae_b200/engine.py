@@ -92,13 +92,16 @@ class TrainEngine:
             # the encoder (teacher forcing): they run on a side stream under the encoder's recurrences (64 of 148 SMs)
             cur = torch.cuda.current_stream()
             hoist = os.environ.get("DVAE_HOIST", "1") != "0" and not d_bow(pl)
+            fork_prep = None
             if hoist:
                 if self._side is None:
                     self._side = torch.cuda.Stream(device=self.device)
-                self._side.wait_stream(cur)
-                with torch.cuda.stream(self._side):
-                    pl.decode_prepare(P, self.inputs, m.sos_token_idx, True)
-            pl.encode(P, self.inputs, self.lengths, True)
+
+                def fork_prep():      # forked behind the encoder's layer-0 projection GEMMs, which fill the machine themselves
+                    self._side.wait_stream(cur)
+                    with torch.cuda.stream(self._side):
+                        pl.decode_prepare(P, self.inputs, m.sos_token_idx, True)
+            pl.encode(P, self.inputs, self.lengths, True, after_l0_proj=fork_prep)
             pl.heads(P, pl.ctx, pl.eps, self.labels, self.kl_w)
             if hoist:
                 cur.wait_stream(self._side)

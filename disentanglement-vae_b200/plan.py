@@ -126,8 +126,11 @@ class StepPlan:
     # ------------------------------------------------------------------------------------------
     # forward pieces.  P: dict name -> parameter tensor (reference state_dict names + fused groups)
     # ------------------------------------------------------------------------------------------
-    def encode(self, P, inputs, lengths, train):
-        """a1 + a2 (vae/model.py:88-101,373-382): inputs [B,T] int64 (row stride = inputs.stride(0))."""
+    def encode(self, P, inputs, lengths, train, after_l0_proj=None):
+        """a1 + a2 (vae/model.py:88-101,373-382): inputs [B,T] int64 (row stride = inputs.stride(0)).
+        `after_l0_proj`: optional callable invoked once layer 0's input-projection GEMMs are enqueued and before its
+        recurrence kernel is -- the point from which 84 of the 148 SMs are idle for the rest of the encoder (the engine
+        forks the decoder's encoder-independent work there)."""
         lib, d, st = self.lib, self.d, _lib.stream_ptr()
         B, T = self.B, self.T
         p = d.p_enc if train else 0.0
@@ -152,11 +155,17 @@ class StepPlan:
                     x = self.e_hs[l - 1]
             w_ih, w_hh, b_ih, b_hh = self._enc_w(P, l, d.D)
             off = l * d.D * d.H
-            check(lib.dvae_lstm_seq_fwd(ptr(x), I, T, B, I, d.H, d.D, ptr_array(w_ih), ptr_array(w_hh),
-                                        ptr_array(b_ih), ptr_array(b_hh), None, None, 0, 0, ptr(lengths),
-                                        ptr(self.e_hs[l]), d.D * d.H, self.ctx.data_ptr() + 4 * off,
-                                        self.ctx_c.data_ptr() + 4 * off, d.C, d.H, ptr(self.e_gates[l]),
-                                        ptr(self.e_cs[l]), ptr(self.state_ws), st), "dvae_lstm_seq_fwd(enc)")
+            split = l == 0 and after_l0_proj is not None
+            if split:
+                check(lib.dvae_lstm_input_proj(ptr(x), I, T, B, I, d.H, d.D, ptr_array(w_ih), ptr_array(b_ih),
+                                               ptr_array(b_hh), ptr(self.e_gates[l]), st), "dvae_lstm_input_proj(enc)")
+                after_l0_proj()
+            check(lib.dvae_lstm_seq_fwd_ex(ptr(x), I, T, B, I, d.H, d.D, ptr_array(w_ih), ptr_array(w_hh),
+                                           ptr_array(b_ih), ptr_array(b_hh), None, None, 0, 0, ptr(lengths),
+                                           ptr(self.e_hs[l]), d.D * d.H, self.ctx.data_ptr() + 4 * off,
+                                           self.ctx_c.data_ptr() + 4 * off, d.C, d.H, ptr(self.e_gates[l]),
+                                           ptr(self.e_cs[l]), ptr(self.state_ws), 1 if split else 0, st),
+                  "dvae_lstm_seq_fwd(enc)")
         self._enc_p = p
         return self.ctx
 
