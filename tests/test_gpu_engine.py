@@ -1,0 +1,84 @@
+"""TrainEngine (the thing bench.py times: forward + losses + backward + clip + Adam behind CUDA graphs, with the
+encoder-independent decoder work forked onto a side stream) against the oracle's train step (run.py:217-262)."""
+import importlib
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import dvae_oracle as O  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dvae():
+    import __graft_entry__ as ge
+    return ge.build()
+
+
+def _batch(gen, B, T, V):
+    lengths = torch.randint(3, T + 1, (B,), generator=gen)
+    lengths[0] = T
+    X = torch.zeros(B, T, dtype=torch.long)
+    for b in range(B):
+        n = int(lengths[b])
+        X[b, 0], X[b, n - 1] = 2, 3
+        X[b, 1:n - 1] = torch.randint(4, V, (n - 2,), generator=gen)
+    Y = {k: (torch.rand(B, 1, generator=gen) < 0.3).float() for k in ("uncertainty", "polarity")}
+    return X, lengths, Y
+
+
+@pytest.mark.parametrize("use_graph,env", [(False, {}), (True, {}), (True, {"DVAE_HOIST": "0"})])
+def test_train_engine_steps_match_oracle(dvae, use_graph, env, monkeypatch):
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    engine_mod = importlib.import_module("disentanglement-vae_b200.engine")
+    E = H = 256                       # the tcgen05 LSTM / fp16-split GEMM / pre-split vocabulary kernels
+    V, B, T, total_steps, lr = 2000, 40, 9, 50, 3e-3
+    cfg = dict(bow_encoder=False, embedding_dim=E, hidden_dim=H, num_rnn_layers=2, encoder_dropout=0.0, decoder_dropout=0.0,
+               bidirectional_encoder=True, latent_dims={"total": 16, "polarity": 1, "uncertainty": 1}, adversarial_loss=False,
+               mi_loss=False, learn_rate=lr, lambdas={"default": "cyclic", "polarity": 0.005, "uncertainty": 0.005},
+               random_seed=10)
+    dvae.set_seed(10)
+    dev = torch.device("cuda")
+    vae = dvae.build_vae(cfg, V, None, {"uncertainty": 1, "polarity": 1}, dev, 2, 3)
+    vae.train()
+    eng = engine_mod.TrainEngine(vae, cfg, B, T, total_steps=total_steps, use_graph=use_graph, seed=7)
+    sd = O.cast_state_dict({k: v.detach().cpu().numpy() for k, v in vae.state_dict().items()})
+    spec = O.ModelSpec(sd, list(vae.context2params.keys()), 2, 3)
+    m = {k: np.zeros_like(v) for k, v in sd.items()}
+    v2 = {k: np.zeros_like(v) for k, v in sd.items()}
+    gen = torch.Generator().manual_seed(99)
+    for step in range(3):             # step 0 also captures the graphs; steps 1-2 replay them with new inputs and scalars
+        X, lengths, Y = _batch(gen, B, T, V)
+        got = eng.step_host(X, lengths, Y)
+        eps = eng.plan.eps.detach().cpu().numpy().reshape(B, -1)       # drawn on the device by the step itself
+        eps_d, off = {}, 0
+        for n, zs in zip(spec.space_names, spec.space_dims):
+            eps_d[n] = eps[:, off:off + zs]
+            off += zs
+        klw = {"default": O.cyclic_kl_weight(step, total_steps), "polarity": 0.005, "uncertainty": 0.005}
+        fw = O.model_forward(sd, spec, X.numpy(), lengths.numpy(), eps_d, labels={k: y.numpy() for k, y in Y.items()},
+                             kl_weights=klw)
+        grads = O.model_backward(sd, spec, fw)
+        assert abs(got["total_loss"] - fw["total_loss"]) <= 1e-5 * abs(fw["total_loss"]), (step, got["total_loss"], fw["total_loss"])
+        before = {k: a.copy() for k, a in sd.items()}
+        O.clip_and_adam(sd, grads, m, v2, step + 1, lr)
+        now = {k: t.detach().cpu().numpy().astype(np.float64) for k, t in vae.state_dict().items()}
+        for k in sd:
+            want, have = sd[k] - before[k], now[k] - before[k]
+            # Adam's first steps move every weight by ~lr * sign(g): entries whose gradient is numerical noise may flip
+            sig = np.abs(grads[k]) > 1e-4 * np.abs(grads[k]).max()
+            if sig.any():
+                err = np.abs(want - have)[sig].max() / max(np.abs(want[sig]).max(), 1e-30)
+                assert err < 2e-2, (step, k, err)
+        # continue from the DEVICE weights and moments so that the comparison does not accumulate drift
+        sd = O.cast_state_dict({k: t.detach().cpu().numpy() for k, t in vae.state_dict().items()})
+        Mv, Vv = vae.grad_views(eng.m), vae.grad_views(eng.v)
+        m = {k: Mv[k].detach().cpu().numpy().astype(np.float64) for k in sd}
+        v2 = {k: Vv[k].detach().cpu().numpy().astype(np.float64) for k in sd}
