@@ -813,6 +813,8 @@ int linear(const float* A, int64_t lda, int trans_a, const float* B, int64_t ldb
       if (t < best * 0.95f) { best = t; splits = se; }      // a larger split count has to be clearly better
     }
   }
+  if (const char* e = getenv("DVAE_TC16_SPLITS_BIG_MN"))          // A/B knob: split count of the large both-transposed GEMMs (dW_out)
+    if (p.a_mn && p.b_mn && tiles >= 64 && act == 0) splits = atoi(e);
   p.kb_per_split = ceil_div(nkb, splits);
   splits = ceil_div(nkb, p.kb_per_split);
   if (splits > 1 && beta != 1.f && !(beta == 0.f && hints.c_zeroed)) {
