@@ -389,8 +389,12 @@ extern "C" int dvae_vocab_ce_fwd_ex(const float* h, int64_t ldh, int T1, int B, 
                            (flags & 1) != 0, stream);
 }
 
+// softmax-gradient chunks alternate between two buffers when there is more than one chunk: the next chunk's P is then
+// computed while this chunk's d_w GEMM (the longer of its two consumers) is still running
+static int p_buffers(int N, int V) { return p_chunk(N, V) < V ? 2 : 1; }
+
 extern "C" int64_t dvae_vocab_ce_bwd_ws_floats(int N, int V, int H) {
-  return (int64_t)N * p_chunk(N, V) + tc16::plane_floats(N, H) + tc16::plane_floats(V, H);
+  return (int64_t)p_buffers(N, V) * N * p_chunk(N, V) + tc16::plane_floats(N, H) + tc16::plane_floats(V, H);
 }
 
 extern "C" int dvae_vocab_ce_bwd(const float* h, int64_t ldh, int T1, int B, int H, int V, const float* w,
@@ -401,7 +405,7 @@ extern "C" int dvae_vocab_ce_bwd(const float* h, int64_t ldh, int T1, int B, int
   cudaStream_t st = (cudaStream_t)stream;
   DVAE_REQUIRE(h && w && bias && targets && lengths && lse && d_h && d_w && d_bias && ws, "dvae_vocab_ce_bwd: null pointer");
   DVAE_REQUIRE(T1 > 0 && B > 0 && H > 0 && V > 0, "dvae_vocab_ce_bwd: bad shape");
-  const int N = T1 * B, vc_max = p_chunk(N, V);
+  const int N = T1 * B, vc_max = p_chunk(N, V), nbuf = p_buffers(N, V);
   PArgs p;
   p.h = h; p.ldh = ldh; p.w = w; p.bias = bias; p.targets = targets; p.tgt_stride_b = tgt_stride_b;
   p.lengths = lengths; p.lse = lse; p.grad_scale = grad_scale_dev; p.N = N; p.B = B; p.H = H; p.V = V;
@@ -417,7 +421,7 @@ extern "C" int dvae_vocab_ce_bwd(const float* h, int64_t ldh, int T1, int B, int
       const float* hp = fwd_ws + ce_part_floats(N, V);
       h_planes = hp; w_planes = hp + tc16::plane_floats(N, H);
     } else {
-      float* hp = ws + (int64_t)N * vc_max;
+      float* hp = ws + (int64_t)nbuf * N * vc_max;
       float* wp = hp + tc16::plane_floats(N, H);
       int rc;
       if ((rc = tc16::split_planes(h, ldh, N, H, 1.f, hp, st))) return rc;
@@ -426,21 +430,23 @@ extern "C" int dvae_vocab_ce_bwd(const float* h, int64_t ldh, int T1, int B, int
     }
   }
   int chunk = 0;
+  const int nchunks = ceil_div(V, vc_max);
   for (int v0 = 0; v0 < V; v0 += vc_max, ++chunk) {
     const int vc = min(vc_max, V - v0);
-    p.v0 = v0; p.vc = vc;
+    float* Pc = ws + (int64_t)(chunk % nbuf) * N * vc_max;      // this chunk's softmax-gradient buffer
+    p.v0 = v0; p.vc = vc; p.P = Pc;
     int rc;
     bool dh_zeroed = false, dw_zeroed = false;
     if (!force_simt_gemm() && N >= 64 && vc >= 128 && H >= 32 && tc16::supported(h, ldh, 0, w, H, 0, N, vc, H)) {
       // the kernel also clears the outputs of this chunk's split-K GEMMs (d_h once, this chunk's rows of d_w): no memset nodes
       const bool zh = chunk == 0 && lddh == H && (((uintptr_t)d_h) & 15) == 0 && ((int64_t)N * H) % 4 == 0;
       const bool zw = (((uintptr_t)(d_w + (int64_t)v0 * H)) & 15) == 0 && ((int64_t)vc * H) % 4 == 0;
-      if ((rc = tc16::softmax_grad(h, ldh, N, B, H, V, v0, vc, w, bias, targets, tgt_stride_b, lengths, lse, grad_scale_dev, ws,
+      if ((rc = tc16::softmax_grad(h, ldh, N, B, H, V, v0, vc, w, bias, targets, tgt_stride_b, lengths, lse, grad_scale_dev, Pc,
                                    vc_max, h_planes, w_planes, zh ? d_h : nullptr, (int64_t)N * H / 4,
                                    zw ? d_w + (int64_t)v0 * H : nullptr, (int64_t)vc * H / 4, st))) return rc;
       dh_zeroed = zh; dw_zeroed = zw;
     } else if (!force_simt_gemm() && N >= 64 && vc >= 128 && H >= 32 && tc::tc_linear_supported(h, ldh, w, H, N, vc, H)) {
-      if ((rc = tc::tc_softmax_grad(h, ldh, N, B, H, v0, vc, w, bias, targets, tgt_stride_b, lengths, lse, grad_scale_dev, ws,
+      if ((rc = tc::tc_softmax_grad(h, ldh, N, B, H, v0, vc, w, bias, targets, tgt_stride_b, lengths, lse, grad_scale_dev, Pc,
                                     vc_max, st))) return rc;
     } else {
       dim3 grid(ceil_div(vc, GCE::BN), ceil_div(N, GCE::BM));
@@ -451,11 +457,15 @@ extern "C" int dvae_vocab_ce_bwd(const float* h, int64_t ldh, int T1, int B, int
     Fork fork(st);         // the three consumers of this chunk of P are independent of each other
     GemmHints ph_h = ph, ph_w = ph;
     ph_h.c_zeroed = dh_zeroed; ph_w.c_zeroed = dw_zeroed;
-    if ((rc = linear_impl_ex(ws, vc_max, 0, w + (int64_t)v0 * H, H, 1, d_h, lddh, N, H, vc, nullptr, nullptr, chunk ? 1.f : 0.f, 0, ph_h, st))) return rc;
+    if ((rc = linear_impl_ex(Pc, vc_max, 0, w + (int64_t)v0 * H, H, 1, d_h, lddh, N, H, vc, nullptr, nullptr, chunk ? 1.f : 0.f, 0, ph_h, st))) return rc;
     // d_w[v0:v0+vc, :] = P^T [vc,N] . h [N,H]
-    if ((rc = linear_impl_ex(ws, vc_max, 1, h, ldh, 1, d_w + (int64_t)v0 * H, H, vc, H, N, nullptr, nullptr, 0.f, 0, ph_w, fork.side(0)))) return rc;
-    if ((rc = colsum_impl(ws, vc_max, N, vc, d_bias + v0, 0.f, fork.side(1)))) return rc;
-    if ((rc = fork.join())) return rc;       // the next chunk overwrites P
+    if ((rc = linear_impl_ex(Pc, vc_max, 1, h, ldh, 1, d_w + (int64_t)v0 * H, H, vc, H, N, nullptr, nullptr, 0.f, 0, ph_w, fork.side(0)))) return rc;
+    if ((rc = colsum_impl(Pc, vc_max, N, vc, d_bias + v0, 0.f, fork.side(1)))) return rc;
+    // main waits for the side branches only when the NEXT chunk reuses a buffer (or at the end): with two buffers the next
+    // chunk's softmax gradient is computed under this chunk's d_w GEMM.  Side streams run their work in order, so a later
+    // join covers the branches of every earlier chunk.
+    if (chunk + 1 == nchunks || chunk + 1 >= nbuf)
+      if ((rc = fork.join())) return rc;
   }
   return DVAE_OK;
 }
