@@ -151,6 +151,33 @@ __device__ __forceinline__ void store_tile(uint32_t tile, int ptid, float s, con
   sts128(base + PS_PLANE, lo);
 }
 
+// ---- CTA-pair helpers (pre-split A-stationary kernels: the B tiles are shared by the CTAs of neighbouring row blocks) ----
+__device__ __forceinline__ uint32_t cluster_size() {
+  uint32_t n;
+  asm volatile("mov.u32 %0, %%cluster_nctaid.x;" : "=r"(n));
+  return n;
+}
+__device__ __forceinline__ uint32_t cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// one global read, delivered to the same shared-memory offset (and mbarrier) of every CTA in `mask`
+__device__ __forceinline__ void bulk_load_multicast(uint32_t smem_dst, const void* src, uint32_t bytes, uint64_t* bar, uint16_t mask) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(smem_dst),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar)), "h"(mask)
+               : "memory");
+}
+// tcgen05.commit arriving on the same mbarrier offset of every CTA in `mask`
+__device__ __forceinline__ void tc_commit_multicast(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+               "h"(mask)
+               : "memory");
+}
+
 // contiguous global -> shared bulk copy (no tensor map), completion on an mbarrier
 __device__ __forceinline__ void bulk_load(uint32_t smem_dst, const void* src, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_dst), "l"(src),
@@ -196,6 +223,10 @@ tc16_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   // pre-split vocabulary kernels: no converters are needed, so the first 8 converter warps join the epilogue (16 warps,
   // one 32-column chunk each) -- with 8 warps the exp-heavy epilogues took 4-7 us per tile against 1.7 us of MMAs
   const bool wide_epi = p.presplit && p.mode != 0;
+  // CTA pair (cluster of 2 along the row blocks, launched only for the A-stationary pre-split kernels): both CTAs walk the
+  // same vocabulary tiles, so each fetches HALF of every B stage and multicasts it to both -- half the L2 -> SM traffic
+  const uint32_t csize = p.mcast ? cluster_size() : 1, crank = p.mcast ? cluster_rank() : 0;
+  const uint16_t cmask = (uint16_t)((1u << csize) - 1);
   const bool conv_as_epi = wide_epi && warp >= PROD_WARP0 && warp < PROD_WARP0 + EPI_WARPS;
   // a programmatically-launched successor (the persistent LSTM kernels) may start its prologue now; it still waits for
   // this grid to complete (griddepcontrol.wait) before it reads anything written here
@@ -229,7 +260,7 @@ tc16_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     for (int s = 0; s < MAX_STAGES; ++s) {
       mbar_init(&full[s], p.presplit ? 1 : PROD_WARPS);
-      mbar_init(&empty[s], 1);
+      mbar_init(&empty[s], p.mcast ? csize : 1);       // CTA pair: a B stage is free once BOTH CTAs' MMAs have read it
       mbar_init(&raw_full[s], 1);
     }
     for (int a = 0; a < 2; ++a) {
@@ -249,6 +280,7 @@ tc16_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == MMA_WARP) tmem_alloc(tmem_slot, TMEM_COLS);
   tc_fence_before();
   __syncthreads();
+  if (p.mcast) cluster_sync_all();      // the peer's mbarriers are initialised before anything of ours can signal them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t smem_u = smem_u32(smem);
@@ -259,7 +291,9 @@ tc16_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       // probes only: no operand traffic at all
     } else if (lane == 0 && a_stat) {
       // A rows once (all k-blocks, both planes), then only B tiles through the ring
-      const uint8_t* a_tiles = reinterpret_cast<const uint8_t*>(p.a_planes) + (int64_t)blockIdx.x * nkb_total * PS_TILE;
+      // (a padding CTA of an odd row-block count re-reads the last real block: it only has to keep the pair's protocol going)
+      const int a_blk = min((int)blockIdx.x, (p.M + BM - 1) / BM - 1);
+      const uint8_t* a_tiles = reinterpret_cast<const uint8_t*>(p.a_planes) + (int64_t)a_blk * nkb_total * PS_TILE;
       const uint8_t* b_planes = reinterpret_cast<const uint8_t*>(p.b_planes);
       mbar_expect_tx(a_full, (uint32_t)nkb * PS_TILE);
       for (int kb = 0; kb < nkb; ++kb) bulk_load(smem_u + kb * PS_TILE, a_tiles + (int64_t)kb * PS_TILE, PS_TILE, a_full);
@@ -272,7 +306,13 @@ tc16_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           DVAE_TC16_MARK(nt == nt0 + 1 && kb < 8, 33 + 2 * kb);
           const uint32_t dst = smem_u + AS_A_BYTES + stage * AS_STAGE_BYTES;
           mbar_expect_tx(&full[stage], AS_STAGE_BYTES);
-          bulk_load(dst, b_planes + ((int64_t)(nt + b_tile0) * nkb_total + kb) * PS_TILE, PS_TILE, &full[stage]);
+          const uint8_t* src = b_planes + ((int64_t)(nt + b_tile0) * nkb_total + kb) * PS_TILE;
+          if (csize == 1) {
+            bulk_load(dst, src, PS_TILE, &full[stage]);
+          } else {              // my share of the stage, to both CTAs; the peer's share lands here through ITS copy
+            const uint32_t part = PS_TILE / csize, off = crank * part;
+            bulk_load_multicast(dst + off, src + off, part, &full[stage], cmask);
+          }
           if (++stage == nstages) { stage = 0; phase ^= 1; }
         }
       }
@@ -382,7 +422,10 @@ tc16_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               mma_f16(d2, desc(sa16 + plane16 + adv), desc(sb16 + adv), idesc, 1u);
             }
           }
-          if (!DVAE_TC16_FLAG(8)) tc_commit(&empty[stage]);
+          if (!DVAE_TC16_FLAG(8)) {
+            if (csize == 1) tc_commit(&empty[stage]);
+            else tc_commit_multicast(&empty[stage], cmask);
+          }
           a16 += a_kb16;
           st16 += stage16;
           if (++stage == nstages) { stage = 0; phase ^= 1; st16 = ring16; }
@@ -679,6 +722,7 @@ tc16_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
   tc_fence_before();
   __syncthreads();
+  if (p.mcast) cluster_sync_all();      // nobody leaves while the peer may still multicast into this CTA or signal its barriers
   if (warp == MMA_WARP) tmem_dealloc(tmem_base, TMEM_COLS);
   if (tid == 0) DBG16(1);
 }
@@ -768,6 +812,25 @@ static int launch(const Params& p_in, dim3 grid, cudaStream_t st) {
   } else {
     if ((rc = make_map(&ma, p.A, p.lda, p.a_mn, p.M, p.K))) return rc;
     if ((rc = make_map(&mb, p.Bm, p.ldb, p.b_mn, p.N, p.K))) return rc;
+  }
+  // A-stationary pre-split kernels (vocabulary forward / softmax gradient), opt-in with DVAE_TC16_MCAST=1: CTA pairs along
+  // the row blocks share their B tiles by multicast (an odd row-block count gets one padding CTA).  Measured at cfg 2:
+  // correct, but no faster (tile period 3.0 vs 3.1 us, whole forward call 82.7 vs 79.7 us): the B ring is bound by the
+  // ~1.3 us latency of a 16 KB fetch against 6 stages, not by L2 -> SM bytes, and the pair runs at the pace of its slower CTA.
+  const char* mc_env = getenv("DVAE_TC16_MCAST");
+  const bool mcast_on = mc_env && mc_env[0] == '1';
+  if (mcast_on && p.presplit && ceil_div(p.K, BK) <= AS_MAX_KB && grid.z == 1 && grid.x >= 2) {
+    p.mcast = 1;
+    grid.x = (grid.x + 1) / 2 * 2;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = dim3(NUM_THREADS); cfg.dynamicSmemBytes = SMEM_BYTES; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    DVAE_CUDA(cudaLaunchKernelEx(&cfg, tc16_gemm_kernel, ma, mb, p));
+    DVAE_LAUNCH_CHECK();
+    return DVAE_OK;
   }
   tc16_gemm_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(ma, mb, p);
   DVAE_LAUNCH_CHECK();

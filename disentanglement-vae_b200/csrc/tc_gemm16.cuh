@@ -27,6 +27,7 @@ struct Params {
   // pre-split mode: the operands are fp16 (hi, lo) planes in global memory (split_planes), blocked by core matrix
   float* zero_buf; int64_t zero_n4;      // optional: up to two buffers (float4 counts) the kernel clears on its way in
   float* zero_buf2; int64_t zero2_n4;    //           (outputs of later split-K GEMMs; see tc_gemm16.cu)
+  int mcast;                             // A-stationary pre-split kernels launched as CTA pairs: B stages fetched half each, multicast
   int presplit; int b_row0;     // b_row0: first B row of this call inside the B planes (a vocabulary chunk)
   const void* a_planes; const void* b_planes; int a_rows, b_rows;      // tile-blocked fp16 planes (split_planes)
   int dbg_skip_epilogue;     // probes only (DVAE_TC_SKIP_EPILOGUE=1): accumulators are released unread

@@ -468,6 +468,13 @@ def test_vocab_ce(lib, L, T1, B, H, V):
     assert rel(d_b2, d_b.cpu().numpy().astype(np.float64)) < 1e-6
 
 
+def test_vocab_ce_cta_pair_multicast(lib, L, monkeypatch):
+    """DVAE_TC16_MCAST=1: CTA pairs fetch half of every B stage each and multicast it (odd row-block count: padding CTA)."""
+    monkeypatch.setenv("DVAE_TC16_MCAST", "1")
+    test_vocab_ce(lib, L, 6, 50, 64, 3001)         # 3 row blocks -> 4 CTAs along x
+    test_vocab_ce(lib, L, 19, 128, 256, 10000)
+
+
 def test_vocab_ce_simt_path_matches_oracle_too(lib, L, monkeypatch):
     """DVAE_GEMM_IMPL=simt forces the fp32 SIMT kernels on a shape the tensor-core path takes."""
     monkeypatch.setenv("DVAE_GEMM_IMPL", "simt")
