@@ -182,6 +182,26 @@ __device__ __forceinline__ void tmem_ld8_pair(uint32_t ta, uint32_t tb, float (&
   for (int i = 0; i < 8; ++i) { v[i] = __uint_as_float(r[i]); w[i] = __uint_as_float(q[i]); }
 }
 
+// A operand from tensor memory (lane = row, one 32-bit column = two consecutive k), B from shared memory
+__device__ __forceinline__ void mma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// registers -> 16 consecutive 32-bit columns of this thread's TMEM lane
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+      "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
 // ---- descriptors -----------------------------------------------------------------------------------
 // Shared-memory matrix descriptor (sm_100 version 1), SWIZZLE_128B canonical layouts of 4-byte elements:
 //   K-major : rows of 128 B (32 floats of K), 8-row swizzle atoms 1024 B apart      -> SBO = 1024, LBO unused (1)

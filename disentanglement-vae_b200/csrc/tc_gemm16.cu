@@ -38,7 +38,7 @@ constexpr int BM = 128, BN = 128, BK = 32;
 // hi + lo out: same bytes, so landing buffers and operand planes share one ring and all of it hides TMA latency
 // (a separate 2-stage landing ring + 3-stage padded plane ring delivered a k-block every 0.73 us; TMA latency under load
 // is ~1.3 us, so the stages in flight, not the converters or the MMAs, set the pace).
-constexpr int STAGES = 6, MAX_STAGES = 6;
+constexpr int STAGES = 6, MAX_STAGES = 14;
 constexpr int RAW_TILE = BM * BK * 4;              // one landed fp32 tile: 16 KB  (= hi + lo fp16 planes of the same tile)
 constexpr int STAGE_BYTES = 2 * RAW_TILE;          // A, B
 constexpr int PS_PLANE = BM * BK * 2, PS_TILE = 2 * PS_PLANE;      // one fp16 plane: 8 KB; [hi, lo] of one operand tile: 16 KB
@@ -51,19 +51,25 @@ constexpr int CONV_BARRIER = 1;                                  // named barrie
 constexpr int EPI_SCRATCH_BYTES = 8 * 32 * 32 * 4;               // per epilogue warp: a 32 x 32 fp32 transpose tile (XOR-swizzled)
 // Pre-split mode (operands already split into tile-blocked fp16 planes in global memory): no converters -- bulk copies
 // deliver MMA-ready stages [A tile | B tile] straight into the ring.
-// A-stationary variant (pre-split, K <= 256, no split-K): the CTA's A rows (both planes, all k-blocks: 128 KB) are loaded
-// once and stay in shared memory for the CTA's whole run of N tiles; only B tiles (16 KB per k-block) stream through a
-// 4-stage ring (6 stages in mode 1, whose epilogue needs no transpose scratch).
-constexpr int AS_MAX_KB = 8, AS_A_BYTES = AS_MAX_KB * PS_TILE, AS_STAGE_BYTES = PS_TILE;
-constexpr int AS_STAGES = 4, AS_STAGES_NOSCRATCH = 6;
+// A-stationary variant (pre-split, K <= 256, no split-K: the vocabulary kernels): the CTA's A rows live in TENSOR MEMORY
+// for its whole run of N tiles (A operand of tcgen05.mma from TMEM: lane = row, 128 columns per fp16 plane), and all
+// three products accumulate into ONE fp32 accumulator -- the planes of this variant keep `lo = fp16(x*s - hi)` unscaled,
+// with s = 2^8 so that lo stays a normal fp16 number -- which leaves TMEM as [acc 0 | acc 1 | A_hi | A_lo] x 128 columns.
+// Shared memory then holds nothing but the B ring: 14 stages of 16 KB in mode 1 (no transpose scratch), 12 in mode 2
+// -- ~3 us of fetch latency covered, where 128 KB of stationary A rows in shared memory left room for 6 stages and the
+// ring, not the MMAs, set the pace.
+constexpr int AS_MAX_KB = 8, AS_STAGE_BYTES = PS_TILE;
+constexpr int AS_STAGES = 12, AS_STAGES_NOSCRATCH = 14;
+constexpr uint32_t AS_T_AHI = 256, AS_T_ALO = 384;       // TMEM columns of the stationary A planes
+constexpr float kSingleScale = 256.f;                    // operand scale of the single-accumulator planes
 // [operand ring 192 KB][epilogue transpose scratch 32 KB][bias tiles 2 KB][barriers]
 constexpr int OFF_SCRATCH = STAGES * STAGE_BYTES;
 constexpr int OFF_BIAS = OFF_SCRATCH + EPI_SCRATCH_BYTES;          // per epilogue warp: the bias values of its tile columns
 constexpr int OFF_BAR = OFF_BIAS + 8 * 64 * 4;
-constexpr int SMEM_BYTES = OFF_BAR + 256;
-static_assert(AS_A_BYTES + AS_STAGES * AS_STAGE_BYTES <= OFF_SCRATCH, "A-stationary layout must fit in the operand ring");
-static_assert(AS_A_BYTES + AS_STAGES_NOSCRATCH * AS_STAGE_BYTES <= OFF_BIAS, "A-stationary mode-1 ring must end before the bias tiles");
-static_assert(AS_STAGES_NOSCRATCH <= MAX_STAGES && (3 * MAX_STAGES + 5) * 8 + 4 <= 256, "barrier area");
+constexpr int SMEM_BYTES = OFF_BAR + 512;
+static_assert(AS_STAGES * AS_STAGE_BYTES <= OFF_SCRATCH, "A-stationary ring must end before the transpose scratch");
+static_assert(AS_STAGES_NOSCRATCH * AS_STAGE_BYTES <= OFF_BIAS, "A-stationary mode-1 ring must end before the bias tiles");
+static_assert(AS_STAGES_NOSCRATCH <= MAX_STAGES && (3 * MAX_STAGES + 5) * 8 + 4 <= 512, "barrier area");
 static_assert(SMEM_BYTES <= 232448, "shared memory per CTA");
 constexpr int TMEM_COLS = 512;
 constexpr float kLoScale = 2048.f, kLoInv = 1.f / 2048.f;
@@ -104,12 +110,12 @@ __device__ __forceinline__ float scale_from_amax(const uint32_t* amax_bits, int 
 }
 
 // (x0, x1) * s -> packed fp16 hi pair (returned) and lo pair; packed fp32 arithmetic (FMUL2 / FFMA2)
-__device__ __forceinline__ uint32_t pack_hi_lo(float x0, float x1, float s, uint32_t& lo) {
+__device__ __forceinline__ uint32_t pack_hi_lo(float x0, float x1, float s, uint32_t& lo, float ls = kLoScale) {
   const float2 x = __fmul2_rn(make_float2(x0, x1), make_float2(s, s));
   const __half2 h = __float22half2_rn(x);
   const float2 hf = __half22float2(h);
-  // (x - hi) * 2^11 = x * 2^11 - hi * 2^11 (both products exact)
-  const float2 r = __ffma2_rn(x, make_float2(kLoScale, kLoScale), __fmul2_rn(hf, make_float2(-kLoScale, -kLoScale)));
+  // (x - hi) * ls = x * ls - hi * ls (ls a power of two: both products exact); ls = 2^11, or 1 for single-accumulator planes
+  const float2 r = __ffma2_rn(x, make_float2(ls, ls), __fmul2_rn(hf, make_float2(-ls, -ls)));
   const __half2 l = __float22half2_rn(r);
   lo = *reinterpret_cast<const uint32_t*>(&l);
   return *reinterpret_cast<const uint32_t*>(&h);
@@ -190,7 +196,8 @@ __device__ __forceinline__ void bulk_load(uint32_t smem_dst, const void* src, ui
 //   tile (rb, kb) = rows rb*128.., k kb*32..  at byte ((rb * KB + kb) * 16384), KB = ceil(K / 32): [hi plane 8 KB][lo plane 8 KB],
 //   element (r, k) of a plane at ((r / 8) * 4 + k / 8) * 128 + (r % 8) * 16 + (k % 8) * 2   (core matrices: LBO 128, SBO 512).
 // Rows / columns beyond R / K are zero (R padded to 128, K to 32).
-__global__ void split_planes_kernel(const float* __restrict__ X, int64_t ld, int R, int K, float scale, uint8_t* __restrict__ planes) {
+__global__ void split_planes_kernel(const float* __restrict__ X, int64_t ld, int R, int K, float scale, float lo_scale,
+                                    uint8_t* __restrict__ planes) {
   const int KB = (K + BK - 1) / BK, KC = KB * (BK / 8), RP = (R + BM - 1) / BM * BM;
   const int64_t total = (int64_t)RP * KC;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -199,8 +206,8 @@ __global__ void split_planes_kernel(const float* __restrict__ X, int64_t ld, int
 #pragma unroll
     for (int e = 0; e < 8; ++e) v[e] = (r < R && kc * 8 + e < K) ? __ldg(X + (int64_t)r * ld + kc * 8 + e) : 0.f;
     uint4 h, l;
-    h.x = pack_hi_lo(v[0], v[1], scale, l.x); h.y = pack_hi_lo(v[2], v[3], scale, l.y);
-    h.z = pack_hi_lo(v[4], v[5], scale, l.z); h.w = pack_hi_lo(v[6], v[7], scale, l.w);
+    h.x = pack_hi_lo(v[0], v[1], scale, l.x, lo_scale); h.y = pack_hi_lo(v[2], v[3], scale, l.y, lo_scale);
+    h.z = pack_hi_lo(v[4], v[5], scale, l.z, lo_scale); h.w = pack_hi_lo(v[6], v[7], scale, l.w, lo_scale);
     const int64_t off = ((int64_t)(r >> 7) * KB + (kc >> 2)) * (2 * PS_PLANE) + ((r & 127) >> 3) * PS_SBO + (kc & 3) * PS_LBO + (r & 7) * 16;
     *reinterpret_cast<uint4*>(planes + off) = h;
     *reinterpret_cast<uint4*>(planes + off + PS_PLANE) = l;
@@ -267,7 +274,7 @@ tc16_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_init(&tmem_full[a], 1);
       mbar_init(&tmem_empty[a], wide_epi ? 2 * EPI_WARPS : EPI_WARPS);
     }
-    mbar_init(a_full, 1);
+    mbar_init(a_full, 2 * EPI_WARPS);         // A-stationary: one arrival per epilogue warp once its share of A is in TMEM
     fence_barrier_init();
   }
   if (warp == TMA_WARP && lane == 0 && !p.presplit) {
@@ -277,6 +284,8 @@ tc16_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const bool a_stat = p.presplit && nkb_total <= AS_MAX_KB && gridDim.z == 1;
   const int nstages = a_stat ? (p.mode == 1 ? AS_STAGES_NOSCRATCH : AS_STAGES) : STAGES;
   const uint32_t stage_bytes = a_stat ? AS_STAGE_BYTES : STAGE_BYTES;
+  // (a padding CTA of an odd row-block count in CTA-pair mode re-reads the last real block: it only keeps the protocol going)
+  const int a_blk = min((int)blockIdx.x, (p.M + BM - 1) / BM - 1);
   if (warp == MMA_WARP) tmem_alloc(tmem_slot, TMEM_COLS);
   tc_fence_before();
   __syncthreads();
@@ -290,13 +299,8 @@ tc16_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (DVAE_TC16_FLAG(16)) {
       // probes only: no operand traffic at all
     } else if (lane == 0 && a_stat) {
-      // A rows once (all k-blocks, both planes), then only B tiles through the ring
-      // (a padding CTA of an odd row-block count re-reads the last real block: it only has to keep the pair's protocol going)
-      const int a_blk = min((int)blockIdx.x, (p.M + BM - 1) / BM - 1);
-      const uint8_t* a_tiles = reinterpret_cast<const uint8_t*>(p.a_planes) + (int64_t)a_blk * nkb_total * PS_TILE;
+      // only B tiles stream through shared memory (the A rows go to tensor memory: see the epilogue warps' prologue)
       const uint8_t* b_planes = reinterpret_cast<const uint8_t*>(p.b_planes);
-      mbar_expect_tx(a_full, (uint32_t)nkb * PS_TILE);
-      for (int kb = 0; kb < nkb; ++kb) bulk_load(smem_u + kb * PS_TILE, a_tiles + (int64_t)kb * PS_TILE, PS_TILE, a_full);
       int stage = 0, phase = 0;
       for (int nt = nt0; nt < nt1; ++nt) {
         for (int kb = 0; kb < nkb; ++kb) {
@@ -304,7 +308,7 @@ tc16_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           if (!DVAE_TC16_FLAG(8)) mbar_wait(&empty[stage], phase ^ 1);
           else mbar_wait(&full[stage], phase ^ 1);      // probes only: free-running ring (previous fill of the slot has landed)
           DVAE_TC16_MARK(nt == nt0 + 1 && kb < 8, 33 + 2 * kb);
-          const uint32_t dst = smem_u + AS_A_BYTES + stage * AS_STAGE_BYTES;
+          const uint32_t dst = smem_u + stage * AS_STAGE_BYTES;
           mbar_expect_tx(&full[stage], AS_STAGE_BYTES);
           const uint8_t* src = b_planes + ((int64_t)(nt + b_tile0) * nkb_total + kb) * PS_TILE;
           if (csize == 1) {
@@ -383,7 +387,10 @@ tc16_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // the issuing thread, not the tensor pipe or operand delivery, the limiter (~820 cycles per k-block).
     constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);   // f16 x f16 -> f32
     if (elect_one() && nkb > 0) {
-      if (a_stat && !(DVAE_TC16_FLAG(16))) mbar_wait(a_full, 0);
+      if (a_stat) {
+        mbar_wait(a_full, 0);
+        tc_fence_after();
+      }
       // shared-memory descriptor = constant high word | (LBO field | address >> 4): only the 14-bit address field moves
       constexpr uint32_t d_hi = ((PS_SBO >> 4) & 0x3FFF) | (1u << 14);          // SBO, descriptor version, no swizzle
       constexpr uint32_t d_lo = ((PS_LBO >> 4) & 0x3FFF) << 16;
@@ -391,8 +398,7 @@ tc16_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const uint32_t stage16 = stage_bytes >> 4;
       const uint32_t base16 = smem_u >> 4;
       // operand bases: ring stage [A_hi, A_lo, B_hi, B_lo], or stationary A (k-block kb) + ring stage [B_hi, B_lo]
-      const uint32_t ring16 = a_stat ? base16 + (AS_A_BYTES >> 4) : base16;
-      const uint32_t a_kb16 = a_stat ? PS_TILE >> 4 : 0;
+      const uint32_t ring16 = base16;
       const uint32_t b_off16 = a_stat ? 0 : 2 * plane16;
       auto desc = [&](uint32_t addr16) { return ((uint64_t)d_hi << 32) | (uint64_t)(d_lo | (addr16 & 0x3FFF)); };
       int stage = 0, phase = 0;
@@ -403,30 +409,40 @@ tc16_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           mbar_wait(&tmem_empty[acc], ((tile >> 1) - 1) & 1);
           tc_fence_after();
         }
-        const uint32_t d1 = tmem_base + acc * 256, d2 = d1 + 128;
-        uint32_t a16 = a_stat ? base16 : 0;
+        const uint32_t d1 = tmem_base + (a_stat ? acc * 128 : acc * 256), d2 = d1 + 128;
         for (int kb = 0; kb < nkb; ++kb) {
           DVAE_TC16_MARK(tile == 1 && kb < 8, 48 + 2 * kb);
           // no tcgen05.fence here: the operands arrive through the async proxy (TMA) or behind the converters'
           // fence.proxy.async, and the mbarrier wait orders them
           if (!DVAE_TC16_FLAG(4)) mbar_wait(&full[stage], phase);
           DVAE_TC16_MARK(tile == 1 && kb < 8, 49 + 2 * kb);
-          const uint32_t sa16 = a_stat ? a16 : st16, sb16 = st16 + b_off16;
+          const uint32_t sa16 = st16, sb16 = st16 + b_off16;
           if (!DVAE_TC16_FLAG(2)) {
+            if (a_stat) {
+              // A from tensor memory (k-block kb = columns 16*kb .. 16*kb+15 of each plane), one accumulator
+              const uint32_t ta = tmem_base + (uint32_t)kb * 16;
 #pragma unroll
-            for (int k = 0; k < BK / 16; ++k) {
-              const uint32_t adv = k * kstep16;
-              const uint32_t accum = (kb | k) ? 1u : 0u;
-              mma_f16(d1, desc(sa16 + adv), desc(sb16 + adv), idesc, accum);
-              mma_f16(d2, desc(sa16 + adv), desc(sb16 + plane16 + adv), idesc, accum);
-              mma_f16(d2, desc(sa16 + plane16 + adv), desc(sb16 + adv), idesc, 1u);
+              for (int k = 0; k < BK / 16; ++k) {
+                const uint32_t adv = k * kstep16;
+                mma_f16_ts(d1, ta + AS_T_AHI + 8 * k, desc(sb16 + adv), idesc, (kb | k) ? 1u : 0u);
+                mma_f16_ts(d1, ta + AS_T_AHI + 8 * k, desc(sb16 + plane16 + adv), idesc, 1u);
+                mma_f16_ts(d1, ta + AS_T_ALO + 8 * k, desc(sb16 + adv), idesc, 1u);
+              }
+            } else {
+#pragma unroll
+              for (int k = 0; k < BK / 16; ++k) {
+                const uint32_t adv = k * kstep16;
+                const uint32_t accum = (kb | k) ? 1u : 0u;
+                mma_f16(d1, desc(sa16 + adv), desc(sb16 + adv), idesc, accum);
+                mma_f16(d2, desc(sa16 + adv), desc(sb16 + plane16 + adv), idesc, accum);
+                mma_f16(d2, desc(sa16 + plane16 + adv), desc(sb16 + adv), idesc, 1u);
+              }
             }
           }
           if (!DVAE_TC16_FLAG(8)) {
             if (csize == 1) tc_commit(&empty[stage]);
             else tc_commit_multicast(&empty[stage], cmask);
           }
-          a16 += a_kb16;
           st16 += stage16;
           if (++stage == nstages) { stage = 0; phase ^= 1; st16 = ring16; }
         }
@@ -458,6 +474,36 @@ tc16_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         row_scale = (tpos < p.lengths[b]) ? (p.grad_scale ? p.grad_scale[0] : 1.f) / (float)p.B : 0.f;
         tgt -= p.v0;
       }
+    }
+    if (a_stat) {
+      // the CTA's A rows -> tensor memory, once: this thread owns row quarter*32 + lane (= its TMEM lane) and, with the
+      // three other warps of its lane quarter, the k-blocks {2*c_lo, 2*c_lo + 1}; a 16-byte chunk of a plane (8 fp16 of K)
+      // is four 32-bit TMEM columns, a k-block sixteen
+      const uint8_t* a_tiles = reinterpret_cast<const uint8_t*>(p.a_planes) + (int64_t)a_blk * nkb_total * PS_TILE;
+      const int r = quarter * 32 + lane;
+      const uint32_t roff = (uint32_t)(r >> 3) * PS_SBO + (r & 7) * 16;
+      const uint32_t tlane = tmem_base + ((uint32_t)(quarter * 32) << 16);
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int kb = 2 * c_lo + i;
+        if (kb < nkb) {
+          const uint8_t* t = a_tiles + (int64_t)kb * PS_TILE + roff;
+#pragma unroll
+          for (int pl = 0; pl < 2; ++pl) {
+            uint32_t v[16];
+#pragma unroll
+            for (int kc = 0; kc < 4; ++kc) {
+              const uint4 q = __ldg(reinterpret_cast<const uint4*>(t + pl * PS_PLANE + kc * PS_LBO));
+              v[4 * kc] = q.x; v[4 * kc + 1] = q.y; v[4 * kc + 2] = q.z; v[4 * kc + 3] = q.w;
+            }
+            tmem_st16(tlane + (pl ? AS_T_ALO : AS_T_AHI) + kb * 16, v);
+          }
+        }
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(a_full);
     }
     float bias_next[2] = {0.f, 0.f};      // this warp's bias values of the next tile (vocabulary modes)
     if (p.mode != 0 && nkb > 0) {
@@ -495,7 +541,7 @@ tc16_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       for (int c = c_lo; c < c_hi; ++c) {
         const int col0 = n0 + c * 32;
         if (col0 >= p.N || DVAE_TC16_FLAG(~0)) continue;                        // warp-uniform (probe builds: any switch skips the epilogue)
-        const uint32_t ta = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * 256 + c * 32;
+        const uint32_t ta = tmem_base + ((uint32_t)(quarter * 32) << 16) + (a_stat ? acc * 128 : acc * 256) + c * 32;
         if (p.mode == 2 && wide_epi) {
           // softmax-gradient chunk with 16 epilogue warps: 2 KB of transpose scratch per warp, so the chunk goes out in two
           // [32 rows x 16 cols] halves; element (r, j) of a half lives at word r * 16 + (j ^ ((r >> 1) & 15)) and store
@@ -510,7 +556,13 @@ tc16_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
             for (int h8 = 0; h8 < 2; ++h8) {            // 8 columns at a time: 72 registers per thread is the cap here
               float v[8], w[8];
-              tmem_ld8_pair(ta + hh * 16 + h8 * 8, ta + 128 + hh * 16 + h8 * 8, v, w);
+              if (a_stat) {        // single accumulator: the lo products are already in it
+                tmem_ld8_pair(ta + hh * 16 + h8 * 8, ta + hh * 16 + h8 * 8, v, w);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) w[j] = 0.f;
+              } else {
+                tmem_ld8_pair(ta + hh * 16 + h8 * 8, ta + 128 + hh * 16 + h8 * 8, v, w);
+              }
 #pragma unroll
               for (int q = 0; q < 2; ++q) {
                 const uint4 t = lds128(sbias_u + (hh * 16 + h8 * 8 + 4 * q) * 4);
@@ -636,7 +688,13 @@ tc16_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int hh = 0; hh < 2; ++hh) {
           float v[16], w[16];
           DVAE_TC16_MARK(tid == 0 && tile == 2, 98 + 3 * hh);
-          tmem_ld16_pair(ta + hh * 16, ta + 128 + hh * 16, v, w);
+          if (a_stat) {          // single accumulator: the lo products are already in it
+            tmem_ld16(ta + hh * 16, v);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) w[j] = 0.f;
+          } else {
+            tmem_ld16_pair(ta + hh * 16, ta + 128 + hh * 16, v, w);
+          }
           DVAE_TC16_MARK(tid == 0 && tile == 2, 99 + 3 * hh);
           if (!row_ok) continue;
           // 16 logits of this row: everything below is a tree or independent per element (the serial running-max /
@@ -784,12 +842,18 @@ bool presplit_enabled() {
   return !(e && e[0] == '0');
 }
 
+// planes of the single-accumulator (A-stationary) kernels: operand scale 2^8, lo unscaled; else scale as given, lo * 2^11
+bool single_acc_planes(int K) { return ceil_div(K, BK) <= AS_MAX_KB; }
+
 int split_planes(const float* X, int64_t ld, int R, int K, float scale, void* planes, cudaStream_t st) {
+  const bool single = single_acc_planes(K);
+  const float lo_scale = single ? 1.f : kLoScale;
+  if (single) scale *= kSingleScale;
   DVAE_REQUIRE(X && planes && R > 0 && K > 0, "tc16 split_planes: bad argument");
   const int64_t work = (int64_t)ceil_div(R, BM) * BM * ceil_div(K, BK) * (BK / 8);
   int blocks = ceil_div(work, 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
-  split_planes_kernel<<<blocks, 256, 0, st>>>(X, ld, R, K, scale, reinterpret_cast<uint8_t*>(planes));
+  split_planes_kernel<<<blocks, 256, 0, st>>>(X, ld, R, K, scale, lo_scale, reinterpret_cast<uint8_t*>(planes));
   DVAE_LAUNCH_CHECK();
   return DVAE_OK;
 }
@@ -905,6 +969,7 @@ int ce_partials(const float* h, int64_t ldh, int N, int B, int H, int V, const f
   p.targets = targets; p.tgt_stride_b = tgt_stride_b; p.lengths = lengths; p.B = B; p.part = part; p.part_idx = part_idx;
   p.gumbel_seed = gumbel_seed; p.gumbel_salt = gumbel_salt;
   apply_hints(p, GemmHints());
+  if (p.presplit && single_acc_planes(H)) p.a_scale = p.b_scale = kSingleScale;      // what split_planes applied
   return launch(p, dim3(ceil_div(N, BM), nsplit, 1), st);
 }
 
@@ -927,6 +992,7 @@ int softmax_grad(const float* h, int64_t ldh, int N, int B, int H, int V, int v0
   p.targets = targets; p.tgt_stride_b = tgt_stride_b; p.lengths = lengths; p.B = B; p.lse = lse; p.grad_scale = grad_scale;
   p.v0 = v0; p.C = P; p.ldc = ldp;
   apply_hints(p, GemmHints());
+  if (p.presplit && single_acc_planes(H)) p.a_scale = p.b_scale = kSingleScale;      // what split_planes applied
   return launch(p, dim3(row_tiles, ceil_div(col_tiles, per_cta), 1), st);
 }
 
