@@ -55,11 +55,14 @@ constexpr int EPI_SCRATCH_BYTES = 8 * 32 * 32 * 4;               // per epilogue
 // for its whole run of N tiles (A operand of tcgen05.mma from TMEM: lane = row, 128 columns per fp16 plane), and all
 // three products accumulate into ONE fp32 accumulator -- the planes of this variant keep `lo = fp16(x*s - hi)` unscaled,
 // with s = 2^8 so that lo stays a normal fp16 number -- which leaves TMEM as [acc 0 | acc 1 | A_hi | A_lo] x 128 columns.
-// Shared memory then holds nothing but the B ring: 14 stages of 16 KB in mode 1 (no transpose scratch), 12 in mode 2
+// Shared memory then holds nothing but the B ring: 7 stages of 32 KB in mode 1 (no transpose scratch), 6 in mode 2
 // -- ~3 us of fetch latency covered, where 128 KB of stationary A rows in shared memory left room for 6 stages and the
 // ring, not the MMAs, set the pace.
-constexpr int AS_MAX_KB = 8, AS_STAGE_BYTES = PS_TILE;
-constexpr int AS_STAGES = 12, AS_STAGES_NOSCRATCH = 14;
+// A stage of this ring is TWO k-blocks (32 KB, one bulk copy: consecutive k-blocks of a row block are contiguous in the
+// planes): the full / empty handshake per stage costs the MMA-issuing thread ~0.1 us (measured: 2.05 us per tile with no
+// handshakes, 2.9 with one per k-block), so it is paid per 12 MMAs instead of per 6.
+constexpr int AS_MAX_KB = 8, AS_KB_PER_STAGE = 2, AS_STAGE_BYTES = AS_KB_PER_STAGE * PS_TILE;
+constexpr int AS_STAGES = 6, AS_STAGES_NOSCRATCH = 7;
 constexpr uint32_t AS_T_AHI = 256, AS_T_ALO = 384;       // TMEM columns of the stationary A planes
 constexpr float kSingleScale = 256.f;                    // operand scale of the single-accumulator planes
 // [operand ring 192 KB][epilogue transpose scratch 32 KB][bias tiles 2 KB][barriers]
@@ -303,18 +306,19 @@ tc16_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const uint8_t* b_planes = reinterpret_cast<const uint8_t*>(p.b_planes);
       int stage = 0, phase = 0;
       for (int nt = nt0; nt < nt1; ++nt) {
-        for (int kb = 0; kb < nkb; ++kb) {
+        for (int kb = 0; kb < nkb; kb += AS_KB_PER_STAGE) {
           DVAE_TC16_MARK(nt == nt0 + 1 && kb < 8, 32 + 2 * kb);
           if (!DVAE_TC16_FLAG(8)) mbar_wait(&empty[stage], phase ^ 1);
           else mbar_wait(&full[stage], phase ^ 1);      // probes only: free-running ring (previous fill of the slot has landed)
           DVAE_TC16_MARK(nt == nt0 + 1 && kb < 8, 33 + 2 * kb);
           const uint32_t dst = smem_u + stage * AS_STAGE_BYTES;
-          mbar_expect_tx(&full[stage], AS_STAGE_BYTES);
+          const uint32_t bytes = (uint32_t)min(AS_KB_PER_STAGE, nkb - kb) * PS_TILE;
+          mbar_expect_tx(&full[stage], bytes);
           const uint8_t* src = b_planes + ((int64_t)(nt + b_tile0) * nkb_total + kb) * PS_TILE;
           if (csize == 1) {
-            bulk_load(dst, src, PS_TILE, &full[stage]);
+            bulk_load(dst, src, bytes, &full[stage]);
           } else {              // my share of the stage, to both CTAs; the peer's share lands here through ITS copy
-            const uint32_t part = PS_TILE / csize, off = crank * part;
+            const uint32_t part = bytes / csize, off = crank * part;
             bulk_load_multicast(dst + off, src + off, part, &full[stage], cmask);
           }
           if (++stage == nstages) { stage = 0; phase ^= 1; }
@@ -410,6 +414,35 @@ tc16_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           tc_fence_after();
         }
         const uint32_t d1 = tmem_base + (a_stat ? acc * 128 : acc * 256), d2 = d1 + 128;
+        if (a_stat) {
+          // A from tensor memory (k-block kb = columns 16*kb .. 16*kb+15 of each plane), one accumulator, two k-blocks per stage
+          for (int kb = 0; kb < nkb; kb += AS_KB_PER_STAGE) {
+            if (!DVAE_TC16_FLAG(4)) mbar_wait(&full[stage], phase);
+            if (!DVAE_TC16_FLAG(2)) {
+#pragma unroll
+              for (int kk = 0; kk < AS_KB_PER_STAGE; ++kk) {
+                if (kb + kk < nkb) {
+                  const uint32_t ta = tmem_base + (uint32_t)(kb + kk) * 16, sb16 = st16 + kk * (PS_TILE >> 4);
+#pragma unroll
+                  for (int k = 0; k < BK / 16; ++k) {
+                    const uint32_t adv = k * kstep16;
+                    mma_f16_ts(d1, ta + AS_T_AHI + 8 * k, desc(sb16 + adv), idesc, (kb | kk | k) ? 1u : 0u);
+                    mma_f16_ts(d1, ta + AS_T_AHI + 8 * k, desc(sb16 + plane16 + adv), idesc, 1u);
+                    mma_f16_ts(d1, ta + AS_T_ALO + 8 * k, desc(sb16 + adv), idesc, 1u);
+                  }
+                }
+              }
+            }
+            if (!DVAE_TC16_FLAG(8)) {
+              if (csize == 1) tc_commit(&empty[stage]);
+              else tc_commit_multicast(&empty[stage], cmask);
+            }
+            st16 += stage16;
+            if (++stage == nstages) { stage = 0; phase ^= 1; st16 = ring16; }
+          }
+          tc_commit(&tmem_full[acc]);
+          continue;
+        }
         for (int kb = 0; kb < nkb; ++kb) {
           DVAE_TC16_MARK(tile == 1 && kb < 8, 48 + 2 * kb);
           // no tcgen05.fence here: the operands arrive through the async proxy (TMA) or behind the converters'
@@ -418,25 +451,13 @@ tc16_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           DVAE_TC16_MARK(tile == 1 && kb < 8, 49 + 2 * kb);
           const uint32_t sa16 = st16, sb16 = st16 + b_off16;
           if (!DVAE_TC16_FLAG(2)) {
-            if (a_stat) {
-              // A from tensor memory (k-block kb = columns 16*kb .. 16*kb+15 of each plane), one accumulator
-              const uint32_t ta = tmem_base + (uint32_t)kb * 16;
 #pragma unroll
-              for (int k = 0; k < BK / 16; ++k) {
-                const uint32_t adv = k * kstep16;
-                mma_f16_ts(d1, ta + AS_T_AHI + 8 * k, desc(sb16 + adv), idesc, (kb | k) ? 1u : 0u);
-                mma_f16_ts(d1, ta + AS_T_AHI + 8 * k, desc(sb16 + plane16 + adv), idesc, 1u);
-                mma_f16_ts(d1, ta + AS_T_ALO + 8 * k, desc(sb16 + adv), idesc, 1u);
-              }
-            } else {
-#pragma unroll
-              for (int k = 0; k < BK / 16; ++k) {
-                const uint32_t adv = k * kstep16;
-                const uint32_t accum = (kb | k) ? 1u : 0u;
-                mma_f16(d1, desc(sa16 + adv), desc(sb16 + adv), idesc, accum);
-                mma_f16(d2, desc(sa16 + adv), desc(sb16 + plane16 + adv), idesc, accum);
-                mma_f16(d2, desc(sa16 + plane16 + adv), desc(sb16 + adv), idesc, 1u);
-              }
+            for (int k = 0; k < BK / 16; ++k) {
+              const uint32_t adv = k * kstep16;
+              const uint32_t accum = (kb | k) ? 1u : 0u;
+              mma_f16(d1, desc(sa16 + adv), desc(sb16 + adv), idesc, accum);
+              mma_f16(d2, desc(sa16 + adv), desc(sb16 + plane16 + adv), idesc, accum);
+              mma_f16(d2, desc(sa16 + plane16 + adv), desc(sb16 + adv), idesc, 1u);
             }
           }
           if (!DVAE_TC16_FLAG(8)) {
