@@ -61,8 +61,11 @@ constexpr int EPI_SCRATCH_BYTES = 8 * 32 * 32 * 4;               // per epilogue
 // A stage of this ring is TWO k-blocks (32 KB, one bulk copy: consecutive k-blocks of a row block are contiguous in the
 // planes): the full / empty handshake per stage costs the MMA-issuing thread ~0.1 us (measured: 2.05 us per tile with no
 // handshakes, 2.9 with one per k-block), so it is paid per 12 MMAs instead of per 6.
-constexpr int AS_MAX_KB = 8, AS_KB_PER_STAGE = 2, AS_STAGE_BYTES = AS_KB_PER_STAGE * PS_TILE;
-constexpr int AS_STAGES = 6, AS_STAGES_NOSCRATCH = 7;
+#ifndef DVAE_AS_KB
+#define DVAE_AS_KB 2
+#endif
+constexpr int AS_MAX_KB = 8, AS_KB_PER_STAGE = DVAE_AS_KB, AS_STAGE_BYTES = AS_KB_PER_STAGE * PS_TILE;
+constexpr int AS_STAGES = 12 / AS_KB_PER_STAGE, AS_STAGES_NOSCRATCH = 14 / AS_KB_PER_STAGE;
 constexpr uint32_t AS_T_AHI = 256, AS_T_ALO = 384;       // TMEM columns of the stationary A planes
 constexpr float kSingleScale = 256.f;                    // operand scale of the single-accumulator planes
 // [operand ring 192 KB][epilogue transpose scratch 32 KB][bias tiles 2 KB][barriers]
