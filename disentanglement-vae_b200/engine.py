@@ -148,9 +148,7 @@ class TrainEngine:
                 return
             if self._graphs is None:
                 self._capture()
-            ga, gb = self._graphs
-            ga.replay()
-            gb.replay()
+            self._graphs[0].replay()          # one graph: forward, backward, clip + Adam
             return
         # data parallel: all-reduce the decoder gradients on a side stream while heads + encoder backward run
         if self._buckets is None:
@@ -195,17 +193,23 @@ class TrainEngine:
                 self._optim()
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
-        parts = [None] if self.world == 1 else [1, 2]
         graphs = []
-        for part in parts:
+        if self.world == 1:
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g, stream=s):
-                self._fwd_bwd(part)
+                self._fwd_bwd(None)
+                self._optim()
             graphs.append(g)
-        gb = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(gb, stream=s):
-            self._optim()
-        graphs.append(gb)
+        else:                 # the all-reduces sit between the graphs (NCCL on its own stream)
+            for part in (1, 2):
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=s):
+                    self._fwd_bwd(part)
+                graphs.append(g)
+            gb = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gb, stream=s):
+                self._optim()
+            graphs.append(gb)
         torch.cuda.synchronize()
         # undo the warm-up updates so that capture leaves the training state untouched
         self.flat.copy_(snap[0]); self.m.copy_(snap[1]); self.v.copy_(snap[2])
