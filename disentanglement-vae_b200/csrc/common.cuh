@@ -76,6 +76,7 @@ struct GemmHints {
   float a_scale = 1.f, b_scale = 1.f;
   bool a_wide = false, b_wide = false;
   bool c_zeroed = false;               // with beta == 0: C already holds zeros (a split-K GEMM then skips its memset node)
+  int concurrency = 1;                 // GEMMs of this size the caller runs at the same time (sizes the CTA count to share the SMs)
 };
 int linear_impl_ex(const float* A, int64_t lda, int trans_a, const float* B, int64_t ldb, int trans_b, float* C,
                    int64_t ldc, int M, int N, int K, const float* bias, const float* bias2, float beta, int act,

@@ -251,9 +251,11 @@ int lstm_input_proj_impl(const float* x, int64_t ldx, int T, int B, int I, int H
   DVAE_REQUIRE(T > 0 && B > 0 && I > 0 && H > 0 && (D == 1 || D == 2), "dvae_lstm_input_proj: bad shape T=%d B=%d I=%d H=%d D=%d", T, B, I, H, D);
   const int64_t slab = (int64_t)T * B * 4 * H;
   Fork fork(st);           // the two directions' input projections are independent
+  GemmHints gh;
+  gh.concurrency = D;      // they run at the same time: each sizes its grid for half of the SMs
   for (int d = 0; d < D; ++d) {
-    int rc = linear_impl(x, ldx, 0, w_ih[d], I, 0, gates + d * slab, 4 * H, T * B, 4 * H, I, b_ih ? b_ih[d] : nullptr,
-                         b_hh ? b_hh[d] : nullptr, 0.f, 0, d == 0 ? st : fork.side(0));
+    int rc = linear_impl_ex(x, ldx, 0, w_ih[d], I, 0, gates + d * slab, 4 * H, T * B, 4 * H, I, b_ih ? b_ih[d] : nullptr,
+                            b_hh ? b_hh[d] : nullptr, 0.f, 0, gh, d == 0 ? st : fork.side(0));
     if (rc) return rc;
   }
   return fork.join();

@@ -984,8 +984,15 @@ int linear(const float* A, int64_t lda, int trans_a, const float* B, int64_t ldb
       DVAE_LAUNCH_CHECK();
     }
   }
-  // more tiles than SMs: two N tiles per CTA, so the second tile's main loop hides the first one's epilogue
-  if (splits == 1 && tiles > 148 && ceil_div(N, BN) >= 2) p.tiles_per_cta = 2;
+  // more tiles than SMs: a run of N tiles per CTA, so that the next tile's main loop hides this one's epilogue and the
+  // grid (times the sibling GEMMs the caller runs concurrently, e.g. the two directions' input projections) is one wave
+  const int conc = hints.concurrency > 1 ? hints.concurrency : 1;
+  if (splits == 1 && tiles * conc > 148 && ceil_div(N, BN) >= 2) {
+    int tpc = ceil_div(tiles * conc, 148);
+    if (tpc < 2) tpc = 2;
+    if (tpc > ceil_div(N, BN)) tpc = ceil_div(N, BN);
+    p.tiles_per_cta = tpc;
+  }
   return launch(p, dim3(ceil_div(M, BM), ceil_div(ceil_div(N, BN), p.tiles_per_cta), splits), st);
 }
 
