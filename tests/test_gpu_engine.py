@@ -68,6 +68,7 @@ def test_train_engine_steps_match_oracle(dvae, use_graph, env, monkeypatch):
         grads = O.model_backward(sd, spec, fw)
         assert abs(got["total_loss"] - fw["total_loss"]) <= 1e-5 * abs(fw["total_loss"]), (step, got["total_loss"], fw["total_loss"])
         before = {k: a.copy() for k, a in sd.items()}
+        worst = 0.0
         O.clip_and_adam(sd, grads, m, v2, step + 1, lr)
         now = {k: t.detach().cpu().numpy().astype(np.float64) for k, t in vae.state_dict().items()}
         for k in sd:
@@ -76,7 +77,9 @@ def test_train_engine_steps_match_oracle(dvae, use_graph, env, monkeypatch):
             sig = np.abs(grads[k]) > 1e-4 * np.abs(grads[k]).max()
             if sig.any():
                 err = np.abs(want - have)[sig].max() / max(np.abs(want[sig]).max(), 1e-30)
-                assert err < 2e-2, (step, k, err)
+                worst = max(worst, err)
+                assert err < 2e-3, (step, k, err)      # observed: <= 4e-4
+        print(f"step {step}: loss rel err {abs(got['total_loss'] - fw['total_loss']) / abs(fw['total_loss']):.2e}, worst Adam-update rel err {worst:.2e}")
         # continue from the DEVICE weights and moments so that the comparison does not accumulate drift
         sd = O.cast_state_dict({k: t.detach().cpu().numpy() for k, t in vae.state_dict().items()})
         Mv, Vv = vae.grad_views(eng.m), vae.grad_views(eng.v)
