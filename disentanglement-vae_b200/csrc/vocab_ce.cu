@@ -281,7 +281,9 @@ static int ce_partials(CeArgs& p, cudaStream_t st) {
 
 static int ce_nsplit(int N, int V, int* tiles_per_split) {
   int row_tiles = ceil_div(N, GCE::BM), vtiles = ceil_div(V, GCE::BN);
-  int want = ceil_div(2 * 148, row_tiles);
+  // ONE wave of CTAs (row tiles x splits <= 148), each with a long run of vocabulary tiles: a second wave pays the
+  // kernel's prologue (A rows into tensor memory, pipeline fill) again -- 2 x 147 CTAs of 6 tiles took 51 us at cfg 2
+  int want = 148 / row_tiles;
   if (want < 1) want = 1;
   if (want > vtiles) want = vtiles;
   int tps = ceil_div(vtiles, want);
