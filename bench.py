@@ -3,17 +3,20 @@
 (forward + all losses + backward + [NCCL all-reduce] + clip + Adam) at BASELINE.json configs[1]
 (the sfu_amazon_100k reproduction shape) on N B200s, plus roofline / CPU-baseline / end-to-end legs.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload cfg1|cfg2|cfg3|cfg4|cfg5]
 
 N > 1 is launched by torchrun (one rank per GPU, NCCL); rank 0 prints ONE JSON line.
 Synthetic data of the reference's shape, reference initialisation under seed 10.
+Workloads: cfg2 = headline; cfg1 (config_example shape), cfg3 (per-GPU shard of the 8 x 64 data-parallel run),
+cfg4 (scaled decoder: H 1024, V 50k, T 64), cfg5 (inference: encode + resample decoding, batch 1024) are recorded under
+profiles/.
 """
 import argparse
 import importlib
 import json
 import os
-import subprocess
 import sys
+import threading
 import time
 
 import numpy as np
@@ -36,9 +39,52 @@ CFG2 = {"name": "bench/sfu_amazon_100k", "random_seed": 10, "data_dir": "", "com
 VOCAB, SEQ_T = 10000, 22
 TOTAL_STEPS = 20 * 1563          # epochs * len(dataloader) of the reproduction run
 LABELS = {"uncertainty": 1, "polarity": 1}
+BATCH = 128
+UNIFORM_LENGTHS = None
+WORKLOAD_NAME = "cfg2"
 WORKLOAD = ("cfg2 sfu_amazon_100k reproduction shape: per-GPU batch 128, T=22 (SFU length histogram: min 3, mean ~10, "
             "max 22), V=10000, E=H=256, 2-layer bi-LSTM encoder, 2-layer decoder, Z=64 (uncertainty 1, polarity 1, "
             "content 62), dropout 0.5, teacher forcing 1.0, cyclic KL")
+
+
+def select_workload(name):
+    """Rebinds the module-level workload description (BASELINE.json `configs`).  Returns the uniform length range or None
+    (SFU-like length histogram)."""
+    global CFG2, VOCAB, SEQ_T, WORKLOAD, TOTAL_STEPS, LABELS, BATCH, UNIFORM_LENGTHS, WORKLOAD_NAME
+    WORKLOAD_NAME = name
+    if name == "cfg1":       # config_example.json shape (BASELINE configs[0]; SURVEY.md 8 table row 1)
+        CFG2 = dict(CFG2, name="bench/config_example", bidirectional_encoder=False, combined_dataset=False,
+                    dataset_minibatch_ratios={}, latent_dims={"total": 32, "polarity": 1}, learn_rate=5e-3, batch_size=64,
+                    epochs=15, lambdas={"default": "cyclic", "polarity": 0.005})
+        VOCAB, SEQ_T, LABELS, BATCH = 10000, 30, {"polarity": 1}, 64
+        TOTAL_STEPS = 15 * 1563
+        UNIFORM_LENGTHS = (5, 30)
+        WORKLOAD = ("cfg1 config_example.json shape: per-GPU batch 64, T=30 (lengths U{5..30}, dSentences-like), V=10000, E=H=256, "
+                    "2-layer uni-directional LSTM encoder, 2-layer decoder, Z=32 (polarity 1, content 31), dropout 0.5, "
+                    "teacher forcing 1.0, cyclic KL, lr 5e-3 (adversarial_loss off: the ELBO + discriminator step)")
+    elif name == "cfg3":     # BASELINE configs[2]: batch 512 data-parallel over 8 GPUs = 64 rows per GPU
+        BATCH = 64
+        WORKLOAD = WORKLOAD.replace("cfg2 sfu_amazon_100k reproduction shape: per-GPU batch 128",
+                                    "cfg3 sfu_amazon_100k model, global batch 512 over 8 GPUs: per-GPU batch 64")
+    elif name == "cfg4":     # scaled decoder (SURVEY.md 8 states B = 128, lengths U{16..64})
+        CFG2 = dict(CFG2, name="bench/scaled_decoder", hidden_dim=1024)
+        VOCAB, SEQ_T = 50000, 64
+        UNIFORM_LENGTHS = (16, 64)
+        WORKLOAD = ("cfg4 scaled decoder: per-GPU batch 128, T=64 (lengths U{16..64}), V=50000, E=256, H=1024, 2-layer bi-LSTM "
+                    "encoder, 2-layer decoder, Z=64, dropout 0.5, teacher forcing 1.0, cyclic KL")
+    elif name == "cfg5":
+        BATCH = 1024
+        WORKLOAD = ("cfg5 inference (consistency-evaluation shape, scripts/evaluation/consistency.py:163-205): batch 1024, T=22, "
+                    "V=10000, E=H=256, model in train mode; per resample: fresh latents -> sampled decode (tf=0) -> on-device "
+                    "length recount -> re-encode of the sampled sentences -> discriminator logits of both passes; 30 resamples")
+    return UNIFORM_LENGTHS
+
+
+def workload_config(world, graph=True):
+    """The `config` object of the JSON line: identical in the b200 and the reference arm."""
+    return {"workload": WORKLOAD, "global_batch": BATCH * world, "seq_len": SEQ_T, "parallelism": f"dp{world}",
+            "l2": "flushed (256 MiB write) between timed steps", "cuda_graph": bool(graph),
+            "tokens": "valid tokens (sum of lengths, incl. SOS/EOS)"}
 
 
 def synth_batch(rng, B, T=None, V=None, uniform_lengths=None):
@@ -63,48 +109,57 @@ def synth_batch(rng, B, T=None, V=None, uniform_lengths=None):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock / throttle reasons / power sampled IN-PROCESS through NVML (nvidia-ml-py) by a background thread that is
+    started before warm-up; only samples taken between begin() and stop() -- the timed region -- are reported (the
+    B200_PROFILING.md clocks line).  nvidia-smi needed ~0.5 s to deliver its first line, longer than the region."""
+    REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
 
-    def __init__(self, gpu):
-        self.path = f"/tmp/dvae_clocks_{os.getpid()}.csv"
-        self.proc = None
+    def __init__(self, gpu, period_s=0.002):
+        self.samples, self.live, self._stop, self.h, self.nv = [], False, False, None, None
         try:
-            self.f = open(self.path, "w")
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "20"], stdout=self.f, stderr=subprocess.DEVNULL)
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(vis.split(",")[gpu]) if vis and all(t.strip().isdigit() for t in vis.split(",")) else gpu
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
         except Exception:
-            self.proc = None
+            self.h = None
+            return
+        self.period = period_s
+        self.t = threading.Thread(target=self._loop, daemon=True)
+        self.t.start()
+
+    def _loop(self):
+        nv = self.nv
+        while not self._stop:
+            if self.live:
+                try:
+                    mhz = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                    rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                        else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                    pw = nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+                    self.samples.append((float(mhz), int(rs), pw))
+                except Exception:
+                    pass
+            time.sleep(self.period)
+
+    def begin(self):
+        self.live = True
 
     def stop(self):
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        if self.proc is None:
+        self.live = False
+        self._stop = True
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "source": "nvml in-process thread"}
+        if self.h is None or not self.samples:
             return out
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
-        self.f.close()
-        sm, mx, reasons = [], [], set()
-        for line in open(self.path):
-            c = [x.strip() for x in line.split(",")]
-            if len(c) < 9:
-                continue
-            try:
-                sm.append(float(c[1])); mx.append(float(c[2]))
-            except ValueError:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        if sm:
-            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
-        try:
-            os.remove(self.path)
-        except OSError:
-            pass
+        sm = [s[0] for s in self.samples]
+        bits = 0
+        for s in self.samples:
+            bits |= s[1]
+        out.update(sm_mhz=float(np.median(sm)), sm_min_mhz=float(min(sm)), sm_max_mhz=self.max_mhz,
+                   reasons=[n for n, b in self.REASONS if bits & b], samples=len(sm), power_w_max=max(s[2] for s in self.samples))
         return out
 
 
@@ -118,12 +173,105 @@ def load_peaks():
         return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "src": "fallback"}
 
 
+def algorithmic_flops(B, T, cfg=None, V=None):
+    """GEMM flops (2 * MAC) of one TRAIN step (forward + backward = 3 x forward) over padded positions:
+    encoder over B*T, decoder and vocabulary projection over B*(T-1), heads per sequence.  Returns a dict per class."""
+    cfg = CFG2 if cfg is None else cfg
+    V = VOCAB if V is None else V
+    E, H = cfg["embedding_dim"], cfg["hidden_dim"]
+    D = 2 if cfg["bidirectional_encoder"] else 1
+    Le = cfg["num_rnn_layers"]
+    Ld = max(Le, 2)
+    Z = cfg["latent_dims"]["total"]
+    C = Le * D * H
+    enc_proj = D * 8 * H * E + (Le - 1) * D * 8 * H * (D * H)          # input projections, per position
+    enc_rec = Le * D * 8 * H * H                                       # recurrent products, per position
+    dec_proj = 8 * H * E + (Ld - 1) * 8 * H * H
+    dec_rec = Ld * 8 * H * H
+    vocab = 2 * H * V
+    heads = 2 * C * 2 * Z + 2 * Z * 2 * H * Ld
+    n_enc, n_dec = B * T, B * (T - 1)
+    fwd = {"lstm_input_projections": enc_proj * n_enc + dec_proj * n_dec, "recurrence": enc_rec * n_enc + dec_rec * n_dec,
+           "vocab": vocab * n_dec, "heads": heads * B}
+    train = {k: 3.0 * v for k, v in fwd.items()}
+    train["total"] = sum(train.values())
+    train["dense_gemm_class"] = train["lstm_input_projections"] + train["vocab"]       # the launches that are plain GEMMs
+    return train
+
+
 # ------------------------------------------------------------------------------------------------
-# CPU legs: the oracle port timed on the host cores (reported baseline only)
+# CPU legs (reported baseline only): the reference's own implementation when it is installed under baseline/_ref
+# (python -m pip install --target baseline/_ref /root/reference; git-ignored, travels to the GPU box), else the oracle port
 # ------------------------------------------------------------------------------------------------
+def _load_installed_reference():
+    ref_dir = os.path.join(ROOT, "baseline", "_ref")
+    if not os.path.isdir(os.path.join(ref_dir, "vae")):
+        return None
+    from oracle.ref_shim import install_stubs       # texar / torchtext import stubs (see oracle/ref_shim.py)
+    install_stubs()
+    if ref_dir not in sys.path:
+        sys.path.insert(0, ref_dir)
+    try:
+        return importlib.import_module("vae.model"), importlib.import_module("vae.losses")
+    except Exception as e:      # noqa: BLE001
+        print(f"[bench] installed reference failed to import ({e}); falling back to the oracle port", file=sys.stderr)
+        return None
+
+
+def cpu_reference_steps(n_steps, warmup, B, budget_s=150.0):
+    """The UNMODIFIED reference (vae/model.py + vae/losses.py from baseline/_ref) on the host cores, the train-step body of
+    run.py:227-262 (forward, compute_all_losses, backward, clip_grad_norm_(5.0), Adam.step, zero_grad) on this workload;
+    torch intra-op threads = all host cores; anomaly detection off (run.py:22 turns it on: favourable to the reference)."""
+    mods = _load_installed_reference()
+    if mods is None:
+        return None
+    ref_model, ref_losses = mods
+    torch.set_num_threads(os.cpu_count())
+    torch.manual_seed(10)
+    np.random.seed(10)
+    vae = ref_model.build_vae(CFG2, VOCAB, None, LABELS, torch.device("cpu"), SOS, EOS)
+    vae.train()
+    opt = torch.optim.Adam(vae.trainable_parameters(), lr=CFG2["learn_rate"])
+    rng = np.random.default_rng(10)
+    names = list(LABELS)
+
+    def one(i, Bs):
+        X, lengths, Y = synth_batch(rng, Bs, uniform_lengths=UNIFORM_LENGTHS)
+        X, lengths = torch.from_numpy(X), torch.from_numpy(lengths)
+        Yb = {n: torch.from_numpy(Y[j]).reshape(-1, 1) for j, n in enumerate(names)}
+        klw = {k: (ref_losses.get_cyclic_kl_weight(i, TOTAL_STEPS) if v == "cyclic" else v) for k, v in CFG2["lambdas"].items()}
+        t0 = time.perf_counter()
+        out = vae(X, lengths, teacher_forcing_prob=CFG2["teacher_forcing_prob"])
+        L = dict()                                                   # run.py:128-163 compute_all_losses
+        L.update(ref_losses.reconstruction_loss(X, out["decoder_logits"], lengths))
+        L.update(ref_losses.compute_kl_divergence_losses(vae, out["latent_params"], klw))
+        L.update(ref_losses.compute_discriminator_losses(vae, out["dsc_logits"], Yb))
+        total = L["reconstruction_loss"] + L["total_weighted_kl"] + L["total_dsc_loss"]
+        total.backward()
+        torch.nn.utils.clip_grad_norm_(vae.trainable_parameters(), 5.0)
+        opt.step()
+        opt.zero_grad()
+        return time.perf_counter() - t0, int(lengths.sum())
+
+    t_probe, _ = one(0, B)
+    Bs, total = B, n_steps + max(warmup - 1, 0)
+    if t_probe * total > budget_s:                       # bounded sample: shrink the batch, keep the shape
+        Bs = max(8, int(B * budget_s / (t_probe * total)) // 8 * 8)
+    for i in range(max(warmup - 1, 0)):
+        one(i + 1, Bs)
+    ts, toks = 0.0, 0
+    for i in range(n_steps):
+        dt, nt = one(warmup + i, Bs)
+        ts += dt
+        toks += nt
+    sample = (f"{n_steps} train steps of the {WORKLOAD_NAME} workload at batch {Bs}: the unmodified reference (vae/model.py + vae/losses.py "
+              f"installed under baseline/_ref, torch {torch.__version__} CPU, {torch.get_num_threads()} intra-op threads), step body of run.py:227-262")
+    return toks / ts, ts / n_steps, sample
+
+
 def cpu_port_steps(n_steps, warmup, B=128, budget_s=150.0):
-    """Times `oracle/dvae_oracle.py` (numpy, float32, BLAS threads = all host cores) on the cfg-2
-    workload: forward + losses + backward + clip + Adam.  Returns (tokens/s, s/step, sample description)."""
+    """Times `oracle/dvae_oracle.py` (numpy, float32, BLAS threads = all host cores) on the selected workload:
+    forward + losses + backward + clip + Adam.  Returns (tokens/s, s/step, sample description)."""
     from oracle import dvae_oracle as O
     dvae = importlib.import_module("disentanglement-vae_b200")
     dvae.set_seed(10)
@@ -134,13 +282,15 @@ def cpu_port_steps(n_steps, warmup, B=128, budget_s=150.0):
     m = {k: np.zeros_like(v) for k, v in sd.items()}
     v_ = {k: np.zeros_like(v) for k, v in sd.items()}
     names = list(LABELS)
+    E, H = CFG2["embedding_dim"], CFG2["hidden_dim"]
+    D = 2 if CFG2["bidirectional_encoder"] else 1
 
     def one(i, Bs):
-        X, lengths, Y = synth_batch(rng, Bs)
+        X, lengths, Y = synth_batch(rng, Bs, uniform_lengths=UNIFORM_LENGTHS)
         eps = {n: rng.standard_normal((Bs, zs)).astype(np.float32) for n, zs in zip(spec.space_names, spec.space_dims)}
-        masks_e = [(rng.random((SEQ_T, Bs, w)) >= 0.5).astype(np.float32) * 2 for w in (256, 512)]
-        masks_d = [(rng.random((SEQ_T - 1, Bs, w)) >= 0.5).astype(np.float32) * 2 for w in (256, 256)]
-        klw = {"default": O.cyclic_kl_weight(i, TOTAL_STEPS), "polarity": 0.005, "uncertainty": 0.005}
+        masks_e = [(rng.random((SEQ_T, Bs, w)) >= 0.5).astype(np.float32) * 2 for w in (E, D * H)]
+        masks_d = [(rng.random((SEQ_T - 1, Bs, w)) >= 0.5).astype(np.float32) * 2 for w in (E, H)]
+        klw = {k: (O.cyclic_kl_weight(i, TOTAL_STEPS) if v == "cyclic" else v) for k, v in CFG2["lambdas"].items()}
         t0 = time.perf_counter()
         fw = O.model_forward(sd, spec, X, lengths, eps, labels={n: Y[j].reshape(-1, 1) for j, n in enumerate(names)},
                              kl_weights=klw, enc_masks=masks_e, dec_masks=masks_d)
@@ -160,90 +310,198 @@ def cpu_port_steps(n_steps, warmup, B=128, budget_s=150.0):
         dt, nt = one(warmup + i, Bs)
         ts += dt
         toks += nt
-    sample = f"{n_steps} train steps of the cfg-2 workload at batch {Bs} (numpy float32 port of vae/model.py + vae/losses.py + run.py:254-262)"
+    sample = f"{n_steps} train steps of the {WORKLOAD_NAME} workload at batch {Bs} (numpy float32 port of vae/model.py + vae/losses.py + run.py:254-262)"
     return toks / ts, ts / n_steps, sample
+
+
+def cpu_baseline(n_steps, warmup, B, budget_s):
+    """(tokens/s, s/step, sample, kind): the installed reference when present, else the oracle port."""
+    r = cpu_reference_steps(n_steps, warmup, B, budget_s)
+    if r is not None:
+        return r + ("reference",)
+    return cpu_port_steps(n_steps, warmup, B, budget_s) + ("port",)
 
 
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    if args.workload == "cfg5":
+        print(json.dumps({"impl": "reference", "unavailable": "the inference workload has no CPU reference arm (60 full forwards "
+                          "of batch 1024 per step do not fit the bench budget); see cpu_baseline of the training workloads"}), flush=True)
+        return
     cores = os.cpu_count()
-    tps, sps, sample = cpu_port_steps(args.steps, args.warmup)
+    torch.set_num_threads(cores)          # torchrun exports OMP_NUM_THREADS=1: the CPU arm uses every host core at any N
+    tps, sps, sample, kind = cpu_baseline(args.steps, args.warmup, BATCH, 150.0)
     line = {"impl": "reference", "metric": "train_tokens_per_sec", "value": tps, "unit": "tokens/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": sps * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD},
-            "cpu_baseline": {"value": tps, "unit": "tokens/s", "cores": cores, "kind": "port", "sample": sample},
+            "config": workload_config(args.gpus, graph=not args.no_graph),
+            "cpu_baseline": {"value": tps, "unit": "tokens/s", "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": tps, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
 
 # ------------------------------------------------------------------------------------------------
-# Secondary workloads (BASELINE.json configs[3] / configs[4]); the headline line is always cfg 2.
+# cfg5: inference
 # ------------------------------------------------------------------------------------------------
-def select_workload(name):
-    """Rebinds the module-level workload description.  cfg4 = scaled decoder (H 1024, V 50k, T 64: stresses the fused
-    vocab-CE kernels; SURVEY.md 8 states B = 128, lengths U{16..64})."""
-    global CFG2, VOCAB, SEQ_T, WORKLOAD, TOTAL_STEPS
-    if name == "cfg4":
-        CFG2 = dict(CFG2, name="bench/scaled_decoder", hidden_dim=1024)
-        VOCAB, SEQ_T = 50000, 64
-        WORKLOAD = ("cfg4 scaled decoder: per-GPU batch 128, T=64 (lengths U{16..64}), V=50000, E=256, H=1024, 2-layer bi-LSTM "
-                    "encoder, 2-layer decoder, Z=64, dropout 0.5, teacher forcing 1.0, cyclic KL")
-        return (16, 64)
-    return None
-
-
 def run_inference_workload(args):
-    """cfg5: consistency-evaluation shape (scripts/evaluation/consistency.py:163-205): for each batch of 1024 sentences,
-    R = 30 resamples of [forward(x, tf=0) -> sampled reconstruction x_hat -> on-device length recount -> forward(x_hat,
-    tf=0)], model in train mode (fresh latents and dropout each time), no gradients.  One 'step' = one resample pair."""
+    """cfg5: consistency-evaluation shape (scripts/evaluation/consistency.py:163-205), batch 1024, R = 30 resamples, model in
+    train mode (consistency.py:151).  `value`: the encode-once / resample-R API (inference.ConsistencyEvaluator: one CUDA
+    graph per resample, second forward without its unused decode).  `e2e`: the reference's call pattern -- two full module
+    forwards per resample with the lengths recounted by torch ops -- with host tensors in and predictions out."""
     import __graft_entry__ as ge
     dvae = ge.build()
+    inf = importlib.import_module("disentanglement-vae_b200.inference")
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(0)
-    B, T, R = 1024, SEQ_T, 30
+    B, T, R = BATCH, SEQ_T, 30
     dvae.set_seed(10)
     vae = dvae.build_vae(CFG2, VOCAB, None, LABELS, dev, SOS, EOS)
     vae.train()
     rng = np.random.default_rng(5)
     X, L, _ = synth_batch(rng, B)
-    Xd, Ld = torch.from_numpy(X).to(dev), torch.from_numpy(L).to(dev)
-
-    def pair():
-        with torch.no_grad():
-            out = vae(Xd, Ld, teacher_forcing_prob=0.0)
-            xh = out["token_predictions"]
-            lh = xh.size(1) - ((xh == EOS) | (xh == PAD)).sum(1)          # consistency.py:186-190
-            lh = lh.clamp_(min=1)
-            out2 = vae(xh, lh, teacher_forcing_prob=0.0)
-            return out2["dsc_logits"]
-
-    n0 = dvae.launch_count()
-    for _ in range(max(args.warmup, 3)):
-        pair()
-    torch.cuda.synchronize()
-    launches = (dvae.launch_count() - n0) // max(args.warmup, 3)
-    steps = args.steps if args.steps != 50 else R
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    Xh, Lh = torch.from_numpy(X).pin_memory(), torch.from_numpy(L).pin_memory()
     clocks = ClockSampler(0)
+    ev_ = inf.ConsistencyEvaluator(vae, B, T, keep_tokens=True)
+    warm = max(args.warmup, 3)
+    steps = args.steps if args.steps != 50 else R
+    n0 = dvae.launch_count()
+    ev_.use_graph = False
+    ev_.encode_once(Xh, Lh)
+    ev_.resample(1)
+    torch.cuda.synchronize()
+    launches = dvae.launch_count() - n0
+    ev_.use_graph = True
+    ev_.resample(warm)
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    clocks.begin()
     a.record()
-    for _ in range(steps):
-        pair()
+    ev_.encode_once(Xh, Lh)
+    out = ev_.resample(steps)
+    preds = {k: v.cpu() for k, v in ev_.predictions(out["dsc_logits"]).items()}
+    preds_hat = {k: v.cpu() for k, v in ev_.predictions(out["dsc_logits_hat"]).items()}
     b.record()
     torch.cuda.synchronize()
     ms = a.elapsed_time(b)
     clk = clocks.stop()
     toks = float(L.sum()) * 2 * steps
+
+    # reference call pattern through the drop-in module surface (consistency.py:163-205)
+    def pair(Xd, Ld):
+        with torch.no_grad():
+            o = vae(Xd, Ld, teacher_forcing_prob=0.0)
+            p1 = {n: vae.discriminators[n].predict(lg).cpu() for n, lg in o["dsc_logits"].items()}
+            xh = o["token_predictions"]
+            lh = xh.size(1) - ((xh == EOS) | (xh == PAD)).sum(1)
+            lh = lh.clamp_(min=1)
+            o2 = vae(xh, lh, teacher_forcing_prob=0.0)
+            p2 = {n: vae.discriminators[n].predict(lg).cpu() for n, lg in o2["dsc_logits"].items()}
+            return p1, p2
+    Xd, Ld = Xh.to(dev), Lh.to(dev)
+    for _ in range(2):
+        pair(Xd, Ld)
+    torch.cuda.synchronize()
+    n_ref = max(3, min(steps, 10))
+    t0 = time.perf_counter()
+    Xd, Ld = Xh.to(dev, non_blocking=True), Lh.to(dev, non_blocking=True)
+    for _ in range(n_ref):
+        pair(Xd, Ld)
+    torch.cuda.synchronize()
+    ref_s = time.perf_counter() - t0
     line = {"metric": "inference_tokens_per_sec", "value": toks / (ms * 1e-3), "unit": "tokens/s", "n_gpus": 1, "steps": steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak",
+            "warmup": warm, "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "cfg5 inference: batch 1024, T=22, V=10000, E=H=256; per step = forward(x, tf=0) with sampled "
-                                   "decoding + re-encode of the sampled sentences (consistency.py loop body), 30 resamples per batch",
-                       "global_batch": B, "seq_len": T, "tokens": "valid input tokens x 2 forwards"},
-            "gpu_launches": int(launches * steps), "launches_per_step": int(launches), "clocks": clk}
+            "config": dict(workload_config(1), tokens="valid input tokens x 2 forwards per resample (the reference's accounting)",
+                           api="inference.ConsistencyEvaluator.encode_once + resample(R): host tokens in, predictions of both passes out"),
+            "e2e": {"value": float(L.sum()) * 2 * n_ref / ref_s, "unit": "tokens/s", "ms_per_step": ref_s * 1e3 / n_ref,
+                    "h2d_bytes_per_step": int(Xh.numel() * 8 + Lh.numel() * 8), "d2h_bytes_per_step": int(2 * len(LABELS) * B * 8),
+                    "path": "reference call pattern: vae(x, tf=0) -> recount -> vae(x_hat, tf=0) through the drop-in module"},
+            "gpu_launches": int(launches * steps), "launches_per_step": int(launches), "clocks": clk,
+            "check": {"resamples": steps, "mean_pred_agreement": {k: float((preds[k] == preds_hat[k]).float().mean()) for k in preds}}}
     print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+def _events(n):
+    return [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n)]
+
+
+def _timed(fn, flush, n=10):
+    evs = _events(n)
+    for a, b in evs:
+        flush.zero_()
+        a.record()
+        fn()
+        b.record()
+    torch.cuda.synchronize()
+    return float(np.median([a.elapsed_time(b) for a, b in evs]))
+
+
+def dropin_e2e(dvae, vae_cfg, dev, hpool, tokens, steps):
+    """The reference's call pattern (run.py:227-262) through the drop-in surface INTEGRATION.md describes: build_vae ->
+    forward -> compute_all_losses -> backward -> clip_grad_norm_ -> torch Adam.step -> zero_grad, host tensors in."""
+    dvae.set_seed(10)
+    vae = dvae.build_vae(vae_cfg, VOCAB, None, LABELS, dev, SOS, EOS)
+    vae.train()
+    opt = torch.optim.Adam(vae.trainable_parameters(), lr=vae_cfg["learn_rate"])
+
+    def one(i, X, L, Y):
+        Xd, Ld = X.to(dev, non_blocking=True), L.to(dev, non_blocking=True)
+        klw = {k: (dvae.losses.get_cyclic_kl_weight(i, TOTAL_STEPS) if v == "cyclic" else v) for k, v in vae_cfg["lambdas"].items()}
+        out = vae(Xd, Ld, teacher_forcing_prob=vae_cfg["teacher_forcing_prob"])
+        total, Ls = dvae.losses.compute_all_losses(vae, out, Xd, {n: y.reshape(-1, 1) for n, y in Y.items()}, Ld, klw)
+        total.backward()
+        torch.nn.utils.clip_grad_norm_(vae.trainable_parameters(), 5.0)
+        opt.step()
+        opt.zero_grad()
+        return float(total)          # D2H read of the loss, as the reference's loss logger does
+
+    for i in range(3):
+        one(i, *hpool[i % len(hpool)])
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    tok = 0
+    for i in range(steps):
+        j = i % len(hpool)
+        one(i + 3, *hpool[j])
+        tok += tokens[j]
+    torch.cuda.synchronize()
+    return tok, time.perf_counter() - t0
+
+
+def gemm_class_trace(eng, batch, steps=3):
+    """Summed device time of the dense GEMM launches (tc16 / tc / SIMT linear kernels) and of the LSTM recurrence kernels
+    in `steps` eager train steps, from CUPTI kernel records (torch.profiler) AFTER the timed region: explains the headline,
+    is never a bench value."""
+    try:
+        from torch.profiler import profile, ProfilerActivity
+        eng.use_graph = False
+        for _ in range(2):
+            eng.step_resident(*batch)
+        torch.cuda.synchronize()
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            for _ in range(steps):
+                eng.step_resident(*batch)
+            torch.cuda.synchronize()
+        gemm = rec = tot = 0.0
+        n_gemm = n_rec = 0
+        for e in prof.events():
+            if e.device_type != torch.autograd.DeviceType.CUDA:
+                continue
+            tot += e.device_time
+            nm = e.name
+            if "gemm_kernel" in nm or "linear_kernel" in nm:
+                gemm += e.device_time
+                n_gemm += 1
+            elif "lstm_" in nm:
+                rec += e.device_time
+                n_rec += 1
+        return {"gemm_us_per_step": gemm / steps, "gemm_launches_per_step": n_gemm / steps, "recurrence_us_per_step": rec / steps,
+                "recurrence_launches_per_step": n_rec / steps, "all_kernels_us_per_step": tot / steps}
+    except Exception as e:      # noqa: BLE001
+        return {"error": str(e)[:200]}
 
 
 def main():
@@ -254,15 +512,22 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--batch", type=int, default=128, help="per-GPU batch")
-    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg4", "cfg5"],
-                    help="cfg2 = headline (BASELINE.json configs[1]); cfg4 / cfg5 = secondary configs, recorded under profiles/")
+    ap.add_argument("--no-trace", action="store_true", help="skip the CUPTI GEMM-class / recurrence breakdown after the timed region")
+    ap.add_argument("--batch", type=int, default=None, help="per-GPU batch (default: the workload's)")
+    ap.add_argument("--tf", type=float, default=None, help="teacher_forcing_prob (default 1.0 = headline; 0.5 = the shipped configs' value)")
+    ap.add_argument("--workload", default="cfg2", choices=["cfg1", "cfg2", "cfg3", "cfg4", "cfg5"],
+                    help="cfg2 = headline (BASELINE.json configs[1]); the others are secondary configs, recorded under profiles/")
     args = ap.parse_args()
+    uniform_lengths = select_workload(args.workload)
+    global BATCH, CFG2
+    if args.batch is not None:
+        BATCH = args.batch
+    if args.tf is not None:
+        CFG2 = dict(CFG2, teacher_forcing_prob=args.tf)
     if args.impl == "reference":
         return run_reference_arm(args)
     if args.workload == "cfg5":
         return run_inference_workload(args)
-    uniform_lengths = select_workload(args.workload)
 
     import torch.distributed as dist
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -287,10 +552,10 @@ def main():
 
     import __graft_entry__ as ge
     dvae = ge.build()
-    from importlib import import_module
-    engine_mod = import_module("disentanglement-vae_b200.engine")
+    engine_mod = importlib.import_module("disentanglement-vae_b200.engine")
 
-    B, T = args.batch, SEQ_T
+    B, T = BATCH, SEQ_T
+    clocks = ClockSampler(local) if rank == 0 else None          # sampling thread up before warm-up; samples only in the timed region
     dvae.set_seed(10)                                     # same initial weights on every rank
     vae = dvae.build_vae(CFG2, VOCAB, None, LABELS, dev, SOS, EOS)
     vae.train()
@@ -320,9 +585,10 @@ def main():
     loss_warm = eng.losses_from(out.cpu())["total_loss"]
 
     # ---- timed region: K steps, device-timed per step, L2 flushed between steps ----
-    clocks = ClockSampler(local) if rank == 0 else None
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    ev = _events(args.steps)
     barrier()
+    if clocks:
+        clocks.begin()
     tok_sum = 0
     for i in range(args.steps):
         flush.zero_()
@@ -336,65 +602,71 @@ def main():
     dev_ms = sum(a.elapsed_time(b) for a, b in ev)
     loss_last = eng.losses_from(out.cpu())["total_loss"]
 
+    # ---- data parallel: every rank must hold bit-identical parameters after the all-reduced steps ----
+    replicas_identical = None
+    if world > 1:
+        ref = eng.flat.detach().clone()
+        dist.broadcast(ref, 0)
+        same = torch.tensor([1.0 if torch.equal(ref, eng.flat) else 0.0], device=dev)
+        dist.all_reduce(same, op=dist.ReduceOp.MIN)
+        replicas_identical = bool(same.item() == 1.0)
+        assert replicas_identical, "data-parallel replicas diverged: parameters differ across ranks after the timed steps"
+
     # ---- end-to-end leg: host buffers in, losses out, through the public engine API ----
     barrier()
     t0 = time.perf_counter()
     e2e_tok = 0
     for i in range(args.steps):
         j = i % len(hpool)
-        L = eng.step_host(*hpool[j])
+        eng.step_host(*hpool[j])
         e2e_tok += tokens[j]
     barrier()
     e2e_s = time.perf_counter() - t0
 
-    # ---- dominant-kernel roofline: vocab-CE forward kernel timed alone with CUDA events ----
+    # ---- end-to-end through the DROP-IN plugin call pattern (INTEGRATION.md's two-import swap), rank 0 of a 1-GPU run ----
+    dropin = None
+    if world == 1 and args.workload != "cfg4":
+        d_steps = min(args.steps, 20)
+        d_tok, d_s = dropin_e2e(dvae, CFG2, dev, hpool, tokens, d_steps)
+        dropin = {"value": d_tok / d_s, "unit": "tokens/s", "ms_per_step": d_s * 1e3 / d_steps, "steps": d_steps,
+                  "path": "build_vae -> forward -> compute_all_losses -> backward -> clip_grad_norm_ -> torch.optim.Adam.step "
+                          "(run.py:227-262 through the drop-in module surface; autograd + ctypes per op, no CUDA graph)"}
+
+    # ---- per-kernel rooflines, each timed alone with CUDA events (L2 flushed) ----
     pl, P = eng.plan, vae._P
     d = pl.d
     N = pl.N
-    evk = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(10)]
-    from importlib import import_module as _im
-    _L = _im("disentanglement-vae_b200._lib")
+    _L = importlib.import_module("disentanglement-vae_b200._lib")
     pl.vocab_ce(P, pl.d_hs[-1], eng.inputs, eng.lengths)            # leaves the fp16 operand planes in the workspace
-    call_ms = []
-    for a, b in evk:                                                 # the whole C-ABI call: split + kernel + finalize + loss
-        flush.zero_()
-        a.record()
-        pl.vocab_ce(P, pl.d_hs[-1], eng.inputs, eng.lengths)
-        b.record()
-    torch.cuda.synchronize()
-    call_ms = float(np.median([a.elapsed_time(b) for a, b in evk]))
-    for a, b in evk:                                                 # the kernel alone (one launch between the events)
-        flush.zero_()
-        a.record()
-        _L.check(pl.lib.dvae_vocab_ce_partials(_L.ptr(pl.d_hs[-1]), d.Hd, pl.T1, pl.B, d.Hd, d.V, _L.ptr(P["decoder.linear.weight"]),
-                                                _L.ptr(P["decoder.linear.bias"]), _L.ptr(eng.inputs), eng.inputs.stride(0),
-                                                _L.ptr(eng.lengths), d.sos, _L.ptr(pl.ce_ws), _L.stream_ptr()), "dvae_vocab_ce_partials")
-        b.record()
-    torch.cuda.synchronize()
-    k_ms = float(np.median([a.elapsed_time(b) for a, b in evk]))
+    call_ms = _timed(lambda: pl.vocab_ce(P, pl.d_hs[-1], eng.inputs, eng.lengths), flush)      # split + kernel + finalize + loss
+    k_ms = _timed(lambda: _L.check(pl.lib.dvae_vocab_ce_partials(
+        _L.ptr(pl.d_hs[-1]), d.Hd, pl.T1, pl.B, d.Hd, d.V, _L.ptr(P["decoder.linear.weight"]), _L.ptr(P["decoder.linear.bias"]),
+        _L.ptr(eng.inputs), eng.inputs.stride(0), _L.ptr(eng.lengths), d.sos, _L.ptr(pl.ce_ws), _L.stream_ptr()), "dvae_vocab_ce_partials"), flush)
+    pl._alloc_bwd()
+    ce_bwd_ms = _timed(lambda: pl.vocab_ce_bwd(P, eng.G, pl.d_hs[-1], eng.inputs, eng.lengths, None), flush)
+    adam_ms = _timed(lambda: eng._optim(), flush)
+    heads_ms = _timed(lambda: pl.heads(P, pl.ctx, pl.eps, eng.labels, eng.kl_w), flush)
+    enc_ms = _timed(lambda: pl.encode(P, eng.inputs, eng.lengths, True), flush)
 
-    # ---- secondary roofline: the fused clip + Adam + zero_grad tail (HBM-bound), timed alone ----
-    eva = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(10)]
-    for a, b in eva:
-        flush.zero_()
-        a.record()
-        eng._optim()
-        b.record()
-    torch.cuda.synchronize()
-    adam_ms = float(np.median([a.elapsed_time(b) for a, b in eva]))
+    def rec_only(enc):       # one recurrence launch alone (gates already projected): the sequential latency chain
+        lib = pl.lib
+        if enc:
+            w_ih, w_hh, b_ih, b_hh = pl._enc_w(P, 0, d.D)
+            return lambda: _L.check(lib.dvae_lstm_seq_fwd_ex(
+                _L.ptr(pl.x_enc), d.E, T, B, d.E, d.H, d.D, _L.ptr_array(w_ih), _L.ptr_array(w_hh), _L.ptr_array(b_ih),
+                _L.ptr_array(b_hh), None, None, 0, 0, _L.ptr(eng.lengths), _L.ptr(pl.e_hs[0]), d.D * d.H, pl.ctx.data_ptr(),
+                pl.ctx_c.data_ptr(), d.C, d.H, _L.ptr(pl.e_gates[0]), _L.ptr(pl.e_cs[0]), _L.ptr(pl.state_ws), 1, _L.stream_ptr()), "rec")
+        w_ih, w_hh, b_ih, b_hh = pl._dec_w(P, 0)
+        return lambda: _L.check(lib.dvae_lstm_seq_fwd_ex(
+            _L.ptr(pl.x_dec), d.E, pl.T1, B, d.E, d.Hd, 1, _L.ptr_array(w_ih), _L.ptr_array(w_hh), _L.ptr_array(b_ih),
+            _L.ptr_array(b_hh), pl.hid.data_ptr(), pl.hid.data_ptr() + 4 * d.Ld * d.Hd, d.H2L, 0, None, _L.ptr(pl.d_hs[0]), d.Hd,
+            None, None, 0, 0, _L.ptr(pl.d_gates[0]), _L.ptr(pl.d_cs[0]), _L.ptr(pl.state_ws), 1, _L.stream_ptr()), "rec")
+    rec_enc_ms = _timed(rec_only(True), flush) if not d.bow else None
+    rec_dec_ms = _timed(rec_only(False), flush)
 
-    # ---- K2 latent heads (one launch) and K1 encoder forward (embedding, 4 input GEMMs, 2 recurrence kernels), timed alone ----
-    def _timed(fn, n=10):
-        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n)]
-        for a, b in evs:
-            flush.zero_()
-            a.record()
-            fn()
-            b.record()
-        torch.cuda.synchronize()
-        return float(np.median([a.elapsed_time(b) for a, b in evs]))
-    heads_ms = _timed(lambda: pl.heads(P, pl.ctx, pl.eps, eng.labels, eng.kl_w))
-    enc_ms = _timed(lambda: pl.encode(P, eng.inputs, eng.lengths, True))
+    trace = None
+    if rank == 0 and world == 1 and not args.no_trace:
+        trace = gemm_class_trace(eng, dpool[0])
 
     stats = torch.tensor([dev_ms, e2e_s, float(tok_sum), float(e2e_tok)], dtype=torch.float64, device=dev)
     if world > 1:
@@ -410,63 +682,94 @@ def main():
         return
 
     peaks = load_peaks()
-    flops = 2.0 * N * d.H * d.V
+    ms_per_step = dev_ms / args.steps
+    alg = algorithmic_flops(B, T)
+    flops = 2.0 * N * d.Hd * d.V
     tf = flops / (k_ms * 1e-3) / 1e12
-    alg_bytes = 4.0 * (N * d.H + d.V * d.H + d.V + 2 * N)
-    traffic = None
-    try:                       # dram__bytes_read + write of this kernel from the committed `ncu --set full` capture
-        with open(os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")) as f:
-            t = json.load(f)["vocab_ce_fwd"]
-        traffic = t["dram_bytes_read"] + t["dram_bytes_write"]
-    except Exception:
-        pass
+    alg_bytes = 4.0 * (N * d.Hd + d.V * d.Hd + d.V + 2 * N)
+    traffic, traffic_src = None, None
+    for fname in ("r2_ncu_traffic.json", "r1_ncu_traffic.json"):
+        try:                   # dram__bytes_read + write of this kernel from the committed `ncu --set full` capture
+            with open(os.path.join(ROOT, "profiles", fname)) as f:
+                t = json.load(f)["vocab_ce_fwd"]
+            if args.workload in ("cfg2", "cfg3"):
+                traffic, traffic_src = t["dram_bytes_read"] + t["dram_bytes_write"], f"profiles/{fname} (ncu --set full, per launch, cfg2 shape)"
+            break
+        except Exception:
+            continue
     gemm_impl = os.environ.get("DVAE_GEMM_IMPL", "")
     kname = ("tc_gemm_kernel mode 1 (TMA + tcgen05.mma.kind::tf32, 3xTF32)" if gemm_impl.startswith("t")
-             else "tc16_gemm_kernel mode 1 (pre-split fp16 hi/lo operand planes by bulk copy, A rows stationary in SMEM, tcgen05.mma.kind::f16, two TMEM accumulators, 16 epilogue warps)")
+             else "tc16_gemm_kernel mode 1 (pre-split fp16 hi/lo operand planes by bulk copy, A rows stationary in tensor memory, tcgen05.mma.kind::f16, one TMEM accumulator, 16 epilogue warps)")
     n_par = eng.n
     Zt = d.Z
     heads_bytes = 4.0 * (B * d.C + d.C * 2 * Zt + 2 * Zt + B * Zt + 3 * B * Zt + Zt * d.H2L + B * d.H2L)
-    Dn = 2 if CFG2.get("bidirectional_encoder", True) else 1
+    Dn = d.D
     enc_flops = float(B * T) * (Dn * 8 * d.H * (d.E + d.H) + Dn * 8 * d.H * (Dn * d.H + d.H))                 # SURVEY 8a, per position
     adam_bytes = 36.0 * n_par                   # sumsq reads g; clip+Adam reads p, g, m, v and writes p, m, v and the zeroed g
+    step_tf = alg["total"] / (ms_per_step * 1e-3) / 1e12
+    secondary = [
+        {"kernel": "WHOLE TRAIN STEP (every launch of the captured graph): algorithmic GEMM flops of SURVEY.md 8a (forward + backward "
+                   "= 3 x forward, padded positions) / device ms_per_step",
+         "bound": "tensor", "achieved": step_tf, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+         "frac": step_tf / peaks["bf16_tflops_sustained"], "algorithmic_flops": alg["total"], "launch_ms": ms_per_step,
+         "peak_source": "MEASURED_PEAKS.json bf16 sustained; fp32-grade emulation executes 3 tensor flops per algorithmic flop (ceiling 1/3), "
+                        "and the step is a dependency chain of ~100 launches with 8 strictly sequential recurrences",
+         "flops_by_class": {k: v for k, v in alg.items() if k != "total"}},
+        {"kernel": "vocabulary backward = softmax-gradient recompute + d_h + d_w + d_bias (dvae_vocab_ce_bwd, all launches of the call)",
+         "bound": "tensor", "achieved": 2 * flops / (ce_bwd_ms * 1e-3) / 1e12, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+         "frac": 2 * flops / (ce_bwd_ms * 1e-3) / 1e12 / peaks["bf16_tflops"], "launch_ms": ce_bwd_ms, "algorithmic_flops": 2 * flops,
+         "note": "algorithmic 4*N*H*V (the recomputed logits, another 2*N*H*V, are not counted)"},
+        {"kernel": "sumsq_kernel + clip_adam_kernel (grad-norm clip 5.0 + Adam + zero_grad over the flat parameter buffer)",
+         "bound": "hbm", "achieved": adam_bytes / (adam_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+         "frac": adam_bytes / (adam_ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "launch_ms": adam_ms, "algorithmic_bytes": adam_bytes},
+        {"kernel": "heads_fwd_kernel (context2params, reparameterisation, KL, discriminators + losses, z2hidden: ONE launch)",
+         "bound": "hbm", "achieved": heads_bytes / (heads_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+         "frac": heads_bytes / (heads_ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "launch_ms": heads_ms, "algorithmic_bytes": heads_bytes,
+         "note": "launch/latency bound as SURVEY 8d predicts"},
+        {"kernel": "encoder forward = embedding + dropout + layers x (input-projection GEMMs + 1 persistent recurrence kernel)",
+         "bound": "latency", "achieved": enc_flops / (enc_ms * 1e-3) / 1e12, "peak": peaks["bf16_tflops"],
+         "unit": "TFLOP/s", "frac": enc_flops / (enc_ms * 1e-3) / 1e12 / peaks["bf16_tflops"], "launch_ms": enc_ms,
+         "algorithmic_flops": enc_flops, "sequential_steps": 2 * T, "us_per_sequential_step": enc_ms * 1e3 / (2 * T)},
+        {"kernel": "LSTM recurrence launches alone (gates already projected): encoder layer 0 (all directions in one launch) and decoder layer 0",
+         "bound": "latency", "unit": "us per sequential step",
+         "encoder_l0": None if rec_enc_ms is None else {"launch_ms": rec_enc_ms, "steps": T, "us_per_step": rec_enc_ms * 1e3 / T},
+         "decoder_l0": {"launch_ms": rec_dec_ms, "steps": T - 1, "us_per_step": rec_dec_ms * 1e3 / (T - 1)},
+         "achieved": rec_dec_ms * 1e3 / (T - 1), "peak": None, "frac": None}]
+    if trace and "gemm_us_per_step" in trace:
+        g_tf = alg["dense_gemm_class"] / (trace["gemm_us_per_step"] * 1e-6) / 1e12
+        secondary.insert(1, {"kernel": "GEMM CLASS aggregate: every tc16 / 3xTF32 / SIMT GEMM launch of one step (input projections, dx / dW "
+                                       "GEMMs, vocabulary forward + backward): algorithmic flops / SUMMED kernel time (they overlap on side streams)",
+                             "bound": "tensor", "achieved": g_tf, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": g_tf / peaks["bf16_tflops"],
+                             "algorithmic_flops": alg["dense_gemm_class"], "summed_kernel_us": trace["gemm_us_per_step"],
+                             "launches": trace["gemm_launches_per_step"], "source": "CUPTI kernel records of 3 eager steps after the timed region",
+                             "recurrence_kernels_summed_us": trace["recurrence_us_per_step"], "all_kernels_summed_us": trace["all_kernels_us_per_step"]})
     roof = {"kernel": kname + " = vocab-CE forward: vocabulary projection + online log-softmax / arg-max / NLL epilogue from TMEM; "
                               "the [N,V] logits are never written to HBM; ONE launch between the CUDA events (dvae_vocab_ce_partials)",
             "bound": "tensor", "achieved": tf, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": tf / peaks["bf16_tflops"],
             "peak_source": f"MEASURED_PEAKS.json bf16 burst ({peaks['src']}); fp32-grade emulation executes 3 tensor flops per algorithmic flop",
-            "traffic": traffic, "traffic_source": "profiles/r1_ncu_traffic.json (ncu --set full, per launch)",
+            "traffic": traffic, "traffic_source": traffic_src,
             "launch_ms": k_ms, "call_ms": call_ms, "call": "dvae_vocab_ce_fwd = operand split x2 + this kernel + finalize + loss",
             "tensor_flops_executed": 3 * flops, "algorithmic_flops": flops, "algorithmic_bytes": alg_bytes,
             "hbm_frac": alg_bytes / (k_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
-            "secondary": [{"kernel": "sumsq_kernel + clip_adam_kernel (grad-norm clip 5.0 + Adam + zero_grad over the flat parameter buffer)",
-                           "bound": "hbm", "achieved": adam_bytes / (adam_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                           "frac": adam_bytes / (adam_ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "launch_ms": adam_ms,
-                           "algorithmic_bytes": adam_bytes},
-                          {"kernel": "heads_fwd_kernel (context2params, reparameterisation, KL, discriminators + losses, z2hidden: ONE launch)",
-                           "bound": "hbm", "achieved": heads_bytes / (heads_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                           "frac": heads_bytes / (heads_ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "launch_ms": heads_ms,
-                           "algorithmic_bytes": heads_bytes,
-                           "note": "launch/latency bound as SURVEY 8d predicts; inside the kernel every CTA streams the full weight "
-                                   "matrices from L2 (profiles/probes/heads_timeline.py)"},
-                          {"kernel": "encoder forward = embedding + dropout + 2 layers x (2 input-projection GEMMs + 1 persistent "
-                                     "bidirectional tcgen05 recurrence kernel)",
-                           "bound": "latency", "achieved": enc_flops / (enc_ms * 1e-3) / 1e12, "peak": peaks["bf16_tflops"],
-                           "unit": "TFLOP/s", "frac": enc_flops / (enc_ms * 1e-3) / 1e12 / peaks["bf16_tflops"], "launch_ms": enc_ms,
-                           "algorithmic_flops": enc_flops, "sequential_steps": 2 * T,
-                           "us_per_sequential_step": enc_ms * 1e3 / (2 * T)}]}
+            "share_of_step": k_ms / ms_per_step, "step_frac": step_tf / peaks["bf16_tflops_sustained"],
+            "secondary": secondary}
     line = {"metric": "train_tokens_per_sec", "value": tok_sum / (dev_ms * 1e-3), "unit": "tokens/s", "n_gpus": world,
-            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "global_batch": B * world, "seq_len": T, "parallelism": f"dp{world}",
-                       "l2": "flushed (256 MiB write) between timed steps", "cuda_graph": not args.no_graph,
-                       "tokens": "valid tokens (sum of lengths, incl. SOS/EOS)"},
+            "config": workload_config(world, graph=not args.no_graph),
             "padded_tokens_per_sec": B * world * T * args.steps / (dev_ms * 1e-3),
             "e2e": {"value": e2e_tok / e2e_s, "unit": "tokens/s", "h2d_bytes_per_step": eng.h2d_bytes_per_step,
-                    "d2h_bytes_per_step": eng.d2h_bytes_per_step, "ms_per_step": e2e_s * 1e3 / args.steps},
+                    "d2h_bytes_per_step": eng.d2h_bytes_per_step, "ms_per_step": e2e_s * 1e3 / args.steps,
+                    "path": "TrainEngine.step_host: host tensors -> pinned -> H2D -> captured step -> D2H of the loss block"},
+            "e2e_dropin": dropin,
             "gpu_launches": int(launches_per_step * args.steps), "launches_per_step": int(launches_per_step),
-            "roofline": roof, "clocks": clk, "loss_after_warmup": loss_warm, "loss_last": loss_last}
-    if not args.no_cpu_baseline and world == 1 and args.workload == "cfg2":
-        tps, sps, sample = cpu_port_steps(3, 1, budget_s=25.0)
-        line["cpu_baseline"] = {"value": tps, "unit": "tokens/s", "cores": os.cpu_count(), "kind": "port", "sample": sample,
+            "roofline": roof, "clocks": clk, "loss_after_warmup": loss_warm, "loss_last": loss_last,
+            "teacher_forcing_prob": CFG2["teacher_forcing_prob"]}
+    if replicas_identical is not None:
+        line["replicas_identical"] = replicas_identical
+    if not args.no_cpu_baseline and world == 1 and args.workload in ("cfg1", "cfg2", "cfg3"):
+        tps, sps, sample, kind = cpu_baseline(3, 1, B, 25.0)
+        line["cpu_baseline"] = {"value": tps, "unit": "tokens/s", "cores": os.cpu_count(), "kind": kind, "sample": sample,
                                 "s_per_step": sps}
     print(json.dumps(line), flush=True)
     if world > 1:

@@ -307,3 +307,34 @@ extern "C" int dvae_clip_adam(float* p, float* g, float* m, float* v, int64_t n,
   DVAE_LAUNCH_CHECK();
   return DVAE_OK;
 }
+
+// ---- length recount of sampled sentences (scripts/evaluation/consistency.py:186-190) ----------------------------
+namespace dvae {
+// lengths_out[b] = max(min_len, T - #{t : tokens[b,t] == eos or tokens[b,t] == pad}); one warp per row
+__global__ void recount_lengths_kernel(const int64_t* __restrict__ tokens, int64_t sb, int64_t st_, int B, int T, int64_t eos,
+                                       int64_t pad, int64_t min_len, int64_t* __restrict__ lengths_out) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= B) return;
+  int n = 0;
+  for (int t = lane; t < T; t += 32) {
+    const int64_t tok = tokens[warp * sb + t * st_];
+    n += (tok == eos || tok == pad) ? 1 : 0;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
+  if (lane == 0) {
+    const int64_t len = (int64_t)T - n;
+    lengths_out[warp] = len < min_len ? min_len : len;
+  }
+}
+}  // namespace dvae
+
+extern "C" int dvae_recount_lengths(const int64_t* tokens, int64_t tok_stride_b, int64_t tok_stride_t, int B, int T,
+                                    int64_t eos, int64_t pad, int64_t min_len, int64_t* lengths_out, void* stream) {
+  DVAE_REQUIRE(tokens && lengths_out && B > 0 && T > 0, "dvae_recount_lengths: bad argument");
+  const int threads = 128, blocks = dvae::ceil_div((int64_t)B * 32, threads);
+  dvae::recount_lengths_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(tokens, tok_stride_b, tok_stride_t, B, T, eos, pad,
+                                                                            min_len, lengths_out);
+  DVAE_LAUNCH_CHECK();
+  return DVAE_OK;
+}

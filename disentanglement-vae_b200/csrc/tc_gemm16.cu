@@ -223,6 +223,7 @@ __global__ void split_planes_kernel(const float* __restrict__ X, int64_t ld, int
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 tc16_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, Params p) {
   extern __shared__ __align__(1024) uint8_t smem[];      // 1024-byte aligned (checked below): TMA 128-byte swizzle atoms
+  if (p.skip_flag && *p.skip_flag) return;               // grid-uniform: nothing has been allocated or initialised yet
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
   uint64_t* full = bars;                       // [MAX_STAGES] converters (or bulk copies, pre-split mode) -> MMA
   uint64_t* empty = bars + MAX_STAGES;         // [MAX_STAGES] MMA -> TMA   (tcgen05.commit)
@@ -999,8 +1000,9 @@ int linear(const float* A, int64_t lda, int trans_a, const float* B, int64_t ldb
 int ce_partials(const float* h, int64_t ldh, int N, int B, int H, int V, const float* w, const float* bias,
                 const int64_t* targets, int64_t tgt_stride_b, const int64_t* lengths, int tiles_per_split, int nsplit,
                 float* part, int* part_idx, const uint64_t* gumbel_seed, uint32_t gumbel_salt, const void* h_planes,
-                const void* w_planes, cudaStream_t st) {
+                const void* w_planes, const int* skip_flag, cudaStream_t st) {
   Params p = {};
+  p.skip_flag = skip_flag;
   if (h_planes && w_planes) { p.presplit = 1; p.a_planes = h_planes; p.b_planes = w_planes; p.a_rows = N; p.b_rows = V; }
   p.A = h; p.lda = ldh; p.Bm = w; p.ldb = H;
   p.M = N; p.N = V; p.K = H; p.tiles_per_cta = tiles_per_split; p.bias = bias; p.mode = 1;

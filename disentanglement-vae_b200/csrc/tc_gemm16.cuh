@@ -30,6 +30,8 @@ struct Params {
   int mcast;                             // A-stationary pre-split kernels launched as CTA pairs: B stages fetched half each, multicast
   int presplit; int b_row0;     // b_row0: first B row of this call inside the B planes (a vocabulary chunk)
   const void* a_planes; const void* b_planes; int a_rows, b_rows;      // tile-blocked fp16 planes (split_planes)
+  const int* skip_flag;      // optional device flag: non-zero = the whole launch is a no-op (sampled decoding: a step whose
+                             // input is teacher-forced needs no vocabulary sample; decided on the device so one CUDA graph serves every step)
   int dbg_skip_epilogue;     // probes only (DVAE_TC_SKIP_EPILOGUE=1): accumulators are released unread
   unsigned long long* dbg;   // optional: pipeline milestone timestamps (ns) of CTA (0,0,0), profiles/probes/tc16_timeline.py
 };
@@ -49,7 +51,7 @@ bool presplit_enabled();      // DVAE_VOCAB_PRESPLIT=0 disables
 int ce_partials(const float* h, int64_t ldh, int N, int B, int H, int V, const float* w, const float* bias,
                 const int64_t* targets, int64_t tgt_stride_b, const int64_t* lengths, int tiles_per_split, int nsplit,
                 float* part, int* part_idx, const uint64_t* gumbel_seed, uint32_t gumbel_salt, const void* h_planes,
-                const void* w_planes, cudaStream_t st);
+                const void* w_planes, const int* skip_flag, cudaStream_t st);
 int softmax_grad(const float* h, int64_t ldh, int N, int B, int H, int V, int v0, int vc, const float* w, const float* bias,
                  const int64_t* targets, int64_t tgt_stride_b, const int64_t* lengths, const float* lse,
                  const float* grad_scale, float* P, int64_t ldp, const void* h_planes, const void* w_planes, float* zero_buf,

@@ -39,6 +39,7 @@ struct CeArgs {
   int* part_idx;    // [nsplit][N]
   const uint64_t* gumbel_seed; uint32_t gumbel_salt;   // sampling: arg-max over logits + Gumbel noise
   const void* h_planes; const void* w_planes;          // optional pre-split fp16 operand planes (tc16::split_planes)
+  const int* skip_flag;                                // optional device flag: non-zero = no-op (see tc16::Params::skip_flag)
 };
 
 __device__ __forceinline__ void merge_ms(float& m, float& s, float m2, float s2) {
@@ -50,6 +51,7 @@ __device__ __forceinline__ void merge_ms(float& m, float& s, float m2, float s2)
 
 __global__ void __launch_bounds__(GCE::NT) vocab_ce_fwd_kernel(CeArgs p) {
   __shared__ __align__(16) float smem[GCE::SMEM_FLOATS];
+  if (p.skip_flag && *p.skip_flag) return;
   const int m0 = blockIdx.x * GCE::BM, split = blockIdx.y;
   const int ty = threadIdx.x / GCE::TX, tx = threadIdx.x % GCE::TX;
   const int vtiles = (p.V + GCE::BN - 1) / GCE::BN;
@@ -206,7 +208,7 @@ __global__ void __launch_bounds__(128) vocab_ce_loss_kernel(CeArgs p, const floa
 // sampled token per row = arg-max over the vocabulary splits of (logit + Gumbel noise)
 __global__ void vocab_sample_finalize_kernel(CeArgs p, int64_t* tokens, int64_t tok_stride) {
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= p.N) return;
+  if (n >= p.N || (p.skip_flag && *p.skip_flag)) return;      // forced step: the pre-filled token stays
   float av = -INFINITY;
   int ai = 0x7fffffff;
   for (int sp = 0; sp < p.nsplit; ++sp) {
@@ -268,7 +270,7 @@ static int ce_partials(CeArgs& p, cudaStream_t st) {
     p.part_idx = reinterpret_cast<int*>(p.part + (int64_t)p.nsplit * p.N * 4);
     return tc16::ce_partials(p.h, p.ldh, p.N, p.B, p.H, p.V, p.w, p.bias, p.targets, p.tgt_stride_b, p.lengths,
                              p.tiles_per_split, launched, p.part, p.part_idx, p.gumbel_seed, p.gumbel_salt, p.h_planes,
-                             p.w_planes, st);
+                             p.w_planes, p.skip_flag, st);
   }
   if (!force_simt_gemm() && p.N >= 64 && p.V >= 128 && p.H >= 32 && tc::tc_linear_supported(p.h, p.ldh, p.w, p.H, p.N, p.V, p.H))
     return tc::tc_ce_partials(p.h, p.ldh, p.N, p.B, p.H, p.V, p.w, p.bias, p.targets, p.tgt_stride_b, p.lengths,
@@ -351,7 +353,7 @@ static int vocab_ce_fwd_impl(const float* h, int64_t ldh, int T1, int B, int H, 
   p.part = ws;
   p.part_idx = reinterpret_cast<int*>(ws + (int64_t)p.nsplit * p.N * 4);
   p.gumbel_seed = nullptr; p.gumbel_salt = 0;
-  p.h_planes = p.w_planes = nullptr;
+  p.h_planes = p.w_planes = nullptr; p.skip_flag = nullptr;
   if (use_tc16(p.N, V, H, h, ldh, w) && use_presplit(p.N, V, H)) {
     // both operands are re-read by every tile of the other dimension: split them into fp16 planes once
     float* hp = ws + ce_part_floats(p.N, V);
@@ -486,7 +488,7 @@ extern "C" int dvae_vocab_ce_partials(const float* h, int64_t ldh, int T1, int B
   p.part = ws;
   p.part_idx = reinterpret_cast<int*>(ws + (int64_t)p.nsplit * p.N * 4);
   p.gumbel_seed = nullptr; p.gumbel_salt = 0;
-  p.h_planes = p.w_planes = nullptr;
+  p.h_planes = p.w_planes = nullptr; p.skip_flag = nullptr;
   if (use_tc16(p.N, V, H, h, ldh, w) && use_presplit(p.N, V, H)) {
     float* hp = ws + ce_part_floats(p.N, V);
     p.h_planes = hp; p.w_planes = hp + tc16::plane_floats(p.N, H);
@@ -494,9 +496,9 @@ extern "C" int dvae_vocab_ce_partials(const float* h, int64_t ldh, int T1, int B
   return ce_partials(p, (cudaStream_t)stream);
 }
 
-extern "C" int dvae_vocab_sample_step(const float* h, int64_t ldh, int B, int H, int V, const float* w, const float* bias,
-                                      const uint64_t* seed_dev, uint32_t salt, int64_t* tokens_out, int64_t tok_stride,
-                                      float* ws, void* stream) {
+static int vocab_sample_step_impl(const float* h, int64_t ldh, int B, int H, int V, const float* w, const float* bias,
+                                  const uint64_t* seed_dev, uint32_t salt, int64_t* tokens_out, int64_t tok_stride,
+                                  const int32_t* forced_flag_dev, float* ws, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   DVAE_REQUIRE(h && w && bias && seed_dev && tokens_out && ws, "dvae_vocab_sample_step: null pointer");
   DVAE_REQUIRE(B > 0 && H > 0 && V > 0, "dvae_vocab_sample_step: bad shape");
@@ -508,9 +510,22 @@ extern "C" int dvae_vocab_sample_step(const float* h, int64_t ldh, int B, int H,
   p.part_idx = reinterpret_cast<int*>(ws + (int64_t)p.nsplit * p.N * 4);
   p.gumbel_seed = seed_dev; p.gumbel_salt = salt;
   p.h_planes = p.w_planes = nullptr;      // one decode step: h has B rows only, splitting w per step would not pay
+  p.skip_flag = forced_flag_dev;
   int rc = ce_partials(p, st);
   if (rc) return rc;
   vocab_sample_finalize_kernel<<<ceil_div(B, 128), 128, 0, st>>>(p, tokens_out, tok_stride);
   DVAE_LAUNCH_CHECK();
   return DVAE_OK;
+}
+
+extern "C" int dvae_vocab_sample_step(const float* h, int64_t ldh, int B, int H, int V, const float* w, const float* bias,
+                                      const uint64_t* seed_dev, uint32_t salt, int64_t* tokens_out, int64_t tok_stride,
+                                      float* ws, void* stream) {
+  return vocab_sample_step_impl(h, ldh, B, H, V, w, bias, seed_dev, salt, tokens_out, tok_stride, nullptr, ws, stream);
+}
+
+extern "C" int dvae_vocab_sample_step_ex(const float* h, int64_t ldh, int B, int H, int V, const float* w, const float* bias,
+                                         const uint64_t* seed_dev, uint32_t salt, int64_t* tokens_out, int64_t tok_stride,
+                                         const int32_t* forced_flag_dev, float* ws, void* stream) {
+  return vocab_sample_step_impl(h, ldh, B, H, V, w, bias, seed_dev, salt, tokens_out, tok_stride, forced_flag_dev, ws, stream);
 }

@@ -1,13 +1,24 @@
 """Graph-captured data-parallel training engine: the reference's train-step body
-(`run.py:217-262`: forward -> compute_all_losses -> backward -> clip_grad_norm_(5.0) -> Adam.step
--> zero_grad) as one fixed sequence of C-ABI kernel launches over pre-allocated buffers, replayed
-as CUDA graphs, with an NCCL all-reduce of the flat gradient buffer between backward and the
+(`run.py:217-276`: forward -> compute_all_losses -> backward -> clip_grad_norm_(5.0) -> [adversary steps] ->
+Adam.step -> zero_grad -> [MI-estimator steps]) as one fixed sequence of C-ABI kernel launches over pre-allocated
+buffers, replayed as CUDA graphs, with the NCCL all-reduce of the flat gradient buffer between backward and the
 optimiser tail when world_size > 1.
 
-Same kernels and the same `StepPlan` as the drop-in autograd path (`functions.py`); what the
-engine removes is per-op host work (autograd bookkeeping, ctypes marshalling, allocator traffic).
+Same kernels and the same `StepPlan` as the drop-in autograd path (`functions.py`); what the engine removes is
+per-op host work (autograd bookkeeping, ctypes marshalling, allocator traffic).
+
+Variants of the step (all with the reference's semantics):
+  * teacher_forcing_prob == 1: whole-sequence decoder launches (the headline path).
+  * teacher_forcing_prob  < 1: one coin per decoding step from a host RNG (vae/model.py:463), uploaded as an int32
+    vector; the decoder advances step by step and the vocabulary-sampling kernels skip forced steps ON THE DEVICE, so
+    the captured graph is the same for every draw.
+  * adversarial_loss / mi_loss models (run.py:254-276): the encoder / heads / decoder / vocabulary path runs through the
+    plan as above; the small objectives on the latent spaces (adversaries, CLUB estimators) run eagerly through their
+    autograd Functions (`functions.py`, C-ABI kernels) and hand d(loss)/dz to the fused heads' backward.  Single GPU,
+    no graph.
 """
 import os
+import random
 
 import torch
 import torch.distributed as dist
@@ -23,23 +34,31 @@ def d_bow(plan):
 
 
 class TrainEngine:
+    NSLOT = 4          # pinned staging slots for the per-step scalar block (ring, guarded by CUDA events)
+
     def __init__(self, model, params, B, T, lr=None, total_steps=None, use_graph=True, max_norm=5.0,
-                 process_group=None, seed=None):
+                 process_group=None, seed=None, teacher_forcing_prob=None):
         model._require_cuda()
-        if len(model.adversaries) or len(model.mi_estimators):
-            raise NotImplementedError("TrainEngine captures the ELBO + discriminator step; models with adversarial_loss / mi_loss "
-                                      "train through the drop-in path (forward / compute_all_losses / backward, run.py:217-276)")
         self.model, self.params, self.B, self.T = model, params, B, T
         self.lib = _lib.load()
         self.device = model._flat.device
         self.plan = StepPlan(model, B, T, self.device)
         self.d = d = self.plan.d
         self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
+        self.rank = dist.get_rank(process_group) if self.world > 1 else 0
         self.pg = process_group
         self.max_norm = max_norm
         self.lr = float(params["learn_rate"] if lr is None else lr)
         self.total_steps = total_steps
         self.lambdas = params["lambdas"]
+        if total_steps is None and any(v == "cyclic" for v in self.lambdas.values()):
+            raise ValueError("a \"cyclic\" lambda needs total_steps (= epochs * len(dataloader), run.py:215-216)")
+        self.tf_prob = float(params.get("teacher_forcing_prob", 1.0) if teacher_forcing_prob is None else teacher_forcing_prob)
+        self.sampled = self.tf_prob < 1.0
+        self.aux = bool(len(model.adversaries) or len(model.mi_estimators))
+        if self.aux and self.world > 1:
+            raise NotImplementedError("adversarial_loss / mi_loss models train on one GPU through the engine (their private "
+                                      "optimizers are not all-reduced)")
         self.n = model._flat_numel
         f32 = dict(device=self.device, dtype=torch.float32)
         self.flat = model._flat[:self.n]
@@ -59,54 +78,89 @@ class TrainEngine:
         self.inputs = torch.zeros(B, T, device=self.device, dtype=torch.int64)
         self.lengths = torch.zeros(B, device=self.device, dtype=torch.int64)
         self.labels = torch.zeros(self.n_dsc, B, **f32)
+        T1 = max(T - 1, 1)
+        self.coins = torch.ones(T1, device=self.device, dtype=torch.int32)          # 1 = teacher-forced step
+        self.preds = torch.zeros(B, T, device=self.device, dtype=torch.int64) if self.sampled else None
         # pinned staging for the end-to-end (host buffers in, loss out) entry point
         self.h_inputs = torch.zeros(B, T, dtype=torch.int64).pin_memory()
         self.h_lengths = torch.zeros(B, dtype=torch.int64).pin_memory()
         self.h_labels = torch.zeros(self.n_dsc, B, dtype=torch.float32).pin_memory()
-        self.h_scal = torch.zeros(8 + max(d.S, 1), dtype=torch.float32).pin_memory()
-        self.h_seed = torch.zeros(1, dtype=torch.int64).pin_memory()
         self.h_out = torch.zeros(self.plan.out.numel(), dtype=torch.float32).pin_memory()
+        # the per-step scalar block is staged through a RING of pinned slots: an asynchronous H2D copy reads host memory
+        # when it executes, so a slot is rewritten only after the event recorded behind its last copy has completed
+        ns = self.NSLOT
+        self.h_scal = torch.zeros(ns, 8 + max(d.S, 1), dtype=torch.float32).pin_memory()
+        self.h_seed = torch.zeros(ns, 1, dtype=torch.int64).pin_memory()
+        self.h_coins = torch.ones(ns, T1, dtype=torch.int32).pin_memory()
+        self._slot_ev = [None] * ns
         self.d_scal = torch.zeros(8 + max(d.S, 1), **f32)
-        self.step_idx = 0
-        self._gen = torch.Generator().manual_seed(int(params.get("random_seed", 10)) if seed is None else seed)
-        self.use_graph = use_graph
+        self.step_idx = 0          # global step: the cyclic-KL schedule's `step` (run.py:215)
+        self.adam_step = 0         # optimizer steps taken (Adam bias correction); differs from step_idx after a resume
+        base = int(params.get("random_seed", 10)) if seed is None else int(seed)
+        if seed is None:
+            base += 7919 * self.rank          # every data-parallel shard draws its own eps / dropout / coin streams
+        self._gen = torch.Generator().manual_seed(base)
+        self._pyrand = random.Random(base)
+        self.use_graph = use_graph and not self.aux
         self._graphs = None
         self._buckets = None
         self._comm = None
         self._side = None
         self.label_names = [n for n, o in zip(d.space_names, d.dsc_out) if o > 0]
+        self.last_aux = {}
+        self.fixed_eps = None
 
     # ---- the kernel sequences ------------------------------------------------------------------
-    def _fwd_bwd(self, part=None):
+    def _forward(self, fork_ok=True):
+        pl, P, m = self.plan, self.model._P, self.model
+        # unpack the per-step scalar block (device-to-device, inside the graph)
+        self.hyper[:5].copy_(self.d_scal[:5])
+        self.kl_w.copy_(self.d_scal[8:8 + self.kl_w.numel()])
+        if self.fixed_eps is not None:      # replay given reparameterisation noise (tests; forward(eps=...) of the drop-in path)
+            pl.eps.copy_(self.fixed_eps)
+        else:
+            pl.randn_eps()
+        # the decoder's input embeddings, its layer-0 input projection and the W_out operand planes do not depend on
+        # the encoder (teacher forcing): they run on a side stream under the encoder's recurrences (64 of 148 SMs)
+        cur = torch.cuda.current_stream()
+        hoist = fork_ok and os.environ.get("DVAE_HOIST", "1") != "0" and not d_bow(pl) and not self.sampled
+        fork_prep = None
+        if hoist:
+            if self._side is None:
+                self._side = torch.cuda.Stream(device=self.device)
+
+            def fork_prep():      # forked behind the encoder's layer-0 projection GEMMs, which fill the machine themselves
+                self._side.wait_stream(cur)
+                with torch.cuda.stream(self._side):
+                    pl.decode_prepare(P, self.inputs, m.sos_token_idx, True)
+        pl.encode(P, self.inputs, self.lengths, True, after_l0_proj=fork_prep)
+        pl.heads(P, pl.ctx, pl.eps, self.labels, self.kl_w)
+        if hoist:
+            cur.wait_stream(self._side)
+        if self.sampled:
+            # vae/model.py:457-472: position i's input is inputs[:, i] when its coin is heads, else the token sampled from
+            # position i's logits; preds doubles as decoder-input buffer and as `token_predictions`
+            self.preds.copy_(self.inputs)
+            self.preds[:, 0].fill_(m.sos_token_idx)
+            h_top = pl.decode_sampled(P, self.preds, self.coins, True)
+        else:
+            h_top = pl.decode_forced(P, self.inputs, m.sos_token_idx, True)
+        pl.vocab_ce(P, h_top, self.inputs, self.lengths)
+        return h_top, hoist
+
+    def _fwd_bwd(self, part=None, g_z=None):
         """part = None: the whole forward + backward; 1: forward, vocabulary backward and decoder backward (every
         decoder.* gradient final); 2: heads and encoder backward.  The split lets the all-reduce of the decoder
-        gradients (half of the parameters) run under part 2 when training data-parallel."""
+        gradients (half of the parameters) run under part 2 when training data-parallel.  `g_z` [B,Z]: extra gradient
+        on the sampled latents (adversarial / MI objectives); a callable is evaluated after the forward pass."""
         pl, P, G, m = self.plan, self.model._P, self.G, self.model
         st = _lib.stream_ptr()
+        cur = torch.cuda.current_stream()
         if part in (None, 1):
-            # unpack the per-step scalar block (device-to-device, inside the graph)
-            self.hyper[:5].copy_(self.d_scal[:5])
-            self.kl_w.copy_(self.d_scal[8:8 + self.kl_w.numel()])
-            pl.randn_eps()
-            # the decoder's input embeddings, its layer-0 input projection and the W_out operand planes do not depend on
-            # the encoder (teacher forcing): they run on a side stream under the encoder's recurrences (64 of 148 SMs)
-            cur = torch.cuda.current_stream()
-            hoist = os.environ.get("DVAE_HOIST", "1") != "0" and not d_bow(pl)
-            fork_prep = None
-            if hoist:
-                if self._side is None:
-                    self._side = torch.cuda.Stream(device=self.device)
-
-                def fork_prep():      # forked behind the encoder's layer-0 projection GEMMs, which fill the machine themselves
-                    self._side.wait_stream(cur)
-                    with torch.cuda.stream(self._side):
-                        pl.decode_prepare(P, self.inputs, m.sos_token_idx, True)
-            pl.encode(P, self.inputs, self.lengths, True, after_l0_proj=fork_prep)
-            pl.heads(P, pl.ctx, pl.eps, self.labels, self.kl_w)
-            if hoist:
-                cur.wait_stream(self._side)
-            h_top = pl.decode_forced(P, self.inputs, m.sos_token_idx, True)
-            pl.vocab_ce(P, h_top, self.inputs, self.lengths)
+            h_top, hoist = self._forward()
+            if callable(g_z):
+                g_z = g_z()
+            self._g_z = g_z
             g_top = pl.vocab_ce_bwd(P, G, h_top, self.inputs, self.lengths, None)
             # weight-gradient GEMMs of each layer keep running on side streams while the next layer's recurrence starts
             check(self.lib.dvae_defer_joins(1), "dvae_defer_joins")
@@ -122,7 +176,7 @@ class TrainEngine:
         if part in (None, 2):
             check(self.lib.dvae_defer_joins(1), "dvae_defer_joins")
             try:
-                g_ctx = pl.heads_bwd(P, G, pl.ctx, pl.eps, self.labels, self.kl_w, pl.g_hid)
+                g_ctx = pl.heads_bwd(P, G, pl.ctx, pl.eps, self.labels, self.kl_w, pl.g_hid, g_z=getattr(self, "_g_z", None))
                 if getattr(self, "_aux_pending", False):      # the decoder's embedding-gradient scatter still reads g_dx[0]
                     torch.cuda.current_stream().wait_stream(self._side)
                     self._aux_pending = False
@@ -136,11 +190,58 @@ class TrainEngine:
         check(self.lib.dvae_clip_adam(ptr(self.flat), ptr(self.grad), ptr(self.m), ptr(self.v), self.n, ptr(self.sumsq),
                                       self.max_norm, 1.0 / self.world, ptr(self.hyper), 1, st), "dvae_clip_adam")
 
+    # ---- adversarial / MI objectives (run.py:254-276), eager ----------------------------------------------------
+    def _latents(self, z):
+        from .model import Params
+        pl, d, lat, off = self.plan, self.d, {}, 0
+        for n, zs in zip(d.space_names, d.space_dims):
+            lat[n] = Params(z[:, off:off + zs], pl.mu[:, off:off + zs], pl.logvar[:, off:off + zs])
+            off += zs
+        return lat
+
+    def _run_aux(self):
+        from . import losses
+        from .functions import adversary_logits
+        m, pl = self.model, self.plan
+        box = {}
+
+        def aux_grad():
+            # the auxiliary objectives read the sampled latents; their gradient w.r.t. z joins the heads' backward
+            z = pl.z.detach().clone().requires_grad_(True)
+            lat = self._latents(z)
+            Y = {n: self.labels[i].reshape(-1, 1) for i, n in enumerate(self.label_names)}
+            A = losses.compute_adversarial_losses(m, adversary_logits(m, lat), Y)
+            M = losses.compute_mi_losses(m, lat, beta=0.01)          # run.py:239: mi_loss_weight = 0.01
+            aux = A["total_adv_loss"] + M["total_mi"]
+            if aux.requires_grad:
+                aux.backward(retain_graph=True)      # also leaves the entropy-term gradients in the adversaries' .grad (run.py:254)
+            box.update(A=A, M=M, z=z)
+            return z.grad.contiguous() if z.grad is not None else None
+
+        self._fwd_bwd(None, g_z=aux_grad)
+        A, M, z = box["A"], box["M"], box["z"]
+        for name, dsc_loss in A["idv_adv_dsc_losses"].items():      # run.py:256-260
+            m.adversaries[name].optimizer_step(dsc_loss)
+        self._optim()                                                # clip_grad_norm_ + optimizer.step + zero_grad
+        est_losses = {}
+        for pair in M["idv_mi_estimates"]:                           # run.py:264-276
+            est = m.mi_estimators[pair]
+            n1, n2 = pair.split('-')
+            lat = self._latents(z.detach())
+            mi_loss = est.learning_loss(lat[n1].z, lat[n2].z)
+            est.optimizer_step(mi_loss)
+            est_losses[pair] = mi_loss
+        self.last_aux = {"total_adv_loss": A["total_adv_loss"], "total_mi": M["total_mi"],
+                         "idv_adv_losses": A["idv_adv_losses"], "idv_adv_dsc_accs": A["idv_adv_dsc_accs"],
+                         "idv_mi_estimates": M["idv_mi_estimates"], "mi_estimator_loss": est_losses}
+
     def _grad_buckets(self):
         from .dist import grad_buckets
         return grad_buckets(self.model, self.grad)
 
     def _run(self):
+        if self.aux:
+            return self._run_aux()
         if self.world == 1:
             if not self.use_graph:
                 self._fwd_bwd()
@@ -217,29 +318,49 @@ class TrainEngine:
         self._graphs = tuple(graphs)
 
     # ---- per-step host scalars -----------------------------------------------------------------
-    def _fill_scalars(self):
+    def _stage_scalars(self):
+        """Fill the next pinned slot (Adam hyper-parameters and step count, KL weights, dropout / noise seed, teacher-forcing
+        coins) and enqueue its upload.  The slot is reused NSLOT steps later, after the event behind this upload."""
+        slot = self._next_slot()
+        ev = self._slot_ev[slot]
+        if ev is not None:
+            ev.synchronize()
         step = self.step_idx
-        h = self.h_scal
-        h[0], h[1], h[2], h[3], h[4] = self.lr, 0.9, 0.999, 1e-8, float(step + 1)
+        h = self.h_scal[slot]
+        h[0], h[1], h[2], h[3], h[4] = self.lr, 0.9, 0.999, 1e-8, float(self.adam_step + 1)
         for i, n in enumerate(self.d.space_names):
             w = self.lambdas[n] if n in self.lambdas else self.lambdas["default"]
             if w == "cyclic":
-                w = get_cyclic_kl_weight(step, self.total_steps if self.total_steps else 1)
+                w = get_cyclic_kl_weight(step, self.total_steps)
             h[8 + i] = float(w)
-        self.h_seed[0] = int(torch.randint(0, 2 ** 62, (1,), generator=self._gen))
+        self.h_seed[slot, 0] = int(torch.randint(0, 2 ** 62, (1,), generator=self._gen))
+        self.d_scal.copy_(h, non_blocking=True)
+        self.plan.seed_dev.copy_(self.h_seed[slot], non_blocking=True)
+        if self.sampled:
+            c = self.h_coins[slot]
+            for i in range(c.numel()):      # one coin per decoding step, shared by the batch (vae/model.py:463)
+                c[i] = 1 if self._pyrand.random() < self.tf_prob else 0
+            self.coins.copy_(c, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        self._slot_ev[slot] = ev
+
+    def _next_slot(self):
+        self._slot = (getattr(self, "_slot", -1) + 1) % self.NSLOT
+        return self._slot
 
     # ---- public entry points -------------------------------------------------------------------
     def step_resident(self, inputs_dev, lengths_dev, labels_dev):
         """One train step on a batch already in HBM; returns the device result block
-        (plan.out: [0] weighted KL, [1] KL, [2] dsc loss, [3..] per space, [27] reconstruction)."""
-        self._fill_scalars()
-        self.d_scal.copy_(self.h_scal, non_blocking=True)
-        self.plan.seed_dev.copy_(self.h_seed, non_blocking=True)
+        (plan.out: [0] weighted KL, [1] KL, [2] dsc loss, [3..] per space, [27] reconstruction).
+        Asynchronous: may be called back to back without synchronising."""
+        self._stage_scalars()
         self.inputs.copy_(inputs_dev, non_blocking=True)
         self.lengths.copy_(lengths_dev, non_blocking=True)
         self.labels.copy_(labels_dev, non_blocking=True)
         self._run()
         self.step_idx += 1
+        self.adam_step += 1
         return self.plan.out
 
     def step_host(self, inputs, lengths, labels):
@@ -249,9 +370,7 @@ class TrainEngine:
         self.h_lengths.copy_(lengths)
         for i, n in enumerate(self.label_names):
             self.h_labels[i].copy_(labels[n].reshape(-1))
-        self._fill_scalars()
-        self.d_scal.copy_(self.h_scal, non_blocking=True)
-        self.plan.seed_dev.copy_(self.h_seed, non_blocking=True)
+        self._stage_scalars()
         self.inputs.copy_(self.h_inputs, non_blocking=True)
         self.lengths.copy_(self.h_lengths, non_blocking=True)
         self.labels.copy_(self.h_labels, non_blocking=True)
@@ -259,6 +378,7 @@ class TrainEngine:
         self.h_out.copy_(self.plan.out, non_blocking=True)
         torch.cuda.current_stream().synchronize()
         self.step_idx += 1
+        self.adam_step += 1
         return self.losses_from(self.h_out)
 
     def losses_from(self, out):
@@ -269,12 +389,88 @@ class TrainEngine:
              "idv_dsc_losses": {n: o[3 + S + i] for i, n in enumerate(self.d.space_names) if self.d.dsc_out[i] > 0},
              "idv_dsc_accs": {n: o[3 + 2 * S + i] for i, n in enumerate(self.d.space_names) if self.d.dsc_out[i] > 0}}
         L["total_loss"] = o[NS] + o[0] + o[2]
+        if self.aux and self.last_aux:
+            L["total_adv_loss"] = float(self.last_aux["total_adv_loss"])
+            L["total_mi"] = float(self.last_aux["total_mi"])
+            for k in ("idv_adv_losses", "idv_adv_dsc_accs", "idv_mi_estimates"):
+                L[k] = self.last_aux[k]
+            L["total_loss"] += L["total_adv_loss"] + L["total_mi"]
         return L
 
     @property
+    def token_predictions(self):
+        """[B,T] decoder inputs of the last step (vae/model.py:455-472): sampled where the coin said so."""
+        if self.sampled:
+            return self.preds
+        p = self.inputs.clone()
+        p[:, 0] = self.model.sos_token_idx
+        return p
+
+    # ---- optimizer state in the reference's checkpoint format (run.py:624-630, vae/utils.py:147-175) -------------
+    def _trainable(self):
+        name_of = {id(p): n for n, p in self.model.named_parameters()}
+        return [(name_of[id(p)], p) for p in self.model.trainable_parameters()]
+
+    def optimizer_state_dict(self):
+        """`torch.optim.Adam(model.trainable_parameters(), lr).state_dict()` of this engine's state: what the reference
+        stores under "optimizer_state_dict" (run.py:627-628), loadable by its `utils.load_latest_checkpoint`."""
+        opt = torch.optim.Adam([p for _, p in self._trainable()], lr=self.lr)
+        if self.adam_step > 0:
+            Mv, Vv = self.model.grad_views(self.m), self.model.grad_views(self.v)
+            for n, p in self._trainable():
+                opt.state[p] = {"step": torch.tensor(float(self.adam_step)), "exp_avg": Mv[n].detach().clone(),
+                                "exp_avg_sq": Vv[n].detach().clone()}
+        return opt.state_dict()
+
+    def load_optimizer_state_dict(self, sd):
+        """Inverse of optimizer_state_dict(): accepts the state of the reference's Adam over the same model."""
+        tr = self._trainable()
+        groups = sd["param_groups"]
+        ids = [i for g in groups for i in g["params"]]
+        if len(ids) != len(tr):
+            raise ValueError(f"optimizer state has {len(ids)} parameters, the model has {len(tr)} trainable ones")
+        self.lr = float(groups[0]["lr"])
+        Mv, Vv = self.model.grad_views(self.m), self.model.grad_views(self.v)
+        self.m.zero_(); self.v.zero_()
+        steps = set()
+        for i, (n, p) in zip(ids, tr):
+            st = sd["state"].get(i)
+            if st is None:
+                continue
+            if tuple(st["exp_avg"].shape) != tuple(p.shape):
+                raise ValueError(f"optimizer state of '{n}' has shape {tuple(st['exp_avg'].shape)}, expected {tuple(p.shape)}")
+            Mv[n].copy_(st["exp_avg"].to(self.device, torch.float32).reshape(Mv[n].shape))
+            Vv[n].copy_(st["exp_avg_sq"].to(self.device, torch.float32).reshape(Vv[n].shape))
+            steps.add(int(float(st["step"])))
+        if len(steps) > 1:
+            raise ValueError(f"per-parameter Adam step counts differ: {sorted(steps)}")
+        self.adam_step = steps.pop() if steps else 0
+
+    # the engine can stand in for the reference's `optimizer` object in utils.load_latest_checkpoint / torch.save
+    state_dict = optimizer_state_dict
+    load_state_dict = load_optimizer_state_dict
+
+    def save_checkpoint(self, ckpt_dir, epoch):
+        """run.py:624-630: {model_state_dict, optimizer_state_dict, epoch} -> model_{epoch}.pt"""
+        os.makedirs(ckpt_dir, exist_ok=True)
+        path = os.path.join(ckpt_dir, f"model_{epoch}.pt")
+        torch.save({"model_state_dict": self.model.state_dict(), "optimizer_state_dict": self.optimizer_state_dict(),
+                    "epoch": epoch}, path)
+        return path
+
+    def load_latest_checkpoint(self, ckpt_dir, steps_per_epoch=None):
+        """vae/utils.py:147-175 for this engine; returns (next_epoch, file name or None).  With `steps_per_epoch` the
+        global step of the cyclic-KL schedule resumes at next_epoch * steps_per_epoch (run.py:215)."""
+        from .utils import load_latest_checkpoint
+        _, _, next_epoch, fname = load_latest_checkpoint(self.model, self, ckpt_dir, map_location=self.device)
+        if fname is not None and steps_per_epoch is not None:
+            self.step_idx = next_epoch * steps_per_epoch
+        return next_epoch, fname
+
+    @property
     def h2d_bytes_per_step(self):
-        return (self.h_inputs.numel() + self.h_lengths.numel() + self.h_seed.numel()) * 8 + \
-            (self.h_labels.numel() + self.h_scal.numel()) * 4
+        n = (self.h_inputs.numel() + self.h_lengths.numel() + 1) * 8 + (self.h_labels.numel() + self.h_scal.size(1)) * 4
+        return n + (self.h_coins.size(1) * 4 if self.sampled else 0)
 
     @property
     def d2h_bytes_per_step(self):

@@ -238,7 +238,10 @@ class StepPlan:
         decoder-input buffer and the returned `token_predictions`: preds[:,0] = <SOS>, preds[:,i] = the forced
         token (pre-filled by the caller) when coins[i-1] is true, else the token sampled from position i's
         logits, which is written here by the sampling kernel before step i reads it.  Leaves x_dec / d_gates /
-        d_cs / d_hs exactly as a whole-sequence call would, so decode_bwd / vocab_ce are shared."""
+        d_cs / d_hs exactly as a whole-sequence call would, so decode_bwd / vocab_ce are shared.
+        `coins`: a host sequence of bools, or an int32 DEVICE tensor [T1] (non-zero = forced): then every step
+        enqueues its sampling call and the kernels themselves skip the forced steps, so the launch sequence does not
+        depend on the draw and can be captured once as a CUDA graph (engine.TrainEngine with teacher forcing < 1)."""
         lib, d, st = self.lib, self.d, _lib.stream_ptr()
         B, T1 = self.B, self.T1
         hid = self.hid if hid is None else hid
@@ -247,6 +250,9 @@ class StepPlan:
             self.sample_ws = torch.empty(lib.dvae_vocab_ce_ws_floats(B, d.V, d.Hd), device=self.device, dtype=torch.float32)
         emb = P["decoder.embedding.weight"]
         W = [self._dec_w(P, l) for l in range(d.Ld)]
+        dev_coins = torch.is_tensor(coins)
+        if dev_coins:
+            assert coins.dtype == torch.int32 and coins.is_cuda and coins.numel() >= T1
         for s in range(T1):
             check(lib.dvae_embedding_fwd(ptr(emb), d.E, ptr(preds), preds.stride(0), preds.stride(1), 1, B, p,
                                          ptr(self.seed_dev), SALT_DEC_EMB, d.sos, s, ptr(self.x_dec), st),
@@ -267,12 +273,13 @@ class StepPlan:
                                          hid.data_ptr() + 4 * (d.Ld + l) * d.Hd, d.H2L, ptr(self.d_hs[l]),
                                          ptr(self.d_gates[l]), ptr(self.d_cs[l]), ptr(self.state_ws), st),
                       "dvae_lstm_step")
-            if not coins[s]:
+            if dev_coins or not coins[s]:
                 h_s = self.d_hs[-1].data_ptr() + 4 * s * B * d.Hd
-                check(lib.dvae_vocab_sample_step(h_s, d.Hd, B, d.Hd, d.V, ptr(P["decoder.linear.weight"]),
-                                                 ptr(P["decoder.linear.bias"]), ptr(self.seed_dev), SALT_SAMPLE + s,
-                                                 preds.data_ptr() + 8 * (s + 1) * preds.stride(1), preds.stride(0),
-                                                 ptr(self.sample_ws), st), "dvae_vocab_sample_step")
+                flag = coins.data_ptr() + 4 * s if dev_coins else None
+                check(lib.dvae_vocab_sample_step_ex(h_s, d.Hd, B, d.Hd, d.V, ptr(P["decoder.linear.weight"]),
+                                                    ptr(P["decoder.linear.bias"]), ptr(self.seed_dev), SALT_SAMPLE + s,
+                                                    preds.data_ptr() + 8 * (s + 1) * preds.stride(1), preds.stride(0),
+                                                    flag, ptr(self.sample_ws), st), "dvae_vocab_sample_step")
         self._dec_p = p
         self._dec_tokens, self._dec_first = preds, d.sos
         self._dec_hid = hid
@@ -394,7 +401,14 @@ class StepPlan:
                                          ptr(self.seed_dev), SALT_ENC_EMB, -1, 0, ptr(G["encoder.embedding.weight"]),
                                          st), "dvae_embedding_bwd")
 
-    def randn_eps(self):
-        check(self.lib.dvae_randn(ptr(self.eps), self.eps.numel(), ptr(self.seed_dev), SALT_EPS, _lib.stream_ptr()),
-              "dvae_randn")
+    def randn_eps(self, salt_offset=0):
+        """N(0,1) reparameterisation noise from the step seed; `salt_offset` separates several draws under one seed."""
+        check(self.lib.dvae_randn(ptr(self.eps), self.eps.numel(), ptr(self.seed_dev), SALT_EPS + salt_offset,
+                                  _lib.stream_ptr()), "dvae_randn")
         return self.eps
+
+    def recount_lengths(self, tokens, lengths_out, eos, pad=0, min_len=1):
+        """scripts/evaluation/consistency.py:186-190 on the device: length = T - #(EOS or PAD tokens), at least min_len."""
+        check(self.lib.dvae_recount_lengths(ptr(tokens), tokens.stride(0), tokens.stride(1), tokens.size(0), tokens.size(1),
+                                            eos, pad, min_len, ptr(lengths_out), _lib.stream_ptr()), "dvae_recount_lengths")
+        return lengths_out

@@ -309,6 +309,21 @@ int dvae_vocab_sample_step(const float* h, int64_t ldh, int B, int H, int V, con
                            const float* bias, const uint64_t* seed_dev, uint32_t salt, int64_t* tokens_out,
                            int64_t tok_stride, float* ws, void* stream);
 
+/* Same, decided on the DEVICE: when forced_flag_dev != NULL and *forced_flag_dev != 0 the call is a no-op and the token
+ * already in tokens_out stays (the teacher-forced input of vae/model.py:464-466).  The coin of every decoding step lives in
+ * device memory, so ONE captured CUDA graph serves every draw of the teacher-forcing coins. */
+int dvae_vocab_sample_step_ex(const float* h, int64_t ldh, int B, int H, int V, const float* w,
+                              const float* bias, const uint64_t* seed_dev, uint32_t salt, int64_t* tokens_out,
+                              int64_t tok_stride, const int32_t* forced_flag_dev, float* ws, void* stream);
+
+/* Length recount of sampled sentences before they are re-encoded (scripts/evaluation/consistency.py:186-190):
+ * lengths_out[b] = max(min_len, T - #{t : tokens[b,t] == eos or tokens[b,t] == pad}).  The reference computes this with
+ * torch ops on the token tensor it built on the CPU; here it stays on the device between the sampled decode and the
+ * re-encode.  min_len = 0 reproduces the reference exactly (which then fails inside pack_padded_sequence on an empty
+ * row); the evaluation path passes 1. */
+int dvae_recount_lengths(const int64_t* tokens, int64_t tok_stride_b, int64_t tok_stride_t, int B, int T,
+                         int64_t eos, int64_t pad, int64_t min_len, int64_t* lengths_out, void* stream);
+
 /* Backward: d_h [N,H], d_w [V,H], d_bias [V] (all overwritten) for d(loss) = grad_scale_dev[0]
  * (NULL = 1).  Softmax tiles are recomputed from h, w and the saved lse.
  *   ws: dvae_vocab_ce_bwd_ws_floats(N, V, H) floats.

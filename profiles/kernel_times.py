@@ -17,12 +17,14 @@ dvae = ge.build()
 engine_mod = import_module("disentanglement-vae_b200.engine")
 dev = torch.device("cuda")
 steps = int(sys.argv[1]) if len(sys.argv) > 1 else 5
+workload = sys.argv[2] if len(sys.argv) > 2 else "cfg2"
+uniform_lengths = bench.select_workload(workload)
 dvae.set_seed(10)
 vae = dvae.build_vae(bench.CFG2, bench.VOCAB, None, bench.LABELS, dev, bench.SOS, bench.EOS)
 vae.train()
 eng = engine_mod.TrainEngine(vae, bench.CFG2, 128, bench.SEQ_T, total_steps=bench.TOTAL_STEPS, use_graph=False)
 rng = np.random.default_rng(1000)
-X, L, Y = bench.synth_batch(rng, 128)
+X, L, Y = bench.synth_batch(rng, 128, uniform_lengths=uniform_lengths)
 batch = (torch.from_numpy(X).to(dev), torch.from_numpy(L).to(dev), torch.from_numpy(Y).to(dev))
 for _ in range(3):
     eng.step_resident(*batch)
@@ -39,6 +41,6 @@ for e in prof.events():
         a[0] += 1
         a[1] += e.device_time
 tot = sum(v[1] for v in agg.values())
-print(f"# {steps} eager steps, {tot / steps:.1f} us kernel time per step")
+print(f"# {workload}: {steps} eager steps, {tot / steps:.1f} us kernel time per step")
 for k, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:28]:
     print(f"{t / steps:10.1f} us {100 * t / tot:5.1f}% x{c // steps:4d}  {k}")

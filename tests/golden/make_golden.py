@@ -262,8 +262,83 @@ def cyclic_table():
     print(f"wrote {path}")
 
 
+def sampler_case():
+    """Batches of the reference's RatioSampler (vae/data_utils.py:13-87) on a seeded two-source dataset, for three
+    (batch size, ratios) settings -> ratio_sampler.npz (index lists are ragged: stored flat with offsets)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("ref_data_utils", os.path.join(os.environ.get("DVAE_REFERENCE_ROOT", "/root/reference"),
+                                                                                 "vae", "data_utils.py"))
+    du = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(du)
+    rnd = random.Random(0)
+    sources = [rnd.choice(["sfu", "amazon", "amazon", "amazon", "amazon"]) for _ in range(203)]
+    data = [{"source_dataset": s_} for s_ in sources]
+    out = {"sources": np.array(sources)}
+    settings = [(16, None), (12, {"sfu": 0.5, "amazon": 0.5}), (10, {"amazon": 0.7, "sfu": 0.3})]
+    for i, (bs, ratios) in enumerate(settings):
+        torch.manual_seed(3)
+        sampler = du.RatioSampler(data, "source_dataset", ratios, bs)
+        batches = [b.numpy() for b in sampler]
+        out[f"case{i}.batch_size"] = np.int64(bs)
+        out[f"case{i}.ratio_keys"] = np.array(list(ratios) if ratios else [], dtype=str)
+        out[f"case{i}.ratio_vals"] = np.array(list(ratios.values()) if ratios else [], dtype=np.float64)
+        out[f"case{i}.flat"] = np.concatenate(batches)
+        out[f"case{i}.sizes"] = np.array([len(b) for b in batches], dtype=np.int64)
+        out[f"case{i}.len"] = np.int64(len(sampler))
+    path = os.path.join(HERE, "ratio_sampler.npz")
+    np.savez_compressed(path, **out)
+    print(f"wrote {path}")
+
+
+def formats_case():
+    """On-disk formats: the metadata logs `run.log_params` writes (run.py:166-194) for a seeded dict, as file-name ->
+    content strings, and the key structure of the reference's checkpoint (run.py:624-630) -> formats.npz."""
+    import importlib
+    import tempfile
+    sys.path.insert(0, os.environ.get("DVAE_REFERENCE_ROOT", "/root/reference"))
+    ref_run = importlib.import_module("run")
+    rng = np.random.default_rng(5)
+    params = {"polarity": {"z": rng.standard_normal((7, 1)).tolist(), "mu": rng.standard_normal((7, 1)).tolist()},
+              "content": {"z": (rng.standard_normal((7, 3)) * 10).tolist(), "logvar": rng.standard_normal((7, 3)).tolist()}}
+    ids = [f"ex{i}" for i in range(7)]
+    out = {"ids": np.array(ids)}
+    for ln, d_ in params.items():
+        for pn, v in d_.items():
+            out[f"in.{ln}.{pn}"] = np.array(v)
+    with tempfile.TemporaryDirectory() as td:
+        ref_run.log_params(params, ids, td, "train", 4)
+        files = {}
+        for root, _, fs in os.walk(td):
+            for f in fs:
+                files[os.path.relpath(os.path.join(root, f), td)] = open(os.path.join(root, f), newline="").read()
+    out["file_names"] = np.array(sorted(files))
+    out["file_contents"] = np.array([files[k] for k in sorted(files)])
+    # checkpoint structure: one Adam step on a tiny reference model
+    torch.manual_seed(10)
+    p = make_params()
+    vae = ref_model.build_vae(p, 23, None, {"polarity": 1}, torch.device("cpu"), SOS, EOS)
+    opt = torch.optim.Adam(vae.trainable_parameters(), lr=p["learn_rate"])
+    sum(q.sum() for q in vae.trainable_parameters()).backward()
+    opt.step()
+    sd = opt.state_dict()
+    out["opt.param_group_keys"] = np.array(sorted(sd["param_groups"][0].keys()))
+    out["opt.state_keys"] = np.array(sorted(sd["state"][0].keys()))
+    out["opt.n_params"] = np.int64(len(sd["param_groups"][0]["params"]))
+    out["opt.trainable_names"] = np.array([n for n, q in vae.named_parameters()
+                                           if q.requires_grad and not n.startswith("adversaries")])
+    path = os.path.join(HERE, "formats.npz")
+    np.savez_compressed(path, **out)
+    print(f"wrote {path}")
+
+
 if __name__ == "__main__":
     torch.set_num_threads(1)
+    if "--sampler" in sys.argv:
+        sampler_case()
+        sys.exit(0)
+    if "--formats" in sys.argv:
+        formats_case()
+        sys.exit(0)
     if "--bow" in sys.argv:             # only the BOWEncoder case (vae/model.py:13-49)
         run_case("tiny_bow", make_params(bow_encoder=True, embedding_dim=10, hidden_dim=8,
                                          latent_dims={"total": 5, "polarity": 1}),

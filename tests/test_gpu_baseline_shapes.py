@@ -1,0 +1,237 @@
+"""Model-level parity at the EXACT shapes of BASELINE.json's configs (VERDICT r1 "next 1a"):
+
+  cfg 2  sfu_amazon_100k: B 128, T 22, V 10 000, E = H = 256, 2-layer bi-LSTM encoder, Z 64, dropout 0.5 (Philox masks
+         replayed into the oracle), through BOTH host paths -- the drop-in module (every gradient, arg-max) and the
+         graph-captured TrainEngine that bench.py times (loss + Adam update; this is the path that runs the two-row-group
+         lstm_tc kernels, the hoisted decoder work and the pre-split vocabulary kernels);
+  cfg 1  config_example: uni-directional encoder, B 64, T 30, V 10 000, Z 32 (polarity 1 + content 31), dropout 0.5;
+  cfg 4  scaled decoder slice: H 1024, V 50 000 (small B / T so the float64 oracle stays cheap), then T 64 forward-only
+         at B 16 for the long recurrence;
+  cfg 5  inference batch 1024: eval forward vs the oracle (loss, arg-max).
+
+Gates (BASELINE.json north_star): forward loss <= 1e-5 relative, per-latent KL and gradients <= 1e-3 relative,
+token-level reconstruction arg-max identical (positions whose top-two float64 logits are closer than 1e-5 are skipped
+and must be rare)."""
+import importlib
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402   (synthetic workload generator: the tests use the bench's own batches)
+from oracle import dvae_oracle as O  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+LABELS2 = {"uncertainty": 1, "polarity": 1}
+
+
+@pytest.fixture(scope="module")
+def dvae():
+    import __graft_entry__ as ge
+    return ge.build()
+
+
+def _rel(a, b):
+    a = a.detach().cpu().numpy().astype(np.float64) if torch.is_tensor(a) else np.asarray(a, np.float64)
+    b = np.asarray(b, np.float64)
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-30)
+
+
+def _cfg(**over):
+    c = dict(bench.CFG2)
+    c.update(over)
+    return c
+
+
+def _masks(dvae, plan, T, B, E, Henc_out, Hd, p_enc, p_dec):
+    """The dropout masks the kernels used, regenerated through the same C-ABI call (same seed, salts of plan.py)."""
+    L_ = dvae._lib
+    lib = L_.load()
+
+    def mask(rows, width, salt, p):
+        ones = torch.ones(rows, width, device="cuda")
+        y = torch.zeros_like(ones)
+        L_.check(lib.dvae_dropout(L_.ptr(ones), width, rows, width, p, L_.ptr(plan.seed_dev), salt, L_.ptr(y), width, 0,
+                                  L_.stream_ptr()), "dropout")
+        return y.cpu().numpy().astype(np.float64)
+
+    enc = [mask(T * B, E, 1, p_enc).reshape(T, B, E), mask(T * B, Henc_out, 16 + 1, p_enc).reshape(T, B, Henc_out)] if p_enc > 0 else None
+    dec = [mask((T - 1) * B, E, 3, p_dec).reshape(T - 1, B, E), mask((T - 1) * B, Hd, 32 + 1, p_dec).reshape(T - 1, B, Hd)] if p_dec > 0 else None
+    return enc, dec
+
+
+def _oracle(vae, X, lengths, Y, eps, klw, enc_masks=None, dec_masks=None, backward=True):
+    sd = O.cast_state_dict({k: v.detach().cpu().numpy() for k, v in vae.state_dict().items()})
+    spec = O.ModelSpec(sd, list(vae.context2params.keys()), vae.sos_token_idx, vae.eos_token_idx)
+    eps_d, off = {}, 0
+    eps = eps.detach().cpu().numpy() if torch.is_tensor(eps) else eps
+    for n, zs in zip(spec.space_names, spec.space_dims):
+        eps_d[n] = eps[:, off:off + zs]
+        off += zs
+    fw = O.model_forward(sd, spec, np.asarray(X), np.asarray(lengths), eps_d, labels={k: np.asarray(v) for k, v in Y.items()},
+                         kl_weights=klw, enc_masks=enc_masks, dec_masks=dec_masks)
+    return sd, fw, (O.model_backward(sd, spec, fw) if backward else None)
+
+
+def _check_argmax(am, fw, lengths, T):
+    lg = fw["decoder_logits"]
+    srt = np.sort(lg, axis=-1)
+    clear = (srt[..., -1] - srt[..., -2]) > 1e-5
+    live = np.arange(T)[None, :] < np.asarray(lengths)[:, None]
+    sel = live & clear
+    assert clear[live].mean() > 0.999
+    assert np.array_equal(am[sel], lg.argmax(-1)[sel])
+
+
+def _dropin_case(dvae, cfg, V, label_dims, B, T, uniform_lengths, seed):
+    dev = torch.device("cuda")
+    dvae.set_seed(10)
+    vae = dvae.build_vae(cfg, V, None, label_dims, dev, bench.SOS, bench.EOS)
+    vae.train()
+    rng = np.random.default_rng(seed)
+    X, lengths, Yr = bench.synth_batch(rng, B, T=T, V=V, uniform_lengths=uniform_lengths)
+    Y = {n: torch.from_numpy(Yr[j]).reshape(-1, 1) for j, n in enumerate(label_dims)}
+    Z = cfg["latent_dims"]["total"]
+    eps = torch.from_numpy(rng.standard_normal((B, Z)).astype(np.float32))
+    klw = {"default": 0.37, "polarity": 0.005, "uncertainty": 0.005}
+    Xd, Ld = torch.from_numpy(X).to(dev), torch.from_numpy(lengths).to(dev)
+    out = vae(Xd, Ld, teacher_forcing_prob=1.0, eps=eps.to(dev))
+    total, L = dvae.losses.compute_all_losses(vae, out, Xd, Y, Ld, klw)
+    total.backward()
+    plan = vae._plans[(B, T)][0]
+    d = plan.d
+    enc_m, dec_m = _masks(dvae, plan, T, B, d.E, d.D * d.H, d.Hd, d.p_enc, d.p_dec)
+    _, fw, grads = _oracle(vae, X, lengths, {k: v.numpy() for k, v in Y.items()}, eps, klw, enc_m, dec_m)
+    assert abs(total.item() - fw["total_loss"]) <= 1e-5 * abs(fw["total_loss"]), (total.item(), fw["total_loss"])
+    for n in fw["kls"]:
+        assert abs(L["idv_kls"][n] - fw["kls"][n]) <= 1e-3 * abs(fw["kls"][n])
+    _check_argmax(out["decoder_logits"].argmax().cpu().numpy(), fw, lengths, T)
+    worst = 0.0
+    for k, prm in vae.named_parameters():
+        e = _rel(prm.grad, grads[k])
+        worst = max(worst, e)
+        assert e < 1e-3, (k, e)
+    print(f"loss rel err {abs(total.item() - fw['total_loss']) / abs(fw['total_loss']):.2e}, worst grad rel err {worst:.2e}")
+
+
+def test_cfg2_dropin_train_step_exact_shape_with_dropout(dvae):
+    _dropin_case(dvae, _cfg(), bench.VOCAB, LABELS2, 128, 22, None, seed=2)
+
+
+def test_cfg1_dropin_train_step_exact_shape_with_dropout(dvae):
+    cfg = _cfg(bidirectional_encoder=False, latent_dims={"total": 32, "polarity": 1}, learn_rate=5e-3, batch_size=64)
+    _dropin_case(dvae, cfg, 10000, {"polarity": 1}, 64, 30, (5, 30), seed=1)
+
+
+def test_cfg4_slice_h1024_v50k_train_step(dvae):
+    cfg = _cfg(hidden_dim=1024, encoder_dropout=0.5, decoder_dropout=0.5)
+    _dropin_case(dvae, cfg, 50000, LABELS2, 16, 7, (3, 7), seed=4)
+
+
+def test_cfg4_long_recurrence_forward_t64(dvae):
+    """H = 1024 over T = 64 steps (cfg 4's sequence length) at B = 16, eval mode: forward loss and arg-max vs the oracle."""
+    dev = torch.device("cuda")
+    cfg = _cfg(hidden_dim=1024)
+    dvae.set_seed(10)
+    V, B, T = 50000, 16, 64
+    vae = dvae.build_vae(cfg, V, None, LABELS2, dev, bench.SOS, bench.EOS)
+    vae.eval()
+    rng = np.random.default_rng(8)
+    X, lengths, Yr = bench.synth_batch(rng, B, T=T, V=V, uniform_lengths=(16, 64))
+    Y = {n: torch.from_numpy(Yr[j]).reshape(-1, 1) for j, n in enumerate(LABELS2)}
+    eps = torch.from_numpy(rng.standard_normal((B, 64)).astype(np.float32))
+    klw = {"default": 1.0, "polarity": 0.005, "uncertainty": 0.005}
+    with torch.no_grad():
+        out = vae(torch.from_numpy(X).to(dev), torch.from_numpy(lengths).to(dev), teacher_forcing_prob=1.0, eps=eps.to(dev))
+        total, _ = dvae.losses.compute_all_losses(vae, out, torch.from_numpy(X).to(dev), Y, torch.from_numpy(lengths).to(dev), klw)
+    _, fw, _ = _oracle(vae, X, lengths, {k: v.numpy() for k, v in Y.items()}, eps, klw, backward=False)
+    assert abs(total.item() - fw["total_loss"]) <= 1e-5 * abs(fw["total_loss"])
+    _check_argmax(out["decoder_logits"].argmax().cpu().numpy(), fw, lengths, T)
+
+
+def test_cfg5_inference_batch_1024_forward(dvae):
+    dev = torch.device("cuda")
+    dvae.set_seed(10)
+    B, T, V = 1024, 22, bench.VOCAB
+    vae = dvae.build_vae(_cfg(), V, None, LABELS2, dev, bench.SOS, bench.EOS)
+    vae.eval()
+    rng = np.random.default_rng(5)
+    X, lengths, Yr = bench.synth_batch(rng, B)
+    Y = {n: torch.from_numpy(Yr[j]).reshape(-1, 1) for j, n in enumerate(LABELS2)}
+    eps = torch.from_numpy(rng.standard_normal((B, 64)).astype(np.float32))
+    klw = {"default": 1.0, "polarity": 0.005, "uncertainty": 0.005}
+    with torch.no_grad():
+        out = vae(torch.from_numpy(X).to(dev), torch.from_numpy(lengths).to(dev), teacher_forcing_prob=1.0, eps=eps.to(dev))
+        total, _ = dvae.losses.compute_all_losses(vae, out, torch.from_numpy(X).to(dev), Y, torch.from_numpy(lengths).to(dev), klw)
+    # every loss term is a batch mean and rows are independent: the float64 oracle runs on four chunks of 256 rows
+    am = out["decoder_logits"].argmax().cpu().numpy()
+    want_total = 0.0
+    for c in range(4):
+        sl = slice(256 * c, 256 * (c + 1))
+        _, fw, _ = _oracle(vae, X[sl], lengths[sl], {k: v.numpy()[sl] for k, v in Y.items()}, eps[sl], klw, backward=False)
+        want_total += fw["total_loss"] / 4
+        _check_argmax(am[sl], fw, lengths[sl], T)
+        for n in LABELS2:
+            assert _rel(out["dsc_logits"][n][sl], fw["dsc_logits"][n]) < 1e-4
+    assert abs(total.item() - want_total) <= 1e-5 * abs(want_total)
+
+
+@pytest.mark.parametrize("workload,B", [("cfg2", 128), ("cfg3", 64)])
+def test_train_engine_exact_bench_workload_matches_oracle(dvae, workload, B):
+    """The engine bench.py times (CUDA graph, hoisted decoder work, dropout 0.5, cyclic KL) at the bench's own shapes:
+    cfg 2 = per-GPU batch 128, cfg 3 = the per-GPU shard (64) of the 8 x 64 data-parallel run."""
+    engine_mod = importlib.import_module("disentanglement-vae_b200.engine")
+    dev = torch.device("cuda")
+    cfg, V, T = _cfg(), bench.VOCAB, bench.SEQ_T
+    dvae.set_seed(10)
+    vae = dvae.build_vae(cfg, V, None, LABELS2, dev, bench.SOS, bench.EOS)
+    vae.train()
+    eng = engine_mod.TrainEngine(vae, cfg, B, T, total_steps=bench.TOTAL_STEPS, use_graph=True, seed=10)
+    eng.step_idx = 1234                      # a non-trivial point of the cyclic schedule
+    rng = np.random.default_rng(1000)
+    lr = cfg["learn_rate"]
+    for step in range(2):
+        X, lengths, Yr = bench.synth_batch(rng, B)
+        Y = {n: torch.from_numpy(Yr[j]).reshape(-1, 1) for j, n in enumerate(LABELS2)}
+        sd0 = {k: t.detach().cpu().numpy().astype(np.float64) for k, t in vae.state_dict().items()}
+        Mv, Vv = vae.grad_views(eng.m), vae.grad_views(eng.v)
+        m = {k: Mv[k].detach().cpu().numpy().astype(np.float64) for k in sd0}
+        v2 = {k: Vv[k].detach().cpu().numpy().astype(np.float64) for k in sd0}
+        got = eng.step_host(torch.from_numpy(X), torch.from_numpy(lengths), Y)
+        d = eng.plan.d
+        enc_m, dec_m = _masks(dvae, eng.plan, T, B, d.E, d.D * d.H, d.Hd, d.p_enc, d.p_dec)
+        klw = {"default": O.cyclic_kl_weight(1234 + step, bench.TOTAL_STEPS), "polarity": 0.005, "uncertainty": 0.005}
+        # the oracle starts from the weights the step started from
+        spec = O.ModelSpec(sd0, list(vae.context2params.keys()), bench.SOS, bench.EOS)
+        eps = eng.plan.eps.detach().cpu().numpy()
+        eps_d, off = {}, 0
+        for n, zs in zip(spec.space_names, spec.space_dims):
+            eps_d[n] = eps[:, off:off + zs]
+            off += zs
+        fw = O.model_forward(sd0, spec, X, lengths, eps_d, labels={k: v.numpy() for k, v in Y.items()}, kl_weights=klw,
+                             enc_masks=enc_m, dec_masks=dec_m)
+        grads = O.model_backward(sd0, spec, fw)
+        assert abs(got["total_loss"] - fw["total_loss"]) <= 1e-5 * abs(fw["total_loss"]), (step, got["total_loss"], fw["total_loss"])
+        for n in fw["kls"]:
+            assert abs(got["idv_kls"][n] - fw["kls"][n]) <= 1e-3 * abs(fw["kls"][n])
+        am = eng.plan.argmax[:eng.plan.N].view(T - 1, B).t().cpu().numpy()
+        lg = fw["decoder_logits"][:, 1:]
+        srt = np.sort(lg, axis=-1)
+        sel = ((srt[..., -1] - srt[..., -2]) > 1e-5) & (np.arange(1, T)[None, :] < lengths[:, None])
+        assert np.array_equal(am[sel], lg.argmax(-1)[sel])
+        after = {k: a.copy() for k, a in sd0.items()}
+        O.clip_and_adam(after, grads, m, v2, eng.adam_step, lr)
+        now = {k: t.detach().cpu().numpy().astype(np.float64) for k, t in vae.state_dict().items()}
+        worst = 0.0
+        for k in sd0:
+            sig = np.abs(grads[k]) > 1e-4 * np.abs(grads[k]).max()
+            if sig.any():
+                want, have = after[k] - sd0[k], now[k] - sd0[k]
+                err = np.abs(want - have)[sig].max() / max(np.abs(want[sig]).max(), 1e-30)
+                worst = max(worst, err)
+                assert err < 2e-3, (step, k, err)
+        print(f"{workload} step {step}: loss rel err {abs(got['total_loss'] - fw['total_loss']) / abs(fw['total_loss']):.2e}, worst Adam-update rel err {worst:.2e}")
