@@ -145,6 +145,20 @@ class ClockSampler:
                     pass
             time.sleep(self.period)
 
+    def sample_now(self):
+        """One sample from the CALLING thread (the launch loop holds the GIL most of the time, so the background thread
+        alone can miss a region of a few tens of milliseconds)."""
+        if self.h is None:
+            return
+        nv = self.nv
+        try:
+            mhz = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+            rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+            self.samples.append((float(mhz), int(rs), nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0))
+        except Exception:
+            pass
+
     def begin(self):
         self.live = True
 
@@ -456,7 +470,7 @@ def dropin_e2e(dvae, vae_cfg, dev, hpool, tokens, steps):
         torch.nn.utils.clip_grad_norm_(vae.trainable_parameters(), 5.0)
         opt.step()
         opt.zero_grad()
-        return float(total)          # D2H read of the loss, as the reference's loss logger does
+        return float(total.detach())          # D2H read of the loss, as the reference's loss logger does
 
     for i in range(3):
         one(i, *hpool[i % len(hpool)])
@@ -597,6 +611,8 @@ def main():
         out = eng.step_resident(*dpool[j])
         ev[i][1].record()
         tok_sum += tokens[j]
+        if clocks and i % 4 == 3:
+            clocks.sample_now()                          # GPU is under load here: the host runs ahead of the queued steps
     barrier()
     clk = clocks.stop() if clocks else None
     dev_ms = sum(a.elapsed_time(b) for a, b in ev)

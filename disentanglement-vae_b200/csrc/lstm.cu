@@ -41,6 +41,17 @@ __global__ void transpose_kernel(const float* __restrict__ in, float* __restrict
     if (c0 + j < C && r < R) out[(int64_t)(c0 + j) * R + r] = tile[threadIdx.x][j];
 }
 
+int transpose_launch(const float* in, float* out, int R, int C, cudaStream_t st) {
+  transpose_kernel<<<dim3(ceil_div(C, 32), ceil_div(R, 32)), dim3(32, 8), 0, st>>>(in, out, R, C);
+  DVAE_LAUNCH_CHECK();
+  return DVAE_OK;
+}
+int copy_rows_launch(const float* src, int64_t lds, float* dst, int64_t ldd, int B, int H, cudaStream_t st) {
+  copy_state_kernel<<<ceil_div((int64_t)B * H, 256), 256, 0, st>>>(src, lds, 0, dst, ldd, 0, 1, B, H);
+  DVAE_LAUNCH_CHECK();
+  return DVAE_OK;
+}
+
 // ---- per-step mini GEMM -----------------------------------------------------------------------
 // acc[r][c] = sum_k A[row0 + rb*2 + r][k] * W[wrow(c)][k]   (both K-contiguous)
 // 256 threads: rb = tid / 16 (16 row pairs -> 32 rows), tu = tid % 16; the caller maps (tu, c) to a
@@ -243,6 +254,8 @@ static bool force_step_path() {
   return e && !strcmp(e, "step");
 }
 static int64_t state_floats(int B, int H, int D) { return 4LL * D * B * H; }
+// state workspace (floats): [carried state 4*D*B*H][transposed W_hh 4*D*H*H][8 rotating max|dG| slot sets][operand planes]
+static int64_t planes_ws_offset(int B, int H, int D) { return state_floats(B, H, D) + 4LL * D * H * H + 8LL * amax_slot_entries(B, D); }
 
 // gates[d] [T*B, 4H] = x . W_ih[d]^T + b_ih[d] + b_hh[d]: the time-parallel half of the layer (one GEMM per direction)
 int lstm_input_proj_impl(const float* x, int64_t ldx, int T, int B, int I, int H, int D, const float* const* w_ih,
@@ -287,6 +300,10 @@ int lstm_seq_fwd_impl(const float* x, int64_t ldx, int T, int B, int I, int H, i
       if (const char* e = getenv("DVAE_LSTM_DBG")) a.dbg = reinterpret_cast<unsigned long long*>(strtoull(e, nullptr, 0));
       return persist_fwd(H, a, st);
     }
+    // hidden sizes beyond the cluster-resident kernels (512, 1024, ...): per-step tensor-core GEMMs over operand planes
+    if (!force_step_path() && planes_lstm_supported(B, H, D, ptrs, 11, lds, 5))
+      return planes_lstm_fwd(T, B, H, D, w_hh, h0, c0, ld0, dir0, lengths, hs, ldhs, hn, cn, ldn, dirn, gates, cs, ws,
+                             ws + planes_ws_offset(B, H, D), st);
   }
   float* hbuf[2] = {ws, ws + 2 * sf};
   float* cbuf[2] = {ws + sf, ws + 3 * sf};
@@ -356,6 +373,17 @@ int lstm_seq_bwd_impl(const float* x, int64_t ldx, int T, int B, int I, int H, i
       int rc = persist_bwd(H, a, st);
       if (rc) return rc;
       persisted = true;
+    } else {
+      const void* ptrs2[] = {w_hh[0], w_hh[D - 1], c0, gates, cs, d_hs, d_hn, d_cn, d_h0, d_c0, ws};
+      if (!force_step_path() && planes_lstm_supported(B, H, D, ptrs2, 11, lds, 7)) {
+        static thread_local unsigned slot2 = 0;      // rotating: deferred weight-gradient GEMMs of earlier layers may still read theirs
+        amax = reinterpret_cast<uint32_t*>(ws + state_floats(B, H, D) + 4LL * D * H * H) + amax_slot_entries(B, D) * (slot2++ & 7);
+        amax_n = D;
+        int rc = planes_lstm_bwd(T, B, H, D, w_hh, c0, ld0, dir0, lengths, gates, cs, d_hs, lddhs, d_hn, d_cn, ldn, dirn, d_h0,
+                                 d_c0, ldd0, dird0, ws, ws + 4 * sf, ws + planes_ws_offset(B, H, D), amax, st);
+        if (rc) return rc;
+        persisted = true;
+      }
     }
   }
   float* carry[2] = {ws, ws + 2 * sf};
@@ -486,7 +514,8 @@ extern "C" int dvae_lstm_step(const float* x, int64_t ldx, int t, int T, int B, 
 }
 
 extern "C" int64_t dvae_lstm_state_ws_floats(int B, int H, int D) {
-  return dvae::state_floats(B, H, D) + 4LL * D * H * H + 8 * dvae::amax_slot_entries(B, D);   // + 8 rotating sets of per-CTA max |dG| slots
+  // + 8 rotating sets of per-CTA max |dG| slots + the operand planes of the large-H path (0 for H it does not take)
+  return dvae::planes_ws_offset(B, H, D) + dvae::planes_lstm_ws_floats(B, H, D);
 }
 
 extern "C" int dvae_lstm_seq_fwd(const float* x, int64_t ldx, int T, int B, int I, int H, int D,

@@ -43,4 +43,17 @@ int tc_lstm_bwd_ctas(int B, int D);          // grid size of that launch (= per-
 // entries reserved per max |dG| slot set: the largest grid the backward kernel can have for (B, D) (one row group per cluster)
 inline int amax_slot_entries(int B, int D) { const int n = 8 * ((B + 15) / 16) * D; return n < 128 ? 128 : n; }
 
+
+// Large-H path (lstm_planes.cu): per-step tensor-core GEMMs over fp16 operand planes + element-wise cell kernels, for hidden
+// sizes the cluster-resident kernels do not take (H >= 128, H % 32 == 0; e.g. 512, 1024).
+bool planes_lstm_supported(int B, int H, int D, const void* const* ptrs, int nptr, const int64_t* lds, int nld);
+int64_t planes_lstm_ws_floats(int B, int H, int D);
+int planes_lstm_fwd(int T, int B, int H, int D, const float* const* w_hh, const float* h0, const float* c0, int64_t ld0,
+                    int64_t dir0, const int64_t* lengths, float* hs, int64_t ldhs, float* hn, float* cn, int64_t ldn,
+                    int64_t dirn, float* gates, float* cs, float* ws, float* pws, cudaStream_t st);
+int planes_lstm_bwd(int T, int B, int H, int D, const float* const* w_hh, const float* c0, int64_t ld0, int64_t dir0,
+                    const int64_t* lengths, float* gates, const float* cs, const float* d_hs, int64_t lddhs, const float* d_hn,
+                    const float* d_cn, int64_t ldn, int64_t dirn, float* d_h0, float* d_c0, int64_t ldd0, int64_t dird0,
+                    float* ws, float* wt, float* pws, uint32_t* amax_slots, cudaStream_t st);
+
 }  // namespace dvae

@@ -25,6 +25,7 @@
 
 #include "tc_gemm.cuh"
 #include "tc_gemm16.cuh"
+#include "tc_planes.cuh"
 
 namespace dvae {
 namespace tc16 {
@@ -113,18 +114,6 @@ __device__ __forceinline__ float scale_from_amax(const uint32_t* amax_bits, int 
   int se = 267 - (int)(mx >> 23);
   se = se < 1 ? 1 : (se > 253 ? 253 : se);
   return __uint_as_float((unsigned)se << 23);
-}
-
-// (x0, x1) * s -> packed fp16 hi pair (returned) and lo pair; packed fp32 arithmetic (FMUL2 / FFMA2)
-__device__ __forceinline__ uint32_t pack_hi_lo(float x0, float x1, float s, uint32_t& lo, float ls = kLoScale) {
-  const float2 x = __fmul2_rn(make_float2(x0, x1), make_float2(s, s));
-  const __half2 h = __float22half2_rn(x);
-  const float2 hf = __half22float2(h);
-  // (x - hi) * ls = x * ls - hi * ls (ls a power of two: both products exact); ls = 2^11, or 1 for single-accumulator planes
-  const float2 r = __ffma2_rn(x, make_float2(ls, ls), __fmul2_rn(hf, make_float2(-ls, -ls)));
-  const __half2 l = __float22half2_rn(r);
-  lo = *reinterpret_cast<const uint32_t*>(&l);
-  return *reinterpret_cast<const uint32_t*>(&h);
 }
 
 // One landed k-block (128 rows x 32 k, fp32) of one operand -> 8 registers per converter thread (512 threads): thread
@@ -288,7 +277,7 @@ tc16_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
   }
-  const bool a_stat = p.presplit && nkb_total <= AS_MAX_KB && gridDim.z == 1;
+  const bool a_stat = p.presplit && !p.no_astat && nkb_total <= AS_MAX_KB && gridDim.z == 1;
   const int nstages = a_stat ? (p.mode == 1 ? AS_STAGES_NOSCRATCH : AS_STAGES) : STAGES;
   const uint32_t stage_bytes = a_stat ? AS_STAGE_BYTES : STAGE_BYTES;
   // (a padding CTA of an odd row-block count in CTA-pair mode re-reads the last real block: it only keeps the protocol going)
@@ -493,7 +482,9 @@ tc16_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int ew = wide_epi ? c_lo * 4 + quarter : ehalf * 4 + quarter;      // 0..15 | 0..7
     const int row = m0 + quarter * 32 + lane;      // output row owned by this thread (TMEM lane)
     const bool row_ok = row < p.M;
-    const float oscale = p.alpha * (p.alpha_dev ? *p.alpha_dev : 1.f) /
+    // c_row_scale: per-output-row factor (the A planes of that row were scaled by its inverse, e.g. per-row power-of-two
+    // scaling of LSTM gate gradients); applied here, before the transpose, where a thread still owns one row
+    const float oscale = p.alpha * (p.alpha_dev ? *p.alpha_dev : 1.f) * ((p.c_row_scale && row_ok) ? __ldg(p.c_row_scale + row) : 1.f) /
                          (scale_from_amax(p.a_amax, p.a_amax_n, p.a_scale) * scale_from_amax(p.b_amax, p.b_amax_n, p.b_scale));
     // per-row state of the fused vocabulary epilogues
     float rm = -INFINITY, rs = 0.f, rt = 0.f, rav = -INFINITY, row_lse = 0.f, row_nlse2 = 0.f, row_scale = 0.f;
@@ -878,8 +869,8 @@ bool presplit_enabled() {
 // planes of the single-accumulator (A-stationary) kernels: operand scale 2^8, lo unscaled; else scale as given, lo * 2^11
 bool single_acc_planes(int K) { return ceil_div(K, BK) <= AS_MAX_KB; }
 
-int split_planes(const float* X, int64_t ld, int R, int K, float scale, void* planes, cudaStream_t st) {
-  const bool single = single_acc_planes(K);
+int split_planes(const float* X, int64_t ld, int R, int K, float scale, void* planes, cudaStream_t st, bool force_dual) {
+  const bool single = !force_dual && single_acc_planes(K);
   const float lo_scale = single ? 1.f : kLoScale;
   if (single) scale *= kSingleScale;
   DVAE_REQUIRE(X && planes && R > 0 && K > 0, "tc16 split_planes: bad argument");
@@ -990,6 +981,51 @@ int linear(const float* A, int64_t lda, int trans_a, const float* B, int64_t ldb
   const int conc = hints.concurrency > 1 ? hints.concurrency : 1;
   if (splits == 1 && tiles * conc > 148 && ceil_div(N, BN) >= 2) {
     int tpc = ceil_div(tiles * conc, 148);
+    if (tpc < 2) tpc = 2;
+    if (tpc > ceil_div(N, BN)) tpc = ceil_div(N, BN);
+    p.tiles_per_cta = tpc;
+  }
+  return launch(p, dim3(ceil_div(M, BM), ceil_div(ceil_div(N, BN), p.tiles_per_cta), splits), st);
+}
+
+// C[M,N] = act(A . B^T + bias) + beta * C with BOTH operands given as tile-blocked fp16 planes (dual-accumulator convention,
+// see tc_planes.cuh): no tensor maps, no landing ring, no converter warps -- a k-block is two 16 KB bulk copies.  Used where
+// an operand is produced on the device directly in plane format (the recurrent state of the large-H LSTM path) and the other
+// is split once per call (its weights).  c_row_scale: optional per-row output factor (device, [M]).
+int linear_planes(const void* a_planes, const void* b_planes, float* C, int64_t ldc, int M, int N, int K, const float* bias,
+                  float beta, int act, float a_scale, float b_scale, const float* c_row_scale, bool c_zeroed, int max_splits,
+                  cudaStream_t st) {
+  DVAE_REQUIRE(a_planes && b_planes && C && M > 0 && N > 0 && K > 0, "tc16 linear_planes: bad argument");
+  Params p = {};
+  p.presplit = 1; p.no_astat = 1; p.a_planes = a_planes; p.b_planes = b_planes; p.a_rows = M; p.b_rows = N;
+  p.M = M; p.N = N; p.K = K; p.tiles_per_cta = 1; p.C = C; p.ldc = ldc; p.bias = bias; p.beta = beta; p.act = act; p.mode = 0;
+  apply_hints(p, GemmHints());
+  p.a_scale = a_scale; p.b_scale = b_scale; p.c_row_scale = c_row_scale;
+  const int tiles = ceil_div(M, BM) * ceil_div(N, BN), nkb = ceil_div(K, BK);
+  int splits = 1;
+  if (act == 0 && nkb >= 8) {      // same cost model as linear(), with the bulk-copy-fed k-block time
+    const float t_kb = 0.27f;
+    float best = 1e30f;
+    for (int s2 = 1; s2 <= max_splits && s2 <= nkb / 4; ++s2) {
+      const int kbs = ceil_div(nkb, s2), se = ceil_div(nkb, kbs);
+      if (se != s2) continue;
+      const int waves = ceil_div(tiles * se, 148);
+      const float t = waves * (kbs * t_kb + (se > 1 ? 5.f : 4.f)) + (se > 1 ? 1.5f : 0.f);
+      if (t < best * 0.95f) { best = t; splits = se; }
+    }
+  }
+  p.kb_per_split = ceil_div(nkb, splits);
+  splits = ceil_div(nkb, p.kb_per_split);
+  if (splits > 1 && beta != 1.f && !(beta == 0.f && c_zeroed)) {
+    if (beta == 0.f && ldc == N) {
+      DVAE_CUDA(cudaMemsetAsync(C, 0, sizeof(float) * (size_t)M * N, st));
+    } else {
+      tc16_scale_rows_kernel<<<ceil_div((int64_t)M * N, 256), 256, 0, st>>>(C, ldc, M, N, beta);
+      DVAE_LAUNCH_CHECK();
+    }
+  }
+  if (splits == 1 && tiles > 148 && ceil_div(N, BN) >= 2) {
+    int tpc = ceil_div(tiles, 148);
     if (tpc < 2) tpc = 2;
     if (tpc > ceil_div(N, BN)) tpc = ceil_div(N, BN);
     p.tiles_per_cta = tpc;

@@ -28,6 +28,8 @@ struct Params {
   float* zero_buf; int64_t zero_n4;      // optional: up to two buffers (float4 counts) the kernel clears on its way in
   float* zero_buf2; int64_t zero2_n4;    //           (outputs of later split-K GEMMs; see tc_gemm16.cu)
   int mcast;                             // A-stationary pre-split kernels launched as CTA pairs: B stages fetched half each, multicast
+  int no_astat;                          // pre-split operands in the dual-accumulator convention: never the A-stationary variant
+  const float* c_row_scale;              // optional per-output-row factor [M] (mode 0)
   int presplit; int b_row0;     // b_row0: first B row of this call inside the B planes (a vocabulary chunk)
   const void* a_planes; const void* b_planes; int a_rows, b_rows;      // tile-blocked fp16 planes (split_planes)
   const int* skip_flag;      // optional device flag: non-zero = the whole launch is a no-op (sampled decoding: a step whose
@@ -45,7 +47,10 @@ int linear(const float* A, int64_t lda, int trans_a, const float* B, int64_t ldb
 // plane_floats: size of BOTH planes in floats.  Operands that many tiles re-read (the decoder states and the vocabulary
 // matrix in the vocab-CE kernels) are split once; the GEMM then runs without landing ring and converter warps.
 int64_t plane_floats(int R, int K);
-int split_planes(const float* X, int64_t ld, int R, int K, float scale, void* planes, cudaStream_t st);
+int split_planes(const float* X, int64_t ld, int R, int K, float scale, void* planes, cudaStream_t st, bool force_dual = false);
+int linear_planes(const void* a_planes, const void* b_planes, float* C, int64_t ldc, int M, int N, int K, const float* bias,
+                  float beta, int act, float a_scale, float b_scale, const float* c_row_scale, bool c_zeroed, int max_splits,
+                  cudaStream_t st);
 bool presplit_enabled();      // DVAE_VOCAB_PRESPLIT=0 disables
 // h_planes / w_planes (both or neither): planes of h [N, H] and of the WHOLE w [V, H]
 int ce_partials(const float* h, int64_t ldh, int N, int B, int H, int V, const float* w, const float* bias,

@@ -78,13 +78,18 @@ def _oracle(vae, X, lengths, Y, eps, klw, enc_masks=None, dec_masks=None, backwa
 
 
 def _check_argmax(am, fw, lengths, T):
+    """Arg-max identical wherever the float64 top-two logits are more than 1e-5 apart (random-init logits over 10k-50k
+    words are close to uniform: about 1 position in 1000 is that close); on the near-ties the kernel's choice must still
+    be a maximiser within 1e-5."""
     lg = fw["decoder_logits"]
     srt = np.sort(lg, axis=-1)
     clear = (srt[..., -1] - srt[..., -2]) > 1e-5
     live = np.arange(T)[None, :] < np.asarray(lengths)[:, None]
     sel = live & clear
-    assert clear[live].mean() > 0.999
+    assert clear[live].mean() > 0.99
     assert np.array_equal(am[sel], lg.argmax(-1)[sel])
+    chosen = np.take_along_axis(lg, am[..., None].astype(np.int64), axis=-1)[..., 0]
+    assert (chosen[live] >= srt[..., -1][live] - 1e-5).all()
 
 
 def _dropin_case(dvae, cfg, V, label_dims, B, T, uniform_lengths, seed):
