@@ -30,6 +30,11 @@ SIGNATURES = {
     "dvae_last_error_string": (C.c_char_p, []),
     "dvae_version": (_i, []),
     "dvae_launch_count": (_l, []),
+    "dvae_weight_planes_floats": (_l, [_i, _i, _i]),
+    "dvae_weight_planes_register": (_i, [_p, _i, _i, _p, _p]),
+    "dvae_weight_planes_refresh": (_i, [_p]),
+    "dvae_weight_planes_enable": (_i, [_i]),
+    "dvae_weight_planes_clear": (_i, []),
     "dvae_defer_joins": (_i, [_i]),
     "dvae_join_side_streams": (_i, [_p]),
     "dvae_linear": (_i, [_p, _l, _i, _p, _l, _i, _p, _l, _i, _i, _i, _p, _p, _f, _i, _p]),

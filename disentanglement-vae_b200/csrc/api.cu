@@ -4,7 +4,11 @@
 
 #include <atomic>
 
+#include <mutex>
+#include <vector>
+
 #include "common.cuh"
+#include "tc_gemm16.cuh"
 
 namespace dvae {
 static thread_local char g_err[512] = "";
@@ -103,6 +107,78 @@ int join_side_streams(cudaStream_t main) {
 }
 void set_defer_joins(bool on) { g_defer_joins = on; }
 }  // namespace dvae
+
+// ---- weight-plane registry -------------------------------------------------------------------------
+// A caller that knows when its weights change (the training engine: once per optimizer step) registers them with
+// pre-allocated plane buffers, refreshes all planes with ONE launch, and enables the registry around its own launches.
+// While enabled, every tensor-core GEMM whose B operand lies inside a registered weight fetches it as pre-split fp16
+// (hi, lo) tiles by bulk copy instead of converting the fp32 matrix again in every CTA.  Disabled (the default), the
+// registry is never consulted, so stale entries cannot affect other callers.
+namespace dvae {
+namespace tc16 {
+namespace {
+std::mutex g_plane_mu;
+std::vector<PlaneTable::Entry> g_plane_reg;
+bool g_planes_enabled = false;
+}  // namespace
+
+bool find_weight_planes(const float* B, int64_t ldb, int trans_b, int N, int K, PlaneHit* hit) {
+  if (!g_planes_enabled) return false;
+  std::lock_guard<std::mutex> lk(g_plane_mu);
+  for (const PlaneTable::Entry& e : g_plane_reg) {
+    if (B < e.w || B >= e.w + (int64_t)e.R * e.C || ldb != e.C) continue;
+    const int64_t off = B - e.w;
+    const int r0 = (int)(off / e.C), c0 = (int)(off % e.C);
+    if (!trans_b) {          // B = W[r0 : r0 + N, c0 : c0 + K]: planes of W (rows = N axis, K along the columns)
+      if (!e.planes || r0 % 128 || c0 % 32 || r0 + N > e.R || c0 + K > e.C) return false;
+      hit->planes = e.planes; hit->tile0 = r0 / 128; hit->kb0 = c0 / 32; hit->kbtot = (e.C + 31) / 32;
+    } else {                 // B stored [K, N] = W[r0 : r0 + K, c0 : c0 + N]: planes of W^T (rows = columns of W, K along W's rows)
+      if (!e.planes_t || c0 % 128 || r0 % 32 || r0 + K > e.R || c0 + N > e.C) return false;
+      hit->planes = e.planes_t; hit->tile0 = c0 / 128; hit->kb0 = r0 / 32; hit->kbtot = (e.R + 31) / 32;
+    }
+    return true;
+  }
+  return false;
+}
+}  // namespace tc16
+}  // namespace dvae
+
+extern "C" int64_t dvae_weight_planes_floats(int R, int C, int transposed) {
+  return transposed ? dvae::tc16::plane_floats(C, R) : dvae::tc16::plane_floats(R, C);
+}
+extern "C" int dvae_weight_planes_register(const float* w, int R, int C, void* planes, void* planes_t) {
+  using namespace dvae::tc16;
+  DVAE_REQUIRE(w && R > 0 && C > 0 && (planes || planes_t), "dvae_weight_planes_register: bad argument");
+  DVAE_REQUIRE(((reinterpret_cast<uintptr_t>(planes) | reinterpret_cast<uintptr_t>(planes_t)) & 15) == 0,
+               "dvae_weight_planes_register: plane buffers must be 16-byte aligned");
+  std::lock_guard<std::mutex> lk(g_plane_mu);
+  for (PlaneTable::Entry& e : g_plane_reg)
+    if (e.w == w) { e.R = R; e.C = C; e.planes = planes; e.planes_t = planes_t; return DVAE_OK; }
+  DVAE_REQUIRE((int)g_plane_reg.size() < kMaxPlaneEntries, "dvae_weight_planes_register: more than %d weights", kMaxPlaneEntries);
+  g_plane_reg.push_back(PlaneTable::Entry{w, R, C, planes, planes_t});
+  return DVAE_OK;
+}
+extern "C" int dvae_weight_planes_clear(void) {
+  using namespace dvae::tc16;
+  std::lock_guard<std::mutex> lk(g_plane_mu);
+  g_plane_reg.clear();
+  g_planes_enabled = false;
+  return DVAE_OK;
+}
+extern "C" int dvae_weight_planes_enable(int on) {
+  dvae::tc16::g_planes_enabled = on != 0;
+  return DVAE_OK;
+}
+extern "C" int dvae_weight_planes_refresh(void* stream) {
+  using namespace dvae::tc16;
+  PlaneTable tab;
+  {
+    std::lock_guard<std::mutex> lk(g_plane_mu);
+    tab.n = (int)g_plane_reg.size();
+    for (int i = 0; i < tab.n; ++i) tab.e[i] = g_plane_reg[i];
+  }
+  return weight_planes_launch(tab, (cudaStream_t)stream);
+}
 
 extern "C" int dvae_defer_joins(int on) {
   dvae::set_defer_joins(on != 0);

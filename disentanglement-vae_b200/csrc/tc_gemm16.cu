@@ -209,6 +209,44 @@ __global__ void split_planes_kernel(const float* __restrict__ X, int64_t ld, int
   }
 }
 
+// Planes of up to kMaxPlaneEntries registered weights in ONE launch (blockIdx.y = 2 * entry + orientation):
+//   orientation 0: planes of W [R, C] (K = C), as split_planes_kernel (dual-accumulator convention);
+//   orientation 1: planes of W^T [C, R] (K = R): the B operand of the GEMMs that read W as [K, N] (dx = dG . W_ih, d_h = P . W_out).
+//     Consecutive threads take consecutive columns of W, so each of a thread's 8 loads is a coalesced row segment.
+__global__ void weight_planes_kernel(PlaneTable tab) {
+  const PlaneTable::Entry e = tab.e[blockIdx.y >> 1];
+  const int tr = blockIdx.y & 1;
+  uint8_t* out = reinterpret_cast<uint8_t*>(tr ? e.planes_t : e.planes);
+  if (!out) return;
+  const int R = tr ? e.C : e.R, K = tr ? e.R : e.C;           // rows / depth of the matrix being split
+  const int KB = (K + BK - 1) / BK, KC = KB * (BK / 8), RP = (R + BM - 1) / BM * BM;
+  const int64_t total = (int64_t)RP * KC;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int kc, r;
+    if (!tr) { kc = (int)(i % KC); r = (int)(i / KC); }
+    else { r = (int)(i % RP); kc = (int)(i / RP); }
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = kc * 8 + j;
+      v[j] = (r < R && k < K) ? __ldg(tr ? e.w + (int64_t)k * e.C + r : e.w + (int64_t)r * e.C + k) : 0.f;
+    }
+    uint4 h, l;
+    h.x = pack_hi_lo(v[0], v[1], 1.f, l.x); h.y = pack_hi_lo(v[2], v[3], 1.f, l.y);
+    h.z = pack_hi_lo(v[4], v[5], 1.f, l.z); h.w = pack_hi_lo(v[6], v[7], 1.f, l.w);
+    const int64_t off = ((int64_t)(r >> 7) * KB + (kc >> 2)) * (2 * PS_PLANE) + ((r & 127) >> 3) * PS_SBO + (kc & 3) * PS_LBO + (r & 7) * 16;
+    *reinterpret_cast<uint4*>(out + off) = h;
+    *reinterpret_cast<uint4*>(out + off + PS_PLANE) = l;
+  }
+}
+
+int weight_planes_launch(const PlaneTable& tab, cudaStream_t st) {
+  if (tab.n <= 0) return DVAE_OK;
+  weight_planes_kernel<<<dim3(96, 2 * tab.n), 256, 0, st>>>(tab);
+  DVAE_LAUNCH_CHECK();
+  return DVAE_OK;
+}
+
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 tc16_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, Params p) {
   extern __shared__ __align__(1024) uint8_t smem[];      // 1024-byte aligned (checked below): TMA 128-byte swizzle atoms
@@ -262,7 +300,8 @@ tc16_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       __trap();
     }
     for (int s = 0; s < MAX_STAGES; ++s) {
-      mbar_init(&full[s], p.presplit ? 1 : PROD_WARPS / 2);      // one converter group (8 warps) per k-block
+      // one converter group (8 warps) per k-block; hybrid: + the TMA warp's arrive.expect_tx for the bulk-copied B tile
+      mbar_init(&full[s], p.presplit ? 1 : PROD_WARPS / 2 + (p.b_presplit ? 1 : 0));
       mbar_init(&empty[s], p.mcast ? csize : 1);       // CTA pair: a B stage is free once BOTH CTAs' MMAs have read it
       mbar_init(&raw_full[s], 1);
     }
@@ -341,11 +380,18 @@ tc16_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
           uint8_t* dst = smem + stage * STAGE_BYTES;
-          mbar_expect_tx(&raw_full[stage], STAGE_BYTES);
+          mbar_expect_tx(&raw_full[stage], p.b_presplit ? RAW_TILE : STAGE_BYTES);
           const int k0 = (kb0 + kb) * BK;
           if (!p.a_mn) tma_load_2d(dst, &tmA, k0, m0, &raw_full[stage]);
           else tma_load_2d(dst, &tmA, m0, k0, &raw_full[stage]);
-          if (!p.b_mn) tma_load_2d(dst + RAW_TILE, &tmB, k0, nt * BN, &raw_full[stage]);
+          if (p.b_presplit) {
+            // B is a registered weight: its MMA-ready [hi | lo] tile lands straight in the operand slot and completes on the
+            // MMA's own barrier (one more arrival + 16 KB of transaction bytes); the converters only touch A
+            mbar_expect_tx(&full[stage], PS_TILE);
+            bulk_load(smem_u + stage * STAGE_BYTES + RAW_TILE,
+                      reinterpret_cast<const uint8_t*>(p.b_planes) + ((int64_t)(nt + b_tile0) * p.b_kbtot + p.b_kb0 + kb0 + kb) * PS_TILE,
+                      PS_TILE, &full[stage]);
+          } else if (!p.b_mn) tma_load_2d(dst + RAW_TILE, &tmB, k0, nt * BN, &raw_full[stage]);
           else tma_load_2d(dst + RAW_TILE, &tmB, nt * BN, k0, &raw_full[stage]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -370,14 +416,18 @@ tc16_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const uint32_t st = smem_u + stage * STAGE_BYTES;
       load_tile(st, p.a_mn, gtid, va0);
       load_tile(st, p.a_mn, gtid + 256, va1);
-      load_tile(st + RAW_TILE, p.b_mn, gtid, vb0);
-      load_tile(st + RAW_TILE, p.b_mn, gtid + 256, vb1);
+      if (!p.b_presplit) {
+        load_tile(st + RAW_TILE, p.b_mn, gtid, vb0);
+        load_tile(st + RAW_TILE, p.b_mn, gtid + 256, vb1);
+      }
       // every thread of the group has its fp32 values in registers before anyone overwrites the tiles with fp16 planes
       asm volatile("bar.sync %0, %1;" ::"r"(CONV_BARRIER + grp), "n"(PROD_WARPS * 16) : "memory");
       store_tile(st, gtid, sa, va0);
       store_tile(st, gtid + 256, sa, va1);
-      store_tile(st + PS_TILE, gtid, sb, vb0);
-      store_tile(st + PS_TILE, gtid + 256, sb, vb1);
+      if (!p.b_presplit) {
+        store_tile(st + PS_TILE, gtid, sb, vb0);
+        store_tile(st + PS_TILE, gtid + 256, sb, vb1);
+      }
       DVAE_TC16_MARK(ptid == 0 && it == 12, 4);
       fence_proxy_async();
       __syncwarp();
@@ -899,7 +949,8 @@ static int launch(const Params& p_in, dim3 grid, cudaStream_t st) {
     memset(&mb, 0, sizeof(mb));
   } else {
     if ((rc = make_map(&ma, p.A, p.lda, p.a_mn, p.M, p.K))) return rc;
-    if ((rc = make_map(&mb, p.Bm, p.ldb, p.b_mn, p.N, p.K))) return rc;
+    if (p.b_presplit) memset(&mb, 0, sizeof(mb));
+    else if ((rc = make_map(&mb, p.Bm, p.ldb, p.b_mn, p.N, p.K))) return rc;
   }
   // A-stationary pre-split kernels (vocabulary forward / softmax gradient), opt-in with DVAE_TC16_MCAST=1: CTA pairs along
   // the row blocks share their B tiles by multicast (an odd row-block count gets one padding CTA).  Measured at cfg 2:
@@ -947,6 +998,10 @@ int linear(const float* A, int64_t lda, int trans_a, const float* B, int64_t ldb
   p.M = M; p.N = N; p.K = K; p.a_mn = trans_a ? 1 : 0; p.b_mn = trans_b ? 1 : 0; p.tiles_per_cta = 1;
   p.C = C; p.ldc = ldc; p.bias = bias; p.bias2 = bias2; p.beta = beta; p.act = act; p.mode = 0;
   apply_hints(p, hints);
+  PlaneHit hit;
+  if (!hints.b_amax_bits && hints.b_scale == 1.f && find_weight_planes(B, ldb, trans_b, N, K, &hit)) {
+    p.b_presplit = 1; p.b_planes = hit.planes; p.b_row0 = hit.tile0 * BN; p.b_kb0 = hit.kb0; p.b_kbtot = hit.kbtot;
+  }
   // split-K (weight-gradient shapes: few output tiles, deep K): pick the split count with the smallest modelled time
   //   waves(tiles * s) * (k-blocks per split * t_kb + fixed per-CTA cost)   [us; measured orders of magnitude]
   // -- "split only when tiles <= 74" left the 80-tile dW_out GEMM of a 5120-column vocabulary chunk at one 84-k-block
@@ -954,7 +1009,7 @@ int linear(const float* A, int64_t lda, int trans_a, const float* B, int64_t ldb
   const int tiles = ceil_div(M, BM) * ceil_div(N, BN), nkb = ceil_div(K, BK);
   int splits = 1;
   if (act == 0 && nkb >= 16) {
-    const float t_kb = 0.5f + 0.2f * (p.a_mn + p.b_mn);
+    const float t_kb = p.b_presplit ? 0.33f + 0.15f * p.a_mn : 0.5f + 0.2f * (p.a_mn + p.b_mn);
     float best = 1e30f;
     for (int s2 = 1; s2 <= 16 && s2 <= nkb / 4; ++s2) {
       const int kbs = ceil_div(nkb, s2), se = ceil_div(nkb, kbs);

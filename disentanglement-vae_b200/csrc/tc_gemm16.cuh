@@ -28,6 +28,7 @@ struct Params {
   float* zero_buf; int64_t zero_n4;      // optional: up to two buffers (float4 counts) the kernel clears on its way in
   float* zero_buf2; int64_t zero2_n4;    //           (outputs of later split-K GEMMs; see tc_gemm16.cu)
   int mcast;                             // A-stationary pre-split kernels launched as CTA pairs: B stages fetched half each, multicast
+  int b_presplit; int b_kbtot; int b_kb0;   // HYBRID: A through the converter ring, B (a weight) from registered planes: k-blocks per row block / first k-block
   int no_astat;                          // pre-split operands in the dual-accumulator convention: never the A-stationary variant
   const float* c_row_scale;              // optional per-output-row factor [M] (mode 0)
   int presplit; int b_row0;     // b_row0: first B row of this call inside the B planes (a vocabulary chunk)
@@ -51,6 +52,17 @@ int split_planes(const float* X, int64_t ld, int R, int K, float scale, void* pl
 int linear_planes(const void* a_planes, const void* b_planes, float* C, int64_t ldc, int M, int N, int K, const float* bias,
                   float beta, int act, float a_scale, float b_scale, const float* c_row_scale, bool c_zeroed, int max_splits,
                   cudaStream_t st);
+// Weight-plane registry (api.cu): GEMMs whose B operand is a registered weight matrix (or a 128-row / 32-column aligned
+// block of it) fetch B as pre-split planes by bulk copy; only A goes through the converter warps.
+constexpr int kMaxPlaneEntries = 24;
+struct PlaneTable {
+  struct Entry { const float* w; int R, C; void* planes; void* planes_t; };
+  Entry e[kMaxPlaneEntries];
+  int n;
+};
+int weight_planes_launch(const PlaneTable& tab, cudaStream_t st);
+struct PlaneHit { const void* planes; int tile0, kb0, kbtot; };
+bool find_weight_planes(const float* B, int64_t ldb, int trans_b, int N, int K, PlaneHit* hit);
 bool presplit_enabled();      // DVAE_VOCAB_PRESPLIT=0 disables
 // h_planes / w_planes (both or neither): planes of h [N, H] and of the WHOLE w [V, H]
 int ce_partials(const float* h, int64_t ldh, int N, int B, int H, int V, const float* w, const float* bias,

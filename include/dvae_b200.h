@@ -95,6 +95,24 @@ int dvae_club_nll(const float* mu, const float* logvar, const float* y, int B, i
 int dvae_act_bwd(const float* y, const float* g, float* d, int64_t n, int act, void* stream);
 int dvae_relu(float* x, int64_t n, void* stream);
 
+/* Weight planes.  The tensor-core GEMMs multiply fp16 (hi, lo) operand planes; for an fp32 operand those planes are
+ * normally produced inside every CTA that reads it.  A caller that knows when a weight matrix changes (a training loop:
+ * once per optimizer step) can instead register it with caller-allocated plane buffers
+ *     planes   : dvae_weight_planes_floats(R, C, 0) floats -- W   [R, C] as a K-major B operand (x . W^T: the input projections)
+ *     planes_t : dvae_weight_planes_floats(R, C, 1) floats -- W^T [C, R] (g . W: the dx / d_h GEMMs); either may be NULL
+ * recompute the planes of ALL registered weights with one launch (dvae_weight_planes_refresh, e.g. first thing in a step)
+ * and switch the registry on around its own calls (dvae_weight_planes_enable; host-side, per process, off by default).
+ * While on, a GEMM inside any entry point whose B operand is a registered weight -- or a block of it starting on a
+ * multiple of 128 rows / 32 columns -- fetches B as ready-made tiles by bulk copy.  The planes MUST be current whenever
+ * such a GEMM runs; dvae_weight_planes_clear forgets every registration and switches the registry off.
+ * Replaces nothing in the reference: it is operand staging for vae/model.py:95,158 (nn.LSTM input projections) and
+ * their autograd transposes. */
+int64_t dvae_weight_planes_floats(int R, int C, int transposed);
+int dvae_weight_planes_register(const float* w, int R, int C, void* planes, void* planes_t);
+int dvae_weight_planes_refresh(void* stream);
+int dvae_weight_planes_enable(int on);
+int dvae_weight_planes_clear(void);
+
 /* Independent kernels inside one call (e.g. the weight-gradient GEMMs of an LSTM layer) run on library-owned side
  * streams and are joined back into `stream` before the call returns.  dvae_defer_joins(1) lets the backward entry
  * points (dvae_lstm_seq_bwd, dvae_latent_heads_bwd) return with that side work still in flight, so that it overlaps

@@ -35,12 +35,24 @@ with profile(activities=[ProfilerActivity.CUDA]) as prof:
         eng.step_resident(*batch)
     torch.cuda.synchronize()
 agg = collections.defaultdict(lambda: [0, 0.0])
-for e in prof.events():
+by_grid = os.environ.get("KT_BY_GRID", "0") == "1"      # KT_BY_GRID=1: split each kernel name by launch grid (chrome trace)
+if by_grid:
+    import json
+    path = os.path.join(ROOT, "gpurun_out", "kt_trace.json")
+    prof.export_chrome_trace(path)
+    for e in json.load(open(path))["traceEvents"]:
+        if e.get("cat") == "kernel":
+            nm = e["name"].split("(")[0].replace("void ", "").replace("dvae::", "").replace("(anonymous namespace)::", "")[:60]
+            a = agg[f"{nm} {e['args'].get('grid', '')}"]
+            a[0] += 1
+            a[1] += e["dur"]
+    os.remove(path)
+for e in ([] if by_grid else prof.events()):
     if e.device_type == torch.autograd.DeviceType.CUDA:
         a = agg[e.name[:100]]
         a[0] += 1
         a[1] += e.device_time
 tot = sum(v[1] for v in agg.values())
 print(f"# {workload}: {steps} eager steps, {tot / steps:.1f} us kernel time per step")
-for k, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:28]:
+for k, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:(60 if by_grid else 28)]:
     print(f"{t / steps:10.1f} us {100 * t / tot:5.1f}% x{c // steps:4d}  {k}")
