@@ -653,6 +653,8 @@ def main():
     d = pl.d
     N = pl.N
     _L = importlib.import_module("disentanglement-vae_b200._lib")
+    planes_cm = eng.weight_planes()        # same GEMM operand staging as inside the engine's step
+    planes_cm.__enter__()
     pl.vocab_ce(P, pl.d_hs[-1], eng.inputs, eng.lengths)            # leaves the fp16 operand planes in the workspace
     call_ms = _timed(lambda: pl.vocab_ce(P, pl.d_hs[-1], eng.inputs, eng.lengths), flush)      # split + kernel + finalize + loss
     k_ms = _timed(lambda: _L.check(pl.lib.dvae_vocab_ce_partials(
@@ -679,6 +681,7 @@ def main():
             None, None, 0, 0, _L.ptr(pl.d_gates[0]), _L.ptr(pl.d_cs[0]), _L.ptr(pl.state_ws), 1, _L.stream_ptr()), "rec")
     rec_enc_ms = _timed(rec_only(True), flush) if not d.bow else None
     rec_dec_ms = _timed(rec_only(False), flush)
+    planes_cm.__exit__(None, None, None)
 
     trace = None
     if rank == 0 and world == 1 and not args.no_trace:

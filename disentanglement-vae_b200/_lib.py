@@ -33,6 +33,7 @@ SIGNATURES = {
     "dvae_weight_planes_floats": (_l, [_i, _i, _i]),
     "dvae_weight_planes_register": (_i, [_p, _i, _i, _p, _p]),
     "dvae_weight_planes_refresh": (_i, [_p]),
+    "dvae_weight_planes_refresh_ex": (_i, [_i, _i, _p]),
     "dvae_weight_planes_enable": (_i, [_i]),
     "dvae_weight_planes_clear": (_i, []),
     "dvae_defer_joins": (_i, [_i]),
@@ -50,6 +51,9 @@ SIGNATURES = {
     "dvae_lstm_step": (_i, [_p, _l, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _l, _p, _p, _p, _p, _p]),
     "dvae_vocab_sample_step": (_i, [_p, _l, _i, _i, _i, _p, _p, _p, _u32, _p, _l, _p, _p]),
     "dvae_vocab_sample_step_ex": (_i, [_p, _l, _i, _i, _i, _p, _p, _p, _u32, _p, _l, _p, _p, _p]),
+    "dvae_vocab_w_planes_floats": (_l, [_i, _i]),
+    "dvae_vocab_w_planes": (_i, [_p, _i, _i, _p, _p]),
+    "dvae_vocab_sample_step_planes": (_i, [_p, _l, _i, _i, _i, _p, _p, _p, _p, _u32, _p, _l, _p, _p, _p]),
     "dvae_recount_lengths": (_i, [_p, _l, _l, _i, _i, _l, _l, _l, _p, _p]),
     "dvae_lstm_state_ws_floats": (_l, [_i, _i, _i]),
     "dvae_lstm_seq_fwd": (_i, [_p, _l, _i, _i, _i, _i, _i, _pp, _pp, _pp, _pp, _p, _p, _l, _l, _p, _p, _l, _p, _p,
@@ -83,6 +87,7 @@ SIGNATURES = {
 }
 
 _lib = None
+planes_owner = None      # id() of the engine whose weights are in the library's weight-plane registry (engine.py)
 
 
 def load():

@@ -169,15 +169,25 @@ extern "C" int dvae_weight_planes_enable(int on) {
   dvae::tc16::g_planes_enabled = on != 0;
   return DVAE_OK;
 }
-extern "C" int dvae_weight_planes_refresh(void* stream) {
+extern "C" int dvae_weight_planes_refresh_ex(int first, int count, void* stream) {
   using namespace dvae::tc16;
   PlaneTable tab;
   {
     std::lock_guard<std::mutex> lk(g_plane_mu);
-    tab.n = (int)g_plane_reg.size();
-    for (int i = 0; i < tab.n; ++i) tab.e[i] = g_plane_reg[i];
+    const int n = (int)g_plane_reg.size();
+    DVAE_REQUIRE(first >= 0 && count >= 0 && first + count <= n, "dvae_weight_planes_refresh_ex: entries [%d, %d) of %d", first, first + count, n);
+    tab.n = count;
+    for (int i = 0; i < count; ++i) tab.e[i] = g_plane_reg[first + i];
   }
   return weight_planes_launch(tab, (cudaStream_t)stream);
+}
+extern "C" int dvae_weight_planes_refresh(void* stream) {
+  int n;
+  {
+    std::lock_guard<std::mutex> lk(dvae::tc16::g_plane_mu);
+    n = (int)dvae::tc16::g_plane_reg.size();
+  }
+  return dvae_weight_planes_refresh_ex(0, n, stream);
 }
 
 extern "C" int dvae_defer_joins(int on) {

@@ -75,6 +75,10 @@ struct GemmHints {
   int a_amax_n = 1, b_amax_n = 1;      // number of partial maxima behind each pointer (the kernels take their maximum)
   float a_scale = 1.f, b_scale = 1.f;
   bool a_wide = false, b_wide = false;
+  // B operand available as pre-split tile-blocked fp16 planes (tc_planes.cuh, dual-accumulator convention, scale 1): first
+  // 128-row block / first k-block of this GEMM inside the planes, and the planes' k-blocks per row block
+  const void* b_planes = nullptr;
+  int b_tile0 = 0, b_kb0 = 0, b_kbtot = 0;
   bool c_zeroed = false;               // with beta == 0: C already holds zeros (a split-K GEMM then skips its memset node)
   int concurrency = 1;                 // GEMMs of this size the caller runs at the same time (sizes the CTA count to share the SMs)
 };

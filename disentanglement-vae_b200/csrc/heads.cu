@@ -61,19 +61,23 @@ __device__ __forceinline__ int space_of(const HeadsMeta& m, int zi) {
   return s;
 }
 
+// ROWS batch rows per CTA: 2 at training batch sizes (more CTAs, shorter critical path); 4 for the large inference
+// batches, where the per-CTA pass over the full weight matrices, not the row count, sets the time (B = 1024: 512 CTAs x 768 KB
+// from L2 took 193 us)
+template <int ROWS>
 __global__ void __launch_bounds__(kHeadsThreads) heads_fwd_kernel(HeadsFwdArgs a, HeadsMeta m) {
   extern __shared__ __align__(16) float sm[];
   const int C = a.C, Z = m.Z, S = m.S, OD = m.OD, B = a.B;
-  float* ctx_s = sm;                         // [kRows][C]
-  float* par_s = ctx_s + kRows * C;          // [kRows][2Z]
-  float* z_s = par_s + kRows * 2 * Z;        // [kRows][Z]
-  float* klt_s = z_s + kRows * Z;            // [kRows][Z] KL terms
-  float* lg_s = klt_s + kRows * Z;           // [kRows][OD]
+  float* ctx_s = sm;                         // [ROWS][C]
+  float* par_s = ctx_s + ROWS * C;          // [ROWS][2Z]
+  float* z_s = par_s + ROWS * 2 * Z;        // [ROWS][Z]
+  float* klt_s = z_s + ROWS * Z;            // [ROWS][Z] KL terms
+  float* lg_s = klt_s + ROWS * Z;           // [ROWS][OD]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = kHeadsThreads / 32;
-  const int b0 = blockIdx.x * kRows;
+  const int b0 = blockIdx.x * ROWS;
   HEADS_MARK(0);
 
-  for (int i = tid; i < kRows * C; i += kHeadsThreads) {
+  for (int i = tid; i < ROWS * C; i += kHeadsThreads) {
     int r = i / C, k = i % C;
     ctx_s[i] = (b0 + r < B) ? a.ctx[(int64_t)(b0 + r) * C + k] : 0.f;
   }
@@ -84,7 +88,7 @@ __global__ void __launch_bounds__(kHeadsThreads) heads_fwd_kernel(HeadsFwdArgs a
   for (int j0 = warp * 4; j0 < 2 * Z; j0 += nwarp * 4) {
     const int nj = min(4, 2 * Z - j0);
     const float* w = a.w_c2p + (int64_t)j0 * C;
-    float acc[4][kRows] = {};
+    float acc[4][ROWS] = {};
     if ((C & 3) == 0 && (reinterpret_cast<uintptr_t>(a.w_c2p) & 15) == 0) {
       // 16-byte loads: 4 weight rows x 4 k per lane and iteration, two iterations in flight
 #pragma unroll 2
@@ -94,7 +98,7 @@ __global__ void __launch_bounds__(kHeadsThreads) heads_fwd_kernel(HeadsFwdArgs a
         for (int q = 0; q < 4; ++q)
           wv[q] = q < nj ? __ldg(reinterpret_cast<const float4*>(w + (int64_t)q * C + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-        for (int r = 0; r < kRows; ++r) {
+        for (int r = 0; r < ROWS; ++r) {
           const float4 c = *reinterpret_cast<const float4*>(ctx_s + r * C + k);
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
@@ -109,7 +113,7 @@ __global__ void __launch_bounds__(kHeadsThreads) heads_fwd_kernel(HeadsFwdArgs a
 #pragma unroll
         for (int q = 0; q < 4; ++q) wv[q] = q < nj ? w[(int64_t)q * C + k] : 0.f;
 #pragma unroll
-        for (int r = 0; r < kRows; ++r) {
+        for (int r = 0; r < ROWS; ++r) {
           const float c = ctx_s[r * C + k];
 #pragma unroll
           for (int q = 0; q < 4; ++q) acc[q][r] = fmaf(c, wv[q], acc[q][r]);
@@ -119,7 +123,7 @@ __global__ void __launch_bounds__(kHeadsThreads) heads_fwd_kernel(HeadsFwdArgs a
 #pragma unroll
     for (int q = 0; q < 4; ++q)
 #pragma unroll
-      for (int r = 0; r < kRows; ++r) {
+      for (int r = 0; r < ROWS; ++r) {
         float v = warp_sum(acc[q][r]);
         if (lane == 0 && q < nj) par_s[r * 2 * Z + j0 + q] = v + a.b_c2p[j0 + q];
       }
@@ -127,7 +131,7 @@ __global__ void __launch_bounds__(kHeadsThreads) heads_fwd_kernel(HeadsFwdArgs a
   __syncthreads();
   HEADS_MARK(2);
   // reparameterisation + KL terms
-  for (int i = tid; i < kRows * Z; i += kHeadsThreads) {
+  for (int i = tid; i < ROWS * Z; i += kHeadsThreads) {
     int r = i / Z, zi = i % Z, b = b0 + r;
     int s = space_of(m, zi), d = zi - m.zoff[s];
     float mu = par_s[r * 2 * Z + 2 * m.zoff[s] + d];
@@ -146,7 +150,7 @@ __global__ void __launch_bounds__(kHeadsThreads) heads_fwd_kernel(HeadsFwdArgs a
   }
   __syncthreads();
   // discriminator logits
-  for (int i = tid; i < kRows * OD; i += kHeadsThreads) {
+  for (int i = tid; i < ROWS * OD; i += kHeadsThreads) {
     int r = i / OD, od = i % OD, b = b0 + r;
     int s = 0;
     while (!(m.dout[s] > 0 && od >= m.doff[s] && od < m.doff[s] + m.dout[s])) ++s;
@@ -161,14 +165,14 @@ __global__ void __launch_bounds__(kHeadsThreads) heads_fwd_kernel(HeadsFwdArgs a
   // decoder initial state: hid = tanh(z . Wz^T + bz); one thread per output column, vectorised weight row
   for (int j = tid; j < a.H2L; j += kHeadsThreads) {
     const float* w = a.w_z2h + (int64_t)j * Z;
-    float acc[kRows];
+    float acc[ROWS];
 #pragma unroll
-    for (int r = 0; r < kRows; ++r) acc[r] = a.b_z2h[j];
+    for (int r = 0; r < ROWS; ++r) acc[r] = a.b_z2h[j];
     if ((Z & 3) == 0 && (reinterpret_cast<uintptr_t>(a.w_z2h) & 15) == 0) {
       for (int k = 0; k < Z; k += 4) {
         const float4 wv = *reinterpret_cast<const float4*>(w + k);
 #pragma unroll
-        for (int r = 0; r < kRows; ++r) {
+        for (int r = 0; r < ROWS; ++r) {
           const float* zr = z_s + r * Z + k;
           acc[r] = fmaf(zr[0], wv.x, acc[r]); acc[r] = fmaf(zr[1], wv.y, acc[r]);
           acc[r] = fmaf(zr[2], wv.z, acc[r]); acc[r] = fmaf(zr[3], wv.w, acc[r]);
@@ -178,11 +182,11 @@ __global__ void __launch_bounds__(kHeadsThreads) heads_fwd_kernel(HeadsFwdArgs a
       for (int k = 0; k < Z; ++k) {
         const float wv = w[k];
 #pragma unroll
-        for (int r = 0; r < kRows; ++r) acc[r] = fmaf(z_s[r * Z + k], wv, acc[r]);
+        for (int r = 0; r < ROWS; ++r) acc[r] = fmaf(z_s[r * Z + k], wv, acc[r]);
       }
     }
 #pragma unroll
-    for (int r = 0; r < kRows; ++r)
+    for (int r = 0; r < ROWS; ++r)
       if (b0 + r < B) a.hid[(int64_t)(b0 + r) * a.H2L + j] = tanhf(acc[r]);
   }
   __syncthreads();
@@ -191,7 +195,7 @@ __global__ void __launch_bounds__(kHeadsThreads) heads_fwd_kernel(HeadsFwdArgs a
   if (tid < S) {
     const int s = tid;
     float kl = 0.f, dl = 0.f, da = 0.f;
-    for (int r = 0; r < kRows; ++r) {
+    for (int r = 0; r < ROWS; ++r) {
       if (b0 + r >= B) break;
       for (int d = 0; d < m.zdim[s]; ++d) kl += klt_s[r * Z + m.zoff[s] + d];
       if (m.dout[s] > 0 && a.labels) {
@@ -232,7 +236,7 @@ __global__ void __launch_bounds__(kHeadsThreads) heads_fwd_kernel(HeadsFwdArgs a
   // all threads of the last CTA fetch the partials into shared memory in parallel; thread 0 then adds them in block
   // order from there (a single thread walking 3*S*grid dependent L2 loads was a serial tail of this kernel)
   const int n_part = (int)gridDim.x * 3 * S;
-  const bool staged = n_part <= kRows * C;          // ctx_s is free by now
+  const bool staged = n_part <= ROWS * C;          // ctx_s is free by now
   if (is_last && staged) {
     __threadfence();
     for (int i = tid; i < n_part; i += kHeadsThreads) ctx_s[i] = __ldcg(a.ws + i);
@@ -417,11 +421,20 @@ extern "C" int dvae_latent_heads_fwd(const float* ctx, int B, int C, int S, cons
   HeadsFwdArgs a{ctx, w_c2p, b_c2p, eps, w_dsc, b_dsc, labels, kl_w_dev, w_z2h, b_z2h,
                  z, mu, logvar, hid, dsc_logits, scalars, ws, B, C, H2L, nullptr};
   if (const char* e = getenv("DVAE_HEADS_DBG")) a.dbg = reinterpret_cast<unsigned long long*>(strtoull(e, nullptr, 0));
-  const int grid = ceil_div(B, kRows);
-  size_t smem = sizeof(float) * ((size_t)kRows * C + kRows * 4 * m.Z + kRows * (m.OD > 0 ? m.OD : 1) + 3 * S);
+  auto smem_for = [&](int rows) { return sizeof(float) * ((size_t)rows * C + rows * 4 * m.Z + rows * (m.OD > 0 ? m.OD : 1) + 3 * S); };
+  int rows = B > 256 ? 4 : kRows;      // 8 rows per CTA spills at 1024 threads (64 registers each)
+  while (rows > kRows && smem_for(rows) > 160 * 1024) rows /= 2;
+  const size_t smem = smem_for(rows);
   DVAE_REQUIRE(smem <= 200 * 1024, "dvae_latent_heads_fwd: context width %d too large for shared memory", C);
-  if (smem > 48 * 1024) DVAE_CUDA(cudaFuncSetAttribute(heads_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  heads_fwd_kernel<<<grid, kHeadsThreads, smem, st>>>(a, m);
+  const int grid = ceil_div(B, rows);
+#define DVAE_HEADS_LAUNCH(R)                                                                                                  \
+  do {                                                                                                                        \
+    if (smem > 48 * 1024) DVAE_CUDA(cudaFuncSetAttribute(heads_fwd_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    heads_fwd_kernel<R><<<grid, kHeadsThreads, smem, st>>>(a, m);                                                             \
+  } while (0)
+  if (rows == 4) DVAE_HEADS_LAUNCH(4);
+  else DVAE_HEADS_LAUNCH(2);
+#undef DVAE_HEADS_LAUNCH
   DVAE_LAUNCH_CHECK();
   return DVAE_OK;
 }

@@ -473,6 +473,27 @@ int lstm_seq_bwd_impl(const float* x, int64_t ldx, int T, int B, int I, int H, i
   return DVAE_OK;
 }
 
+// gates_t [B,4H] pre-activations -> post-activation gates; c = f * c_prev + i * g; h = o * tanh(c).  One thread = 4 units.
+__global__ void lstm_cell_step_kernel(float* __restrict__ gates_t, const float* __restrict__ c_prev, int64_t ldc, float* __restrict__ cs_t,
+                                      float* __restrict__ hs_t, int B, int H) {
+  const int HQ = H / 4, idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * HQ) return;
+  const int b = idx / HQ, u0 = (idx % HQ) * 4;
+  float* g = gates_t + (int64_t)b * 4 * H + u0;
+  float4 gi = *reinterpret_cast<float4*>(g), gf = *reinterpret_cast<float4*>(g + H), gg = *reinterpret_cast<float4*>(g + 2 * H),
+         go = *reinterpret_cast<float4*>(g + 3 * H);
+  float4 c = c_prev ? *reinterpret_cast<const float4*>(c_prev + (int64_t)b * ldc + u0) : make_float4(0.f, 0.f, 0.f, 0.f), h;
+#define DVAE_CELL(x)                                                                  \
+  gi.x = sigmoidf_(gi.x); gf.x = sigmoidf_(gf.x); gg.x = tanhf(gg.x); go.x = sigmoidf_(go.x); \
+  c.x = fmaf(gf.x, c.x, gi.x * gg.x); h.x = go.x * tanhf(c.x);
+  DVAE_CELL(x) DVAE_CELL(y) DVAE_CELL(z) DVAE_CELL(w)
+#undef DVAE_CELL
+  *reinterpret_cast<float4*>(g) = gi; *reinterpret_cast<float4*>(g + H) = gf; *reinterpret_cast<float4*>(g + 2 * H) = gg;
+  *reinterpret_cast<float4*>(g + 3 * H) = go;
+  *reinterpret_cast<float4*>(cs_t + (int64_t)b * H + u0) = c;
+  *reinterpret_cast<float4*>(hs_t + (int64_t)b * H + u0) = h;
+}
+
 // One time step of one (uni-directional) layer on the full-sequence buffers: used by sampled decoding, where step
 // t+1's input token is only known after step t's vocabulary sample (vae/model.py:457-472).
 int lstm_step_impl(const float* x, int64_t ldx, int t, int T, int B, int I, int H, const float* w_ih, const float* w_hh,
@@ -484,6 +505,26 @@ int lstm_step_impl(const float* x, int64_t ldx, int t, int T, int B, int I, int 
                        0.f, 0, st);
   if (rc) return rc;
   const int64_t sf = (int64_t)B * H;
+  // Large batches (inference at B = 1024): the recurrent product is a dense contraction too -- gates[t] += h_{t-1} . W_hh^T on
+  // the tensor cores (W_hh arrives as registered weight planes when the caller registered it), then an element-wise cell
+  // kernel; the SIMT step kernel below took 32 us per layer and step at B = 1024, H = 256
+  {
+    const void* ptrs[] = {x, w_hh, h0, c0, hs, gates, cs};
+    bool aligned = H % 4 == 0 && ld0 % 4 == 0;
+    for (const void* q : ptrs) aligned = aligned && ((reinterpret_cast<uintptr_t>(q) & 15) == 0);
+    const char* e = getenv("DVAE_LSTM_IMPL");
+    if (aligned && B >= 256 && H >= 64 && !force_simt_gemm() && !(e && !strcmp(e, "step"))) {
+      float* gates_t = gates + (int64_t)t * B * 4 * H;
+      const float* h_prev = t == 0 ? h0 : hs + (int64_t)(t - 1) * sf;
+      const float* c_prev = t == 0 ? c0 : cs + (int64_t)(t - 1) * sf;
+      if (h_prev && (rc = linear_impl(h_prev, t == 0 ? ld0 : H, 0, w_hh, H, 0, gates_t, 4 * H, B, 4 * H, H, nullptr, nullptr, 1.f, 0, st)))
+        return rc;
+      lstm_cell_step_kernel<<<ceil_div((int64_t)B * (H / 4), 256), 256, 0, st>>>(gates_t, c_prev, t == 0 ? ld0 : H, cs + (int64_t)t * sf,
+                                                                               hs + (int64_t)t * sf, B, H);
+      DVAE_LAUNCH_CHECK();
+      return DVAE_OK;
+    }
+  }
   const float *h_in, *c_in;
   if (t == 0) {
     const int nthr = 256, nblk = ceil_div(sf, nthr);

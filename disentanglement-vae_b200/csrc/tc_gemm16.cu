@@ -242,7 +242,11 @@ __global__ void weight_planes_kernel(PlaneTable tab) {
 
 int weight_planes_launch(const PlaneTable& tab, cudaStream_t st) {
   if (tab.n <= 0) return DVAE_OK;
-  weight_planes_kernel<<<dim3(96, 2 * tab.n), 256, 0, st>>>(tab);
+  int64_t most = 1;          // 8-element items of the largest matrix: sizes the x extent (smaller entries' extra blocks exit at once)
+  for (int i = 0; i < tab.n; ++i) most = max(most, (int64_t)tab.e[i].R * tab.e[i].C / 8);
+  int bx = ceil_div(most, 256 * 4);
+  bx = bx < 8 ? 8 : (bx > 4 * 148 ? 4 * 148 : bx);
+  weight_planes_kernel<<<dim3(bx, 2 * tab.n), 256, 0, st>>>(tab);
   DVAE_LAUNCH_CHECK();
   return DVAE_OK;
 }
@@ -999,7 +1003,9 @@ int linear(const float* A, int64_t lda, int trans_a, const float* B, int64_t ldb
   p.C = C; p.ldc = ldc; p.bias = bias; p.bias2 = bias2; p.beta = beta; p.act = act; p.mode = 0;
   apply_hints(p, hints);
   PlaneHit hit;
-  if (!hints.b_amax_bits && hints.b_scale == 1.f && find_weight_planes(B, ldb, trans_b, N, K, &hit)) {
+  if (hints.b_planes) {
+    p.b_presplit = 1; p.b_planes = hints.b_planes; p.b_row0 = hints.b_tile0 * BN; p.b_kb0 = hints.b_kb0; p.b_kbtot = hints.b_kbtot;
+  } else if (!hints.b_amax_bits && hints.b_scale == 1.f && find_weight_planes(B, ldb, trans_b, N, K, &hit)) {
     p.b_presplit = 1; p.b_planes = hit.planes; p.b_row0 = hit.tile0 * BN; p.b_kb0 = hit.kb0; p.b_kbtot = hit.kbtot;
   }
   // split-K (weight-gradient shapes: few output tiles, deep K): pick the split count with the smallest modelled time

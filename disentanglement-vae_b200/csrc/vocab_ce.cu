@@ -397,8 +397,11 @@ extern "C" int dvae_vocab_ce_fwd_ex(const float* h, int64_t ldh, int T1, int B, 
 // computed while this chunk's d_w GEMM (the longer of its two consumers) is still running
 static int p_buffers(int N, int V) { return p_chunk(N, V) < V ? 2 : 1; }
 
+// [softmax-gradient buffers][planes of h and w (when the forward call's are not reused)][planes of w^T and h^T: the
+// B operands of d_h = P . W and d_w = P^T . h, which read W_out / h as [K, N]]
 extern "C" int64_t dvae_vocab_ce_bwd_ws_floats(int N, int V, int H) {
-  return (int64_t)p_buffers(N, V) * N * p_chunk(N, V) + tc16::plane_floats(N, H) + tc16::plane_floats(V, H);
+  return (int64_t)p_buffers(N, V) * N * p_chunk(N, V) + tc16::plane_floats(N, H) + tc16::plane_floats(V, H) +
+         tc16::plane_floats(H, V) + tc16::plane_floats(H, N);
 }
 
 extern "C" int dvae_vocab_ce_bwd(const float* h, int64_t ldh, int T1, int B, int H, int V, const float* w,
@@ -433,6 +436,28 @@ extern "C" int dvae_vocab_ce_bwd(const float* h, int64_t ldh, int T1, int B, int
       h_planes = hp; w_planes = wp;
     }
   }
+  // B operands of the two gradient GEMMs as fp16 planes, written once per call instead of converted in every CTA:
+  // W_out^T [H, V] (registered by the caller, or split here) and h^T [H, N]
+  const void *wT_planes = nullptr, *hT_planes = nullptr;
+  int wT_kbtot = 0;
+  if (h_planes && H % 32 == 0 && N >= 128 && (reinterpret_cast<uintptr_t>(w) & 15) == 0 && ldh == H &&
+      !(getenv("DVAE_VOCAB_TPLANES") && getenv("DVAE_VOCAB_TPLANES")[0] == '0')) {
+    float* tp = ws + (int64_t)nbuf * N * vc_max + tc16::plane_floats(N, H) + tc16::plane_floats(V, H);
+    tc16::PlaneHit hit;
+    tc16::PlaneTable tab;
+    tab.n = 0;
+    if (tc16::find_weight_planes(w, H, 1, H, V, &hit) && hit.tile0 == 0 && hit.kb0 == 0) {
+      wT_planes = hit.planes; wT_kbtot = hit.kbtot;
+    } else {
+      tab.e[tab.n++] = tc16::PlaneTable::Entry{w, V, H, nullptr, tp};
+      wT_planes = tp; wT_kbtot = ceil_div(V, 32);
+    }
+    float* hp_t = tp + tc16::plane_floats(H, V);
+    tab.e[tab.n++] = tc16::PlaneTable::Entry{h, N, H, nullptr, hp_t};
+    hT_planes = hp_t;
+    int rc = tc16::weight_planes_launch(tab, st);
+    if (rc) return rc;
+  }
   int chunk = 0;
   const int nchunks = ceil_div(V, vc_max);
   for (int v0 = 0; v0 < V; v0 += vc_max, ++chunk) {
@@ -461,6 +486,8 @@ extern "C" int dvae_vocab_ce_bwd(const float* h, int64_t ldh, int T1, int B, int
     Fork fork(st);         // the three consumers of this chunk of P are independent of each other
     GemmHints ph_h = ph, ph_w = ph;
     ph_h.c_zeroed = dh_zeroed; ph_w.c_zeroed = dw_zeroed;
+    if (wT_planes) { ph_h.b_planes = wT_planes; ph_h.b_tile0 = 0; ph_h.b_kb0 = v0 / 32; ph_h.b_kbtot = wT_kbtot; }
+    if (hT_planes) { ph_w.b_planes = hT_planes; ph_w.b_tile0 = 0; ph_w.b_kb0 = 0; ph_w.b_kbtot = ceil_div(N, 32); }
     if ((rc = linear_impl_ex(Pc, vc_max, 0, w + (int64_t)v0 * H, H, 1, d_h, lddh, N, H, vc, nullptr, nullptr, chunk ? 1.f : 0.f, 0, ph_h, st))) return rc;
     // d_w[v0:v0+vc, :] = P^T [vc,N] . h [N,H]
     if ((rc = linear_impl_ex(Pc, vc_max, 1, h, ldh, 1, d_w + (int64_t)v0 * H, H, vc, H, N, nullptr, nullptr, 0.f, 0, ph_w, fork.side(0)))) return rc;
@@ -498,7 +525,7 @@ extern "C" int dvae_vocab_ce_partials(const float* h, int64_t ldh, int T1, int B
 
 static int vocab_sample_step_impl(const float* h, int64_t ldh, int B, int H, int V, const float* w, const float* bias,
                                   const uint64_t* seed_dev, uint32_t salt, int64_t* tokens_out, int64_t tok_stride,
-                                  const int32_t* forced_flag_dev, float* ws, void* stream) {
+                                  const int32_t* forced_flag_dev, const float* w_planes, float* ws, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   DVAE_REQUIRE(h && w && bias && seed_dev && tokens_out && ws, "dvae_vocab_sample_step: null pointer");
   DVAE_REQUIRE(B > 0 && H > 0 && V > 0, "dvae_vocab_sample_step: bad shape");
@@ -509,8 +536,16 @@ static int vocab_sample_step_impl(const float* h, int64_t ldh, int B, int H, int
   p.part = ws;
   p.part_idx = reinterpret_cast<int*>(ws + (int64_t)p.nsplit * p.N * 4);
   p.gumbel_seed = seed_dev; p.gumbel_salt = salt;
-  p.h_planes = p.w_planes = nullptr;      // one decode step: h has B rows only, splitting w per step would not pay
+  p.h_planes = p.w_planes = nullptr;      // one decode step: h has B rows only, splitting w per step would not pay ...
   p.skip_flag = forced_flag_dev;
+  if (w_planes && use_tc16(B, V, H, h, ldh, w) && use_presplit(B, V, H)) {
+    // ... unless the caller split W_out once for the whole decode (dvae_vocab_w_planes): then only the step's B x H states
+    // are split here (a few KB) and the projection runs as the bulk-copy-fed A-stationary kernel of the forward pass
+    float* hp = ws + ce_part_floats(B, V);
+    int rc2 = tc16::split_planes(h, ldh, B, H, 1.f, hp, st);
+    if (rc2) return rc2;
+    p.h_planes = hp; p.w_planes = w_planes;
+  }
   int rc = ce_partials(p, st);
   if (rc) return rc;
   vocab_sample_finalize_kernel<<<ceil_div(B, 128), 128, 0, st>>>(p, tokens_out, tok_stride);
@@ -521,11 +556,24 @@ static int vocab_sample_step_impl(const float* h, int64_t ldh, int B, int H, int
 extern "C" int dvae_vocab_sample_step(const float* h, int64_t ldh, int B, int H, int V, const float* w, const float* bias,
                                       const uint64_t* seed_dev, uint32_t salt, int64_t* tokens_out, int64_t tok_stride,
                                       float* ws, void* stream) {
-  return vocab_sample_step_impl(h, ldh, B, H, V, w, bias, seed_dev, salt, tokens_out, tok_stride, nullptr, ws, stream);
+  return vocab_sample_step_impl(h, ldh, B, H, V, w, bias, seed_dev, salt, tokens_out, tok_stride, nullptr, nullptr, ws, stream);
 }
 
 extern "C" int dvae_vocab_sample_step_ex(const float* h, int64_t ldh, int B, int H, int V, const float* w, const float* bias,
                                          const uint64_t* seed_dev, uint32_t salt, int64_t* tokens_out, int64_t tok_stride,
                                          const int32_t* forced_flag_dev, float* ws, void* stream) {
-  return vocab_sample_step_impl(h, ldh, B, H, V, w, bias, seed_dev, salt, tokens_out, tok_stride, forced_flag_dev, ws, stream);
+  return vocab_sample_step_impl(h, ldh, B, H, V, w, bias, seed_dev, salt, tokens_out, tok_stride, forced_flag_dev, nullptr, ws, stream);
+}
+
+extern "C" int64_t dvae_vocab_w_planes_floats(int V, int H) { return tc16::plane_floats(V, H); }
+
+extern "C" int dvae_vocab_w_planes(const float* w, int V, int H, float* planes, void* stream) {
+  DVAE_REQUIRE(w && planes && V > 0 && H > 0, "dvae_vocab_w_planes: bad argument");
+  return tc16::split_planes(w, H, V, H, 1.f, planes, (cudaStream_t)stream);
+}
+
+extern "C" int dvae_vocab_sample_step_planes(const float* h, int64_t ldh, int B, int H, int V, const float* w, const float* bias,
+                                             const float* w_planes, const uint64_t* seed_dev, uint32_t salt, int64_t* tokens_out,
+                                             int64_t tok_stride, const int32_t* forced_flag_dev, float* ws, void* stream) {
+  return vocab_sample_step_impl(h, ldh, B, H, V, w, bias, seed_dev, salt, tokens_out, tok_stride, forced_flag_dev, w_planes, ws, stream);
 }

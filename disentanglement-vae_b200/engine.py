@@ -109,10 +109,40 @@ class TrainEngine:
         self.label_names = [n for n, o in zip(d.space_names, d.dsc_out) if o > 0]
         self.last_aux = {}
         self.fixed_eps = None
+        self._wplanes, self._plane_token = [], object()
+        if os.environ.get("DVAE_WEIGHT_PLANES", "1") != "0" and not d.bow:
+            self._alloc_weight_planes()
+
+    # ---- weight planes: fp16 (hi, lo) operand tiles of the LSTM input weights and of W_out^T, refreshed once per step ------
+    def _alloc_weight_planes(self):
+        """Every GEMM that reads an LSTM input weight (x . W_ih^T forward, dG . W_ih backward) or W_out as [K, N] (d_h = P . W_out)
+        would otherwise re-convert the fp32 matrix in every CTA; the engine knows the weights change exactly once per step."""
+        lib, P = self.lib, self.model._P
+        names = [n for n in P if (".recurrent.weight_ih_" in n)]
+        todo = [(n, True, True) for n in names] + [("decoder.linear.weight", False, True)]
+        for n, normal, transposed in todo:
+            w = P[n]
+            R, C = w.shape
+            if R * C < (1 << 14) or (w.data_ptr() & 15):
+                continue
+            mk = lambda tr: torch.empty(lib.dvae_weight_planes_floats(R, C, tr), device=self.device, dtype=torch.float32)
+            self._wplanes.append((w, mk(0) if normal else None, mk(1) if transposed else None))
+
+    def _register_weight_planes(self):
+        if not self._wplanes or _lib.planes_owner is self._plane_token:
+            return
+        check(self.lib.dvae_weight_planes_clear(), "dvae_weight_planes_clear")
+        for w, pl, plt in self._wplanes:
+            check(self.lib.dvae_weight_planes_register(ptr(w), w.size(0), w.size(1), ptr(pl), ptr(plt)), "dvae_weight_planes_register")
+        _lib.planes_owner = self._plane_token
 
     # ---- the kernel sequences ------------------------------------------------------------------
     def _forward(self, fork_ok=True):
         pl, P, m = self.plan, self.model._P, self.model
+        n_pl = len(self._wplanes)
+        n_ih = sum(1 for w, a, b in self._wplanes if a is not None)      # LSTM input weights come first, W_out^T last
+        if n_pl:               # operand planes of the weights the encoder reads first: one launch, first thing in the step
+            check(self.lib.dvae_weight_planes_refresh_ex(0, n_ih, _lib.stream_ptr()), "dvae_weight_planes_refresh")
         # unpack the per-step scalar block (device-to-device, inside the graph)
         self.hyper[:5].copy_(self.d_scal[:5])
         self.kl_w.copy_(self.d_scal[8:8 + self.kl_w.numel()])
@@ -133,6 +163,10 @@ class TrainEngine:
                 self._side.wait_stream(cur)
                 with torch.cuda.stream(self._side):
                     pl.decode_prepare(P, self.inputs, m.sos_token_idx, True)
+                    if n_pl > n_ih:      # W_out^T planes (10 MB at cfg 2) are read by the vocabulary backward only
+                        check(self.lib.dvae_weight_planes_refresh_ex(n_ih, n_pl - n_ih, _lib.stream_ptr()), "dvae_weight_planes_refresh")
+        if n_pl > n_ih and not hoist:
+            check(self.lib.dvae_weight_planes_refresh_ex(n_ih, n_pl - n_ih, _lib.stream_ptr()), "dvae_weight_planes_refresh")
         pl.encode(P, self.inputs, self.lengths, True, after_l0_proj=fork_prep)
         pl.heads(P, pl.ctx, pl.eps, self.labels, self.kl_w)
         if hoist:
@@ -239,7 +273,36 @@ class TrainEngine:
         from .dist import grad_buckets
         return grad_buckets(self.model, self.grad)
 
+    def weight_planes(self):
+        """Context manager for callers that drive the plan's kernel sequences themselves (bench.py's per-kernel timings):
+        current planes, registry on inside the block."""
+        import contextlib
+
+        @contextlib.contextmanager
+        def cm():
+            self._register_weight_planes()
+            if self._wplanes:
+                check(self.lib.dvae_weight_planes_refresh(_lib.stream_ptr()), "dvae_weight_planes_refresh")
+                check(self.lib.dvae_weight_planes_enable(1), "dvae_weight_planes_enable")
+            try:
+                yield self
+            finally:
+                if self._wplanes:
+                    check(self.lib.dvae_weight_planes_enable(0), "dvae_weight_planes_enable")
+        return cm()
+
     def _run(self):
+        # the registry is consulted while kernels are ENQUEUED (eager steps, graph capture): on around this engine's launches only
+        self._register_weight_planes()
+        if self._wplanes:
+            check(self.lib.dvae_weight_planes_enable(1), "dvae_weight_planes_enable")
+        try:
+            return self._run_inner()
+        finally:
+            if self._wplanes:
+                check(self.lib.dvae_weight_planes_enable(0), "dvae_weight_planes_enable")
+
+    def _run_inner(self):
         if self.aux:
             return self._run_aux()
         if self.world == 1:

@@ -48,6 +48,31 @@ class ConsistencyEvaluator:
         self.plan.seed_dev.fill_(int(torch.randint(0, 2 ** 61, (1,), generator=g)))
         self._graph = {}
         self._encoded = False
+        # weight planes of the decoder's LSTM matrices: every decode step multiplies by them (x_t . W_ih^T, h_{t-1} . W_hh^T);
+        # the weights do not change during evaluation, so the planes are written once per resample() call
+        self._wplanes, self._plane_token = [], object()
+        if B >= 256 and not d.bow:
+            for n, w in model._P.items():
+                if n.startswith("decoder.recurrent.weight_") and w.dim() == 2 and w.numel() >= (1 << 14) and not (w.data_ptr() & 15):
+                    R, C = w.shape
+                    self._wplanes.append((w, torch.empty(self.plan.lib.dvae_weight_planes_floats(R, C, 0), device=dev, dtype=torch.float32)))
+
+    def _planes_on(self, refresh):
+        lib = self.plan.lib
+        if not self._wplanes:
+            return
+        if _lib.planes_owner is not self._plane_token:
+            _lib.check(lib.dvae_weight_planes_clear(), "dvae_weight_planes_clear")
+            for w, pl in self._wplanes:
+                _lib.check(lib.dvae_weight_planes_register(_lib.ptr(w), w.size(0), w.size(1), _lib.ptr(pl), None), "dvae_weight_planes_register")
+            _lib.planes_owner = self._plane_token
+        if refresh:
+            _lib.check(lib.dvae_weight_planes_refresh(_lib.stream_ptr()), "dvae_weight_planes_refresh")
+        _lib.check(lib.dvae_weight_planes_enable(1), "dvae_weight_planes_enable")
+
+    def _planes_off(self):
+        if self._wplanes:
+            _lib.check(self.plan.lib.dvae_weight_planes_enable(0), "dvae_weight_planes_enable")
 
     # ------------------------------------------------------------------------------------------
     def encode_once(self, inputs, lengths):
@@ -117,17 +142,24 @@ class ConsistencyEvaluator:
                "lengths_hat": torch.empty(R, B, device=dev, dtype=torch.int64)}
         if self.keep_tokens:
             out["token_predictions"] = torch.empty(R, B, T, device=dev, dtype=torch.int64)
-        with torch.no_grad():
-            for r in range(R):
-                self._run_body(bool(reencode_each))
-                out["dsc_logits"][r].copy_(self.logits)
-                out["dsc_logits_hat"][r].copy_(self.logits_hat)
-                out["z"][r].copy_(self.z)
-                out["z_hat"][r].copy_(self.z_hat)
-                out["lengths_hat"][r].copy_(self.lengths_hat)
-                if self.keep_tokens:
-                    out["token_predictions"][r].copy_(self.preds)
+        self._planes_on(refresh=True)
+        try:
+            with torch.no_grad():
+                for r in range(R):
+                    self._run_body(bool(reencode_each))
+                    self._copy_out(out, r)
+        finally:
+            self._planes_off()
         return out
+
+    def _copy_out(self, out, r):
+        out["dsc_logits"][r].copy_(self.logits)
+        out["dsc_logits_hat"][r].copy_(self.logits_hat)
+        out["z"][r].copy_(self.z)
+        out["z_hat"][r].copy_(self.z_hat)
+        out["lengths_hat"][r].copy_(self.lengths_hat)
+        if self.keep_tokens:
+            out["token_predictions"][r].copy_(self.preds)
 
     def predictions(self, packed_logits):
         """{label: [..., B] int64} = Discriminator.predict (vae/model.py:204-210) on packed logits [..., B, OD]."""

@@ -253,6 +253,13 @@ class StepPlan:
         dev_coins = torch.is_tensor(coins)
         if dev_coins:
             assert coins.dtype == torch.int32 and coins.is_cuda and coins.numel() >= T1
+        # large batches: W_out is split into the vocabulary kernels' operand planes once per decode, not once per CTA and step
+        w_planes = None
+        if B >= 256 and d.V >= 1024 and d.Hd % 32 == 0:
+            if getattr(self, "w_out_planes", None) is None:
+                self.w_out_planes = torch.empty(lib.dvae_vocab_w_planes_floats(d.V, d.Hd), device=self.device, dtype=torch.float32)
+            w_planes = self.w_out_planes
+            check(lib.dvae_vocab_w_planes(ptr(P["decoder.linear.weight"]), d.V, d.Hd, ptr(w_planes), st), "dvae_vocab_w_planes")
         for s in range(T1):
             check(lib.dvae_embedding_fwd(ptr(emb), d.E, ptr(preds), preds.stride(0), preds.stride(1), 1, B, p,
                                          ptr(self.seed_dev), SALT_DEC_EMB, d.sos, s, ptr(self.x_dec), st),
@@ -276,10 +283,10 @@ class StepPlan:
             if dev_coins or not coins[s]:
                 h_s = self.d_hs[-1].data_ptr() + 4 * s * B * d.Hd
                 flag = coins.data_ptr() + 4 * s if dev_coins else None
-                check(lib.dvae_vocab_sample_step_ex(h_s, d.Hd, B, d.Hd, d.V, ptr(P["decoder.linear.weight"]),
-                                                    ptr(P["decoder.linear.bias"]), ptr(self.seed_dev), SALT_SAMPLE + s,
-                                                    preds.data_ptr() + 8 * (s + 1) * preds.stride(1), preds.stride(0),
-                                                    flag, ptr(self.sample_ws), st), "dvae_vocab_sample_step")
+                check(lib.dvae_vocab_sample_step_planes(h_s, d.Hd, B, d.Hd, d.V, ptr(P["decoder.linear.weight"]),
+                                                        ptr(P["decoder.linear.bias"]), ptr(w_planes), ptr(self.seed_dev),
+                                                        SALT_SAMPLE + s, preds.data_ptr() + 8 * (s + 1) * preds.stride(1),
+                                                        preds.stride(0), flag, ptr(self.sample_ws), st), "dvae_vocab_sample_step")
         self._dec_p = p
         self._dec_tokens, self._dec_first = preds, d.sos
         self._dec_hid = hid

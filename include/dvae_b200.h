@@ -110,6 +110,9 @@ int dvae_relu(float* x, int64_t n, void* stream);
 int64_t dvae_weight_planes_floats(int R, int C, int transposed);
 int dvae_weight_planes_register(const float* w, int R, int C, void* planes, void* planes_t);
 int dvae_weight_planes_refresh(void* stream);
+/* Only the entries [first, first + count) in registration order: lets a caller refresh the weights its first kernels
+ * read on the main stream and the others (e.g. W_out^T, needed by the vocabulary backward only) on a side stream. */
+int dvae_weight_planes_refresh_ex(int first, int count, void* stream);
 int dvae_weight_planes_enable(int on);
 int dvae_weight_planes_clear(void);
 
@@ -333,6 +336,17 @@ int dvae_vocab_sample_step(const float* h, int64_t ldh, int B, int H, int V, con
 int dvae_vocab_sample_step_ex(const float* h, int64_t ldh, int B, int H, int V, const float* w,
                               const float* bias, const uint64_t* seed_dev, uint32_t salt, int64_t* tokens_out,
                               int64_t tok_stride, const int32_t* forced_flag_dev, float* ws, void* stream);
+
+/* Decoding many steps against the same W_out: split it ONCE into the fp16 operand planes the vocabulary kernels read
+ * (dvae_vocab_w_planes; planes: dvae_vocab_w_planes_floats(V, H) floats) and hand them to every step.  The step then
+ * splits only its B x H decoder states and runs the bulk-copy-fed projection of the forward pass; shapes that kernel does
+ * not take (B < 256, V < 1024, H % 32 != 0) fall back to dvae_vocab_sample_step_ex.  w_planes must be current with w. */
+int64_t dvae_vocab_w_planes_floats(int V, int H);
+int dvae_vocab_w_planes(const float* w, int V, int H, float* planes, void* stream);
+int dvae_vocab_sample_step_planes(const float* h, int64_t ldh, int B, int H, int V, const float* w,
+                                  const float* bias, const float* w_planes, const uint64_t* seed_dev, uint32_t salt,
+                                  int64_t* tokens_out, int64_t tok_stride, const int32_t* forced_flag_dev, float* ws,
+                                  void* stream);
 
 /* Length recount of sampled sentences before they are re-encoded (scripts/evaluation/consistency.py:186-190):
  * lengths_out[b] = max(min_len, T - #{t : tokens[b,t] == eos or tokens[b,t] == pad}).  The reference computes this with

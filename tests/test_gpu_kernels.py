@@ -149,6 +149,53 @@ def test_tc16_linear_fp16_split(lib, L, M, N, K, ta, tb):
     assert rel(c_d, want_t) < tol, rel(c_d, want_t)
 
 
+@pytest.mark.parametrize("M,R,C", [(300, 1024, 256), (2688, 1024, 512), (130, 384, 100)])
+def test_tc16_linear_with_registered_weight_planes(lib, L, M, R, C):
+    """Hybrid GEMM: B is a registered weight whose fp16 (hi, lo) planes were written once (dvae_weight_planes_refresh) and
+    arrive by bulk copy; A still goes through the converter ring.  Both orientations (x . W^T and g . W), blocks of W that
+    start on a 128-row / 32-column boundary, and the registry switched off again."""
+    rng = np.random.default_rng(M + R)
+    W = (rng.standard_normal((R, C)) / np.sqrt(C)).astype(np.float32)
+    Wd = dev(W)
+    pl = torch.empty(lib.dvae_weight_planes_floats(R, C, 0), device="cuda")
+    plt = torch.empty(lib.dvae_weight_planes_floats(R, C, 1), device="cuda")
+    st = L.stream_ptr()
+    L.check(lib.dvae_weight_planes_clear(), "clear")
+    L.check(lib.dvae_weight_planes_register(L.ptr(Wd), R, C, L.ptr(pl), L.ptr(plt)), "register")
+    L.check(lib.dvae_weight_planes_refresh(st), "refresh")
+    try:
+        for enable in (1, 0):
+            L.check(lib.dvae_weight_planes_enable(enable), "enable")
+            # y = x . W^T + b   (trans_b = 0; N = R, K = C)
+            x = rng.standard_normal((M, C)).astype(np.float32)
+            b = rng.standard_normal(R).astype(np.float32)
+            y = torch.zeros(M, R, device="cuda")
+            L.check(lib.dvae_tc16_linear(L.ptr(dev(x)), C, 0, L.ptr(Wd), C, 0, L.ptr(y), R, M, R, C, L.ptr(dev(b)), None, 0.0, 0,
+                                         1.0, 1.0, None, None, st), "x W^T")
+            assert rel(y, x.astype(np.float64) @ W.astype(np.float64).T + b) < 3e-6
+            # d = g . W         (trans_b = 1: B stored [K = R, N = C])
+            g = rng.standard_normal((M, R)).astype(np.float32)
+            d = torch.zeros(M, C, device="cuda")
+            L.check(lib.dvae_tc16_linear(L.ptr(dev(g)), R, 0, L.ptr(Wd), C, 1, L.ptr(d), C, M, C, R, None, None, 0.0, 0,
+                                         1.0, 1.0, None, None, st), "g W")
+            assert rel(d, g.astype(np.float64) @ W.astype(np.float64)) < 3e-6
+            if R >= 512:
+                # a row block of W as the K range of g . W[r0:r0+K, :]  (the vocabulary chunks of d_h = P . W_out)
+                r0, K = 256, R - 256 - 24
+                g2 = rng.standard_normal((M, K)).astype(np.float32)
+                d2 = torch.zeros(M, C, device="cuda")
+                L.check(lib.dvae_tc16_linear(L.ptr(dev(g2)), K, 0, Wd.data_ptr() + 4 * r0 * C, C, 1, L.ptr(d2), C, M, C, K, None, None,
+                                             0.0, 0, 1.0, 1.0, None, None, st), "g W[r0:]")
+                assert rel(d2, g2.astype(np.float64) @ W[r0:r0 + K].astype(np.float64)) < 3e-6
+                # a row block of W as the N range of x . W[r0:r0+N, :]^T
+                y2 = torch.zeros(M, 256, device="cuda")
+                L.check(lib.dvae_tc16_linear(L.ptr(dev(x)), C, 0, Wd.data_ptr() + 4 * 128 * C, C, 0, L.ptr(y2), 256, M, 256, C, None, None,
+                                             0.0, 0, 1.0, 1.0, None, None, st), "x W[128:384]^T")
+                assert rel(y2, x.astype(np.float64) @ W[128:384].astype(np.float64).T) < 3e-6
+    finally:
+        L.check(lib.dvae_weight_planes_clear(), "clear")
+
+
 def test_tc16_linear_tanh_and_rejects_unaligned(lib, L):
     rng = np.random.default_rng(5)
     M, N, K = 128, 512, 64
