@@ -52,3 +52,39 @@ def allreduce_buckets_(flat_grad, buckets, group=None):
     for b in rest:
         dist.all_reduce(b, op=dist.ReduceOp.SUM, group=group)
     return flat_grad
+
+
+def grad_buckets3(model, flat_grad):
+    """Three exchange steps in the order the backward pass finishes gradients (engine.TrainEngine, world > 1):
+      [0] decoder.*                                   -- final after the decoder backward
+      [1] encoder layers >= 1 + z2hidden + heads      -- final after the heads' and the upper encoder layers' backward
+      [2] encoder embedding + encoder layer 0         -- final at the end of the backward pass
+    Each entry is a list of contiguous views of `flat_grad`; together they cover it exactly once."""
+    lay, named = model._layout, dict(model.named_parameters())
+    n = flat_grad.numel()
+    end = {name: (off + named[name].numel() + 3) // 4 * 4 for name, off in lay.items()}
+
+    def span(pred):
+        names = [k for k in lay if pred(k)]
+        if not names:
+            return None
+        lo, hi = min(lay[k] for k in names), max(end[k] for k in names)
+        for k, off in lay.items():
+            if not pred(k) and lo <= off < hi:
+                raise AssertionError(f"{k} lies inside a gradient bucket it does not belong to")
+        return lo, hi
+
+    dec = span(lambda k: k.startswith("decoder."))
+    low = span(lambda k: k.startswith("encoder.embedding.") or (k.startswith("encoder.recurrent.") and "_l0" in k))
+    if dec is None or low is None or low[0] != 0:
+        d, rest = grad_buckets(model, flat_grad)
+        return [[d], rest, []]
+    covered = sorted([dec, low])
+    gaps, pos = [], 0
+    for lo, hi in covered:
+        if lo > pos:
+            gaps.append((pos, lo))
+        pos = max(pos, hi)
+    if pos < n:
+        gaps.append((pos, n))
+    return [[flat_grad[dec[0]:dec[1]]], [flat_grad[a:b] for a, b in gaps if b > a], [flat_grad[low[0]:low[1]]]]

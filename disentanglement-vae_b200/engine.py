@@ -207,6 +207,7 @@ class TrainEngine:
                     if hoist:
                         cur.wait_stream(self._side)
             self._aux_pending = hoist and part is None
+        emb_enc = "encoder.embedding.weight" in m._layout
         if part in (None, 2):
             check(self.lib.dvae_defer_joins(1), "dvae_defer_joins")
             try:
@@ -214,9 +215,21 @@ class TrainEngine:
                 if getattr(self, "_aux_pending", False):      # the decoder's embedding-gradient scatter still reads g_dx[0]
                     torch.cuda.current_stream().wait_stream(self._side)
                     self._aux_pending = False
-                pl.encode_bwd(P, G, self.inputs, self.lengths, g_ctx, emb_grad="encoder.embedding.weight" in m._layout)
+                self._g_ctx = g_ctx
+                # data parallel with a multi-layer encoder: stop after the upper layers (their gradients go out under layer 0)
+                split = part == 2 and self._three_buckets()
+                pl.encode_bwd(P, G, self.inputs, self.lengths, g_ctx, emb_grad=emb_enc, layers=(pl.d.Le - 1, 1) if split else None)
             finally:
                 check(self.lib.dvae_join_side_streams(st), "dvae_join_side_streams")
+        if part == 3:
+            check(self.lib.dvae_defer_joins(1), "dvae_defer_joins")
+            try:
+                pl.encode_bwd(P, G, self.inputs, self.lengths, self._g_ctx, emb_grad=emb_enc, layers=(0, 0))
+            finally:
+                check(self.lib.dvae_join_side_streams(st), "dvae_join_side_streams")
+
+    def _three_buckets(self):
+        return (self.world > 1 and not self.plan.d.bow and self.plan.d.Le >= 2 and os.environ.get("DVAE_DP_BUCKETS", "3") == "3")
 
     def _optim(self):
         st = _lib.stream_ptr()
@@ -314,35 +327,48 @@ class TrainEngine:
                 self._capture()
             self._graphs[0].replay()          # one graph: forward, backward, clip + Adam
             return
-        # data parallel: all-reduce the decoder gradients on a side stream while heads + encoder backward run
+        # data parallel: gradients are all-reduced in the order the backward pass finishes them, on a communication stream,
+        # under the rest of the backward pass: decoder.* | upper encoder layers + heads | encoder embedding + layer 0
         if self._buckets is None:
-            self._buckets = self._grad_buckets()
+            from .dist import grad_buckets3
+            self._buckets = grad_buckets3(self.model, self.grad)
             self._comm = torch.cuda.Stream(device=self.device)
-        dec_bucket, rest = self._buckets
         cur = torch.cuda.current_stream()
+        three = self._three_buckets()
         if self.use_graph and self._graphs is None:
             self._capture()
-        if self.use_graph:
-            self._graphs[0].replay()
-        else:
-            self._fwd_bwd(1)
         overlap = os.environ.get("DVAE_DP_OVERLAP", "1") != "0"
-        if overlap:
+
+        def run(part, gi):
+            if self.use_graph:
+                self._graphs[gi].replay()
+            else:
+                self._fwd_bwd(part)
+
+        def reduce_async(views):
             self._comm.wait_stream(cur)
             with torch.cuda.stream(self._comm):
-                dist.all_reduce(dec_bucket, op=dist.ReduceOp.SUM, group=self.pg)
-        if self.use_graph:
-            self._graphs[1].replay()
-        else:
-            self._fwd_bwd(2)
+                for v in views:
+                    dist.all_reduce(v, op=dist.ReduceOp.SUM, group=self.pg)
+
+        run(1, 0)
         if overlap:
-            for b in rest:
-                dist.all_reduce(b, op=dist.ReduceOp.SUM, group=self.pg)
+            reduce_async(self._buckets[0])
+        run(2, 1)
+        if three:
+            if overlap:
+                reduce_async(self._buckets[1])
+            run(3, 2)
+            if overlap:
+                reduce_async(self._buckets[2])
+        elif overlap:
+            reduce_async(self._buckets[1] + self._buckets[2])
+        if overlap:
             cur.wait_stream(self._comm)
         else:
             dist.all_reduce(self.grad, op=dist.ReduceOp.SUM, group=self.pg)
         if self.use_graph:
-            self._graphs[2].replay()
+            self._graphs[-1].replay()
         else:
             self._optim()
 
@@ -365,7 +391,7 @@ class TrainEngine:
                 self._optim()
             graphs.append(g)
         else:                 # the all-reduces sit between the graphs (NCCL on its own stream)
-            for part in (1, 2):
+            for part in ((1, 2, 3) if self._three_buckets() else (1, 2)):
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g, stream=s):
                     self._fwd_bwd(part)

@@ -373,7 +373,10 @@ class StepPlan:
                                         ptr(self.heads_bwd_ws), st), "dvae_latent_heads_bwd")
         return self.g_ctx
 
-    def encode_bwd(self, P, G, inputs, lengths, g_ctx, emb_grad=True):
+    def encode_bwd(self, P, G, inputs, lengths, g_ctx, emb_grad=True, layers=None):
+        """BPTT through the encoder stack.  `layers`: optional (first, last) pair, first >= last, to run only layers
+        first..last of the top-down sweep in this call (the data-parallel engine all-reduces layer 1's gradients while layer
+        0 is still running); a later call continues from the gradient the earlier one left."""
         self._alloc_bwd()
         lib, d, st = self.lib, self.d, _lib.stream_ptr()
         B, T = self.B, self.T
@@ -384,8 +387,9 @@ class StepPlan:
                                                inputs.stride(1), T, B, p, ptr(self.seed_dev), SALT_ENC_EMB,
                                                ptr(G["encoder.embedding.weight"]), st), "dvae_bow_encoder_bwd")
             return
-        g_in = None
-        for l in range(d.Le - 1, -1, -1):
+        first, last = (d.Le - 1, 0) if layers is None else layers
+        g_in = None if first == d.Le - 1 else self._enc_g_in
+        for l in range(first, last - 1, -1):
             I = d.E if l == 0 else d.D * d.H
             x = self.x_enc if l == 0 else (self.e_xin[l] if p > 0.0 else self.e_hs[l - 1])
             g_out = self.g_dx[l % 2]
@@ -403,7 +407,8 @@ class StepPlan:
                 check(lib.dvae_dropout(ptr(g_out), I, T * B, I, p, ptr(self.seed_dev), SALT_ENC_LAYER + l,
                                        ptr(g_out), I, 0, st), "dvae_dropout(bwd)")
             g_in = g_out
-        if emb_grad:
+        self._enc_g_in = g_in
+        if emb_grad and last == 0:
             check(lib.dvae_embedding_bwd(ptr(g_in), d.E, ptr(inputs), inputs.stride(0), inputs.stride(1), T, B, p,
                                          ptr(self.seed_dev), SALT_ENC_EMB, -1, 0, ptr(G["encoder.embedding.weight"]),
                                          st), "dvae_embedding_bwd")

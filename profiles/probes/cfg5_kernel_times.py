@@ -14,7 +14,7 @@ dvae.set_seed(10)
 vae = dvae.build_vae(B.CFG2, B.VOCAB, None, B.LABELS, dev, B.SOS, B.EOS); vae.train()
 rng = np.random.default_rng(5)
 X, L, _ = B.synth_batch(rng, B.BATCH)
-ev = inf.ConsistencyEvaluator(vae, B.BATCH, B.SEQ_T, use_graph=False)
+ev = inf.ConsistencyEvaluator(vae, B.BATCH, B.SEQ_T, use_graph=os.environ.get("TRACE_GRAPH", "0") == "1")
 ev.encode_once(torch.from_numpy(X), torch.from_numpy(L))
 ev.resample(2)
 torch.cuda.synchronize()
@@ -36,3 +36,16 @@ span = (max(e["ts"] + e["dur"] for e in evs) - min(e["ts"] for e in evs)) / 2
 print(f"# cfg5: per resample {tot / 2:.1f} us summed kernel time, {span:.1f} us span (eager)")
 for k, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:40]:
     print(f"{t / 2:10.1f} us {100 * t / tot:5.1f}% x{c // 2:4d}  {k}")
+
+# the largest idle gaps between consecutive kernels of the second resample (graph replays expose launch / dependency latencies)
+evs.sort(key=lambda e: e["ts"])
+half = evs[len(evs) // 2:]
+end, gaps = half[0]["ts"], []
+for e in half:
+    g = e["ts"] - end
+    if g > 0:
+        gaps.append((g, e["name"][:50]))
+    end = max(end, e["ts"] + e["dur"])
+print(f"# second resample: {len(half)} kernels, idle {sum(g for g, _ in gaps):.1f} us in {len(gaps)} gaps; largest:")
+for g, n in sorted(gaps, reverse=True)[:12]:
+    print(f"   {g:8.1f} us before {n}")

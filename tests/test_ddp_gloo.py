@@ -111,3 +111,32 @@ def test_bucketed_allreduce_covers_flat_gradient_exactly_once(tmp_path):
     mp.spawn(_bucket_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
     got = np.load(tmp_path / "buckets.npy")
     assert np.array_equal(got, np.arange(got.size, dtype=np.float32) * 3)
+
+
+def test_three_bucket_split_covers_flat_gradient_exactly_once(dvae):
+    """grad_buckets3: decoder | upper encoder layers + heads | encoder embedding + layer 0 -- disjoint, complete, and every
+    parameter's gradient lies in the bucket of the backward phase that produces it."""
+    import importlib
+    dvae_dist = importlib.import_module("disentanglement-vae_b200.dist")
+    p = dict(bow_encoder=False, embedding_dim=12, hidden_dim=16, num_rnn_layers=2, encoder_dropout=0.0, decoder_dropout=0.0,
+             bidirectional_encoder=True, latent_dims={"total": 7, "polarity": 1, "uncertainty": 2}, adversarial_loss=False, mi_loss=False)
+    vae = dvae.build_vae(p, 29, None, {"uncertainty": 3, "polarity": 1}, torch.device("cpu"), 2, 3)
+    n = vae._flat_numel
+    flat = torch.zeros(n)
+    buckets = dvae_dist.grad_buckets3(vae, flat)
+    assert len(buckets) == 3 and all(len(b) >= 1 for b in buckets)
+    for i, views in enumerate(buckets):
+        for v in views:
+            v += 1.0
+            assert v.data_ptr() % 16 == 0
+    assert torch.equal(flat, torch.ones(n))                      # every element in exactly one bucket
+    named = dict(vae.named_parameters())
+    marks = torch.zeros(n)
+    for i, views in enumerate(buckets):
+        for v in views:
+            off = (v.data_ptr() - flat.data_ptr()) // 4
+            marks[off:off + v.numel()] = i
+    for name, off in vae._layout.items():
+        want = 0 if name.startswith("decoder.") else (2 if name.startswith("encoder.embedding") or "_l0" in name else 1)
+        got = marks[off:off + named[name].numel()]
+        assert (got == want).all(), (name, want, got.unique())
