@@ -301,6 +301,9 @@ int lstm_seq_fwd_impl(const float* x, int64_t ldx, int T, int B, int I, int H, i
       return persist_fwd(H, a, st);
     }
     // hidden sizes beyond the cluster-resident kernels (512, 1024, ...): per-step tensor-core GEMMs over operand planes
+    if (!force_step_path() && planes_lstm_supported(B, H, D, ptrs, 11, lds, 5) && resident_lstm_supported(B, H))
+      return resident_lstm_fwd(T, B, H, D, w_hh, h0, c0, ld0, dir0, lengths, hs, ldhs, hn, cn, ldn, dirn, gates, cs,
+                               ws + planes_ws_offset(B, H, D), st);
     if (!force_step_path() && planes_lstm_supported(B, H, D, ptrs, 11, lds, 5))
       return planes_lstm_fwd(T, B, H, D, w_hh, h0, c0, ld0, dir0, lengths, hs, ldhs, hn, cn, ldn, dirn, gates, cs, ws,
                              ws + planes_ws_offset(B, H, D), st);

@@ -56,4 +56,12 @@ int planes_lstm_bwd(int T, int B, int H, int D, const float* const* w_hh, const 
                     const float* d_cn, int64_t ldn, int64_t dirn, float* d_h0, float* d_c0, int64_t ldd0, int64_t dird0,
                     float* ws, float* wt, float* pws, uint32_t* amax_slots, cudaStream_t st);
 
+// Grid-resident forward recurrence (lstm_resident.cu): H = 512 / 1024, B <= 128 -- W_hh tiled over the grid's tensor memory,
+// one launch per direction for all T steps.
+bool resident_lstm_supported(int B, int H);
+int64_t resident_lstm_ws_floats(int H);
+int resident_lstm_fwd(int T, int B, int H, int D, const float* const* w_hh, const float* h0, const float* c0, int64_t ld0,
+                      int64_t dir0, const int64_t* lengths, float* hs, int64_t ldhs, float* hn, float* cn, int64_t ldn,
+                      int64_t dirn, float* gates, float* cs, float* pws, cudaStream_t st);
+
 }  // namespace dvae
