@@ -373,7 +373,8 @@ tc16_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const uint32_t dst = smem_u + stage * STAGE_BYTES;
           mbar_expect_tx(&full[stage], STAGE_BYTES);
           bulk_load(dst, a_tiles + (int64_t)(kb0 + kb) * PS_TILE, PS_TILE, &full[stage]);
-          bulk_load(dst + PS_TILE, b_planes + ((int64_t)(nt + b_tile0) * nkb_total + kb0 + kb) * PS_TILE, PS_TILE, &full[stage]);
+          bulk_load(dst + PS_TILE, b_planes + ((int64_t)(nt + b_tile0) * (p.b_kbtot ? p.b_kbtot : nkb_total) + p.b_kb0 + kb0 + kb) * PS_TILE,
+                    PS_TILE, &full[stage]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -652,10 +653,39 @@ tc16_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                   v[j] = (dead || col >= p.N) ? 0.f : (e - (col == tgt ? 1.f : 0.f)) * row_scale;
                 }
               }
+              // planes output: this thread's 8 columns of its row are one 16-byte chunk of each K-major plane of P (the A
+              // operand of d_h = P . W); padding rows / columns carry zeros
+              // (a tile reaches past the planes' last k-block when N is not a multiple of 128: those chunks do not exist)
+              // (nor do the rows of a CTA pair's padding row block)
+              if (p.p_planes_a && col0 + hh * 16 + h8 * 8 < p.p_kb_a * BK && m0 < (p.M + BM - 1) / BM * BM)
+                store_plane_chunk(p.p_planes_a, row, col0 + hh * 16 + h8 * 8, p.p_kb_a, v, p.p_scale);
 #pragma unroll
               for (int j = 0; j < 8; ++j) sts32(sc + (lane * 16 + ((h8 * 8 + j) ^ ((lane >> 1) & 15))) * 4, v[j]);
             }
             __syncwarp();
+            if (p.p_planes_t) {
+              // transposed planes (rows = vocabulary ids, K = decoder positions: the A operand of d_w = P^T . h): after the
+              // transpose through shared memory a thread holds 16 consecutive rows of one column = two 16-byte chunks per
+              // plane; their sum, folded over the two row halves, is this warp's share of the bias gradient
+              const int cc = lane & 15, rg = lane >> 4, colw = col0 + hh * 16 + cc;
+              float tv[16], ssum = 0.f;
+#pragma unroll
+              for (int k = 0; k < 16; ++k) {
+                const int r = rg * 16 + k;
+                tv[k] = lds32(sc + (r * 16 + (cc ^ ((r >> 1) & 15))) * 4);
+                ssum += tv[k];
+              }
+              ssum += __shfl_xor_sync(0xffffffffu, ssum, 16);
+              if (colw < p.N) {
+                if (rg == 0 && p.p_colsum) atomicAdd(p.p_colsum + colw, ssum);
+                const float lo8[8] = {tv[0], tv[1], tv[2], tv[3], tv[4], tv[5], tv[6], tv[7]};
+                const float hi8[8] = {tv[8], tv[9], tv[10], tv[11], tv[12], tv[13], tv[14], tv[15]};
+                if (r0 + rg * 16 < p.p_kb_t * BK) store_plane_chunk(p.p_planes_t, colw, r0 + rg * 16, p.p_kb_t, lo8, p.p_scale);
+                if (r0 + rg * 16 + 8 < p.p_kb_t * BK) store_plane_chunk(p.p_planes_t, colw, r0 + rg * 16 + 8, p.p_kb_t, hi8, p.p_scale);
+              }
+              __syncwarp();
+              continue;
+            }
             const int colw = col0 + hh * 16 + (lane & 15);
             float* cp = p.C + (int64_t)(r0 + (lane >> 4)) * p.ldc + colw;
             if (colw < p.N) {
@@ -1055,13 +1085,14 @@ int linear(const float* A, int64_t lda, int trans_a, const float* B, int64_t ldb
 // is split once per call (its weights).  c_row_scale: optional per-row output factor (device, [M]).
 int linear_planes(const void* a_planes, const void* b_planes, float* C, int64_t ldc, int M, int N, int K, const float* bias,
                   float beta, int act, float a_scale, float b_scale, const float* c_row_scale, bool c_zeroed, int max_splits,
-                  cudaStream_t st) {
+                  cudaStream_t st, int b_kb0, int b_kbtot) {
   DVAE_REQUIRE(a_planes && b_planes && C && M > 0 && N > 0 && K > 0, "tc16 linear_planes: bad argument");
   Params p = {};
   p.presplit = 1; p.no_astat = 1; p.a_planes = a_planes; p.b_planes = b_planes; p.a_rows = M; p.b_rows = N;
   p.M = M; p.N = N; p.K = K; p.tiles_per_cta = 1; p.C = C; p.ldc = ldc; p.bias = bias; p.beta = beta; p.act = act; p.mode = 0;
   apply_hints(p, GemmHints());
   p.a_scale = a_scale; p.b_scale = b_scale; p.c_row_scale = c_row_scale;
+  p.b_kb0 = b_kb0; p.b_kbtot = b_kbtot;          // B planes wider than this GEMM's K range (a vocabulary chunk of W_out^T)
   const int tiles = ceil_div(M, BM) * ceil_div(N, BN), nkb = ceil_div(K, BK);
   int splits = 1;
   if (act == 0 && nkb >= 8) {      // same cost model as linear(), with the bulk-copy-fed k-block time
@@ -1114,8 +1145,13 @@ int ce_partials(const float* h, int64_t ldh, int N, int B, int H, int V, const f
 int softmax_grad(const float* h, int64_t ldh, int N, int B, int H, int V, int v0, int vc, const float* w, const float* bias,
                  const int64_t* targets, int64_t tgt_stride_b, const int64_t* lengths, const float* lse,
                  const float* grad_scale, float* P, int64_t ldp, const void* h_planes, const void* w_planes, float* zero_buf,
-                 int64_t zero_n4, float* zero_buf2, int64_t zero2_n4, cudaStream_t st) {
+                 int64_t zero_n4, float* zero_buf2, int64_t zero2_n4, cudaStream_t st, void* p_planes_a, void* p_planes_t,
+                 float* p_colsum, float p_scale) {
   Params p = {};
+  if (p_planes_a && p_planes_t && h_planes && w_planes) {
+    p.p_planes_a = reinterpret_cast<uint8_t*>(p_planes_a); p.p_planes_t = reinterpret_cast<uint8_t*>(p_planes_t);
+    p.p_colsum = p_colsum; p.p_scale = p_scale; p.p_kb_a = ceil_div(vc, BK); p.p_kb_t = ceil_div(N, BK);
+  }
   p.zero_buf = zero_buf; p.zero_n4 = zero_n4; p.zero_buf2 = zero_buf2; p.zero2_n4 = zero2_n4;
   if (!p.zero_buf) { p.zero_buf = p.zero_buf2; p.zero_n4 = p.zero2_n4; p.zero_buf2 = nullptr; p.zero2_n4 = 0; }
   DVAE_REQUIRE(!(h_planes && w_planes) || v0 % BN == 0, "tc16 softmax_grad: pre-split chunks must start on a %d-row block (v0=%d)", BN, v0);

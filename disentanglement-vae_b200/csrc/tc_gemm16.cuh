@@ -33,6 +33,11 @@ struct Params {
   const float* c_row_scale;              // optional per-output-row factor [M] (mode 0)
   int presplit; int b_row0;     // b_row0: first B row of this call inside the B planes (a vocabulary chunk)
   const void* a_planes; const void* b_planes; int a_rows, b_rows;      // tile-blocked fp16 planes (split_planes)
+  // mode 2, pre-split kernels only: P leaves the kernel as fp16 operand planes (dual-accumulator convention, values * p_scale)
+  // in both orientations instead of fp32 -- p_planes_a [M rows, K = N cols] for d_h = P . W, p_planes_t [N cols as rows, K = M]
+  // for d_w = P^T . h -- and its column sums are added to p_colsum (the bias gradient): no fp32 P, no converter warps and no
+  // separate column-sum kernel downstream
+  uint8_t* p_planes_a; uint8_t* p_planes_t; float* p_colsum; float p_scale; int p_kb_a, p_kb_t;
   const int* skip_flag;      // optional device flag: non-zero = the whole launch is a no-op (sampled decoding: a step whose
                              // input is teacher-forced needs no vocabulary sample; decided on the device so one CUDA graph serves every step)
   int dbg_skip_epilogue;     // probes only (DVAE_TC_SKIP_EPILOGUE=1): accumulators are released unread
@@ -51,7 +56,7 @@ int64_t plane_floats(int R, int K);
 int split_planes(const float* X, int64_t ld, int R, int K, float scale, void* planes, cudaStream_t st, bool force_dual = false);
 int linear_planes(const void* a_planes, const void* b_planes, float* C, int64_t ldc, int M, int N, int K, const float* bias,
                   float beta, int act, float a_scale, float b_scale, const float* c_row_scale, bool c_zeroed, int max_splits,
-                  cudaStream_t st);
+                  cudaStream_t st, int b_kb0 = 0, int b_kbtot = 0);
 // Weight-plane registry (api.cu): GEMMs whose B operand is a registered weight matrix (or a 128-row / 32-column aligned
 // block of it) fetch B as pre-split planes by bulk copy; only A goes through the converter warps.
 constexpr int kMaxPlaneEntries = 24;
@@ -72,7 +77,8 @@ int ce_partials(const float* h, int64_t ldh, int N, int B, int H, int V, const f
 int softmax_grad(const float* h, int64_t ldh, int N, int B, int H, int V, int v0, int vc, const float* w, const float* bias,
                  const int64_t* targets, int64_t tgt_stride_b, const int64_t* lengths, const float* lse,
                  const float* grad_scale, float* P, int64_t ldp, const void* h_planes, const void* w_planes, float* zero_buf,
-                 int64_t zero_n4, float* zero_buf2, int64_t zero2_n4, cudaStream_t st);
+                 int64_t zero_n4, float* zero_buf2, int64_t zero2_n4, cudaStream_t st, void* p_planes_a = nullptr,
+                 void* p_planes_t = nullptr, float* p_colsum = nullptr, float p_scale = 1.f);
 
 }  // namespace tc16
 }  // namespace dvae

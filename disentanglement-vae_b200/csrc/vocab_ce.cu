@@ -307,6 +307,21 @@ static int p_chunk(int N, int V) {
   return (int)vc;
 }
 
+// P as fp16 operand planes in both orientations (8 bytes per element instead of 4): chunk width for ~80 MB per chunk
+static int p_chunk_planes(int N, int V) {
+  int64_t vmax = (10LL << 20) / (N > 0 ? N : 1);
+  vmax = vmax / 128 * 128;
+  if (vmax < 128) vmax = 128;
+  const int64_t vr = (int64_t)ceil_div(V, 128) * 128;
+  if (vmax >= vr) return (int)vr;
+  const int64_t nc = (vr + vmax - 1) / vmax;
+  return (int)(((V + nc - 1) / nc + 127) / 128 * 128);
+}
+static bool p_planes_enabled() {
+  const char* e = getenv("DVAE_VOCAB_PPLANES");
+  return !(e && e[0] == '0');
+}
+
 }  // namespace dvae
 
 using namespace dvae;
@@ -399,9 +414,17 @@ static int p_buffers(int N, int V) { return p_chunk(N, V) < V ? 2 : 1; }
 
 // [softmax-gradient buffers][planes of h and w (when the forward call's are not reused)][planes of w^T and h^T: the
 // B operands of d_h = P . W and d_w = P^T . h, which read W_out / h as [K, N]]
+static int p_buffers_planes(int N, int V) { return p_chunk_planes(N, V) < V ? 2 : 1; }
+// front region: the softmax-gradient chunk buffers, as fp32 [N, vc] or as operand planes in both orientations
+static int64_t p_region_floats(int N, int V) {
+  const int64_t a = (int64_t)p_buffers(N, V) * N * p_chunk(N, V);
+  const int vcp = p_chunk_planes(N, V);
+  const int64_t b = (int64_t)p_buffers_planes(N, V) * (tc16::plane_floats(N, vcp) + tc16::plane_floats(vcp, N));
+  return (a > b ? a : b) + 4;
+}
 extern "C" int64_t dvae_vocab_ce_bwd_ws_floats(int N, int V, int H) {
-  return (int64_t)p_buffers(N, V) * N * p_chunk(N, V) + tc16::plane_floats(N, H) + tc16::plane_floats(V, H) +
-         tc16::plane_floats(H, V) + tc16::plane_floats(H, N);
+  return p_region_floats(N, V) / 4 * 4 + tc16::plane_floats(N, H) + tc16::plane_floats(V, H) + tc16::plane_floats(H, V) +
+         tc16::plane_floats(H, N);
 }
 
 extern "C" int dvae_vocab_ce_bwd(const float* h, int64_t ldh, int T1, int B, int H, int V, const float* w,
@@ -412,7 +435,9 @@ extern "C" int dvae_vocab_ce_bwd(const float* h, int64_t ldh, int T1, int B, int
   cudaStream_t st = (cudaStream_t)stream;
   DVAE_REQUIRE(h && w && bias && targets && lengths && lse && d_h && d_w && d_bias && ws, "dvae_vocab_ce_bwd: null pointer");
   DVAE_REQUIRE(T1 > 0 && B > 0 && H > 0 && V > 0, "dvae_vocab_ce_bwd: bad shape");
-  const int N = T1 * B, vc_max = p_chunk(N, V), nbuf = p_buffers(N, V);
+  const int N = T1 * B;
+  int vc_max = p_chunk(N, V), nbuf = p_buffers(N, V);
+  const int64_t front = p_region_floats(N, V) / 4 * 4;
   PArgs p;
   p.h = h; p.ldh = ldh; p.w = w; p.bias = bias; p.targets = targets; p.tgt_stride_b = tgt_stride_b;
   p.lengths = lengths; p.lse = lse; p.grad_scale = grad_scale_dev; p.N = N; p.B = B; p.H = H; p.V = V;
@@ -428,7 +453,7 @@ extern "C" int dvae_vocab_ce_bwd(const float* h, int64_t ldh, int T1, int B, int
       const float* hp = fwd_ws + ce_part_floats(N, V);
       h_planes = hp; w_planes = hp + tc16::plane_floats(N, H);
     } else {
-      float* hp = ws + (int64_t)nbuf * N * vc_max;
+      float* hp = ws + front;
       float* wp = hp + tc16::plane_floats(N, H);
       int rc;
       if ((rc = tc16::split_planes(h, ldh, N, H, 1.f, hp, st))) return rc;
@@ -442,7 +467,7 @@ extern "C" int dvae_vocab_ce_bwd(const float* h, int64_t ldh, int T1, int B, int
   int wT_kbtot = 0;
   if (h_planes && H % 32 == 0 && N >= 128 && (reinterpret_cast<uintptr_t>(w) & 15) == 0 && ldh == H &&
       !(getenv("DVAE_VOCAB_TPLANES") && getenv("DVAE_VOCAB_TPLANES")[0] == '0')) {
-    float* tp = ws + (int64_t)nbuf * N * vc_max + tc16::plane_floats(N, H) + tc16::plane_floats(V, H);
+    float* tp = ws + front + tc16::plane_floats(N, H) + tc16::plane_floats(V, H);
     tc16::PlaneHit hit;
     tc16::PlaneTable tab;
     tab.n = 0;
@@ -458,6 +483,16 @@ extern "C" int dvae_vocab_ce_bwd(const float* h, int64_t ldh, int T1, int B, int
     int rc = tc16::weight_planes_launch(tab, st);
     if (rc) return rc;
   }
+  // P never exists as fp32: the softmax-gradient kernel writes fp16 operand planes in both orientations (and adds the bias
+  // gradient), and the two gradient GEMMs are bulk-copy fed on both operands
+  const bool pp = wT_planes && hT_planes && h_planes && w_planes && p_planes_enabled() && lddh % 4 == 0 &&
+                  tc16::supported(h, ldh, 0, w, H, 0, N, min(vc_max, V), H);
+  int64_t pa_fl = 0, pt_fl = 0;
+  if (pp) {
+    vc_max = p_chunk_planes(N, V); nbuf = p_buffers_planes(N, V);
+    pa_fl = tc16::plane_floats(N, vc_max); pt_fl = tc16::plane_floats(vc_max, N);
+    DVAE_CUDA(cudaMemsetAsync(d_bias, 0, sizeof(float) * V, st));
+  }
   int chunk = 0;
   const int nchunks = ceil_div(V, vc_max);
   for (int v0 = 0; v0 < V; v0 += vc_max, ++chunk) {
@@ -466,6 +501,25 @@ extern "C" int dvae_vocab_ce_bwd(const float* h, int64_t ldh, int T1, int B, int
     p.v0 = v0; p.vc = vc; p.P = Pc;
     int rc;
     bool dh_zeroed = false, dw_zeroed = false;
+    if (pp) {
+      float* pa = ws + (int64_t)(chunk % nbuf) * (pa_fl + pt_fl);
+      float* pt = pa + pa_fl;
+      const bool zh = chunk == 0 && lddh == H && (((uintptr_t)d_h) & 15) == 0 && ((int64_t)N * H) % 4 == 0;
+      const bool zw = (((uintptr_t)(d_w + (int64_t)v0 * H)) & 15) == 0 && ((int64_t)vc * H) % 4 == 0;
+      if ((rc = tc16::softmax_grad(h, ldh, N, B, H, V, v0, vc, w, bias, targets, tgt_stride_b, lengths, lse, grad_scale_dev, nullptr,
+                                   vc_max, h_planes, w_planes, zh ? d_h : nullptr, (int64_t)N * H / 4,
+                                   zw ? d_w + (int64_t)v0 * H : nullptr, (int64_t)vc * H / 4, st, pa, pt, d_bias + v0, ph.a_scale))) return rc;
+      Fork fork(st);
+      // d_h [N,H] (+)= P [N,vc] . W[v0:v0+vc, :]: A = P planes, B = planes of W_out^T, k-blocks v0/32 .. of its K = V axis
+      if ((rc = tc16::linear_planes(pa, wT_planes, d_h, lddh, N, H, vc, nullptr, chunk ? 1.f : 0.f, 0, ph.a_scale, 1.f, nullptr, zh, 16, st,
+                                    v0 / 32, wT_kbtot))) return rc;
+      // d_w[v0:v0+vc, :] = P^T [vc,N] . h [N,H]: A = transposed P planes, B = planes of h^T
+      if ((rc = tc16::linear_planes(pt, hT_planes, d_w + (int64_t)v0 * H, H, vc, H, N, nullptr, 0.f, 0, ph.a_scale, 1.f, nullptr, zw, 16,
+                                    fork.side(0), 0, 0))) return rc;
+      if (chunk + 1 == nchunks || chunk + 1 >= nbuf)
+        if ((rc = fork.join())) return rc;
+      continue;
+    }
     if (!force_simt_gemm() && N >= 64 && vc >= 128 && H >= 32 && tc16::supported(h, ldh, 0, w, H, 0, N, vc, H)) {
       // the kernel also clears the outputs of this chunk's split-K GEMMs (d_h once, this chunk's rows of d_w): no memset nodes
       const bool zh = chunk == 0 && lddh == H && (((uintptr_t)d_h) & 15) == 0 && ((int64_t)N * H) % 4 == 0;
