@@ -307,9 +307,16 @@ static int p_chunk(int N, int V) {
   return (int)vc;
 }
 
-// P as fp16 operand planes in both orientations (8 bytes per element instead of 4): chunk width for ~80 MB per chunk
+// P as fp16 operand planes in both orientations (8 bytes per element instead of 4).  Each plane set is written once and read
+// once, so it may stream through HBM: ONE chunk (the whole vocabulary) up to 4 GB of planes -- 217 MB at cfg 2, 3.2 GB at
+// cfg 4 -- instead of L2-sized chunks: a third fewer launches and longer K loops (measured: cfg 2 step 1.290 -> 1.237 ms with
+// 1 chunk instead of 3, the backward call 247 -> 188 us; cfg 4: 9.7 -> 7.9 ms).
 static int p_chunk_planes(int N, int V) {
-  int64_t vmax = (10LL << 20) / (N > 0 ? N : 1);
+  static const int64_t budget = [] {      // elements per chunk (8 bytes each); DVAE_VOCAB_PCHUNK_M = millions (A/B knob)
+    const char* e = getenv("DVAE_VOCAB_PCHUNK_M");
+    return (int64_t)(e ? atoi(e) : 512) << 20;
+  }();
+  int64_t vmax = budget / (N > 0 ? N : 1);
   vmax = vmax / 128 * 128;
   if (vmax < 128) vmax = 128;
   const int64_t vr = (int64_t)ceil_div(V, 128) * 128;
