@@ -540,6 +540,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-trace", action="store_true", help="skip the CUPTI GEMM-class / recurrence breakdown after the timed region")
+    ap.add_argument("--only-steps", action="store_true", help="warm-up + timed steps only (launch lists under ncu): no e2e / roofline legs")
     ap.add_argument("--batch", type=int, default=None, help="per-GPU batch (default: the workload's)")
     ap.add_argument("--tf", type=float, default=None, help="teacher_forcing_prob (default 1.0 = headline; 0.5 = the shipped configs' value)")
     ap.add_argument("--workload", default="cfg2", choices=["cfg1", "cfg2", "cfg3", "cfg4", "cfg5"],
@@ -630,6 +631,15 @@ def main():
     clk = clocks.stop() if clocks else None
     dev_ms = sum(a.elapsed_time(b) for a, b in ev)
     loss_last = eng.losses_from(out.cpu())["total_loss"]
+
+    if args.only_steps:
+        if rank == 0:
+            print(json.dumps({"metric": "train_tokens_per_sec", "value": tok_sum / (dev_ms * 1e-3), "unit": "tokens/s", "n_gpus": world,
+                              "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps,
+                              "config": workload_config(world, graph=not args.no_graph), "note": "--only-steps: no e2e / roofline legs"}), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
+        return
 
     # ---- data parallel: every rank must hold bit-identical parameters after the all-reduced steps ----
     replicas_identical = None

@@ -479,8 +479,8 @@ class TrainEngine:
              "idv_dsc_accs": {n: o[3 + 2 * S + i] for i, n in enumerate(self.d.space_names) if self.d.dsc_out[i] > 0}}
         L["total_loss"] = o[NS] + o[0] + o[2]
         if self.aux and self.last_aux:
-            L["total_adv_loss"] = float(self.last_aux["total_adv_loss"])
-            L["total_mi"] = float(self.last_aux["total_mi"])
+            L["total_adv_loss"] = float(self.last_aux["total_adv_loss"].detach())
+            L["total_mi"] = float(self.last_aux["total_mi"].detach())
             for k in ("idv_adv_losses", "idv_adv_dsc_accs", "idv_mi_estimates"):
                 L[k] = self.last_aux[k]
             L["total_loss"] += L["total_adv_loss"] + L["total_mi"]

@@ -20,7 +20,7 @@ def main(path):
     for row, n in zip(rows[a:b], names[a:b]):
         t = float(row["Metric Value"].replace(",", ""))
         t = {"ns": t / 1e3, "us": t, "ms": t * 1e3, "s": t * 1e6}.get(row["Metric Unit"], t)
-        c = agg.setdefault(n[:90], [0, 0.0, row["Grid Size"], row["Block Size"]])
+        c = agg.setdefault(n[:90] + "  " + row["Grid Size"].replace(" ", ""), [0, 0.0, "", row["Block Size"]])
         c[0] += 1
         c[1] += t
         tot += t
