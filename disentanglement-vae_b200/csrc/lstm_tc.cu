@@ -82,7 +82,7 @@ __device__ __forceinline__ void bulk_copy_to_peer(uint32_t dst_cluster, uint32_t
                : "memory");
 }
 // hardware barrier of one 512-thread row group (barrier 0 is __syncthreads)
-__device__ __forceinline__ void group_sync(int grp) { asm volatile("bar.sync %0, 512;" ::"r"(grp + 1) : "memory"); }
+__device__ __forceinline__ void group_sync(int grp, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "r"(nthreads) : "memory"); }
 // 32 lanes x 4 consecutive fp32 columns
 __device__ __forceinline__ void tmem_ld4(uint32_t taddr, float (&v)[4]) {
   uint32_t r[4];
@@ -124,7 +124,9 @@ constexpr int kG_SG = 4 * kF_BPlane;             // activated gates [4][NB][32] 
 constexpr int kG_LEN = kG_SG + 4 * kNB * 32 * 4; // int [NB]
 constexpr int kG_BAR = kG_LEN + kNB * 4;         // full[2], mma_done
 constexpr int kG_BYTES = kG_BAR + 64;
-constexpr int fwd_smem_bytes(int G) { return kF_GRP + G * kG_BYTES + 16; }
+// per-group block for NB batch rows per group (the constants above are the NB = 16 instance; the kernels re-derive them)
+__host__ __device__ constexpr int fwd_group_bytes(int NB) { return 4 * (NB * kH * 2) + 4 * NB * 32 * 4 + NB * 4 + 64; }
+constexpr int fwd_smem_bytes(int G, int NB) { return kF_GRP + G * fwd_group_bytes(NB) + 16; }
 // operand layouts (no swizzle, K-major; a "chunk" is 8 fp16 = 16 bytes, a core matrix is 8 rows x 1 chunk = 128 B)
 //   A: chunk(m, kc) at (m >> 3) * 4096 + kc * 128 + (m & 7) * 16      SBO = 4096 (next 8 rows), LBO = 128 (next chunk)
 //   B: chunk(n, kc) at kc * (NB * 16) + n * 16                         SBO = 128, LBO = NB * 16
@@ -135,8 +137,15 @@ constexpr int kT_AHI = 64, kT_ALO = 192, kT_FWD_COLS = DVAE_LSTM_A_TMEM ? 512 : 
 // G row groups of NB = 16 batch rows share the resident weights; each group is 16 warps with its own operand
 // buffers, accumulators and barriers and runs the step loop independently, so one group's state exchange and gate
 // math overlap the other group's MMAs on the (single) tensor pipe.
-template <int G>
-__global__ void __cluster_dims__(kCS, 1, 1) __launch_bounds__(kGT * G, 1) lstm_tc_fwd_kernel(PersistFwdArgs p) {
+// NB = batch rows per group: 16, or 32 (one group of 32 warps) -- an N = 32 MMA takes the tensor pipe as long as an N = 16 one,
+// so a bidirectional layer at B = 128 (8 clusters of 32 rows) runs ONE group per cluster instead of two that share the MMA
+// issue slot, the barriers and the exchange
+template <int G, int NB>
+__global__ void __cluster_dims__(kCS, 1, 1) __launch_bounds__(32 * NB * G, 1) lstm_tc_fwd_kernel(PersistFwdArgs p) {
+  constexpr int kNB = NB, kGT = 32 * NB;
+  constexpr int kF_BPlane = kNB * kH * 2, kG_B = 0, kG_SG = 4 * kF_BPlane, kG_LEN = kG_SG + 4 * kNB * 32 * 4, kG_BAR = kG_LEN + kNB * 4,
+                kG_BYTES = kG_BAR + 64, kB_LBO = kNB * 16, kSlice = 4 * kB_LBO;
+  static_assert(kG_BYTES == fwd_group_bytes(NB), "shared-memory layout");
   extern __shared__ __align__(1024) uint8_t smem[];
   const int tid = threadIdx.x, grp = tid / kGT, gtid = tid % kGT, warp = gtid >> 5, lane = tid & 31, B = p.B, T = p.T;
   const uint32_t sbase = smem_u32(smem), gbase = sbase + kF_GRP + grp * kG_BYTES;
@@ -189,7 +198,7 @@ __global__ void __cluster_dims__(kCS, 1, 1) __launch_bounds__(kGT * G, 1) lstm_t
   __syncthreads();
   cluster.sync();           // every CTA's mbarriers are initialised before any peer can signal them
   tc_fence_after();
-  if (DVAE_LSTM_A_TMEM && grp == 0) {
+  if (DVAE_LSTM_A_TMEM && grp == 0 && cgp < 4) {      // 16 warps: 4 TMEM lane quadrants x 4 k ranges (a 32-row group has 32)
     // weights -> tensor memory: this thread owns gate row m = 32*q + lane (its TMEM lane) and k in [64*cgp, 64*cgp + 64)
     const float* wrow = p.w_hh[d] + (int64_t)(q * kH + u0 + lane) * kH + 64 * cgp;
     const uint32_t tbase = *tmem_slot + ((uint32_t)(q * 32) << 16) + 32 * cgp;
@@ -214,7 +223,7 @@ __global__ void __cluster_dims__(kCS, 1, 1) __launch_bounds__(kGT * G, 1) lstm_t
     __syncthreads();
     tc_fence_after();
   }
-  const uint32_t tmem = *tmem_slot + 32 * grp;
+  const uint32_t tmem = *tmem_slot + 2 * kNB * grp;
   const uint32_t slice_off = (uint32_t)(4 * rank) * kB_LBO;
   constexpr uint32_t kIdesc = make_idesc_f16(128, kNB);
 
@@ -230,7 +239,7 @@ __global__ void __cluster_dims__(kCS, 1, 1) __launch_bounds__(kGT * G, 1) lstm_t
     sts_h(blo + off, lo);
     fence_proxy_async();         // generic-proxy stores -> visible to the bulk-copy engine and to tcgen05.mma
     tc_fence_before();
-    group_sync(grp);
+    group_sync(grp, kGT);
     if (gtid == 0) mbar_expect_tx(&bars[buf], 14 * kSlice);
     if (warp == 1 && lane < 14) {
       const int pi = lane >> 1, peer = pi + (pi >= rank ? 1 : 0), plane = lane & 1;
@@ -283,7 +292,7 @@ __global__ void __cluster_dims__(kCS, 1, 1) __launch_bounds__(kGT * G, 1) lstm_t
       TC_MARK_S(4);
       mbar_wait(&bars[2], s & 1);               // only this warp polls; the other 15 sleep in the hardware barrier
     }
-    group_sync(grp);
+    group_sync(grp, kGT);
     TC_MARK_S(5);
     tc_fence_after();
     {
@@ -302,7 +311,7 @@ __global__ void __cluster_dims__(kCS, 1, 1) __launch_bounds__(kGT * G, 1) lstm_t
       }
     }
     tc_fence_before();
-    group_sync(grp);
+    group_sync(grp, kGT);
     TC_MARK_S(6);
     {
       float out = 0.f;
@@ -345,13 +354,19 @@ constexpr int kBG_RED = kBG_STAGE + 2 * 8 * kB_Tile;  // incoming partials [2 bu
 constexpr int kBG_INV = kBG_RED + 2 * 8 * kB_Tile;    // float inv_scale[NB]
 constexpr int kBG_BAR = kBG_INV + kNB * 4;            // red_full[2], mma_done
 constexpr int kBG_BYTES = kBG_BAR + 64;
-constexpr int bwd_smem_bytes(int G) { return G * kBG_BYTES + 16; }
+__host__ __device__ constexpr int bwd_group_bytes(int NB) { return 2 * (NB * 128 * 2) + 2 * (2 * 8 * NB * 32 * 4) + NB * 4 + 64; }
+constexpr int bwd_smem_bytes(int G, int NB) { return G * bwd_group_bytes(NB) + 16; }
 // tensor memory columns: [0, 128) accumulators (row group g: 64 g + 32 half + {0: D1, 16: D2}),
 // [128, 256) A_hi (half h at 128 + 64 h: k pair j of unit 128 h + lane at column j), [256, 384) A_lo
 constexpr int kTB_AHI = 128, kTB_ALO = 256, kTB_COLS = 512;
 
-template <int G>
-__global__ void __cluster_dims__(kCS, 1, 1) __launch_bounds__(kGT * G, 1) lstm_tc_bwd_kernel(PersistBwdArgs p) {
+template <int G, int NB>
+__global__ void __cluster_dims__(kCS, 1, 1) __launch_bounds__(32 * NB * G, 1) lstm_tc_bwd_kernel(PersistBwdArgs p) {
+  constexpr int kNB = NB, kGT = 32 * NB, kB_LBO = kNB * 16;
+  constexpr int kB_BPlane = kNB * 128 * 2, kB_Tile = kNB * 32 * 4, kBG_B = 0, kBG_STAGE = kBG_B + 2 * kB_BPlane,
+                kBG_RED = kBG_STAGE + 2 * 8 * kB_Tile, kBG_INV = kBG_RED + 2 * 8 * kB_Tile, kBG_BAR = kBG_INV + kNB * 4,
+                kBG_BYTES = kBG_BAR + 64;
+  static_assert(kBG_BYTES == bwd_group_bytes(NB), "shared-memory layout");
   extern __shared__ __align__(1024) uint8_t smem[];
   const int tid = threadIdx.x, grp = tid / kGT, gtid = tid % kGT, warp = gtid >> 5, lane = tid & 31, B = p.B, T = p.T;
   uint8_t* gsm = smem + grp * kBG_BYTES;
@@ -384,7 +399,7 @@ __global__ void __cluster_dims__(kCS, 1, 1) __launch_bounds__(kGT * G, 1) lstm_t
   cluster.sync();
   tc_fence_after();
   const uint32_t tmem0 = *tmem_slot;
-  if (grp == 0) {
+  if (grp == 0 && cgp < 4) {      // 16 warps: 4 TMEM lane quadrants x the 4 gates
     // resident weights, transposed, into tensor memory: A[m = unit j][k = g*32 + u] = W_hh[g*H + u0 + u][j].
     // This thread owns TMEM lane 32q + lane of both 128-unit halves and the k range of gate cgp (32 values).
     const float* W = p.w_hh[d] + (int64_t)(cgp * kH + u0) * kH;
@@ -409,7 +424,7 @@ __global__ void __cluster_dims__(kCS, 1, 1) __launch_bounds__(kGT * G, 1) lstm_t
   }
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem = tmem0 + 64 * grp;
+  const uint32_t tmem = tmem0 + 4 * kNB * grp;
   constexpr uint32_t kIdesc = make_idesc_f16(128, kNB);
   const int nsteps = T + ((p.d_h0 || p.d_c0) ? 1 : 0);
   unsigned amax_run = 0;           // bit pattern of max |dG| over this warp's row, all steps
@@ -464,7 +479,7 @@ __global__ void __cluster_dims__(kCS, 1, 1) __launch_bounds__(kGT * G, 1) lstm_t
         __syncwarp();
         mbar_wait(&bars[2], (s - 1) & 1);
       }
-      group_sync(grp);
+      group_sync(grp, kGT);
       tc_fence_after();
       // read-out: each partial value goes to the staging tile of the CTA that owns its unit
       float* st_out = stage + (size_t)buf * 8 * kNB * 32;
@@ -480,7 +495,7 @@ __global__ void __cluster_dims__(kCS, 1, 1) __launch_bounds__(kGT * G, 1) lstm_t
       }
       fence_proxy_async();
       tc_fence_before();
-      group_sync(grp);
+      group_sync(grp, kGT);
       if (gtid == 0) mbar_expect_tx(&bars[buf], 7 * kB_Tile);
       if (warp == 1 && lane < 7) {
         const int peer = lane + (lane >= rank ? 1 : 0);
@@ -489,7 +504,7 @@ __global__ void __cluster_dims__(kCS, 1, 1) __launch_bounds__(kGT * G, 1) lstm_t
         bulk_copy_to_peer(mapa_u32(dst, peer), src, kB_Tile, mapa_u32(smem_u32(&bars[buf]), peer));
       }
       if (warp == 0) mbar_wait(&bars[buf], ((s - 1) >> 1) & 1);
-      group_sync(grp);
+      group_sync(grp, kGT);
       const float* rin = red + (size_t)buf * 8 * kNB * 32 + prow * 32 + lane;
       rec = st_out[(size_t)rank * kNB * 32 + prow * 32 + lane];
 #pragma unroll
@@ -542,7 +557,7 @@ __global__ void __cluster_dims__(kCS, 1, 1) __launch_bounds__(kGT * G, 1) lstm_t
     }
     fence_proxy_async();
     tc_fence_before();
-    group_sync(grp);
+    group_sync(grp, kGT);
   }
   // max |dG| of this CTA -> its own slot (plain store: nothing to initialise, no memset node in front of the kernel);
   // the GEMMs that use dG as an operand take the maximum over the grid's slots
@@ -578,55 +593,61 @@ static cudaError_t launch_pdl(void (*kernel)(Args), int grid, int block, size_t 
   return cudaLaunchKernelEx(&cfg, kernel, args);
 }
 
-template <int G>
+template <int G, int NB>
 static int launch_tc_fwd(const PersistFwdArgs& a, cudaStream_t st) {
   static bool ready = false;
   if (!ready) {
-    DVAE_CUDA(cudaFuncSetAttribute(lstm_tc_fwd_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, fwd_smem_bytes(G)));
+    DVAE_CUDA(cudaFuncSetAttribute(lstm_tc_fwd_kernel<G, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, fwd_smem_bytes(G, NB)));
     ready = true;
   }
   PersistFwdArgs b = a;
-  b.n_slices = ceil_div(a.B, kNB * G);
+  b.n_slices = ceil_div(a.B, NB * G);
   b.d_off = 0;
-  DVAE_CUDA(launch_pdl(lstm_tc_fwd_kernel<G>, kCS * b.n_slices * a.D, kGT * G, fwd_smem_bytes(G), st, b));
+  DVAE_CUDA(launch_pdl(lstm_tc_fwd_kernel<G, NB>, kCS * b.n_slices * a.D, 32 * NB * G, fwd_smem_bytes(G, NB), st, b));
   DVAE_LAUNCH_CHECK();
   return DVAE_OK;
+}
+
+// rows per cluster: 16 (one 16-row group) while D * ceil(B / 16) clusters fit the 15 a B200 keeps resident; else 32, as two
+// 16-row groups whose phases interleave (one group's exchange and gate math under the other's MMAs).  DVAE_LSTM_GROUPS=32
+// selects ONE 32-row group instead (N = 32 MMAs, half the barriers): measured SLOWER at cfg 2 -- 3.54 vs 3.26 us per step of
+// the bidirectional encoder, step 1.415 vs 1.293 ms -- because a single group serialises its phases; kept as a tested A/B.
+static int tc_layout(int B, int D) {
+  const char* e = getenv("DVAE_LSTM_GROUPS");
+  const int want = e ? atoi(e) : 0;
+  if (want == 1 || want == 2 || want == 32) return want;
+  return D * ceil_div(B, kNB) <= 15 ? 1 : 2;
 }
 
 int tc_lstm_fwd(const PersistFwdArgs& a, cudaStream_t st) {
   // at most 15 clusters of 8 are co-resident on a B200 (profiles/probes/cluster_occupancy.cu).  One row group per
   // cluster (lowest step latency) while everything fits in one wave; two row groups per cluster otherwise, which
   // also keeps both directions of a bidirectional layer in ONE launch at B = 128.
-  const char* e = getenv("DVAE_LSTM_GROUPS");
-  const int want = e ? atoi(e) : (a.D * ceil_div(a.B, kNB) <= 15 ? 1 : 2);
-  return want >= 2 ? launch_tc_fwd<2>(a, st) : launch_tc_fwd<1>(a, st);
+  const int lay = tc_layout(a.B, a.D);
+  return lay == 32 ? launch_tc_fwd<1, 32>(a, st) : (lay == 2 ? launch_tc_fwd<2, 16>(a, st) : launch_tc_fwd<1, 16>(a, st));
 }
 
-template <int G>
+template <int G, int NB>
 static int launch_tc_bwd(const PersistBwdArgs& a, cudaStream_t st) {
   static bool ready = false;
   if (!ready) {
-    DVAE_CUDA(cudaFuncSetAttribute(lstm_tc_bwd_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd_smem_bytes(G)));
+    DVAE_CUDA(cudaFuncSetAttribute(lstm_tc_bwd_kernel<G, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd_smem_bytes(G, NB)));
     ready = true;
   }
   PersistBwdArgs b = a;
-  b.n_slices = ceil_div(a.B, kNB * G);
+  b.n_slices = ceil_div(a.B, NB * G);
   b.d_off = 0;
-  DVAE_CUDA(launch_pdl(lstm_tc_bwd_kernel<G>, kCS * b.n_slices * a.D, kGT * G, bwd_smem_bytes(G), st, b));
+  DVAE_CUDA(launch_pdl(lstm_tc_bwd_kernel<G, NB>, kCS * b.n_slices * a.D, 32 * NB * G, bwd_smem_bytes(G, NB), st, b));
   DVAE_LAUNCH_CHECK();
   return DVAE_OK;
 }
 
-static int bwd_groups(int B, int D) {
-  const char* e = getenv("DVAE_LSTM_GROUPS");
-  return (e ? atoi(e) : (D * ceil_div(B, kNB) <= 15 ? 1 : 2)) >= 2 ? 2 : 1;
-}
-
 int tc_lstm_bwd(const PersistBwdArgs& a, cudaStream_t st) {
-  return bwd_groups(a.B, a.D) == 2 ? launch_tc_bwd<2>(a, st) : launch_tc_bwd<1>(a, st);
+  const int lay = tc_layout(a.B, a.D);
+  return lay == 32 ? launch_tc_bwd<1, 32>(a, st) : (lay == 2 ? launch_tc_bwd<2, 16>(a, st) : launch_tc_bwd<1, 16>(a, st));
 }
 
 // CTAs of the backward launch = entries written to PersistBwdArgs::amax_out
-int tc_lstm_bwd_ctas(int B, int D) { return kCS * ceil_div(B, kNB * bwd_groups(B, D)) * D; }
+int tc_lstm_bwd_ctas(int B, int D) { return kCS * ceil_div(B, tc_layout(B, D) == 1 ? kNB : 2 * kNB) * D; }
 
 }  // namespace dvae

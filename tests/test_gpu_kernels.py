@@ -363,6 +363,15 @@ def test_lstm_step_kernels_still_cover_large_hidden(lib, L, monkeypatch):
     _lstm_case(lib, L, 4, 20, 32, 512, 2, True, False, seed=3)
 
 
+@pytest.mark.parametrize("groups,T,B,D,with_len,with_h0", [("32", 9, 50, 2, True, False), ("32", 7, 128, 1, False, True), ("32", 3, 33, 2, True, False),
+                                                           ("2", 9, 50, 2, True, False), ("1", 6, 40, 1, False, True)])
+def test_lstm_tc_row_group_layouts(lib, L, groups, T, B, D, with_len, with_h0, monkeypatch):
+    """tcgen05 LSTM kernels, H = 256: one 32-row group per cluster (the layout a bidirectional layer at B = 128 runs), two
+    16-row groups (round 1's), one 16-row group -- forced through DVAE_LSTM_GROUPS on shapes with partial row groups."""
+    monkeypatch.setenv("DVAE_LSTM_GROUPS", groups)
+    _lstm_case(lib, L, T, B, 48, 256, D, with_len, with_h0, seed=int(groups) * 7 + T + B)
+
+
 @pytest.mark.parametrize("D,with_len,with_h0", [(2, True, False), (1, False, True)])
 def test_lstm_simt_persistent_path_matches_oracle_too(lib, L, D, with_len, with_h0, monkeypatch):
     """DVAE_LSTM_IMPL=simt keeps the fp32 SIMT persistent-cluster kernels at H=256 (the tcgen05 kernels' A/B partner)."""
