@@ -32,7 +32,7 @@ void set_defer_joins(bool on);
 namespace {
 struct SideStreams {
   cudaStream_t s[3];
-  cudaEvent_t fork_ev, join_ev[3];
+  cudaEvent_t fork_ev, join_ev[3], mark_ev;
   bool ok = false;
   bool pending[3] = {false, false, false};     // detached work (deferred joins)
 };
@@ -43,7 +43,8 @@ SideStreams* side_streams() {
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
   if (!per_dev[dev]) {
     SideStreams* ss = new SideStreams();
-    ss->ok = cudaEventCreateWithFlags(&ss->fork_ev, cudaEventDisableTiming) == cudaSuccess;
+    ss->ok = cudaEventCreateWithFlags(&ss->fork_ev, cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&ss->mark_ev, cudaEventDisableTiming) == cudaSuccess;
     for (int i = 0; i < 3 && ss->ok; ++i)
       ss->ok = cudaStreamCreateWithFlags(&ss->s[i], cudaStreamNonBlocking) == cudaSuccess &&
                cudaEventCreateWithFlags(&ss->join_ev[i], cudaEventDisableTiming) == cudaSuccess;
@@ -82,6 +83,18 @@ int Fork::join() {
       used_[i] = false;
       ss->pending[i] = false;      // stream order: everything detached earlier on this side stream is covered too
     }
+  return DVAE_OK;
+}
+int Fork::mark(int i) {
+  if (!ok_ || !used_[i]) return DVAE_OK;
+  DVAE_CUDA(cudaEventRecord(side_streams()->mark_ev, side_streams()->s[i]));
+  marked_ = true;
+  return DVAE_OK;
+}
+int Fork::wait_mark() {
+  if (!ok_ || !marked_) return DVAE_OK;
+  DVAE_CUDA(cudaStreamWaitEvent(main_, side_streams()->mark_ev, 0));
+  marked_ = false;
   return DVAE_OK;
 }
 int Fork::join_or_defer() {

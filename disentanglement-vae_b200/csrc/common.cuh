@@ -56,9 +56,14 @@ class Fork {
   // this call -- e.g. a layer's weight-gradient GEMMs overlap the next layer's recurrence -- until
   // dvae_join_side_streams().  Only for work whose inputs / outputs nothing on the main stream touches before that.
   int join_or_defer();
+  // Ordering point for ONE piece of side work that the main stream needs soon while the rest of the fork stays detached:
+  // mark(i) right after enqueueing it on side(i), wait_mark() where the main stream consumes it.
+  int mark(int i);
+  int wait_mark();
  private:
   cudaStream_t main_;
   bool used_[3] = {false, false, false};
+  bool marked_ = false;
   bool ok_;
 };
 
@@ -79,6 +84,8 @@ struct GemmHints {
   // 128-row block / first k-block of this GEMM inside the planes, and the planes' k-blocks per row block
   const void* b_planes = nullptr;
   int b_tile0 = 0, b_kb0 = 0, b_kbtot = 0;
+  bool atomic_out = false;             // accumulate into C with atomics even without split-K (C zeroed by the caller): lets two
+                                       // GEMMs that add into the same output run concurrently
   bool c_zeroed = false;               // with beta == 0: C already holds zeros (a split-K GEMM then skips its memset node)
   int concurrency = 1;                 // GEMMs of this size the caller runs at the same time (sizes the CTA count to share the SMs)
 };

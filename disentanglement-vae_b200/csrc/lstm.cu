@@ -427,14 +427,28 @@ int lstm_seq_bwd_impl(const float* x, int64_t ldx, int T, int B, int I, int H, i
   // d_x accumulates over the directions (main stream, in order); the weight / bias gradients of each direction are
   // independent of it and of each other: parallel branches
   Fork fork(st);
+  // d_x of a bidirectional layer = sum of the two directions' products.  When the recurrence kernel already cleared d_x, both
+  // GEMMs add into it with atomics and run CONCURRENTLY (the reverse direction's on a side stream, marked so that only this
+  // one launch is waited for before d_x is consumed) instead of back to back on the critical path
+  const bool dx_pair = d_x && D == 2 && dx_zeroed && !force_simt_gemm() && tc_lstm_supported(H) &&
+                       !(getenv("DVAE_DX_PAIR") && getenv("DVAE_DX_PAIR")[0] == '0');
+  if (dx_pair) {
+    GemmHints ghx = gh;
+    ghx.c_zeroed = true; ghx.atomic_out = true; ghx.concurrency = 2;
+    int rc = linear_impl_ex(gates + slab, 4 * H, 0, w_ih[1], I, 1, d_x, lddx, T * B, I, 4 * H, nullptr, nullptr, 1.f, 0, ghx, fork.side(2));
+    if (rc) return rc;
+    if ((rc = fork.mark(2))) return rc;
+  }
   for (int d = 0; d < D; ++d) {
     const float* dG = gates + d * slab;
     int rc;
-    if (d_x) {
+    if (d_x && !(dx_pair && d == 1)) {
       GemmHints ghx = gh;
       ghx.c_zeroed = dx_zeroed;
-      rc = linear_impl_ex(dG, 4 * H, 0, w_ih[d], I, 1, d_x, lddx, T * B, I, 4 * H, nullptr, nullptr, d == 0 ? 0.f : 1.f, 0, ghx, st);
+      if (dx_pair) { ghx.atomic_out = true; ghx.concurrency = 2; }
+      rc = linear_impl_ex(dG, 4 * H, 0, w_ih[d], I, 1, d_x, lddx, T * B, I, 4 * H, nullptr, nullptr, (d == 0 && !dx_pair) ? 0.f : 1.f, 0, ghx, st);
       if (rc) return rc;
+      if (dx_pair && (rc = fork.wait_mark())) return rc;
     }
     if (d_w_ih && d_w_ih[d]) {
       rc = linear_impl_ex(dG, 4 * H, 1, x, ldx, 1, d_w_ih[d], I, 4 * H, I, T * B, nullptr, nullptr, 0.f, 0, gh, fork.side(0));

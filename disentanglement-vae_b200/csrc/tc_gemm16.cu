@@ -740,7 +740,7 @@ tc16_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const int r0 = m0 + quarter * 32;
           const int nr = min(32, p.M - r0);              // valid rows of this warp's 32-row band
           if (col < p.N && nr > 0) {
-            const bool split = gridDim.z > 1;
+            const bool split = gridDim.z > 1 || p.atomic_out;
             float badd = 0.f;
             if (p.mode == 0 && (!split || blockIdx.z == 0)) {
               if (p.bias) badd += __ldg(p.bias + col);
@@ -1023,6 +1023,7 @@ static void apply_hints(Params& p, const GemmHints& h) {
   p.a_amax = h.a_amax_bits; p.b_amax = h.b_amax_bits; p.a_amax_n = h.a_amax_n; p.b_amax_n = h.b_amax_n;
   p.a_scale = h.a_scale; p.b_scale = h.b_scale;
   p.alpha = 1.f; p.alpha_dev = nullptr;
+  p.atomic_out = h.atomic_out ? 1 : 0;
 }
 
 int linear(const float* A, int64_t lda, int trans_a, const float* B, int64_t ldb, int trans_b, float* C, int64_t ldc, int M,

@@ -29,6 +29,7 @@ struct Params {
   float* zero_buf2; int64_t zero2_n4;    //           (outputs of later split-K GEMMs; see tc_gemm16.cu)
   int mcast;                             // A-stationary pre-split kernels launched as CTA pairs: B stages fetched half each, multicast
   int b_presplit; int b_kbtot; int b_kb0;   // HYBRID: A through the converter ring, B (a weight) from registered planes: k-blocks per row block / first k-block
+  int atomic_out;                        // mode 0: atomicAdd into C even with one k-split (C zeroed by the caller)
   int no_astat;                          // pre-split operands in the dual-accumulator convention: never the A-stationary variant
   const float* c_row_scale;              // optional per-output-row factor [M] (mode 0)
   int presplit; int b_row0;     // b_row0: first B row of this call inside the B planes (a vocabulary chunk)
