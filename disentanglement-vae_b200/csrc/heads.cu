@@ -473,20 +473,21 @@ extern "C" int dvae_latent_heads_bwd(const float* ctx, int B, int C, int S, cons
   HeadsBwdArgs a{eps, w_dsc, labels, kl_w_dev, z, mu, logvar, dsc_logits, d_z, d_z_extra, d_mu_extra, d_logvar_extra, d_logits_extra, dp, dl, B};
   heads_bwd_elem_kernel<<<ceil_div((int64_t)B * Z, 256), 256, 0, st>>>(a, m);
   DVAE_LAUNCH_CHECK();
-  if (m.OD > 0) {
-    DVAE_REQUIRE(d_w_dsc && d_b_dsc, "dvae_latent_heads_bwd: discriminator gradient buffers missing");
-    int n_w = 0;
-    for (int s = 0; s < S; ++s) n_w += m.dout[s] * m.zdim[s];
-    heads_bwd_dsc_kernel<<<ceil_div((int64_t)(n_w + m.OD) * 32, 256), 256, 0, st>>>(dl, z, d_w_dsc, d_b_dsc, B, m, n_w);
-    DVAE_LAUNCH_CHECK();
-  }
-  // context2params: d_w = dp^T ctx, d_b = colsum(dp), d_ctx = dp W
+  // everything below that is not on the dp -> d_ctx chain (the encoder's backward waits for d_ctx only) runs on side stream 2:
+  // discriminator weight gradients, context2params weight and bias gradients.  Side streams 0 / 1 still hold the z2hidden ones.
   {
-    // side streams 0 / 1 are still running the z2hidden gradients; dp is ready on the main stream only
     Fork fork2(st);
+    if (m.OD > 0) {
+      DVAE_REQUIRE(d_w_dsc && d_b_dsc, "dvae_latent_heads_bwd: discriminator gradient buffers missing");
+      int n_w = 0;
+      for (int s = 0; s < S; ++s) n_w += m.dout[s] * m.zdim[s];
+      heads_bwd_dsc_kernel<<<ceil_div((int64_t)(n_w + m.OD) * 32, 256), 256, 0, fork2.side(2)>>>(dl, z, d_w_dsc, d_b_dsc, B, m, n_w);
+      DVAE_LAUNCH_CHECK();
+    }
+    // context2params: d_w = dp^T ctx, d_b = colsum(dp), d_ctx = dp W
     if ((rc = linear_impl_ex(dp, 2 * Z, 1, ctx, C, 1, d_w_c2p, C, 2 * Z, C, B, nullptr, nullptr, 0.f, 0, grad_hints, fork2.side(2)))) return rc;
+    if ((rc = colsum_impl(dp, 2 * Z, B, 2 * Z, d_b_c2p, 0.f, fork2.side(2)))) return rc;
     if ((rc = linear_impl_ex(dp, 2 * Z, 0, w_c2p, C, 1, d_ctx, C, B, C, 2 * Z, nullptr, nullptr, 0.f, 0, grad_hints, st))) return rc;
-    if ((rc = colsum_impl(dp, 2 * Z, B, 2 * Z, d_b_c2p, 0.f, st))) return rc;
     if ((rc = fork2.join_or_defer())) return rc;
   }
   if ((rc = fork.join_or_defer())) return rc;
