@@ -88,3 +88,21 @@ def grad_buckets3(model, flat_grad):
     if pos < n:
         gaps.append((pos, n))
     return [[flat_grad[dec[0]:dec[1]]], [flat_grad[a:b] for a, b in gaps if b > a], [flat_grad[low[0]:low[1]]]]
+
+
+def grad_buckets4(model, flat_grad):
+    """grad_buckets3 with the decoder bucket split in two: [0a] decoder.linear.* (W_out and its bias: final as soon as the
+    vocabulary backward has run, before any recurrence of the backward pass) and [0b] the decoder's embedding and LSTM
+    gradients.  The exchange of the 10 MB W_out gradient then starts ~250 us earlier in the step."""
+    b = grad_buckets3(model, flat_grad)
+    lay, named = model._layout, dict(model.named_parameters())
+    lin = [k for k in lay if k.startswith("decoder.linear.")]
+    if len(b[0]) != 1 or not lin:
+        return [[], b[0], b[1], b[2]]
+    dec = b[0][0]
+    base = (dec.data_ptr() - flat_grad.data_ptr()) // 4
+    lo = min(lay[k] for k in lin)
+    hi = max((lay[k] + named[k].numel() + 3) // 4 * 4 for k in lin)
+    if hi != base + dec.numel() or lo <= base:          # decoder.linear.* must be the tail of the decoder range
+        return [[], b[0], b[1], b[2]]
+    return [[flat_grad[lo:hi]], [flat_grad[base:lo]], b[1], b[2]]

@@ -190,12 +190,19 @@ class TrainEngine:
         pl, P, G, m = self.plan, self.model._P, self.G, self.model
         st = _lib.stream_ptr()
         cur = torch.cuda.current_stream()
-        if part in (None, 1):
+        # part 0 (data parallel only): forward + vocabulary backward on their own, so that W_out's gradient is exchanged first
+        if part == 0 or part is None or (part == 1 and not self._three_buckets()):
             h_top, hoist = self._forward()
             if callable(g_z):
                 g_z = g_z()
             self._g_z = g_z
-            g_top = pl.vocab_ce_bwd(P, G, h_top, self.inputs, self.lengths, None)
+            self._g_top = pl.vocab_ce_bwd(P, G, h_top, self.inputs, self.lengths, None)
+            self._hoist = hoist
+            if part == 0:
+                check(self.lib.dvae_join_side_streams(st), "dvae_join_side_streams")      # d_w runs on a side stream
+                return
+        if part in (None, 1):
+            g_top, hoist = self._g_top, self._hoist
             # weight-gradient GEMMs of each layer keep running on side streams while the next layer's recurrence starts
             check(self.lib.dvae_defer_joins(1), "dvae_defer_joins")
             try:
@@ -229,7 +236,7 @@ class TrainEngine:
                 check(self.lib.dvae_join_side_streams(st), "dvae_join_side_streams")
 
     def _three_buckets(self):
-        return (self.world > 1 and not self.plan.d.bow and self.plan.d.Le >= 2 and os.environ.get("DVAE_DP_BUCKETS", "3") == "3")
+        return (self.world > 1 and not self.plan.d.bow and self.plan.d.Le >= 2 and os.environ.get("DVAE_DP_BUCKETS", "4") != "2")
 
     def _optim(self):
         st = _lib.stream_ptr()
@@ -328,41 +335,32 @@ class TrainEngine:
             self._graphs[0].replay()          # one graph: forward, backward, clip + Adam
             return
         # data parallel: gradients are all-reduced in the order the backward pass finishes them, on a communication stream,
-        # under the rest of the backward pass: decoder.* | upper encoder layers + heads | encoder embedding + layer 0
+        # under the rest of the backward pass: W_out | decoder embedding + LSTM | upper encoder layers + heads | encoder
+        # embedding + layer 0 (four stages, four graphs); DVAE_DP_BUCKETS=2: decoder | everything else (round 1)
+        three = self._three_buckets()
         if self._buckets is None:
-            from .dist import grad_buckets3
-            self._buckets = grad_buckets3(self.model, self.grad)
+            from .dist import grad_buckets4, grad_buckets3
+            if three:
+                self._buckets = grad_buckets4(self.model, self.grad)
+            else:
+                b3 = grad_buckets3(self.model, self.grad)
+                self._buckets = [b3[0], b3[1] + b3[2]]
             self._comm = torch.cuda.Stream(device=self.device)
         cur = torch.cuda.current_stream()
-        three = self._three_buckets()
         if self.use_graph and self._graphs is None:
             self._capture()
         overlap = os.environ.get("DVAE_DP_OVERLAP", "1") != "0"
-
-        def run(part, gi):
+        stages = (0, 1, 2, 3) if three else (1, 2)
+        for gi, part in enumerate(stages):
             if self.use_graph:
                 self._graphs[gi].replay()
             else:
                 self._fwd_bwd(part)
-
-        def reduce_async(views):
-            self._comm.wait_stream(cur)
-            with torch.cuda.stream(self._comm):
-                for v in views:
-                    dist.all_reduce(v, op=dist.ReduceOp.SUM, group=self.pg)
-
-        run(1, 0)
-        if overlap:
-            reduce_async(self._buckets[0])
-        run(2, 1)
-        if three:
-            if overlap:
-                reduce_async(self._buckets[1])
-            run(3, 2)
-            if overlap:
-                reduce_async(self._buckets[2])
-        elif overlap:
-            reduce_async(self._buckets[1] + self._buckets[2])
+            if overlap and self._buckets[gi]:
+                self._comm.wait_stream(cur)
+                with torch.cuda.stream(self._comm):
+                    for v in self._buckets[gi]:
+                        dist.all_reduce(v, op=dist.ReduceOp.SUM, group=self.pg)
         if overlap:
             cur.wait_stream(self._comm)
         else:
@@ -391,7 +389,7 @@ class TrainEngine:
                 self._optim()
             graphs.append(g)
         else:                 # the all-reduces sit between the graphs (NCCL on its own stream)
-            for part in ((1, 2, 3) if self._three_buckets() else (1, 2)):
+            for part in ((0, 1, 2, 3) if self._three_buckets() else (1, 2)):
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g, stream=s):
                     self._fwd_bwd(part)

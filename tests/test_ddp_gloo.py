@@ -140,3 +140,23 @@ def test_three_bucket_split_covers_flat_gradient_exactly_once(dvae):
         want = 0 if name.startswith("decoder.") else (2 if name.startswith("encoder.embedding") or "_l0" in name else 1)
         got = marks[off:off + named[name].numel()]
         assert (got == want).all(), (name, want, got.unique())
+
+
+def test_four_stage_split_puts_the_output_layer_first(dvae):
+    import importlib
+    dvae_dist = importlib.import_module("disentanglement-vae_b200.dist")
+    p = dict(bow_encoder=False, embedding_dim=12, hidden_dim=16, num_rnn_layers=2, encoder_dropout=0.0, decoder_dropout=0.0,
+             bidirectional_encoder=True, latent_dims={"total": 7, "polarity": 1, "uncertainty": 2}, adversarial_loss=False, mi_loss=False)
+    vae = dvae.build_vae(p, 29, None, {"uncertainty": 3, "polarity": 1}, torch.device("cpu"), 2, 3)
+    flat = torch.zeros(vae._flat_numel)
+    b = dvae_dist.grad_buckets4(vae, flat)
+    assert len(b) == 4
+    for views in b:
+        for v in views:
+            v += 1.0
+    assert torch.equal(flat, torch.ones_like(flat))
+    named = dict(vae.named_parameters())
+    n_lin = sum(named[k].numel() for k in named if k.startswith("decoder.linear."))
+    assert sum(v.numel() for v in b[0]) >= n_lin and sum(v.numel() for v in b[0]) <= n_lin + 8
+    off = vae._layout["decoder.linear.weight"]
+    assert b[0][0].data_ptr() == flat.data_ptr() + 4 * off
