@@ -633,6 +633,11 @@ def main():
     loss_last = eng.losses_from(out.cpu())["total_loss"]
 
     if args.only_steps:
+        if world > 1:
+            st_ = torch.tensor([dev_ms, float(tok_sum)], dtype=torch.float64, device=dev)
+            mx_ = st_.clone(); dist.all_reduce(mx_, op=dist.ReduceOp.MAX)
+            dist.all_reduce(st_, op=dist.ReduceOp.SUM)
+            dev_ms, tok_sum = float(mx_[0]), float(st_[1])
         if rank == 0:
             print(json.dumps({"metric": "train_tokens_per_sec", "value": tok_sum / (dev_ms * 1e-3), "unit": "tokens/s", "n_gpus": world,
                               "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps,

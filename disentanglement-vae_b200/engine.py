@@ -235,6 +235,16 @@ class TrainEngine:
             finally:
                 check(self.lib.dvae_join_side_streams(st), "dvae_join_side_streams")
 
+    def _ensure_buckets(self):
+        if self._buckets is None:
+            from .dist import grad_buckets4, grad_buckets3
+            if self._three_buckets():
+                self._buckets = grad_buckets4(self.model, self.grad)
+            else:
+                b3 = grad_buckets3(self.model, self.grad)
+                self._buckets = [b3[0], b3[1] + b3[2]]
+            self._comm = torch.cuda.Stream(device=self.device)
+
     def _three_buckets(self):
         return (self.world > 1 and not self.plan.d.bow and self.plan.d.Le >= 2 and os.environ.get("DVAE_DP_BUCKETS", "4") != "2")
 
@@ -338,14 +348,7 @@ class TrainEngine:
         # under the rest of the backward pass: W_out | decoder embedding + LSTM | upper encoder layers + heads | encoder
         # embedding + layer 0 (four stages, four graphs); DVAE_DP_BUCKETS=2: decoder | everything else (round 1)
         three = self._three_buckets()
-        if self._buckets is None:
-            from .dist import grad_buckets4, grad_buckets3
-            if three:
-                self._buckets = grad_buckets4(self.model, self.grad)
-            else:
-                b3 = grad_buckets3(self.model, self.grad)
-                self._buckets = [b3[0], b3[1] + b3[2]]
-            self._comm = torch.cuda.Stream(device=self.device)
+        self._ensure_buckets()
         cur = torch.cuda.current_stream()
         if self.use_graph and self._graphs is None:
             self._capture()
