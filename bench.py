@@ -657,15 +657,21 @@ def main():
         assert replicas_identical, "data-parallel replicas diverged: parameters differ across ranks after the timed steps"
 
     # ---- end-to-end leg: host buffers in, losses out, through the public engine API ----
+    # (TrainEngine.train_steps: every step stages its HOST batch into pinned memory, ONE H2D copy, the captured step, ONE D2H
+    #  read of the loss block; batch k + 1 is staged while the GPU runs step k, losses are consumed two steps behind)
     barrier()
     t0 = time.perf_counter()
-    e2e_tok = 0
-    for i in range(args.steps):
-        j = i % len(hpool)
-        eng.step_host(*hpool[j])
-        e2e_tok += tokens[j]
+    e2e_tok = sum(tokens[i % len(hpool)] for i in range(args.steps))
+    e2e_losses = [L["total_loss"] for L in eng.train_steps(hpool[i % len(hpool)] for i in range(args.steps))]
     barrier()
     e2e_s = time.perf_counter() - t0
+    assert len(e2e_losses) == args.steps and all(np.isfinite(e2e_losses))
+    # the same, one synchronous call per step (step_host: stage, upload, step, read back, wait)
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        eng.step_host(*hpool[i % len(hpool)])
+    barrier()
+    e2e_sync_s = time.perf_counter() - t0
 
     # ---- end-to-end through the DROP-IN plugin call pattern (INTEGRATION.md's two-import swap), rank 0 of a 1-GPU run ----
     dropin = None
@@ -715,13 +721,13 @@ def main():
     if rank == 0 and world == 1 and not args.no_trace:
         trace = gemm_class_trace(eng, dpool[0])
 
-    stats = torch.tensor([dev_ms, e2e_s, float(tok_sum), float(e2e_tok)], dtype=torch.float64, device=dev)
+    stats = torch.tensor([dev_ms, e2e_s, float(tok_sum), float(e2e_tok), e2e_sync_s], dtype=torch.float64, device=dev)
     if world > 1:
         mx = stats.clone()
         dist.all_reduce(mx, op=dist.ReduceOp.MAX)
         sm = stats.clone()
         dist.all_reduce(sm, op=dist.ReduceOp.SUM)
-        dev_ms, e2e_s = float(mx[0]), float(mx[1])
+        dev_ms, e2e_s, e2e_sync_s = float(mx[0]), float(mx[1]), float(mx[4])
         tok_sum, e2e_tok = float(sm[2]), float(sm[3])
     if rank != 0:
         if world > 1:
@@ -807,7 +813,10 @@ def main():
             "padded_tokens_per_sec": B * world * T * args.steps / (dev_ms * 1e-3),
             "e2e": {"value": e2e_tok / e2e_s, "unit": "tokens/s", "h2d_bytes_per_step": eng.h2d_bytes_per_step,
                     "d2h_bytes_per_step": eng.d2h_bytes_per_step, "ms_per_step": e2e_s * 1e3 / args.steps,
-                    "path": "TrainEngine.step_host: host tensors -> pinned -> H2D -> captured step -> D2H of the loss block"},
+                    "path": "TrainEngine.train_steps(host batches): per step host tensors -> pinned block -> one H2D -> captured step -> "
+                            "one D2H of the loss block; pipelined (losses consumed two steps behind)",
+                    "ms_per_step_synchronous": e2e_sync_s * 1e3 / args.steps,
+                    "synchronous_path": "TrainEngine.step_host per batch (waits for every step's losses)"},
             "e2e_dropin": dropin,
             "gpu_launches": int(launches_per_step * args.steps), "launches_per_step": int(launches_per_step),
             "roofline": roof, "clocks": clk, "loss_after_warmup": loss_warm, "loss_last": loss_last,

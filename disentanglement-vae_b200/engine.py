@@ -75,25 +75,43 @@ class TrainEngine:
         self.kl_w = torch.zeros(max(d.S, 1), **f32)
         self.sumsq = torch.zeros(1, **f32)
         self.red_ws = torch.zeros(1032, **f32)
-        self.inputs = torch.zeros(B, T, device=self.device, dtype=torch.int64)
-        self.lengths = torch.zeros(B, device=self.device, dtype=torch.int64)
-        self.labels = torch.zeros(self.n_dsc, B, **f32)
         T1 = max(T - 1, 1)
-        self.coins = torch.ones(T1, device=self.device, dtype=torch.int32)          # 1 = teacher-forced step
+        # Everything the host sends per step lives in ONE device block (typed views below) filled by ONE H2D copy from a ring
+        # of pinned host blocks: token ids, lengths, Philox seed, labels, Adam / KL scalars, teacher-forcing coins.  An
+        # asynchronous H2D copy reads host memory when it executes, so a slot is rewritten only after the event recorded
+        # behind its last use has completed (un-synchronised step_resident calls saw a later step's scalars).
+        lay, off = {}, 0
+        for name, nbytes in (("inputs", B * T * 8), ("lengths", B * 8), ("seed", 8), ("labels", self.n_dsc * B * 4),
+                             ("scal", (8 + max(d.S, 1)) * 4), ("coins", T1 * 4)):
+            lay[name] = (off, nbytes)
+            off = (off + nbytes + 15) // 16 * 16
+        self._stage_bytes, self._stage_lay = off, lay
+        self.d_stage = torch.zeros(off, device=self.device, dtype=torch.uint8)
+
+        def view(buf, name, dtype, *shape):
+            o, n = lay[name]
+            return buf[o:o + n].view(dtype).view(*shape)
+        self.inputs = view(self.d_stage, "inputs", torch.int64, B, T)
+        self.lengths = view(self.d_stage, "lengths", torch.int64, B)
+        self.labels = view(self.d_stage, "labels", torch.float32, self.n_dsc, B)
+        self.d_scal = view(self.d_stage, "scal", torch.float32, 8 + max(d.S, 1))
+        self.coins = view(self.d_stage, "coins", torch.int32, T1)          # 1 = teacher-forced step
+        self.coins.fill_(1)
+        self.plan.seed_dev = view(self.d_stage, "seed", torch.int64, 1)     # the plan's kernels read the seed from here
         self.preds = torch.zeros(B, T, device=self.device, dtype=torch.int64) if self.sampled else None
-        # pinned staging for the end-to-end (host buffers in, loss out) entry point
-        self.h_inputs = torch.zeros(B, T, dtype=torch.int64).pin_memory()
-        self.h_lengths = torch.zeros(B, dtype=torch.int64).pin_memory()
-        self.h_labels = torch.zeros(self.n_dsc, B, dtype=torch.float32).pin_memory()
-        self.h_out = torch.zeros(self.plan.out.numel(), dtype=torch.float32).pin_memory()
-        # the per-step scalar block is staged through a RING of pinned slots: an asynchronous H2D copy reads host memory
-        # when it executes, so a slot is rewritten only after the event recorded behind its last copy has completed
         ns = self.NSLOT
-        self.h_scal = torch.zeros(ns, 8 + max(d.S, 1), dtype=torch.float32).pin_memory()
-        self.h_seed = torch.zeros(ns, 1, dtype=torch.int64).pin_memory()
-        self.h_coins = torch.ones(ns, T1, dtype=torch.int32).pin_memory()
+        self.h_stage = torch.zeros(ns, off, dtype=torch.uint8).pin_memory()
+        self.h_outs = torch.zeros(ns, self.plan.out.numel(), dtype=torch.float32).pin_memory()
+        self._hv = [{k: view(self.h_stage[i], k, dt, *shp).numpy() for k, dt, shp in
+                     (("inputs", torch.int64, (B, T)), ("lengths", torch.int64, (B,)), ("seed", torch.int64, (1,)),
+                      ("labels", torch.float32, (self.n_dsc, B)), ("scal", torch.float32, (8 + max(d.S, 1),)),
+                      ("coins", torch.int32, (T1,)))} for i in range(ns)]
+        for hv in self._hv:
+            hv["coins"][:] = 1
+            hv["lengths"][:] = 1
+        self.h_out = self.h_outs[0]
         self._slot_ev = [None] * ns
-        self.d_scal = torch.zeros(8 + max(d.S, 1), **f32)
+        self._slot = -1
         self.step_idx = 0          # global step: the cyclic-KL schedule's `step` (run.py:215)
         self.adam_step = 0         # optimizer steps taken (Adam bias correction); differs from step_idx after a resume
         base = int(params.get("random_seed", 10)) if seed is None else int(seed)
@@ -408,68 +426,103 @@ class TrainEngine:
         self._graphs = tuple(graphs)
 
     # ---- per-step host scalars -----------------------------------------------------------------
-    def _stage_scalars(self):
-        """Fill the next pinned slot (Adam hyper-parameters and step count, KL weights, dropout / noise seed, teacher-forcing
-        coins) and enqueue its upload.  The slot is reused NSLOT steps later, after the event behind this upload."""
-        slot = self._next_slot()
-        ev = self._slot_ev[slot]
+    def _acquire_slot(self):
+        self._slot = (self._slot + 1) % self.NSLOT
+        ev = self._slot_ev[self._slot]
         if ev is not None:
             ev.synchronize()
-        step = self.step_idx
-        h = self.h_scal[slot]
-        h[0], h[1], h[2], h[3], h[4] = self.lr, 0.9, 0.999, 1e-8, float(self.adam_step + 1)
+        return self._slot
+
+    def _fill_scalars(self, hv):
+        """Adam hyper-parameters and step count, KL weights (cyclic value of this global step), dropout / noise seed and the
+        teacher-forcing coins of this step, written into a pinned host block."""
+        sc = hv["scal"]
+        sc[0], sc[1], sc[2], sc[3], sc[4] = self.lr, 0.9, 0.999, 1e-8, float(self.adam_step + 1)
         for i, n in enumerate(self.d.space_names):
             w = self.lambdas[n] if n in self.lambdas else self.lambdas["default"]
             if w == "cyclic":
-                w = get_cyclic_kl_weight(step, self.total_steps)
-            h[8 + i] = float(w)
-        self.h_seed[slot, 0] = int(torch.randint(0, 2 ** 62, (1,), generator=self._gen))
-        self.d_scal.copy_(h, non_blocking=True)
-        self.plan.seed_dev.copy_(self.h_seed[slot], non_blocking=True)
-        if self.sampled:
-            c = self.h_coins[slot]
-            for i in range(c.numel()):      # one coin per decoding step, shared by the batch (vae/model.py:463)
+                w = get_cyclic_kl_weight(self.step_idx, self.total_steps)
+            sc[8 + i] = float(w)
+        hv["seed"][0] = int(torch.randint(0, 2 ** 62, (1,), generator=self._gen))
+        if self.sampled:      # one coin per decoding step, shared by the batch (vae/model.py:463)
+            c = hv["coins"]
+            for i in range(c.shape[0]):
                 c[i] = 1 if self._pyrand.random() < self.tf_prob else 0
-            self.coins.copy_(c, non_blocking=True)
+
+    def _upload(self, slot, names=None):
+        """H2D of a pinned block: the whole block (one copy), or only the named fields (device-resident batches)."""
+        if names is None:
+            self.d_stage.copy_(self.h_stage[slot], non_blocking=True)
+        else:
+            for k in names:
+                o, n = self._stage_lay[k]
+                self.d_stage[o:o + n].copy_(self.h_stage[slot, o:o + n], non_blocking=True)
+
+    def _release_slot(self, slot):
         ev = torch.cuda.Event()
         ev.record()
         self._slot_ev[slot] = ev
-
-    def _next_slot(self):
-        self._slot = (getattr(self, "_slot", -1) + 1) % self.NSLOT
-        return self._slot
 
     # ---- public entry points -------------------------------------------------------------------
     def step_resident(self, inputs_dev, lengths_dev, labels_dev):
         """One train step on a batch already in HBM; returns the device result block
         (plan.out: [0] weighted KL, [1] KL, [2] dsc loss, [3..] per space, [27] reconstruction).
         Asynchronous: may be called back to back without synchronising."""
-        self._stage_scalars()
+        slot = self._acquire_slot()
+        self._fill_scalars(self._hv[slot])
+        self._upload(slot, ("seed", "scal", "coins") if self.sampled else ("seed", "scal"))
         self.inputs.copy_(inputs_dev, non_blocking=True)
         self.lengths.copy_(lengths_dev, non_blocking=True)
         self.labels.copy_(labels_dev, non_blocking=True)
         self._run()
+        self._release_slot(slot)
         self.step_idx += 1
         self.adam_step += 1
         return self.plan.out
 
-    def step_host(self, inputs, lengths, labels):
-        """End-to-end step: HOST tensors in (inputs [B,T] int64, lengths [B] int64, labels {name: [B,1]}),
-        python floats out.  Copies host->pinned->device, runs the step, reads the loss block back."""
-        self.h_inputs.copy_(inputs)
-        self.h_lengths.copy_(lengths)
+    def _enqueue_host_step(self, inputs, lengths, labels):
+        """Stage one HOST batch into the next pinned block, enqueue its single H2D copy, the step and the D2H copy of the
+        result block; returns the slot (its event completes when the losses are in h_outs[slot])."""
+        slot = self._acquire_slot()
+        hv = self._hv[slot]
+        hv["inputs"][...] = inputs.numpy() if torch.is_tensor(inputs) else inputs
+        hv["lengths"][...] = lengths.numpy() if torch.is_tensor(lengths) else lengths
         for i, n in enumerate(self.label_names):
-            self.h_labels[i].copy_(labels[n].reshape(-1))
-        self._stage_scalars()
-        self.inputs.copy_(self.h_inputs, non_blocking=True)
-        self.lengths.copy_(self.h_lengths, non_blocking=True)
-        self.labels.copy_(self.h_labels, non_blocking=True)
+            y = labels[n]
+            hv["labels"][i] = (y.numpy() if torch.is_tensor(y) else y).reshape(-1)
+        self._fill_scalars(hv)
+        self._upload(slot)
         self._run()
-        self.h_out.copy_(self.plan.out, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+        self.h_outs[slot].copy_(self.plan.out, non_blocking=True)
+        self._release_slot(slot)
         self.step_idx += 1
         self.adam_step += 1
+        return slot
+
+    def step_host(self, inputs, lengths, labels):
+        """End-to-end step: HOST tensors in (inputs [B,T] int64, lengths [B] int64, labels {name: [B,1]}),
+        python floats out.  One H2D copy of the staged block, the step, one D2H read of the loss block, then a wait."""
+        slot = self._enqueue_host_step(inputs, lengths, labels)
+        self._slot_ev[slot].synchronize()
+        self.h_out = self.h_outs[slot]
         return self.losses_from(self.h_out)
+
+    def train_steps(self, batches, lag=2):
+        """Pipelined training loop over an iterable of HOST batches (inputs, lengths, labels): yields the loss dict of every
+        step, in order, `lag` steps behind the step being enqueued -- batch k + 1 is staged and uploaded while the GPU runs
+        step k, and nothing waits for the device except the read of a result that is `lag` steps old.  Same arithmetic as
+        calling step_host() per batch (run.py:217-262); `lag` must be smaller than NSLOT."""
+        assert 0 <= lag < self.NSLOT
+        pending = []
+        for inputs, lengths, labels in batches:
+            pending.append(self._enqueue_host_step(inputs, lengths, labels))
+            if len(pending) > lag:
+                slot = pending.pop(0)
+                self._slot_ev[slot].synchronize()
+                yield self.losses_from(self.h_outs[slot])
+        for slot in pending:
+            self._slot_ev[slot].synchronize()
+            yield self.losses_from(self.h_outs[slot])
 
     def losses_from(self, out):
         S, NS = self.d.S, _lib.HEADS_NSCALARS
@@ -559,9 +612,8 @@ class TrainEngine:
 
     @property
     def h2d_bytes_per_step(self):
-        n = (self.h_inputs.numel() + self.h_lengths.numel() + 1) * 8 + (self.h_labels.numel() + self.h_scal.size(1)) * 4
-        return n + (self.h_coins.size(1) * 4 if self.sampled else 0)
+        return self._stage_bytes
 
     @property
     def d2h_bytes_per_step(self):
-        return self.h_out.numel() * 4
+        return self.h_outs.size(1) * 4

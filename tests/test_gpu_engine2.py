@@ -233,3 +233,27 @@ def test_engine_adversarial_mi_step_matches_reference_golden(dvae, engine_mod):
     for n, est in vae.mi_estimators.items():
         for k, v in est.state_dict().items():
             assert np.abs(v.cpu().numpy() - g[f"mi_after.{n}.{k}"]).max() < 2e-6, (n, k)
+
+
+def test_pipelined_train_steps_equal_synchronous_steps(dvae, engine_mod):
+    """TrainEngine.train_steps (batch k + 1 staged while step k runs, losses read two steps behind) takes exactly the steps
+    of one step_host call per batch: same per-step losses under the same seed, every batch consumed, in order."""
+    V, B, T = 500, 24, 9
+    dev = torch.device("cuda")
+    gen = torch.Generator().manual_seed(3)
+    batches = [_batch(gen, B, T, V) for _ in range(7)]
+    runs = []
+    for mode in ("sync", "pipe"):
+        dvae.set_seed(10)
+        vae = dvae.build_vae(_cfg(), V, None, {"uncertainty": 1, "polarity": 1}, dev, 2, 3)
+        vae.train()
+        eng = engine_mod.TrainEngine(vae, _cfg(), B, T, total_steps=40, use_graph=True, seed=5)
+        if mode == "sync":
+            runs.append([eng.step_host(*b)["total_loss"] for b in batches])
+        else:
+            runs.append([L["total_loss"] for L in eng.train_steps(iter(batches))])
+        assert eng.adam_step == 7 and eng.step_idx == 7
+    a, b = runs
+    assert len(a) == len(b) == 7 and len(set(round(x, 3) for x in b)) == 7
+    for x, y in zip(a, b):
+        assert abs(x - y) <= 1e-4 * abs(x), (a, b)
