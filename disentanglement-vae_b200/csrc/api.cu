@@ -45,8 +45,13 @@ SideStreams* side_streams() {
     SideStreams* ss = new SideStreams();
     ss->ok = cudaEventCreateWithFlags(&ss->fork_ev, cudaEventDisableTiming) == cudaSuccess &&
              cudaEventCreateWithFlags(&ss->mark_ev, cudaEventDisableTiming) == cudaSuccess;
+    // side streams 0 / 1 carry the weight-gradient GEMMs that run beside the next layer's recurrence: lowest priority, so
+    // that CTAs of the caller's (critical-path) stream are placed first whenever SMs free up (DVAE_SIDE_PRIO=0: default priority)
+    int least = 0, greatest = 0;
+    const char* pe = getenv("DVAE_SIDE_PRIO");
+    const bool low = !(pe && pe[0] == '0') && cudaDeviceGetStreamPriorityRange(&least, &greatest) == cudaSuccess;
     for (int i = 0; i < 3 && ss->ok; ++i)
-      ss->ok = cudaStreamCreateWithFlags(&ss->s[i], cudaStreamNonBlocking) == cudaSuccess &&
+      ss->ok = cudaStreamCreateWithPriority(&ss->s[i], cudaStreamNonBlocking, (low && i < 2) ? least : 0) == cudaSuccess &&
                cudaEventCreateWithFlags(&ss->join_ev[i], cudaEventDisableTiming) == cudaSuccess;
     per_dev[dev] = ss;
   }

@@ -84,6 +84,9 @@ struct GemmHints {
   // 128-row block / first k-block of this GEMM inside the planes, and the planes' k-blocks per row block
   const void* b_planes = nullptr;
   int b_tile0 = 0, b_kb0 = 0, b_kbtot = 0;
+  int max_ctas = 0;                    // > 0: background GEMM (runs beside a latency-critical kernel): keep the grid at or below
+                                       // this many CTAs -- a tensor-core GEMM CTA takes a whole SM (227 KB of shared memory), so a
+                                       // machine-filling side GEMM keeps the main stream's next kernel from being scheduled at all
   bool atomic_out = false;             // accumulate into C with atomics even without split-K (C zeroed by the caller): lets two
                                        // GEMMs that add into the same output run concurrently
   bool c_zeroed = false;               // with beta == 0: C already holds zeros (a split-K GEMM then skips its memset node)

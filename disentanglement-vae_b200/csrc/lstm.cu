@@ -424,6 +424,14 @@ int lstm_seq_bwd_impl(const float* x, int64_t ldx, int T, int B, int I, int H, i
   gh.a_wide = true;
   gh.a_amax_bits = amax;
   gh.a_amax_n = amax_n;
+  // the weight-gradient GEMMs below run on side streams beside the NEXT layer's recurrence (deferred joins): sized to leave
+  // that recurrence its SMs (64 at cfg 2).  Two machine-filling split-K grids (2 x 144 CTAs) kept the recurrence kernel
+  // from being scheduled for 25-40 us at every layer boundary.
+  GemmHints gh_bg = gh;
+  {
+    static const int cap = [] { const char* e = getenv("DVAE_DW_MAX_CTAS"); return e ? atoi(e) : 48; }();
+    gh_bg.max_ctas = cap;
+  }
   // d_x accumulates over the directions (main stream, in order); the weight / bias gradients of each direction are
   // independent of it and of each other: parallel branches
   Fork fork(st);
@@ -451,7 +459,7 @@ int lstm_seq_bwd_impl(const float* x, int64_t ldx, int T, int B, int I, int H, i
       if (dx_pair && (rc = fork.wait_mark())) return rc;
     }
     if (d_w_ih && d_w_ih[d]) {
-      rc = linear_impl_ex(dG, 4 * H, 1, x, ldx, 1, d_w_ih[d], I, 4 * H, I, T * B, nullptr, nullptr, 0.f, 0, gh, fork.side(0));
+      rc = linear_impl_ex(dG, 4 * H, 1, x, ldx, 1, d_w_ih[d], I, 4 * H, I, T * B, nullptr, nullptr, 0.f, 0, gh_bg, fork.side(0));
       if (rc) return rc;
     }
     if (d_w_hh && d_w_hh[d]) {
@@ -461,13 +469,13 @@ int lstm_seq_bwd_impl(const float* x, int64_t ldx, int T, int B, int I, int H, i
       if (T > 1) {
         const float* dGs = d == 0 ? dG + (int64_t)B * 4 * H : dG;
         const float* hp = d == 0 ? hs + d * H : hs + (int64_t)B * ldhs + d * H;
-        rc = linear_impl_ex(dGs, 4 * H, 1, hp, ldhs, 1, d_w_hh[d], H, 4 * H, H, (T - 1) * B, nullptr, nullptr, 0.f, 0, gh, s1);
+        rc = linear_impl_ex(dGs, 4 * H, 1, hp, ldhs, 1, d_w_hh[d], H, 4 * H, H, (T - 1) * B, nullptr, nullptr, 0.f, 0, gh_bg, s1);
         if (rc) return rc;
         wrote = true;
       }
       if (h0) {
         const float* dG0 = d == 0 ? dG : dG + (int64_t)(T - 1) * B * 4 * H;
-        rc = linear_impl_ex(dG0, 4 * H, 1, h0 + d * dir0, ld0, 1, d_w_hh[d], H, 4 * H, H, B, nullptr, nullptr, wrote ? 1.f : 0.f, 0, gh, s1);
+        rc = linear_impl_ex(dG0, 4 * H, 1, h0 + d * dir0, ld0, 1, d_w_hh[d], H, 4 * H, H, B, nullptr, nullptr, wrote ? 1.f : 0.f, 0, gh_bg, s1);
         if (rc) return rc;
         wrote = true;
       }

@@ -1051,6 +1051,7 @@ int linear(const float* A, int64_t lda, int trans_a, const float* B, int64_t ldb
     for (int s2 = 1; s2 <= 16 && s2 <= nkb / 4; ++s2) {
       const int kbs = ceil_div(nkb, s2), se = ceil_div(nkb, kbs);
       if (se != s2) continue;
+      if (hints.max_ctas > 0 && s2 > 1 && tiles * se > hints.max_ctas) break;
       const int waves = ceil_div(tiles * se, 148);
       const float t = waves * (kbs * t_kb + (se > 1 ? 6.f : 4.f)) + (se > 1 ? 2.f : 0.f);
       if (t < best * 0.95f) { best = t; splits = se; }      // a larger split count has to be clearly better
@@ -1071,8 +1072,9 @@ int linear(const float* A, int64_t lda, int trans_a, const float* B, int64_t ldb
   // more tiles than SMs: a run of N tiles per CTA, so that the next tile's main loop hides this one's epilogue and the
   // grid (times the sibling GEMMs the caller runs concurrently, e.g. the two directions' input projections) is one wave
   const int conc = hints.concurrency > 1 ? hints.concurrency : 1;
-  if (splits == 1 && tiles * conc > 148 && ceil_div(N, BN) >= 2) {
-    int tpc = ceil_div(tiles * conc, 148);
+  const int sm_budget = hints.max_ctas > 0 ? hints.max_ctas : 148;
+  if (splits == 1 && tiles * conc > sm_budget && ceil_div(N, BN) >= 2) {
+    int tpc = ceil_div(tiles * conc, sm_budget);
     if (tpc < 2) tpc = 2;
     if (tpc > ceil_div(N, BN)) tpc = ceil_div(N, BN);
     p.tiles_per_cta = tpc;
@@ -1086,7 +1088,7 @@ int linear(const float* A, int64_t lda, int trans_a, const float* B, int64_t ldb
 // is split once per call (its weights).  c_row_scale: optional per-row output factor (device, [M]).
 int linear_planes(const void* a_planes, const void* b_planes, float* C, int64_t ldc, int M, int N, int K, const float* bias,
                   float beta, int act, float a_scale, float b_scale, const float* c_row_scale, bool c_zeroed, int max_splits,
-                  cudaStream_t st, int b_kb0, int b_kbtot) {
+                  cudaStream_t st, int b_kb0, int b_kbtot, int max_ctas) {
   DVAE_REQUIRE(a_planes && b_planes && C && M > 0 && N > 0 && K > 0, "tc16 linear_planes: bad argument");
   Params p = {};
   p.presplit = 1; p.no_astat = 1; p.a_planes = a_planes; p.b_planes = b_planes; p.a_rows = M; p.b_rows = N;
@@ -1102,6 +1104,7 @@ int linear_planes(const void* a_planes, const void* b_planes, float* C, int64_t 
     for (int s2 = 1; s2 <= max_splits && s2 <= nkb / 4; ++s2) {
       const int kbs = ceil_div(nkb, s2), se = ceil_div(nkb, kbs);
       if (se != s2) continue;
+      if (max_ctas > 0 && s2 > 1 && tiles * se > max_ctas) break;
       const int waves = ceil_div(tiles * se, 148);
       const float t = waves * (kbs * t_kb + (se > 1 ? 5.f : 4.f)) + (se > 1 ? 1.5f : 0.f);
       if (t < best * 0.95f) { best = t; splits = se; }
@@ -1117,8 +1120,9 @@ int linear_planes(const void* a_planes, const void* b_planes, float* C, int64_t 
       DVAE_LAUNCH_CHECK();
     }
   }
-  if (splits == 1 && tiles > 148 && ceil_div(N, BN) >= 2) {
-    int tpc = ceil_div(tiles, 148);
+  const int sm_budget = max_ctas > 0 ? max_ctas : 148;
+  if (splits == 1 && tiles > sm_budget && ceil_div(N, BN) >= 2) {
+    int tpc = ceil_div(tiles, sm_budget);
     if (tpc < 2) tpc = 2;
     if (tpc > ceil_div(N, BN)) tpc = ceil_div(N, BN);
     p.tiles_per_cta = tpc;

@@ -57,7 +57,7 @@ int64_t plane_floats(int R, int K);
 int split_planes(const float* X, int64_t ld, int R, int K, float scale, void* planes, cudaStream_t st, bool force_dual = false);
 int linear_planes(const void* a_planes, const void* b_planes, float* C, int64_t ldc, int M, int N, int K, const float* bias,
                   float beta, int act, float a_scale, float b_scale, const float* c_row_scale, bool c_zeroed, int max_splits,
-                  cudaStream_t st, int b_kb0 = 0, int b_kbtot = 0);
+                  cudaStream_t st, int b_kb0 = 0, int b_kbtot = 0, int max_ctas = 0);
 // Weight-plane registry (api.cu): GEMMs whose B operand is a registered weight matrix (or a 128-row / 32-column aligned
 // block of it) fetch B as pre-split planes by bulk copy; only A goes through the converter warps.
 constexpr int kMaxPlaneEntries = 24;

@@ -521,8 +521,9 @@ extern "C" int dvae_vocab_ce_bwd(const float* h, int64_t ldh, int T1, int B, int
       if ((rc = tc16::linear_planes(pa, wT_planes, d_h, lddh, N, H, vc, nullptr, chunk ? 1.f : 0.f, 0, ph.a_scale, 1.f, nullptr, zh, 16, st,
                                     v0 / 32, wT_kbtot))) return rc;
       // d_w[v0:v0+vc, :] = P^T [vc,N] . h [N,H]: A = transposed P planes, B = planes of h^T
+      static const int dw_cap = [] { const char* e = getenv("DVAE_VOCAB_DW_MAX_CTAS"); return e ? atoi(e) : 0; }();      // measured: capping this one costs 17 us (it outlasts the recurrence it runs beside)
       if ((rc = tc16::linear_planes(pt, hT_planes, d_w + (int64_t)v0 * H, H, vc, H, N, nullptr, 0.f, 0, ph.a_scale, 1.f, nullptr, zw, 16,
-                                    fork.side(0), 0, 0))) return rc;
+                                    fork.side(0), 0, 0, dw_cap))) return rc;
       if (chunk + 1 == nchunks || chunk + 1 >= nbuf)
         if ((rc = fork.join())) return rc;
       continue;
