@@ -124,6 +124,7 @@ int join_side_streams(cudaStream_t main) {
   return DVAE_OK;
 }
 void set_defer_joins(bool on) { g_defer_joins = on; }
+bool defer_joins_enabled() { return g_defer_joins; }
 }  // namespace dvae
 
 // ---- weight-plane registry -------------------------------------------------------------------------

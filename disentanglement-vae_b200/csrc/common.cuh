@@ -67,6 +67,9 @@ class Fork {
   bool ok_;
 };
 
+// true between dvae_defer_joins(1) and dvae_join_side_streams(): side work of this call will overlap the caller's next calls
+bool defer_joins_enabled();
+
 // DVAE_GEMM_IMPL=simt forces the fp32 SIMT kernels, =tf32 the 3xTF32 tensor-core kernel (A/B tests of the fp16-split path)
 bool force_simt_gemm();
 

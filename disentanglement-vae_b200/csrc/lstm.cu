@@ -430,7 +430,7 @@ int lstm_seq_bwd_impl(const float* x, int64_t ldx, int T, int B, int I, int H, i
   GemmHints gh_bg = gh;
   {
     static const int cap = [] { const char* e = getenv("DVAE_DW_MAX_CTAS"); return e ? atoi(e) : 48; }();
-    gh_bg.max_ctas = cap;
+    gh_bg.max_ctas = defer_joins_enabled() ? cap : 0;      // nothing follows (last layer of the backward pass): whole machine
   }
   // d_x accumulates over the directions (main stream, in order); the weight / bias gradients of each direction are
   // independent of it and of each other: parallel branches
