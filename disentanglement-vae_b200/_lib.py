@@ -63,6 +63,9 @@ SIGNATURES = {
                                   _l, _l, _p, _p, _p, _i, _p]),
     "dvae_lstm_seq_bwd": (_i, [_p, _l, _i, _i, _i, _i, _i, _pp, _pp, _p, _p, _l, _l, _p, _p, _l, _p, _p, _p, _l,
                                _p, _p, _l, _l, _p, _l, _pp, _pp, _pp, _pp, _p, _p, _l, _l, _p, _p]),
+    "dvae_lstm_bwd_planes_ws_floats": (_l, [_i, _i, _i, _i, _i]),
+    "dvae_lstm_seq_bwd_ex": (_i, [_p, _l, _i, _i, _i, _i, _i, _pp, _pp, _p, _p, _l, _l, _p, _p, _l, _p, _p, _p, _l,
+                                  _p, _p, _l, _l, _p, _l, _pp, _pp, _pp, _pp, _p, _p, _l, _l, _p, _p, _p]),
     "dvae_heads_ws_floats": (_l, [_i, _i]),
     "dvae_latent_heads_fwd": (_i, [_p, _i, _i, _i, _ip, _ip, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _p, _p, _p,
                                    _p, _p, _p, _p, _p]),

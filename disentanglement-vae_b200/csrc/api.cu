@@ -32,7 +32,7 @@ void set_defer_joins(bool on);
 namespace {
 struct SideStreams {
   cudaStream_t s[3];
-  cudaEvent_t fork_ev, join_ev[3], mark_ev;
+  cudaEvent_t fork_ev, join_ev[3], mark_ev, chain_ev;
   bool ok = false;
   bool pending[3] = {false, false, false};     // detached work (deferred joins)
 };
@@ -44,7 +44,8 @@ SideStreams* side_streams() {
   if (!per_dev[dev]) {
     SideStreams* ss = new SideStreams();
     ss->ok = cudaEventCreateWithFlags(&ss->fork_ev, cudaEventDisableTiming) == cudaSuccess &&
-             cudaEventCreateWithFlags(&ss->mark_ev, cudaEventDisableTiming) == cudaSuccess;
+             cudaEventCreateWithFlags(&ss->mark_ev, cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&ss->chain_ev, cudaEventDisableTiming) == cudaSuccess;
     // side streams 0 / 1 carry the weight-gradient GEMMs that run beside the next layer's recurrence: lowest priority, so
     // that CTAs of the caller's (critical-path) stream are placed first whenever SMs free up (DVAE_SIDE_PRIO=0: default priority)
     int least = 0, greatest = 0;
@@ -100,6 +101,14 @@ int Fork::wait_mark() {
   if (!ok_ || !marked_) return DVAE_OK;
   DVAE_CUDA(cudaStreamWaitEvent(main_, side_streams()->mark_ev, 0));
   marked_ = false;
+  return DVAE_OK;
+}
+int Fork::chain(int from, int to) {
+  if (!ok_ || !used_[from]) return DVAE_OK;
+  cudaStream_t dst = side(to);
+  if (dst == main_) return DVAE_OK;
+  DVAE_CUDA(cudaEventRecord(side_streams()->chain_ev, side_streams()->s[from]));
+  DVAE_CUDA(cudaStreamWaitEvent(dst, side_streams()->chain_ev, 0));
   return DVAE_OK;
 }
 int Fork::join_or_defer() {

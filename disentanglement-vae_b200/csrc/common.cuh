@@ -60,6 +60,7 @@ class Fork {
   // mark(i) right after enqueueing it on side(i), wait_mark() where the main stream consumes it.
   int mark(int i);
   int wait_mark();
+  int chain(int from, int to);   // side(to) waits for everything enqueued on side(from) so far
  private:
   cudaStream_t main_;
   bool used_[3] = {false, false, false};

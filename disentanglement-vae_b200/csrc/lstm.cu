@@ -11,6 +11,7 @@
 
 #include "common.cuh"
 #include "lstm_persist.cuh"
+#include "tc_gemm16.cuh"
 
 namespace dvae {
 
@@ -342,7 +343,7 @@ int lstm_seq_bwd_impl(const float* x, int64_t ldx, int T, int B, int I, int H, i
                       const float* d_hs, int64_t lddhs, const float* d_hn, const float* d_cn, int64_t ldn,
                       int64_t dirn, float* d_x, int64_t lddx, float* const* d_w_ih, float* const* d_w_hh,
                       float* const* d_b_ih, float* const* d_b_hh, float* d_h0, float* d_c0, int64_t ldd0,
-                      int64_t dird0, float* ws, cudaStream_t st) {
+                      int64_t dird0, float* ws, float* planes_ws, cudaStream_t st) {
   DVAE_REQUIRE(x && hs && gates && cs && ws && w_ih && w_hh, "dvae_lstm_seq_bwd: null pointer");
   DVAE_REQUIRE(T > 0 && B > 0 && I > 0 && H > 0 && (D == 1 || D == 2), "dvae_lstm_seq_bwd: bad shape");
   DVAE_REQUIRE(!(lengths && h0), "dvae_lstm_seq_bwd: length-masked layers start from the zero state");
@@ -447,6 +448,35 @@ int lstm_seq_bwd_impl(const float* x, int64_t ldx, int T, int B, int I, int H, i
     if (rc) return rc;
     if ((rc = fork.mark(2))) return rc;
   }
+  // Weight gradients dW_ih = dG^T x, dW_hh = dG^T h_prev contract over the T*B positions: both operands are read "transposed"
+  // (MN-major), the converter path's slowest case (0.74 us per k-block, tensor pipe 9 %).  With a plane workspace the three
+  // matrices are transposed ONCE into fp16 operand planes by one launch (dG scaled by its measured amax) and the GEMMs run
+  // bulk-copy fed on both operands; time steps shift by whole k-blocks (B % 32 == 0) for the h_{t-1} pairing.
+  const int TB = T * B, KBt = ceil_div(TB, 32);
+  // Measured (A/B on one box, graph replay): 25.7 vs 28.0 ms per step at H = 1024 (cfg4), but 1.163 vs 1.142 ms at cfg2 and
+  // 0.938 vs 0.929 at cfg3, where the GEMMs are a few k-blocks per CTA and the extra transposing launch sits in the step's
+  // tail: the planes are used from 2^32 multiply-adds per GEMM upwards (DVAE_DW_PLANES=1 / 0 forces either way).
+  const char* dwp_env = getenv("DVAE_DW_PLANES");
+  const bool dwp_on = dwp_env ? dwp_env[0] != '0' : (int64_t)4 * H * (I > H ? I : H) * TB >= ((int64_t)1 << 32);
+  const bool dw_planes = planes_ws && amax && !force_simt_gemm() && tc16::enabled() && TB >= 128 &&
+                         (reinterpret_cast<uintptr_t>(planes_ws) & 15) == 0 && dwp_on;
+  const bool hh_planes = dw_planes && T > 1 && B % 32 == 0;
+  float *xT = planes_ws, *dGt[2] = {nullptr, nullptr}, *hsT[2] = {nullptr, nullptr};
+  if (dw_planes) {
+    float* q = xT + tc16::plane_floats(I, TB);
+    for (int d = 0; d < D; ++d) { dGt[d] = q; q += tc16::plane_floats(4 * H, TB); }
+    for (int d = 0; d < D; ++d) { hsT[d] = q; q += tc16::plane_floats(H, TB); }
+    tc16::PlaneTable tab;
+    tab.n = 0;
+    if (d_w_ih) tab.e[tab.n++] = tc16::PlaneTable::Entry{x, TB, I, nullptr, xT, ldx, nullptr, 0};
+    for (int d = 0; d < D; ++d) {
+      tab.e[tab.n++] = tc16::PlaneTable::Entry{gates + d * slab, TB, 4 * H, nullptr, dGt[d], 4 * H, amax, amax_n};
+      if (hh_planes && d_w_hh) tab.e[tab.n++] = tc16::PlaneTable::Entry{hs + d * H, TB, H, nullptr, hsT[d], ldhs, nullptr, 0};
+    }
+    int rc = tc16::weight_planes_launch(tab, fork.side(0));
+    if (rc) return rc;
+    if ((rc = fork.chain(0, 1))) return rc;
+  }
   for (int d = 0; d < D; ++d) {
     const float* dG = gates + d * slab;
     int rc;
@@ -459,7 +489,11 @@ int lstm_seq_bwd_impl(const float* x, int64_t ldx, int T, int B, int I, int H, i
       if (dx_pair && (rc = fork.wait_mark())) return rc;
     }
     if (d_w_ih && d_w_ih[d]) {
-      rc = linear_impl_ex(dG, 4 * H, 1, x, ldx, 1, d_w_ih[d], I, 4 * H, I, T * B, nullptr, nullptr, 0.f, 0, gh_bg, fork.side(0));
+      if (dw_planes)
+        rc = tc16::linear_planes(dGt[d], xT, d_w_ih[d], I, 4 * H, I, TB, nullptr, 0.f, 0, 1.f, 1.f, nullptr, false, 16, fork.side(0), 0, 0,
+                                 gh_bg.max_ctas, 0, 0, amax, amax_n);
+      else
+        rc = linear_impl_ex(dG, 4 * H, 1, x, ldx, 1, d_w_ih[d], I, 4 * H, I, T * B, nullptr, nullptr, 0.f, 0, gh_bg, fork.side(0));
       if (rc) return rc;
     }
     if (d_w_hh && d_w_hh[d]) {
@@ -469,7 +503,11 @@ int lstm_seq_bwd_impl(const float* x, int64_t ldx, int T, int B, int I, int H, i
       if (T > 1) {
         const float* dGs = d == 0 ? dG + (int64_t)B * 4 * H : dG;
         const float* hp = d == 0 ? hs + d * H : hs + (int64_t)B * ldhs + d * H;
-        rc = linear_impl_ex(dGs, 4 * H, 1, hp, ldhs, 1, d_w_hh[d], H, 4 * H, H, (T - 1) * B, nullptr, nullptr, 0.f, 0, gh_bg, s1);
+        if (hh_planes)      // forward direction: dG rows t >= 1 against h rows t <= T-2 (the reverse direction the other way round)
+          rc = tc16::linear_planes(dGt[d], hsT[d], d_w_hh[d], H, 4 * H, H, (T - 1) * B, nullptr, 0.f, 0, 1.f, 1.f, nullptr, false, 16, s1,
+                                   d == 0 ? 0 : B / 32, KBt, gh_bg.max_ctas, d == 0 ? B / 32 : 0, KBt, amax, amax_n);
+        else
+          rc = linear_impl_ex(dGs, 4 * H, 1, hp, ldhs, 1, d_w_hh[d], H, 4 * H, H, (T - 1) * B, nullptr, nullptr, 0.f, 0, gh_bg, s1);
         if (rc) return rc;
         wrote = true;
       }
@@ -623,5 +661,23 @@ extern "C" int dvae_lstm_seq_bwd(const float* x, int64_t ldx, int T, int B, int 
                                  int64_t ldd0, int64_t dird0, float* state_ws, void* stream) {
   return dvae::lstm_seq_bwd_impl(x, ldx, T, B, I, H, D, w_ih, w_hh, h0, c0, ld0, dir0, lengths, hs, ldhs, gates, cs,
                                  d_hs, lddhs, d_hn, d_cn, ldn, dirn, d_x, lddx, d_w_ih, d_w_hh, d_b_ih, d_b_hh,
-                                 d_h0, d_c0, ldd0, dird0, state_ws, (cudaStream_t)stream);
+                                 d_h0, d_c0, ldd0, dird0, state_ws, nullptr, (cudaStream_t)stream);
+}
+
+extern "C" int64_t dvae_lstm_bwd_planes_ws_floats(int T, int B, int I, int H, int D) {
+  const int TB = T * B;
+  return dvae::tc16::plane_floats(I, TB) + (int64_t)D * (dvae::tc16::plane_floats(4 * H, TB) + dvae::tc16::plane_floats(H, TB));
+}
+
+extern "C" int dvae_lstm_seq_bwd_ex(const float* x, int64_t ldx, int T, int B, int I, int H, int D,
+                                    const float* const* w_ih, const float* const* w_hh, const float* h0,
+                                    const float* c0, int64_t ld0, int64_t dir0, const int64_t* lengths,
+                                    const float* hs, int64_t ldhs, float* gates, const float* cs, const float* d_hs,
+                                    int64_t lddhs, const float* d_hn, const float* d_cn, int64_t ldn, int64_t dirn,
+                                    float* d_x, int64_t lddx, float* const* d_w_ih, float* const* d_w_hh,
+                                    float* const* d_b_ih, float* const* d_b_hh, float* d_h0, float* d_c0,
+                                    int64_t ldd0, int64_t dird0, float* state_ws, float* planes_ws, void* stream) {
+  return dvae::lstm_seq_bwd_impl(x, ldx, T, B, I, H, D, w_ih, w_hh, h0, c0, ld0, dir0, lengths, hs, ldhs, gates, cs,
+                                 d_hs, lddhs, d_hn, d_cn, ldn, dirn, d_x, lddx, d_w_ih, d_w_hh, d_b_ih, d_b_hh,
+                                 d_h0, d_c0, ldd0, dird0, state_ws, planes_ws, (cudaStream_t)stream);
 }

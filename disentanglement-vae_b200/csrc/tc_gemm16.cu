@@ -219,6 +219,8 @@ __global__ void weight_planes_kernel(PlaneTable tab) {
   uint8_t* out = reinterpret_cast<uint8_t*>(tr ? e.planes_t : e.planes);
   if (!out) return;
   const int R = tr ? e.C : e.R, K = tr ? e.R : e.C;           // rows / depth of the matrix being split
+  const int64_t ld = e.ld ? e.ld : e.C;
+  const float sc = scale_from_amax(e.amax, e.amax_n, 1.f);
   const int KB = (K + BK - 1) / BK, KC = KB * (BK / 8), RP = (R + BM - 1) / BM * BM;
   const int64_t total = (int64_t)RP * KC;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -229,11 +231,11 @@ __global__ void weight_planes_kernel(PlaneTable tab) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int k = kc * 8 + j;
-      v[j] = (r < R && k < K) ? __ldg(tr ? e.w + (int64_t)k * e.C + r : e.w + (int64_t)r * e.C + k) : 0.f;
+      v[j] = (r < R && k < K) ? __ldg(tr ? e.w + (int64_t)k * ld + r : e.w + (int64_t)r * ld + k) : 0.f;
     }
     uint4 h, l;
-    h.x = pack_hi_lo(v[0], v[1], 1.f, l.x); h.y = pack_hi_lo(v[2], v[3], 1.f, l.y);
-    h.z = pack_hi_lo(v[4], v[5], 1.f, l.z); h.w = pack_hi_lo(v[6], v[7], 1.f, l.w);
+    h.x = pack_hi_lo(v[0], v[1], sc, l.x); h.y = pack_hi_lo(v[2], v[3], sc, l.y);
+    h.z = pack_hi_lo(v[4], v[5], sc, l.z); h.w = pack_hi_lo(v[6], v[7], sc, l.w);
     const int64_t off = ((int64_t)(r >> 7) * KB + (kc >> 2)) * (2 * PS_PLANE) + ((r & 127) >> 3) * PS_SBO + (kc & 3) * PS_LBO + (r & 7) * 16;
     *reinterpret_cast<uint4*>(out + off) = h;
     *reinterpret_cast<uint4*>(out + off + PS_PLANE) = l;
@@ -364,7 +366,8 @@ tc16_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int s2 = 0; s2 < nstages; ++s2) mbar_wait(&full[s2], s2 < stage ? phase : phase ^ 1);
     } else if (lane == 0 && p.presplit) {
       // operand planes straight into the operand ring: one 16 KB tile k-block [hi, lo] per operand
-      const uint8_t* a_tiles = reinterpret_cast<const uint8_t*>(p.a_planes) + (int64_t)blockIdx.x * nkb_total * PS_TILE;
+      const uint8_t* a_tiles = reinterpret_cast<const uint8_t*>(p.a_planes) +
+                               ((int64_t)blockIdx.x * (p.a_kbtot ? p.a_kbtot : nkb_total) + p.a_kb0) * PS_TILE;
       const uint8_t* b_planes = reinterpret_cast<const uint8_t*>(p.b_planes);
       int stage = 0, phase = 0;
       for (int nt = nt0; nt < nt1; ++nt) {
@@ -1088,7 +1091,7 @@ int linear(const float* A, int64_t lda, int trans_a, const float* B, int64_t ldb
 // is split once per call (its weights).  c_row_scale: optional per-row output factor (device, [M]).
 int linear_planes(const void* a_planes, const void* b_planes, float* C, int64_t ldc, int M, int N, int K, const float* bias,
                   float beta, int act, float a_scale, float b_scale, const float* c_row_scale, bool c_zeroed, int max_splits,
-                  cudaStream_t st, int b_kb0, int b_kbtot, int max_ctas) {
+                  cudaStream_t st, int b_kb0, int b_kbtot, int max_ctas, int a_kb0, int a_kbtot, const uint32_t* a_amax, int a_amax_n) {
   DVAE_REQUIRE(a_planes && b_planes && C && M > 0 && N > 0 && K > 0, "tc16 linear_planes: bad argument");
   Params p = {};
   p.presplit = 1; p.no_astat = 1; p.a_planes = a_planes; p.b_planes = b_planes; p.a_rows = M; p.b_rows = N;
@@ -1096,6 +1099,8 @@ int linear_planes(const void* a_planes, const void* b_planes, float* C, int64_t 
   apply_hints(p, GemmHints());
   p.a_scale = a_scale; p.b_scale = b_scale; p.c_row_scale = c_row_scale;
   p.b_kb0 = b_kb0; p.b_kbtot = b_kbtot;          // B planes wider than this GEMM's K range (a vocabulary chunk of W_out^T)
+  p.a_kb0 = a_kb0; p.a_kbtot = a_kbtot;
+  if (a_amax) { p.a_amax = a_amax; p.a_amax_n = a_amax_n; }      // A planes were scaled by 2^(13 - floor(log2 amax)) (weight_planes_kernel)
   const int tiles = ceil_div(M, BM) * ceil_div(N, BN), nkb = ceil_div(K, BK);
   int splits = 1;
   if (act == 0 && nkb >= 8) {      // same cost model as linear(), with the bulk-copy-fed k-block time

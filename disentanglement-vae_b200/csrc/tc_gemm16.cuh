@@ -28,6 +28,7 @@ struct Params {
   float* zero_buf; int64_t zero_n4;      // optional: up to two buffers (float4 counts) the kernel clears on its way in
   float* zero_buf2; int64_t zero2_n4;    //           (outputs of later split-K GEMMs; see tc_gemm16.cu)
   int mcast;                             // A-stationary pre-split kernels launched as CTA pairs: B stages fetched half each, multicast
+  int a_kbtot; int a_kb0;                 // both-operands-presplit mode: A planes wider than this GEMM's K range
   int b_presplit; int b_kbtot; int b_kb0;   // HYBRID: A through the converter ring, B (a weight) from registered planes: k-blocks per row block / first k-block
   int atomic_out;                        // mode 0: atomicAdd into C even with one k-split (C zeroed by the caller)
   int no_astat;                          // pre-split operands in the dual-accumulator convention: never the A-stationary variant
@@ -57,12 +58,14 @@ int64_t plane_floats(int R, int K);
 int split_planes(const float* X, int64_t ld, int R, int K, float scale, void* planes, cudaStream_t st, bool force_dual = false);
 int linear_planes(const void* a_planes, const void* b_planes, float* C, int64_t ldc, int M, int N, int K, const float* bias,
                   float beta, int act, float a_scale, float b_scale, const float* c_row_scale, bool c_zeroed, int max_splits,
-                  cudaStream_t st, int b_kb0 = 0, int b_kbtot = 0, int max_ctas = 0);
+                  cudaStream_t st, int b_kb0 = 0, int b_kbtot = 0, int max_ctas = 0, int a_kb0 = 0, int a_kbtot = 0,
+                  const uint32_t* a_amax = nullptr, int a_amax_n = 1);
 // Weight-plane registry (api.cu): GEMMs whose B operand is a registered weight matrix (or a 128-row / 32-column aligned
 // block of it) fetch B as pre-split planes by bulk copy; only A goes through the converter warps.
 constexpr int kMaxPlaneEntries = 24;
 struct PlaneTable {
-  struct Entry { const float* w; int R, C; void* planes; void* planes_t; };
+  // ld: row stride of w (0 = C); amax: optional device bit patterns of max |w| (the planes then hold w * 2^(13 - floor(log2 amax)))
+  struct Entry { const float* w; int R, C; void* planes; void* planes_t; int64_t ld; const uint32_t* amax; int amax_n; };
   Entry e[kMaxPlaneEntries];
   int n;
 };

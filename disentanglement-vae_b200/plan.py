@@ -112,6 +112,10 @@ class StepPlan:
         self.g_ctx = torch.empty(B, d.C, **f32)
         self.heads_bwd_ws = torch.empty(self.lib.dvae_heads_bwd_ws_floats(B, d.Z, d.H2L), **f32)
         self.ce_bwd_ws = torch.empty(self.lib.dvae_vocab_ce_bwd_ws_floats(max(self.N, 1), d.V, d.Hd), **f32)
+        # operand planes of x, dG and hs for the LSTM weight-gradient GEMMs: one buffer, sized for the largest layer
+        need = [self.lib.dvae_lstm_bwd_planes_ws_floats(T1, B, d.E if l == 0 else d.Hd, d.Hd, 1) for l in range(d.Ld)]
+        need += [self.lib.dvae_lstm_bwd_planes_ws_floats(T, B, d.E if l == 0 else d.D * d.H, d.H, d.D) for l in range(d.Le)]
+        self.lstm_bwd_planes = torch.empty(max(need), **f32)
         self._bwd_ready = True
 
     @staticmethod
@@ -338,14 +342,14 @@ class StepPlan:
             w_ih, w_hh, _, _ = self._dec_w(P, l)
             gw_ih, gw_hh, gb_ih, gb_hh = self._dec_w(G, l)
             need_dx = l > 0 or emb_grad
-            check(lib.dvae_lstm_seq_bwd(ptr(x), I, T1, B, I, d.Hd, 1, ptr_array(w_ih), ptr_array(w_hh),
+            check(lib.dvae_lstm_seq_bwd_ex(ptr(x), I, T1, B, I, d.Hd, 1, ptr_array(w_ih), ptr_array(w_hh),
                                         hid.data_ptr() + 4 * l * d.Hd, hid.data_ptr() + 4 * (d.Ld + l) * d.Hd,
                                         d.H2L, 0, None, ptr(self.d_hs[l]), d.Hd, ptr(self.d_gates[l]),
                                         ptr(self.d_cs[l]), ptr(g_in), d.Hd, None, None, 0, 0,
                                         ptr(g_out) if need_dx else None, I, ptr_array(gw_ih), ptr_array(gw_hh),
                                         ptr_array(gb_ih), ptr_array(gb_hh), self.g_hid.data_ptr() + 4 * l * d.Hd,
                                         self.g_hid.data_ptr() + 4 * (d.Ld + l) * d.Hd, d.H2L, 0,
-                                        ptr(self.state_ws), st), "dvae_lstm_seq_bwd(dec)")
+                                        ptr(self.state_ws), ptr(self.lstm_bwd_planes), st), "dvae_lstm_seq_bwd(dec)")
             if l > 0 and p > 0.0:
                 check(lib.dvae_dropout(ptr(g_out), I, T1 * B, I, p, ptr(self.seed_dev), SALT_DEC_LAYER + l,
                                        ptr(g_out), I, 0, st), "dvae_dropout(bwd)")
@@ -397,12 +401,12 @@ class StepPlan:
             gw_ih, gw_hh, gb_ih, gb_hh = self._enc_w(G, l, d.D)
             need_dx = l > 0 or emb_grad
             off = l * d.D * d.H
-            check(lib.dvae_lstm_seq_bwd(ptr(x), I, T, B, I, d.H, d.D, ptr_array(w_ih), ptr_array(w_hh), None, None,
+            check(lib.dvae_lstm_seq_bwd_ex(ptr(x), I, T, B, I, d.H, d.D, ptr_array(w_ih), ptr_array(w_hh), None, None,
                                         0, 0, ptr(lengths), ptr(self.e_hs[l]), d.D * d.H, ptr(self.e_gates[l]),
                                         ptr(self.e_cs[l]), ptr(g_in), d.D * d.H, g_ctx.data_ptr() + 4 * off, None,
                                         d.C, d.H, ptr(g_out) if need_dx else None, I, ptr_array(gw_ih),
                                         ptr_array(gw_hh), ptr_array(gb_ih), ptr_array(gb_hh), None, None, 0, 0,
-                                        ptr(self.state_ws), st), "dvae_lstm_seq_bwd(enc)")
+                                        ptr(self.state_ws), ptr(self.lstm_bwd_planes), st), "dvae_lstm_seq_bwd(enc)")
             if l > 0 and p > 0.0:
                 check(lib.dvae_dropout(ptr(g_out), I, T * B, I, p, ptr(self.seed_dev), SALT_ENC_LAYER + l,
                                        ptr(g_out), I, 0, st), "dvae_dropout(bwd)")

@@ -228,6 +228,22 @@ int dvae_lstm_seq_bwd(const float* x, int64_t ldx, int T, int B, int I, int H, i
                       float* const* d_b_ih_host, float* const* d_b_hh_host, float* d_h0,
                       float* d_c0, int64_t ldd0, int64_t dird0, float* state_ws, void* stream);
 
+/* The same with a plane workspace (dvae_lstm_bwd_planes_ws_floats(T, B, I, H, D) floats, 16-byte aligned, or NULL): the
+ * weight gradients dW_ih = dG^T x and dW_hh = dG^T h_prev contract over the T*B positions, i.e. read both operands
+ * transposed.  With the workspace x, dG and hs are transposed once into fp16 operand planes (one launch; dG scaled by the
+ * max |dG| the recurrence kernel measured) and those GEMMs are bulk-copy fed on both operands. */
+int64_t dvae_lstm_bwd_planes_ws_floats(int T, int B, int I, int H, int D);
+int dvae_lstm_seq_bwd_ex(const float* x, int64_t ldx, int T, int B, int I, int H, int D,
+                         const float* const* w_ih_host, const float* const* w_hh_host,
+                         const float* h0, const float* c0, int64_t ld0, int64_t dir0,
+                         const int64_t* lengths, const float* hs, int64_t ldhs, float* gates,
+                         const float* cs, const float* d_hs, int64_t lddhs, const float* d_hn,
+                         const float* d_cn, int64_t ldn, int64_t dirn, float* d_x, int64_t lddx,
+                         float* const* d_w_ih_host, float* const* d_w_hh_host,
+                         float* const* d_b_ih_host, float* const* d_b_hh_host, float* d_h0,
+                         float* d_c0, int64_t ldd0, int64_t dird0, float* state_ws, float* planes_ws,
+                         void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Fused latent heads.  Replaces compute_latent_params (vae/model.py:384-398), the
  * discriminators' forward / loss / accuracy (vae/model.py:195-216, vae/losses.py:180-196),

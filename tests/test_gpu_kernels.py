@@ -234,7 +234,7 @@ def test_linear_rejects_bad_arguments(lib, L):
 
 
 # ---------------------------------------------------------------------------------------------
-def _lstm_case(lib, L, T, B, I, H, D, with_len, with_h0, seed):
+def _lstm_case(lib, L, T, B, I, H, D, with_len, with_h0, seed, dw_planes=False):
     rng = np.random.default_rng(seed)
     x = rng.standard_normal((T, B, I)).astype(np.float32)
     k = 1.0 / np.sqrt(H)
@@ -302,11 +302,16 @@ def _lstm_case(lib, L, T, B, I, H, D, with_len, with_h0, seed):
     d_x = torch.zeros(T, B, I, device="cuda")
     d_h0 = torch.zeros(D, B, H, device="cuda")
     d_c0 = torch.zeros(D, B, H, device="cuda")
-    L.check(lib.dvae_lstm_seq_bwd(L.ptr(xd), I, T, B, I, H, D, pa("w_ih"), pa("w_hh"), L.ptr(h0d), L.ptr(c0d), H, B * H,
-                                  L.ptr(len_d), L.ptr(hs), D * H, L.ptr(gates), L.ptr(cs), L.ptr(dev(d_hs)), D * H,
-                                  L.ptr(dev(d_hn)), L.ptr(dev(d_cn)), H, B * H, L.ptr(d_x), I, ga("w_ih"), ga("w_hh"),
-                                  ga("b_ih"), ga("b_hh"), L.ptr(d_h0) if with_h0 else None,
-                                  L.ptr(d_c0) if with_h0 else None, H, B * H, L.ptr(ws), st), "lstm bwd")
+    bwd_args = (L.ptr(xd), I, T, B, I, H, D, pa("w_ih"), pa("w_hh"), L.ptr(h0d), L.ptr(c0d), H, B * H,
+                L.ptr(len_d), L.ptr(hs), D * H, L.ptr(gates), L.ptr(cs), L.ptr(dev(d_hs)), D * H,
+                L.ptr(dev(d_hn)), L.ptr(dev(d_cn)), H, B * H, L.ptr(d_x), I, ga("w_ih"), ga("w_hh"),
+                ga("b_ih"), ga("b_hh"), L.ptr(d_h0) if with_h0 else None,
+                L.ptr(d_c0) if with_h0 else None, H, B * H, L.ptr(ws))
+    if dw_planes:     # weight gradients from transposed operand planes of x, dG and hs (the caller set DVAE_DW_PLANES=1)
+        pws = torch.full((lib.dvae_lstm_bwd_planes_ws_floats(T, B, I, H, D),), float("nan"), device="cuda")
+        L.check(lib.dvae_lstm_seq_bwd_ex(*bwd_args, L.ptr(pws), st), "lstm bwd (planes)")
+    else:
+        L.check(lib.dvae_lstm_seq_bwd(*bwd_args, st), "lstm bwd")
     dx_want = sum(want[d][3]["dx"] for d in range(D))
     assert rel(d_x, dx_want) < 1e-4
     for d in range(D):
@@ -349,6 +354,20 @@ def test_lstm_seq(lib, L, T, B, I, H, D, with_len, with_h0):
 ])
 def test_lstm_seq_large_hidden_plane_path(lib, L, T, B, I, H, D, with_len, with_h0):
     _lstm_case(lib, L, T, B, I, H, D, with_len, with_h0, seed=T * 17 + B + H)
+
+
+@pytest.mark.parametrize("T,B,I,H,D,with_len,with_h0", [
+    (22, 128, 64, 256, 2, True, False),   # both directions, ragged; B % 32 == 0: dW_hh pairs dG_t with h_{t-1} by a k-block shift
+    (9, 50, 32, 256, 2, True, False),     # B % 32 != 0: dW_ih from planes, dW_hh on the converter path
+    (21, 128, 256, 256, 1, False, True),  # initial state: the h0 . dG_0 term is added after the plane GEMM
+    (5, 128, 32, 1024, 1, False, True),   # cfg-4 hidden size (where the planes are the default)
+    (6, 96, 200, 512, 2, True, False),    # I not a multiple of the tile sizes
+    (1, 128, 32, 256, 1, False, True),    # single step: no h_{t-1} pairs at all
+    (3, 16, 32, 256, 1, False, True),     # T*B < 128: falls back to the converter GEMMs
+])
+def test_lstm_seq_bwd_weight_gradient_planes(lib, L, T, B, I, H, D, with_len, with_h0, monkeypatch):
+    monkeypatch.setenv("DVAE_DW_PLANES", "1")
+    _lstm_case(lib, L, T, B, I, H, D, with_len, with_h0, seed=T * 13 + B + I, dw_planes=True)
 
 
 @pytest.mark.parametrize("splits", ["1", "4"])
