@@ -641,7 +641,8 @@ def main():
         if rank == 0:
             print(json.dumps({"metric": "train_tokens_per_sec", "value": tok_sum / (dev_ms * 1e-3), "unit": "tokens/s", "n_gpus": world,
                               "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps,
-                              "config": workload_config(world, graph=not args.no_graph), "note": "--only-steps: no e2e / roofline legs"}), flush=True)
+                              "config": workload_config(world, graph=not args.no_graph), "dp_exchange": eng.exchange_mode,
+                              "note": "--only-steps: no e2e / roofline legs"}), flush=True)
         if world > 1:
             dist.destroy_process_group()
         return
@@ -810,6 +811,7 @@ def main():
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(world, graph=not args.no_graph),
+            "dp_exchange": eng.exchange_mode,      # none | p2p | nvls (repo all-reduce kernel inside the one-graph step) | nccl+...
             "padded_tokens_per_sec": B * world * T * args.steps / (dev_ms * 1e-3),
             "e2e": {"value": e2e_tok / e2e_s, "unit": "tokens/s", "h2d_bytes_per_step": eng.h2d_bytes_per_step,
                     "d2h_bytes_per_step": eng.d2h_bytes_per_step, "ms_per_step": e2e_s * 1e3 / args.steps,

@@ -106,3 +106,15 @@ def grad_buckets4(model, flat_grad):
     if hi != base + dec.numel() or lo <= base:          # decoder.linear.* must be the tail of the decoder range
         return [[], b[0], b[1], b[2]]
     return [[flat_grad[lo:hi]], [flat_grad[base:lo]], b[1], b[2]]
+
+
+def all_reduce_views_(views, group=None):
+    """SUM all-reduce of several views as ONE NCCL launch where the backend coalesces (each launch costs ~20 us of fixed
+    latency at these sizes: 1 MB 24 us, 10 MB 51 us, 36 MB 91 us on 2 B200s); one call per view otherwise."""
+    if len(views) > 1 and views[0].is_cuda and hasattr(dist, "_coalescing_manager"):
+        with dist._coalescing_manager(group=group, device=views[0].device, async_ops=False):
+            for v in views:
+                dist.all_reduce(v, op=dist.ReduceOp.SUM, group=group)
+        return
+    for v in views:
+        dist.all_reduce(v, op=dist.ReduceOp.SUM, group=group)

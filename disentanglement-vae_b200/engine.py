@@ -27,6 +27,7 @@ from . import _lib
 from ._lib import ptr, check
 from .plan import StepPlan
 from .losses import get_cyclic_kl_weight
+from .dist import all_reduce_views_
 
 
 def d_bow(plan):
@@ -62,7 +63,12 @@ class TrainEngine:
         self.n = model._flat_numel
         f32 = dict(device=self.device, dtype=torch.float32)
         self.flat = model._flat[:self.n]
-        self.grad = torch.zeros(self.n, **f32)
+        self.use_graph = use_graph
+        self._nvls = None
+        if self.world > 1 and use_graph and not self.aux and os.environ.get("DVAE_DP_NVLS", "1") != "0":
+            self._setup_nvls()          # gradient buffer in multicast memory (self.grad), or None: NCCL exchanges
+        if self._nvls is None:
+            self.grad = torch.zeros(self.n, **f32)
         self.m = torch.zeros(self.n, **f32)
         self.v = torch.zeros(self.n, **f32)
         self.G = model.grad_views(self.grad)
@@ -123,6 +129,11 @@ class TrainEngine:
         self._graphs = None
         self._buckets = None
         self._comm = None
+        # one-graph data parallel (dvae_flag_*): step counter, "bucket k final" flags [0..3] and "exchanges done" flag [7]
+        self._flag_mode = False
+        self._dp_step = 0
+        self._dp_ctr = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self._dp_flags = torch.zeros(8, dtype=torch.int32, device=self.device)
         self._side = None
         self.label_names = [n for n, o in zip(d.space_names, d.dsc_out) if o > 0]
         self.last_aux = {}
@@ -209,6 +220,9 @@ class TrainEngine:
         st = _lib.stream_ptr()
         cur = torch.cuda.current_stream()
         # part 0 (data parallel only): forward + vocabulary backward on their own, so that W_out's gradient is exchanged first
+        flags = self._flag_mode and part is None      # one-graph data parallel: exchanges / "bucket final" flags inside the graph
+        if flags:
+            check(self.lib.dvae_counter_increment(ptr(self._dp_ctr), st), "dvae_counter_increment")
         if part == 0 or part is None or (part == 1 and not self._three_buckets()):
             h_top, hoist = self._forward()
             if callable(g_z):
@@ -219,6 +233,8 @@ class TrainEngine:
             if part == 0:
                 check(self.lib.dvae_join_side_streams(st), "dvae_join_side_streams")      # d_w runs on a side stream
                 return
+            if flags:
+                self._signal(0, True)
         if part in (None, 1):
             g_top, hoist = self._g_top, self._hoist
             # weight-gradient GEMMs of each layer keep running on side streams while the next layer's recurrence starts
@@ -232,6 +248,8 @@ class TrainEngine:
                     if hoist:
                         cur.wait_stream(self._side)
             self._aux_pending = hoist and part is None
+            if flags:
+                self._signal(1, True, self._side if hoist else None)
         emb_enc = "encoder.embedding.weight" in m._layout
         if part in (None, 2):
             check(self.lib.dvae_defer_joins(1), "dvae_defer_joins")
@@ -243,15 +261,126 @@ class TrainEngine:
                 self._g_ctx = g_ctx
                 # data parallel with a multi-layer encoder: stop after the upper layers (their gradients go out under layer 0)
                 split = part == 2 and self._three_buckets()
-                pl.encode_bwd(P, G, self.inputs, self.lengths, g_ctx, emb_grad=emb_enc, layers=(pl.d.Le - 1, 1) if split else None)
+                if flags:
+                    pl.encode_bwd(P, G, self.inputs, self.lengths, g_ctx, emb_grad=emb_enc, layers=(pl.d.Le - 1, 1))
+                    self._signal(2, True)
+                    pl.encode_bwd(P, G, self.inputs, self.lengths, g_ctx, emb_grad=emb_enc, layers=(0, 0))
+                    # (sending the encoder embedding's 10 MB ahead of layer 0's 4 MB measured slower with NCCL: two launches of
+                    # ~20 us fixed latency each behind a communication stream that is still busy with stage 2)
+                    self._signal(3, True)
+                else:
+                    pl.encode_bwd(P, G, self.inputs, self.lengths, g_ctx, emb_grad=emb_enc, layers=(pl.d.Le - 1, 1) if split else None)
             finally:
                 check(self.lib.dvae_join_side_streams(st), "dvae_join_side_streams")
+            if flags and self._nvls is None:      # every exchange of this step has finished (the communication stream says so)
+                check(self.lib.dvae_flag_wait(ptr(self._dp_flags[7:]), ptr(self._dp_ctr), st), "dvae_flag_wait")
         if part == 3:
             check(self.lib.dvae_defer_joins(1), "dvae_defer_joins")
             try:
                 pl.encode_bwd(P, G, self.inputs, self.lengths, self._g_ctx, emb_grad=emb_enc, layers=(0, 0))
             finally:
                 check(self.lib.dvae_join_side_streams(st), "dvae_join_side_streams")
+
+    def _setup_nvls(self):
+        """The flat gradient buffer as a symmetric allocation bound to an NVSwitch multicast object, plus a barrier block,
+        for the repo's own all-reduce kernel (csrc/nvls.cu).  A start-up self-test (known values, 5 s soft timeout) must
+        pass on EVERY rank, otherwise all ranks keep the NCCL exchange -- said loudly on stderr, never silently."""
+        import sys
+        import ctypes as C
+        ok, why = 1, ""
+        try:
+            import torch.distributed._symmetric_memory as symm
+            grp = self.pg if self.pg is not None else dist.group.WORLD
+            n_pad = (self.n + 3) // 4 * 4
+            buf = symm.empty(n_pad, dtype=torch.float32, device=self.device)
+            hb = symm.rendezvous(buf, group=grp)
+            bar = symm.empty(int(self.lib.dvae_nvls_barrier_words()), dtype=torch.int32, device=self.device)
+            bar.zero_()
+            hbar = symm.rendezvous(bar, group=grp)
+            if not hb.multicast_ptr:
+                raise RuntimeError("no multicast address (NVSwitch multicast unavailable)")
+            torch.cuda.synchronize()
+            dist.barrier(group=self.pg)
+            bar_ptrs = (C.c_void_p * self.world)(*[int(p) for p in hbar.buffer_ptrs])
+            one = torch.ones(1, dtype=torch.int32, device=self.device)
+            err = torch.zeros(1, dtype=torch.int32, device=self.device)
+            buf.fill_(float(self.rank + 1))
+            torch.cuda.synchronize()
+            dist.barrier(group=self.pg)
+            # two GPUs: plain peer-to-peer loads / stores move a third of the bytes of the switch detour (measured 1.35 ms per
+            # cfg2 step with multimem against 1.26 with NCCL at N = 2, 1.25 against 1.32 at N = 4); DVAE_DP_XCHG=p2p|nvls forces
+            mode = os.environ.get("DVAE_DP_XCHG", "p2p" if self.world == 2 else "nvls")
+            buf_ptrs = [int(p) for p in hb.buffer_ptrs]
+            if mode == "p2p":
+                peers = (C.c_void_p * self.world)(*buf_ptrs)
+                check(self.lib.dvae_p2p_all_reduce(peers, n_pad, bar_ptrs, self.rank, self.world, ptr(one), 1, 0, 0,
+                                                   5_000_000_000, ptr(err), _lib.stream_ptr()), "dvae_p2p_all_reduce")
+            else:
+                check(self.lib.dvae_nvls_all_reduce(hb.multicast_ptr, n_pad, bar_ptrs, self.rank, self.world, ptr(one), 1, 0, 0,
+                                                    5_000_000_000, ptr(err), _lib.stream_ptr()), "dvae_nvls_all_reduce")
+            torch.cuda.synchronize()
+            want = float(self.world * (self.world + 1) // 2)
+            if int(err.item()) != 0 or not bool((buf == want).all()):
+                raise RuntimeError("self-test failed (timeout or wrong sums)")
+        except Exception as e:  # noqa: BLE001 -- any failure means "use NCCL", decided by all ranks together below
+            ok, why = 0, repr(e)[:200]
+        flag = torch.tensor([ok], dtype=torch.int32, device=self.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.pg)
+        if int(flag.item()) != 1:
+            print(f"[dvae_b200] rank {self.rank}: multicast gradient exchange unavailable ({why or 'another rank failed'}); "
+                  "using NCCL all-reduce", file=sys.stderr, flush=True)
+            return
+        buf.zero_()
+        torch.cuda.synchronize()
+        dist.barrier(group=self.pg)
+        self.grad = buf[:self.n]
+        self._nvls = dict(buf=buf, bar=bar, hb=hb, hbar=hbar, mc=int(hb.multicast_ptr), bar_ptrs=bar_ptrs, mode=mode, buf_ptrs=buf_ptrs)
+
+    def _signal(self, k, include_sides, extra=None):
+        """Bucket k's gradients are final once everything enqueued so far (and, include_sides, the detached side-stream
+        work and `extra`) has run: start its exchange there, beside the rest of the backward pass."""
+        if self._nvls is not None:
+            # the exchange itself, as graph nodes on the library's signal stream: one multicast all-reduce kernel per view
+            import ctypes as C
+            out = C.c_void_p()
+            check(self.lib.dvae_fork_after(1 if include_sides else 0, extra.cuda_stream if extra is not None else None,
+                                           _lib.stream_ptr(), C.byref(out)), "dvae_fork_after")
+            nv = self._nvls
+            last = k == len(self._buckets) - 1
+            ctas = int(os.environ.get("DVAE_NVLS_CTAS_LAST" if last else "DVAE_NVLS_CTAS", "64" if last else "16"))
+            for j, v in enumerate(self._buckets[k]):
+                off = v.data_ptr() - nv["buf"].data_ptr()
+                n = (v.numel() + 3) // 4 * 4
+                if nv["mode"] == "p2p":
+                    peers = (C.c_void_p * self.world)(*[bp + off for bp in nv["buf_ptrs"]])
+                    check(self.lib.dvae_p2p_all_reduce(peers, n, nv["bar_ptrs"], self.rank, self.world, ptr(self._dp_ctr),
+                                                       16, 2 * k + j + 1, ctas, 0, None, out.value), "dvae_p2p_all_reduce")
+                else:
+                    check(self.lib.dvae_nvls_all_reduce(nv["mc"] + off, n, nv["bar_ptrs"], self.rank, self.world, ptr(self._dp_ctr),
+                                                        16, 2 * k + j + 1, ctas, 0, None, out.value), "dvae_nvls_all_reduce")
+            return
+        check(self.lib.dvae_flag_signal(ptr(self._dp_flags[k:]), ptr(self._dp_ctr), 1 if include_sides else 0,
+                                        extra.cuda_stream if extra is not None else None, _lib.stream_ptr()), "dvae_flag_signal")
+
+    def _one_graph_dp(self):
+        """Data parallel as ONE graph per step: the exchanges are the repo's all-reduce kernels inside it (csrc/nvls.cu), or
+        (DVAE_DP_FLAGS=1) NCCL calls outside it ordered by device flags.  Otherwise: four stage graphs with NCCL between
+        them, whose ends also end the overlap of the weight-gradient GEMMs with the next recurrence."""
+        if not (self._three_buckets() and self.use_graph and not self.aux):
+            return False
+        # NCCL behind device flags is opt-in: it measured 1.26 (N=2) / 1.32 ms (N=4) per cfg2 step against 1.37 / 1.51 for the
+        # stage graphs, but two of seven runs sat at ~5 ms per step (a polling kernel ahead of NCCL's own stream ordering)
+        return self._nvls is not None or os.environ.get("DVAE_DP_FLAGS", "0") == "1"
+
+    @property
+    def exchange_mode(self):
+        """How this engine exchanges gradients: none | p2p | nvls (repo kernel inside the one-graph step) | nccl+flags |
+        nccl+stages."""
+        if self.world == 1:
+            return "none"
+        if self._nvls is not None and self._one_graph_dp():
+            return self._nvls["mode"]
+        return "nccl+flags" if self._one_graph_dp() else "nccl+stages"
 
     def _ensure_buckets(self):
         if self._buckets is None:
@@ -370,6 +499,22 @@ class TrainEngine:
         cur = torch.cuda.current_stream()
         if self.use_graph and self._graphs is None:
             self._capture()
+        if self._one_graph_dp():
+            self._dp_step += 1
+            self._graphs[0].replay()
+            if self._nvls is not None:      # the exchanges are nodes of the graph
+                return
+            # each NCCL exchange waits (on the device) for its bucket's flag of THIS step, and the graph's optimizer kernels
+            # wait for the flag written after the last exchange
+            cs = self._comm.cuda_stream
+            with torch.cuda.stream(self._comm):
+                for k, bucket in enumerate(self._buckets):
+                    if not bucket:
+                        continue
+                    check(self.lib.dvae_flag_wait_value(ptr(self._dp_flags[k:]), self._dp_step, cs), "dvae_flag_wait_value")
+                    all_reduce_views_(bucket, self.pg)
+                check(self.lib.dvae_flag_signal_value(ptr(self._dp_flags[7:]), self._dp_step, cs), "dvae_flag_signal_value")
+            return
         overlap = os.environ.get("DVAE_DP_OVERLAP", "1") != "0"
         stages = (0, 1, 2, 3) if three else (1, 2)
         for gi, part in enumerate(stages):
@@ -408,6 +553,20 @@ class TrainEngine:
             with torch.cuda.graph(g, stream=s):
                 self._fwd_bwd(None)
                 self._optim()
+            graphs.append(g)
+        elif self._one_graph_dp():
+            for bucket in self._buckets:      # communicator set-up (seconds) must not happen under a polling kernel
+                if bucket and self._nvls is None:
+                    all_reduce_views_(bucket, self.pg)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            self._flag_mode = True
+            try:
+                with torch.cuda.graph(g, stream=s):
+                    self._fwd_bwd(None)
+                    self._optim()
+            finally:
+                self._flag_mode = False
             graphs.append(g)
         else:                 # the all-reduces sit between the graphs (NCCL on its own stream)
             for part in ((0, 1, 2, 3) if self._three_buckets() else (1, 2)):

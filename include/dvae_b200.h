@@ -125,6 +125,46 @@ int dvae_weight_planes_clear(void);
 int dvae_defer_joins(int on);
 int dvae_join_side_streams(void* stream);
 
+/* Device flags: ordering between a step captured as ONE CUDA graph and the gradient exchanges (NCCL) enqueued outside it.
+ * An event recorded by a graph node cannot be waited on by a stream call issued before the node has run, so the order is
+ * carried by step counters in device memory instead:
+ *   dvae_counter_increment   *counter += 1                                  (first node of the captured step)
+ *   dvae_flag_signal         *flag = *counter once everything enqueued so far on `stream` -- and, include_sides != 0, the
+ *                            detached side-stream work (dvae_defer_joins) and `extra_stream` (or NULL) -- has finished;
+ *                            runs on a library stream, does not block `stream`; joined by dvae_join_side_streams
+ *   dvae_flag_wait           in-stream: a one-thread kernel polls until *flag >= *counter (wrap-safe), traps after 60 s
+ *   dvae_flag_signal_value / dvae_flag_wait_value: the same with the value passed from the host (the eager side).
+ * Replaces nothing in the reference: it is the scheduling of DistributedDataParallel's bucketed gradient exchange. */
+int dvae_counter_increment(uint32_t* counter, void* stream);
+/* The library's signal stream, made to wait for everything enqueued so far on `stream` (+ detached side work / extra_stream
+ * as for dvae_flag_signal); what the caller enqueues on *forked_stream_out afterwards runs beside `stream` until
+ * dvae_join_side_streams(stream).  Used for the gradient-exchange kernels of a data-parallel step. */
+int dvae_fork_after(int include_sides, void* extra_stream, void* stream, void** forked_stream_out);
+int dvae_flag_signal(uint32_t* flag, const uint32_t* counter, int include_sides, void* extra_stream, void* stream);
+int dvae_flag_wait(const uint32_t* flag, const uint32_t* counter, void* stream);
+int dvae_flag_signal_value(uint32_t* flag, uint32_t value, void* stream);
+int dvae_flag_wait_value(const uint32_t* flag, uint32_t value, void* stream);
+
+/* All-reduce (SUM, in place) of one gradient bucket over NVSwitch multicast memory, one kernel per rank (nvls.cu):
+ * cross-rank barrier, multimem.ld_reduce of this rank's 1/world slice, multimem.st of the sums into every rank's buffer,
+ * cross-rank barrier.  `mc_ptr` is the MULTICAST address of the bucket inside a symmetric allocation that every rank made
+ * with the same size (torch.distributed._symmetric_memory: handle.multicast_ptr + byte offset), 16-byte aligned, n % 4 == 0.
+ * `barrier_ptrs_host[r]`: peer-mapped address of rank r's barrier block (dvae_nvls_barrier_words() zeroed uint32 words in
+ * a second symmetric allocation).  Every call on a barrier block must use a larger epoch = *counter_dev * epoch_mul +
+ * epoch_add than the one before (>= 1), and all ranks must make the same sequence of calls with the same n and ctas.
+ * ctas = 0: sized from the bucket (<= 128).  soft_timeout_ns > 0: a rank that waits longer sets *err_dev = 1 and returns
+ * (start-up self-test); 0: trap after 60 s.  Replaces DistributedDataParallel's bucketed ncclAllReduce. */
+/* dvae_p2p_all_reduce: the same kernel with plain loads / stores through peer-mapped addresses (peer_ptrs_host[r] = the
+ * bucket inside rank r's buffer) instead of the switch: the owner adds the world copies in rank order and stores the sum
+ * to every copy.  The better of the two on 2 GPUs (0.5x the bucket per direction instead of 1.5x). */
+int64_t dvae_nvls_barrier_words(void);
+int dvae_p2p_all_reduce(float* const* peer_ptrs_host, int64_t n, uint32_t* const* barrier_ptrs_host, int rank, int world,
+                        const uint32_t* counter_dev, uint32_t epoch_mul, uint32_t epoch_add, int ctas,
+                        uint64_t soft_timeout_ns, uint32_t* err_dev, void* stream);
+int dvae_nvls_all_reduce(float* mc_ptr, int64_t n, uint32_t* const* barrier_ptrs_host, int rank, int world,
+                         const uint32_t* counter_dev, uint32_t epoch_mul, uint32_t epoch_add, int ctas,
+                         uint64_t soft_timeout_ns, uint32_t* err_dev, void* stream);
+
 /* out[n] = sum_m X[m, n] (+ out[n] if beta == 1); X is [M,N] row-major with row stride ldx. */
 int dvae_colsum(const float* X, int64_t ldx, int M, int N, float* out, float beta, void* stream);
 

@@ -88,7 +88,7 @@ def main():
     same = torch.tensor([1.0 if torch.equal(ref, flat) else 0.0], device=dev)
     dist.all_reduce(same, op=dist.ReduceOp.MIN)
     if rank == 0:
-        np.savez(out_path, flat=flat.cpu().numpy(), losses=lt.cpu().numpy(), replicas_identical=same.cpu().numpy(),
+        np.savez(out_path, flat=flat.cpu().numpy(), losses=lt.cpu().numpy(), replicas_identical=same.cpu().numpy(), exchange=np.array(eng.exchange_mode),
                  adam_step=np.int64(eng.adam_step))
     dist.barrier()
     dist.destroy_process_group()

@@ -160,3 +160,4 @@ def test_four_stage_split_puts_the_output_layer_first(dvae):
     assert sum(v.numel() for v in b[0]) >= n_lin and sum(v.numel() for v in b[0]) <= n_lin + 8
     off = vae._layout["decoder.linear.weight"]
     assert b[0][0].data_ptr() == flat.data_ptr() + 4 * off
+
