@@ -265,9 +265,11 @@ class TrainEngine:
                     pl.encode_bwd(P, G, self.inputs, self.lengths, g_ctx, emb_grad=emb_enc, layers=(pl.d.Le - 1, 1))
                     self._signal(2, True)
                     pl.encode_bwd(P, G, self.inputs, self.lengths, g_ctx, emb_grad=emb_enc, layers=(0, 0))
-                    # (sending the encoder embedding's 10 MB ahead of layer 0's 4 MB measured slower with NCCL: two launches of
-                    # ~20 us fixed latency each behind a communication stream that is still busy with stage 2)
-                    self._signal(3, True)
+                    if len(self._buckets) == 5:      # exchange kernels: the encoder embedding's 10 MB go out as soon as the scatter
+                        self._signal(3, False)       # (on this stream) has run, under layer 0's weight-gradient GEMMs ...
+                        self._signal(4, True)        # ... whose 4 MB follow when the side streams have drained
+                    else:                            # NCCL: one launch (each costs ~20 us of fixed latency)
+                        self._signal(3, True)
                 else:
                     pl.encode_bwd(P, G, self.inputs, self.lengths, g_ctx, emb_grad=emb_enc, layers=(pl.d.Le - 1, 1) if split else None)
             finally:
@@ -346,8 +348,10 @@ class TrainEngine:
             check(self.lib.dvae_fork_after(1 if include_sides else 0, extra.cuda_stream if extra is not None else None,
                                            _lib.stream_ptr(), C.byref(out)), "dvae_fork_after")
             nv = self._nvls
-            last = k == len(self._buckets) - 1
-            ctas = int(os.environ.get("DVAE_NVLS_CTAS_LAST" if last else "DVAE_NVLS_CTAS", "64" if last else "16"))
+            # early buckets finish under hundreds of us of backward pass: few CTAs; the late ones are (nearly) exposed
+            ctas = [int(c) for c in os.environ.get("DVAE_XCHG_CTAS", "16,16,32,64,64").split(",")][min(k, 4)]
+            if len(self._buckets) == 4 and k == 3:
+                ctas = max(ctas, 64)
             for j, v in enumerate(self._buckets[k]):
                 off = v.data_ptr() - nv["buf"].data_ptr()
                 n = (v.numel() + 3) // 4 * 4
@@ -384,8 +388,12 @@ class TrainEngine:
 
     def _ensure_buckets(self):
         if self._buckets is None:
-            from .dist import grad_buckets4, grad_buckets3
-            if self._three_buckets():
+            from .dist import grad_buckets4, grad_buckets3, grad_buckets5
+            # DVAE_DP_BUCKETS=5: encoder embedding ahead of layer 0's weights.  Measured no gain at N = 2 (1.27 vs 1.25 ms): the
+            # signal stream is still busy with stage 2's exchange when the embedding's gradient becomes final
+            if self._three_buckets() and self._nvls is not None and os.environ.get("DVAE_DP_BUCKETS", "4") == "5":
+                self._buckets = grad_buckets5(self.model, self.grad)
+            elif self._three_buckets():
                 self._buckets = grad_buckets4(self.model, self.grad)
             else:
                 b3 = grad_buckets3(self.model, self.grad)
@@ -522,10 +530,12 @@ class TrainEngine:
                 self._graphs[gi].replay()
             else:
                 self._fwd_bwd(part)
-            if overlap and self._buckets[gi]:
+            # the last stage takes every remaining bucket (five of them when the exchange kernels' finer split is in use)
+            views = [v for b in (self._buckets[gi:] if gi == len(stages) - 1 else self._buckets[gi:gi + 1]) for v in b]
+            if overlap and views:
                 self._comm.wait_stream(cur)
                 with torch.cuda.stream(self._comm):
-                    for v in self._buckets[gi]:
+                    for v in views:
                         dist.all_reduce(v, op=dist.ReduceOp.SUM, group=self.pg)
         if overlap:
             cur.wait_stream(self._comm)
