@@ -285,58 +285,69 @@ class TrainEngine:
 
     def _setup_nvls(self):
         """The flat gradient buffer as a symmetric allocation bound to an NVSwitch multicast object, plus a barrier block,
-        for the repo's own all-reduce kernel (csrc/nvls.cu).  A start-up self-test (known values, 5 s soft timeout) must
-        pass on EVERY rank, otherwise all ranks keep the NCCL exchange -- said loudly on stderr, never silently."""
+        for the repo's own all-reduce kernel (csrc/nvls.cu).  Two phases -- allocate + exchange handles, then a self-test
+        on known values with a 5 s soft timeout in the kernel's barrier -- and after each the ranks agree (all-reduce MIN
+        of an ok flag; no other collective sits on a path a failing rank could skip).  Unless every rank passes both, all
+        ranks keep the NCCL exchange -- said loudly on stderr, never silently."""
         import sys
         import ctypes as C
-        ok, why = 1, ""
+
+        def agreed(ok, why, phase):
+            flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=self.device)
+            torch.cuda.synchronize()
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.pg)
+            if int(flag.item()) == 1:
+                return True
+            print(f"[dvae_b200] rank {self.rank}: in-graph gradient exchange unavailable ({phase}: {why or 'another rank failed'}); "
+                  "using NCCL all-reduce between stage graphs", file=sys.stderr, flush=True)
+            return False
+
+        # two GPUs: plain peer-to-peer loads / stores move a third of the bytes of the switch detour (measured 1.35 ms per cfg2
+        # step with multimem against 1.25 peer-to-peer at N = 2; multimem 1.25 against NCCL's 1.51 at N = 4); DVAE_DP_XCHG forces
+        mode = os.environ.get("DVAE_DP_XCHG", "p2p" if self.world == 2 else "nvls")
+        n_pad = (self.n + 3) // 4 * 4
+        ok, why, st = True, "", {}
         try:
             import torch.distributed._symmetric_memory as symm
             grp = self.pg if self.pg is not None else dist.group.WORLD
-            n_pad = (self.n + 3) // 4 * 4
             buf = symm.empty(n_pad, dtype=torch.float32, device=self.device)
             hb = symm.rendezvous(buf, group=grp)
             bar = symm.empty(int(self.lib.dvae_nvls_barrier_words()), dtype=torch.int32, device=self.device)
             bar.zero_()
             hbar = symm.rendezvous(bar, group=grp)
-            if not hb.multicast_ptr:
+            if mode != "p2p" and not hb.multicast_ptr:
                 raise RuntimeError("no multicast address (NVSwitch multicast unavailable)")
-            torch.cuda.synchronize()
-            dist.barrier(group=self.pg)
-            bar_ptrs = (C.c_void_p * self.world)(*[int(p) for p in hbar.buffer_ptrs])
+            buf.fill_(float(self.rank + 1))
+            st = dict(buf=buf, bar=bar, hb=hb, hbar=hbar, mc=int(hb.multicast_ptr), mode=mode,
+                      bar_ptrs=(C.c_void_p * self.world)(*[int(p) for p in hbar.buffer_ptrs]),
+                      buf_ptrs=[int(p) for p in hb.buffer_ptrs])
+        except Exception as e:  # noqa: BLE001 -- any failure means "use NCCL", decided by all ranks together
+            ok, why = False, repr(e)[:200]
+        if not agreed(ok, why, "symmetric memory"):      # also the barrier behind every rank's fill_ / zero_
+            return
+        try:
             one = torch.ones(1, dtype=torch.int32, device=self.device)
             err = torch.zeros(1, dtype=torch.int32, device=self.device)
-            buf.fill_(float(self.rank + 1))
-            torch.cuda.synchronize()
-            dist.barrier(group=self.pg)
-            # two GPUs: plain peer-to-peer loads / stores move a third of the bytes of the switch detour (measured 1.35 ms per
-            # cfg2 step with multimem against 1.26 with NCCL at N = 2, 1.25 against 1.32 at N = 4); DVAE_DP_XCHG=p2p|nvls forces
-            mode = os.environ.get("DVAE_DP_XCHG", "p2p" if self.world == 2 else "nvls")
-            buf_ptrs = [int(p) for p in hb.buffer_ptrs]
             if mode == "p2p":
-                peers = (C.c_void_p * self.world)(*buf_ptrs)
-                check(self.lib.dvae_p2p_all_reduce(peers, n_pad, bar_ptrs, self.rank, self.world, ptr(one), 1, 0, 0,
+                peers = (C.c_void_p * self.world)(*st["buf_ptrs"])
+                check(self.lib.dvae_p2p_all_reduce(peers, n_pad, st["bar_ptrs"], self.rank, self.world, ptr(one), 1, 0, 0,
                                                    5_000_000_000, ptr(err), _lib.stream_ptr()), "dvae_p2p_all_reduce")
             else:
-                check(self.lib.dvae_nvls_all_reduce(hb.multicast_ptr, n_pad, bar_ptrs, self.rank, self.world, ptr(one), 1, 0, 0,
+                check(self.lib.dvae_nvls_all_reduce(st["mc"], n_pad, st["bar_ptrs"], self.rank, self.world, ptr(one), 1, 0, 0,
                                                     5_000_000_000, ptr(err), _lib.stream_ptr()), "dvae_nvls_all_reduce")
             torch.cuda.synchronize()
             want = float(self.world * (self.world + 1) // 2)
-            if int(err.item()) != 0 or not bool((buf == want).all()):
-                raise RuntimeError("self-test failed (timeout or wrong sums)")
-        except Exception as e:  # noqa: BLE001 -- any failure means "use NCCL", decided by all ranks together below
-            ok, why = 0, repr(e)[:200]
-        flag = torch.tensor([ok], dtype=torch.int32, device=self.device)
-        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.pg)
-        if int(flag.item()) != 1:
-            print(f"[dvae_b200] rank {self.rank}: multicast gradient exchange unavailable ({why or 'another rank failed'}); "
-                  "using NCCL all-reduce", file=sys.stderr, flush=True)
+            if int(err.item()) != 0 or not bool((st["buf"] == want).all()):
+                raise RuntimeError("timeout or wrong sums")
+        except Exception as e:  # noqa: BLE001
+            ok, why = False, repr(e)[:200]
+        if not agreed(ok, why, "self-test"):
             return
-        buf.zero_()
-        torch.cuda.synchronize()
-        dist.barrier(group=self.pg)
-        self.grad = buf[:self.n]
-        self._nvls = dict(buf=buf, bar=bar, hb=hb, hbar=hbar, mc=int(hb.multicast_ptr), bar_ptrs=bar_ptrs, mode=mode, buf_ptrs=buf_ptrs)
+        st["buf"].zero_()
+        if not agreed(True, "", "zero"):                   # every rank's buffer is zero before anyone's first step writes to it
+            return
+        self.grad = st["buf"][:self.n]
+        self._nvls = st
 
     def _signal(self, k, include_sides, extra=None):
         """Bucket k's gradients are final once everything enqueued so far (and, include_sides, the detached side-stream
