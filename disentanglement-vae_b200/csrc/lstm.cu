@@ -431,7 +431,10 @@ int lstm_seq_bwd_impl(const float* x, int64_t ldx, int T, int B, int I, int H, i
   GemmHints gh_bg = gh;
   {
     static const int cap = [] { const char* e = getenv("DVAE_DW_MAX_CTAS"); return e ? atoi(e) : 48; }();
-    gh_bg.max_ctas = defer_joins_enabled() ? cap : 0;      // nothing follows (last layer of the backward pass): whole machine
+    // Only where the neighbour is the cluster recurrence (H <= 256: a 64-CTA launch that must be placed at once).  At
+    // H = 1024 the recurrences are per-step launches / a grid-resident kernel and the GEMMs are 100x larger: the cap cost
+    // 2.3 % there (cfg 4: 25.70 ms capped, 25.10 ms uncapped).
+    gh_bg.max_ctas = (defer_joins_enabled() && tc_lstm_supported(H)) ? cap : 0;
   }
   // d_x accumulates over the directions (main stream, in order); the weight / bias gradients of each direction are
   // independent of it and of each other: parallel branches
