@@ -108,26 +108,85 @@ def synth_batch(rng, B, T=None, V=None, uniform_lengths=None):
     return X, lengths, Y
 
 
+_SAMPLER_CHILD = r"""
+import json, select, sys, time
+idx, period = int(sys.argv[1]), float(sys.argv[2])
+fake = len(sys.argv) > 3
+try:
+    if fake:
+        read = lambda: (1965.0, 0, 250.0)
+        max_mhz = 1965.0
+    else:
+        import pynvml as nv
+        nv.nvmlInit()
+        h = nv.nvmlDeviceGetHandleByIndex(idx)
+        max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+        reasons = nv.nvmlDeviceGetCurrentClocksEventReasons if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+            else nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        read = lambda: (float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)), int(reasons(h)), nv.nvmlDeviceGetPowerUsage(h) / 1000.0)
+        read()
+except Exception as e:
+    print("fail " + repr(e)[:200], flush=True)
+    sys.exit(0)
+print("ready %f" % max_mhz, flush=True)
+if not sys.stdin.readline().startswith("b"):
+    sys.exit(0)
+samples = []
+while True:
+    try:
+        samples.append(read())
+    except Exception:
+        pass
+    if select.select([sys.stdin], [], [], period)[0]:
+        break
+print(json.dumps(samples), flush=True)
+"""
+
+
 class ClockSampler:
-    """SM clock / throttle reasons / power sampled IN-PROCESS through NVML (nvidia-ml-py) by a background thread that is
-    started before warm-up; only samples taken between begin() and stop() -- the timed region -- are reported (the
-    B200_PROFILING.md clocks line).  nvidia-smi needed ~0.5 s to deliver its first line, longer than the region."""
+    """SM clock / throttle reasons / power sampled through NVML (nvidia-ml-py) during the timed region only (the
+    B200_PROFILING.md clocks line), by a HELPER PROCESS that polls every 2 ms between begin() and stop().  Sampling from
+    the launch loop itself (round 2, first half) stalled rank 0's host for milliseconds at a time: invisible at N = 1 (the
+    stall falls between the per-step event pairs) but at N > 1 the other ranks wait for rank 0 inside their exchange
+    kernels, and the max-over-ranks step time jumped from 1.23 to 1.35-3.6 ms in half of the runs.  nvidia-smi needed
+    ~0.5 s to deliver its first line, longer than the region.  Fallback: an in-process thread (no launch-loop samples)."""
     REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
 
-    def __init__(self, gpu, period_s=0.005):
-        self.samples, self.live, self._stop, self.h, self.nv = [], False, False, None, None
+    def __init__(self, gpu, period_s=0.002):
+        self.samples, self.live, self._stop, self.h, self.nv, self.child = [], False, False, None, None, None
+        self.source = "nvml helper process"
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        idx = int(vis.split(",")[gpu]) if vis and all(t.strip().isdigit() for t in vis.split(",")) else gpu
+        try:
+            import subprocess
+            extra = ["fake"] if os.environ.get("DVAE_FAKE_NVML") == "1" else []
+            self.child = subprocess.Popen([sys.executable, "-c", _SAMPLER_CHILD, str(idx), str(period_s)] + extra, stdin=subprocess.PIPE,
+                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            import select
+            line = self.child.stdout.readline() if select.select([self.child.stdout], [], [], 20.0)[0] else ""
+            if not line.startswith("ready"):
+                raise RuntimeError(line.strip() or "no answer")
+            self.max_mhz = float(line.split()[1])
+            return
+        except Exception:
+            if self.child is not None:
+                try:
+                    self.child.kill()
+                except Exception:
+                    pass
+            self.child = None
+        # fallback: background thread in this process
+        self.source = "nvml in-process thread"
         try:
             import pynvml
             pynvml.nvmlInit()
             self.nv = pynvml
-            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
-            idx = int(vis.split(",")[gpu]) if vis and all(t.strip().isdigit() for t in vis.split(",")) else gpu
             self.h = pynvml.nvmlDeviceGetHandleByIndex(idx)
             self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
         except Exception:
             self.h = None
             return
-        self.period = period_s
+        self.period = 0.005
         self.t = threading.Thread(target=self._loop, daemon=True)
         self.t.start()
 
@@ -146,27 +205,36 @@ class ClockSampler:
             time.sleep(self.period)
 
     def sample_now(self):
-        """One sample from the CALLING thread (the launch loop holds the GIL most of the time, so the background thread
-        alone can miss a region of a few tens of milliseconds)."""
-        if self.h is None:
-            return
-        nv = self.nv
-        try:
-            mhz = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
-            rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
-                else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
-            self.samples.append((float(mhz), int(rs), nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0))
-        except Exception:
-            pass
+        """Kept for callers' sake: nothing is sampled from the launch loop any more (see the class docstring)."""
+        return
 
     def begin(self):
         self.live = True
+        if self.child is not None:
+            try:
+                self.child.stdin.write("b\n")
+                self.child.stdin.flush()
+            except Exception:
+                self.child = None
 
     def stop(self):
         self.live = False
         self._stop = True
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "source": "nvml in-process thread"}
-        if self.h is None or not self.samples:
+        if self.child is not None:
+            try:
+                self.child.stdin.write("e\n")
+                self.child.stdin.flush()
+                import select
+                line = self.child.stdout.readline() if select.select([self.child.stdout], [], [], 10.0)[0] else "[]"
+                self.samples = [tuple(x) for x in json.loads(line or "[]")]
+                self.child.wait(timeout=5)
+            except Exception:
+                try:
+                    self.child.kill()
+                except Exception:
+                    pass
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "source": self.source}
+        if (self.h is None and self.child is None) or not self.samples:
             return out
         sm = [s[0] for s in self.samples]
         bits = 0
@@ -629,7 +697,11 @@ def main():
             clocks.sample_now()                          # GPU is under load here: the host runs ahead of the queued steps
     barrier()
     clk = clocks.stop() if clocks else None
-    dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+    per_step = [a.elapsed_time(b) for a, b in ev]
+    dev_ms = sum(per_step)
+    srt = sorted(per_step)
+    step_ms = {"min": srt[0], "median": srt[len(srt) // 2], "p90": srt[min(len(srt) - 1, int(0.9 * len(srt)))], "max": srt[-1],
+               "note": "per-step CUDA-event times of this rank's timed region (ms_per_step is their mean, max over ranks)"}
     loss_last = eng.losses_from(out.cpu())["total_loss"]
 
     if args.only_steps:
@@ -642,7 +714,7 @@ def main():
             print(json.dumps({"metric": "train_tokens_per_sec", "value": tok_sum / (dev_ms * 1e-3), "unit": "tokens/s", "n_gpus": world,
                               "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps,
                               "config": workload_config(world, graph=not args.no_graph), "dp_exchange": eng.exchange_mode,
-                              "note": "--only-steps: no e2e / roofline legs"}), flush=True)
+                              "step_ms": step_ms, "note": "--only-steps: no e2e / roofline legs"}), flush=True)
         if world > 1:
             dist.destroy_process_group()
         return
@@ -812,6 +884,7 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(world, graph=not args.no_graph),
             "dp_exchange": eng.exchange_mode,      # none | p2p | nvls (repo all-reduce kernel inside the one-graph step) | nccl+...
+            "step_ms": step_ms,
             "padded_tokens_per_sec": B * world * T * args.steps / (dev_ms * 1e-3),
             "e2e": {"value": e2e_tok / e2e_s, "unit": "tokens/s", "h2d_bytes_per_step": eng.h2d_bytes_per_step,
                     "d2h_bytes_per_step": eng.d2h_bytes_per_step, "ms_per_step": e2e_s * 1e3 / args.steps,

@@ -35,7 +35,8 @@ def d_bow(plan):
 
 
 class TrainEngine:
-    NSLOT = 4          # pinned staging slots for the per-step scalar block (ring, guarded by CUDA events)
+    # pinned staging slots for the per-step scalar block (ring, guarded by CUDA events) = how many steps the host may run ahead
+    NSLOT = max(3, int(os.environ.get("DVAE_ENGINE_SLOTS", "4")))
 
     def __init__(self, model, params, B, T, lr=None, total_steps=None, use_graph=True, max_norm=5.0,
                  process_group=None, seed=None, teacher_forcing_prob=None):
