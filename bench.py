@@ -12,6 +12,7 @@ cfg4 (scaled decoder: H 1024, V 50k, T 64), cfg5 (inference: encode + resample d
 profiles/.
 """
 import argparse
+import copy
 import importlib
 import json
 import os
@@ -47,10 +48,17 @@ WORKLOAD = ("cfg2 sfu_amazon_100k reproduction shape: per-GPU batch 128, T=22 (S
             "content 62), dropout 0.5, teacher forcing 1.0, cyclic KL")
 
 
+_CFG2_DEFAULTS = dict(CFG2=copy.deepcopy(CFG2), VOCAB=VOCAB, SEQ_T=SEQ_T, TOTAL_STEPS=TOTAL_STEPS, LABELS=dict(LABELS), BATCH=BATCH,
+                      UNIFORM_LENGTHS=UNIFORM_LENGTHS, WORKLOAD=WORKLOAD)
+
+
 def select_workload(name):
-    """Rebinds the module-level workload description (BASELINE.json `configs`).  Returns the uniform length range or None
-    (SFU-like length histogram)."""
+    """Rebinds the module-level workload description (BASELINE.json `configs`), always starting from the cfg2 defaults.
+    Returns the uniform length range or None (SFU-like length histogram)."""
     global CFG2, VOCAB, SEQ_T, WORKLOAD, TOTAL_STEPS, LABELS, BATCH, UNIFORM_LENGTHS, WORKLOAD_NAME
+    d = _CFG2_DEFAULTS
+    CFG2, VOCAB, SEQ_T, TOTAL_STEPS, LABELS = copy.deepcopy(d["CFG2"]), d["VOCAB"], d["SEQ_T"], d["TOTAL_STEPS"], dict(d["LABELS"])
+    BATCH, UNIFORM_LENGTHS, WORKLOAD = d["BATCH"], d["UNIFORM_LENGTHS"], d["WORKLOAD"]
     WORKLOAD_NAME = name
     if name == "cfg1":       # config_example.json shape (BASELINE configs[0]; SURVEY.md 8 table row 1)
         CFG2 = dict(CFG2, name="bench/config_example", bidirectional_encoder=False, combined_dataset=False,
