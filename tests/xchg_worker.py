@@ -36,7 +36,8 @@ def main():
     err = torch.zeros(1, dtype=torch.int32, device=dev)
     st = torch.cuda.current_stream().cuda_stream
     epoch, bad = 0, []
-    for mode in ("nvls", "p2p"):
+    # the peer-to-peer variant is what the engine uses on 2 GPUs (on more it must pass the engine's start-up self-test first)
+    for mode in (("nvls", "p2p") if world == 2 else ("nvls",)):
         for n, off, ctas in ((4, 0, 0), (8, 4, 0), (1024 + 4, 0, 3), (1 << 20, 12, 0), (14 * 1024 * 1024 // 4, 0, 64), (100003 * 4, 8, 16)):
             base = (torch.arange(n, device=dev) % 97 + 1).float()
             buf.fill_(-5.0)
